@@ -1,0 +1,201 @@
+/* rnla.h -- C ABI of the B200-native sketch-and-factor hot path of randnla (crate `randblas`).
+ *
+ * This is the drop-in boundary: every entry point below is what a Rust FFI binding
+ * for the corresponding reference function would call.  Plain pointers and sizes only; all matrices
+ * are column-major f64 with lda = nrows unless an explicit leading dimension is given (nalgebra
+ * `DMatrix<f64>` layout).  The caller owns every buffer: the library never returns memory the caller
+ * must free, and never frees caller memory.
+ *
+ * Two flavours per operation:
+ *   rnla_xxx      host buffers in/out (what the reference-signature Rust function binds);
+ *                 host<->device copies happen inside the call
+ *   rnla_xxx_dev  device buffers in/out on the library stream (needed for the 32-320 GB configs
+ *                 where a host DMatrix cannot be the carrier, and for benchmarks)
+ *
+ * Every function returns an rnla_status; codes map 1:1 onto the reference's `RandNLAError`
+ * variants (reference src/errors.rs:3-14).  rnla_last_error_message() returns the text the
+ * reference would have put in the variant's String (thread-local, valid until the next call).
+ *
+ * There is NO CPU fallback: if no CUDA device is usable every compute entry point fails with
+ * RNLA_ERR_COMPUTATION.
+ */
+#ifndef RNLA_H
+#define RNLA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rnla_status {
+    RNLA_OK = 0,
+    RNLA_ERR_INVALID_PARAMETERS = 1,   /* RandNLAError::InvalidParameters        errors.rs:4  */
+    RNLA_ERR_INVALID_DIMENSIONS = 2,   /* RandNLAError::InvalidDimensions        errors.rs:5  */
+    RNLA_ERR_NEGATIVE_DIMENSIONS = 3,  /* RandNLAError::NegativeDimensions       errors.rs:6  */
+    RNLA_ERR_NOT_OVERDETERMINED = 4,   /* RandNLAError::NotOverdetermined        errors.rs:7  */
+    RNLA_ERR_NOT_SQUARE = 5,           /* RandNLAError::NotSquare                errors.rs:8  */
+    RNLA_ERR_SINGULAR_MATRIX = 6,      /* RandNLAError::SingularMatrix           errors.rs:9  */
+    RNLA_ERR_MATRIX_DECOMPOSITION = 7, /* RandNLAError::MatrixDecompositionError errors.rs:10 */
+    RNLA_ERR_NOT_HERMITIAN = 8,        /* RandNLAError::NotHermitian             errors.rs:11 */
+    RNLA_ERR_NOT_PSD = 9,              /* RandNLAError::NotPositiveSemiDefinite  errors.rs:12 */
+    RNLA_ERR_COMPUTATION = 10          /* RandNLAError::ComputationError         errors.rs:13 (CUDA/NCCL failures land here) */
+} rnla_status;
+
+/* reference src/sketch.rs:9-13 */
+typedef enum rnla_dist { RNLA_GAUSSIAN = 0, RNLA_UNIFORM = 1, RNLA_RADEMACHER = 2 } rnla_dist;
+/* reference src/sketch.rs:18-21 */
+typedef enum rnla_attr { RNLA_ROW = 0, RNLA_COLUMN = 1 } rnla_attr;
+
+/* Which `tsog1` the drivers run:
+ *   INTENDED  monograph TSOG1: S = Omega; (S = A S; stab; S = A^T S; stab)*, QR-based stabiliser.
+ *   LITERAL   statement-for-statement src/lora_helpers.rs:58-105 including the zero-S1 defect and the
+ *             permutation-dropping full-pivot-LU `Stabilizer` (:144-146): Omega is never used for even
+ *             num_passes, exactly as in the reference. */
+typedef enum rnla_mode { RNLA_MODE_INTENDED = 0, RNLA_MODE_LITERAL = 1 } rnla_mode;
+
+/* Generator behind rnla_sketching_operator:
+ *   PHILOX    this build's counter-based map (Philox4x32-10, entry = pure function of seed,row,col)
+ *   THREEFRY  the reference's ThreeFry2x64-20 sequential stream seeded with seed_from_u64(seed)
+ *             (src/sketch.rs:112-127); available for UNIFORM and RADEMACHER, whose rand 0.8.5
+ *             transforms are closed-form.  GAUSSIAN needs rand_distr's ziggurat tables, which are
+ *             not in the reference tree -> RNLA_ERR_INVALID_PARAMETERS. */
+typedef enum rnla_generator { RNLA_GEN_PHILOX = 0, RNLA_GEN_THREEFRY = 1 } rnla_generator;
+
+typedef struct rnla_options {
+    int32_t mode;             /* rnla_mode; default INTENDED */
+    int32_t dist;             /* rnla_dist of the range-finder sketch; reference hard-codes GAUSSIAN (lora_helpers.rs:71,74) */
+    uint64_t seed;            /* reference hard-codes 0 (sketch.rs:112) */
+    int32_t num_passes;       /* <=0: reference constants (2 for rand_svd/rand_evd1 lora_helpers.rs:40, 3 for rand_evd2 lora_drivers.rs:186) */
+    int32_t passes_per_stab;  /* <=0: 1 (same lines) */
+    int32_t fused_sketch;     /* 1 (default): Omega is generated inside the A*Omega kernel and never materialised; 0: materialise then multiply */
+    int32_t reserved;
+} rnla_options;
+
+/* ---- library / context ------------------------------------------------------------------------- */
+int32_t rnla_version(void);
+const char* rnla_last_error_message(void);
+/* bind the calling process to a CUDA device (default 0) and create the context (stream, workspace pool) */
+rnla_status rnla_init(int32_t device);
+void rnla_shutdown(void);
+/* library stream as a cudaStream_t (so callers can order their own work / events against it) */
+void* rnla_stream(void);
+/* run on a caller-owned cudaStream_t instead (e.g. torch's current stream); NULL restores the library stream */
+rnla_status rnla_set_stream(void* cuda_stream);
+rnla_status rnla_synchronize(void);
+void rnla_default_options(rnla_options* opt);
+/* process-wide defaults used by the reference-signature entry points */
+rnla_status rnla_set_options(const rnla_options* opt);
+void rnla_get_options(rnla_options* opt);
+/* kernels launched by this library since load (bench.py `gpu_launches`) */
+uint64_t rnla_kernel_launches(void);
+/* per-phase device timings of the last driver call: names[i] / ms[i]; returns the number of phases */
+int32_t rnla_get_timings(const char** names, double* ms, int32_t cap);
+
+/* ---- multi-GPU: one process per GPU, A row-sharded ------------------------------ */
+/* 128-byte NCCL unique id; rank 0 creates it, the host side broadcasts it (torch.distributed / MPI / files) */
+rnla_status rnla_comm_unique_id(uint8_t id[128]);
+rnla_status rnla_comm_init(int32_t nranks, int32_t rank, const uint8_t id[128]);
+rnla_status rnla_comm_destroy(void);
+int32_t rnla_comm_size(void);
+int32_t rnla_comm_rank(void);
+
+/* ---- L0: counter-based RNG (reference rust-random123/src/philox.rs:211-223, threefry.rs:69-93) -- */
+/* nblocks independent Philox4x32-10 blocks evaluated ON THE DEVICE: ctr[4*i..], key[2*i..] -> out[4*i..] (host buffers) */
+rnla_status rnla_philox4x32_10(int64_t nblocks, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
+/* nblocks ThreeFry2x64-20 blocks on the device: ctr[2*i..], key[2*i..] -> out[2*i..] */
+rnla_status rnla_threefry2x64_20(int64_t nblocks, const uint64_t* ctr, const uint64_t* key, uint64_t* out);
+
+/* ---- L1: sketch operators (reference src/sketch.rs) -------------------------------------------- */
+/* sketching_operator(dist, rows, cols)  src/sketch.rs:102-130.  Errors: InvalidDimensions if rows==0||cols==0 (:107-111). */
+rnla_status rnla_sketching_operator(int32_t dist, int64_t rows, int64_t cols, double* out);
+/* extended: explicit generator / seed / stream / global row offset (row-sharded operators) / leading dimension */
+rnla_status rnla_sketch_fill(int32_t generator, int32_t dist, uint64_t seed, uint32_t stream,
+                             int64_t rows, int64_t cols, int64_t row_offset, double* out, int64_t ld);
+rnla_status rnla_sketch_fill_dev(int32_t generator, int32_t dist, uint64_t seed, uint32_t stream,
+                                 int64_t rows, int64_t cols, int64_t row_offset, double* d_out, int64_t ld);
+/* haar_sample(rows, cols, attr)  src/sketch.rs:45-85 */
+rnla_status rnla_haar_sample(int64_t rows, int64_t cols, int32_t attr, double* out);
+
+/* ---- L3: range-finder helpers (reference src/lora_helpers.rs) ----------------------------------- */
+/* Orth(X) :131-133 -> thin Q (rows x min(rows,cols)), R diag >= 0 convention.  R (qcols x cols) optional (NULL ok). */
+rnla_status rnla_orth(const double* X, int64_t rows, int64_t cols, double* Q, double* R, int64_t* qcols);
+/* Stabilizer(X) :144-146 -> unit-lower-trapezoidal L of full-pivot LU, permutations dropped (rows x min(rows,cols)) */
+rnla_status rnla_stabilizer(const double* X, int64_t rows, int64_t cols, double* L, int64_t* lcols);
+/* tsog1(A, k, num_passes, passes_per_stab) :58-105 -> S (n x k).  mode from the current options. */
+rnla_status rnla_tsog1(const double* A, int64_t m, int64_t n, int64_t k, int32_t num_passes,
+                       int32_t passes_per_stab, double* S);
+/* RF1(A, k) :37-44 -> Q (m x qcols) */
+rnla_status rnla_rf1(const double* A, int64_t m, int64_t n, int64_t k, double* Q, int64_t* qcols);
+/* QB1(A, k, epsilon) :17-23 -> Q (m x qcols), B (qcols x n, ld = qcols) */
+rnla_status rnla_qb1(const double* A, int64_t m, int64_t n, int64_t k, double epsilon,
+                     double* Q, double* B, int64_t* qcols);
+
+/* ---- L4: drivers (reference src/lora_drivers.rs) ------------------------------------------------ */
+/* rand_svd(A, k, epsilon, s) :30-69.  U: m x k buffer, S: k x k buffer (dense diagonal matrix, as the
+ * reference returns), Vt: k x n buffer; *r = min(k, Q.ncols()) columns/rows are valid, packed with
+ * leading dimensions m, r, r.  Errors: InvalidParameters for k==0, epsilon<=0, s==0 (:31-45). */
+rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, double epsilon, int64_t s,
+                          double* U, double* S, double* Vt, int64_t* r);
+/* rand_evd1(A, k, epsilon, s) :87-151.  V: n x k, lambda: k.  NotHermitian if A != A^T exactly (:106). */
+rnla_status rnla_rand_evd1(const double* A, int64_t n, int64_t k, double epsilon, int64_t s,
+                           double* V, double* lambda, int64_t* r);
+/* rand_evd2(A, k, s) :167-224 (Nystrom).  NotPositiveSemiDefinite / MatrixDecompositionError as the reference. */
+rnla_status rnla_rand_evd2(const double* A, int64_t n, int64_t k, int64_t s,
+                           double* V, double* lambda, int64_t* r);
+
+/* device-resident drivers: A is the LOCAL row shard (m_local x n, lda) when a communicator is active,
+ * U is the matching local row shard; n-side outputs are replicated on every rank. */
+rnla_status rnla_rand_svd_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t k, int64_t s,
+                              const rnla_options* opt, double* dU, int64_t ldu, double* dSigma /* k */,
+                              double* dVt, int64_t ldvt, int64_t* r);
+rnla_status rnla_rand_evd1_dev(const double* dA, int64_t lda, int64_t n, int64_t k, int64_t s,
+                               const rnla_options* opt, double* dV, int64_t ldv, double* dLambda, int64_t* r);
+rnla_status rnla_rand_evd2_dev(const double* dA, int64_t lda, int64_t n, int64_t k, int64_t s,
+                               const rnla_options* opt, double* dV, int64_t ldv, double* dLambda, int64_t* r);
+
+/* ---- sketch step of sketch_and_precondition (reference src/sketch_and_precondition.rs:49-52,105-107,172-176) */
+typedef enum rnla_sketch_kind { RNLA_SKETCH_DENSE = 0, RNLA_SKETCH_SASO = 1 } rnla_sketch_kind;
+/* d = sketch dimension rule of the reference: blendenpik/lsrn (:49,:105) rule 0, saddle point (:172) rule 1 */
+int64_t rnla_sketch_dim(int64_t m, int64_t n, double sampling_factor, int32_t rule);
+/* A_sk (d x n) = S A, b_sk (d x nrhs) = S b with S (d x m): dense i.i.d. `dist`, or sparse-sign with zeta nonzeros per column.
+ * b may be NULL (nrhs = 0).  Validation of m>=n, sampling_factor, epsilon, l stays with the caller-facing wrappers. */
+rnla_status rnla_sketch_apply(int32_t kind, int32_t dist, uint64_t seed, int64_t d, int32_t zeta,
+                              const double* A, int64_t m, int64_t n, const double* b, int64_t nrhs,
+                              double* A_sk, double* b_sk);
+rnla_status rnla_sketch_apply_dev(int32_t kind, int32_t dist, uint64_t seed, int64_t d, int32_t zeta,
+                                  const double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t row_offset,
+                                  double* dA_sk, int64_t ld_sk);
+
+/* ---- building blocks on device buffers (tests, benches, host mirrors) ---------------------------- */
+/* C (m x N) = A (m x K) * B (K x N) */
+rnla_status rnla_gemm_nn_dev(const double* dA, int64_t lda, int64_t m, int64_t K,
+                             const double* dB, int64_t ldb, int64_t N, double* dC, int64_t ldc);
+/* C (m x N) = A (m x K) * Omega(K x N), Omega generated in-kernel (never materialised) */
+rnla_status rnla_sketch_gemm_dev(const double* dA, int64_t lda, int64_t m, int64_t K, int32_t dist, uint64_t seed,
+                                 uint32_t stream, int64_t N, double* dC, int64_t ldc);
+/* Z (n x N) = A (m x n)^T * Q (m x N); all-reduced over the communicator if one is active and allreduce != 0 */
+rnla_status rnla_gemm_tn_dev(const double* dA, int64_t lda, int64_t m, int64_t n,
+                             const double* dQ, int64_t ldq, int64_t N, double* dZ, int64_t ldz, int32_t allreduce);
+/* in-place orthonormalisation of a (row-sharded if `sharded`) panel; R (cols x cols, ld = cols) optional */
+rnla_status rnla_orth_dev(double* dX, int64_t ldx, int64_t rows_local, int64_t cols, int32_t sharded,
+                          double* dR, int64_t* deficient);
+/* small dense core on one GPU: SVD of a (rows x cols) matrix with cols <= 512 columns... see DESIGN.md */
+rnla_status rnla_small_svd_dev(const double* dM, int64_t ldm, int64_t p, double* dU, double* dSigma, double* dV);
+rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double* dW, double* dLambda);
+
+/* synthetic inputs, generated on the device shard by shard: A = U0 diag(sigma) V0^T + eta G */
+rnla_status rnla_generate_lowrank_dev(double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t row_offset,
+                                      int64_t m_global, int64_t r0, const double* sigma_host, double eta, uint64_t seed);
+
+/* raw device memory helpers for hosts without a CUDA runtime binding (Rust shim, ctypes) */
+rnla_status rnla_malloc(void** dptr, size_t bytes);
+rnla_status rnla_free(void* dptr);
+rnla_status rnla_memcpy_h2d(void* dst, const void* src, size_t bytes);
+rnla_status rnla_memcpy_d2h(void* dst, const void* src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNLA_H */

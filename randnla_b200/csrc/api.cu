@@ -1,0 +1,443 @@
+// extern "C" surface (include/rnla.h): argument validation with the reference's own messages,
+// host<->device staging for the host-buffer entry points, and the *_dev pass-throughs.
+#include "drivers.cuh"
+#include "gemm.cuh"
+#include "panel.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rnla;
+
+namespace rnla {
+rnla_status dev_sketch_apply(int kind, int dist, uint64_t seed, int64_t d, int zeta, const double* dA, int64_t lda,
+                             int64_t m_local, int64_t n, int64_t row_offset, double* dAsk, int64_t ldk);
+rnla_status dev_generate_lowrank(double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t row_offset, int64_t m_global,
+                                 int64_t r0, const double* sigma_host, double eta, uint64_t seed);
+}
+
+static std::string fmt(const char* f, long long v) { char b[256]; snprintf(b, sizeof b, f, v); return b; }
+static std::string fmtd(const char* f, double v) { char b[256]; snprintf(b, sizeof b, f, v); return b; }
+// Rust's `{}` for f64 prints the shortest representation that round-trips; %g is close enough for messages
+static std::string rust_f64(double v) {
+    char b[64];
+    if (v == (long long)v && std::fabs(v) < 1e15) snprintf(b, sizeof b, "%lld", (long long)v);
+    else snprintf(b, sizeof b, "%.17g", v);
+    return b;
+}
+
+static rnla_status h2d(DevBuf& buf, const double* host, size_t count) {
+    RNLA_CUDA(buf.alloc(std::max<size_t>(count, 1) * 8));
+    if (count) RNLA_CUDA(cudaMemcpyAsync(buf.p, host, count * 8, cudaMemcpyHostToDevice, ctx().stream));
+    return RNLA_OK;
+}
+static rnla_status d2h(double* host, const double* dev, size_t count) {
+    if (count) RNLA_CUDA(cudaMemcpyAsync(host, dev, count * 8, cudaMemcpyDeviceToHost, ctx().stream));
+    RNLA_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RNLA_OK;
+}
+
+// rand_core 0.6.4 SeedableRng::seed_from_u64 (PCG32 expansion) -> ThreeFry2x64 key (rust-random123/src/threefry.rs:23-27)
+static void threefry_key_from_u64(uint64_t state, uint64_t key[2]) {
+    const uint64_t MUL = 6364136223846793005ull, INC = 11634580027462260723ull;
+    uint32_t w[4];
+    for (int i = 0; i < 4; ++i) {
+        state = state * MUL + INC;
+        const uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27);
+        const uint32_t rot = (uint32_t)(state >> 59);
+        w[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+    }
+    key[0] = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+    key[1] = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
+}
+
+static rnla_status validate_svd_like(int64_t k, double epsilon, int64_t s) {
+    // reference src/lora_drivers.rs:31-45 / :89-103
+    if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, fmt("Rank k must be positive, current input is %lld", (long long)k));
+    if (!(epsilon > 0.0)) return fail(RNLA_ERR_INVALID_PARAMETERS, "Epsilon must be positive, current input is " + rust_f64(epsilon));
+    if (s <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, fmt("Oversampling parameter s must be positive, current input is %lld", (long long)s));
+    return RNLA_OK;
+}
+
+extern "C" {
+
+// ------------------------------------------------------------------ RNG hooks
+rnla_status rnla_philox4x32_10(int64_t nblocks, const uint32_t* hctr, const uint32_t* hkey, uint32_t* hout) {
+    RNLA_TRY(ensure_ctx());
+    if (nblocks <= 0) return RNLA_OK;
+    Ctx& c = ctx();
+    DevBuf dc, dk, dout;
+    RNLA_CUDA(dc.alloc((size_t)nblocks * 16)); RNLA_CUDA(dk.alloc((size_t)nblocks * 8)); RNLA_CUDA(dout.alloc((size_t)nblocks * 16));
+    RNLA_CUDA(cudaMemcpyAsync(dc.p, hctr, (size_t)nblocks * 16, cudaMemcpyHostToDevice, c.stream));
+    RNLA_CUDA(cudaMemcpyAsync(dk.p, hkey, (size_t)nblocks * 8, cudaMemcpyHostToDevice, c.stream));
+    RNLA_CUDA(philox_blocks(nblocks, dc.as<uint32_t>(), dk.as<uint32_t>(), dout.as<uint32_t>(), c.stream));
+    RNLA_CUDA(cudaMemcpyAsync(hout, dout.p, (size_t)nblocks * 16, cudaMemcpyDeviceToHost, c.stream));
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    return RNLA_OK;
+}
+rnla_status rnla_threefry2x64_20(int64_t nblocks, const uint64_t* hctr, const uint64_t* hkey, uint64_t* hout) {
+    RNLA_TRY(ensure_ctx());
+    if (nblocks <= 0) return RNLA_OK;
+    Ctx& c = ctx();
+    DevBuf dc, dk, dout;
+    RNLA_CUDA(dc.alloc((size_t)nblocks * 16)); RNLA_CUDA(dk.alloc((size_t)nblocks * 16)); RNLA_CUDA(dout.alloc((size_t)nblocks * 16));
+    RNLA_CUDA(cudaMemcpyAsync(dc.p, hctr, (size_t)nblocks * 16, cudaMemcpyHostToDevice, c.stream));
+    RNLA_CUDA(cudaMemcpyAsync(dk.p, hkey, (size_t)nblocks * 16, cudaMemcpyHostToDevice, c.stream));
+    RNLA_CUDA(threefry_blocks(nblocks, dc.as<uint64_t>(), dk.as<uint64_t>(), dout.as<uint64_t>(), c.stream));
+    RNLA_CUDA(cudaMemcpyAsync(hout, dout.p, (size_t)nblocks * 16, cudaMemcpyDeviceToHost, c.stream));
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    return RNLA_OK;
+}
+
+// ------------------------------------------------------------------ sketch operators
+rnla_status rnla_sketch_fill_dev(int32_t generator, int32_t dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols,
+                                 int64_t row_offset, double* d_out, int64_t ld) {
+    if (rows <= 0 || cols <= 0)   // src/sketch.rs:107-111
+        return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    if (dist < RNLA_GAUSSIAN || dist > RNLA_RADEMACHER) return fail(RNLA_ERR_INVALID_PARAMETERS, "unknown distribution");
+    if (ld < rows) return fail(RNLA_ERR_INVALID_DIMENSIONS, "leading dimension smaller than rows");
+    RNLA_TRY(ensure_ctx());
+    if (generator == RNLA_GEN_THREEFRY) {
+        if (dist == RNLA_GAUSSIAN)
+            return fail(RNLA_ERR_INVALID_PARAMETERS,
+                        "the reference's Gaussian stream needs rand_distr's ziggurat tables, which are not part of the reference tree; use RNLA_GEN_PHILOX");
+        if (row_offset != 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "the ThreeFry stream is sequential: row_offset must be 0");
+        uint64_t key[2];
+        threefry_key_from_u64(seed, key);
+        RNLA_CUDA(fill_threefry(dist, key[0], key[1], rows, cols, d_out, ld, ctx().stream));
+        return RNLA_OK;
+    }
+    if (generator != RNLA_GEN_PHILOX) return fail(RNLA_ERR_INVALID_PARAMETERS, "unknown generator");
+    RNLA_CUDA(fill_philox(dist, seed, stream, rows, cols, row_offset, d_out, ld, ctx().stream));
+    return RNLA_OK;
+}
+rnla_status rnla_sketch_fill(int32_t generator, int32_t dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols,
+                             int64_t row_offset, double* out, int64_t ld) {
+    if (rows <= 0 || cols <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    if (ld < rows) return fail(RNLA_ERR_INVALID_DIMENSIONS, "leading dimension smaller than rows");
+    RNLA_TRY(ensure_ctx());
+    DevBuf d;
+    RNLA_CUDA(d.alloc((size_t)rows * cols * 8));
+    RNLA_TRY(rnla_sketch_fill_dev(generator, dist, seed, stream, rows, cols, row_offset, d.d(), rows));
+    RNLA_CUDA(cudaMemcpy2DAsync(out, (size_t)ld * 8, d.p, (size_t)rows * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyDeviceToHost, ctx().stream));
+    RNLA_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RNLA_OK;
+}
+rnla_status rnla_sketching_operator(int32_t dist, int64_t rows, int64_t cols, double* out) {
+    if (rows <= 0 || cols <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    RNLA_TRY(ensure_ctx());
+    return rnla_sketch_fill(RNLA_GEN_PHILOX, dist, ctx().opts.seed, 0, rows, cols, 0, out, rows);
+}
+
+rnla_status rnla_haar_sample(int64_t rows, int64_t cols, int32_t attr, double* out) {
+    // src/sketch.rs:45-85
+    int64_t m, n;
+    if (attr == RNLA_ROW) {
+        if (rows > cols) {
+            char b[200]; snprintf(b, sizeof b, "Cannot have more rows (%lld) than columns (%lld) for row-orthonormal matrix", (long long)rows, (long long)cols);
+            return fail(RNLA_ERR_INVALID_DIMENSIONS, b);
+        }
+        m = cols; n = rows;
+    } else if (attr == RNLA_COLUMN) {
+        if (cols > rows) {
+            char b[200]; snprintf(b, sizeof b, "Cannot have more columns (%lld) than rows (%lld) for column-orthonormal matrix", (long long)cols, (long long)rows);
+            return fail(RNLA_ERR_INVALID_DIMENSIONS, b);
+        }
+        m = rows; n = cols;
+    } else return fail(RNLA_ERR_INVALID_PARAMETERS, "unknown matrix attribute");
+    if (m <= 0 || n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    RNLA_TRY(ensure_ctx());
+    Ctx& c = ctx();
+    DevBuf G, T;
+    RNLA_CUDA(G.alloc((size_t)m * n * 8));
+    RNLA_CUDA(fill_philox(RNLA_GAUSSIAN, c.opts.seed, 0, m, n, 0, G.d(), m, c.stream));      // :68-72
+    ShardInfo sh{m, 0, m};
+    RNLA_TRY(orth_inplace(G.d(), m, sh, (int)n, false, nullptr, nullptr));                  // :73-80 (R_ii >= 0, sign fix is a no-op)
+    if (attr == RNLA_ROW) {
+        RNLA_CUDA(T.alloc((size_t)m * n * 8));
+        RNLA_CUDA(transpose_matrix(G.d(), m, T.d(), n, m, n, c.stream));
+        return d2h(out, T.d(), (size_t)m * n);
+    }
+    return d2h(out, G.d(), (size_t)m * n);
+}
+
+// ------------------------------------------------------------------ helpers (host buffers)
+rnla_status rnla_orth(const double* X, int64_t rows, int64_t cols, double* Q, double* R, int64_t* qcols) {
+    if (rows <= 0 || cols <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    RNLA_TRY(ensure_ctx());
+    Ctx& c = ctx();
+    const int p = (int)std::min(rows, cols);
+    if (qcols) *qcols = p;
+    DevBuf dX, dR;
+    RNLA_TRY(h2d(dX, X, (size_t)rows * cols));
+    RNLA_CUDA(dR.alloc((size_t)p * std::max<int64_t>(cols, p) * 8));
+    ShardInfo sh{rows, 0, rows};
+    if (cols <= rows) {
+        RNLA_TRY(orth_inplace(dX.d(), rows, sh, p, false, R ? dR.d() : nullptr, nullptr));
+        RNLA_TRY(d2h(Q, dX.d(), (size_t)rows * p));
+        if (R) RNLA_TRY(d2h(R, dR.d(), (size_t)p * p));
+    } else {
+        // wide input: thin Q of the leading rows x rows block, R = Q^T X (rows x cols)
+        DevBuf dQ, dRt;
+        RNLA_CUDA(dQ.alloc((size_t)rows * p * 8));
+        RNLA_CUDA(copy_matrix(dX.d(), rows, dQ.d(), rows, rows, p, c.stream));
+        RNLA_TRY(orth_inplace(dQ.d(), rows, sh, p, false, nullptr, nullptr));
+        RNLA_TRY(d2h(Q, dQ.d(), (size_t)rows * p));
+        if (R) {
+            RNLA_CUDA(dRt.alloc((size_t)cols * p * 8));
+            RNLA_TRY(dev_gemm_tn(dX.d(), rows, rows, cols, dQ.d(), rows, p, dRt.d(), cols, false));   // X^T Q  (cols x p)
+            RNLA_CUDA(transpose_matrix(dRt.d(), cols, dR.d(), p, cols, p, c.stream));
+            RNLA_TRY(d2h(R, dR.d(), (size_t)p * cols));
+        }
+    }
+    return RNLA_OK;
+}
+
+rnla_status rnla_stabilizer(const double* X, int64_t rows, int64_t cols, double* L, int64_t* lcols) {
+    if (rows <= 0 || cols <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    RNLA_TRY(ensure_ctx());
+    const int64_t mn = std::min(rows, cols);
+    if (lcols) *lcols = mn;
+    DevBuf dX, dL;
+    RNLA_TRY(h2d(dX, X, (size_t)rows * cols));
+    RNLA_CUDA(dL.alloc((size_t)rows * mn * 8));
+    RNLA_TRY(dev_stabilizer(dX.d(), rows, rows, cols, dL.d(), rows));
+    return d2h(L, dL.d(), (size_t)rows * mn);
+}
+
+static rnla_status check_range_args(int64_t m, int64_t n, int64_t k) {
+    if (m <= 0 || n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, fmt("Rank k must be positive, current input is %lld", (long long)k));
+    return RNLA_OK;
+}
+
+rnla_status rnla_tsog1(const double* A, int64_t m, int64_t n, int64_t k, int32_t num_passes, int32_t passes_per_stab, double* S) {
+    RNLA_TRY(check_range_args(m, n, k));
+    if (num_passes < 0 || passes_per_stab <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "num_passes must be >= 0 and passes_per_stab > 0");
+    if (k > std::min(m, n)) return fail(RNLA_ERR_INVALID_DIMENSIONS, "tsog1: k must not exceed min(m, n)");
+    RNLA_TRY(ensure_ctx());
+    phases_reset();
+    DevBuf dA, dS;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_CUDA(dS.alloc((size_t)n * k * 8));
+    ShardInfo sh{m, 0, m};
+    RNLA_TRY(dev_tsog1(dA.d(), m, sh, n, (int)k, num_passes, passes_per_stab, ctx().opts, dS.d()));
+    return d2h(S, dS.d(), (size_t)n * k);
+}
+
+rnla_status rnla_rf1(const double* A, int64_t m, int64_t n, int64_t k, double* Q, int64_t* qcols) {
+    RNLA_TRY(check_range_args(m, n, k));
+    RNLA_TRY(ensure_ctx());
+    phases_reset();
+    const rnla_options o = ctx().opts;
+    const int l = (int)std::min<int64_t>(k, std::min(m, n));
+    if (qcols) *qcols = l;
+    DevBuf dA, dQ;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_CUDA(dQ.alloc((size_t)m * l * 8));
+    ShardInfo sh{m, 0, m};
+    RNLA_TRY(dev_rf1(dA.d(), m, sh, n, l, o.num_passes > 0 ? o.num_passes : 2, o.passes_per_stab > 0 ? o.passes_per_stab : 1, o, dQ.d(), m));
+    return d2h(Q, dQ.d(), (size_t)m * l);
+}
+
+rnla_status rnla_qb1(const double* A, int64_t m, int64_t n, int64_t k, double epsilon, double* Q, double* B, int64_t* qcols) {
+    (void)epsilon;   // ignored, as in the reference (src/lora_helpers.rs:18-19)
+    RNLA_TRY(check_range_args(m, n, k));
+    RNLA_TRY(ensure_ctx());
+    phases_reset();
+    Ctx& c = ctx();
+    const rnla_options o = c.opts;
+    const int l = (int)std::min<int64_t>(k, std::min(m, n));
+    if (qcols) *qcols = l;
+    DevBuf dA, dQ, dBt, dB;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_CUDA(dQ.alloc((size_t)m * l * 8)); RNLA_CUDA(dBt.alloc((size_t)n * l * 8)); RNLA_CUDA(dB.alloc((size_t)n * l * 8));
+    ShardInfo sh{m, 0, m};
+    RNLA_TRY(dev_qb1(dA.d(), m, sh, n, l, o.num_passes > 0 ? o.num_passes : 2, o.passes_per_stab > 0 ? o.passes_per_stab : 1, o, dQ.d(), m, dBt.d()));
+    RNLA_CUDA(transpose_matrix(dBt.d(), n, dB.d(), l, n, l, c.stream));
+    RNLA_TRY(d2h(Q, dQ.d(), (size_t)m * l));
+    return d2h(B, dB.d(), (size_t)l * n);
+}
+
+// ------------------------------------------------------------------ drivers (host buffers)
+rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, double epsilon, int64_t s,
+                          double* U, double* S, double* Vt, int64_t* r_out) {
+    RNLA_TRY(validate_svd_like(k, epsilon, s));
+    if (m <= 0 || n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    RNLA_TRY(ensure_ctx());
+    Ctx& c = ctx();
+    const int64_t l = std::min<int64_t>(k + s, std::min(m, n));
+    const int64_t r = std::min(k, l);
+    DevBuf dA, dU, dS, dVt;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_CUDA(dU.alloc((size_t)m * r * 8)); RNLA_CUDA(dS.alloc((size_t)r * 8)); RNLA_CUDA(dVt.alloc((size_t)r * n * 8));
+    int64_t rr = 0;
+    RNLA_TRY(dev_rand_svd(dA.d(), m, m, n, k, s, c.opts, dU.d(), m, dS.d(), dVt.d(), r, &rr));
+    std::vector<double> sig((size_t)r);
+    RNLA_TRY(d2h(U, dU.d(), (size_t)m * r));
+    RNLA_TRY(d2h(Vt, dVt.d(), (size_t)r * n));
+    RNLA_TRY(d2h(sig.data(), dS.d(), (size_t)r));
+    // S is returned as a dense r x r diagonal matrix (src/lora_drivers.rs:64)
+    memset(S, 0, (size_t)r * r * 8);
+    for (int64_t i = 0; i < r; ++i) S[i + i * r] = sig[(size_t)i];
+    if (r_out) *r_out = r;
+    return RNLA_OK;
+}
+
+rnla_status rnla_rand_evd1(const double* A, int64_t n, int64_t k, double epsilon, int64_t s, double* V, double* lambda, int64_t* r_out) {
+    RNLA_TRY(validate_svd_like(k, epsilon, s));
+    if (n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    RNLA_TRY(ensure_ctx());
+    Ctx& c = ctx();
+    const int64_t l = std::min<int64_t>(k + s, n);
+    const int64_t r = std::min(k, l);
+    DevBuf dA, dV, dL;
+    RNLA_TRY(h2d(dA, A, (size_t)n * n));
+    RNLA_CUDA(dV.alloc((size_t)n * r * 8)); RNLA_CUDA(dL.alloc((size_t)r * 8));
+    int64_t rr = 0;
+    RNLA_TRY(dev_rand_evd1(dA.d(), n, n, n, k, s, c.opts, dV.d(), n, dL.d(), &rr));
+    RNLA_TRY(d2h(V, dV.d(), (size_t)n * r));
+    RNLA_TRY(d2h(lambda, dL.d(), (size_t)r));
+    if (r_out) *r_out = rr;
+    return RNLA_OK;
+}
+
+rnla_status rnla_rand_evd2(const double* A, int64_t n, int64_t k, int64_t s, double* V, double* lambda, int64_t* r_out) {
+    // src/lora_drivers.rs:169-173: only k is validated (s may be 0)
+    if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, fmt("Rank k must be positive, current input is %lld", (long long)k));
+    if (s < 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "Oversampling parameter s must be non-negative");
+    if (n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    RNLA_TRY(ensure_ctx());
+    Ctx& c = ctx();
+    const int64_t kk = std::min(k, n);
+    DevBuf dA, dV, dL;
+    RNLA_TRY(h2d(dA, A, (size_t)n * n));
+    RNLA_CUDA(dV.alloc((size_t)n * kk * 8)); RNLA_CUDA(dL.alloc((size_t)kk * 8));
+    int64_t rr = 0;
+    RNLA_TRY(dev_rand_evd2(dA.d(), n, n, n, k, s, c.opts, dV.d(), n, dL.d(), &rr));
+    RNLA_TRY(d2h(V, dV.d(), (size_t)n * rr));
+    RNLA_TRY(d2h(lambda, dL.d(), (size_t)rr));
+    if (r_out) *r_out = rr;
+    return RNLA_OK;
+}
+
+// ------------------------------------------------------------------ drivers (device buffers)
+static const rnla_options& pick(const rnla_options* o) { return o ? *o : ctx().opts; }
+
+rnla_status rnla_rand_svd_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t k, int64_t s,
+                              const rnla_options* opt, double* dU, int64_t ldu, double* dSigma, double* dVt, int64_t ldvt, int64_t* r) {
+    RNLA_TRY(validate_svd_like(k, 1.0, s));
+    RNLA_TRY(ensure_ctx());
+    const rnla_options o = pick(opt);
+    return dev_rand_svd(dA, lda, m_local, n, k, s, o, dU, ldu, dSigma, dVt, ldvt, r);
+}
+rnla_status rnla_rand_evd1_dev(const double* dA, int64_t lda, int64_t n, int64_t k, int64_t s, const rnla_options* opt,
+                               double* dV, int64_t ldv, double* dLambda, int64_t* r) {
+    RNLA_TRY(validate_svd_like(k, 1.0, s));
+    RNLA_TRY(ensure_ctx());
+    const rnla_options o = pick(opt);
+    return dev_rand_evd1(dA, lda, n, n, k, s, o, dV, ldv, dLambda, r);
+}
+rnla_status rnla_rand_evd2_dev(const double* dA, int64_t lda, int64_t n, int64_t k, int64_t s, const rnla_options* opt,
+                               double* dV, int64_t ldv, double* dLambda, int64_t* r) {
+    if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, fmt("Rank k must be positive, current input is %lld", (long long)k));
+    RNLA_TRY(ensure_ctx());
+    const rnla_options o = pick(opt);
+    return dev_rand_evd2(dA, lda, n, n, k, s, o, dV, ldv, dLambda, r);
+}
+
+// ------------------------------------------------------------------ sketch step of sketch_and_precondition
+int64_t rnla_sketch_dim(int64_t m, int64_t n, double sampling_factor, int32_t rule) {
+    if (rule == 0) {
+        // src/sketch_and_precondition.rs:49,105
+        if (sampling_factor * (double)n > (double)m) return m;
+        return (int64_t)std::floor(sampling_factor * (double)n);
+    }
+    // :172
+    int64_t d = (int64_t)std::floor(sampling_factor * (double)n);
+    if (d < 1) d = 1;
+    if (d > m) d = m;
+    return d;
+}
+
+rnla_status rnla_sketch_apply_dev(int32_t kind, int32_t dist, uint64_t seed, int64_t d, int32_t zeta, const double* dA, int64_t lda,
+                                  int64_t m_local, int64_t n, int64_t row_offset, double* dA_sk, int64_t ld_sk) {
+    RNLA_TRY(ensure_ctx());
+    return dev_sketch_apply(kind, dist, seed, d, zeta, dA, lda, m_local, n, row_offset, dA_sk, ld_sk);
+}
+
+rnla_status rnla_sketch_apply(int32_t kind, int32_t dist, uint64_t seed, int64_t d, int32_t zeta, const double* A, int64_t m, int64_t n,
+                              const double* b, int64_t nrhs, double* A_sk, double* b_sk) {
+    if (m <= 0 || n <= 0 || d <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, dAsk, db, dbsk;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_CUDA(dAsk.alloc((size_t)d * n * 8));
+    RNLA_TRY(dev_sketch_apply(kind, dist, seed, d, zeta, dA.d(), m, m, n, 0, dAsk.d(), d));
+    RNLA_TRY(d2h(A_sk, dAsk.d(), (size_t)d * n));
+    if (b && nrhs > 0) {
+        RNLA_TRY(h2d(db, b, (size_t)m * nrhs));
+        RNLA_CUDA(dbsk.alloc((size_t)d * nrhs * 8));
+        RNLA_TRY(dev_sketch_apply(kind, dist, seed, d, zeta, db.d(), m, m, nrhs, 0, dbsk.d(), d));
+        RNLA_TRY(d2h(b_sk, dbsk.d(), (size_t)d * nrhs));
+    }
+    return RNLA_OK;
+}
+
+// ------------------------------------------------------------------ building blocks
+rnla_status rnla_gemm_nn_dev(const double* dA, int64_t lda, int64_t m, int64_t K, const double* dB, int64_t ldb, int64_t N, double* dC, int64_t ldc) {
+    RNLA_TRY(ensure_ctx());
+    return dev_gemm_nn(dA, lda, m, K, dB, ldb, N, dC, ldc);
+}
+rnla_status rnla_sketch_gemm_dev(const double* dA, int64_t lda, int64_t m, int64_t K, int32_t dist, uint64_t seed, uint32_t stream,
+                                 int64_t N, double* dC, int64_t ldc) {
+    RNLA_TRY(ensure_ctx());
+    return dev_sketch_gemm(dA, lda, m, K, dist, seed, stream, N, dC, ldc);
+}
+rnla_status rnla_gemm_tn_dev(const double* dA, int64_t lda, int64_t m, int64_t n, const double* dQ, int64_t ldq, int64_t N,
+                             double* dZ, int64_t ldz, int32_t allreduce) {
+    RNLA_TRY(ensure_ctx());
+    return dev_gemm_tn(dA, lda, m, n, dQ, ldq, N, dZ, ldz, allreduce != 0);
+}
+rnla_status rnla_orth_dev(double* dX, int64_t ldx, int64_t rows_local, int64_t cols, int32_t sharded, double* dR, int64_t* deficient) {
+    RNLA_TRY(ensure_ctx());
+    ShardInfo sh{rows_local, 0, rows_local};
+    if (sharded) RNLA_TRY(shard_layout(rows_local, &sh));
+    return orth_inplace(dX, ldx, sh, (int)cols, sharded != 0, dR, deficient);
+}
+rnla_status rnla_small_svd_dev(const double* dM, int64_t ldm, int64_t p, double* dU, double* dSigma, double* dV) {
+    RNLA_TRY(ensure_ctx());
+    Ctx& c = ctx();
+    if (p <= 0 || p > 1024) return fail(RNLA_ERR_INVALID_DIMENSIONS, "small_svd: 1 <= p <= 1024");
+    DevBuf work, info;
+    RNLA_CUDA(work.alloc((2 * (size_t)p * p + (size_t)p) * 8)); RNLA_CUDA(info.alloc(8));
+    RNLA_CUDA(jacobi_svd(dM, ldm, (int)p, dU, p, dSigma, dV, p, work.d(), info.as<int>(), c.stream));
+    int h[2];
+    RNLA_CUDA(cudaMemcpyAsync(h, info.p, 8, cudaMemcpyDeviceToHost, c.stream));
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    if (h[1]) return fail(RNLA_ERR_MATRIX_DECOMPOSITION, "SVD decomposition failed");
+    return RNLA_OK;
+}
+rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double* dW, double* dLambda) {
+    RNLA_TRY(ensure_ctx());
+    Ctx& c = ctx();
+    if (p <= 0 || p > 1024) return fail(RNLA_ERR_INVALID_DIMENSIONS, "small_eigh: 1 <= p <= 1024");
+    DevBuf work, info;
+    RNLA_CUDA(work.alloc((2 * (size_t)p * p + (size_t)p) * 8)); RNLA_CUDA(info.alloc(8));
+    RNLA_CUDA(jacobi_eigh(dC, ldc, (int)p, dW, p, dLambda, 0, work.d(), info.as<int>(), c.stream));
+    int h[2];
+    RNLA_CUDA(cudaMemcpyAsync(h, info.p, 8, cudaMemcpyDeviceToHost, c.stream));
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    if (h[1]) return fail(RNLA_ERR_COMPUTATION, "symmetric eigen-decomposition did not converge");
+    return RNLA_OK;
+}
+
+rnla_status rnla_generate_lowrank_dev(double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t row_offset, int64_t m_global,
+                                      int64_t r0, const double* sigma_host, double eta, uint64_t seed) {
+    RNLA_TRY(ensure_ctx());
+    return dev_generate_lowrank(dA, lda, m_local, n, row_offset, m_global, r0, sigma_host, eta, seed);
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Process-global context: device, stream, options, NCCL communicator (dlopen'ed), timings, error text.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/rnla.h"
+
+namespace rnla {
+
+struct PhaseTiming { std::string name; cudaEvent_t e0, e1; };
+
+struct Ctx {
+    bool ready = false;
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    rnla_options opts;
+    // communicator (one process per GPU)
+    void* nccl_lib = nullptr;
+    void* comm = nullptr;
+    int nranks = 1, rank = 0;
+    // timings of the last driver call
+    std::vector<PhaseTiming> phases;
+    std::vector<cudaEvent_t> event_pool;
+    std::vector<std::string> timing_names;   // storage handed out by rnla_get_timings
+};
+
+Ctx& ctx();
+void set_error(const std::string& msg);
+rnla_status fail(rnla_status code, const std::string& msg);
+rnla_status cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+rnla_status ensure_ctx();
+
+#define RNLA_CUDA(expr)                                                             \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return ::rnla::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+#define RNLA_TRY(expr)                          \
+    do {                                        \
+        rnla_status _s = (expr);                \
+        if (_s != RNLA_OK) return _s;           \
+    } while (0)
+
+// stream-ordered device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) n = 8;
+        bytes = n;
+        return cudaMallocAsync(&p, n, ctx().stream);
+    }
+    void release() {
+        if (p) { cudaFreeAsync(p, ctx().stream); p = nullptr; }
+    }
+    double* d() const { return static_cast<double*>(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// collectives over the communicator; no-ops when nranks == 1
+rnla_status allreduce_sum_f64(double* buf, size_t count);
+rnla_status allgather_i64(const int64_t* send_dev, int64_t* recv_dev, size_t count_per_rank);
+
+void phase_begin(const char* name);
+void phase_end();
+void phases_reset();
+
+struct PhaseScope {
+    explicit PhaseScope(const char* n) { phase_begin(n); }
+    ~PhaseScope() { phase_end(); }
+};
+
+}  // namespace rnla

@@ -1,0 +1,36 @@
+#pragma once
+#include "context.cuh"
+
+namespace rnla {
+
+struct ShardInfo { int64_t rows_local; int64_t row_off; int64_t rows_global; };
+
+rnla_status shard_layout(int64_t rows_local, ShardInfo* out);
+
+rnla_status dev_gemm_nn(const double* A, int64_t lda, int64_t m, int64_t K, const double* B, int64_t ldb, int64_t N,
+                        double* C, int64_t ldc);
+rnla_status dev_sketch_gemm(const double* A, int64_t lda, int64_t m, int64_t K, int dist, uint64_t seed, uint32_t stream,
+                            int64_t N, double* C, int64_t ldc);
+rnla_status dev_gemm_tn(const double* A, int64_t lda, int64_t m, int64_t n, const double* Q, int64_t ldq, int64_t N,
+                        double* Z, int64_t ldz, bool allreduce);
+rnla_status orth_inplace(double* X, int64_t ldx, const ShardInfo& sh, int p, bool sharded, double* R_out, int64_t* deficient_out);
+
+rnla_status dev_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
+                      const rnla_options& o, double* S);
+rnla_status dev_rf1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
+                    const rnla_options& o, double* Q, int64_t ldq);
+rnla_status dev_qb1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
+                    const rnla_options& o, double* Q, int64_t ldq, double* Bt);
+rnla_status dev_rand_svd(const double* A, int64_t lda, int64_t m_local, int64_t n, int64_t k, int64_t s,
+                         const rnla_options& o, double* U, int64_t ldu, double* Sigma, double* Vt, int64_t ldvt, int64_t* r_out);
+rnla_status dev_rand_evd1(const double* A, int64_t lda, int64_t m_local, int64_t n, int64_t k, int64_t s,
+                          const rnla_options& o, double* V, int64_t ldv, double* Lambda, int64_t* r_out);
+rnla_status dev_rand_evd2(const double* A, int64_t lda, int64_t m_local, int64_t n, int64_t k, int64_t s,
+                          const rnla_options& o, double* V, int64_t ldv, double* Lambda, int64_t* r_out);
+
+// literal.cu: bug-compatible pieces of the reference
+rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
+                          const rnla_options& o, double* S);
+rnla_status dev_stabilizer(const double* X, int64_t ldx, int64_t rows, int64_t cols, double* L, int64_t ldl);
+
+}  // namespace rnla

@@ -1,0 +1,478 @@
+// K1 / K1' / K5  (gemm_nn: tall A streamed once, optional in-kernel Philox right operand) and
+// K2 (gemm_tn: A^T Q / Gram, split over the long row dimension with a fixed-order reduction).
+//
+// Replaces the nalgebra products at reference src/lora_helpers.rs:21,41,76,89,95 and
+// src/lora_drivers.rs:66,121,148,187,191.
+//
+// Shape of both kernels (one CTA per SM, 384 threads):
+//   warps 0-3  producers: TMA-engine bulk copies (cp.async.bulk, one per tile column, into a padded
+//              bank-conflict-free smem layout), Philox/Gaussian generation of the Omega tile,
+//              manual zero-filling loads for ragged edges / unaligned inputs
+//   warps 4-11 consumers: 4 (M) x 2 (N) warp grid over a 128 x (16*NT) tile, DMMA.8x8x4 from smem
+//   mbarrier full/empty ring between them.
+#include "gemm.cuh"
+#include "ptx.cuh"
+#include "rng.cuh"
+
+namespace rnla {
+
+unsigned long long g_kernel_launches = 0;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int NCONS = 8;
+constexpr int NPROD = 4;
+constexpr int NPROD_THREADS = NPROD * 32;
+constexpr int NTHREADS = (NCONS + NPROD) * 32;
+constexpr int SMEM_BUDGET = 200 * 1024;
+// 384 threads x 168 regs at launch; producers give registers back, consumers take them:
+// 128 x 72 + 256 x 216 = 64512 = 384 x 168
+constexpr int PROD_REGS = 72;
+constexpr int CONS_REGS = 216;
+
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------------------------------------
+//  NN
+// ------------------------------------------------------------------------------------------
+constexpr int NN_BK = 16;
+constexpr int NN_BMP = BM + 4;      // A tile  [k][BMP]   (row index contiguous, as in global memory)
+constexpr int NN_BKP = NN_BK + 4;   // B tile  [j][BKP]   (k contiguous, as in global memory)
+
+template <int NT>
+struct NNCfg {
+    static constexpr int BN = 16 * NT;
+    static constexpr int A_TILE = NN_BK * NN_BMP;
+    static constexpr int B_TILE = BN * NN_BKP;
+    static constexpr int STAGE = A_TILE + B_TILE;                       // doubles
+    static constexpr int STAGES = cmin(6, SMEM_BUDGET / (STAGE * 8));
+    static constexpr int SMEM = STAGES * STAGE * 8 + 2 * STAGES * 8;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_nn_kernel(const GemmNN p, const int a_bulk, const int b_bulk) {
+    using Cfg = NNCfg<NT>;
+    constexpr int BN = Cfg::BN, BK = NN_BK, BMP = NN_BMP, BKP = NN_BKP, STAGES = Cfg::STAGES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tiles = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * Cfg::STAGE * 8);
+    uint64_t* empty = full + STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i0 = (int64_t)blockIdx.x * BM;
+    const int64_t j0 = (int64_t)blockIdx.y * BN;
+    const int rows_valid = (int)min((int64_t)BM, p.m - i0);
+    const int cols_valid = (int)min((int64_t)BN, p.N - j0);
+    const int KT = (int)((p.K + BK - 1) / BK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], NCONS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp < NPROD) {
+        // ================= producers =================
+        reg_dec<PROD_REGS>();
+        const int tid = threadIdx.x;   // 0..127
+        const double* Ablk = p.A + i0;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            double* As = tiles + (size_t)s * Cfg::STAGE;
+            double* Bs = As + Cfg::A_TILE;
+            const int64_t k0 = (int64_t)kt * BK;
+            const int kv = (int)min((int64_t)BK, p.K - k0);
+            const bool fullk = (kv == BK);
+            uint32_t tx = 0;
+            // ---- A tile ----
+            if (a_bulk && fullk) {
+                if (warp == 0) {
+                    const uint32_t bytes = (uint32_t)(rows_valid & ~1) * 8u;
+                    if (lane < BK) {
+                        const double* src = Ablk + (k0 + lane) * p.lda;
+                        if (bytes) bulk_g2s(As + lane * BMP, src, bytes, &full[s]);
+                        if (rows_valid & 1) As[lane * BMP + rows_valid - 1] = src[rows_valid - 1];
+                    }
+                    tx += bytes * BK;
+                }
+            } else {
+                for (int idx = tid; idx < BK * BM; idx += NPROD_THREADS) {
+                    const int kk = idx / BM, r = idx - kk * BM;
+                    double v = 0.0;
+                    if (kk < kv && r < rows_valid) v = ldg_stream(Ablk + r + (k0 + kk) * p.lda);
+                    As[kk * BMP + r] = v;
+                }
+            }
+            // ---- B tile ----
+            if (p.gen) {
+                const uint64_t q0 = (p.k_off + (uint64_t)k0) >> 2;
+                for (int idx = tid; idx < (BK / 4) * BN; idx += NPROD_THREADS) {
+                    const int j = idx >> 2, qd = idx & 3;
+                    if (j < cols_valid) {
+                        const u32x4 b = omega_block(p.seed, p.stream, q0 + qd, (uint32_t)(j0 + j));
+                        double2 lo, hi;
+                        lo.x = sample_from_u32(p.dist, b.x); lo.y = sample_from_u32(p.dist, b.y);
+                        hi.x = sample_from_u32(p.dist, b.z); hi.y = sample_from_u32(p.dist, b.w);
+                        double2* dst = reinterpret_cast<double2*>(Bs + j * BKP + 4 * qd);
+                        dst[0] = lo; dst[1] = hi;
+                    }
+                }
+            } else if (b_bulk && fullk) {
+                if (warp == 0) {
+                    for (int j = lane; j < cols_valid; j += 32)
+                        bulk_g2s(Bs + j * BKP, p.B + k0 + (j0 + j) * p.ldb, BK * 8, &full[s]);
+                    tx += (uint32_t)cols_valid * BK * 8u;
+                }
+            } else {
+                for (int idx = tid; idx < BK * BN; idx += NPROD_THREADS) {
+                    const int j = idx / BK, kk = idx - j * BK;
+                    double v = 0.0;
+                    if (kk < kv && j < cols_valid) v = p.B[k0 + kk + (j0 + j) * p.ldb];
+                    Bs[j * BKP + kk] = v;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (warp == 0) mbar_arrive_expect_tx(&full[s], tx);
+                else mbar_arrive(&full[s]);
+            }
+        }
+    } else {
+        // ================= consumers =================
+        reg_inc<CONS_REGS>();
+        const int cw = warp - NPROD;
+        const int wm = cw & 3, wn = cw >> 2;
+        const int g = lane >> 2, t = lane & 3;
+        double acc[4][NT][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+
+        const int a_off = t * BMP + wm * 32 + g;
+        const int b_off = (wn * 8 * NT + g) * BKP + t;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+            mbar_wait(&full[s], ph);
+            const double* As = tiles + (size_t)s * Cfg::STAGE + a_off;
+            const double* Bs = tiles + (size_t)s * Cfg::STAGE + Cfg::A_TILE + b_off;
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ++ks) {
+                double a[4], b[NT];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) a[mi] = As[ks * 4 * BMP + mi * 8];
+#pragma unroll
+                for (int ni = 0; ni < NT; ++ni) b[ni] = Bs[ni * 8 * BKP + ks * 4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // ---- epilogue ----
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int64_t row = i0 + wm * 32 + mi * 8 + g;
+            if (row < p.m) {
+#pragma unroll
+                for (int ni = 0; ni < NT; ++ni) {
+                    const int64_t col = j0 + wn * 8 * NT + ni * 8 + 2 * t;
+                    if (col < p.N) p.C[row + col * p.ldc] = acc[mi][ni][0];
+                    if (col + 1 < p.N) p.C[row + (col + 1) * p.ldc] = acc[mi][ni][1];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+//  TN
+// ------------------------------------------------------------------------------------------
+template <int NT, int BK>
+struct TNCfg {
+    static constexpr int BN = 16 * NT;
+    static constexpr int BKP = BK + 4;
+    static constexpr int A_TILE = BM * BKP;      // [j][BKP]
+    static constexpr int B_TILE = BN * BKP;      // [c][BKP]
+    static constexpr int STAGE = A_TILE + B_TILE;
+    static constexpr int STAGES = cmin(6, SMEM_BUDGET / (STAGE * 8));
+    static constexpr int SMEM = STAGES * STAGE * 8 + 2 * STAGES * 8;
+};
+
+template <int NT, int BK>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tn_kernel(const GemmTN p, double* __restrict__ P, const int64_t ldp, const int64_t pstride,
+               const int chunks, const int64_t chunk_rows, const int njb, const int a_bulk, const int q_bulk) {
+    using Cfg = TNCfg<NT, BK>;
+    constexpr int BN = Cfg::BN, BKP = Cfg::BKP, STAGES = Cfg::STAGES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tiles = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * Cfg::STAGE * 8);
+    uint64_t* empty = full + STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jb = blockIdx.x % njb, chunk = blockIdx.x / njb;
+    const int64_t j0 = (int64_t)jb * BM;              // first column of A (= output row)
+    const int64_t c0 = (int64_t)blockIdx.y * BN;      // first column of Q (= output column)
+    const int jv = (int)min((int64_t)BM, p.n - j0);
+    const int cv = (int)min((int64_t)BN, p.N - c0);
+    const int64_t r0 = (int64_t)chunk * chunk_rows;
+    const int64_t r1 = min(p.m, r0 + chunk_rows);
+    const int KT = (int)((r1 - r0 + BK - 1) / BK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], NCONS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp < NPROD) {
+        reg_dec<PROD_REGS>();
+        const int tid = threadIdx.x;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            double* As = tiles + (size_t)s * Cfg::STAGE;
+            double* Qs = As + Cfg::A_TILE;
+            const int64_t r = r0 + (int64_t)kt * BK;
+            const int kv = (int)min((int64_t)BK, r1 - r);
+            const bool fullk = (kv == BK);
+            uint32_t tx = 0;
+            if (a_bulk && fullk) {
+                int cnt = 0;
+                for (int j = tid; j < jv; j += NPROD_THREADS, ++cnt)
+                    bulk_g2s(As + j * BKP, p.A + r + (j0 + j) * p.lda, BK * 8, &full[s]);
+                // every lane must know the warp's byte count: recompute it arithmetically
+                const int wfirst = warp * 32;
+                int wcnt = 0;
+                for (int base = wfirst; base < jv; base += NPROD_THREADS) wcnt += min(32, jv - base);
+                tx += (uint32_t)wcnt * BK * 8u;
+            } else {
+                for (int idx = tid; idx < BM * BK; idx += NPROD_THREADS) {
+                    const int j = idx / BK, kk = idx - j * BK;
+                    double v = 0.0;
+                    if (kk < kv && j < jv) v = ldg_stream(p.A + r + kk + (j0 + j) * p.lda);
+                    As[j * BKP + kk] = v;
+                }
+            }
+            if (q_bulk && fullk) {
+                for (int c = tid; c < cv; c += NPROD_THREADS)
+                    bulk_g2s(Qs + c * BKP, p.Q + r + (c0 + c) * p.ldq, BK * 8, &full[s]);
+                const int wfirst = warp * 32;
+                int wcnt = 0;
+                for (int base = wfirst; base < cv; base += NPROD_THREADS) wcnt += min(32, cv - base);
+                tx += (uint32_t)wcnt * BK * 8u;
+            } else {
+                for (int idx = tid; idx < BN * BK; idx += NPROD_THREADS) {
+                    const int c = idx / BK, kk = idx - c * BK;
+                    double v = 0.0;
+                    if (kk < kv && c < cv) v = p.Q[r + kk + (c0 + c) * p.ldq];
+                    Qs[c * BKP + kk] = v;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (tx) mbar_arrive_expect_tx(&full[s], tx);
+                else mbar_arrive(&full[s]);
+            }
+        }
+    } else {
+        reg_inc<CONS_REGS>();
+        const int cw = warp - NPROD;
+        const int wm = cw & 3, wn = cw >> 2;
+        const int g = lane >> 2, t = lane & 3;
+        double acc[4][NT][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+
+        const int a_off = (wm * 32 + g) * BKP + t;
+        const int b_off = (wn * 8 * NT + g) * BKP + t;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+            mbar_wait(&full[s], ph);
+            const double* As = tiles + (size_t)s * Cfg::STAGE + a_off;
+            const double* Qs = tiles + (size_t)s * Cfg::STAGE + Cfg::A_TILE + b_off;
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ++ks) {
+                double a[4], b[NT];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * BKP + ks * 4];
+#pragma unroll
+                for (int ni = 0; ni < NT; ++ni) b[ni] = Qs[ni * 8 * BKP + ks * 4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        double* out; int64_t ld;
+        if (chunks > 1) { out = P + (int64_t)chunk * pstride; ld = ldp; }
+        else { out = p.Z; ld = p.ldz; }
+        const bool accum = (chunks == 1) && p.accumulate;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int64_t row = j0 + wm * 32 + mi * 8 + g;
+            if (row < p.n) {
+#pragma unroll
+                for (int ni = 0; ni < NT; ++ni) {
+                    const int64_t col = c0 + wn * 8 * NT + ni * 8 + 2 * t;
+                    if (col < p.N) {
+                        double* d = out + row + col * ld;
+                        *d = accum ? *d + acc[mi][ni][0] : acc[mi][ni][0];
+                    }
+                    if (col + 1 < p.N) {
+                        double* d = out + row + (col + 1) * ld;
+                        *d = accum ? *d + acc[mi][ni][1] : acc[mi][ni][1];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// fixed-order reduction of the per-chunk partials
+__global__ void __launch_bounds__(256)
+tn_reduce_kernel(const double* __restrict__ P, int64_t ldp, int64_t pstride, int chunks,
+                 double* __restrict__ Z, int64_t ldz, int64_t n, int64_t N, int accumulate) {
+    const int64_t total = n * N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = idx / n, i = idx - j * n;
+        const double* src = P + i + j * ldp;
+        double s = 0.0;
+        for (int c = 0; c < chunks; ++c) s += src[(int64_t)c * pstride];
+        double* d = Z + i + j * ldz;
+        *d = accumulate ? *d + s : s;
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int NT>
+cudaError_t launch_nn(const GemmNN& p, int nblkN, cudaStream_t st) {
+    using Cfg = NNCfg<NT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_nn_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int a_bulk = aligned16(p.A) && (p.lda % 2 == 0);
+    const int b_bulk = !p.gen && aligned16(p.B) && (p.ldb % 2 == 0);
+    dim3 grid((unsigned)((p.m + BM - 1) / BM), (unsigned)nblkN);
+    gemm_nn_kernel<NT><<<grid, NTHREADS, Cfg::SMEM, st>>>(p, a_bulk, b_bulk);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+constexpr int TN_BK = 32;
+
+struct TNPlan { int nblkN, NT, njb, chunks; int64_t chunk_rows, ldp, pstride; };
+
+TNPlan plan_tn(int64_t m, int64_t n, int64_t N, int sms) {
+    TNPlan pl;
+    pl.nblkN = (int)((N + 127) / 128);
+    const int64_t per = (N + pl.nblkN - 1) / pl.nblkN;
+    pl.NT = (int)((per + 15) / 16);
+    pl.njb = (int)((n + BM - 1) / BM);
+    const int64_t tiles = (int64_t)pl.njb * pl.nblkN;
+    int64_t want = (8LL * sms + tiles - 1) / tiles;
+    const int64_t maxc = m / (16 * TN_BK) > 0 ? m / (16 * TN_BK) : 1;
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    int64_t cr = (m + want - 1) / want;
+    cr = (cr + TN_BK - 1) / TN_BK * TN_BK;
+    if (cr <= 0) cr = TN_BK;
+    pl.chunk_rows = cr;
+    pl.chunks = (int)((m + cr - 1) / cr);
+    if (pl.chunks < 1) pl.chunks = 1;
+    pl.ldp = n;
+    pl.pstride = n * N;
+    return pl;
+}
+
+template <int NT>
+cudaError_t launch_tn(const GemmTN& p, const TNPlan& pl, double* ws, cudaStream_t st) {
+    using Cfg = TNCfg<NT, TN_BK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<NT, TN_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int a_bulk = aligned16(p.A) && (p.lda % 2 == 0);
+    const int q_bulk = aligned16(p.Q) && (p.ldq % 2 == 0);
+    dim3 grid((unsigned)(pl.njb * pl.chunks), (unsigned)pl.nblkN);
+    gemm_tn_kernel<NT, TN_BK><<<grid, NTHREADS, Cfg::SMEM, st>>>(p, ws, pl.ldp, pl.pstride, pl.chunks,
+                                                               pl.chunk_rows, pl.njb, a_bulk, q_bulk);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t gemm_nn(const GemmNN& p, cudaStream_t st) {
+    if (p.m <= 0 || p.N <= 0) return cudaSuccess;
+    if (p.gen && (p.k_off & 3)) return cudaErrorInvalidValue;
+    const int nblkN = (int)((p.N + 127) / 128);
+    const int64_t per = (p.N + nblkN - 1) / nblkN;
+    const int NT = (int)((per + 15) / 16);
+    switch (NT) {
+        case 1: return launch_nn<1>(p, nblkN, st);
+        case 2: return launch_nn<2>(p, nblkN, st);
+        case 3: return launch_nn<3>(p, nblkN, st);
+        case 4: return launch_nn<4>(p, nblkN, st);
+        case 5: return launch_nn<5>(p, nblkN, st);
+        case 6: return launch_nn<6>(p, nblkN, st);
+        case 7: return launch_nn<7>(p, nblkN, st);
+        default: return launch_nn<8>(p, nblkN, st);
+    }
+}
+
+size_t gemm_tn_workspace_bytes(int64_t m, int64_t n, int64_t N, int sms) {
+    const TNPlan pl = plan_tn(m, n, N, sms);
+    return pl.chunks > 1 ? (size_t)pl.chunks * (size_t)pl.pstride * sizeof(double) : 0;
+}
+
+cudaError_t gemm_tn(const GemmTN& p, double* workspace, size_t workspace_bytes, int sms, cudaStream_t st) {
+    if (p.n <= 0 || p.N <= 0) return cudaSuccess;
+    const TNPlan pl = plan_tn(p.m, p.n, p.N, sms);
+    if (pl.chunks > 1 && workspace_bytes < (size_t)pl.chunks * (size_t)pl.pstride * sizeof(double))
+        return cudaErrorInvalidValue;
+    cudaError_t e;
+    switch (pl.NT) {
+        case 1: e = launch_tn<1>(p, pl, workspace, st); break;
+        case 2: e = launch_tn<2>(p, pl, workspace, st); break;
+        case 3: e = launch_tn<3>(p, pl, workspace, st); break;
+        case 4: e = launch_tn<4>(p, pl, workspace, st); break;
+        case 5: e = launch_tn<5>(p, pl, workspace, st); break;
+        case 6: e = launch_tn<6>(p, pl, workspace, st); break;
+        case 7: e = launch_tn<7>(p, pl, workspace, st); break;
+        default: e = launch_tn<8>(p, pl, workspace, st); break;
+    }
+    if (e != cudaSuccess) return e;
+    if (pl.chunks > 1) {
+        const int64_t total = p.n * p.N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > sms * 8) blocks = sms * 8;
+        tn_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, pl.ldp, pl.pstride, pl.chunks, p.Z, p.ldz, p.n, p.N, p.accumulate);
+        ++g_kernel_launches;
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+}  // namespace rnla

@@ -1,0 +1,587 @@
+// Small dense core and panel utilities; see panel.cuh.  These are latency-/HBM-bound helpers next to
+// the GEMM passes (<3 % of a rand_svd at the headline size), written for clarity.
+#include "panel.cuh"
+#include "gemm.cuh"
+#include "rng.cuh"
+#include <cfloat>
+#include <cmath>
+
+namespace rnla {
+
+#define LAUNCHED() (++g_kernel_launches, cudaGetLastError())
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- K0 fills
+__global__ void __launch_bounds__(256)
+fill_philox_kernel(int dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols, int64_t row_off,
+                   double* __restrict__ out, int64_t ld) {
+    const uint64_t q_first = (uint64_t)row_off >> 2;
+    const uint64_t q_last = (uint64_t)(row_off + rows - 1) >> 2;
+    const int64_t nq = (int64_t)(q_last - q_first + 1);
+    const int64_t total = nq * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / nq, qi = idx - c * nq;
+        const uint64_t q = q_first + (uint64_t)qi;
+        const u32x4 b = omega_block(seed, stream, q, (uint32_t)c);
+        const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t r = (int64_t)(4 * q + e) - row_off;
+            if (r >= 0 && r < rows) out[r + c * ld] = sample_from_u32(dist, w[e]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fill_threefry_kernel(int dist, uint64_t k0, uint64_t k1, int64_t rows, int64_t cols, double* __restrict__ out, int64_t ld) {
+    const int64_t total = rows * cols;
+    const int64_t nblk = (total + 1) / 2;
+    for (int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; blk < nblk;
+         blk += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t x[2];
+        threefry2x64_20((uint64_t)blk, 0ull, k0, k1, x[0], x[1]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int64_t t = 2 * blk + e;
+            if (t < total) {
+                const int64_t c = t / rows, r = t - c * rows;
+                double v;
+                if (dist == DIST_UNIFORM) {
+                    // rand 0.8.5 UniformFloat<f64>::sample: [1,2) from the top 52 bits, -1, * scale(2) + low(-1), no fma
+                    const double v12 = __longlong_as_double((long long)((x[e] >> 12) | 0x3FF0000000000000ull));
+                    v = __dadd_rn(__dmul_rn(__dadd_rn(v12, -1.0), 2.0), -1.0);
+                } else {
+                    v = (x[e] < 0x8000000000000000ull) ? 1.0 : -1.0;   // Bernoulli(0.5): u64 < 2^63
+                }
+                out[r + c * ld] = v;
+            }
+        }
+    }
+}
+
+__global__ void philox_blocks_kernel(int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const u32x4 r = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1]);
+        out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+    }
+}
+__global__ void threefry_blocks_kernel(int64_t n, const uint64_t* ctr, const uint64_t* key, uint64_t* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) threefry2x64_20(ctr[2 * i], ctr[2 * i + 1], key[2 * i], key[2 * i + 1], out[2 * i], out[2 * i + 1]);
+}
+
+// ---------------------------------------------------------------- Cholesky with deficiency detection
+__global__ void __launch_bounds__(1024)
+chol_upper_kernel(double* __restrict__ G, int64_t ld, int p, double tol2, int* __restrict__ flags, int* __restrict__ info) {
+    __shared__ double s_red[32];
+    __shared__ double s_piv;
+    __shared__ int s_def, s_ndef, s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (tid == 0) { s_ndef = 0; s_bad = 0; }
+    __syncthreads();
+    for (int j = 0; j < p; ++j) {
+        // pivot d = G_jj - sum_{k<j} R_kj^2
+        double part = 0.0;
+        for (int k = tid; k < j; k += blockDim.x) { const double v = G[k + j * ld]; part += v * v; }
+        part = warp_sum(part);
+        if (lane == 0) s_red[warp] = part;
+        __syncthreads();
+        if (warp == 0) {
+            double v = lane < nwarps ? s_red[lane] : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) {
+                const double gjj = G[j + j * ld];
+                const double d = gjj - v;
+                // 0 = regular column, 1 = numerically dependent on the previous ones (keep its residual,
+                // it gets a fresh chance in the next pass), 2 = exactly zero column (caller replaces it)
+                int def = 0;
+                if (!(gjj > 0.0)) def = 2;
+                else if (!(d > tol2 * gjj)) def = 1;
+                if (!isfinite(gjj) || !isfinite(v)) { s_bad = 1; def = 2; }
+                const double piv = def ? 1.0 : sqrt(d);
+                G[j + j * ld] = piv;
+                flags[j] = def;
+                s_ndef += (def != 0);
+                s_piv = piv; s_def = def;
+            }
+        }
+        __syncthreads();
+        const double piv = s_piv; const int def = s_def;
+        // row j of R, one warp per column i
+        for (int i = j + 1 + warp; i < p; i += nwarps) {
+            double dot = 0.0;
+            if (!def) for (int k = lane; k < j; k += 32) dot += G[k + j * ld] * G[k + (int64_t)i * ld];
+            dot = warp_sum(dot);
+            if (lane == 0) G[j + (int64_t)i * ld] = def ? 0.0 : (G[j + (int64_t)i * ld] - dot) / piv;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        if (r > c) G[r + (int64_t)c * ld] = 0.0;
+    }
+    if (tid == 0) { info[0] = s_ndef; info[1] = s_bad; }
+}
+
+__global__ void __launch_bounds__(1024)
+tri_inv_upper_kernel(const double* __restrict__ R, int64_t ldr, int p, double* __restrict__ X, int64_t ldi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < p; j += nwarps) {
+        double* x = X + (int64_t)j * ldi;
+        for (int i = lane; i < p; i += 32) if (i > j) x[i] = 0.0;
+        __syncwarp();
+        for (int i = j; i >= 0; --i) {
+            double s = 0.0;
+            for (int k = i + 1 + lane; k <= j; k += 32) s += R[i + (int64_t)k * ldr] * x[k];
+            s = warp_sum(s);
+            if (lane == 0) x[i] = ((i == j ? 1.0 : 0.0) - s) / R[i + (int64_t)i * ldr];
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+small_gemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                  double* __restrict__ C, int64_t ldc, int M, int N, int K) {
+    const int64_t total = (int64_t)M * N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx / M), r = (int)(idx - (int64_t)c * M);
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s += A[r + (int64_t)k * lda] * B[k + (int64_t)c * ldb];
+        C[r + (int64_t)c * ldc] = s;
+    }
+}
+
+__global__ void zero_flagged_diag_kernel(double* R, int64_t ld, int p, const int* flags) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < p && flags[j] == 2) R[j + (int64_t)j * ld] = 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+replace_columns_kernel(double* __restrict__ X, int64_t ld, int64_t rows, int64_t row_off, int p,
+                       const int* __restrict__ flags, const int64_t* __restrict__ target) {
+    const int j = blockIdx.y;
+    if (j >= p || flags[j] != 2) return;
+    const int64_t tgt = target[j] - row_off;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)
+        X[r + (int64_t)j * ld] = (r == tgt) ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+set_identity_kernel(double* X, int64_t ld, int64_t rows, int64_t cols) {
+    const int64_t total = rows * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / rows, r = idx - c * rows;
+        X[r + c * ld] = (r == c) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+axpby_kernel(double a, const double* __restrict__ x, int64_t ldx, double b, const double* __restrict__ y, int64_t ldy,
+             double* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
+    const int64_t total = rows * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / rows, r = idx - c * rows;
+        double v = 0.0;
+        if (x) v = a * x[r + c * ldx];
+        if (y) v += b * y[r + c * ldy];
+        dst[r + c * ldd] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t r = r0 + tx, c = c0 + k;
+        tile[k][tx] = (r < rows && c < cols) ? src[r + c * lds] : 0.0;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t c = c0 + tx, r = r0 + k;       // dst(c, r) = src(r, c)
+        if (r < rows && c < cols) dst[c + r * ldd] = tile[tx][k];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_partial_kernel(const double* __restrict__ X, int64_t ld, int64_t rows, int64_t cols, double* __restrict__ scratch) {
+    __shared__ double s_red[8];
+    const int64_t total = rows * cols;
+    double s = 0.0;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / rows, r = idx - c * rows;
+        const double v = X[r + c * ld];
+        s += v * v;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        scratch[blockIdx.x] = t;
+    }
+}
+__global__ void sumsq_final_kernel(const double* scratch, int n, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += scratch[i];
+        out[0] += t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+check_symmetric_kernel(const double* __restrict__ A, int64_t lda, int64_t n, int* flag) {
+    const int64_t total = n * n;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / n, r = idx - c * n;
+        if (r > c && A[r + c * lda] != A[c + r * lda]) *flag = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scale_columns_kernel(double* X, int64_t ld, int64_t rows, int64_t cols, const double* s) {
+    const int64_t total = rows * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / rows, r = idx - c * rows;
+        X[r + c * ld] *= s[c];
+    }
+}
+
+// ---------------------------------------------------------------- Jacobi kernels (single CTA)
+__device__ __forceinline__ void rr_pair(int round, int idx, int P, int& a, int& b) {
+    // round-robin tournament on P (even) players
+    if (idx == 0) { a = P - 1; b = round; }
+    else { a = (round + idx) % (P - 1); b = (round - idx + (P - 1)) % (P - 1); }
+    if (a > b) { const int t = a; a = b; b = t; }
+}
+
+constexpr int JACOBI_MAX_SWEEPS = 40;
+
+__global__ void __launch_bounds__(1024)
+jacobi_svd_kernel(const double* __restrict__ M, int64_t ldm, int p, double* __restrict__ U, int64_t ldu,
+                  double* __restrict__ sigma, double* __restrict__ Vout, int64_t ldv, double* __restrict__ work, int* info) {
+    double* W = work;                    // p x p, ld p
+    double* V = work + (size_t)p * p;    // p x p, ld p
+    __shared__ int s_rot;
+    __shared__ int s_sweeps, s_conv;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        W[idx] = M[r + (int64_t)c * ldm];
+        V[idx] = (r == c) ? 1.0 : 0.0;
+    }
+    if (tid == 0) { s_sweeps = 0; s_conv = 0; }
+    __syncthreads();
+    const int P = (p & 1) ? p + 1 : p;
+    const double tol = sqrt((double)(p > 1 ? p : 1)) * DBL_EPSILON;
+    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS && P >= 2; ++sweep) {
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        for (int round = 0; round < P - 1; ++round) {
+            for (int pi = warp; pi < P / 2; pi += nwarps) {
+                int a, b; rr_pair(round, pi, P, a, b);
+                if (b >= p) continue;
+                double* wa = W + (size_t)a * p; double* wb = W + (size_t)b * p;
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int k = lane; k < p; k += 32) { const double x = wa[k], y = wb[k]; al += x * x; be += y * y; ga += x * y; }
+                al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+                if (fabs(ga) > tol * sqrt(al * be) && fabs(ga) > DBL_MIN) {
+                    const double zeta = (be - al) / (2.0 * ga);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    double* va = V + (size_t)a * p; double* vb = V + (size_t)b * p;
+                    for (int k = lane; k < p; k += 32) {
+                        const double x = wa[k], y = wb[k];
+                        wa[k] = cs * x - sn * y; wb[k] = sn * x + cs * y;
+                        const double vx = va[k], vy = vb[k];
+                        va[k] = cs * vx - sn * vy; vb[k] = sn * vx + cs * vy;
+                    }
+                    if (lane == 0) s_rot = 1;
+                }
+            }
+            __syncthreads();
+        }
+        const int rot = s_rot;
+        __syncthreads();
+        if (tid == 0) s_sweeps = sweep + 1;
+        if (!rot) { if (tid == 0) s_conv = 1; break; }
+    }
+    __syncthreads();
+    // column norms -> sigma (unsorted, stored temporarily in sigma[]), then rank by value (stable, descending)
+    for (int j = warp; j < p; j += nwarps) {
+        double s = 0.0;
+        for (int k = lane; k < p; k += 32) { const double x = W[(size_t)j * p + k]; s += x * x; }
+        s = warp_sum(s);
+        if (lane == 0) sigma[j] = sqrt(s);
+    }
+    __syncthreads();
+    // rank: one thread per column; ranks kept in registers; needs sigma unsorted snapshot -> copy into U's first column? use V diag trick: keep in work tail
+    double* sig_tmp = work + 2 * (size_t)p * p;   // p doubles (caller provides 2*p*p + p)
+    for (int j = tid; j < p; j += blockDim.x) sig_tmp[j] = sigma[j];
+    __syncthreads();
+    for (int j = warp; j < p; j += nwarps) {
+        const double sj = sig_tmp[j];
+        int rank = 0;
+        for (int i = lane; i < p; i += 32) { const double si = sig_tmp[i]; rank += (si > sj) || (si == sj && i < j); }
+        rank = (int)(warp_sum((double)rank) + 0.5);
+        const double inv = sj > 0.0 ? 1.0 / sj : 0.0;
+        for (int k = lane; k < p; k += 32) {
+            U[k + (int64_t)rank * ldu] = W[(size_t)j * p + k] * inv;
+            Vout[k + (int64_t)rank * ldv] = V[(size_t)j * p + k];
+        }
+        if (lane == 0) sigma[rank] = sj;
+    }
+    __syncthreads();
+    // orthonormal completion of U for exactly-zero singular values: candidates e_0, e_1, ... (two Gram-Schmidt passes)
+    // executed by warp 0 only (rare path)
+    if (warp == 0) {
+        int cand = 0;
+        for (int j = 0; j < p; ++j) {
+            if (sigma[j] > 0.0) continue;
+            double* uj = U + (int64_t)j * ldu;
+            for (; cand < p; ++cand) {
+                for (int k = lane; k < p; k += 32) uj[k] = (k == cand) ? 1.0 : 0.0;
+                __syncwarp();
+                for (int pass = 0; pass < 2; ++pass) {
+                    for (int i = 0; i < p; ++i) {
+                        if (i == j) continue;
+                        if (i > j && !(sigma[i] > 0.0)) continue;      // not yet built
+                        const double* ui = U + (int64_t)i * ldu;
+                        double d = 0.0;
+                        for (int k = lane; k < p; k += 32) d += ui[k] * uj[k];
+                        d = warp_sum(d);
+                        for (int k = lane; k < p; k += 32) uj[k] -= d * ui[k];
+                        __syncwarp();
+                    }
+                }
+                double nn = 0.0;
+                for (int k = lane; k < p; k += 32) nn += uj[k] * uj[k];
+                nn = warp_sum(nn);
+                if (nn > 0.25) {
+                    const double inv = 1.0 / sqrt(nn);
+                    for (int k = lane; k < p; k += 32) uj[k] *= inv;
+                    __syncwarp();
+                    ++cand;
+                    break;
+                }
+            }
+        }
+    }
+    if (tid == 0) { info[0] = s_sweeps; info[1] = s_conv ? 0 : 1; }
+}
+
+constexpr int EIGH_MAX_PAIRS = 512;
+
+__global__ void __launch_bounds__(1024)
+jacobi_eigh_kernel(const double* __restrict__ C, int64_t ldc, int p, double* __restrict__ Wout, int64_t ldw,
+                   double* __restrict__ lambda, int order, double* __restrict__ work, int* info) {
+    double* A = work;                    // p x p
+    double* V = work + (size_t)p * p;    // p x p
+    double* lam_tmp = work + 2 * (size_t)p * p;
+    __shared__ double s_cs[EIGH_MAX_PAIRS], s_sn[EIGH_MAX_PAIRS];
+    __shared__ int s_a[EIGH_MAX_PAIRS], s_b[EIGH_MAX_PAIRS];
+    __shared__ int s_rot, s_sweeps, s_conv;
+    __shared__ double s_red[32];
+    __shared__ double s_floor;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    double fro = 0.0;
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        // symmetrise defensively: use the average of the two triangles
+        const double v = 0.5 * (C[r + (int64_t)c * ldc] + C[c + (int64_t)r * ldc]);
+        A[idx] = v; fro += v * v;
+        V[idx] = (r == c) ? 1.0 : 0.0;
+    }
+    fro = warp_sum(fro);
+    if (lane == 0) s_red[warp] = fro;
+    if (tid == 0) { s_sweeps = 0; s_conv = 0; }
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < nwarps; ++w) t += s_red[w]; s_floor = 1e-20 * sqrt(t); }
+    __syncthreads();
+    const double afloor = s_floor;
+    const int P = (p & 1) ? p + 1 : p;
+    const int npairs = P / 2;
+    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS && P >= 2; ++sweep) {
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        for (int round = 0; round < P - 1; ++round) {
+            for (int pi = tid; pi < npairs; pi += blockDim.x) {
+                int a, b; rr_pair(round, pi, P, a, b);
+                double cs = 1.0, sn = 0.0;
+                if (b < p) {
+                    const double aa = A[a + (size_t)a * p], bb = A[b + (size_t)b * p], ab = A[a + (size_t)b * p];
+                    if (fabs(ab) > DBL_EPSILON * sqrt(fabs(aa * bb)) && fabs(ab) > afloor) {
+                        const double tau = (bb - aa) / (2.0 * ab);
+                        const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        cs = 1.0 / sqrt(1.0 + t * t); sn = t * cs;
+                        s_rot = 1;
+                    }
+                } else { a = -1; }
+                s_a[pi] = a; s_b[pi] = b; s_cs[pi] = cs; s_sn[pi] = sn;
+            }
+            __syncthreads();
+            // columns: A <- A J, V <- V J
+            for (int idx = tid; idx < npairs * p; idx += blockDim.x) {
+                const int pi = idx / p, k = idx - pi * p;
+                const int a = s_a[pi]; const double sn = s_sn[pi];
+                if (a < 0 || sn == 0.0) continue;
+                const int b = s_b[pi]; const double cs = s_cs[pi];
+                const double x = A[k + (size_t)a * p], y = A[k + (size_t)b * p];
+                A[k + (size_t)a * p] = cs * x - sn * y; A[k + (size_t)b * p] = sn * x + cs * y;
+                const double vx = V[k + (size_t)a * p], vy = V[k + (size_t)b * p];
+                V[k + (size_t)a * p] = cs * vx - sn * vy; V[k + (size_t)b * p] = sn * vx + cs * vy;
+            }
+            __syncthreads();
+            // rows: A <- J^T A
+            for (int idx = tid; idx < npairs * p; idx += blockDim.x) {
+                const int pi = idx / p, k = idx - pi * p;
+                const int a = s_a[pi]; const double sn = s_sn[pi];
+                if (a < 0 || sn == 0.0) continue;
+                const int b = s_b[pi]; const double cs = s_cs[pi];
+                const double x = A[a + (size_t)k * p], y = A[b + (size_t)k * p];
+                A[a + (size_t)k * p] = cs * x - sn * y; A[b + (size_t)k * p] = sn * x + cs * y;
+            }
+            __syncthreads();
+        }
+        const int rot = s_rot;
+        __syncthreads();
+        if (tid == 0) s_sweeps = sweep + 1;
+        if (!rot) { if (tid == 0) s_conv = 1; break; }
+    }
+    __syncthreads();
+    for (int j = tid; j < p; j += blockDim.x) lam_tmp[j] = A[j + (size_t)j * p];
+    __syncthreads();
+    for (int j = warp; j < p; j += nwarps) {
+        const double lj = lam_tmp[j];
+        const double kj = order ? fabs(lj) : lj;
+        int rank = 0;
+        for (int i = lane; i < p; i += 32) {
+            const double li = lam_tmp[i]; const double ki = order ? fabs(li) : li;
+            rank += (ki > kj) || (ki == kj && i < j);
+        }
+        rank = (int)(warp_sum((double)rank) + 0.5);
+        for (int k = lane; k < p; k += 32) Wout[k + (int64_t)rank * ldw] = V[k + (size_t)j * p];
+        if (lane == 0) lambda[rank] = lj;
+    }
+    if (tid == 0) { info[0] = s_sweeps; info[1] = s_conv ? 0 : 1; }
+}
+
+inline int grid_for(int64_t total, int threads, int cap = 148 * 16) {
+    int64_t b = (total + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
+
+}  // namespace
+
+cudaError_t fill_philox(int dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols, int64_t row_off,
+                        double* out, int64_t ld, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    fill_philox_kernel<<<grid_for((rows / 4 + 2) * cols, 256), 256, 0, st>>>(dist, seed, stream, rows, cols, row_off, out, ld);
+    return LAUNCHED();
+}
+cudaError_t fill_threefry(int dist, uint64_t key0, uint64_t key1, int64_t rows, int64_t cols, double* out, int64_t ld, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    fill_threefry_kernel<<<grid_for((rows * cols + 1) / 2, 256), 256, 0, st>>>(dist, key0, key1, rows, cols, out, ld);
+    return LAUNCHED();
+}
+cudaError_t philox_blocks(int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    philox_blocks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ctr, key, out);
+    return LAUNCHED();
+}
+cudaError_t threefry_blocks(int64_t n, const uint64_t* ctr, const uint64_t* key, uint64_t* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    threefry_blocks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ctr, key, out);
+    return LAUNCHED();
+}
+cudaError_t chol_upper(double* G, int64_t ld, int p, double tol2, int* flags, int* info, cudaStream_t st) {
+    chol_upper_kernel<<<1, 1024, 0, st>>>(G, ld, p, tol2, flags, info);
+    return LAUNCHED();
+}
+cudaError_t tri_inv_upper(const double* R, int64_t ldr, int p, double* Rinv, int64_t ldi, cudaStream_t st) {
+    tri_inv_upper_kernel<<<1, 1024, 0, st>>>(R, ldr, p, Rinv, ldi);
+    return LAUNCHED();
+}
+cudaError_t small_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                       int M, int N, int K, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    small_gemm_kernel<<<grid_for((int64_t)M * N, 256), 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K);
+    return LAUNCHED();
+}
+cudaError_t zero_flagged_diag(double* R, int64_t ld, int p, const int* flags, cudaStream_t st) {
+    zero_flagged_diag_kernel<<<(p + 255) / 256, 256, 0, st>>>(R, ld, p, flags);
+    return LAUNCHED();
+}
+cudaError_t replace_columns(double* X, int64_t ld, int64_t rows, int64_t row_off, int p, const int* flags,
+                            const int64_t* target, cudaStream_t st) {
+    if (rows <= 0 || p <= 0) return cudaSuccess;
+    dim3 grid((unsigned)grid_for(rows, 256, 64), (unsigned)p);
+    replace_columns_kernel<<<grid, 256, 0, st>>>(X, ld, rows, row_off, p, flags, target);
+    return LAUNCHED();
+}
+cudaError_t set_identity(double* X, int64_t ld, int64_t rows, int64_t cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    set_identity_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(X, ld, rows, cols);
+    return LAUNCHED();
+}
+cudaError_t copy_matrix(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows, int64_t cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    return cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyDeviceToDevice, st);
+}
+cudaError_t transpose_matrix(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows, int64_t cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+    transpose_kernel<<<grid, 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
+    return LAUNCHED();
+}
+cudaError_t axpby_matrix(double a, const double* x, int64_t ldx, double b, const double* y, int64_t ldy,
+                         double* dst, int64_t ldd, int64_t rows, int64_t cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    axpby_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(a, x, ldx, b, y, ldy, dst, ldd, rows, cols);
+    return LAUNCHED();
+}
+cudaError_t sumsq(const double* X, int64_t ld, int64_t rows, int64_t cols, double* out, double* scratch, int nscratch, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    int blocks = grid_for(rows * cols, 256, nscratch);
+    sumsq_partial_kernel<<<blocks, 256, 0, st>>>(X, ld, rows, cols, scratch);
+    ++g_kernel_launches;
+    sumsq_final_kernel<<<1, 32, 0, st>>>(scratch, blocks, out);
+    return LAUNCHED();
+}
+cudaError_t check_symmetric(const double* A, int64_t lda, int64_t n, int* flag, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    check_symmetric_kernel<<<grid_for(n * n, 256), 256, 0, st>>>(A, lda, n, flag);
+    return LAUNCHED();
+}
+cudaError_t scale_columns(double* X, int64_t ld, int64_t rows, int64_t cols, const double* s, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    scale_columns_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(X, ld, rows, cols, s);
+    return LAUNCHED();
+}
+cudaError_t jacobi_svd(const double* M, int64_t ldm, int p, double* U, int64_t ldu, double* sigma,
+                       double* V, int64_t ldv, double* work, int* info, cudaStream_t st) {
+    jacobi_svd_kernel<<<1, 1024, 0, st>>>(M, ldm, p, U, ldu, sigma, V, ldv, work, info);
+    return LAUNCHED();
+}
+cudaError_t jacobi_eigh(const double* C, int64_t ldc, int p, double* W, int64_t ldw, double* lambda,
+                        int order, double* work, int* info, cudaStream_t st) {
+    if (p > 2 * EIGH_MAX_PAIRS) return cudaErrorInvalidValue;
+    jacobi_eigh_kernel<<<1, 1024, 0, st>>>(C, ldc, p, W, ldw, lambda, order, work, info);
+    return LAUNCHED();
+}
+
+}  // namespace rnla

@@ -1,0 +1,70 @@
+"""Sketch step of the sketch-and-precondition solvers -- mirror of the first lines of
+`blendenpik_overdetermined` (reference src/sketch_and_precondition.rs:26-52), `lsrn_overdetermined`
+(:82-107) and `sketch_saddle_point_precondition` (:150-176): argument validation, the sketch dimension
+rule and A_sk = S A (and b_sk = S b).  The preconditioned CGLS iteration that follows in the reference is a
+"next" row of SURVEY.md §8(f) and is not part of this path."""
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from . import runtime
+from .errors import InvalidParameters, NotOverdetermined
+
+SKETCH_DENSE, SKETCH_SASO = 0, 1
+
+
+def _validate(a, epsilon, l, sampling_factor):
+    m, n = a.shape
+    if m < n:  # :29-33
+        raise NotOverdetermined(f"Need more columns than rows, found {m} rows and {n} columns")
+    if sampling_factor < 1.0:  # :34-38
+        raise InvalidParameters(f"Sampling factor must be greater than 1, current input is {sampling_factor}")
+    if epsilon <= 0.0:  # :39-43
+        raise InvalidParameters(f"Epsilon must be positive, current input is {epsilon}")
+    if l == 0:  # :44-48
+        raise InvalidParameters(f"Number of iterations must be positive, current input is {l}")
+
+
+def sketch_dim(m, n, sampling_factor, saddle=False):
+    """d of reference :49 / :105 (saddle=False) or :172 (saddle=True)."""
+    return int(_lib.load().rnla_sketch_dim(int(m), int(n), float(sampling_factor), 1 if saddle else 0))
+
+
+def sketch_apply(a, b=None, d=None, kind=SKETCH_DENSE, dist=runtime.GAUSSIAN, seed=0, zeta=8):
+    """A_sk = S a (d x n) and b_sk = S b for a dense i.i.d. or sparse-sign S (d x m)."""
+    lib = _lib.load()
+    a = runtime.as_f(a)
+    m, n = a.shape
+    a_sk = np.empty((d, n), dtype=np.float64, order="F")
+    if b is not None:
+        b = runtime.as_f(b)
+        b_sk = np.empty((d, b.shape[1]), dtype=np.float64, order="F")
+        check(lib.rnla_sketch_apply(kind, dist, seed, d, zeta, runtime.ptr(a), m, n, runtime.ptr(b), b.shape[1],
+                                    runtime.ptr(a_sk), runtime.ptr(b_sk)))
+        return a_sk, b_sk
+    check(lib.rnla_sketch_apply(kind, dist, seed, d, zeta, runtime.ptr(a), m, n, None, 0, runtime.ptr(a_sk), None))
+    return a_sk
+
+
+def blendenpik_sketch(a, b, epsilon, l, sampling_factor, kind=SKETCH_DENSE, zeta=8):
+    """Validation + sketch step of `blendenpik_overdetermined` (reference :26-52) -> (a_sk, b_sk)."""
+    a = runtime.as_f(a)
+    _validate(a, epsilon, l, sampling_factor)
+    d = sketch_dim(a.shape[0], a.shape[1], sampling_factor)
+    return sketch_apply(a, b, d, kind=kind, zeta=zeta, seed=runtime.get_options().seed)
+
+
+def lsrn_sketch(a, b, epsilon, l, sampling_factor, kind=SKETCH_DENSE, zeta=8):
+    """Validation + sketch step of `lsrn_overdetermined` (reference :82-107) -> a_sk."""
+    a = runtime.as_f(a)
+    _validate(a, epsilon, l, sampling_factor)
+    d = sketch_dim(a.shape[0], a.shape[1], sampling_factor)
+    return sketch_apply(a, None, d, kind=kind, zeta=zeta, seed=runtime.get_options().seed)
+
+
+def saddle_point_sketch(a, b, c, mu, epsilon, l, sampling_factor, kind=SKETCH_DENSE, zeta=8):
+    """Validation + sketch step of `sketch_saddle_point_precondition` (reference :150-176) -> a_sk."""
+    a = runtime.as_f(a)
+    _validate(a, epsilon, l, sampling_factor)
+    d = sketch_dim(a.shape[0], a.shape[1], sampling_factor, saddle=True)
+    return sketch_apply(a, None, d, kind=kind, zeta=zeta, seed=runtime.get_options().seed)
