@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sketch-and-factor path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one `rand_svd` (k=100, s=10, q=2, Gaussian sketch) of a synthetic low-rank-plus-noise f64 matrix with
+200 000 rows per GPU and 20 000 columns (N=1: BASELINE config 2, 200k x 20k = 32 GB; N>1: the rows are sharded,
+weak scaling).  The metric is the algorithmic A-stream rate: 4 passes x 8*m*n bytes per step / time
+(SURVEY.md §8d), whole job.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_RANK, S_OVER, Q_PASSES = 100, 10, 2
+N_COLS = 20000
+ROWS_PER_GPU = 200000
+R0 = 200
+METRIC = "rand_svd_A_stream_GBps"
+
+
+def planted_sigma():
+    # geometric 1 -> 1e-3 over the first 100, then 1e-5 (gap >= 100 at k = 100)
+    return np.concatenate([np.logspace(0, -3, 100), np.full(R0 - 100, 1e-5)])
+
+
+def algorithmic_bytes(m, n):
+    return 4.0 * 8.0 * m * n          # q + 2 = 4 passes, A read exactly once per pass
+
+
+def algorithmic_flops(m, n, l):
+    return 4.0 * 2.0 * m * n * l
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(n, sample_rows, threads=None, steps=1, warmup=0):
+    """The reference's CPU dataflow (oracle `literal` mode: src/lora_helpers.rs:17-146 + src/lora_drivers.rs:30-69
+    statement for statement) timed on the host cores, on a bounded row sample of the same workload."""
+    from oracle import oracle as orc
+    orc.load()
+    if threads:
+        orc.set_threads(threads)
+    rng = np.random.default_rng(1234)
+    sig = planted_sigma()
+    U0, _ = np.linalg.qr(rng.standard_normal((sample_rows, R0)))
+    V0, _ = np.linalg.qr(rng.standard_normal((n, R0)))
+    A = np.asfortranarray((U0 * sig) @ V0.T)
+    del U0
+    o = orc.make_opts(mode=orc.MODE_LITERAL)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        U, S, Vt = orc.rand_svd(A, K_RANK, 1e-6, S_OVER, o)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    return {"value": algorithmic_bytes(sample_rows, n) / t * 1e-9, "unit": "GB/s", "cores": orc.get_threads(), "kind": "port",
+            "sample": f"oracle literal-mode rand_svd (k={K_RANK}, s={S_OVER}) on {sample_rows} x {n} rows-sample of the workload, "
+                      f"{t:.2f} s per call, all products are real GEMMs as in the reference",
+            "seconds_per_call": t, "tflops": algorithmic_flops(sample_rows, n, K_RANK + S_OVER) / t * 1e-12}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cols
+    sample_rows = args.ref_rows
+    cb = cpu_baseline(n, sample_rows, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_call"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"rand_svd f64 {args.rows * args.gpus}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}",
+                   "timed_on": f"{sample_rows}x{n} row sample (CPU), throughput is per byte of A streamed"},
+        "cpu_baseline": cb, "gpu_launches": 0,
+        "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import randnla_b200 as rb
+    from randnla_b200 import runtime as rt, _lib, lora_drivers as ld
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: randnla_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    rt.init(local_rank)
+    if world > 1:
+        rt.init_comm_from_torch()
+    # a non-default torch stream: the library launches on it, so torch.cuda.Event brackets see its kernels
+    torch.cuda.set_stream(torch.cuda.Stream())
+    rt.use_torch_stream()
+
+    n = args.cols
+    m_local = args.rows
+    m_global = m_local * world
+    row_off = rank * m_local
+    l = K_RANK + S_OVER
+    sig = planted_sigma()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic input, generated on the device shard by shard ----
+    dA = rt.empty_colmajor(m_local, n)
+    pA, lda = rt.dev_ptr_ld(dA)
+    _lib.check(lib.rnla_generate_lowrank_dev(pA, lda, m_local, n, row_off, m_global, R0, sig.ctypes.data_as(C.c_void_p), 1e-7, 1234))
+    opts = rt.make_options(fused_sketch=args.fused)
+
+    # ---- roofs of this box, this run ----
+    fp64 = C.c_double(0); hbm = C.c_double(0)
+    _lib.check(lib.rnla_measure_roofs(C.byref(fp64), C.byref(hbm), 4 << 30))
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_file):
+        try:
+            hbm_peak = float(json.load(open(peaks_file))["hbm_gbs"]); hbm_src = "MEASURED_PEAKS.json (driver copy benchmark)"
+        except Exception:
+            pass
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        U, S, Vt = ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = rt.kernel_launches()
+    phase_acc = {}
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        U, S, Vt = ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
+        for name, ms in rt.timings():             # library-side CUDA events of this step (stream already drained by the call)
+            phase_acc.setdefault(name, []).append(ms)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = rt.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ms_total / args.steps)
+    value = algorithmic_bytes(m_global, n) / (ms_step * 1e-3) * 1e-9
+
+    # ---- accuracy of the timed result (size-independent properties) ----
+    Sg = S.cpu().numpy()
+    gram = rt.empty_colmajor(K_RANK, K_RANK)
+    pU, ldu = rt.dev_ptr_ld(U); pG, ldg = rt.dev_ptr_ld(gram)
+    _lib.check(lib.rnla_gemm_tn_dev(pU, ldu, m_local, K_RANK, pU, ldu, K_RANK, pG, ldg, 1))     # U^T U, all-reduced over the shards
+    rt.synchronize()
+    orth_err = float((gram - torch.eye(K_RANK, dtype=torch.float64, device="cuda")).abs().max().item())
+    sigma_vs_planted = float(np.max(np.abs(Sg - sig[:K_RANK]) / sig[:K_RANK]))
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory -> device -> host) ----
+    e2e = None
+    if args.e2e_steps > 0:
+        host_bytes = 8 * m_local * n
+        import psutil
+        avail = psutil.virtual_memory().available
+        full = host_bytes * world < 0.7 * avail if world > 1 else host_bytes < 0.7 * avail
+        if full:
+            hA = torch.empty((n, m_local), dtype=torch.float64, pin_memory=True)      # column-major m_local x n
+            hA.copy_(dA.t())
+            hAn = hA.numpy().T
+            kk = K_RANK
+            hU = np.empty((m_local, kk), order="F"); hS = np.empty((kk, kk), order="F"); hVt = np.empty((kk, n), order="F")
+            r = C.c_int64(0)
+
+            def e2e_step():
+                _lib.check(lib.rnla_rand_svd(C.c_void_p(hA.data_ptr()), m_local, n, kk, 1e-6, S_OVER, rt.ptr(hU), rt.ptr(hS), rt.ptr(hVt), C.byref(r)))
+            staging = "full shard in pinned host memory"
+            d2h = (m_local * kk + kk + kk * n) * 8
+        else:
+            win_rows = 25000
+            hW = torch.empty((n, win_rows), dtype=torch.float64, pin_memory=True)
+            hW.copy_(dA[:win_rows].t())
+            dB = rt.empty_colmajor(m_local, n)
+
+            def e2e_step():
+                for r0 in range(0, m_local, win_rows):
+                    rr = min(win_rows, m_local - r0)
+                    dB[r0:r0 + rr].t().copy_(hW[:, :rr], non_blocking=True)
+                Ue, Se, Vte = ld.rand_svd_dev(dB, K_RANK, S_OVER, opts)
+                Ue.cpu(); Se.cpu(); Vte.cpu()
+            staging = f"pinned {win_rows}-row window reused cyclically (host RAM cannot hold {world} x {host_bytes >> 30} GiB)"
+            d2h = (m_local * K_RANK + K_RANK + K_RANK * n) * 8
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        e2e = {"value": algorithmic_bytes(m_global, n) / dt * 1e-9, "unit": "GB/s", "h2d_bytes_per_step": int(host_bytes),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "staging": staging,
+               "api": "rnla_rand_svd (host buffers, include/rnla.h)" if full else "runtime copy + lora_drivers.rand_svd_dev"}
+        if full:
+            del hA
+        else:
+            del dB
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    # ---- roofline of the dominant kernels (per launch, CUDA events on the launching stream, timed region) ----
+    phases = {k: float(np.mean(v)) for k, v in phase_acc.items()}
+    nn_ms = [v for k, v in phases.items() if k.startswith("pass:A*")]
+    tn_ms = [v for k, v in phases.items() if k.startswith("pass:At*")]
+    gemm_ms = nn_ms + tn_ms
+    per_launch_ms = float(np.mean(gemm_ms))
+    fl = 2.0 * m_local * n * l
+    by = 8.0 * m_local * n
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_nn_kernel / gemm_tn_kernel (FP64 DMMA.8x8x4, 2 launches each per step)",
+        "achieved": fl / (per_launch_ms * 1e-3) * 1e-12, "peak": fp64.value, "unit": "TFLOP/s",
+        "frac": fl / (per_launch_ms * 1e-3) * 1e-12 / fp64.value,
+        "peak_source": "FP64 DMMA peak measured live by rnla_measure_roofs on this GPU (MEASURED_PEAKS.json holds no FP64 number)",
+        "traffic": None,
+        "hbm": {"achieved": by / (per_launch_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": by / (per_launch_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src, "read_only_stream_measured_gbs": hbm.value},
+        "note": "l = k+p = 110 makes every pass FP64-pipe bound (27.5 flop/B vs a 5.7 flop/B ridge), SURVEY.md §0 fact 3",
+        "per_kernel_ms": {"gemm_nn": float(np.mean(nn_ms)) if nn_ms else None, "gemm_tn": float(np.mean(tn_ms)) if tn_ms else None},
+        "share_of_step": float(sum(gemm_ms) / sum(phases.values())),
+    }
+    ncu_traffic = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(ncu_traffic):
+        try:
+            roofline["traffic"] = json.load(open(ncu_traffic)).get("gemm_bytes_per_launch")
+        except Exception:
+            pass
+
+    cb = None
+    if world == 1 and args.cpu_rows > 0:
+        cb = cpu_baseline(n, args.cpu_rows)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"rand_svd f64 {m_global}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}, Gaussian sketch",
+                   "rows_per_gpu": m_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                   "sketch": "auto (materialised while Omega is L2-resident)" if args.fused == 2 else ("fused in-kernel Philox" if args.fused == 1 else "materialised"),
+                   "l2": f"inputs larger than L2 (A shard = {8 * m_local * n / 2**30:.1f} GiB per GPU, streamed 4x per step)"},
+        "rand_svd_ms": ms_step, "tflops_fp64": algorithmic_flops(m_global, n, l) / (ms_step * 1e-3) * 1e-12,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cb, "phases_ms": phases,
+        "accuracy": {"max_abs_UtU_minus_I": orth_err, "max_rel_sigma_vs_planted(noise-limited)": sigma_vs_planted},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (debug)")
+    ap.add_argument("--cols", type=int, default=N_COLS)
+    ap.add_argument("--fused", type=int, default=2, help="0 materialise Omega, 1 in-kernel Philox, 2 auto")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-rows", type=int, default=25000, help="row sample of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--ref-rows", type=int, default=25000, help="row sample per step of --impl reference")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

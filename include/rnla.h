@@ -69,7 +69,8 @@ typedef struct rnla_options {
     uint64_t seed;            /* reference hard-codes 0 (sketch.rs:112) */
     int32_t num_passes;       /* <=0: reference constants (2 for rand_svd/rand_evd1 lora_helpers.rs:40, 3 for rand_evd2 lora_drivers.rs:186) */
     int32_t passes_per_stab;  /* <=0: 1 (same lines) */
-    int32_t fused_sketch;     /* 1 (default): Omega is generated inside the A*Omega kernel and never materialised; 0: materialise then multiply */
+    int32_t fused_sketch;     /* 1: Omega is generated inside the A*Omega kernel and never materialised; 0: materialise (K0) then multiply;
+                               * 2 (default): fuse iff the n x l operand would not stay L2-resident (> 48 MiB) */
     int32_t reserved;
 } rnla_options;
 
@@ -188,6 +189,10 @@ rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double
 /* synthetic inputs, generated on the device shard by shard: A = U0 diag(sigma) V0^T + eta G */
 rnla_status rnla_generate_lowrank_dev(double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t row_offset,
                                       int64_t m_global, int64_t r0, const double* sigma_host, double eta, uint64_t seed);
+
+/* live roof measurement for bench.py (same box, same run): peak DMMA.8x8x4 rate of all SMs in TFLOP/s (register-resident
+ * chains, no memory) and a read-only HBM stream over `hbm_bytes` (>= 1 GiB recommended) in GB/s.  Either pointer may be NULL. */
+rnla_status rnla_measure_roofs(double* fp64_dmma_tflops, double* hbm_read_gbs, size_t hbm_bytes);
 
 /* raw device memory helpers for hosts without a CUDA runtime binding (Rust shim, ctypes) */
 rnla_status rnla_malloc(void** dptr, size_t bytes);

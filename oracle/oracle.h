@@ -1,0 +1,77 @@
+/* oracle.h -- CPU restatement of the reference's sketch-and-factor path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build,
+ * load or call this; nothing under randnla_b200/ does.  See oracle/README.md for what is pinned how.
+ *
+ * All matrices column-major f64 with lda = nrows (nalgebra DMatrix layout).
+ */
+#ifndef RNLA_ORACLE_H
+#define RNLA_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- L0 RNG: rust-random123/src/philox.rs:149-154,173-176,211-223; threefry.rs:30-93; rand_core seed_from_u64 */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void orc_threefry2x64_20(const uint64_t ctr[2], const uint64_t key[2], uint64_t out[2]);
+void orc_seed_from_u64(uint64_t state, uint64_t key[2]);
+/* t-th u64 of ThreeFry2x64Rng::seed_from_u64(seed) (BlockRng64 order: x[0], x[1] of block 0, then block 1 ...) */
+uint64_t orc_threefry_rng_u64(uint64_t seed, uint64_t t);
+
+/* ---- L1 sketch operators ----------------------------------------------------------------------- */
+/* this build's counter map (restated independently of randnla_b200/csrc/rng.cuh):
+ * out(r,c) = T_dist(philox4x32_10((q_lo,q_hi,c,stream),(seed_lo,seed_hi))[R&3]), R = row_off + r, q = R>>2 */
+void orc_omega_fill(int dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols, int64_t row_off,
+                    double* out, int64_t ld);
+float orc_gauss_from_u32(uint32_t k);
+/* what the reference's sketching_operator returns for Uniform (dist 1) / Rademacher (dist 2):
+ * src/sketch.rs:112-127 with rand 0.8.5 Uniform<f64> / Bernoulli over the seed-0 ThreeFry stream.  Returns -1 for Gaussian
+ * (needs rand_distr's ziggurat tables, not in the tree). */
+int orc_sketching_operator_ref(int dist, uint64_t seed, int64_t rows, int64_t cols, double* out);
+
+/* ---- L2 dense kernels with nalgebra 0.33 conventions ------------------------------------------- */
+void orc_gemm_nn(const double* A, int64_t lda, int64_t m, int64_t K, const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc);
+void orc_gemm_tn(const double* A, int64_t lda, int64_t m, int64_t n, const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz);
+/* X.qr(): thin Q (rows x p), R (p x cols), p = min(rows, cols), R diag >= 0.  R may be NULL. */
+void orc_qr(const double* X, int64_t rows, int64_t cols, double* Q, double* R);
+/* X.full_piv_lu().l(): rows x min(rows, cols) */
+void orc_stabilizer(const double* X, int64_t rows, int64_t cols, double* L);
+/* lower Cholesky; returns 0 on success, -1 if not positive definite */
+int orc_cholesky_lower(const double* A, int64_t n, double* L);
+/* thin SVD of M (rows x cols, any shape): U rows x p, sigma p (descending), Vt p x cols */
+int orc_svd(const double* M, int64_t rows, int64_t cols, double* U, double* sigma, double* Vt);
+/* symmetric eigen-decomposition (values ascending) */
+int orc_symmetric_eigen(const double* A, int64_t n, double* W, double* lambda);
+
+/* ---- L3/L4: the path.  mode 0 = intended (monograph TSOG1, QR stabiliser), 1 = literal (as written).
+ * omega_n: optional n x l operator used where tsog1 draws sketching_operator(Gaussian, n, l) (lora_helpers.rs:71);
+ * omega_m: optional m x l operator for the odd branch (:74).  NULL -> generated with orc_omega_fill(dist, seed, stream 1 / 2). */
+typedef struct orc_opts {
+    int mode; int dist; uint64_t seed; int num_passes; int passes_per_stab;
+    const double* omega_n; const double* omega_m;
+} orc_opts;
+void orc_tsog1(const double* A, int64_t m, int64_t n, int64_t k, int num_passes, int passes_per_stab, const orc_opts* o, double* S);
+void orc_rf1(const double* A, int64_t m, int64_t n, int64_t k, const orc_opts* o, double* Q);
+void orc_qb1(const double* A, int64_t m, int64_t n, int64_t k, const orc_opts* o, double* Q, double* B);
+/* returns 0 or the RandNLAError status code (same numbering as include/rnla.h); *r = min(k, min(k+s, m, n)) */
+int orc_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, double epsilon, int64_t s, const orc_opts* o,
+                 double* U, double* S, double* Vt, int64_t* r);
+int orc_rand_evd1(const double* A, int64_t n, int64_t k, double epsilon, int64_t s, const orc_opts* o, double* V, double* lambda, int64_t* r);
+int orc_rand_evd2(const double* A, int64_t n, int64_t k, int64_t s, const orc_opts* o, double* V, double* lambda, int64_t* r);
+
+/* ---- sketch step of sketch_and_precondition (src/sketch_and_precondition.rs:49-52,105-107,172-176) */
+int64_t orc_sketch_dim(int64_t m, int64_t n, double sampling_factor, int rule);
+/* dense: A_sk = S A with S(i,j) = omega(row j, col i) (stream 3), the definition the GPU path uses */
+void orc_sketch_apply_dense(int dist, uint64_t seed, int64_t d, const double* A, int64_t m, int64_t n, double* A_sk);
+/* sparse sign: zeta non-zeros per column of S */
+void orc_sketch_apply_saso(uint64_t seed, int64_t d, int zeta, const double* A, int64_t m, int64_t n, double* A_sk);
+
+void orc_set_threads(int nthreads);
+int orc_get_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,259 @@
+"""ctypes wrapper of oracle/liboracle.so -- the CPU restatement of the reference path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing under randnla_b200/ imports this module."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+i32, i64, u32, u64, f64, P = C.c_int, C.c_int64, C.c_uint32, C.c_uint64, C.c_double, C.c_void_p
+
+
+class Opts(C.Structure):
+    _fields_ = [("mode", C.c_int), ("dist", C.c_int), ("seed", u64), ("num_passes", C.c_int),
+                ("passes_per_stab", C.c_int), ("omega_n", P), ("omega_m", P)]
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    lib.orc_threefry_rng_u64.restype = u64
+    lib.orc_threefry_rng_u64.argtypes = [u64, u64]
+    lib.orc_gauss_from_u32.restype = C.c_float
+    lib.orc_gauss_from_u32.argtypes = [u32]
+    lib.orc_sketch_dim.restype = i64
+    lib.orc_sketch_dim.argtypes = [i64, i64, f64, C.c_int]
+    lib.orc_get_threads.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def F(a):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    return np.asfortranarray(a)
+
+
+def p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+MODE_INTENDED, MODE_LITERAL = 0, 1
+
+
+def make_opts(mode=MODE_INTENDED, dist=0, seed=0, num_passes=0, passes_per_stab=0, omega_n=None, omega_m=None):
+    o = Opts(mode, dist, seed, num_passes, passes_per_stab, None, None)
+    keep = []
+    if omega_n is not None:
+        on = F(omega_n); keep.append(on); o.omega_n = on.ctypes.data
+    if omega_m is not None:
+        om = F(omega_m); keep.append(om); o.omega_m = om.ctypes.data
+    o._keep = keep
+    return o
+
+
+def philox4x32_10(ctr, key):
+    lib = load()
+    ctr = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 4)
+    key = np.ascontiguousarray(key, dtype=np.uint32).reshape(-1, 2)
+    out = np.empty_like(ctr)
+    for i in range(ctr.shape[0]):
+        k = key[i if key.shape[0] > 1 else 0]
+        lib.orc_philox4x32_10(p(ctr[i]), p(np.ascontiguousarray(k)), C.c_void_p(out[i].ctypes.data))
+    return out
+
+
+def threefry2x64_20(ctr, key):
+    lib = load()
+    ctr = np.ascontiguousarray(ctr, dtype=np.uint64).reshape(-1, 2)
+    key = np.ascontiguousarray(key, dtype=np.uint64).reshape(-1, 2)
+    out = np.empty_like(ctr)
+    for i in range(ctr.shape[0]):
+        k = key[i if key.shape[0] > 1 else 0]
+        lib.orc_threefry2x64_20(p(ctr[i]), p(np.ascontiguousarray(k)), C.c_void_p(out[i].ctypes.data))
+    return out
+
+
+def seed_from_u64(state):
+    key = np.zeros(2, dtype=np.uint64)
+    load().orc_seed_from_u64(u64(state), p(key))
+    return key
+
+
+def threefry_rng_u64(seed, t):
+    return int(load().orc_threefry_rng_u64(seed, t))
+
+
+def omega_fill(dist, rows, cols, seed=0, stream=0, row_off=0):
+    out = np.empty((rows, cols), dtype=np.float64, order="F")
+    load().orc_omega_fill(C.c_int(dist), u64(seed), u32(stream), i64(rows), i64(cols), i64(row_off), p(out), i64(max(rows, 1)))
+    return out
+
+
+def gauss_from_u32(k):
+    return float(load().orc_gauss_from_u32(u32(k)))
+
+
+def sketching_operator_ref(dist, rows, cols, seed=0):
+    out = np.empty((rows, cols), dtype=np.float64, order="F")
+    rc = load().orc_sketching_operator_ref(C.c_int(dist), u64(seed), i64(rows), i64(cols), p(out))
+    if rc != 0:
+        raise NotImplementedError("the reference's Gaussian stream needs rand_distr's ziggurat tables (not in the tree)")
+    return out
+
+
+def gemm_nn(A, B):
+    A, B = F(A), F(B)
+    m, K = A.shape; N = B.shape[1]
+    Cm = np.empty((m, N), dtype=np.float64, order="F")
+    load().orc_gemm_nn(p(A), i64(m), i64(m), i64(K), p(B), i64(K), i64(N), p(Cm), i64(m))
+    return Cm
+
+
+def gemm_tn(A, Q):
+    A, Q = F(A), F(Q)
+    m, n = A.shape; N = Q.shape[1]
+    Z = np.empty((n, N), dtype=np.float64, order="F")
+    load().orc_gemm_tn(p(A), i64(m), i64(m), i64(n), p(Q), i64(m), i64(N), p(Z), i64(n))
+    return Z
+
+
+def qr(X):
+    X = F(X); rows, cols = X.shape; pp = min(rows, cols)
+    Q = np.empty((rows, pp), dtype=np.float64, order="F"); R = np.empty((pp, cols), dtype=np.float64, order="F")
+    load().orc_qr(p(X), i64(rows), i64(cols), p(Q), p(R))
+    return Q, R
+
+
+def Orth(X):
+    return qr(X)[0]
+
+
+def Stabilizer(X):
+    X = F(X); rows, cols = X.shape
+    L = np.empty((rows, min(rows, cols)), dtype=np.float64, order="F")
+    load().orc_stabilizer(p(X), i64(rows), i64(cols), p(L))
+    return L
+
+
+def svd(M):
+    M = F(M); rows, cols = M.shape; pp = min(rows, cols)
+    U = np.empty((rows, pp), order="F"); s = np.empty(pp); Vt = np.empty((pp, cols), order="F")
+    rc = load().orc_svd(p(M), i64(rows), i64(cols), p(U), p(s), p(Vt))
+    assert rc == 0
+    return U, s, Vt
+
+
+def symmetric_eigen(A):
+    A = F(A); n = A.shape[0]
+    W = np.empty((n, n), order="F"); lam = np.empty(n)
+    rc = load().orc_symmetric_eigen(p(A), i64(n), p(W), p(lam))
+    assert rc == 0
+    return lam, W
+
+
+def tsog1(A, k, num_passes, passes_per_stab, opts=None):
+    A = F(A); m, n = A.shape
+    o = opts or make_opts()
+    S = np.empty((n, k), dtype=np.float64, order="F")
+    load().orc_tsog1(p(A), i64(m), i64(n), i64(k), C.c_int(num_passes), C.c_int(passes_per_stab), C.byref(o), p(S))
+    return S
+
+
+def RF1(A, k, opts=None):
+    A = F(A); m, n = A.shape
+    o = opts or make_opts()
+    Q = np.empty((m, k), dtype=np.float64, order="F")
+    load().orc_rf1(p(A), i64(m), i64(n), i64(k), C.byref(o), p(Q))
+    return Q
+
+
+def QB1(A, k, epsilon=0.0, opts=None):
+    A = F(A); m, n = A.shape
+    o = opts or make_opts()
+    Q = np.empty((m, k), dtype=np.float64, order="F"); B = np.empty((k, n), dtype=np.float64, order="F")
+    load().orc_qb1(p(A), i64(m), i64(n), i64(k), C.byref(o), p(Q), p(B))
+    return Q, B
+
+
+class OracleError(Exception):
+    def __init__(self, code):
+        self.code = code
+        super().__init__(f"oracle status {code}")
+
+
+def rand_svd(A, k, epsilon, s, opts=None):
+    A = F(A); m, n = A.shape
+    o = opts or make_opts()
+    cap = max(min(max(k, 1), m, n), 1)
+    U = np.empty((m, cap), order="F"); S = np.empty((cap, cap), order="F"); Vt = np.empty((cap, n), order="F")
+    r = i64(0)
+    rc = load().orc_rand_svd(p(A), i64(m), i64(n), i64(k), f64(epsilon), i64(s), C.byref(o), p(U), p(S), p(Vt), C.byref(r))
+    if rc:
+        raise OracleError(rc)
+    return U, S, Vt
+
+
+def rand_evd1(A, k, epsilon, s, opts=None):
+    A = F(A); n = A.shape[0]
+    o = opts or make_opts()
+    cap = max(min(max(k, 1), n), 1)
+    V = np.empty((n, cap), order="F"); lam = np.empty(cap)
+    r = i64(0)
+    rc = load().orc_rand_evd1(p(A), i64(n), i64(k), f64(epsilon), i64(s), C.byref(o), p(V), p(lam), C.byref(r))
+    if rc:
+        raise OracleError(rc)
+    return V[:, :r.value], lam[:r.value]
+
+
+def rand_evd2(A, k, s, opts=None):
+    A = F(A); n = A.shape[0]
+    o = opts or make_opts()
+    cap = max(min(max(k, 1), n), 1)
+    V = np.empty((n, cap), order="F"); lam = np.empty(cap)
+    r = i64(0)
+    rc = load().orc_rand_evd2(p(A), i64(n), i64(k), i64(s), C.byref(o), p(V), p(lam), C.byref(r))
+    if rc:
+        raise OracleError(rc)
+    return V[:, :r.value], lam[:r.value]
+
+
+def sketch_dim(m, n, sf, saddle=False):
+    return int(load().orc_sketch_dim(m, n, sf, 1 if saddle else 0))
+
+
+def sketch_apply_dense(A, d, dist=0, seed=0):
+    A = F(A); m, n = A.shape
+    out = np.empty((d, n), order="F")
+    load().orc_sketch_apply_dense(C.c_int(dist), u64(seed), i64(d), p(A), i64(m), i64(n), p(out))
+    return out
+
+
+def sketch_apply_saso(A, d, zeta=8, seed=0):
+    A = F(A); m, n = A.shape
+    out = np.empty((d, n), order="F")
+    load().orc_sketch_apply_saso(u64(seed), i64(d), C.c_int(zeta), p(A), i64(m), i64(n), p(out))
+    return out
+
+
+def set_threads(n):
+    load().orc_set_threads(C.c_int(n))
+
+
+def get_threads():
+    return int(load().orc_get_threads())

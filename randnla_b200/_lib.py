@@ -65,6 +65,7 @@ SIGNATURES = {
     "rnla_small_svd_dev": (c_i32, [P, c_i64, c_i64, P, P, P]),
     "rnla_small_eigh_dev": (c_i32, [P, c_i64, c_i64, P, P]),
     "rnla_generate_lowrank_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, P, c_f64, c_u64]),
+    "rnla_measure_roofs": (c_i32, [C.POINTER(c_f64), C.POINTER(c_f64), C.c_size_t]),
     "rnla_malloc": (c_i32, [C.POINTER(P), C.c_size_t]),
     "rnla_free": (c_i32, [P]),
     "rnla_memcpy_h2d": (c_i32, [P, P, C.c_size_t]),

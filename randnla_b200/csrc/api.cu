@@ -19,7 +19,6 @@ rnla_status dev_generate_lowrank(double* dA, int64_t lda, int64_t m_local, int64
 }
 
 static std::string fmt(const char* f, long long v) { char b[256]; snprintf(b, sizeof b, f, v); return b; }
-static std::string fmtd(const char* f, double v) { char b[256]; snprintf(b, sizeof b, f, v); return b; }
 // Rust's `{}` for f64 prints the shortest representation that round-trips; %g is close enough for messages
 static std::string rust_f64(double v) {
     char b[64];

@@ -30,7 +30,7 @@ static void default_opts(rnla_options* o) {
     o->seed = 0;
     o->num_passes = 0;
     o->passes_per_stab = 0;
-    o->fused_sketch = 1;
+    o->fused_sketch = 2;
     const char* m = getenv("RNLA_MODE");
     if (m && (!strcmp(m, "literal") || !strcmp(m, "LITERAL") || !strcmp(m, "1"))) o->mode = RNLA_MODE_LITERAL;
 }

@@ -176,6 +176,15 @@ rnla_status orth_inplace(double* X, int64_t ldx, const ShardInfo& sh, int p, boo
 }
 
 // ---------------------------------------------------------------- tsog1 / RF1 / QB1 (intended mode)
+// Omega (n x l) is re-read by every 128-row block of A.  While it is L2-resident (17.6 MB at the headline size) the
+// materialised operand is a little cheaper than regenerating it per block (measured: 25.7 ms vs 30.2 ms per pass,
+// profiles/r01_*); once it no longer fits the 126 MB L2 it would stream from HBM once per row block, and the fused
+// in-kernel generator is the only sane choice.  fused_sketch = 2 picks by that criterion.
+static inline bool use_fused(const rnla_options& o, int64_t n, int l) {
+    if (o.fused_sketch == 0) return false;
+    if (o.fused_sketch == 1) return true;
+    return (double)n * l * 8.0 > 48.0 * 1024 * 1024;
+}
 static inline int eff_passes(const rnla_options& o, int dflt) { return o.num_passes > 0 ? o.num_passes : dflt; }
 static inline int eff_pps(const rnla_options& o) { return o.passes_per_stab > 0 ? o.passes_per_stab : 1; }
 
@@ -201,8 +210,8 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
     }
     while (q - done >= 2) {
         {
-            PhaseScope ph(virt ? "pass:A*Omega(fused)" : "pass:A*S");
-            if (virt && o.fused_sketch) {
+            PhaseScope ph(virt ? (use_fused(o, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)") : "pass:A*S");
+            if (virt && use_fused(o, n, l)) {
                 RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
             } else {
                 if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n, c.stream));
@@ -252,8 +261,8 @@ rnla_status dev_rf1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
         DevBuf Ytmp; double* ytmp = Q;
         if (ldq != std::max<int64_t>(m, 1)) { RNLA_CUDA(Ytmp.alloc((size_t)std::max<int64_t>(m, 1) * l * 8)); ytmp = Ytmp.d(); }
         RNLA_TRY(tsog1_intended(A, lda, sh, n, l, q, pps, o, S.d(), ytmp, true, &virt));
-        PhaseScope ph(virt ? "pass:A*Omega(fused)" : "pass:A*S");
-        if (virt && o.fused_sketch) {
+        PhaseScope ph(virt ? (use_fused(o, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)") : "pass:A*S");
+        if (virt && use_fused(o, n, l)) {
             RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Q, ldq));
         } else {
             if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S.d(), n, c.stream));

@@ -25,18 +25,22 @@ constexpr int NCONS = 8;
 constexpr int NPROD = 4;
 constexpr int NPROD_THREADS = NPROD * 32;
 constexpr int NTHREADS = (NCONS + NPROD) * 32;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 226 * 1024;
 // 384 threads x 168 regs at launch; producers give registers back, consumers take them:
-// 128 x 72 + 256 x 216 = 64512 = 384 x 168
-constexpr int PROD_REGS = 72;
-constexpr int CONS_REGS = 216;
+// 128 x 96 + 256 x 200 = 63488 <= 64512 = 384 x 168
+constexpr int PROD_REGS = 96;
+constexpr int CONS_REGS = 200;
+// TN producers only issue copies: 128 x 40 + 256 x 224 = 62464
+constexpr int TN_PROD_REGS = 40;
+constexpr int TN_CONS_REGS = 224;
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
 // ------------------------------------------------------------------------------------------
 //  NN
 // ------------------------------------------------------------------------------------------
-constexpr int NN_BK = 16;
+constexpr int NN_BK = 32;
+constexpr int GEN_ILP = 2;
 constexpr int NN_BMP = BM + 4;      // A tile  [k][BMP]   (row index contiguous, as in global memory)
 constexpr int NN_BKP = NN_BK + 4;   // B tile  [j][BKP]   (k contiguous, as in global memory)
 
@@ -50,7 +54,7 @@ struct NNCfg {
     static constexpr int SMEM = STAGES * STAGE * 8 + 2 * STAGES * 8;
 };
 
-template <int NT>
+template <int NT, int GEN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_nn_kernel(const GemmNN p, const int a_bulk, const int b_bulk) {
     using Cfg = NNCfg<NT>;
@@ -91,12 +95,11 @@ gemm_nn_kernel(const GemmNN p, const int a_bulk, const int b_bulk) {
             // ---- A tile ----
             if (a_bulk && fullk) {
                 if (warp == 0) {
+                    static_assert(BK == 32, "one A column per lane of warp 0");
                     const uint32_t bytes = (uint32_t)(rows_valid & ~1) * 8u;
-                    if (lane < BK) {
-                        const double* src = Ablk + (k0 + lane) * p.lda;
-                        if (bytes) bulk_g2s(As + lane * BMP, src, bytes, &full[s]);
-                        if (rows_valid & 1) As[lane * BMP + rows_valid - 1] = src[rows_valid - 1];
-                    }
+                    const double* src = Ablk + (k0 + lane) * p.lda;
+                    if (bytes) bulk_g2s(As + lane * BMP, src, bytes, &full[s]);
+                    if (rows_valid & 1) As[lane * BMP + rows_valid - 1] = src[rows_valid - 1];
                     tx += bytes * BK;
                 }
             } else {
@@ -108,25 +111,51 @@ gemm_nn_kernel(const GemmNN p, const int a_bulk, const int b_bulk) {
                 }
             }
             // ---- B tile ----
-            if (p.gen) {
+            if (GEN) {
+                // (BK/4) * BN Philox blocks per stage = exactly NT per producer thread; groups of GEN_ILP
+                // independent blocks are evaluated together so the 10 dependent rounds of one block overlap
+                // with those of the others (a single warp per scheduler has no other latency hiding)
                 const uint64_t q0 = (p.k_off + (uint64_t)k0) >> 2;
-                for (int idx = tid; idx < (BK / 4) * BN; idx += NPROD_THREADS) {
-                    const int j = idx >> 2, qd = idx & 3;
-                    if (j < cols_valid) {
-                        const u32x4 b = omega_block(p.seed, p.stream, q0 + qd, (uint32_t)(j0 + j));
-                        double2 lo, hi;
-                        lo.x = sample_from_u32(p.dist, b.x); lo.y = sample_from_u32(p.dist, b.y);
-                        hi.x = sample_from_u32(p.dist, b.z); hi.y = sample_from_u32(p.dist, b.w);
-                        double2* dst = reinterpret_cast<double2*>(Bs + j * BKP + 4 * qd);
-                        dst[0] = lo; dst[1] = hi;
+                constexpr int QPS = BK / 4;                      // row-quads per stage
+                constexpr int PER_THREAD = QPS * BN / NPROD_THREADS;
+                static_assert(QPS * BN % NPROD_THREADS == 0 && PER_THREAD == NT, "generation tiling");
+#pragma unroll
+                for (int base = 0; base < PER_THREAD; base += GEN_ILP) {
+                    u32x4 blk[GEN_ILP];
+#pragma unroll
+                    for (int u = 0; u < GEN_ILP; ++u) {
+                        if (base + u < PER_THREAD) {
+                            const int idx = tid + (base + u) * NPROD_THREADS;
+                            blk[u] = omega_block(p.seed, p.stream, q0 + (idx % QPS), (uint32_t)(j0 + idx / QPS));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < GEN_ILP; ++u) {
+                        if (base + u < PER_THREAD) {
+                            const int idx = tid + (base + u) * NPROD_THREADS;
+                            const int j = idx / QPS, qd = idx % QPS;
+                            double2 lo, hi;
+                            if (GEN == 1) {
+                                float z[4];
+                                gauss_block4(blk[u], z);       // all lanes take part (warp vote inside)
+                                lo.x = bits_d(f32_bits_to_f64_bits(f_bits(z[0]))); lo.y = bits_d(f32_bits_to_f64_bits(f_bits(z[1])));
+                                hi.x = bits_d(f32_bits_to_f64_bits(f_bits(z[2]))); hi.y = bits_d(f32_bits_to_f64_bits(f_bits(z[3])));
+                            } else {
+                                lo.x = sample_from_u32(GEN - 1, blk[u].x); lo.y = sample_from_u32(GEN - 1, blk[u].y);
+                                hi.x = sample_from_u32(GEN - 1, blk[u].z); hi.y = sample_from_u32(GEN - 1, blk[u].w);
+                            }
+                            if (j < cols_valid) {
+                                double2* dst = reinterpret_cast<double2*>(Bs + j * BKP + 4 * qd);
+                                dst[0] = lo; dst[1] = hi;
+                            }
+                        }
                     }
                 }
             } else if (b_bulk && fullk) {
-                if (warp == 0) {
-                    for (int j = lane; j < cols_valid; j += 32)
-                        bulk_g2s(Bs + j * BKP, p.B + k0 + (j0 + j) * p.ldb, BK * 8, &full[s]);
-                    tx += (uint32_t)cols_valid * BK * 8u;
-                }
+                static_assert(BN <= NPROD_THREADS, "one B column per producer thread");
+                if (tid < cols_valid) bulk_g2s(Bs + tid * BKP, p.B + k0 + (j0 + tid) * p.ldb, BK * 8, &full[s]);
+                const int wcnt = max(0, min(32, cols_valid - warp * 32));
+                tx += (uint32_t)wcnt * BK * 8u;
             } else {
                 for (int idx = tid; idx < BK * BN; idx += NPROD_THREADS) {
                     const int j = idx / BK, kk = idx - j * BK;
@@ -137,7 +166,7 @@ gemm_nn_kernel(const GemmNN p, const int a_bulk, const int b_bulk) {
             }
             __syncwarp();
             if (lane == 0) {
-                if (warp == 0) mbar_arrive_expect_tx(&full[s], tx);
+                if (tx) mbar_arrive_expect_tx(&full[s], tx);
                 else mbar_arrive(&full[s]);
             }
         }
@@ -234,7 +263,7 @@ gemm_tn_kernel(const GemmTN p, double* __restrict__ P, const int64_t ldp, const 
     __syncthreads();
 
     if (warp < NPROD) {
-        reg_dec<PROD_REGS>();
+        reg_dec<TN_PROD_REGS>();
         const int tid = threadIdx.x;
         for (int kt = 0; kt < KT; ++kt) {
             const int s = kt % STAGES;
@@ -285,7 +314,7 @@ gemm_tn_kernel(const GemmTN p, double* __restrict__ P, const int64_t ldp, const 
             }
         }
     } else {
-        reg_inc<CONS_REGS>();
+        reg_inc<TN_CONS_REGS>();
         const int cw = warp - NPROD;
         const int wm = cw & 3, wn = cw >> 2;
         const int g = lane >> 2, t = lane & 3;
@@ -361,21 +390,30 @@ tn_reduce_kernel(const double* __restrict__ P, int64_t ldp, int64_t pstride, int
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int NT>
-cudaError_t launch_nn(const GemmNN& p, int nblkN, cudaStream_t st) {
+template <int NT, int GEN>
+cudaError_t launch_nn_g(const GemmNN& p, int nblkN, cudaStream_t st) {
     using Cfg = NNCfg<NT>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_nn_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_nn_kernel<NT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const int a_bulk = aligned16(p.A) && (p.lda % 2 == 0);
     const int b_bulk = !p.gen && aligned16(p.B) && (p.ldb % 2 == 0);
     dim3 grid((unsigned)((p.m + BM - 1) / BM), (unsigned)nblkN);
-    gemm_nn_kernel<NT><<<grid, NTHREADS, Cfg::SMEM, st>>>(p, a_bulk, b_bulk);
+    gemm_nn_kernel<NT, GEN><<<grid, NTHREADS, Cfg::SMEM, st>>>(p, a_bulk, b_bulk);
     ++g_kernel_launches;
     return cudaGetLastError();
+}
+template <int NT>
+cudaError_t launch_nn(const GemmNN& p, int nblkN, cudaStream_t st) {
+    if (!p.gen) return launch_nn_g<NT, 0>(p, nblkN, st);
+    switch (p.dist) {
+        case DIST_GAUSSIAN: return launch_nn_g<NT, 1>(p, nblkN, st);
+        case DIST_UNIFORM: return launch_nn_g<NT, 2>(p, nblkN, st);
+        default: return launch_nn_g<NT, 3>(p, nblkN, st);
+    }
 }
 
 constexpr int TN_BK = 32;

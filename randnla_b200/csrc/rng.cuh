@@ -98,7 +98,9 @@ RNLA_HD float log_pos(float t) {
     const uint32_t b = f_bits(t);
     int e = (int)(b >> 23) - 127;
     float m = bits_f((b & 0x007fffffu) | 0x3f800000u);          // [1,2)
-    if (m > 1.41421354f) { m = f_mul(m, 0.5f); e += 1; }        // [sqrt(.5), sqrt(2))
+    const bool big = m > 1.41421354f;                            // branch-free: fold into [sqrt(.5), sqrt(2))
+    m = big ? f_mul(m, 0.5f) : m;
+    e += big ? 1 : 0;
     const float f = f_sub(m, 1.0f);
     float p = -0x1.4237fep-4f;
     p = f_fma(p, f, 0x1.0696e4p-3f);
@@ -149,12 +151,98 @@ RNLA_HD float gauss_from_u32(uint32_t k) {
     return (k >> 31) ? -z : z;
 }
 
-// Uniform(-1,1): (2k+1) 2^-32 - 1, exact in f64.  Rademacher: +1 iff top bit clear
-// (mirrors `Bernoulli(0.5)`: true iff u < 2^63, src/sketch.rs:124-125).
+#if defined(__CUDACC__)
+// Four samples of one Philox block at once, for the in-kernel generator: the common path of all four is straight-line
+// code (so the independent polynomial chains interleave), and the rare |z| > ~3.1 tail polynomial runs under ONE
+// warp-uniform vote instead of a divergent per-sample branch.  Bit-identical to gauss_from_u32 sample by sample.
+// Must be called by all 32 lanes of a converged warp.
+__device__ __forceinline__ void gauss_block4(const u32x4& b, float z[4]) {
+    const uint32_t k[4] = {b.x, b.y, b.z, b.w};
+    float w[4], x[4], pc[4];
+    bool tail = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t j = k[e] & 0x7fffffffu;
+        const float v = f_fma((float)j, 0x1p-31f, 0x1p-32f);
+        const float t = f_mul(v, f_sub(2.0f, v));
+        x[e] = f_sub(1.0f, v);
+        w[e] = -log_pos(t);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float wc = f_sub(w[e], 2.5f);
+        float p = 2.81022636e-08f;
+        p = f_fma(p, wc, 3.43273939e-07f);
+        p = f_fma(p, wc, -3.5233877e-06f);
+        p = f_fma(p, wc, -4.39150654e-06f);
+        p = f_fma(p, wc, 0.00021858087f);
+        p = f_fma(p, wc, -0.00125372503f);
+        p = f_fma(p, wc, -0.00417768164f);
+        p = f_fma(p, wc, 0.246640727f);
+        p = f_fma(p, wc, 1.50140941f);
+        pc[e] = p;
+        tail |= !(w[e] < 5.0f);
+    }
+    if (__any_sync(0xffffffffu, tail)) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (!(w[e] < 5.0f)) {
+                const float ws = f_sub(f_sqrt(w[e]), 3.0f);
+                float p = -0.000200214257f;
+                p = f_fma(p, ws, 0.000100950558f);
+                p = f_fma(p, ws, 0.00134934322f);
+                p = f_fma(p, ws, -0.00367342844f);
+                p = f_fma(p, ws, 0.00573950773f);
+                p = f_fma(p, ws, -0.0076224613f);
+                p = f_fma(p, ws, 0.00943887047f);
+                p = f_fma(p, ws, 1.00167406f);
+                p = f_fma(p, ws, 2.83297682f);
+                pc[e] = p;
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float zz = f_mul(f_mul(pc[e], x[e]), 1.41421354f);
+        z[e] = (k[e] >> 31) ? -zz : zz;
+    }
+}
+#endif
+
+// Integer-only widening f32 -> f64 (exact; the Gaussian transform never yields denormals or non-finite values).
+// Keeps the generator off the FP64 pipe, which the DMMA main loop saturates (F2F.F64.F32 runs there).
+RNLA_HD uint64_t f32_bits_to_f64_bits(uint32_t b) {
+    const uint32_t e = (b >> 23) & 0xffu;
+    if (e == 0) return (uint64_t)(b & 0x80000000u) << 32;                       // +-0
+    return ((uint64_t)(b & 0x80000000u) << 32) | ((uint64_t)(e + 896u) << 52) | ((uint64_t)(b & 0x007fffffu) << 29);
+}
+RNLA_HD double bits_d(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double a; __builtin_memcpy(&a, &u, 8); return a;
+#endif
+}
+RNLA_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return __builtin_clzll(x);
+#endif
+}
+
+// Uniform(-1,1): (2k+1) 2^-32 - 1, exact in f64 (a 33-bit odd integer times 2^-32), built with integer ops only.
+// Rademacher: +1 iff top bit clear (mirrors `Bernoulli(0.5)`: true iff u < 2^63, src/sketch.rs:124-125).
 RNLA_HD double sample_from_u32(int dist, uint32_t k) {
-    if (dist == DIST_GAUSSIAN) return (double)gauss_from_u32(k);
-    if (dist == DIST_UNIFORM) return ((double)k * 2.0 + 1.0) * 0x1p-32 - 1.0;
-    return (k >> 31) ? -1.0 : 1.0;
+    if (dist == DIST_GAUSSIAN) return bits_d(f32_bits_to_f64_bits(f_bits(gauss_from_u32(k))));
+    if (dist == DIST_UNIFORM) {
+        const int64_t nsig = 2 * (int64_t)k + 1 - ((int64_t)1 << 32);           // odd, |n| < 2^32
+        const uint64_t mag = (uint64_t)(nsig < 0 ? -nsig : nsig);
+        const int p = 63 - clz64(mag);                                          // position of the leading one
+        const uint64_t mant = (mag << (52 - p)) & 0x000fffffffffffffull;
+        return bits_d((nsig < 0 ? 0x8000000000000000ull : 0ull) | ((uint64_t)(p - 32 + 1023) << 52) | mant);
+    }
+    return bits_d((k >> 31) ? 0xBFF0000000000000ull : 0x3FF0000000000000ull);
 }
 
 // the four entries rows 4q..4q+3 of column c

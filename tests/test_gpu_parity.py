@@ -1,0 +1,500 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle, on a B200.  Every test here needs the GPU.
+
+Bars (north_star): bit-exact for the integer streams and for Omega; singular / eigen values to relative 1e-10 in
+f64 when GPU and oracle are given the same Omega (they are by construction: Omega is a pure function of
+(seed, stream, row, col), restated independently in oracle/); subspace angle and ||A - U S V^T|| / ||A|| reported
+and bounded.  The test bodies follow the reference's own tests (src/*.rs #[cfg(test)] modules, cited inline).
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rank_k_matrix, random_matrix, random_hermitian, random_psd, lowrank_plus_noise, subspace_angle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SIG_TOL = 1e-10          # relative tolerance on singular values / eigenvalues (north_star)
+GEMM_TOL = 1e-13         # relative to the largest entry, per unit of inner dimension growth
+
+
+# ---------------------------------------------------------------- L0: integer streams, bit exact
+def test_philox_kat_on_device(rb):
+    k = json.load(open(os.path.join(GOLD, "reference_kats.json")))["philox4x32_10"]
+    key = np.array([[int(x, 16) for x in k["key"]]], dtype=np.uint32)
+    ctr = np.zeros((10, 4), dtype=np.uint32); ctr[:, 0] = np.arange(10)
+    exp = np.array([[int(x, 16) for x in row] for row in k["out"]], dtype=np.uint32)
+    assert (rb.sketch.philox4x32_10(ctr, key) == exp).all()
+
+
+def test_threefry_kat_on_device(rb):
+    k = json.load(open(os.path.join(GOLD, "reference_kats.json")))["threefry2x64_20"]
+    key = np.array([[int(x, 16) for x in k["key"]]], dtype=np.uint64)
+    ctr = np.zeros((10, 2), dtype=np.uint64); ctr[:, 0] = np.arange(10)
+    exp = np.array([[int(x, 16) for x in row] for row in k["out"]], dtype=np.uint64)
+    assert (rb.sketch.threefry2x64_20(ctr, key) == exp).all()
+
+
+def test_philox_random_counters_match_oracle(rb, orc):
+    rng = np.random.default_rng(0)
+    ctr = rng.integers(0, 2**32, size=(4096, 4), dtype=np.uint64).astype(np.uint32)
+    key = rng.integers(0, 2**32, size=(4096, 2), dtype=np.uint64).astype(np.uint32)
+    assert (rb.sketch.philox4x32_10(ctr, key) == orc.philox4x32_10(ctr, key)).all()
+
+
+# ---------------------------------------------------------------- L1: sketch operators
+@pytest.mark.parametrize("dist", [0, 1, 2])
+@pytest.mark.parametrize("shape,row_off", [((257, 19), 0), ((64, 64), 4), ((33, 7), 3), ((1, 1), 0), ((1000, 3), 1234567)])
+def test_omega_bit_exact(rb, orc, dist, shape, row_off):
+    """Omega(r, c) on the device == the oracle's restatement, bit for bit (Gaussian included)"""
+    got = rb.sketch.sketch_fill(dist, shape[0], shape[1], seed=99, stream=1, row_offset=row_off)
+    exp = orc.omega_fill(dist, shape[0], shape[1], seed=99, stream=1, row_off=row_off)
+    assert got.tobytes() == exp.tobytes()
+
+
+def test_sketching_operator_reference_cases(rb):
+    """src/sketch.rs:216-248 test_sketching_operator: shapes, Err on zero rows/cols; plus distribution sanity"""
+    from randnla_b200.sketch import DistributionType as D
+    from randnla_b200.errors import InvalidDimensions
+    for d in (D.Gaussian, D.Uniform, D.Rademacher):
+        M = rb.sketch.sketching_operator(d, 6, 4)
+        assert M.shape == (6, 4)
+        with pytest.raises(InvalidDimensions):
+            rb.sketch.sketching_operator(d, 0, 4)
+        with pytest.raises(InvalidDimensions):
+            rb.sketch.sketching_operator(d, 4, 0)
+    G = rb.sketch.sketching_operator(D.Gaussian, 2000, 100)
+    assert abs(G.mean()) < 0.01 and abs(G.std() - 1) < 0.01
+    # deterministic, like the reference's fixed seed 0 (src/sketch.rs:112)
+    assert (rb.sketch.sketching_operator(D.Gaussian, 50, 5) == rb.sketch.sketching_operator(D.Gaussian, 50, 5)).all()
+    R = rb.sketch.sketching_operator(D.Rademacher, 100, 10)
+    assert set(np.unique(R)) == {-1.0, 1.0}
+    U = rb.sketch.sketching_operator(D.Uniform, 100, 10)
+    assert U.min() > -1 and U.max() < 1
+
+
+@pytest.mark.parametrize("dist", [1, 2])
+def test_reference_threefry_stream(rb, orc, dist):
+    """generator=THREEFRY reproduces what the reference's sketching_operator returns for Uniform / Rademacher"""
+    from randnla_b200 import runtime as rt
+    got = rb.sketch.sketch_fill(dist, 37, 11, seed=0, generator=rt.GEN_THREEFRY)
+    assert got.tobytes() == orc.sketching_operator_ref(dist, 37, 11, seed=0).tobytes()
+    from randnla_b200.errors import InvalidParameters
+    with pytest.raises(InvalidParameters):
+        rb.sketch.sketch_fill(0, 4, 4, generator=rt.GEN_THREEFRY)
+
+
+def test_haar_sample(rb):
+    """src/sketch.rs:140-214 test_row_attribute / test_column_attribute"""
+    from randnla_b200.sketch import MatrixAttribute as M
+    Q = rb.sketch.haar_sample(3, 6, M.Row)
+    assert Q.shape == (3, 6) and np.abs(Q @ Q.T - np.eye(3)).max() < 1e-6
+    Q = rb.sketch.haar_sample(6, 3, M.Column)
+    assert Q.shape == (6, 3) and np.abs(Q.T @ Q - np.eye(3)).max() < 1e-6
+
+
+# ---------------------------------------------------------------- K1 / K1' / K2 streaming GEMMs
+def _dev(rt, a):
+    return rt.to_device_colmajor(a)
+
+
+GEMM_SHAPES = [(1, 1, 1), (7, 5, 3), (128, 32, 16), (129, 33, 17), (300, 70, 9), (1025, 515, 110), (777, 333, 210),
+               (4096, 2048, 128), (2000, 1000, 60), (513, 1, 40), (2, 4096, 5)]
+
+
+@pytest.mark.parametrize("m,K,N", GEMM_SHAPES)
+def test_gemm_nn_tn_vs_oracle(rb, orc, m, K, N):
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    A, B, Q = random_matrix(m, K, 1), random_matrix(K, N, 2), random_matrix(m, N, 3)
+    dA, dB, dQ = _dev(rt, A), _dev(rt, B), _dev(rt, Q)
+    dC, dZ = rt.empty_colmajor(m, N), rt.empty_colmajor(K, N)
+    (pA, lda), (pB, ldb), (pQ, ldq), (pC, ldc), (pZ, ldz) = map(rt.dev_ptr_ld, (dA, dB, dQ, dC, dZ))
+    _lib.check(lib.rnla_gemm_nn_dev(pA, lda, m, K, pB, ldb, N, pC, ldc))
+    _lib.check(lib.rnla_gemm_tn_dev(pA, lda, m, K, pQ, ldq, N, pZ, ldz, 0))
+    rt.synchronize()
+    ref = orc.gemm_nn(A, B)
+    assert np.abs(dC.cpu().numpy() - ref).max() <= GEMM_TOL * K * max(np.abs(ref).max(), 1)
+    ref = orc.gemm_tn(A, Q)
+    assert np.abs(dZ.cpu().numpy() - ref).max() <= GEMM_TOL * m * max(np.abs(ref).max(), 1)
+
+
+@pytest.mark.parametrize("dist", [0, 1, 2])
+@pytest.mark.parametrize("m,K,N", [(300, 70, 9), (1025, 516, 110), (513, 33, 210), (128, 4, 1)])
+def test_fused_sketch_gemm_equals_materialised(rb, orc, m, K, N, dist):
+    """A * Omega with Omega generated inside the kernel is bit-identical to multiplying by the materialised Omega
+    (same tiles, same DMMA order) and agrees with the oracle product on the oracle's own Omega."""
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    A = random_matrix(m, K, 5)
+    dA = _dev(rt, A); dC = rt.empty_colmajor(m, N); dC2 = rt.empty_colmajor(m, N)
+    pA, lda = rt.dev_ptr_ld(dA); pC, ldc = rt.dev_ptr_ld(dC); pC2, ldc2 = rt.dev_ptr_ld(dC2)
+    _lib.check(lib.rnla_sketch_gemm_dev(pA, lda, m, K, dist, 7, 1, N, pC, ldc))
+    Om = rb.sketch.sketch_fill(dist, K, N, seed=7, stream=1)
+    dOm = _dev(rt, Om); pO, ldo = rt.dev_ptr_ld(dOm)
+    _lib.check(lib.rnla_gemm_nn_dev(pA, lda, m, K, pO, ldo, N, pC2, ldc2))
+    rt.synchronize()
+    assert dC.cpu().numpy().tobytes() == dC2.cpu().numpy().tobytes()
+    ref = orc.gemm_nn(A, orc.omega_fill(dist, K, N, seed=7, stream=1))
+    assert np.abs(dC.cpu().numpy() - ref).max() <= GEMM_TOL * K * max(np.abs(ref).max(), 1)
+
+
+def test_gemm_unaligned_inputs(rb, orc):
+    """odd leading dimensions / offsets take the manual (non-TMA) staging path"""
+    from randnla_b200 import runtime as rt, _lib
+    import torch
+    lib = _lib.load()
+    A = random_matrix(301, 71, 1); B = random_matrix(71, 33, 2); Q = random_matrix(301, 33, 3)
+    dA, dB, dQ = _dev(rt, A), _dev(rt, B), _dev(rt, Q)
+    dC, dZ = rt.empty_colmajor(301, 33), rt.empty_colmajor(71, 33)
+    (pA, lda), (pB, ldb), (pQ, ldq), (pC, ldc), (pZ, ldz) = map(rt.dev_ptr_ld, (dA, dB, dQ, dC, dZ))
+    assert lda % 2 == 1
+    _lib.check(lib.rnla_gemm_nn_dev(pA, lda, 301, 71, pB, ldb, 33, pC, ldc))
+    _lib.check(lib.rnla_gemm_tn_dev(pA, lda, 301, 71, pQ, ldq, 33, pZ, ldz, 0))
+    rt.synchronize()
+    assert np.abs(dC.cpu().numpy() - orc.gemm_nn(A, B)).max() < 1e-11
+    assert np.abs(dZ.cpu().numpy() - orc.gemm_tn(A, Q)).max() < 1e-11
+    # sub-matrix views: row offset 1 (8-byte aligned only) inside a larger allocation
+    big = rt.to_device_colmajor(random_matrix(400, 80, 4))
+    sub = big[1:302, 3:74]
+    pS, lds = rt.dev_ptr_ld(sub)
+    _lib.check(lib.rnla_gemm_nn_dev(pS, lds, 301, 71, pB, ldb, 33, pC, ldc))
+    rt.synchronize()
+    assert np.abs(dC.cpu().numpy() - sub.cpu().numpy() @ B).max() < 1e-11
+
+
+def test_gemm_tn_is_deterministic(rb):
+    """the split over the long dimension is reduced in a fixed order: two runs agree bit for bit"""
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    A = random_matrix(20000, 300, 1); Q = random_matrix(20000, 60, 2)
+    dA, dQ = _dev(rt, A), _dev(rt, Q)
+    out = []
+    for _ in range(2):
+        dZ = rt.empty_colmajor(300, 60)
+        (pA, lda), (pQ, ldq), (pZ, ldz) = map(rt.dev_ptr_ld, (dA, dQ, dZ))
+        _lib.check(lib.rnla_gemm_tn_dev(pA, lda, 20000, 300, pQ, ldq, 60, pZ, ldz, 0)); rt.synchronize()
+        out.append(dZ.cpu().numpy().tobytes())
+    assert out[0] == out[1]
+
+
+# ---------------------------------------------------------------- K3 orth / literal Stabilizer
+def test_orth_reference_cases(rb):
+    """src/lora_helpers.rs:306-340: Q^T Q = I to 1e-6; Orth(0) = I; Orth(I) = I"""
+    from randnla_b200.lora_helpers import Orth
+    X = random_matrix(10, 5, 1)
+    Q = Orth(X)
+    assert Q.shape == (10, 5) and np.abs(Q.T @ Q - np.eye(5)).max() < 1e-6
+    assert (Orth(np.zeros((5, 5))) == np.eye(5)).all()
+    assert np.abs(Orth(np.eye(5)) - np.eye(5)).max() < 1e-15
+
+
+@pytest.mark.parametrize("rows,cols", [(50, 8), (500, 40), (2000, 110), (64, 64), (4097, 210), (9, 20)])
+def test_orth_matches_householder_q(rb, orc, rows, cols):
+    """full-rank input: the CholeskyQR2 factor equals nalgebra's Householder Q (R_ii >= 0 makes it unique)"""
+    from randnla_b200.lora_helpers import Orth
+    X = random_matrix(rows, cols, 3)
+    Q, R = Orth(X, return_r=True)
+    Qo, Ro = orc.qr(X)
+    p = min(rows, cols)
+    assert np.abs(Q.T @ Q - np.eye(p)).max() < 1e-13
+    assert np.abs(Q - Qo).max() < 1e-11 and np.abs(R - Ro).max() < 1e-11 * np.abs(Ro).max()
+    assert np.abs(Q @ R - X).max() < 1e-12 * np.abs(X).max()
+
+
+@pytest.mark.parametrize("case", ["rank_deficient", "zero_columns", "duplicate_columns", "ill_conditioned", "tiny_scale"])
+def test_orth_degenerate_panels(rb, case):
+    """rank-deficient panels are the normal case on this path: Q must still be orthonormal,
+    span the input, and reproduce it through an upper-triangular R with a non-negative diagonal"""
+    from randnla_b200.lora_helpers import Orth
+    rng = np.random.default_rng(8)
+    if case == "rank_deficient":
+        X = rng.standard_normal((400, 12)) @ rng.standard_normal((12, 30))
+    elif case == "zero_columns":
+        X = rng.standard_normal((300, 20)); X[:, [0, 7, 19]] = 0
+    elif case == "duplicate_columns":
+        X = rng.standard_normal((300, 10)); X = np.concatenate([X, X[:, :5]], axis=1)
+    elif case == "ill_conditioned":
+        U, _ = np.linalg.qr(rng.standard_normal((500, 24))); V, _ = np.linalg.qr(rng.standard_normal((24, 24)))
+        X = (U * np.logspace(0, -11, 24)) @ V.T
+    else:
+        X = 1e-150 * rng.standard_normal((200, 16))
+    Q, R = Orth(X, return_r=True)
+    p = X.shape[1]
+    assert np.abs(Q.T @ Q - np.eye(p)).max() < 1e-12
+    assert np.abs(Q @ R - X).max() <= 1e-12 * np.abs(X).max()
+    assert np.abs(np.tril(R, -1)).max() == 0 and (np.diag(R) >= 0).all()
+
+
+@pytest.mark.parametrize("shape", [(30, 6), (6, 6), (5, 9), (64, 17), (1000, 110), (2000, 60)])
+def test_stabilizer_bit_exact(rb, orc, shape):
+    """literal Stabilizer = L of the full-pivot LU: the GPU performs the same operations in the same order"""
+    from randnla_b200.lora_helpers import Stabilizer
+    X = random_matrix(*shape, seed=7)
+    assert Stabilizer(X).tobytes() == orc.Stabilizer(X).tobytes()
+
+
+def test_stabilizer_reference_cases(rb):
+    """src/lora_helpers.rs:342-373"""
+    from randnla_b200.lora_helpers import Stabilizer
+    assert (Stabilizer(np.zeros((5, 5))) == np.eye(5)).all()
+    assert Stabilizer(random_matrix(10, 5, 1)).shape == (10, 5)
+    assert Stabilizer(random_matrix(5, 10, 1)).shape == (5, 5)
+    X = np.ones((6, 4))                     # all ties: first maximum in column-major order
+    L = Stabilizer(X)
+    assert np.abs(L).max() <= 1.0 and (np.diag(L) == 1).all()
+
+
+# ---------------------------------------------------------------- tsog1 / RF1 / QB1
+def test_tsog1_shapes_and_parity(rb, orc):
+    """src/lora_helpers.rs:160-232 (shapes for passes in {3,4}, stab in {1,2,3}) + parity with the oracle on the same Omega"""
+    from randnla_b200 import runtime as rt
+    from randnla_b200.lora_helpers import tsog1
+    A = random_matrix(60, 40, seed=9)
+    for mode in (rt.MODE_INTENDED, rt.MODE_LITERAL):
+        with rt.options(mode=mode, fused_sketch=1):
+            for q in (2, 3, 4):
+                for pps in (1, 2, 3):
+                    S = tsog1(A, 5, q, pps)
+                    assert S.shape == (40, 5)
+                    So = orc.tsog1(A, 5, q, pps, orc.make_opts(mode=mode))
+                    if mode == rt.MODE_LITERAL:
+                        assert np.abs(S - So).max() <= 1e-9 * max(np.abs(So).max(), 1)
+                    else:
+                        # same subspace (the stabiliser is a QR on both sides; an un-stabilised S is the raw product)
+                        Qa, _ = np.linalg.qr(S); Qb, _ = np.linalg.qr(So)
+                        assert subspace_angle(Qa, Qb) < 1e-6
+
+
+def test_rf1_qb1_reference_cases(rb, orc):
+    """src/lora_helpers.rs:236-304: shapes, ||A - QQ^T A|| < ||A||, relative QB error <= 1; plus parity"""
+    from randnla_b200.lora_helpers import RF1, QB1
+    A = random_matrix(20, 10, seed=11)
+    Q = RF1(A, 5)
+    assert Q.shape == (20, 5) and np.abs(Q.T @ Q - np.eye(5)).max() < 1e-12
+    assert np.linalg.norm(A - Q @ Q.T @ A) < np.linalg.norm(A)
+    Q, B = QB1(A, 5, 0.01)
+    assert Q.shape == (20, 5) and B.shape == (5, 10)
+    assert np.abs(B - Q.T @ A).max() < 1e-12
+    assert np.linalg.norm(A - Q @ B) / np.linalg.norm(A) <= 1.0
+    Qo, Bo = orc.QB1(A, 5, 0.01, orc.make_opts(mode=0))
+    assert subspace_angle(Q, Qo) < 1e-8
+    assert abs(np.linalg.norm(A - Q @ B) - np.linalg.norm(A - Qo @ Bo)) < 1e-10 * np.linalg.norm(A)
+
+
+# ---------------------------------------------------------------- rand_svd
+def test_rand_svd_reference_cases(rb):
+    """src/lora_drivers.rs:236-475"""
+    from randnla_b200.lora_drivers import rand_svd
+    from randnla_b200.errors import InvalidParameters
+    for (m, n, k) in [(20, 10, 5), (10, 20, 5), (10, 10, 5), (100, 50, 10)]:       # tall / wide / square
+        A = random_matrix(m, n, seed=m + n)
+        U, S, Vt = rand_svd(A, k, 0.1, 5)
+        assert U.shape == (m, k) and S.shape == (k, k) and Vt.shape == (k, n)
+        s = np.diag(S)
+        assert np.count_nonzero(S - np.diag(s)) == 0
+        assert (np.diff(s) <= 1e-14).all() and (s >= 0).all()                        # :446-460 non-increasing
+        assert np.abs(U.T @ U - np.eye(k)).max() < 1e-12 and np.abs(Vt @ Vt.T - np.eye(k)).max() < 1e-12
+        assert np.linalg.norm(A - U @ S @ Vt) / np.linalg.norm(A) <= 1.0
+    U, S, Vt = rand_svd(np.eye(5), 3, 0.01, 2)                                        # :359-373 identity
+    assert U.shape == (5, 3) and np.abs(np.diag(S) - 1).max() < 1e-12
+    U, S, Vt = rand_svd(np.zeros((10, 10)), 5, 0.1, 5)                                # :341-357 zero matrix
+    assert np.abs(U - np.eye(10, 5)).max() < 1e-6 and np.abs(S).max() < 1e-6 and np.abs(Vt - np.eye(5, 10)).max() < 1e-6
+    with pytest.raises(InvalidParameters):
+        rand_svd(random_matrix(5, 5), 0, 0.1, 5)                                      # :329-339
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("fused", [0, 1])
+def test_rand_svd_c1_parity(rb, orc, mode, fused):
+    """BASELINE config 1: 2000 x 1000 rank-50, k=50, p=10, q=2 -- GPU vs oracle (same mode, same Omega) and vs LAPACK"""
+    from randnla_b200 import runtime as rt
+    from randnla_b200.lora_drivers import rand_svd
+    A = rank_k_matrix(2000, 1000, 50, seed=1)
+    with rt.options(mode=mode, fused_sketch=fused):
+        U, S, Vt = rand_svd(A, 50, 1e-6, 10)
+    Uo, So, Vto = orc.rand_svd(A, 50, 1e-6, 10, orc.make_opts(mode=mode))
+    s, so = np.diag(S), np.diag(So)
+    sv = np.linalg.svd(A, compute_uv=False)[:50]
+    assert (np.abs(s - so) / so).max() < SIG_TOL
+    assert (np.abs(s - sv) / sv).max() < SIG_TOL
+    assert subspace_angle(U, Uo) < 1e-7 and subspace_angle(Vt.T.copy(), Vto.T.copy()) < 1e-7
+    assert np.linalg.norm(A - U @ S @ Vt) / np.linalg.norm(A) < 1e-12
+    assert np.abs(U.T @ U - np.eye(50)).max() < 1e-12
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_rand_svd_lowrank_plus_noise_parity(rb, orc, mode):
+    """C2-style spectrum at oracle-sized dimensions: same Omega on both sides -> sigma to 1e-10"""
+    from randnla_b200 import runtime as rt
+    from randnla_b200.lora_drivers import rand_svd
+    A, sig = lowrank_plus_noise(3000, 700, seed=3, k=40)
+    with rt.options(mode=mode, fused_sketch=1):
+        U, S, Vt = rand_svd(A, 40, 1e-6, 10)
+    Uo, So, Vto = orc.rand_svd(A, 40, 1e-6, 10, orc.make_opts(mode=mode))
+    s, so = np.diag(S), np.diag(So)
+    assert (np.abs(s - so) / so).max() < SIG_TOL
+    assert subspace_angle(U[:, :20], Uo[:, :20]) < 1e-6
+    ra, rbo = np.linalg.norm(A - U @ S @ Vt), np.linalg.norm(A - Uo @ So @ Vto)
+    assert abs(ra - rbo) <= 1e-8 * np.linalg.norm(A)
+
+
+def test_rand_svd_options(rb, orc):
+    """extended knobs: seed, num_passes (odd branch draws Omega (m x l)), passes_per_stab, distribution"""
+    from randnla_b200 import runtime as rt
+    from randnla_b200.lora_drivers import rand_svd
+    A, sig = lowrank_plus_noise(900, 400, seed=5, k=15)
+    for kw in [dict(seed=7), dict(num_passes=3), dict(num_passes=4, passes_per_stab=2), dict(num_passes=1), dict(dist=2), dict(dist=1, num_passes=3)]:
+        with rt.options(fused_sketch=1, **kw):
+            U, S, Vt = rand_svd(A, 15, 1e-6, 5)
+        So = orc.rand_svd(A, 15, 1e-6, 5, orc.make_opts(mode=0, **kw))[1]
+        assert (np.abs(np.diag(S) - np.diag(So)) / np.diag(So)).max() < 1e-9, kw
+
+
+# ---------------------------------------------------------------- rand_evd1 / rand_evd2
+def test_rand_evd1_reference_cases(rb, orc):
+    """src/lora_drivers.rs:490-673"""
+    from randnla_b200.lora_drivers import rand_evd1
+    from randnla_b200.errors import NotHermitian, InvalidParameters
+    H = random_hermitian(10, seed=1)
+    V, lam = rand_evd1(H, 5, 0.1, 5)
+    assert V.shape == (10, 5) and len(lam) == 5
+    assert np.abs(V.T @ V - np.eye(5)).max() < 1e-6                                 # :630-641
+    assert (np.diff(np.abs(lam)) <= 1e-12).all()                                    # :643-657
+    w = np.linalg.eigvalsh(H); w = w[np.argsort(-np.abs(w))][:5]
+    assert np.abs(np.array(lam) - w).max() < 1e-10
+    with pytest.raises(NotHermitian):
+        rand_evd1(random_matrix(6, 6, seed=2), 3, 0.1, 2)                           # :503-515
+    with pytest.raises(InvalidParameters):
+        rand_evd1(H, 0, 0.1, 2)
+    V, lam = rand_evd1(np.zeros((10, 10)), 5, 0.1, 5)                               # :531-548
+    assert np.abs(np.array(lam)).max() == 0 and np.abs(V - np.eye(10, 5)).max() < 1e-6
+    # parity on a larger indefinite matrix with decay
+    rng = np.random.default_rng(4)
+    Qm, _ = np.linalg.qr(rng.standard_normal((400, 400)))
+    ev = np.concatenate([np.array([5, -4, 3, -2.5, 2, 1.5, -1.2, 1.0]), 1e-6 * rng.standard_normal(392)])
+    Hm = np.asfortranarray((Qm * ev) @ Qm.T); Hm = np.asfortranarray(0.5 * (Hm + Hm.T))
+    V, lam = rand_evd1(Hm, 8, 0.1, 8)
+    Vo, lamo = orc.rand_evd1(Hm, 8, 0.1, 8, orc.make_opts(mode=0))
+    assert (np.abs(np.array(lam) - lamo) / np.abs(lamo)).max() < SIG_TOL
+    assert subspace_angle(V, Vo) < 1e-6
+
+
+def test_rand_evd2_reference_cases(rb, orc):
+    """src/lora_drivers.rs:688-878"""
+    from randnla_b200.lora_drivers import rand_evd2
+    from randnla_b200.errors import MatrixDecompositionError, NotPositiveSemiDefinite, InvalidParameters
+    A = random_psd(5, seed=6)
+    V, lam = rand_evd2(A, 3, 2)                                                      # :747-775
+    w, W = np.linalg.eigh(A); idx = np.argsort(-w)[:3]
+    assert np.abs(np.array(lam) - w[idx]).max() < 1e-6
+    assert np.abs(V.T @ V - np.eye(3)).max() < 1e-6
+    assert np.abs(V @ V.T @ A - W[:, idx] @ W[:, idx].T @ A).max() < 1e-6
+    with pytest.raises(MatrixDecompositionError):
+        rand_evd2(np.zeros((5, 5)), 3, 2)                                            # :724-732
+    with pytest.raises(NotPositiveSemiDefinite):
+        rand_evd2(-random_psd(5, seed=7), 3, 2)                                      # :705-722
+    with pytest.raises(InvalidParameters):
+        rand_evd2(A, 0, 2)
+    V, lam = rand_evd2(random_psd(8, seed=8), 3, 0)                                  # :841 s = 0 accepted
+    assert V.shape[0] == 8 and len(lam) <= 3
+    # parity with the oracle on a PSD matrix with decay
+    rng = np.random.default_rng(9)
+    Qm, _ = np.linalg.qr(rng.standard_normal((300, 300)))
+    ev = np.concatenate([np.logspace(1, -1, 12), 1e-7 * np.abs(rng.standard_normal(288))])
+    P = np.asfortranarray((Qm * ev) @ Qm.T); P = np.asfortranarray(0.5 * (P + P.T))
+    V, lam = rand_evd2(P, 12, 6)
+    Vo, lamo = orc.rand_evd2(P, 12, 6, orc.make_opts(mode=0))
+    assert len(lam) == len(lamo)
+    assert (np.abs(np.array(lam) - lamo) / lamo).max() < 1e-9
+    assert subspace_angle(V, Vo) < 1e-6
+
+
+# ---------------------------------------------------------------- sketch step of sketch_and_precondition
+def test_sketch_step_dense_and_saso(rb, orc):
+    from randnla_b200 import sketch_and_precondition as sp
+    A = random_matrix(5000, 37, seed=5); b = random_matrix(5000, 1, seed=6)
+    d = sp.sketch_dim(5000, 37, 4.0)
+    assert d == 148
+    a_sk, b_sk = sp.blendenpik_sketch(A, b, 1e-6, 50, 4.0)                           # reference :49-52
+    assert a_sk.shape == (148, 37) and b_sk.shape == (148, 1)
+    ref = orc.sketch_apply_dense(A, d, seed=0)
+    assert np.abs(a_sk - ref).max() <= 1e-12 * np.abs(ref).max() * 50
+    assert np.abs(b_sk - orc.sketch_apply_dense(b, d, seed=0)).max() <= 1e-10
+    a_sk2 = sp.lsrn_sketch(A, b, 1e-6, 50, 4.0)                                      # :105-107
+    assert a_sk2.tobytes() == a_sk.tobytes()
+    a_sk3 = sp.saddle_point_sketch(A, b, None, 0.0, 1e-6, 50, 4.0)                   # :172-176
+    assert a_sk3.shape == (148, 37)
+    for zeta in (1, 4, 8):
+        got = sp.sketch_apply(A, None, 200, kind=sp.SKETCH_SASO, zeta=zeta, seed=3)
+        ref = orc.sketch_apply_saso(A, 200, zeta=zeta, seed=3)
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max() * 10
+    # subspace-embedding property of the sketch: singular values of S A within a constant of those of A
+    s_full = np.linalg.svd(A, compute_uv=False)
+    s_sk = np.linalg.svd(sp.sketch_apply(A, None, 400, kind=sp.SKETCH_SASO, zeta=8, seed=1), compute_uv=False)
+    assert 0.6 < (s_sk / s_full).min() and (s_sk / s_full).max() < 1.4
+
+
+# ---------------------------------------------------------------- committed golden fixtures (oracle outputs)
+def test_golden_fixtures(rb):
+    """tests/golden/*.npz were written by tests/golden/make_golden.py from the oracle; the GPU must reproduce them"""
+    from randnla_b200 import runtime as rt
+    from randnla_b200.lora_drivers import rand_svd, rand_evd1, rand_evd2
+    g = np.load(os.path.join(GOLD, "path_golden.npz"))
+    A = np.asfortranarray(g["svd_A"])
+    for mode in (0, 1):
+        with rt.options(mode=mode, fused_sketch=1):
+            U, S, Vt = rand_svd(A, int(g["svd_k"]), 1e-6, int(g["svd_s"]))
+        so = g[f"svd_sigma_mode{mode}"]
+        assert (np.abs(np.diag(S) - so) / so).max() < SIG_TOL
+    assert rb.sketch.sketch_fill(0, 16, 5, seed=int(g["omega_seed"]), stream=1).tobytes() == np.asfortranarray(g["omega_gauss"]).tobytes()
+    V, lam = rand_evd1(np.asfortranarray(g["evd1_A"]), 6, 0.1, 6)
+    assert (np.abs(np.array(lam) - g["evd1_lambda"]) / np.abs(g["evd1_lambda"])).max() < SIG_TOL
+    V, lam = rand_evd2(np.asfortranarray(g["evd2_A"]), 6, 4)
+    assert (np.abs(np.array(lam) - g["evd2_lambda"]) / g["evd2_lambda"]).max() < 1e-9
+    from randnla_b200.lora_helpers import Stabilizer
+    assert Stabilizer(np.asfortranarray(g["stab_X"])).tobytes() == np.asfortranarray(g["stab_L"]).tobytes()
+
+
+# ---------------------------------------------------------------- full size (BASELINE config 2), size-independent properties
+def test_c2_full_size_properties(rb):
+    """200 000 x 20 000 f64 (32 GB), k=100, p=10, q=2: the oracle cannot run this in seconds, so check what does not
+    depend on size: U^T U = I, V^T V = I, sigma sorted and equal to the planted spectrum up to the noise level,
+    ||A - U S V^T||_F^2 = ||A||_F^2 - sum sigma^2 (Pythagoras for an orthogonal projection), seed-insensitivity."""
+    import torch
+    from randnla_b200 import runtime as rt, _lib, lora_drivers as ld
+    lib = _lib.load()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 80 * 2**30:
+        pytest.skip("needs ~80 GB of free HBM")
+    m, n, k, s, r0 = 200000, 20000, 100, 10, 200
+    sig = np.concatenate([np.logspace(0, -3, 100), np.full(r0 - 100, 1e-5)])
+    dA = rt.empty_colmajor(m, n)
+    pA, lda = rt.dev_ptr_ld(dA)
+    _lib.check(lib.rnla_generate_lowrank_dev(pA, lda, m, n, 0, m, r0, sig.ctypes.data_as(C.c_void_p), 1e-7, 1234))
+    res = {}
+    for seed, fused in [(0, 1), (1, 0)]:
+        U, S, Vt = ld.rand_svd_dev(dA, k, s, rt.make_options(seed=seed, fused_sketch=fused))
+        rt.synchronize()
+        res[seed] = (U, S.cpu().numpy(), Vt)
+    U, Sg, Vt = res[0]
+    assert (np.diff(Sg) <= 0).all()
+    assert (np.abs(Sg - sig[:k]) / sig[:k]).max() < 1e-5                  # noise eta = 1e-7 perturbs sigma_100 = 1e-3 by ~1e-7
+    assert (np.abs(res[0][1] - res[1][1]) / res[0][1]).max() < 1e-9        # two different Omega, gap of 100 at k
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    gram = rt.empty_colmajor(k, k); pG, ldg = rt.dev_ptr_ld(gram)
+    pU, ldu = rt.dev_ptr_ld(U)
+    _lib.check(lib.rnla_gemm_tn_dev(pU, ldu, m, k, pU, ldu, k, pG, ldg, 0)); rt.synchronize()
+    assert float((gram - eye).abs().max()) < 1e-12
+    V = Vt.t().contiguous().t() if False else None
+    vg = (Vt @ Vt.t())
+    assert float((vg - eye).abs().max()) < 1e-12
+    # ||A||_F^2 - sum sigma_i^2 ~ tail energy (100 x 1e-10) + noise energy (n * eta^2)
+    a2 = float((dA * dA).sum()) if False else float(torch.linalg.vector_norm(dA) ** 2)
+    resid2 = a2 - float((Sg ** 2).sum())
+    expect = 100 * 1e-10 + n * 1e-14
+    assert 0 < resid2 < 3 * expect
+    del dA
+    torch.cuda.empty_cache()
