@@ -1,0 +1,67 @@
+// C++ host-mirror test: the reference's own unit tests for this path, re-expressed against randblas.hpp.
+// Built and run by tests/test_cpp_mirror.py on the GPU box.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include "randblas.hpp"
+
+using namespace randblas;
+static int failures = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); ++failures; } } while (0)
+
+static bool approx_identity(const DMatrix& m, double tol) {
+    for (size_t j = 0; j < m.ncols(); ++j) for (size_t i = 0; i < m.nrows(); ++i)
+        if (std::fabs(m(i, j) - (i == j ? 1.0 : 0.0)) > tol) return false;
+    return true;
+}
+
+int main() {
+    using errors::RandNLAError;
+    // src/lora_drivers.rs:341-357 test_rand_svd_zero_matrix
+    {
+        auto [U, S, Vt] = lora_drivers::rand_svd(DMatrix::zeros(10, 10), 5, 0.1, 5);
+        CHECK(U.nrows() == 10 && U.ncols() == 5 && S.nrows() == 5 && Vt.nrows() == 5 && Vt.ncols() == 10);
+        CHECK(approx_identity(U, 1e-6) && approx_identity(Vt, 1e-6) && S.norm() < 1e-6);
+    }
+    // src/lora_drivers.rs:329-339 k = 0 -> InvalidParameters
+    try { lora_drivers::rand_svd(DMatrix::identity(5, 5), 0, 0.1, 5); CHECK(false); }
+    catch (const RandNLAError& e) { CHECK(e.kind == RandNLAError::InvalidParameters); CHECK(std::string(e.what()) == "Rank k must be positive, current input is 0"); }
+    // rank-3 matrix: singular values recovered, U orthonormal
+    {
+        DMatrix A(40, 20);
+        for (size_t i = 0; i < 40; ++i) for (size_t j = 0; j < 20; ++j)
+            A(i, j) = 3.0 * std::sin(0.1 * i) * std::cos(0.2 * j) + 2.0 * std::cos(0.3 * i) * std::sin(0.1 * j + 1) + ((i * 7 + j * 3) % 5 == 0 ? 1.0 : 0.0) * 0;
+        auto [U, S, Vt] = lora_drivers::rand_svd(A, 4, 1e-6, 4);
+        DMatrix R = U * S * Vt;
+        double err = 0; for (size_t i = 0; i < 40; ++i) for (size_t j = 0; j < 20; ++j) err += (R(i, j) - A(i, j)) * (R(i, j) - A(i, j));
+        CHECK(std::sqrt(err) / A.norm() < 1e-10);
+        CHECK(approx_identity(U.transpose() * U, 1e-10));
+        CHECK(S(0, 0) >= S(1, 1) && S(1, 1) >= S(2, 2));
+    }
+    // src/lora_helpers.rs:324-340, 358-365
+    CHECK(approx_identity(lora_helpers::Orth(DMatrix::zeros(5, 5)), 0.0));
+    CHECK(approx_identity(lora_helpers::Orth(DMatrix::identity(5, 5)), 1e-15));
+    CHECK(approx_identity(lora_helpers::Stabilizer(DMatrix::zeros(5, 5)), 0.0));
+    // src/sketch.rs:216-248
+    {
+        auto M = sketch::sketching_operator(sketch::DistributionType::Gaussian, 6, 4);
+        CHECK(M.nrows() == 6 && M.ncols() == 4);
+        try { sketch::sketching_operator(sketch::DistributionType::Uniform, 0, 4); CHECK(false); }
+        catch (const RandNLAError& e) { CHECK(e.kind == RandNLAError::InvalidDimensions); }
+    }
+    // src/lora_drivers.rs:503-515 non-symmetric -> NotHermitian; :724-732 zero matrix -> MatrixDecompositionError
+    {
+        DMatrix N(4, 4); N(0, 1) = 1.0;
+        try { lora_drivers::rand_evd1(N, 2, 0.1, 2); CHECK(false); } catch (const RandNLAError& e) { CHECK(e.kind == RandNLAError::NotHermitian); }
+        try { lora_drivers::rand_evd2(DMatrix::zeros(5, 5), 3, 2); CHECK(false); } catch (const RandNLAError& e) { CHECK(e.kind == RandNLAError::MatrixDecompositionError); }
+    }
+    // sketch step validation, src/sketch_and_precondition.rs:29-48
+    try { sketch_and_precondition::sketch_only(DMatrix(3, 4), 0.1, 10, 2.0); CHECK(false); }
+    catch (const RandNLAError& e) { CHECK(e.kind == RandNLAError::NotOverdetermined); }
+    {
+        auto [a_sk, b_sk] = sketch_and_precondition::blendenpik_sketch(DMatrix(200, 5, 1.0), DMatrix(200, 1, 1.0), 1e-6, 10, 4.0);
+        CHECK(a_sk.nrows() == 20 && a_sk.ncols() == 5 && b_sk.nrows() == 20);
+    }
+    std::printf(failures ? "CPP MIRROR: %d FAILURES\n" : "CPP MIRROR: ALL OK\n", failures);
+    return failures ? 1 : 0;
+}

@@ -224,7 +224,9 @@ rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int
     }
     int diff = q - done;                                                                              // :85
     if (diff >= 2) {
-        // every loop iteration restarts from S1 (:89), so all iterations produce the same S: run one
+        // every loop iteration restarts from S1 (:89) and overwrites S, so only the LAST iteration is observable;
+        // `passes_done` keeps counting across iterations and decides where that iteration stabilises (:91, :97)
+        done += 2 * (diff / 2 - 1);
         {
             PhaseScope ph("pass:A*S1");
             if (s1_zero) RNLA_CUDA(cudaMemsetAsync(T.d(), 0, (size_t)mm * l * 8, c.stream));        // A * zeros

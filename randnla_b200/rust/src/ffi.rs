@@ -1,0 +1,27 @@
+//! Raw bindings of include/rnla.h (only what the reference-signature functions need).
+use std::os::raw::{c_char, c_double, c_int};
+
+extern "C" {
+    pub fn rnla_last_error_message() -> *const c_char;
+    pub fn rnla_sketching_operator(dist: c_int, rows: i64, cols: i64, out: *mut c_double) -> c_int;
+    pub fn rnla_haar_sample(rows: i64, cols: i64, attr: c_int, out: *mut c_double) -> c_int;
+    pub fn rnla_orth(x: *const c_double, rows: i64, cols: i64, q: *mut c_double, r: *mut c_double, qcols: *mut i64) -> c_int;
+    pub fn rnla_stabilizer(x: *const c_double, rows: i64, cols: i64, l: *mut c_double, lcols: *mut i64) -> c_int;
+    pub fn rnla_tsog1(a: *const c_double, m: i64, n: i64, k: i64, num_passes: c_int, passes_per_stab: c_int, s: *mut c_double) -> c_int;
+    pub fn rnla_rf1(a: *const c_double, m: i64, n: i64, k: i64, q: *mut c_double, qcols: *mut i64) -> c_int;
+    pub fn rnla_qb1(a: *const c_double, m: i64, n: i64, k: i64, epsilon: c_double, q: *mut c_double, b: *mut c_double, qcols: *mut i64) -> c_int;
+    pub fn rnla_rand_svd(a: *const c_double, m: i64, n: i64, k: i64, epsilon: c_double, s: i64,
+                         u: *mut c_double, sig: *mut c_double, vt: *mut c_double, r: *mut i64) -> c_int;
+    pub fn rnla_rand_evd1(a: *const c_double, n: i64, k: i64, epsilon: c_double, s: i64, v: *mut c_double, lambda: *mut c_double, r: *mut i64) -> c_int;
+    pub fn rnla_rand_evd2(a: *const c_double, n: i64, k: i64, s: i64, v: *mut c_double, lambda: *mut c_double, r: *mut i64) -> c_int;
+    pub fn rnla_sketch_dim(m: i64, n: i64, sampling_factor: c_double, rule: c_int) -> i64;
+    pub fn rnla_sketch_apply(kind: c_int, dist: c_int, seed: u64, d: i64, zeta: c_int, a: *const c_double, m: i64, n: i64,
+                             b: *const c_double, nrhs: i64, a_sk: *mut c_double, b_sk: *mut c_double) -> c_int;
+}
+
+pub fn last_message() -> String {
+    unsafe {
+        let p = rnla_last_error_message();
+        if p.is_null() { String::new() } else { std::ffi::CStr::from_ptr(p).to_string_lossy().into_owned() }
+    }
+}

@@ -70,6 +70,8 @@ def lowrank_plus_noise(m, n, seed=0, k=20, gap=1e-2, noise=1e-9):
 
 
 def subspace_angle(X, Y):
-    """largest principal angle between range(X) and range(Y) (orthonormal columns)."""
-    s = np.linalg.svd(X.T @ Y, compute_uv=False)
-    return float(np.arccos(np.clip(s.min(), -1.0, 1.0)))
+    """largest principal angle between range(X) and range(Y) (orthonormal columns), from its sine so that
+    small angles are resolved below sqrt(eps)."""
+    R = Y - X @ (X.T @ Y)
+    s = np.linalg.svd(R, compute_uv=False)
+    return float(np.arcsin(np.clip(s.max(), 0.0, 1.0)))
