@@ -157,7 +157,13 @@ rnla_status rnla_rand_evd2_dev(const double* dA, int64_t lda, int64_t n, int64_t
                                const rnla_options* opt, double* dV, int64_t ldv, double* dLambda, int64_t* r);
 
 /* ---- sketch step of sketch_and_precondition (reference src/sketch_and_precondition.rs:49-52,105-107,172-176) */
-typedef enum rnla_sketch_kind { RNLA_SKETCH_DENSE = 0, RNLA_SKETCH_SASO = 1 } rnla_sketch_kind;
+/* DENSE: i.i.d. `dist` entries (what the reference draws).  SASO: textbook sparse-sign operator, zeta independent row
+ * indices per column (shared-memory scatter; 1 <= zeta <= 8, d <= 25600).  SASO_BLOCK: sparse-sign operator whose zeta
+ * zeta = g*w non-zeros per column come as g groups of w consecutive rows, one group per stripe of d/g rows (OSNAP block
+ * construction), dealt chunk-wise by keyed bijections (register accumulators, no atomics, fixed summation order, A
+ * streamed once; zeta in {1,2,4,8}, zeta <= d <= 16384).  For this kind the `dist` argument carries the block width w
+ * (1, 2 or 4, w | zeta; 0 = default min(zeta, 4); w = 1 is statistically the textbook SASO).  DESIGN.md section 5. */
+typedef enum rnla_sketch_kind { RNLA_SKETCH_DENSE = 0, RNLA_SKETCH_SASO = 1, RNLA_SKETCH_SASO_BLOCK = 2 } rnla_sketch_kind;
 /* d = sketch dimension rule of the reference: blendenpik/lsrn (:49,:105) rule 0, saddle point (:172) rule 1 */
 int64_t rnla_sketch_dim(int64_t m, int64_t n, double sampling_factor, int32_t rule);
 /* A_sk (d x n) = S A, b_sk (d x nrhs) = S b with S (d x m): dense i.i.d. `dist`, or sparse-sign with zeta nonzeros per column.

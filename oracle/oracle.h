@@ -67,6 +67,8 @@ int64_t orc_sketch_dim(int64_t m, int64_t n, double sampling_factor, int rule);
 void orc_sketch_apply_dense(int dist, uint64_t seed, int64_t d, const double* A, int64_t m, int64_t n, double* A_sk);
 /* sparse sign: zeta non-zeros per column of S */
 void orc_sketch_apply_saso(uint64_t seed, int64_t d, int zeta, const double* A, int64_t m, int64_t n, double* A_sk);
+void orc_sketch_apply_saso_block(uint64_t seed, int64_t d, int zeta, int w, const double* A, int64_t m, int64_t n,
+                                 int64_t row_off, double* A_sk);
 
 void orc_set_threads(int nthreads);
 int orc_get_threads(void);

@@ -251,6 +251,14 @@ def sketch_apply_saso(A, d, zeta=8, seed=0):
     return out
 
 
+def sketch_apply_saso_block(A, d, zeta=8, seed=0, row_off=0, width=0):
+    A = F(A); m, n = A.shape
+    out = np.empty((d, n), order="F")
+    w = width if width else min(zeta, 4)
+    load().orc_sketch_apply_saso_block(u64(seed), i64(d), C.c_int(zeta), C.c_int(w), p(A), i64(m), i64(n), i64(row_off), p(out))
+    return out
+
+
 def set_threads(n):
     load().orc_set_threads(C.c_int(n))
 

@@ -638,3 +638,52 @@ void orc_sketch_apply_saso(uint64_t seed, int64_t d, int zeta, const double* A, 
     }
     for (int64_t i = 0; i < d * n; ++i) A_sk[i] *= scale;
 }
+
+/* Block sparse-sign operator (kind RNLA_SKETCH_SASO_BLOCK; not in the reference, SURVEY.md Appendix A.9 -- the
+ * operator is defined by this build, DESIGN.md section 5, and restated here independently of the CUDA source).
+ * zeta = g * w non-zeros per column: g groups ("stripes") of w consecutive rows each.  Stripe t owns output rows
+ * [t*nbs*w, (t+1)*nbs*w), nbs = d / (g*w) blocks of width w.  Global row gr: chunk q = gr / 2048, x = gr % 2048.
+ * Two Philox blocks per (chunk, stripe), ctr = (q_lo, q_hi, 2t, 5) -> k and (q_lo, q_hi, 2t+1, 5) -> k2, key a
+ * bijection sigma on [0, 2048): with y = 16 yh + yl,  sigma(y) = 16 tau(yh) + (mo * yl + rho(yh)) mod 16, where tau is
+ * three multiply-xorshift rounds on 7 bits keyed by k0..k2, mo = (k2[0] & 15) | 1, rho(yh) = (((yh+1) * (k2[1]|1)) >> 11) & 15
+ * (sixteen consecutive slots hit sixteen different residues mod 16: shared-memory banks on the device).  The block
+ * offset is off = 16 * ((k3 % nbs) / 16).  Slot y holds row x = sigma(y) and feeds block (y + off) % nbs of stripe t;
+ * the w entries are rows (t*nbs + block)*w + r with sign bit (t*w + r) of word 0 of philox(ctr = (gr_lo, gr_hi, 1, 5));
+ * value 1/sqrt(zeta).
+ * Rows of A are global rows row_off .. row_off + m - 1 (so a row shard reproduces its slice of the operator). */
+void orc_sketch_apply_saso_block(uint64_t seed, int64_t d, int zeta, int w, const double* A, int64_t m, int64_t n,
+                                 int64_t row_off, double* A_sk) {
+    memset(A_sk, 0, (size_t)(d * n) * sizeof(double));
+    if (m <= 0) return;
+    const int g = zeta / w;
+    const int64_t R = 2048, nbs = d / zeta;
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const double scale = 1.0 / sqrt((double)zeta);
+    for (int64_t q = row_off / R; q <= (row_off + m - 1) / R; ++q)
+        for (int t = 0; t < g; ++t) {
+            const uint32_t ctr[4] = {(uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)(2 * t), 5u};
+            const uint32_t ctr2[4] = {(uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)(2 * t + 1), 5u};
+            uint32_t k[4], k2[4]; orc_philox4x32_10(ctr, key, k); orc_philox4x32_10(ctr2, key, k2);
+            const int64_t off = (int64_t)(((k[3] % (uint32_t)nbs) >> 4) << 4);
+            const uint32_t mo = (k2[0] & 15u) | 1u, rk = k2[1] | 1u;
+            for (int64_t y = 0; y < R; ++y) {
+                const uint32_t yh = (uint32_t)y >> 4, yl = (uint32_t)y & 15u;
+                uint32_t h = yh;
+                h = (h * (k[0] | 1u) + (k[0] >> 16)) & 127u; h ^= h >> 3;
+                h = (h * (k[1] | 1u) + (k[1] >> 16)) & 127u; h ^= h >> 4;
+                h = (h * (k[2] | 1u) + (k[2] >> 16)) & 127u; h ^= h >> 2;
+                const uint32_t rho = (((yh + 1u) * rk) >> 11) & 15u;
+                const uint32_t x = (h << 4) | ((yl * mo + rho) & 15u);
+                const int64_t gr = q * R + (int64_t)x;
+                if (gr < row_off || gr >= row_off + m) continue;
+                const int64_t blk = (int64_t)t * nbs + (y + off) % nbs;
+                const uint32_t cs[4] = {(uint32_t)gr, (uint32_t)((uint64_t)gr >> 32), 1u, 5u};
+                uint32_t sw[4]; orc_philox4x32_10(cs, key, sw);
+                for (int64_t c = 0; c < n; ++c) {
+                    const double v = AT(A, m, gr - row_off, c);
+                    for (int r = 0; r < w; ++r) AT(A_sk, d, blk * w + r, c) += ((sw[0] >> (t * w + r)) & 1u) ? -v : v;
+                }
+            }
+        }
+    for (int64_t i = 0; i < d * n; ++i) A_sk[i] *= scale;
+}

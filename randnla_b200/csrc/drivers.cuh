@@ -28,6 +28,10 @@ rnla_status dev_rand_evd1(const double* A, int64_t lda, int64_t m_local, int64_t
 rnla_status dev_rand_evd2(const double* A, int64_t lda, int64_t m_local, int64_t n, int64_t k, int64_t s,
                           const rnla_options& o, double* V, int64_t ldv, double* Lambda, int64_t* r_out);
 
+// saso_block.cu: block sparse-sign sketch, A_sk fully overwritten with S A_local
+rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const double* A, int64_t lda, int64_t m_local,
+                             int64_t n, int64_t row_off, double* Ask, int64_t ldk);
+
 // literal.cu: bug-compatible pieces of the reference
 rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
                           const rnla_options& o, double* S);

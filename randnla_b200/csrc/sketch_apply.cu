@@ -173,6 +173,19 @@ rnla_status dev_sketch_apply(int kind, int dist, uint64_t seed, int64_t d, int z
         }
         return RNLA_OK;
     }
+    if (kind == RNLA_SKETCH_SASO_BLOCK) {
+        PhaseScope ph("sketch:saso_block");
+        const bool ar = c.nranks > 1;
+        DevBuf packed;
+        double* out = dAsk; int64_t ldo = ldk;
+        if (ar && ldk != d) { RNLA_CUDA(packed.alloc((size_t)d * n * 8)); out = packed.d(); ldo = d; }
+        RNLA_TRY(saso_block_apply(seed, d, zeta, dist /* block width, 0 = default */, dA, lda, m_local, n, row_offset, out, ldo));
+        if (ar) {
+            RNLA_TRY(allreduce_sum_f64(out, (size_t)d * n));
+            if (out != dAsk) RNLA_CUDA(copy_matrix(out, ldo, dAsk, ldk, d, n, c.stream));
+        }
+        return RNLA_OK;
+    }
     return fail(RNLA_ERR_INVALID_PARAMETERS, "unknown sketch kind");
 }
 

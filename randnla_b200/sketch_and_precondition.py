@@ -10,7 +10,7 @@ from ._lib import check
 from . import runtime
 from .errors import InvalidParameters, NotOverdetermined
 
-SKETCH_DENSE, SKETCH_SASO = 0, 1
+SKETCH_DENSE, SKETCH_SASO, SKETCH_SASO_BLOCK = 0, 1, 2
 
 
 def _validate(a, epsilon, l, sampling_factor):
@@ -30,9 +30,12 @@ def sketch_dim(m, n, sampling_factor, saddle=False):
     return int(_lib.load().rnla_sketch_dim(int(m), int(n), float(sampling_factor), 1 if saddle else 0))
 
 
-def sketch_apply(a, b=None, d=None, kind=SKETCH_DENSE, dist=runtime.GAUSSIAN, seed=0, zeta=8):
-    """A_sk = S a (d x n) and b_sk = S b for a dense i.i.d. or sparse-sign S (d x m)."""
+def sketch_apply(a, b=None, d=None, kind=SKETCH_DENSE, dist=runtime.GAUSSIAN, seed=0, zeta=8, width=0):
+    """A_sk = S a (d x n) and b_sk = S b for a dense i.i.d. or sparse-sign S (d x m).
+    For SKETCH_SASO_BLOCK `width` is the block width w (0 = default), carried in the C ABI's `dist` slot."""
     lib = _lib.load()
+    if kind == SKETCH_SASO_BLOCK:
+        dist = width
     a = runtime.as_f(a)
     m, n = a.shape
     a_sk = np.empty((d, n), dtype=np.float64, order="F")

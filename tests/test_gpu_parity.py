@@ -437,6 +437,83 @@ def test_sketch_step_dense_and_saso(rb, orc):
     assert 0.6 < (s_sk / s_full).min() and (s_sk / s_full).max() < 1.4
 
 
+@pytest.mark.parametrize("zeta,width", [(8, 0), (8, 4), (8, 2), (8, 1), (4, 4), (4, 1), (2, 2), (1, 1)])
+def test_sketch_saso_block_matches_oracle(rb, orc, zeta, width):
+    """block sparse-sign operator (K6b): same operator on the device and in the oracle's independent restatement"""
+    from randnla_b200 import sketch_and_precondition as sp
+    A = random_matrix(5000, 37, seed=11)
+    for d in (200, 203):                                   # 203: d not a multiple of zeta -> trailing zero rows
+        got = sp.sketch_apply(A, None, d, kind=sp.SKETCH_SASO_BLOCK, zeta=zeta, seed=3, width=width)
+        ref = orc.sketch_apply_saso_block(A, d, zeta=zeta, seed=3, width=width)
+        assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max() * 50
+    # the operator itself: S = S I has exactly zeta non-zeros +-1/sqrt(zeta) per column
+    S = sp.sketch_apply(np.eye(600), None, 64, kind=sp.SKETCH_SASO_BLOCK, zeta=zeta, seed=9, width=width)
+    assert ((S != 0).sum(axis=0) == zeta).all()
+    assert np.allclose(np.abs(S[S != 0]), 1 / np.sqrt(zeta), rtol=0, atol=1e-16)
+    assert S.tobytes() == orc.sketch_apply_saso_block(np.eye(600), 64, zeta=zeta, seed=9, width=width).tobytes()
+
+
+@pytest.mark.parametrize("m,n,d", [(5001, 3, 200), (4099, 9, 8000), (6000, 5, 16384), (2049, 1, 8), (70000, 6, 4000)])
+def test_sketch_saso_block_shapes(rb, orc, m, n, d):
+    """odd row counts (no bulk copies), one thread owning several blocks (d = 8000, 16384), tiny d (parts > 1),
+    many chunks with row splits"""
+    from randnla_b200 import sketch_and_precondition as sp
+    A = random_matrix(m, n, seed=m % 97)
+    got = sp.sketch_apply(A, None, d, kind=sp.SKETCH_SASO_BLOCK, zeta=8, seed=1)
+    ref = orc.sketch_apply_saso_block(A, d, zeta=8, seed=1)
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max() * 100
+
+
+def test_sketch_saso_block_row_shards_and_views(rb, orc):
+    """a row shard applies its own slice of the operator (global row offsets), with padded leading dimensions"""
+    import torch
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    m, n, d = 9000, 11, 400
+    A = random_matrix(m, n, seed=21)
+    ref = orc.sketch_apply_saso_block(A, d, zeta=8, seed=4)
+    total = np.zeros((d, n))
+    for lo, hi in ((0, 2300), (2300, 6148), (6148, 9000), (0, 0)):
+        big = rt.empty_colmajor(hi - lo + 6, n)            # lda = rows + 6
+        sub = big[: hi - lo, :]
+        sub.copy_(torch.from_numpy(np.ascontiguousarray(A[lo:hi])))
+        out = rt.empty_colmajor(d + 3, n)[:d, :]
+        pA, lda = rt.dev_ptr_ld(sub) if hi > lo else (C.c_void_p(big.data_ptr()), hi - lo + 6)
+        pO, ldo = rt.dev_ptr_ld(out)
+        _lib.check(lib.rnla_sketch_apply_dev(2, 0, 4, d, 8, pA, lda, hi - lo, n, lo, pO, ldo))
+        rt.synchronize()
+        part = out.cpu().numpy()
+        assert np.abs(part - orc.sketch_apply_saso_block(A[lo:hi], d, zeta=8, seed=4, row_off=lo)).max() <= 1e-12
+        total += part
+    assert np.abs(total - ref).max() <= 1e-12 * np.abs(ref).max() * 10
+    # odd offset: the cooperative-load variant
+    lo, hi = 1001, 5000
+    sub = rt.to_device_colmajor(A[lo:hi]); out = rt.empty_colmajor(d, n)
+    pA, lda = rt.dev_ptr_ld(sub); pO, ldo = rt.dev_ptr_ld(out)
+    _lib.check(lib.rnla_sketch_apply_dev(2, 0, 4, d, 8, pA, lda, hi - lo, n, lo, pO, ldo)); rt.synchronize()
+    assert np.abs(out.cpu().numpy() - orc.sketch_apply_saso_block(A[lo:hi], d, zeta=8, seed=4, row_off=lo)).max() <= 1e-12
+
+
+def test_sketch_saso_block_errors_and_embedding(rb, orc):
+    from randnla_b200 import sketch_and_precondition as sp
+    from randnla_b200.errors import InvalidParameters, InvalidDimensions
+    A = random_matrix(3000, 20, seed=2)
+    with pytest.raises(InvalidParameters):
+        sp.sketch_apply(A, None, 100, kind=sp.SKETCH_SASO_BLOCK, zeta=3)
+    with pytest.raises(InvalidParameters):
+        sp.sketch_apply(A, None, 100, kind=sp.SKETCH_SASO_BLOCK, zeta=4, width=8)
+    with pytest.raises(InvalidDimensions):
+        sp.sketch_apply(A, None, 20000, kind=sp.SKETCH_SASO_BLOCK, zeta=8)
+    with pytest.raises(InvalidDimensions):
+        sp.sketch_apply(A, None, 4, kind=sp.SKETCH_SASO_BLOCK, zeta=8)
+    # subspace embedding at d = 4n on an incoherent and on a coherent basis (100 heavy rows), default width
+    rng = np.random.default_rng(1)
+    for M in (rng.standard_normal((20000, 100)), np.vstack([100 * np.eye(100), 1e-2 * rng.standard_normal((19900, 100))])):
+        Q, _ = np.linalg.qr(M)
+        sv = np.linalg.svd(sp.sketch_apply(Q, None, 400, kind=sp.SKETCH_SASO_BLOCK, zeta=8, seed=0), compute_uv=False)
+        assert 0.25 < sv.min() and sv.max() < 1.8
+
+
 # ---------------------------------------------------------------- committed golden fixtures (oracle outputs)
 def test_golden_fixtures(rb):
     """tests/golden/*.npz were written by tests/golden/make_golden.py from the oracle; the GPU must reproduce them"""

@@ -342,3 +342,48 @@ def test_sketch_step(orc):
     assert np.abs(S @ A - Ask).max() < 1e-12
     assert np.allclose((S**2).sum(axis=0), 1.0) or ((S != 0).sum(axis=0) <= 8).all()
     assert abs(np.linalg.norm(Ask) / np.linalg.norm(A) - 1.0) < 0.2
+
+
+@pytest.mark.parametrize("zeta,width", [(8, 4), (8, 8), (8, 2), (8, 1), (4, 4), (2, 1), (1, 1)])
+def test_block_sparse_sign_operator_definition(orc, zeta, width):
+    """the block sparse-sign operator this build defines (the reference has no sparse sketch):
+    structure of S recovered from S I, balanced dealing per chunk, shard consistency"""
+    m, d = 5000, 240
+    g, nbs = zeta // width, d // zeta
+    S = orc.sketch_apply_saso_block(np.eye(m), d, zeta=zeta, seed=3, width=width)
+    assert ((S != 0).sum(axis=0) == zeta).all()
+    assert np.allclose(np.abs(S[S != 0]), 1 / np.sqrt(zeta), rtol=0, atol=1e-16)
+    assert 0.47 < (S > 0).sum() / (S != 0).sum() < 0.53
+    for j in range(0, m, 37):
+        rows = np.nonzero(S[:, j])[0]
+        for t in range(g):                                   # one aligned block of `width` rows in every stripe
+            blk = rows[t * width:(t + 1) * width]
+            assert blk[0] % width == 0 and (np.diff(blk) == 1).all()
+            assert t * nbs * width <= blk[0] < (t + 1) * nbs * width
+    # dealing: inside one chunk of 2048 rows every block of a stripe receives floor or ceil of 2048 / nbs rows
+    first = np.array([np.nonzero(S[:, j])[0][0] // width for j in range(2048)])
+    counts = np.bincount(first, minlength=nbs)[:nbs]
+    assert counts.min() >= 2048 // nbs and counts.max() <= -(-2048 // nbs)
+    A = random_matrix(m, 6, seed=8)
+    full = orc.sketch_apply_saso_block(A, d, zeta=zeta, seed=3, width=width)
+    assert np.abs(full - S @ A).max() < 1e-12
+    parts = orc.sketch_apply_saso_block(A[:2300], d, zeta, 3, 0, width) + orc.sketch_apply_saso_block(A[2300:], d, zeta, 3, 2300, width)
+    assert np.abs(full - parts).max() < 1e-12
+    # different seeds give different operators
+    assert (orc.sketch_apply_saso_block(np.eye(300), d, zeta, 4, 0, width) != S[:, :300]).any()
+
+
+def test_block_sparse_sign_embedding_quality(orc):
+    """subspace-embedding quality at d = 4n next to the textbook SASO: width <= 4 holds on a coherent basis,
+    width 8 (one block per column) does not -- the reason the default width is min(zeta, 4)"""
+    rng = np.random.default_rng(1)
+    Qi, _ = np.linalg.qr(rng.standard_normal((20000, 100)))
+    Qc, _ = np.linalg.qr(np.vstack([100 * np.eye(100), 1e-2 * rng.standard_normal((19900, 100))]))
+    sv = lambda M: np.linalg.svd(M, compute_uv=False)
+    for Q in (Qi, Qc):
+        t = sv(orc.sketch_apply_saso(Q, 400, zeta=8, seed=0))
+        assert 0.35 < t.min() and t.max() < 1.7
+        for w in (1, 2, 4):
+            b = sv(orc.sketch_apply_saso_block(Q, 400, zeta=8, seed=0, width=w))
+            assert 0.25 < b.min() and b.max() < 1.8
+    assert sv(orc.sketch_apply_saso_block(Qc, 400, zeta=8, seed=0, width=8)).min() < 0.1

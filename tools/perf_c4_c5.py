@@ -19,11 +19,19 @@ if which in ("c4", "both"):
     m, n = 1000000, 2000
     dA = rt.empty_colmajor(m, n); pA, lda = rt.dev_ptr_ld(dA)
     _lib.check(lib.rnla_sketch_fill_dev(0, 0, 77, 9, m, n, 0, pA, lda)); rt.synchronize()
-    for d, zeta in [(8000, 8), (8000, 4), (4000, 8)]:
+    for d, zeta in [(8000, 8)]:
         dS = rt.empty_colmajor(d, n); pS, lds = rt.dev_ptr_ld(dS)
         t = timed(lambda: _lib.check(lib.rnla_sketch_apply_dev(1, 0, 5, d, zeta, pA, lda, m, n, 0, pS, lds)))
         out[f"c4_saso_d{d}_z{zeta}"] = {"ms": t * 1e3, "A_stream_GBps": 8.0 * m * n / t * 1e-9, "frob_ratio": float(torch.linalg.vector_norm(dS) / torch.linalg.vector_norm(dA))}
         print(out[f"c4_saso_d{d}_z{zeta}"], flush=True)
+    for d, zeta, w in [(8000, 8, 4), (8000, 8, 2), (8000, 8, 1), (4000, 8, 4), (8000, 4, 4), (2000, 8, 4)]:
+        dS = rt.empty_colmajor(d, n); pS, lds = rt.dev_ptr_ld(dS)
+        t = timed(lambda: _lib.check(lib.rnla_sketch_apply_dev(2, w, 5, d, zeta, pA, lda, m, n, 0, pS, lds)), reps=5)
+        key = f"c4_saso_block_d{d}_z{zeta}_w{w}"
+        out[key] = {"ms": t * 1e3, "A_stream_GBps": 8.0 * m * n / t * 1e-9, "frob_ratio": float(torch.linalg.vector_norm(dS) / torch.linalg.vector_norm(dA)), "phases": rt.timings()[-3:]}
+        print(key, out[key], flush=True)
+    if "nodense" in sys.argv:
+        print(json.dumps(out)); sys.exit(0)
     d = 4000
     dS = rt.empty_colmajor(d, n); pS, lds = rt.dev_ptr_ld(dS)
     t = timed(lambda: _lib.check(lib.rnla_sketch_apply_dev(0, 0, 5, d, 0, pA, lda, m, n, 0, pS, lds)), reps=2)
