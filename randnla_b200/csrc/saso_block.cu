@@ -26,8 +26,8 @@
 //
 // Kernel: one CTA per (column group of CB columns) x (row split), 512 threads.  Thread 0 streams, per chunk, the CB
 // column segments (16 KB each, contiguous) and the chunk's slot tables (4 KB per stripe) with cp.async.bulk (TMA
-// engine) through a full/empty mbarrier ring (a dedicated producer warp would cap the kernel at 96 registers per
-// thread); all 512 threads each own BPT blocks (BPT * w * CB f64 accumulators
+// engine) into a ring of stages with one `full` mbarrier each; the last warp to finish a chunk refills its stage (a
+// dedicated producer warp would cap the kernel at 96 registers per thread); all 512 threads each own BPT blocks (BPT * w * CB f64 accumulators
 // in registers), walk their slots of the chunk, read A(x, c) from shared memory and apply the w signed updates as DFMAs.
 // HBM traffic: A exactly once (8 m n bytes) + d n 8 written; the slot tables (4 g bytes per row) are L2-resident.
 #include "drivers.cuh"
@@ -124,7 +124,8 @@ template <int W, int BPT, int CB, bool TMA>
 __global__ void __launch_bounds__(SB_T, 1)
 saso_block_kernel(const SbArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[SB_MAXSTAGES], empty_bar[SB_MAXSTAGES];
+    __shared__ uint64_t full_bar[SB_MAXSTAGES];
+    __shared__ int done_cnt[SB_MAXSTAGES];      // warps that have finished the chunk in a stage; the last one refills it
     const int tab_bytes = a.g * SB_TABW * (int)sizeof(sbtab_t);
     const int stage_bytes = SB_R * 8 * CB + tab_bytes;
     const int stages = a.stages;
@@ -147,7 +148,7 @@ saso_block_kernel(const SbArgs a) {
     }
     if (TMA) {
         if (tid == 0) {
-            for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], SB_T / 32); }
+            for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); done_cnt[s] = 0; }
             mbar_fence_init();
         }
     }
@@ -160,11 +161,10 @@ saso_block_kernel(const SbArgs a) {
         xlo = (int)(g0 - gbase); xhi = (int)(g1 - gbase); lr0 = g0 - a.row_off;
     };
 
-    // producer role (thread 0, in line with its consumer work): chunk ci goes to stage ci % stages; the copy for chunk
-    // ci + stages - 1 is issued at the top of iteration ci, once every warp has released the stage chunk ci - 1 used
+    // producer role: chunk ci goes to stage ci % stages.  Thread 0 fills the ring once; afterwards the LAST warp to finish
+    // a chunk (shared-memory counter) issues the copy that refills the stage, so nobody ever waits for a free stage.
     auto issue = [&](int ci) {
         const int s = ci % stages;
-        if (ci >= stages) mbar_wait(&empty_bar[s], ((ci / stages) - 1) & 1);
         int xlo, xhi; int64_t lr0;
         chunk_rows(ch0 + ci, xlo, xhi, lr0);
         unsigned char* st = smem_raw + (size_t)s * stage_bytes;
@@ -176,7 +176,7 @@ saso_block_kernel(const SbArgs a) {
         bulk_g2s(st + (size_t)SB_R * 8 * CB, a.tab + (ch0 + ci) * a.g * SB_TABW, (uint32_t)tab_bytes, &full_bar[s]);
     };
     if (TMA && tid == 0)
-        for (int ci = 0; ci < stages - 1 && ci < nch; ++ci) issue(ci);
+        for (int ci = 0; ci < stages && ci < nch; ++ci) issue(ci);
 
     // ---------------- consumers
     double acc[BPT][W][CB];
@@ -213,7 +213,6 @@ saso_block_kernel(const SbArgs a) {
         int xlo, xhi; int64_t lr0;
         chunk_rows(ch0 + ci, xlo, xhi, lr0);
         if (TMA) {
-            if (tid == 0 && ci + stages - 1 < nch) issue(ci + stages - 1);
             mbar_wait(&full_bar[s], ph);
         } else {
             // cooperative loads for inputs the bulk copy cannot take (odd leading dimension / offsets)
@@ -250,8 +249,7 @@ saso_block_kernel(const SbArgs a) {
                 for (int i = 0; i < BPT; ++i) {
                     if (!TAIL || y[i] < SB_R) {
                         const uint32_t e = tabs[tabo[i] + y[i]];
-                        const uint32_t xoff = (e << 3) & (uint32_t)((SB_R - 1) << 3);
-                        const unsigned char* src = reinterpret_cast<const unsigned char*>(tile) + xoff;
+                        const unsigned char* src = reinterpret_cast<const unsigned char*>(tile) + (e & (uint32_t)(SB_R - 1)) * 8u;
                         double v[CB];
 #pragma unroll
                         for (int c = 0; c < CB; ++c) v[c] = *reinterpret_cast<const double*>(src + (size_t)c * SB_R * 8);
@@ -287,7 +285,13 @@ saso_block_kernel(const SbArgs a) {
         }
         if (TMA) {
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);
+            if ((tid & 31) == 0) {
+                __threadfence_block();
+                if (atomicAdd(&done_cnt[s], 1) == SB_T / 32 - 1) {
+                    done_cnt[s] = 0;
+                    if (ci + stages < nch) issue(ci + stages);
+                }
+            }
         }
         if (++s == stages) { s = 0; ph ^= 1u; }
     }
@@ -368,6 +372,7 @@ template <int W, int BPT>
 cudaError_t sb_dispatch_cb(const SbArgs& a, int cb, int grid, bool tma, cudaStream_t st) {
     constexpr int CBMAX = SB_MAXACC / (W * BPT);
     if constexpr (CBMAX >= 4) { if (cb == 4) return sb_launch<W, BPT, 4>(a, grid, tma, st); }
+    if constexpr (W == 4 && BPT == 4) { if (cb == 3) return sb_launch<W, BPT, 3>(a, grid, tma, st); }   // 48 accumulators: 126 registers
     if constexpr (CBMAX >= 2) { if (cb == 2) return sb_launch<W, BPT, 2>(a, grid, tma, st); }
     if (cb == 1) return sb_launch<W, BPT, 1>(a, grid, tma, st);
     return cudaErrorInvalidValue;
@@ -407,6 +412,7 @@ rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const do
         return fail(RNLA_ERR_INVALID_DIMENSIONS, "block SASO: sketch dimension d must be <= 16384");
     int cb = SB_MAXACC / (bpt * w);
     cb = cb >= 4 ? 4 : cb >= 2 ? 2 : 1;
+    if (bpt * w == 16 && w == 4 && n >= 3) cb = 3;   // w < 4 spills at 48 accumulators
     while (cb > 1 && cb / 2 >= n) cb /= 2;
     while (cb > 1 && SB_SMEM / (SB_R * 8 * cb + g * SB_TABW * (int)sizeof(sbtab_t)) < 2) cb /= 2;
     const int parts = nbt64 < SB_T ? (int)(SB_T / nbt64) : 1;
