@@ -410,13 +410,21 @@ rnla_status rnla_small_svd_dev(const double* dM, int64_t ldm, int64_t p, double*
     RNLA_TRY(ensure_ctx());
     Ctx& c = ctx();
     if (p <= 0 || p > 1024) return fail(RNLA_ERR_INVALID_DIMENSIONS, "small_svd: 1 <= p <= 1024");
-    DevBuf work, info;
-    RNLA_CUDA(work.alloc((2 * (size_t)p * p + (size_t)p) * 8)); RNLA_CUDA(info.alloc(8));
-    RNLA_CUDA(jacobi_svd(dM, ldm, (int)p, dU, p, dSigma, dV, p, work.d(), info.as<int>(), c.stream));
+    // the same route the drivers take for B: M = Q R (CholeskyQR2 with deficiency handling), one-sided Jacobi on R^T
+    // (R = Ur diag(sigma) Vr^T), U = Q Ur, V = Vr
+    DevBuf Q, R, Ur, work, info;
+    RNLA_CUDA(Q.alloc((size_t)p * p * 8)); RNLA_CUDA(R.alloc((size_t)p * p * 8)); RNLA_CUDA(Ur.alloc((size_t)p * p * 8));
+    RNLA_CUDA(work.alloc(jacobi_svd_work_doubles((int)p) * 8)); RNLA_CUDA(info.alloc(8));
+    RNLA_CUDA(copy_matrix(dM, ldm, Q.d(), p, p, p, c.stream));
+    ShardInfo sh{p, 0, p};
+    RNLA_TRY(orth_inplace(Q.d(), p, sh, (int)p, false, R.d(), nullptr));
+    RNLA_CUDA(jacobi_svd(R.d(), p, (int)p, Ur.d(), p, dSigma, dV, p, work.d(), info.as<int>(), c.stream, 1));
     int h[2];
     RNLA_CUDA(cudaMemcpyAsync(h, info.p, 8, cudaMemcpyDeviceToHost, c.stream));
     RNLA_CUDA(cudaStreamSynchronize(c.stream));
     if (h[1]) return fail(RNLA_ERR_MATRIX_DECOMPOSITION, "SVD decomposition failed");
+    RNLA_TRY(dev_gemm_nn(Q.d(), p, p, p, Ur.d(), p, p, dU, p));
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
     return RNLA_OK;
 }
 rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double* dW, double* dLambda) {

@@ -288,9 +288,9 @@ static rnla_status tall_svd(double* X, int64_t ldx, const ShardInfo& sh, int p, 
     Ctx& c = ctx();
     const size_t pp = (size_t)p * p;
     DevBuf R, work, info;
-    RNLA_CUDA(R.alloc(pp * 8)); RNLA_CUDA(work.alloc((2 * pp + (size_t)p) * 8)); RNLA_CUDA(info.alloc(8));
+    RNLA_CUDA(R.alloc(pp * 8)); RNLA_CUDA(work.alloc(jacobi_svd_work_doubles(p) * 8)); RNLA_CUDA(info.alloc(8));
     RNLA_TRY(orth_inplace(X, ldx, sh, p, sharded, R.d(), nullptr));
-    RNLA_CUDA(jacobi_svd(R.d(), p, p, Ur, p, sigma, Vr, p, work.d(), info.as<int>(), c.stream));
+    RNLA_CUDA(jacobi_svd(R.d(), p, p, Ur, p, sigma, Vr, p, work.d(), info.as<int>(), c.stream, 1 /* sweeps on R^T */));
     int hinfo[2];
     RNLA_CUDA(cudaMemcpyAsync(hinfo, info.p, 8, cudaMemcpyDeviceToHost, c.stream));
     RNLA_TRY(sync_stream());

@@ -3,6 +3,7 @@
 #include "panel.cuh"
 #include "gemm.cuh"
 #include "rng.cuh"
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -269,56 +270,141 @@ __device__ __forceinline__ void rr_pair(int round, int idx, int P, int& a, int& 
 
 constexpr int JACOBI_MAX_SWEEPS = 40;
 
-__global__ void __launch_bounds__(1024)
-jacobi_svd_kernel(const double* __restrict__ M, int64_t ldm, int p, double* __restrict__ U, int64_t ldu,
-                  double* __restrict__ sigma, double* __restrict__ Vout, int64_t ldv, double* __restrict__ work, int* info) {
-    double* W = work;                    // p x p, ld p
-    double* V = work + (size_t)p * p;    // p x p, ld p
-    __shared__ int s_rot;
-    __shared__ int s_sweeps, s_conv;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+// Reciprocal, reciprocal square root and square root for the rotation parameters: the MUFU.RCP64H / RSQ64H seeds
+// (~20 bits, full double exponent range) plus two Newton steps, a few ulp -- the IEEE division and square root of the
+// math library are ~10x longer dependent chains, and the rotation parameters sit on the critical path of every round.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0); y = fma(y, e, y);
+    e = fma(-x, y, 1.0); y = fma(y, e, y);
+    return y;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {     // x > 0, normal
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = 0.5 * x;
+    r = r * fma(-h * r, r, 1.5);
+    r = r * fma(-h * r, r, 1.5);
+    return r;
+}
+__device__ __forceinline__ double fast_sqrt(double x) {      // x >= 0
+    if (!(x > DBL_MIN)) return sqrt(x);
+    const double r = fast_rsqrt(x);
+    double s = x * r;
+    s = fma(fma(-s, s, x), 0.5 * r, s);                      // one correction step on the root itself
+    return s;
+}
+
+// One-sided (Hestenes) Jacobi, blocked for shared memory.  W (p x p, ld p) starts as M and V as I, both in global
+// `work`; the columns are cut into blocks of b columns and one CTA orthogonalises the union of two blocks (2b columns of
+// W and of V, 32 b p bytes) entirely in shared memory with a cyclic round-robin sweep, one warp per column pair.  Block
+// pairs of one round-robin round are disjoint and run on different CTAs; rounds are separate launches.  When the whole
+// matrix fits (2b >= p, e.g. p = 110 at the headline size) a single CTA runs every sweep without leaving shared memory.
+// flags[0] = some rotation happened in this sweep; single mode also sets flags[1] = sweeps, flags[2] = converged.
+__global__ void __launch_bounds__(256)
+jacobi_init_kernel(const double* __restrict__ M, int64_t ldm, int p, int transpose, double* __restrict__ W,
+                   double* __restrict__ V, int* flags) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p * p; idx += gridDim.x * blockDim.x) {
         const int c = idx / p, r = idx - c * p;
-        W[idx] = M[r + (int64_t)c * ldm];
+        W[idx] = transpose ? M[c + (int64_t)r * ldm] : M[r + (int64_t)c * ldm];
         V[idx] = (r == c) ? 1.0 : 0.0;
     }
-    if (tid == 0) { s_sweeps = 0; s_conv = 0; }
+    if (blockIdx.x == 0 && threadIdx.x < 4) flags[threadIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(1024)
+jacobi_block_kernel(double* __restrict__ W, double* __restrict__ V, int p, int b, int nblocks, int NB, int round,
+                    int max_inner, int single, int* __restrict__ flags) {
+    extern __shared__ double jsm[];
+    __shared__ int s_rot, s_first;
+    const int tid = threadIdx.x;
+    int I = 0, J = 1;
+    if (!single) {
+        rr_pair(round, blockIdx.x, NB, I, J);
+        if (J >= nblocks) return;                   // padding block: block I sits this round out
+    }
+    const int i0 = I * b, i1 = min(p, i0 + b), j0 = J * b, j1 = max(j0, min(p, j0 + b));
+    const int nI = i1 - i0, nc = nI + (j1 - j0);
+    double* sW = jsm;
+    double* sV = jsm + (size_t)nc * p;
+    for (int idx = tid; idx < nc * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        const int gc = c < nI ? i0 + c : j0 + (c - nI);
+        sW[idx] = W[(size_t)gc * p + r];
+        sV[idx] = V[(size_t)gc * p + r];
+    }
+    if (tid == 0) s_first = 0;
     __syncthreads();
-    const int P = (p & 1) ? p + 1 : p;
+    const int NC = (nc & 1) ? nc + 1 : nc;
     const double tol = sqrt((double)(p > 1 ? p : 1)) * DBL_EPSILON;
-    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS && P >= 2; ++sweep) {
+    int sweeps = 0, conv = 0;
+    // one 16-lane group per column pair: nc <= 128 columns give <= 64 pairs, so a round is a single pass of the 64 groups
+    const int l16 = tid & 15, grp = tid >> 4, ngrp = blockDim.x >> 4;
+    for (int sw = 0; sw < max_inner && NC >= 2; ++sw) {
         if (tid == 0) s_rot = 0;
         __syncthreads();
-        for (int round = 0; round < P - 1; ++round) {
-            for (int pi = warp; pi < P / 2; pi += nwarps) {
-                int a, b; rr_pair(round, pi, P, a, b);
-                if (b >= p) continue;
-                double* wa = W + (size_t)a * p; double* wb = W + (size_t)b * p;
+        for (int rd = 0; rd < NC - 1; ++rd) {
+            for (int pi0 = 0; pi0 < NC / 2; pi0 += ngrp) {          // uniform trip count: the shuffles below need whole warps
+                const int pi = pi0 + grp;
+                int ca = 0, cb = 0;
+                bool valid = pi < NC / 2;
+                if (valid) { rr_pair(rd, pi, NC, ca, cb); valid = cb < nc; }
+                double* wa = sW + (size_t)ca * p; double* wb = sW + (size_t)cb * p;
                 double al = 0.0, be = 0.0, ga = 0.0;
-                for (int k = lane; k < p; k += 32) { const double x = wa[k], y = wb[k]; al += x * x; be += y * y; ga += x * y; }
-                al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-                if (fabs(ga) > tol * sqrt(al * be) && fabs(ga) > DBL_MIN) {
-                    const double zeta = (be - al) / (2.0 * ga);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-                    double* va = V + (size_t)a * p; double* vb = V + (size_t)b * p;
-                    for (int k = lane; k < p; k += 32) {
+                if (valid)
+                    for (int k = l16; k < p; k += 16) { const double x = wa[k], y = wb[k]; al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga); }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    al += __shfl_xor_sync(0xffffffffu, al, o);
+                    be += __shfl_xor_sync(0xffffffffu, be, o);
+                    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+                }
+                const double aga = fabs(ga);
+                if (valid && aga > DBL_MIN && aga > tol * (fast_sqrt(al) * fast_sqrt(be))) {
+                    const double zeta = (be - al) * fast_rcp(2.0 * ga);
+                    const double az = fabs(zeta);
+                    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)); beyond 1e8 the square root is |zeta| to the last bit
+                    const double t = az > 1e8 ? 0.5 * fast_rcp(zeta) : copysign(fast_rcp(az + fast_sqrt(fma(zeta, zeta, 1.0))), zeta);
+                    const double cs = fast_rsqrt(fma(t, t, 1.0)), sn = cs * t;
+                    double* va = sV + (size_t)ca * p; double* vb = sV + (size_t)cb * p;
+                    for (int k = l16; k < p; k += 16) {
                         const double x = wa[k], y = wb[k];
                         wa[k] = cs * x - sn * y; wb[k] = sn * x + cs * y;
                         const double vx = va[k], vy = vb[k];
                         va[k] = cs * vx - sn * vy; vb[k] = sn * vx + cs * vy;
                     }
-                    if (lane == 0) s_rot = 1;
+                    if (l16 == 0) s_rot = 1;
                 }
             }
             __syncthreads();
         }
         const int rot = s_rot;
+        if (tid == 0 && sw == 0) s_first = rot;
         __syncthreads();
-        if (tid == 0) s_sweeps = sweep + 1;
-        if (!rot) { if (tid == 0) s_conv = 1; break; }
+        sweeps = sw + 1;
+        if (!rot) { conv = 1; break; }
     }
-    __syncthreads();
+    for (int idx = tid; idx < nc * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        const int gc = c < nI ? i0 + c : j0 + (c - nI);
+        W[(size_t)gc * p + r] = sW[idx];
+        V[(size_t)gc * p + r] = sV[idx];
+    }
+    if (tid == 0) {
+        if (s_first) atomicOr(&flags[0], 1);
+        if (single) { flags[1] = sweeps; flags[2] = (conv || NC < 2) ? 1 : 0; }
+    }
+}
+
+// sigma, ordering, U = W / sigma, orthonormal completion; W, V as left by the sweeps.  flags -> info
+__global__ void __launch_bounds__(1024)
+jacobi_svd_finish_kernel(int p, double* __restrict__ U, int64_t ldu, double* __restrict__ sigma, double* __restrict__ Vout,
+                         int64_t ldv, double* __restrict__ work, const int* __restrict__ flags, int* info) {
+    double* W = work;                    // p x p, ld p
+    double* V = work + (size_t)p * p;    // p x p, ld p
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int s_sweeps = flags[1], s_conv = flags[2];
     // column norms -> sigma (unsorted, stored temporarily in sigma[]), then rank by value (stable, descending)
     for (int j = warp; j < p; j += nwarps) {
         double s = 0.0;
@@ -572,9 +658,62 @@ cudaError_t scale_columns(double* X, int64_t ld, int64_t rows, int64_t cols, con
     scale_columns_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(X, ld, rows, cols, s);
     return LAUNCHED();
 }
+size_t jacobi_svd_work_doubles(int p) { return 2 * (size_t)p * p + (size_t)p + 8; }
+
 cudaError_t jacobi_svd(const double* M, int64_t ldm, int p, double* U, int64_t ldu, double* sigma,
-                       double* V, int64_t ldv, double* work, int* info, cudaStream_t st) {
-    jacobi_svd_kernel<<<1, 1024, 0, st>>>(M, ldm, p, U, ldu, sigma, V, ldv, work, info);
+                       double* V, int64_t ldv, double* work, int* info, cudaStream_t st, int transpose) {
+    constexpr int JSMEM = 224 * 1024;
+    double* W = work;
+    double* Vw = work + (size_t)p * p;
+    int* flags = reinterpret_cast<int*>(work + 2 * (size_t)p * p + (size_t)p);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JSMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    jacobi_init_kernel<<<grid_for((int64_t)p * p, 256), 256, 0, st>>>(M, ldm, p, transpose, W, Vw, flags);
+    ++g_kernel_launches;
+    if (16 * (size_t)p * p <= (size_t)JSMEM) {
+        // everything fits: two "blocks" [0, b) and [b, p), every sweep inside one CTA
+        const int b = (p + 1) / 2;
+        jacobi_block_kernel<<<1, 1024, 16 * (size_t)p * p + 16, st>>>(W, Vw, p, b, 2, 2, 0, JACOBI_MAX_SWEEPS, 1, flags);
+        ++g_kernel_launches;
+    } else {
+        // block width: a block pair must fit one SM's shared memory, but the sweep is bound by that SM's shared-memory
+        // bandwidth (80 bytes move per element of a column pair), so ~20 narrower blocks spread a round over ~10 SMs
+        int b = (int)(JSMEM / (32 * (size_t)p));
+        if (b > 64) b = 64;
+        if (b < 1) return cudaErrorInvalidValue;
+        b = std::min(b, std::max(8, (p + 19) / 20));
+        const int nblocks = (p + b - 1) / b;
+        const int NB = (nblocks & 1) ? nblocks + 1 : nblocks;
+        int sweeps = 0, conv = 0;
+        for (; sweeps < JACOBI_MAX_SWEEPS; ) {
+            cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int), st);
+            if (e != cudaSuccess) return e;
+            for (int round = 0; round < NB - 1; ++round) {
+                jacobi_block_kernel<<<NB / 2, 1024, 32 * (size_t)b * p + 16, st>>>(W, Vw, p, b, nblocks, NB, round, 1, 0, flags);
+                ++g_kernel_launches;
+            }
+            ++sweeps;
+            int rot = 0;
+            e = cudaMemcpyAsync(&rot, flags, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            if (!rot) { conv = 1; break; }
+        }
+        const int h[2] = {sweeps, conv};
+        cudaError_t e = cudaMemcpyAsync(flags + 1, h, 2 * sizeof(int), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(st);      // h lives on this stack frame
+        if (e != cudaSuccess) return e;
+    }
+    // the sweeps factor W0 = X diag(sigma) Y^T with X from the rotated columns and Y the accumulated rotations;
+    // W0 = M^T swaps the roles of the two sides
+    if (transpose) jacobi_svd_finish_kernel<<<1, 1024, 0, st>>>(p, V, ldv, sigma, U, ldu, work, flags, info);
+    else jacobi_svd_finish_kernel<<<1, 1024, 0, st>>>(p, U, ldu, sigma, V, ldv, work, flags, info);
     return LAUNCHED();
 }
 cudaError_t jacobi_eigh(const double* C, int64_t ldc, int p, double* W, int64_t ldw, double* lambda,

