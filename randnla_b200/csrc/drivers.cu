@@ -108,7 +108,7 @@ rnla_status dev_gemm_tn(const double* A, int64_t lda, int64_t m, int64_t n, cons
 static const int ORTH_MAX_PASSES = 8;
 
 rnla_status orth_inplace(double* X, int64_t ldx, const ShardInfo& sh, int p, bool sharded, double* R_out /* p x p, ld p or null */,
-                         int64_t* deficient_out) {
+                         int64_t* deficient_out, int need_clean) {
     Ctx& c = ctx();
     const int64_t rows = sh.rows_local;
     const int64_t rows_global = sharded ? sh.rows_global : rows;
@@ -117,54 +117,48 @@ rnla_status orth_inplace(double* X, int64_t ldx, const ShardInfo& sh, int p, boo
     if (p <= 0) return RNLA_OK;
     if (rows_global < p) return fail(RNLA_ERR_INVALID_DIMENSIONS, "orth: panel has more columns than rows");
     const size_t pp = (size_t)p * p;
-    DevBuf G, Rinv, Rtot, Rtmp, X2, flags, info, target;
+    DevBuf G, Rinv, Rtot, Rtmp, X2, flags, info, state;
     RNLA_CUDA(G.alloc(pp * 8)); RNLA_CUDA(Rinv.alloc(pp * 8)); RNLA_CUDA(Rtot.alloc(pp * 8)); RNLA_CUDA(Rtmp.alloc(pp * 8));
     RNLA_CUDA(X2.alloc((size_t)std::max<int64_t>(rows, 1) * p * 8));
-    RNLA_CUDA(flags.alloc((size_t)p * 4)); RNLA_CUDA(info.alloc(8)); RNLA_CUDA(target.alloc((size_t)p * 8));
+    RNLA_CUDA(flags.alloc((size_t)p * 4)); RNLA_CUDA(info.alloc(16));
+    RNLA_CUDA(state.alloc((1 + 3 * ORTH_MAX_PASSES) * 4));                 // attempt counter, then (deficient, bad, zero) per pass
+    RNLA_CUDA(cudaMemsetAsync(state.p, 0, (1 + 3 * ORTH_MAX_PASSES) * 4, c.stream));
     if (R_out) RNLA_CUDA(set_identity(Rtot.d(), p, p, p, c.stream));
     double* cur = X; int64_t ldc = ldx;
     double* alt = X2.d(); int64_t lda = std::max<int64_t>(rows, 1);
     const double tol2 = 64.0 * p * (DBL_EPSILON / 2);
-    std::vector<int> hflags((size_t)p);
-    std::vector<int64_t> htarget((size_t)p);
-    int hinfo[2];
-    int clean = 0;
+    int hist[1 + 3 * ORTH_MAX_PASSES];
+    int clean = 0, seen = 0;
     int64_t total_def = 0;
-    int attempt = 0;
+    // Every pass is enqueued without a host round trip: the deficiency handling (flags from the Cholesky kernel, unit-vector
+    // replacement of exactly-zero columns, attempt counter) is device-driven.  The host looks at the per-pass history only
+    // after the second pass -- on a healthy panel that is the single synchronisation of a CholeskyQR2 -- and then after
+    // every further pass until `need_clean` consecutive passes were clean.  need_clean = 2 is CholeskyQR2 (orthonormal to
+    // working precision, Q of the Householder QR column for column); need_clean = 1 is a single CholeskyQR pass, enough for
+    // the stabiliser between power-iteration passes, whose only job is a well-conditioned basis of the same range (the
+    // Cholesky flags still force further passes on a panel with cond^2 > 1/(64 l u)).
     for (int pass = 0; pass < ORTH_MAX_PASSES; ++pass) {
         RNLA_TRY(dev_gemm_tn(cur, ldc, rows, p, cur, ldc, p, G.d(), p, sharded));
         RNLA_CUDA(chol_upper(G.d(), p, p, tol2, flags.as<int>(), info.as<int>(), c.stream));
-        RNLA_CUDA(cudaMemcpyAsync(hinfo, info.p, 8, cudaMemcpyDeviceToHost, c.stream));
-        RNLA_CUDA(cudaMemcpyAsync(hflags.data(), flags.p, (size_t)p * 4, cudaMemcpyDeviceToHost, c.stream));
-        RNLA_TRY(sync_stream());
-        if (hinfo[1]) return fail(RNLA_ERR_COMPUTATION, "orth: non-finite values in the panel");
         RNLA_CUDA(tri_inv_upper(G.d(), p, p, Rinv.d(), p, c.stream));
         RNLA_TRY(dev_gemm_nn(cur, ldc, rows, p, Rinv.d(), p, p, alt, lda));
-        int nzero = 0;
-        if (hinfo[0]) {
-            for (int j = 0; j < p; ++j) {
-                htarget[(size_t)j] = -1;
-                if (hflags[(size_t)j] == 2) {
-                    ++nzero;
-                    htarget[(size_t)j] = attempt == 0 ? (int64_t)j
-                                                      : (int64_t)(((uint64_t)j * 7919u + (uint64_t)attempt * 104729u + 13u) % (uint64_t)rows_global);
-                }
-            }
-            if (nzero) {
-                RNLA_CUDA(cudaMemcpyAsync(target.p, htarget.data(), (size_t)p * 8, cudaMemcpyHostToDevice, c.stream));
-                RNLA_CUDA(replace_columns(alt, lda, rows, row_off, p, flags.as<int>(), target.as<int64_t>(), c.stream));
-                RNLA_CUDA(zero_flagged_diag(G.d(), p, p, flags.as<int>(), c.stream));
-                ++attempt;
-            }
-            if (pass == 0) total_def = hinfo[0];
-        }
+        RNLA_CUDA(orth_fixup(alt, lda, rows, row_off, rows_global, p, flags.as<int>(), info.as<int>(), state.as<int>(),
+                             state.as<int>() + 1, pass, G.d(), p, c.stream));
         if (R_out) {
             RNLA_CUDA(small_gemm(G.d(), p, Rtot.d(), p, Rtmp.d(), p, p, p, p, c.stream));
             std::swap(Rtot.p, Rtmp.p);
         }
         std::swap(cur, alt); std::swap(ldc, lda);
-        clean = hinfo[0] ? 0 : clean + 1;
-        if (clean >= 2) break;
+        if (pass + 1 < need_clean) continue;
+        RNLA_CUDA(cudaMemcpyAsync(hist, state.p, (size_t)(1 + 3 * (pass + 1)) * 4, cudaMemcpyDeviceToHost, c.stream));
+        RNLA_TRY(sync_stream());
+        for (; seen <= pass; ++seen) {
+            const int* h = hist + 1 + 3 * seen;
+            if (h[1]) return fail(RNLA_ERR_COMPUTATION, "orth: non-finite values in the panel");
+            if (seen == 0) total_def = h[0];
+            clean = h[0] ? 0 : clean + 1;
+        }
+        if (clean >= need_clean) break;
         if (pass == ORTH_MAX_PASSES - 1)
             return fail(RNLA_ERR_MATRIX_DECOMPOSITION, "orth: CholeskyQR did not reach two clean passes");
     }
@@ -206,7 +200,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
         RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_M, m, l, sh.row_off, Ytmp, std::max<int64_t>(m, 1), c.stream));
         RNLA_TRY(dev_gemm_tn(A, lda, m, n, Ytmp, std::max<int64_t>(m, 1), l, S, n, true));
         done = 1;
-        if (done % pps == 0) RNLA_TRY(orth_inplace(S, n, nside, l, false, nullptr, nullptr));
+        if (done % pps == 0) RNLA_TRY(orth_inplace(S, n, nside, l, false, nullptr, nullptr, 1));
     }
     while (q - done >= 2) {
         {
@@ -220,13 +214,13 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
             virt = false;
         }
         ++done;
-        if (done % pps == 0) { PhaseScope ph("stab:Y"); RNLA_TRY(orth_inplace(Ytmp, std::max<int64_t>(m, 1), sh, l, true, nullptr, nullptr)); }
+        if (done % pps == 0) { PhaseScope ph("stab:Y"); RNLA_TRY(orth_inplace(Ytmp, std::max<int64_t>(m, 1), sh, l, true, nullptr, nullptr, 1)); }
         {
             PhaseScope ph("pass:At*Y");
             RNLA_TRY(dev_gemm_tn(A, lda, m, n, Ytmp, std::max<int64_t>(m, 1), l, S, n, true));
         }
         ++done;
-        if (done % pps == 0) { PhaseScope ph("stab:S"); RNLA_TRY(orth_inplace(S, n, nside, l, false, nullptr, nullptr)); }
+        if (done % pps == 0) { PhaseScope ph("stab:S"); RNLA_TRY(orth_inplace(S, n, nside, l, false, nullptr, nullptr, 1)); }
     }
     if (virt && !allow_virtual) {
         RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n, c.stream));
@@ -415,7 +409,7 @@ rnla_status dev_rand_evd2(const double* A, int64_t lda, int64_t m_local, int64_t
     RNLA_CUDA(S.alloc((size_t)n * l * 8)); RNLA_CUDA(Y.alloc((size_t)mm * l * 8)); RNLA_CUDA(B.alloc((size_t)mm * l * 8));
     RNLA_CUDA(SY.alloc((size_t)l * l * 8)); RNLA_CUDA(Rinv.alloc((size_t)l * l * 8));
     RNLA_CUDA(Ur.alloc((size_t)l * l * 8)); RNLA_CUDA(Vr.alloc((size_t)l * l * 8)); RNLA_CUDA(sig.alloc((size_t)l * 8));
-    RNLA_CUDA(flags.alloc((size_t)l * 4)); RNLA_CUDA(info.alloc(8)); RNLA_CUDA(scal.alloc(8)); RNLA_CUDA(scratch.alloc(1024 * 8));
+    RNLA_CUDA(flags.alloc((size_t)l * 4)); RNLA_CUDA(info.alloc(16)); RNLA_CUDA(scal.alloc(8)); RNLA_CUDA(scratch.alloc(1024 * 8));
     RNLA_TRY(dev_tsog1(A, lda, sh, n, l, q, pps, o, S.d()));
     {
         PhaseScope ph("pass:A*S");

@@ -13,7 +13,8 @@ rnla_status dev_sketch_gemm(const double* A, int64_t lda, int64_t m, int64_t K, 
                             int64_t N, double* C, int64_t ldc);
 rnla_status dev_gemm_tn(const double* A, int64_t lda, int64_t m, int64_t n, const double* Q, int64_t ldq, int64_t N,
                         double* Z, int64_t ldz, bool allreduce);
-rnla_status orth_inplace(double* X, int64_t ldx, const ShardInfo& sh, int p, bool sharded, double* R_out, int64_t* deficient_out);
+rnla_status orth_inplace(double* X, int64_t ldx, const ShardInfo& sh, int p, bool sharded, double* R_out, int64_t* deficient_out,
+                         int need_clean = 2);
 
 rnla_status dev_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
                       const rnla_options& o, double* S);

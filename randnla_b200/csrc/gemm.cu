@@ -388,6 +388,32 @@ tn_reduce_kernel(const double* __restrict__ P, int64_t ldp, int64_t pstride, int
     }
 }
 
+// same reduction for small outputs with many chunks (Gram matrices of tall panels: 110 x 110 outputs, ~370 chunks):
+// 8 threads share one output, thread g sums chunks g, g+8, ... and the 8 partial sums are combined in a fixed tree,
+// so the result is still independent of scheduling.  32 consecutive outputs per block keep the loads coalesced.
+__global__ void __launch_bounds__(256)
+tn_reduce_grouped_kernel(const double* __restrict__ P, int64_t ldp, int64_t pstride, int chunks,
+                         double* __restrict__ Z, int64_t ldz, int64_t n, int64_t N, int accumulate) {
+    __shared__ double sh[8][32];
+    const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t total = n * N;
+    const int64_t idx = (int64_t)blockIdx.x * 32 + o;
+    double s = 0.0;
+    if (idx < total) {
+        const int64_t j = idx / n, i = idx - j * n;
+        const double* src = P + i + j * ldp;
+        for (int c = g; c < chunks; c += 8) s += src[(int64_t)c * pstride];
+    }
+    sh[g][o] = s;
+    __syncthreads();
+    if (g == 0 && idx < total) {
+        const int64_t j = idx / n, i = idx - j * n;
+        const double t = ((sh[0][o] + sh[1][o]) + (sh[2][o] + sh[3][o])) + ((sh[4][o] + sh[5][o]) + (sh[6][o] + sh[7][o]));
+        double* d = Z + i + j * ldz;
+        *d = accumulate ? *d + t : t;
+    }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int NT, int GEN>
@@ -504,9 +530,13 @@ cudaError_t gemm_tn(const GemmTN& p, double* workspace, size_t workspace_bytes, 
     if (e != cudaSuccess) return e;
     if (pl.chunks > 1) {
         const int64_t total = p.n * p.N;
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > sms * 8) blocks = sms * 8;
-        tn_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, pl.ldp, pl.pstride, pl.chunks, p.Z, p.ldz, p.n, p.N, p.accumulate);
+        if (pl.chunks >= 16 && total <= (int64_t)sms * 8 * 32 * 4) {
+            tn_reduce_grouped_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(workspace, pl.ldp, pl.pstride, pl.chunks, p.Z, p.ldz, p.n, p.N, p.accumulate);
+        } else {
+            int blocks = (int)((total + 255) / 256);
+            if (blocks > sms * 8) blocks = sms * 8;
+            tn_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, pl.ldp, pl.pstride, pl.chunks, p.Z, p.ldz, p.n, p.N, p.accumulate);
+        }
         ++g_kernel_launches;
         e = cudaGetLastError();
     }

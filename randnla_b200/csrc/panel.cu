@@ -5,7 +5,10 @@
 #include "rng.cuh"
 #include <algorithm>
 #include <cfloat>
+#include <cooperative_groups.h>
 #include <cmath>
+
+namespace cg = cooperative_groups;
 
 namespace rnla {
 
@@ -85,9 +88,9 @@ __global__ void __launch_bounds__(1024)
 chol_upper_kernel(double* __restrict__ G, int64_t ld, int p, double tol2, int* __restrict__ flags, int* __restrict__ info) {
     __shared__ double s_red[32];
     __shared__ double s_piv;
-    __shared__ int s_def, s_ndef, s_bad;
+    __shared__ int s_def, s_ndef, s_bad, s_nzero;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    if (tid == 0) { s_ndef = 0; s_bad = 0; }
+    if (tid == 0) { s_ndef = 0; s_bad = 0; s_nzero = 0; }
     __syncthreads();
     for (int j = 0; j < p; ++j) {
         // pivot d = G_jj - sum_{k<j} R_kj^2
@@ -111,7 +114,7 @@ chol_upper_kernel(double* __restrict__ G, int64_t ld, int p, double tol2, int* _
                 const double piv = def ? 1.0 : sqrt(d);
                 G[j + j * ld] = piv;
                 flags[j] = def;
-                s_ndef += (def != 0);
+                s_ndef += (def != 0); s_nzero += (def == 2);
                 s_piv = piv; s_def = def;
             }
         }
@@ -130,7 +133,7 @@ chol_upper_kernel(double* __restrict__ G, int64_t ld, int p, double tol2, int* _
         const int c = idx / p, r = idx - c * p;
         if (r > c) G[r + (int64_t)c * ld] = 0.0;
     }
-    if (tid == 0) { info[0] = s_ndef; info[1] = s_bad; }
+    if (tid == 0) { info[0] = s_ndef; info[1] = s_bad; info[2] = s_nzero; }
 }
 
 __global__ void __launch_bounds__(1024)
@@ -147,6 +150,101 @@ tri_inv_upper_kernel(const double* __restrict__ R, int64_t ldr, int p, double* _
             if (lane == 0) x[i] = ((i == j ? 1.0 : 0.0) - s) / R[i + (int64_t)i * ldr];
             __syncwarp();
         }
+    }
+}
+
+// Shared-memory variants of the two kernels above.  Each of the p dependent steps of the global-memory versions costs an
+// L2 round trip, a block-wide reduction and an IEEE division (p = 110: 280 us per factorisation, 165 us per inverse).
+//   chol_upper_smem_kernel: right-looking Cholesky on the packed upper triangle (element (k, j), k <= j, at
+//     j(j+1)/2 + k; 177 KB at p = 210): per step one scalar pivot, a row scaling and a rank-1 update of the trailing
+//     triangle spread over the whole CTA -- no reductions.  Same deficiency rule and flags as chol_upper_kernel.
+//   tri_inv_upper_smem_kernel: R row-packed in shared memory, reciprocal diagonal precomputed, one 16-lane group per
+//     column of the inverse (64 columns in flight), private p-vector per group.
+__device__ __forceinline__ int pk(int k, int j) { return j * (j + 1) / 2 + k; }
+
+__global__ void __launch_bounds__(1024)
+chol_upper_smem_kernel(double* __restrict__ G, int64_t ld, int p, double tol2, int* __restrict__ flags, int* __restrict__ info) {
+    extern __shared__ double gs[];
+    double* diag0 = gs + (size_t)p * (p + 1) / 2;       // original diagonal
+    double* rowj = diag0 + p;                           // scaled row j, contiguous
+    __shared__ double s_inv;
+    __shared__ int s_def, s_ndef, s_bad, s_nzero;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        if (r <= c) { const double v = G[r + (int64_t)c * ld]; gs[pk(r, c)] = v; if (r == c) diag0[c] = v; }
+    }
+    if (tid == 0) { s_ndef = 0; s_bad = 0; s_nzero = 0; }
+    __syncthreads();
+    for (int j = 0; j < p; ++j) {
+        if (tid == 0) {
+            const double gjj = diag0[j];
+            const double d = gs[pk(j, j)];              // G_jj - sum_{k<j} R_kj^2 after the previous rank-1 updates
+            // 0 = regular column, 1 = numerically dependent on the previous ones (keeps its residual, re-examined in the
+            // next pass), 2 = exactly zero column (the caller replaces it)
+            int def = 0;
+            if (!(gjj > 0.0)) def = 2;
+            else if (!(d > tol2 * gjj)) def = 1;
+            if (!isfinite(gjj) || !isfinite(d)) { s_bad = 1; def = 2; }
+            const double piv = def ? 1.0 : sqrt(d);
+            gs[pk(j, j)] = piv;
+            flags[j] = def;
+            s_ndef += (def != 0); s_nzero += (def == 2);
+            s_inv = def ? 0.0 : 1.0 / piv; s_def = def;
+        }
+        __syncthreads();
+        const double inv = s_inv; const int def = s_def;
+        for (int i = j + 1 + tid; i < p; i += blockDim.x) {
+            const double v = def ? 0.0 : gs[pk(j, i)] * inv;
+            gs[pk(j, i)] = v; rowj[i] = v;
+        }
+        __syncthreads();
+        if (!def) {
+            for (int i = j + 1 + ty; i < p; i += 32) {
+                const double rji = rowj[i];
+                double* gi = gs + pk(0, i);
+                for (int k = j + 1 + tx; k <= i; k += 32) gi[k] = fma(-rowj[k], rji, gi[k]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        G[r + (int64_t)c * ld] = r <= c ? gs[pk(r, c)] : 0.0;
+    }
+    if (tid == 0) { info[0] = s_ndef; info[1] = s_bad; info[2] = s_nzero; }
+}
+
+__global__ void __launch_bounds__(1024)
+tri_inv_upper_smem_kernel(const double* __restrict__ R, int64_t ldr, int p, double* __restrict__ X, int64_t ldi) {
+    extern __shared__ double gs[];
+    const int tid = threadIdx.x, l16 = tid & 15, grp = tid >> 4, ngrp = blockDim.x >> 4;
+    double* rs = gs;                                    // row-packed R: (i, k), k >= i, at i p - i(i-1)/2 + k - i
+    double* rinv = gs + (size_t)p * (p + 1) / 2;        // 1 / R_ii
+    double* xs = rinv + p + (size_t)grp * p;            // this group's column of the inverse
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        if (r <= c) {
+            const double v = R[r + (int64_t)c * ldr];
+            rs[r * p - r * (r - 1) / 2 + c - r] = v;
+            if (r == c) rinv[r] = 1.0 / v;
+        }
+    }
+    __syncthreads();
+    const unsigned gmask = 0xffffu << (16 * ((tid >> 4) & 1));     // the two groups of a warp run loops of different length
+    for (int j = grp; j < p; j += ngrp) {
+        for (int i = j; i >= 0; --i) {
+            const double* ri = rs + (i * p - i * (i - 1) / 2 - i);  // ri[k] = R(i, k)
+            double s = 0.0;
+            for (int k = i + 1 + l16; k <= j; k += 16) s = fma(ri[k], xs[k], s);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o);
+            if (l16 == 0) xs[i] = ((i == j ? 1.0 : 0.0) - s) * rinv[i];
+            __syncwarp(gmask);
+        }
+        double* x = X + (int64_t)j * ldi;
+        for (int i = l16; i < p; i += 16) x[i] = i <= j ? xs[i] : 0.0;
+        __syncwarp(gmask);
     }
 }
 
@@ -175,6 +273,31 @@ replace_columns_kernel(double* __restrict__ X, int64_t ld, int64_t rows, int64_t
     const int64_t tgt = target[j] - row_off;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)
         X[r + (int64_t)j * ld] = (r == tgt) ? 1.0 : 0.0;
+}
+
+// Device-driven version of (replace_columns + zero_flagged_diag) for orth_inplace's passes that run without a host round
+// trip: exactly-zero columns (flag 2) become unit vectors e_t, t = j on the first attempt and a hashed global row later
+// (same rule as the host-side code in drivers.cu), and their R_jj is set to 0.  state[0] = attempt counter.
+__global__ void __launch_bounds__(256)
+orth_fixup_kernel(double* __restrict__ X, int64_t ld, int64_t rows, int64_t row_off, int64_t rows_global, int p,
+                  const int* __restrict__ flags, const int* __restrict__ info, const int* __restrict__ state,
+                  double* __restrict__ G, int64_t ldg) {
+    if (info[2] == 0) return;
+    const int attempt = state[0];
+    for (int j = 0; j < p; ++j) {
+        if (flags[j] != 2) continue;
+        const int64_t tgt_g = attempt == 0 ? (int64_t)j
+                                           : (int64_t)(((uint64_t)j * 7919u + (uint64_t)attempt * 104729u + 13u) % (uint64_t)rows_global);
+        const int64_t tgt = tgt_g - row_off;
+        for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)
+            X[r + (int64_t)j * ld] = (r == tgt) ? 1.0 : 0.0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) G[j + (int64_t)j * ldg] = 0.0;
+    }
+}
+// hist[3*pass .. 3*pass+2] = info (deficient, non-finite, exactly-zero); attempt counter advances when a column was replaced
+__global__ void orth_advance_kernel(const int* __restrict__ info, int* __restrict__ state, int* __restrict__ hist, int pass) {
+    hist[3 * pass] = info[0]; hist[3 * pass + 1] = info[1]; hist[3 * pass + 2] = info[2];
+    if (info[2] > 0) state[0] += 1;
 }
 
 __global__ void __launch_bounds__(256)
@@ -305,26 +428,21 @@ __device__ __forceinline__ double fast_sqrt(double x) {      // x >= 0
 __global__ void __launch_bounds__(256)
 jacobi_init_kernel(const double* __restrict__ M, int64_t ldm, int p, int transpose, double* __restrict__ W,
                    double* __restrict__ V, int* flags) {
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 4 + JACOBI_MAX_SWEEPS; i += blockDim.x) flags[i] = 0;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p * p; idx += gridDim.x * blockDim.x) {
         const int c = idx / p, r = idx - c * p;
         W[idx] = transpose ? M[c + (int64_t)r * ldm] : M[r + (int64_t)c * ldm];
         V[idx] = (r == c) ? 1.0 : 0.0;
     }
-    if (blockIdx.x == 0 && threadIdx.x < 4) flags[threadIdx.x] = 0;
 }
 
-__global__ void __launch_bounds__(1024)
-jacobi_block_kernel(double* __restrict__ W, double* __restrict__ V, int p, int b, int nblocks, int NB, int round,
-                    int max_inner, int single, int* __restrict__ flags) {
-    extern __shared__ double jsm[];
-    __shared__ int s_rot, s_first;
+// One block pair: columns [i0, i1) and [j0, j1) of W and V go to shared memory, up to max_inner cyclic sweeps over their
+// union, and back.  Returns (to every thread) whether the first sweep rotated anything; *sweeps_out / *conv_out as named.
+template <int LG>   // lanes per column pair: 16 (up to 64 pairs per round in one pass) or 32 (up to 32 pairs)
+__device__ int jacobi_pair_block(double* __restrict__ W, double* __restrict__ V, int p, int i0, int i1, int j0, int j1,
+                                 int max_inner, int cross_only, double* jsm, int* s_rot, int* sweeps_out, int* conv_out) {
     const int tid = threadIdx.x;
-    int I = 0, J = 1;
-    if (!single) {
-        rr_pair(round, blockIdx.x, NB, I, J);
-        if (J >= nblocks) return;                   // padding block: block I sits this round out
-    }
-    const int i0 = I * b, i1 = min(p, i0 + b), j0 = J * b, j1 = max(j0, min(p, j0 + b));
     const int nI = i1 - i0, nc = nI + (j1 - j0);
     double* sW = jsm;
     double* sV = jsm + (size_t)nc * p;
@@ -334,53 +452,74 @@ jacobi_block_kernel(double* __restrict__ W, double* __restrict__ V, int p, int b
         sW[idx] = W[(size_t)gc * p + r];
         sV[idx] = V[(size_t)gc * p + r];
     }
-    if (tid == 0) s_first = 0;
     __syncthreads();
     const int NC = (nc & 1) ? nc + 1 : nc;
+    // cross_only: only pairs (a in I, b in J), a bipartite cyclic schedule of max(nI, nJ) rounds -- the pairs inside a block
+    // are visited once per sweep elsewhere (outer round 0), not again in every block pair that contains the block
+    const int nJ = nc - nI, mx = nI > nJ ? nI : nJ;
+    const int nrounds = cross_only ? mx : NC - 1, npairs = cross_only ? mx : NC / 2;
     const double tol = sqrt((double)(p > 1 ? p : 1)) * DBL_EPSILON;
-    int sweeps = 0, conv = 0;
-    // one 16-lane group per column pair: nc <= 128 columns give <= 64 pairs, so a round is a single pass of the 64 groups
-    const int l16 = tid & 15, grp = tid >> 4, ngrp = blockDim.x >> 4;
+    int sweeps = 0, conv = NC < 2 ? 1 : 0, first = 0;
+    // one LG-lane group per column pair; a round is a single pass of the groups when NC / 2 <= 1024 / LG
+    const int l16 = tid & (LG - 1), grp = tid / LG, ngrp = blockDim.x / LG;
     for (int sw = 0; sw < max_inner && NC >= 2; ++sw) {
-        if (tid == 0) s_rot = 0;
+        if (tid == 0) *s_rot = 0;
         __syncthreads();
-        for (int rd = 0; rd < NC - 1; ++rd) {
-            for (int pi0 = 0; pi0 < NC / 2; pi0 += ngrp) {          // uniform trip count: the shuffles below need whole warps
+        for (int rd = 0; rd < nrounds; ++rd) {
+            for (int pi0 = 0; pi0 < npairs; pi0 += ngrp) {          // uniform trip count: the shuffles below need whole warps
                 const int pi = pi0 + grp;
                 int ca = 0, cb = 0;
-                bool valid = pi < NC / 2;
-                if (valid) { rr_pair(rd, pi, NC, ca, cb); valid = cb < nc; }
+                bool valid = pi < npairs;
+                if (valid) {
+                    if (cross_only) { int jj = pi + rd; if (jj >= mx) jj -= mx; ca = pi; cb = nI + jj; valid = pi < nI && jj < nJ; }
+                    else { rr_pair(rd, pi, NC, ca, cb); valid = cb < nc; }
+                }
+                if (!valid) { ca = 0; cb = 0; }
                 double* wa = sW + (size_t)ca * p; double* wb = sW + (size_t)cb * p;
                 double al = 0.0, be = 0.0, ga = 0.0;
-                if (valid)
-                    for (int k = l16; k < p; k += 16) { const double x = wa[k], y = wb[k]; al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga); }
+                if (valid) {
+#pragma unroll 4
+                    for (int k = l16; k < p; k += LG) { const double x = wa[k], y = wb[k]; al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga); }
+                }
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {
+                for (int o = LG / 2; o > 0; o >>= 1) {
                     al += __shfl_xor_sync(0xffffffffu, al, o);
                     be += __shfl_xor_sync(0xffffffffu, be, o);
                     ga += __shfl_xor_sync(0xffffffffu, ga, o);
                 }
+                // Rotation parameters, computed unconditionally so that this chain overlaps the threshold chain.  With
+                // a = be - al, b = 2 ga (both scaled by one power of two against under/overflow of the squares):
+                // tan(2 theta) = b / a, |theta| <= pi/4;  r = 1/hypot(a, b);  cos(2 theta) = |a| r;
+                // u = (1 + cos 2theta) / 2 = cos^2(theta);  cs = u rsqrt(u);  sn = sign(ab) |b| r rsqrt(u) / 2.
+                // Two reciprocal square roots (MUFU seed + two Newton steps each) instead of two divisions and three
+                // square roots: the sequence of dependent FP64 operations is the latency of a round.
                 const double aga = fabs(ga);
-                if (valid && aga > DBL_MIN && aga > tol * (fast_sqrt(al) * fast_sqrt(be))) {
-                    const double zeta = (be - al) * fast_rcp(2.0 * ga);
-                    const double az = fabs(zeta);
-                    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)); beyond 1e8 the square root is |zeta| to the last bit
-                    const double t = az > 1e8 ? 0.5 * fast_rcp(zeta) : copysign(fast_rcp(az + fast_sqrt(fma(zeta, zeta, 1.0))), zeta);
-                    const double cs = fast_rsqrt(fma(t, t, 1.0)), sn = cs * t;
+                const double thr = tol * (fast_sqrt(al) * fast_sqrt(be));
+                const double a0 = be - al, b0 = 2.0 * ga;
+                const int ex = (__double2hiint(fmax(fabs(a0), fabs(b0))) >> 20) & 0x7ff;
+                const double sc = __hiloint2double((2046 - ex) << 20, 0);
+                const double a1 = a0 * sc, b1 = b0 * sc;
+                const double r = fast_rsqrt(fma(a1, a1, b1 * b1));
+                const double u = fma(0.5 * fabs(a1), r, 0.5);
+                const double ru = fast_rsqrt(u);
+                const double cs = u * ru;
+                const double sn = copysign(0.5 * fabs(b1) * r * ru, a1 * b1);
+                if (valid && aga > DBL_MIN && aga > thr) {
                     double* va = sV + (size_t)ca * p; double* vb = sV + (size_t)cb * p;
-                    for (int k = l16; k < p; k += 16) {
+#pragma unroll 4
+                    for (int k = l16; k < p; k += LG) {
                         const double x = wa[k], y = wb[k];
                         wa[k] = cs * x - sn * y; wb[k] = sn * x + cs * y;
                         const double vx = va[k], vy = vb[k];
                         va[k] = cs * vx - sn * vy; vb[k] = sn * vx + cs * vy;
                     }
-                    if (l16 == 0) s_rot = 1;
+                    if (l16 == 0) *s_rot = 1;
                 }
             }
             __syncthreads();
         }
-        const int rot = s_rot;
-        if (tid == 0 && sw == 0) s_first = rot;
+        const int rot = *s_rot;
+        if (sw == 0) first = rot;
         __syncthreads();
         sweeps = sw + 1;
         if (!rot) { conv = 1; break; }
@@ -391,10 +530,51 @@ jacobi_block_kernel(double* __restrict__ W, double* __restrict__ V, int p, int b
         W[(size_t)gc * p + r] = sW[idx];
         V[(size_t)gc * p + r] = sV[idx];
     }
-    if (tid == 0) {
-        if (s_first) atomicOr(&flags[0], 1);
-        if (single) { flags[1] = sweeps; flags[2] = (conv || NC < 2) ? 1 : 0; }
+    *sweeps_out = sweeps; *conv_out = conv;
+    return first;
+}
+
+// whole matrix in one CTA (p <= 72): flags[1] = sweeps, flags[2] = converged
+__global__ void __launch_bounds__(1024)
+jacobi_single_kernel(double* __restrict__ W, double* __restrict__ V, int p, int max_sweeps, int* __restrict__ flags) {
+    extern __shared__ double jsm[];
+    __shared__ int s_rot;
+    const int b = (p + 1) / 2;
+    int sweeps, conv;
+    if (p <= 64) jacobi_pair_block<32>(W, V, p, 0, b, b, p, max_sweeps, 0, jsm, &s_rot, &sweeps, &conv);
+    else jacobi_pair_block<16>(W, V, p, 0, b, b, p, max_sweeps, 0, jsm, &s_rot, &sweeps, &conv);
+    if (threadIdx.x == 0) { flags[1] = sweeps; flags[2] = conv; }
+}
+
+// Cooperative launch, NB/2 CTAs (all co-resident): every sweep is NB-1 rounds of disjoint block pairs with a grid barrier
+// between rounds; the sweep loop and its convergence test run on the device (flags[4 + sweep] collects "some rotation").
+__global__ void __launch_bounds__(1024)
+jacobi_coop_kernel(double* __restrict__ W, double* __restrict__ V, int p, int b, int nblocks, int NB, int max_sweeps,
+                   int* __restrict__ flags) {
+    extern __shared__ double jsm[];
+    __shared__ int s_rot;
+    cg::grid_group grid = cg::this_grid();
+    int sweeps = 0, conv = 0;
+    for (int sw = 0; sw < max_sweeps; ++sw) {
+        for (int round = 0; round < NB - 1; ++round) {
+            // outer round 0 pairs every block once: full tournament over the union (covers the pairs inside both blocks);
+            // the other rounds only take the cross pairs.  A block paired with the padding block is swept alone in round 0.
+            int I, J; rr_pair(round, blockIdx.x, NB, I, J);
+            const bool pad = J >= nblocks;
+            if (!pad || round == 0) {
+                int isw, icv;
+                const int i0 = I * b, i1 = min(p, I * b + b), j0 = pad ? i1 : J * b, j1 = pad ? i1 : min(p, J * b + b);
+                const int rot = b <= 32 ? jacobi_pair_block<32>(W, V, p, i0, i1, j0, j1, 1, round != 0, jsm, &s_rot, &isw, &icv)
+                                        : jacobi_pair_block<16>(W, V, p, i0, i1, j0, j1, 1, round != 0, jsm, &s_rot, &isw, &icv);
+                if (rot && threadIdx.x == 0) atomicOr(&flags[4 + sw], 1);
+            }
+            __threadfence();
+            grid.sync();
+        }
+        sweeps = sw + 1;
+        if (*(volatile int*)&flags[4 + sw] == 0) { conv = 1; break; }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { flags[1] = sweeps; flags[2] = conv; }
 }
 
 // sigma, ordering, U = W / sigma, orthonormal completion; W, V as left by the sweeps.  flags -> info
@@ -594,12 +774,37 @@ cudaError_t threefry_blocks(int64_t n, const uint64_t* ctr, const uint64_t* key,
     threefry_blocks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ctr, key, out);
     return LAUNCHED();
 }
+constexpr size_t SMALL_SMEM = 224 * 1024;
 cudaError_t chol_upper(double* G, int64_t ld, int p, double tol2, int* flags, int* info, cudaStream_t st) {
-    chol_upper_kernel<<<1, 1024, 0, st>>>(G, ld, p, tol2, flags, info);
+    const size_t need = ((size_t)p * (p + 1) / 2 + 2 * (size_t)p) * 8;
+    if (need <= SMALL_SMEM) {
+        static bool attr = false;
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(chol_upper_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM);
+            if (e != cudaSuccess) return e;
+            attr = true;
+        }
+        chol_upper_smem_kernel<<<1, 1024, need, st>>>(G, ld, p, tol2, flags, info);
+    } else {
+        chol_upper_kernel<<<1, 1024, 0, st>>>(G, ld, p, tol2, flags, info);
+    }
     return LAUNCHED();
 }
 cudaError_t tri_inv_upper(const double* R, int64_t ldr, int p, double* Rinv, int64_t ldi, cudaStream_t st) {
-    tri_inv_upper_kernel<<<1, 1024, 0, st>>>(R, ldr, p, Rinv, ldi);
+    const size_t base = ((size_t)p * (p + 1) / 2 + (size_t)p) * 8;
+    int ngrp = base + 2 * (size_t)p * 8 <= SMALL_SMEM ? (int)((SMALL_SMEM - base) / ((size_t)p * 8)) : 0;
+    ngrp = std::min(64, ngrp) & ~1;                       // whole warps
+    if (ngrp >= 2) {
+        static bool attr = false;
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(tri_inv_upper_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM);
+            if (e != cudaSuccess) return e;
+            attr = true;
+        }
+        tri_inv_upper_smem_kernel<<<1, 16 * ngrp, base + (size_t)ngrp * p * 8, st>>>(R, ldr, p, Rinv, ldi);
+    } else {
+        tri_inv_upper_kernel<<<1, 1024, 0, st>>>(R, ldr, p, Rinv, ldi);
+    }
     return LAUNCHED();
 }
 cudaError_t small_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
@@ -617,6 +822,13 @@ cudaError_t replace_columns(double* X, int64_t ld, int64_t rows, int64_t row_off
     if (rows <= 0 || p <= 0) return cudaSuccess;
     dim3 grid((unsigned)grid_for(rows, 256, 64), (unsigned)p);
     replace_columns_kernel<<<grid, 256, 0, st>>>(X, ld, rows, row_off, p, flags, target);
+    return LAUNCHED();
+}
+cudaError_t orth_fixup(double* X, int64_t ld, int64_t rows, int64_t row_off, int64_t rows_global, int p, const int* flags,
+                       const int* info, int* state, int* hist, int pass, double* G, int64_t ldg, cudaStream_t st) {
+    orth_fixup_kernel<<<grid_for(std::max<int64_t>(rows, 1), 256, 64), 256, 0, st>>>(X, ld, rows, row_off, rows_global, p, flags, info, state, G, ldg);
+    ++g_kernel_launches;
+    orth_advance_kernel<<<1, 1, 0, st>>>(info, state, hist, pass);
     return LAUNCHED();
 }
 cudaError_t set_identity(double* X, int64_t ld, int64_t rows, int64_t cols, cudaStream_t st) {
@@ -658,57 +870,43 @@ cudaError_t scale_columns(double* X, int64_t ld, int64_t rows, int64_t cols, con
     scale_columns_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(X, ld, rows, cols, s);
     return LAUNCHED();
 }
-size_t jacobi_svd_work_doubles(int p) { return 2 * (size_t)p * p + (size_t)p + 8; }
+size_t jacobi_svd_work_doubles(int p) { return 2 * (size_t)p * p + (size_t)p + 8 + (4 + JACOBI_MAX_SWEEPS + 1) / 2; }
 
 cudaError_t jacobi_svd(const double* M, int64_t ldm, int p, double* U, int64_t ldu, double* sigma,
                        double* V, int64_t ldv, double* work, int* info, cudaStream_t st, int transpose) {
     constexpr int JSMEM = 224 * 1024;
     double* W = work;
     double* Vw = work + (size_t)p * p;
-    int* flags = reinterpret_cast<int*>(work + 2 * (size_t)p * p + (size_t)p);
+    int* flags = reinterpret_cast<int*>(work + 2 * (size_t)p * p + (size_t)p);     // 4 + JACOBI_MAX_SWEEPS ints
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JSMEM);
+        cudaError_t e = cudaFuncSetAttribute(jacobi_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JSMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(jacobi_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JSMEM);
         if (e != cudaSuccess) return e;
         attr = true;
     }
     jacobi_init_kernel<<<grid_for((int64_t)p * p, 256), 256, 0, st>>>(M, ldm, p, transpose, W, Vw, flags);
     ++g_kernel_launches;
-    if (16 * (size_t)p * p <= (size_t)JSMEM) {
-        // everything fits: two "blocks" [0, b) and [b, p), every sweep inside one CTA
-        const int b = (p + 1) / 2;
-        jacobi_block_kernel<<<1, 1024, 16 * (size_t)p * p + 16, st>>>(W, Vw, p, b, 2, 2, 0, JACOBI_MAX_SWEEPS, 1, flags);
+    if (p <= 72) {
+        // small enough that one SM's shared-memory bandwidth is not the limit: every sweep inside one CTA
+        jacobi_single_kernel<<<1, 1024, 16 * (size_t)p * p + 16, st>>>(W, Vw, p, JACOBI_MAX_SWEEPS, flags);
         ++g_kernel_launches;
     } else {
-        // block width: a block pair must fit one SM's shared memory, but the sweep is bound by that SM's shared-memory
-        // bandwidth (80 bytes move per element of a column pair), so ~20 narrower blocks spread a round over ~10 SMs
+        // A block pair must fit one SM's shared memory, but a sweep is bound by that SM's shared-memory bandwidth (80 bytes
+        // move per element of a column pair) and by the latency of a round, so ~14-20 narrow blocks spread every round over
+        // 7-10 SMs (p = 110 in one CTA: 3.2 ms; 7 CTAs of 2 x 8 columns: < 1 ms)
         int b = (int)(JSMEM / (32 * (size_t)p));
         if (b > 64) b = 64;
         if (b < 1) return cudaErrorInvalidValue;
         b = std::min(b, std::max(8, (p + 19) / 20));
-        const int nblocks = (p + b - 1) / b;
-        const int NB = (nblocks & 1) ? nblocks + 1 : nblocks;
-        int sweeps = 0, conv = 0;
-        for (; sweeps < JACOBI_MAX_SWEEPS; ) {
-            cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int), st);
-            if (e != cudaSuccess) return e;
-            for (int round = 0; round < NB - 1; ++round) {
-                jacobi_block_kernel<<<NB / 2, 1024, 32 * (size_t)b * p + 16, st>>>(W, Vw, p, b, nblocks, NB, round, 1, 0, flags);
-                ++g_kernel_launches;
-            }
-            ++sweeps;
-            int rot = 0;
-            e = cudaMemcpyAsync(&rot, flags, sizeof(int), cudaMemcpyDeviceToHost, st);
-            if (e != cudaSuccess) return e;
-            e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) return e;
-            if (!rot) { conv = 1; break; }
-        }
-        const int h[2] = {sweeps, conv};
-        cudaError_t e = cudaMemcpyAsync(flags + 1, h, 2 * sizeof(int), cudaMemcpyHostToDevice, st);
+        int nblocks = (p + b - 1) / b;
+        int NB = (nblocks & 1) ? nblocks + 1 : nblocks;
+        int max_sweeps = JACOBI_MAX_SWEEPS;
+        void* args[] = {&W, &Vw, &p, &b, &nblocks, &NB, &max_sweeps, &flags};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)jacobi_coop_kernel, dim3(NB / 2), dim3(1024), args,
+                                                    32 * (size_t)b * p + 16, st);
         if (e != cudaSuccess) return e;
-        e = cudaStreamSynchronize(st);      // h lives on this stack frame
-        if (e != cudaSuccess) return e;
+        ++g_kernel_launches;
     }
     // the sweeps factor W0 = X diag(sigma) Y^T with X from the rotated columns and Y the accumulated rotations;
     // W0 = M^T swaps the roles of the two sides

@@ -18,7 +18,8 @@ cudaError_t threefry_blocks(int64_t n, const uint64_t* ctr, const uint64_t* key,
 
 // In-place upper Cholesky G = R^T R of a p x p Gram matrix with rank-deficiency detection.
 // Column j is declared deficient when its pivot d_j <= tol2 * G_jj (or G_jj == 0); then R_jj = 1,
-// R_j,j+1.. = 0 and flags[j] = 1.  info[0] = number of deficient columns, info[1] = 1 if non-finite.
+// R_j,j+1.. = 0 and flags[j] = 1.  info[0] = number of deficient columns, info[1] = 1 if non-finite,
+// info[2] = number of exactly-zero columns (flag 2).  info must hold 3 ints.
 cudaError_t chol_upper(double* G, int64_t ld, int p, double tol2, int* flags, int* info, cudaStream_t st);
 // Rinv = R^-1 (upper triangular, p x p)
 cudaError_t tri_inv_upper(const double* R, int64_t ldr, int p, double* Rinv, int64_t ldi, cudaStream_t st);
@@ -30,6 +31,10 @@ cudaError_t zero_flagged_diag(double* R, int64_t ld, int p, const int* flags, cu
 // X(:, j) = e_{p_j} for flagged columns; p_j = global row index target[j]; rows are [row_off, row_off+rows)
 cudaError_t replace_columns(double* X, int64_t ld, int64_t rows, int64_t row_off, int p, const int* flags,
                             const int64_t* target, cudaStream_t st);
+// device-driven replace_columns + zero_flagged_diag (no host round trip): see panel.cu.  info = chol_upper's (3 ints),
+// state[0] = attempt counter (zero it before the first pass), hist receives 3 ints per pass.
+cudaError_t orth_fixup(double* X, int64_t ld, int64_t rows, int64_t row_off, int64_t rows_global, int p, const int* flags,
+                       const int* info, int* state, int* hist, int pass, double* G, int64_t ldg, cudaStream_t st);
 cudaError_t set_identity(double* X, int64_t ld, int64_t rows, int64_t cols, cudaStream_t st);
 cudaError_t copy_matrix(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows, int64_t cols, cudaStream_t st);
 cudaError_t transpose_matrix(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows, int64_t cols, cudaStream_t st);
