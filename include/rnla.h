@@ -190,6 +190,8 @@ rnla_status rnla_orth_dev(double* dX, int64_t ldx, int64_t rows_local, int64_t c
                           double* dR, int64_t* deficient);
 /* small dense core on one GPU: SVD of a (rows x cols) matrix with cols <= 512 columns... see DESIGN.md */
 rnla_status rnla_small_svd_dev(const double* dM, int64_t ldm, int64_t p, double* dU, double* dSigma, double* dV);
+/* diagnostics: Jacobi sweeps used by the last small SVD (drivers and rnla_small_svd_dev) */
+int32_t rnla_last_jacobi_sweeps(void);
 rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double* dW, double* dLambda);
 
 /* synthetic inputs, generated on the device shard by shard: A = U0 diag(sigma) V0^T + eta G */

@@ -422,11 +422,14 @@ rnla_status rnla_small_svd_dev(const double* dM, int64_t ldm, int64_t p, double*
     int h[2];
     RNLA_CUDA(cudaMemcpyAsync(h, info.p, 8, cudaMemcpyDeviceToHost, c.stream));
     RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    g_last_jacobi_sweeps = h[0];
     if (h[1]) return fail(RNLA_ERR_MATRIX_DECOMPOSITION, "SVD decomposition failed");
     RNLA_TRY(dev_gemm_nn(Q.d(), p, p, p, Ur.d(), p, p, dU, p));
     RNLA_CUDA(cudaStreamSynchronize(c.stream));
     return RNLA_OK;
 }
+int32_t rnla_last_jacobi_sweeps(void) { return g_last_jacobi_sweeps; }
+
 rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double* dW, double* dLambda) {
     RNLA_TRY(ensure_ctx());
     Ctx& c = ctx();

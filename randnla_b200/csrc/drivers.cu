@@ -278,6 +278,8 @@ rnla_status dev_qb1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
 // SVD of a tall replicated-or-sharded panel X (rows x p) = Uo diag(sigma) Vo^T through CholeskyQR + Jacobi on R.
 // X is overwritten by its orthonormal factor Qx; Ur (p x p) and Vr (p x p) are such that
 // Uo = Qx * Ur, Vo = Vr.
+int g_last_jacobi_sweeps = 0;     // diagnostics (rnla_last_jacobi_sweeps)
+
 static rnla_status tall_svd(double* X, int64_t ldx, const ShardInfo& sh, int p, bool sharded, double* Ur, double* sigma, double* Vr) {
     Ctx& c = ctx();
     const size_t pp = (size_t)p * p;
@@ -288,6 +290,7 @@ static rnla_status tall_svd(double* X, int64_t ldx, const ShardInfo& sh, int p, 
     int hinfo[2];
     RNLA_CUDA(cudaMemcpyAsync(hinfo, info.p, 8, cudaMemcpyDeviceToHost, c.stream));
     RNLA_TRY(sync_stream());
+    g_last_jacobi_sweeps = hinfo[0];
     if (hinfo[1]) return fail(RNLA_ERR_MATRIX_DECOMPOSITION, "SVD decomposition failed");   // lora_drivers.rs:55-57
     return RNLA_OK;
 }

@@ -33,6 +33,8 @@ rnla_status dev_rand_evd2(const double* A, int64_t lda, int64_t m_local, int64_t
 rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const double* A, int64_t lda, int64_t m_local,
                              int64_t n, int64_t row_off, double* Ask, int64_t ldk);
 
+extern int g_last_jacobi_sweeps;
+
 // literal.cu: bug-compatible pieces of the reference
 rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
                           const rnla_options& o, double* S);

@@ -19,4 +19,4 @@ for p in [int(x) for x in (sys.argv[1:] or [60, 110, 210])]:
     rt.synchronize()
     dt = (time.perf_counter() - t0) / 10
     err = np.abs(dS.cpu().numpy() - np.linalg.svd(M, compute_uv=False)).max()
-    print(f"p={p}: {dt*1e3:.3f} ms per small_svd, max abs sigma err {err:.2e}", flush=True)
+    print(f"p={p}: {dt*1e3:.3f} ms per small_svd, {lib.rnla_last_jacobi_sweeps()} sweeps, max abs sigma err {err:.2e}", flush=True)
