@@ -24,7 +24,7 @@
 // not -- w = 8 (one block per column) loses rank on coherent inputs at d = 4n and is not offered; w <= 4 holds
 // (tests/test_oracle_pinning.py::test_block_sparse_sign_embedding_quality).
 //
-// Kernel: one CTA per (column group of CB columns) x (row split), 512 threads.  Thread 0 streams, per chunk, the CB
+// Kernel: one CTA per work-list entry = (column group of CB columns) x (chunk range), 512 threads.  Thread 0 streams, per chunk, the CB
 // column segments (16 KB each, contiguous) and the chunk's slot tables (4 KB per stripe) with cp.async.bulk (TMA
 // engine) into a ring of stages with one `full` mbarrier each; the last warp to finish a chunk refills its stage (a
 // dedicated producer warp would cap the kernel at 96 registers per thread); all 512 threads each own BPT blocks (BPT * w * CB f64 accumulators
@@ -38,6 +38,7 @@
 #include <algorithm>
 #include <cmath>
 #include <type_traits>
+#include <vector>
 
 namespace rnla {
 
@@ -97,10 +98,12 @@ sb_table_kernel(uint64_t seed, int64_t q_first, int64_t nchunks, uint32_t nbs, i
 
 struct SbArgs {
     const double* A; int64_t lda; int64_t m_local; int64_t n; int64_t row_off;
-    const sbtab_t* tab; int64_t q_first; int64_t nchunks; int64_t chunks_per_split;
+    const sbtab_t* tab; int64_t q_first; int64_t nchunks;
+    const int4* desc;             // per CTA: column group, first chunk, end chunk, partial slot (-1: writes A_sk directly)
     int nbs; int g; int parts;    // parts > 1 only when g * nbs < SB_T
     int stages;
-    double* out; int64_t ldo; int64_t split_stride;   // out + split * split_stride
+    double* out; int64_t ldo;     // A_sk
+    double* partial; int64_t d_used;   // slot s: d_used x CB doubles
     int ncg;                      // column groups
     double scale;
 };
@@ -131,13 +134,12 @@ saso_block_kernel(const SbArgs a) {
     const int stages = a.stages;
 
     const int tid = threadIdx.x;
-    const int cg = blockIdx.x % a.ncg;
-    const int split = blockIdx.x / a.ncg;
+    const int4 dsc = a.desc[blockIdx.x];
+    const int cg = dsc.x;
     const int64_t c0 = (int64_t)cg * CB;
     const int cbv = (int)min((int64_t)CB, a.n - c0);
-    const int64_t ch0 = (int64_t)split * a.chunks_per_split;
-    const int64_t ch1 = min(a.nchunks, ch0 + a.chunks_per_split);
-    const int nch = (int)(ch1 - ch0);
+    const int64_t ch0 = dsc.y;
+    const int nch = dsc.z - dsc.y;
 
     // columns of the tile that have no source stay zero for the whole kernel
     if (cbv < CB) {
@@ -296,7 +298,9 @@ saso_block_kernel(const SbArgs a) {
         if (++s == stages) { s = 0; ph ^= 1u; }
     }
 
-    double* out = a.out + (int64_t)split * a.split_stride;
+    // a CTA that covers all chunks of its column group writes A_sk; a fragment writes its slot (sb_fixup_kernel adds them)
+    double* out = dsc.w < 0 ? a.out + c0 * a.ldo : a.partial + (int64_t)dsc.w * a.d_used * CB;
+    const int64_t ldo = dsc.w < 0 ? a.ldo : a.d_used;
     if (a.parts > 1) {
         // fixed-order reduction over the parts through shared memory (the ring is drained: every full barrier was waited on)
         asm volatile("bar.sync 1, %0;" ::"n"(SB_T));
@@ -315,7 +319,7 @@ saso_block_kernel(const SbArgs a) {
                 for (int c = 0; c < CB; ++c) {
                     double sum = 0.0;
                     for (int p = 0; p < a.parts; ++p) sum += red[((size_t)(p * nbt + B0) * W + r) * CB + c];
-                    if (c < cbv) out[(int64_t)B0 * W + r + (c0 + c) * a.ldo] = sum * a.scale;
+                    if (c < cbv) out[(int64_t)B0 * W + r + c * ldo] = sum * a.scale;
                 }
         }
     } else {
@@ -327,22 +331,26 @@ saso_block_kernel(const SbArgs a) {
                 for (int c = 0; c < CB; ++c)
                     if (c < cbv) {
 #pragma unroll
-                        for (int r = 0; r < W; ++r) out[(int64_t)B * W + r + (c0 + c) * a.ldo] = acc[i][r][c] * a.scale;
+                        for (int r = 0; r < W; ++r) out[(int64_t)B * W + r + c * ldo] = acc[i][r][c] * a.scale;
                     }
             }
         }
     }
 }
 
-// out(i) = sum over splits of partial[s](i), fixed order
+// A column group whose chunks were shared by several CTAs: add their fragments in chunk order (= slot list order)
 __global__ void __launch_bounds__(256)
-sb_reduce_kernel(const double* __restrict__ part, int64_t split_stride, int nsplit, int64_t rows, int64_t cols,
-                 double* __restrict__ out, int64_t ldo) {
-    const int64_t total = rows * cols;
+sb_fixup_kernel(const double* __restrict__ partial, int64_t d_used, int CB, const int* __restrict__ fix_cg,
+                const int* __restrict__ fix_off, const int* __restrict__ fix_cnt, const int* __restrict__ slots,
+                double* __restrict__ out, int64_t ldo, int64_t n) {
+    const int e = blockIdx.y;
+    const int cg = fix_cg[e], off = fix_off[e], cnt = fix_cnt[e];
+    const int cbv = (int)min((int64_t)CB, n - (int64_t)cg * CB);
+    const int64_t total = d_used * cbv;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (int k = 0; k < nsplit; ++k) s += part[(int64_t)k * split_stride + i];
-        out[(i % rows) + (i / rows) * ldo] = s;
+        for (int k = 0; k < cnt; ++k) s += partial[(int64_t)slots[off + k] * d_used * CB + i];
+        out[(i % d_used) + ((int64_t)cg * CB + i / d_used) * ldo] = s;
     }
 }
 
@@ -428,22 +436,7 @@ rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const do
     const int64_t q_last = (row_off + m_local - 1) / SB_R;
     const int64_t nchunks = q_last - q_first + 1;
 
-    // split the rows so that the grid fills the SMs in whole waves (one CTA per SM)
-    int nsplit = 1;
-    {
-        double best = 0.0;
-        const int maxsplit = (int)std::min<int64_t>(8, std::max<int64_t>(1, nchunks / 8));
-        for (int s = 1; s <= maxsplit; ++s) {
-            const int64_t units = (int64_t)ncg * s;
-            const int64_t waves = (units + c.sms - 1) / c.sms;
-            const double eff = (double)units / (double)(waves * c.sms) - 0.01 * (s - 1);
-            if (eff > best + 1e-9) { best = eff; nsplit = s; }
-        }
-    }
-    const int64_t cps = (nchunks + nsplit - 1) / nsplit;
-    nsplit = (int)((nchunks + cps - 1) / cps);
-
-    DevBuf tab, partial;
+    DevBuf tab, partial, meta;
     RNLA_CUDA(tab.alloc((size_t)nchunks * g * SB_TABW * sizeof(sbtab_t)));
     {
         const int64_t total = nchunks * g * SB_R;
@@ -452,30 +445,69 @@ rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const do
         ++g_kernel_launches;
         RNLA_CUDA(cudaGetLastError());
     }
+    // Work list, one CTA per entry, one CTA per SM at a time.  Whole column groups fill as many complete waves as they
+    // can; the chunks of the remaining groups are cut into `sms` equal ranges and every range becomes one or two
+    // fragments (column group, chunk range) with a partial-result slot.  Entries are ordered longest first, so the
+    // hardware's in-order dispatch packs the fragments of the last wave tightly (longest-processing-time rule): every SM
+    // streams nearly the same number of bytes, and only the fragments cost extra traffic (their slots).
+    struct Frag { int cg, lo, hi, slot; };
+    std::vector<Frag> work;
+    std::vector<int> fix_cg, fix_off, fix_cnt, slots;
+    {
+        const int sms = std::max(c.sms, 1);
+        const int nwhole = nchunks >= 16 ? (ncg / sms) * sms : ncg;      // short inputs are not worth fragmenting
+        for (int gidx = 0; gidx < nwhole; ++gidx) work.push_back({gidx, 0, (int)nchunks, -1});
+        const int64_t left = (int64_t)(ncg - nwhole) * nchunks;
+        std::vector<Frag> frags;
+        for (int k = 0; k < sms && left > 0; ++k) {
+            int64_t t = left * k / sms;
+            const int64_t t1 = left * (k + 1) / sms;
+            while (t < t1) {
+                const int64_t gl = t / nchunks, end = std::min(t1, (gl + 1) * nchunks);
+                const int cgi = nwhole + (int)gl, lo = (int)(t - gl * nchunks), hi = (int)(end - gl * nchunks);
+                if (lo == 0 && hi == (int)nchunks) frags.push_back({cgi, lo, hi, -1});
+                else {
+                    const int slot = (int)slots.size();
+                    if (fix_cg.empty() || fix_cg.back() != cgi) { fix_cg.push_back(cgi); fix_off.push_back(slot); fix_cnt.push_back(0); }
+                    slots.push_back(slot); ++fix_cnt.back();
+                    frags.push_back({cgi, lo, hi, slot});
+                }
+                t = end;
+            }
+        }
+        std::stable_sort(frags.begin(), frags.end(), [](const Frag& x, const Frag& y) { return x.hi - x.lo > y.hi - y.lo; });
+        work.insert(work.end(), frags.begin(), frags.end());
+    }
+    const int nfix = (int)fix_cg.size(), nslots = (int)slots.size(), grid = (int)work.size();
+    // one upload: descriptors (int4 per CTA), then the fix-up lists
+    std::vector<int> host((size_t)4 * grid + 3 * (size_t)nfix + (size_t)nslots);
+    for (int i = 0; i < grid; ++i) { host[4 * i] = work[i].cg; host[4 * i + 1] = work[i].lo; host[4 * i + 2] = work[i].hi; host[4 * i + 3] = work[i].slot; }
+    std::copy(fix_cg.begin(), fix_cg.end(), host.begin() + 4 * (size_t)grid);
+    std::copy(fix_off.begin(), fix_off.end(), host.begin() + 4 * (size_t)grid + nfix);
+    std::copy(fix_cnt.begin(), fix_cnt.end(), host.begin() + 4 * (size_t)grid + 2 * (size_t)nfix);
+    std::copy(slots.begin(), slots.end(), host.begin() + 4 * (size_t)grid + 3 * (size_t)nfix);
+    RNLA_CUDA(meta.alloc(host.size() * 4));
+    RNLA_CUDA(cudaMemcpyAsync(meta.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    if (nslots > 0) RNLA_CUDA(partial.alloc((size_t)nslots * d_used * cb * 8));
+
     SbArgs a;
     a.A = A; a.lda = lda; a.m_local = m_local; a.n = n; a.row_off = row_off;
-    a.tab = tab.as<sbtab_t>(); a.q_first = q_first; a.nchunks = nchunks; a.chunks_per_split = cps;
+    a.tab = tab.as<sbtab_t>(); a.q_first = q_first; a.nchunks = nchunks; a.desc = meta.as<int4>();
     a.nbs = (int)nbs64; a.g = g; a.parts = parts; a.stages = 0; a.ncg = ncg; a.scale = 1.0 / std::sqrt((double)zeta);
-    if (nsplit > 1) {
-        RNLA_CUDA(partial.alloc((size_t)nsplit * d_used * n * 8));
-        a.out = partial.d(); a.ldo = d_used; a.split_stride = d_used * n;
-    } else {
-        a.out = Ask; a.ldo = ldk; a.split_stride = 0;
-    }
+    a.out = Ask; a.ldo = ldk; a.partial = partial.d(); a.d_used = d_used;
     // bulk copies need 16-byte aligned sources and sizes: even leading dimension, even row offsets and counts
     const bool tma = (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (lda % 2 == 0) && (row_off % 2 == 0) && (m_local % 2 == 0);
     cudaError_t e;
-    const int grid = ncg * nsplit;
     switch (w) {
         case 1: e = sb_dispatch_bpt<1>(a, bpt, cb, grid, tma, st); break;
         case 2: e = sb_dispatch_bpt<2>(a, bpt, cb, grid, tma, st); break;
         default: e = sb_dispatch_bpt<4>(a, bpt, cb, grid, tma, st); break;
     }
     RNLA_CUDA(e);
-    if (nsplit > 1) {
-        const int64_t total = d_used * n;
-        const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-        sb_reduce_kernel<<<blocks, 256, 0, st>>>(partial.d(), a.split_stride, nsplit, d_used, n, Ask, ldk);
+    if (nfix > 0) {
+        const int* f = meta.as<int>() + 4 * (size_t)grid;
+        const int bx = (int)std::min<int64_t>((d_used * cb + 255) / 256, 64);
+        sb_fixup_kernel<<<dim3((unsigned)bx, (unsigned)nfix), 256, 0, st>>>(partial.d(), d_used, cb, f, f + nfix, f + 2 * nfix, f + 3 * nfix, Ask, ldk, n);
         ++g_kernel_launches;
         RNLA_CUDA(cudaGetLastError());
     }
