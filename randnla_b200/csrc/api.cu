@@ -270,10 +270,49 @@ rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, doub
     const int64_t l = std::min<int64_t>(k + s, std::min(m, n));
     const int64_t r = std::min(k, l);
     DevBuf dA, dU, dS, dVt;
-    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    const rnla_options& o = c.opts;
+    const int q = o.num_passes > 0 ? o.num_passes : 2;
+    const bool streamed = o.mode == RNLA_MODE_INTENDED && q >= 2 && q % 2 == 0 && m >= 8192;
+    if (!streamed) {
+        RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    } else {
+        // The first product of the power iteration, Y = A * Omega, only needs the rows of A it multiplies: upload A in row
+        // blocks on a copy stream and multiply each block as soon as it has landed.  The whole pass hides behind the PCIe
+        // transfer (32 GB at ~55 GB/s against 26 ms of DMMA at the headline size); only the last block's GEMM is exposed.
+        RNLA_CUDA(dA.alloc((size_t)m * n * 8));
+        double* dAp = dA.d();
+        c.first_pass_hook = [&c, A, dAp, m, n, l, o](double* S, double* Y, int64_t ldy) -> rnla_status {
+            cudaEvent_t ready, landed;
+            RNLA_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            RNLA_CUDA(cudaEventCreateWithFlags(&landed, cudaEventDisableTiming));
+            const bool fused = o.fused_sketch == 1 || (o.fused_sketch == 2 && (double)n * l * 8.0 > 48.0 * 1024 * 1024);
+            if (!fused) RNLA_CUDA(fill_philox(o.dist, o.seed, 1 /* STREAM_RANGE_N */, n, l, 0, S, n, c.stream));
+            RNLA_CUDA(cudaEventRecord(ready, c.stream));                    // dA is allocated stream-ordered on c.stream
+            RNLA_CUDA(cudaStreamWaitEvent(c.copy_stream, ready, 0));
+            const int64_t nblk = std::min<int64_t>(16, (m + 8191) / 8192);
+            const int64_t mb = (((m + nblk - 1) / nblk + 127) / 128) * 128;
+            rnla_status rc = RNLA_OK;
+            for (int64_t r0 = 0; r0 < m && rc == RNLA_OK; r0 += mb) {
+                const int64_t rows = std::min(mb, m - r0);
+                cudaError_t e = cudaMemcpy2DAsync(dAp + r0, (size_t)m * 8, A + r0, (size_t)m * 8, (size_t)rows * 8, (size_t)n,
+                                                  cudaMemcpyHostToDevice, c.copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(landed, c.copy_stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, landed, 0);
+                if (e != cudaSuccess) { rc = cuda_fail(e, "streamed upload of A", __FILE__, __LINE__); break; }
+                rc = fused ? dev_sketch_gemm(dAp + r0, m, rows, n, o.dist, o.seed, 1 /* STREAM_RANGE_N */, l, Y + r0, ldy)
+                           : dev_gemm_nn(dAp + r0, m, rows, n, S, n, l, Y + r0, ldy);
+            }
+            cudaEventDestroy(ready); cudaEventDestroy(landed);
+            return rc;
+        };
+    }
     RNLA_CUDA(dU.alloc((size_t)m * r * 8)); RNLA_CUDA(dS.alloc((size_t)r * 8)); RNLA_CUDA(dVt.alloc((size_t)r * n * 8));
     int64_t rr = 0;
-    RNLA_TRY(dev_rand_svd(dA.d(), m, m, n, k, s, c.opts, dU.d(), m, dS.d(), dVt.d(), r, &rr));
+    {
+        const rnla_status st = dev_rand_svd(dA.d(), m, m, n, k, s, c.opts, dU.d(), m, dS.d(), dVt.d(), r, &rr);
+        c.first_pass_hook = nullptr;
+        if (st != RNLA_OK) { cudaStreamSynchronize(c.copy_stream); return st; }
+    }
     std::vector<double> sig((size_t)r);
     RNLA_TRY(d2h(U, dU.d(), (size_t)m * r));
     RNLA_TRY(d2h(Vt, dVt.d(), (size_t)r * n));

@@ -59,6 +59,7 @@ static rnla_status init_locked(int device) {
     c.device = device;
     c.sms = prop.multiProcessorCount;
     RNLA_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    RNLA_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
     cudaMemPool_t pool;
     RNLA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -174,6 +175,8 @@ void rnla_shutdown(void) {
     for (auto e : c.event_pool) cudaEventDestroy(e);
     c.event_pool.clear();
     cudaStreamDestroy(c.own_stream);
+    if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
+    c.first_pass_hook = nullptr;
     c.stream = c.own_stream = nullptr;
     c.ready = false;
 }

@@ -1,6 +1,7 @@
 // Process-global context: device, stream, options, NCCL communicator (dlopen'ed), timings, error text.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -25,6 +26,10 @@ struct Ctx {
     std::vector<PhaseTiming> phases;
     std::vector<cudaEvent_t> event_pool;
     std::vector<std::string> timing_names;   // storage handed out by rnla_get_timings
+    // host-buffer entry points: copy stream for the upload of A, and a one-shot hook that replaces the first product
+    // Y = A * Omega of the power iteration by "upload a row block, multiply it" (the pass hides behind the PCIe copy)
+    cudaStream_t copy_stream = nullptr;
+    std::function<rnla_status(double* S, double* Y, int64_t ldy)> first_pass_hook;
 };
 
 Ctx& ctx();

@@ -204,8 +204,13 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
     }
     while (q - done >= 2) {
         {
-            PhaseScope ph(virt ? (use_fused(o, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)") : "pass:A*S");
-            if (virt && use_fused(o, n, l)) {
+            PhaseScope ph(virt ? (c.first_pass_hook ? "upload+pass:A*Omega" : use_fused(o, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)") : "pass:A*S");
+            if (virt && c.first_pass_hook) {
+                // host-buffer entry point: A is still arriving over PCIe, row block by row block (api.cu)
+                auto hook = std::move(c.first_pass_hook);
+                c.first_pass_hook = nullptr;
+                RNLA_TRY(hook(S, Ytmp, std::max<int64_t>(m, 1)));
+            } else if (virt && use_fused(o, n, l)) {
                 RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
             } else {
                 if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n, c.stream));

@@ -393,16 +393,9 @@ __device__ __forceinline__ void rr_pair(int round, int idx, int P, int& a, int& 
 
 constexpr int JACOBI_MAX_SWEEPS = 40;
 
-// Reciprocal, reciprocal square root and square root for the rotation parameters: the MUFU.RCP64H / RSQ64H seeds
+// Reciprocal square root and square root for the rotation parameters: the MUFU.RSQ64H seed
 // (~20 bits, full double exponent range) plus two Newton steps, a few ulp -- the IEEE division and square root of the
 // math library are ~10x longer dependent chains, and the rotation parameters sit on the critical path of every round.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0); y = fma(y, e, y);
-    e = fma(-x, y, 1.0); y = fma(y, e, y);
-    return y;
-}
 __device__ __forceinline__ double fast_rsqrt(double x) {     // x > 0, normal
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));

@@ -341,6 +341,23 @@ def test_rand_svd_lowrank_plus_noise_parity(rb, orc, mode):
     assert abs(ra - rbo) <= 1e-8 * np.linalg.norm(A)
 
 
+def test_rand_svd_streamed_upload(rb, orc):
+    """host-buffer rand_svd with m >= 8192 uploads A in row blocks and multiplies each block as it lands
+    (the first pass hides behind the PCIe copy); same factors as the device-resident path and as the oracle"""
+    from randnla_b200 import runtime as rt, lora_drivers as ld
+    from randnla_b200.lora_drivers import rand_svd
+    A, _ = lowrank_plus_noise(20001, 300, seed=17, k=20, gap=1e-3)
+    U, S, Vt = rand_svd(A, 20, 1e-6, 10)
+    Uo, So, Vto = orc.rand_svd(A, 20, 1e-6, 10, orc.make_opts(mode=0))
+    s, so = np.diag(S), np.diag(So)
+    assert np.abs(s - so).max() / so.max() < SIG_TOL and (np.abs(s - so) / so).max() < 1e-8
+    assert subspace_angle(U, Uo) < 1e-6
+    dA = rt.to_device_colmajor(A)
+    Ud, Sd, Vtd = ld.rand_svd_dev(dA, 20, 10)
+    assert np.abs(Sd.cpu().numpy() - s).max() <= 1e-13 * s.max()
+    assert np.abs(np.abs(Ud.cpu().numpy()) - np.abs(U)).max() < 1e-9
+
+
 def test_rand_svd_options(rb, orc):
     """extended knobs: seed, num_passes (odd branch draws Omega (m x l)), passes_per_stab, distribution"""
     from randnla_b200 import runtime as rt
