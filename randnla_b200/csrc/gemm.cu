@@ -69,7 +69,10 @@ gemm_nn_kernel(const GemmNN p, const int a_bulk, const int b_bulk) {
     const int64_t j0 = (int64_t)blockIdx.y * BN;
     const int rows_valid = (int)min((int64_t)BM, p.m - i0);
     const int cols_valid = (int)min((int64_t)BN, p.N - j0);
-    const int KT = (int)((p.K + BK - 1) / BK);
+    const int KT_all = (int)((p.K + BK - 1) / BK);
+    // split-K: this CTA takes the BK-steps [kt_lo, kt_lo + KT) and writes a partial tile (gemm_nn reduces them in order)
+    const int kt_lo = p.ksplit > 1 ? (int)blockIdx.z * p.kt_per : 0;
+    const int KT = p.ksplit > 1 ? max(0, min(KT_all - kt_lo, p.kt_per)) : KT_all;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], NCONS); }
@@ -88,7 +91,7 @@ gemm_nn_kernel(const GemmNN p, const int a_bulk, const int b_bulk) {
             mbar_wait(&empty[s], ph ^ 1u);
             double* As = tiles + (size_t)s * Cfg::STAGE;
             double* Bs = As + Cfg::A_TILE;
-            const int64_t k0 = (int64_t)kt * BK;
+            const int64_t k0 = (int64_t)(kt_lo + kt) * BK;
             const int kv = (int)min((int64_t)BK, p.K - k0);
             const bool fullk = (kv == BK);
             uint32_t tx = 0;
@@ -206,6 +209,8 @@ gemm_nn_kernel(const GemmNN p, const int a_bulk, const int b_bulk) {
             if (lane == 0) mbar_arrive(&empty[s]);
         }
         // ---- epilogue ----
+        double* Cout = p.ksplit > 1 ? p.P + (int64_t)blockIdx.z * p.pstride : p.C;
+        const int64_t ldo = p.ksplit > 1 ? p.m : p.ldc;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
             const int64_t row = i0 + wm * 32 + mi * 8 + g;
@@ -213,8 +218,8 @@ gemm_nn_kernel(const GemmNN p, const int a_bulk, const int b_bulk) {
 #pragma unroll
                 for (int ni = 0; ni < NT; ++ni) {
                     const int64_t col = j0 + wn * 8 * NT + ni * 8 + 2 * t;
-                    if (col < p.N) p.C[row + col * p.ldc] = acc[mi][ni][0];
-                    if (col + 1 < p.N) p.C[row + (col + 1) * p.ldc] = acc[mi][ni][1];
+                    if (col < p.N) Cout[row + col * ldo] = acc[mi][ni][0];
+                    if (col + 1 < p.N) Cout[row + (col + 1) * ldo] = acc[mi][ni][1];
                 }
             }
         }
@@ -414,6 +419,17 @@ tn_reduce_grouped_kernel(const double* __restrict__ P, int64_t ldp, int64_t pstr
     }
 }
 
+// C = sum_z P[z] for the split-K partials of gemm_nn, fixed order
+__global__ void __launch_bounds__(256)
+nn_reduce_kernel(const double* __restrict__ P, int64_t pstride, int ksplit, int64_t m, int64_t N, double* __restrict__ C, int64_t ldc) {
+    const int64_t total = m * N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int z = 0; z < ksplit; ++z) s += P[(int64_t)z * pstride + idx];
+        C[(idx % m) + (idx / m) * ldc] = s;
+    }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int NT, int GEN>
@@ -427,7 +443,7 @@ cudaError_t launch_nn_g(const GemmNN& p, int nblkN, cudaStream_t st) {
     }
     const int a_bulk = aligned16(p.A) && (p.lda % 2 == 0);
     const int b_bulk = !p.gen && aligned16(p.B) && (p.ldb % 2 == 0);
-    dim3 grid((unsigned)((p.m + BM - 1) / BM), (unsigned)nblkN);
+    dim3 grid((unsigned)((p.m + BM - 1) / BM), (unsigned)nblkN, (unsigned)p.ksplit);
     gemm_nn_kernel<NT, GEN><<<grid, NTHREADS, Cfg::SMEM, st>>>(p, a_bulk, b_bulk);
     ++g_kernel_launches;
     return cudaGetLastError();
@@ -457,6 +473,19 @@ TNPlan plan_tn(int64_t m, int64_t n, int64_t N, int sms) {
     const int64_t maxc = m / (16 * TN_BK) > 0 ? m / (16 * TN_BK) : 1;
     if (want > maxc) want = maxc;
     if (want < 1) want = 1;
+    // one CTA per SM: among the chunk counts around `want`, take the one whose tiles * chunks fills whole waves best
+    // (157 column blocks x 8 chunks = 8.49 waves at the headline size wastes 5.7 %; x 16 = 16.97 waves wastes 0.2 %)
+    {
+        double best = -1.0; int64_t bestc = want;
+        const int64_t lo = want / 2 > 1 ? want / 2 : 1, hi = want * 2 + 1 < maxc ? want * 2 + 1 : maxc;
+        for (int64_t cnd = lo; cnd <= hi; ++cnd) {
+            const int64_t units = tiles * cnd, waves = (units + sms - 1) / sms;
+            // the partials cost 2 * 8 bytes per output per chunk: a small penalty per extra chunk
+            const double eff = (double)units / (double)(waves * sms) - 0.0005 * (double)cnd;
+            if (eff > best + 1e-12) { best = eff; bestc = cnd; }
+        }
+        want = bestc;
+    }
     int64_t cr = (m + want - 1) / want;
     cr = (cr + TN_BK - 1) / TN_BK * TN_BK;
     if (cr <= 0) cr = TN_BK;
@@ -488,12 +517,7 @@ cudaError_t launch_tn(const GemmTN& p, const TNPlan& pl, double* ws, cudaStream_
 
 }  // namespace
 
-cudaError_t gemm_nn(const GemmNN& p, cudaStream_t st) {
-    if (p.m <= 0 || p.N <= 0) return cudaSuccess;
-    if (p.gen && (p.k_off & 3)) return cudaErrorInvalidValue;
-    const int nblkN = (int)((p.N + 127) / 128);
-    const int64_t per = (p.N + nblkN - 1) / nblkN;
-    const int NT = (int)((per + 15) / 16);
+static cudaError_t gemm_nn_dispatch(const GemmNN& p, int nblkN, int NT, cudaStream_t st) {
     switch (NT) {
         case 1: return launch_nn<1>(p, nblkN, st);
         case 2: return launch_nn<2>(p, nblkN, st);
@@ -504,6 +528,50 @@ cudaError_t gemm_nn(const GemmNN& p, cudaStream_t st) {
         case 7: return launch_nn<7>(p, nblkN, st);
         default: return launch_nn<8>(p, nblkN, st);
     }
+}
+
+cudaError_t gemm_nn(const GemmNN& p0, cudaStream_t st) {
+    if (p0.m <= 0 || p0.N <= 0) return cudaSuccess;
+    if (p0.gen && (p0.k_off & 3)) return cudaErrorInvalidValue;
+    GemmNN p = p0;
+    const int nblkN = (int)((p.N + 127) / 128);
+    const int64_t per = (p.N + nblkN - 1) / nblkN;
+    const int NT = (int)((per + 15) / 16);
+    // One CTA per SM and one 128-row tile per CTA: 1563 tiles on 148 SMs are 10.56 waves, i.e. 4 % of the machine idles
+    // in the last one (12 % at m = 50 000).  Splitting the K loop in s parts multiplies the number of (shorter) CTAs; take
+    // the s whose waves are fullest, net of the partial tiles' extra traffic (2 * 8 bytes per output and part).
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int64_t tiles = ((p.m + BM - 1) / BM) * nblkN;
+    const int KT = (int)((p.K + NN_BK - 1) / NN_BK);
+    int best_s = 1;
+    double best = -1.0;
+    for (int s = 1; s <= 4; ++s) {
+        if (s > 1 && KT / s < 64) break;
+        const int64_t units = tiles * s, waves = (units + sms - 1) / sms;
+        const double eff = (double)units / (double)(waves * sms) - (s > 1 ? 42.0 * s / (double)p.K + 0.002 : 0.0);
+        if (eff > best + 1e-9) { best = eff; best_s = s; }
+    }
+    if (best_s == 1) return gemm_nn_dispatch(p, nblkN, NT, st);
+    p.ksplit = best_s;
+    p.kt_per = (KT + best_s - 1) / best_s;
+    p.pstride = p.m * p.N;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p.P), (size_t)best_s * (size_t)p.pstride * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    e = gemm_nn_dispatch(p, nblkN, NT, st);
+    if (e == cudaSuccess) {
+        const int64_t total = p.m * p.N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > sms * 8) blocks = sms * 8;
+        nn_reduce_kernel<<<blocks, 256, 0, st>>>(p.P, p.pstride, p.ksplit, p.m, p.N, p.C, p.ldc);
+        ++g_kernel_launches;
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(p.P, st);
+    return e;
 }
 
 size_t gemm_tn_workspace_bytes(int64_t m, int64_t n, int64_t N, int sms) {

@@ -13,6 +13,8 @@ struct GemmNN {
     const double* B; int64_t ldb; int64_t N;
     double* C; int64_t ldc;
     int gen; int dist; uint64_t seed; uint32_t stream; uint64_t k_off;
+    // filled in by gemm_nn: split of the K loop over blockIdx.z (partials P[z], m x N packed, reduced in fixed order)
+    int ksplit = 1; int kt_per = 0; double* P = nullptr; int64_t pstride = 0;
 };
 
 // Z[n x N] = A[m x n]^T * Q[m x N]  (K = m is the long, streamed dimension; split over row chunks and

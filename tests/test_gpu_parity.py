@@ -101,7 +101,8 @@ def _dev(rt, a):
 
 
 GEMM_SHAPES = [(1, 1, 1), (7, 5, 3), (128, 32, 16), (129, 33, 17), (300, 70, 9), (1025, 515, 110), (777, 333, 210),
-               (4096, 2048, 128), (2000, 1000, 60), (513, 1, 40), (2, 4096, 5)]
+               (4096, 2048, 128), (2000, 1000, 60), (513, 1, 40), (2, 4096, 5),
+               (300, 9001, 40), (2100, 6200, 130)]   # the last two are long enough for the split-K path of gemm_nn
 
 
 @pytest.mark.parametrize("m,K,N", GEMM_SHAPES)
@@ -122,7 +123,7 @@ def test_gemm_nn_tn_vs_oracle(rb, orc, m, K, N):
 
 
 @pytest.mark.parametrize("dist", [0, 1, 2])
-@pytest.mark.parametrize("m,K,N", [(300, 70, 9), (1025, 516, 110), (513, 33, 210), (128, 4, 1)])
+@pytest.mark.parametrize("m,K,N", [(300, 70, 9), (1025, 516, 110), (513, 33, 210), (128, 4, 1), (260, 8200, 20)])
 def test_fused_sketch_gemm_equals_materialised(rb, orc, m, K, N, dist):
     """A * Omega with Omega generated inside the kernel is bit-identical to multiplying by the materialised Omega
     (same tiles, same DMMA order) and agrees with the oracle product on the oracle's own Omega."""
