@@ -175,7 +175,22 @@ rnla_status rnla_sketch_apply_dev(int32_t kind, int32_t dist, uint64_t seed, int
                                   const double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t row_offset,
                                   double* dA_sk, int64_t ld_sk);
 
+/* ---- blendenpik_overdetermined end to end (reference src/sketch_and_precondition.rs:26-59, src/cg.rs:18-61): sketch, QR of
+ * the sketch, z0 = Q^T b_sk, R^-1, CGLS on A R^-1 in OPERATOR form (the reference forms the dense product), x = R^-1 z.
+ * Validation and messages follow :29-48.  kind/dist/zeta as in rnla_sketch_apply (the reference's own choice is DENSE,
+ * GAUSSIAN).  x: n doubles.  iterations / converged (may be NULL): CGLS iterations used and whether ||s|| < epsilon fired
+ * (the reference only prints that).  A numerically singular R is RNLA_ERR_SINGULAR_MATRIX (the reference unwraps :55). */
+rnla_status rnla_blendenpik_overdetermined(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l,
+                                           double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* x,
+                                           int64_t* iterations, int32_t* converged);
+/* device buffers; A and b are the caller's row shard when a communicator is active, x is replicated */
+rnla_status rnla_blendenpik_overdetermined_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db,
+                                               double epsilon, int64_t l, double sampling_factor, int32_t kind, int32_t dist,
+                                               int32_t zeta, double* dx, int64_t* iterations, int32_t* converged);
+
 /* ---- building blocks on device buffers (tests, benches, host mirrors) ---------------------------- */
+/* y (m) = A x (trans = 0) or y (n) = A^T x (trans != 0, all-reduced over the communicator): the two streaming kernels of CGLS */
+rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int32_t trans, const double* dx, double* dy);
 /* C (m x N) = A (m x K) * B (K x N) */
 rnla_status rnla_gemm_nn_dev(const double* dA, int64_t lda, int64_t m, int64_t K,
                              const double* dB, int64_t ldb, int64_t N, double* dC, int64_t ldc);

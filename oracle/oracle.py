@@ -259,6 +259,31 @@ def sketch_apply_saso_block(A, d, zeta=8, seed=0, row_off=0, width=0):
     return out
 
 
+def cgls(a, b, tolerance, num_iterations, x0=None):
+    """src/cg.rs:18-61 -> (x, iterations, converged)"""
+    a = F(a); m, n = a.shape
+    b = F(np.asarray(b, dtype=np.float64).reshape(-1, 1))
+    x = F(np.zeros((n, 1)) if x0 is None else np.array(x0, dtype=np.float64).reshape(-1, 1))
+    conv = C.c_int(0)
+    lib = load()
+    lib.orc_cgls.restype = i64
+    it = lib.orc_cgls(p(a), i64(m), i64(n), p(b), C.c_double(tolerance), i64(num_iterations), p(x), C.byref(conv))
+    return x, int(it), bool(conv.value)
+
+
+def blendenpik(A, b, epsilon, l, sampling_factor, kind=0, dist_or_width=0, zeta=8, seed=0):
+    """src/sketch_and_precondition.rs:26-59 -> (x, iterations, converged); raises ValueError(code) on the reference's errors"""
+    A = F(A); m, n = A.shape
+    b = F(np.asarray(b, dtype=np.float64).reshape(-1, 1))
+    x = np.zeros((n, 1), order="F")
+    it = i64(0); conv = C.c_int(0)
+    rc = load().orc_blendenpik(p(A), i64(m), i64(n), p(b), C.c_double(epsilon), i64(l), C.c_double(sampling_factor), C.c_int(kind),
+                               C.c_int(dist_or_width), C.c_int(zeta), u64(seed), p(x), C.byref(it), C.byref(conv))
+    if rc:
+        raise ValueError(rc)
+    return x, int(it.value), bool(conv.value)
+
+
 def set_threads(n):
     load().orc_set_threads(C.c_int(n))
 

@@ -687,3 +687,79 @@ void orc_sketch_apply_saso_block(uint64_t seed, int64_t d, int zeta, int w, cons
         }
     for (int64_t i = 0; i < d * n; ++i) A_sk[i] *= scale;
 }
+
+/* ======================================================================== blendenpik + cgls
+ * src/cg.rs:18-61, statement for statement on a dense a (m x n) */
+int64_t orc_cgls(const double* a, int64_t m, int64_t n, const double* b, double tolerance, int64_t num_iterations,
+                 double* x /* in: initial guess, out: solution */, int* converged_out) {
+    double* r = dalloc(m); double* s = dalloc(n); double* p = dalloc(n); double* ap = dalloc(m); double* sn = dalloc(n);
+    orc_gemm_nn(a, m, m, n, x, n, 1, ap, m);
+    for (int64_t i = 0; i < m; ++i) r[i] = b[i] - ap[i];                                  /* :30 */
+    orc_gemm_tn(a, m, m, n, r, m, 1, s, n);                                               /* :31 */
+    memcpy(p, s, (size_t)n * sizeof(double));                                             /* :32 */
+    double norm_s = 0.0; for (int64_t i = 0; i < n; ++i) norm_s += s[i] * s[i];           /* :33 */
+    int converged = 0; int64_t it = 0;
+    for (it = 0; it < num_iterations; ++it) {                                             /* :35 */
+        orc_gemm_nn(a, m, m, n, p, n, 1, ap, m);                                          /* :36 */
+        double apap = 0.0; for (int64_t i = 0; i < m; ++i) apap += ap[i] * ap[i];
+        const double alpha = norm_s / apap;                                               /* :37 */
+        for (int64_t i = 0; i < n; ++i) x[i] += alpha * p[i];                             /* :38 */
+        for (int64_t i = 0; i < m; ++i) r[i] -= alpha * ap[i];                            /* :39 */
+        orc_gemm_tn(a, m, m, n, r, m, 1, sn, n);                                          /* :40 */
+        double nn = 0.0; for (int64_t i = 0; i < n; ++i) nn += sn[i] * sn[i];             /* :41 */
+        if (sqrt(nn) < tolerance) { converged = 1; ++it; break; }                         /* :44-48 */
+        const double beta = nn / norm_s;                                                  /* :50 */
+        norm_s = nn;                                                                      /* :51 */
+        for (int64_t i = 0; i < n; ++i) p[i] = sn[i] + beta * p[i];                       /* :52 */
+    }
+    if (converged_out) *converged_out = converged;
+    free(r); free(s); free(p); free(ap); free(sn);
+    return it;
+}
+
+/* src/sketch_and_precondition.rs:26-59; the sketch operator is this build's (kind 0 dense / 1 SASO / 2 block SASO, the
+ * reference draws a dense Gaussian from its own stream); everything after the sketch follows the
+ * reference literally, including the dense product A R^-1 (:56).  Returns 0, or 4/1 for the validation errors (:29-48),
+ * or 6 if R is singular (the reference unwraps :55). */
+int orc_blendenpik(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l, double sampling_factor,
+                   int kind, int dist_or_width, int zeta, uint64_t seed, double* x, int64_t* iters_out, int* converged_out) {
+    if (m < n) return 4;                                                                  /* :29-33 */
+    if (sampling_factor < 1.0 || epsilon <= 0.0 || l <= 0) return 1;                      /* :34-48 */
+    const int64_t d = orc_sketch_dim(m, n, sampling_factor, 0);                           /* :49 */
+    double* Ask = dalloc(d * n); double* bsk = dalloc(d);
+    if (kind == 0) { orc_sketch_apply_dense(dist_or_width, seed, d, A, m, n, Ask); orc_sketch_apply_dense(dist_or_width, seed, d, b, m, 1, bsk); }
+    else if (kind == 1) { orc_sketch_apply_saso(seed, d, zeta, A, m, n, Ask); orc_sketch_apply_saso(seed, d, zeta, b, m, 1, bsk); }
+    else {
+        const int w = dist_or_width ? dist_or_width : (zeta < 4 ? zeta : 4);
+        orc_sketch_apply_saso_block(seed, d, zeta, w, A, m, n, 0, Ask); orc_sketch_apply_saso_block(seed, d, zeta, w, b, m, 1, 0, bsk);
+    }
+    double* Q = dalloc(d * n); double* R = dalloc(n * n);
+    orc_qr(Ask, d, n, Q, R);                                                              /* :53 */
+    double* z = dalloc(n);
+    orc_gemm_tn(Q, d, d, n, bsk, d, 1, z, n);                                             /* :54 */
+    double* Rinv = dalloc(n * n);                                                         /* :55 solve_upper_triangular(I) */
+    int singular = 0;
+    for (int64_t j = 0; j < n && !singular; ++j) {
+        for (int64_t i = j; i >= 0; --i) {
+            double sum = (i == j) ? 1.0 : 0.0;
+            for (int64_t k = i + 1; k <= j; ++k) sum -= AT(R, n, i, k) * AT(Rinv, n, k, j);
+            const double dii = AT(R, n, i, i);
+            if (dii == 0.0) { singular = 1; break; }
+            AT(Rinv, n, i, j) = sum / dii;
+        }
+    }
+    int rc = 0;
+    if (singular) rc = 6;
+    else {
+        double* Ap = dalloc(m * n);
+        orc_gemm_nn(A, m, m, n, Rinv, n, n, Ap, m);                                       /* :56 */
+        int conv = 0;
+        const int64_t it = orc_cgls(Ap, m, n, b, epsilon, l, z, &conv);                   /* :57 */
+        orc_gemm_nn(Rinv, n, n, n, z, n, 1, x, n);                                        /* :58 */
+        if (iters_out) *iters_out = it;
+        if (converged_out) *converged_out = conv;
+        free(Ap);
+    }
+    free(Ask); free(bsk); free(Q); free(R); free(z); free(Rinv);
+    return rc;
+}

@@ -64,6 +64,9 @@ SIGNATURES = {
     "rnla_orth_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, C.POINTER(c_i64)]),
     "rnla_small_svd_dev": (c_i32, [P, c_i64, c_i64, P, P, P]),
     "rnla_last_jacobi_sweeps": (c_i32, []),
+    "rnla_gemv_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, P]),
+    "rnla_blendenpik_overdetermined": (c_i32, [P, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
+    "rnla_blendenpik_overdetermined_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
     "rnla_small_eigh_dev": (c_i32, [P, c_i64, c_i64, P, P]),
     "rnla_generate_lowrank_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, P, c_f64, c_u64]),
     "rnla_measure_roofs": (c_i32, [C.POINTER(c_f64), C.POINTER(c_f64), C.c_size_t]),

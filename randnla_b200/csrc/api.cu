@@ -429,6 +429,54 @@ rnla_status rnla_gemm_nn_dev(const double* dA, int64_t lda, int64_t m, int64_t K
     RNLA_TRY(ensure_ctx());
     return dev_gemm_nn(dA, lda, m, K, dB, ldb, N, dC, ldc);
 }
+// ---- blendenpik_overdetermined, end to end (reference src/sketch_and_precondition.rs:26-59)
+static rnla_status validate_lsq(int64_t m, int64_t n, double epsilon, int64_t l, double sampling_factor) {
+    char buf[160];
+    if (m < n) {                                                                                   // :29-33
+        snprintf(buf, sizeof buf, "Need more columns than rows, found %lld rows and %lld columns", (long long)m, (long long)n);
+        return fail(RNLA_ERR_NOT_OVERDETERMINED, buf);
+    }
+    if (sampling_factor < 1.0) {                                                                   // :34-38
+        snprintf(buf, sizeof buf, "Sampling factor must be greater than 1, current input is %g", sampling_factor);
+        return fail(RNLA_ERR_INVALID_PARAMETERS, buf);
+    }
+    if (epsilon <= 0.0) {                                                                          // :39-43
+        snprintf(buf, sizeof buf, "Epsilon must be positive, current input is %g", epsilon);
+        return fail(RNLA_ERR_INVALID_PARAMETERS, buf);
+    }
+    if (l <= 0) {                                                                                  // :44-48
+        snprintf(buf, sizeof buf, "Number of iterations must be positive, current input is %lld", (long long)l);
+        return fail(RNLA_ERR_INVALID_PARAMETERS, buf);
+    }
+    return RNLA_OK;
+}
+rnla_status rnla_blendenpik_overdetermined_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db,
+                                               double epsilon, int64_t l, double sampling_factor, int32_t kind, int32_t dist,
+                                               int32_t zeta, double* dx, int64_t* iterations, int32_t* converged) {
+    RNLA_TRY(ensure_ctx());
+    ShardInfo sh;
+    RNLA_TRY(shard_layout(m_local, &sh));
+    RNLA_TRY(validate_lsq(sh.rows_global, n, epsilon, l, sampling_factor));
+    return dev_blendenpik(dA, lda, m_local, n, db, epsilon, l, sampling_factor, kind, dist, zeta, ctx().opts.seed, dx, iterations, converged);
+}
+rnla_status rnla_blendenpik_overdetermined(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l,
+                                           double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* x,
+                                           int64_t* iterations, int32_t* converged) {
+    RNLA_TRY(validate_lsq(m, n, epsilon, l, sampling_factor));
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, db, dx;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_TRY(h2d(db, b, (size_t)m));
+    RNLA_CUDA(dx.alloc((size_t)n * 8));
+    RNLA_TRY(dev_blendenpik(dA.d(), m, m, n, db.d(), epsilon, l, sampling_factor, kind, dist, zeta, ctx().opts.seed, dx.d(), iterations, converged));
+    return d2h(x, dx.d(), (size_t)n);
+}
+
+rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int32_t trans, const double* dx, double* dy) {
+    RNLA_TRY(ensure_ctx());
+    return trans ? dev_gemv_t(dA, lda, m, n, dx, dy) : dev_gemv_n(dA, lda, m, n, dx, dy);
+}
+
 rnla_status rnla_sketch_gemm_dev(const double* dA, int64_t lda, int64_t m, int64_t K, int32_t dist, uint64_t seed, uint32_t stream,
                                  int64_t N, double* dC, int64_t ldc) {
     RNLA_TRY(ensure_ctx());

@@ -35,6 +35,17 @@ rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const do
 
 extern int g_last_jacobi_sweeps;
 
+// solve.cu: blendenpik_overdetermined end to end on the device
+rnla_status dev_sketch_apply(int kind, int dist, uint64_t seed, int64_t d, int zeta, const double* dA, int64_t lda,
+                             int64_t m_local, int64_t n, int64_t row_offset, double* dAsk, int64_t ldk);
+rnla_status dev_gemv_n(const double* A, int64_t lda, int64_t m, int64_t n, const double* x, double* y);
+rnla_status dev_gemv_t(const double* A, int64_t lda, int64_t m, int64_t n, const double* r, double* u);
+rnla_status dev_qr_blocked(double* X, int64_t ldx, int64_t rows, int n, double* R, int64_t* deficient);
+rnla_status dev_tri_inv_blocked(const double* R, int64_t ldr, int n, double* Rinv, int64_t ldi);
+rnla_status dev_blendenpik(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double epsilon,
+                           int64_t maxit, double sampling_factor, int kind, int dist_or_width, int zeta, uint64_t seed,
+                           double* x, int64_t* iters_out, int32_t* converged_out);
+
 // literal.cu: bug-compatible pieces of the reference
 rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
                           const rnla_options& o, double* S);

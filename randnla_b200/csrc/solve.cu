@@ -1,0 +1,350 @@
+// Next row after the sketch step: `blendenpik_overdetermined` end to end on the device
+// (reference src/sketch_and_precondition.rs:26-59 and src/cg.rs:18-61).
+//
+//   d = min(m, floor(sf n))                                       :49
+//   A_sk = S A, b_sk = S b                                        :50-52   (dense Gaussian or sparse-sign S, sketch_apply.cu)
+//   A_sk = Q R                                                    :53      blocked Gram-Schmidt over 128-column panels, each
+//                                                                          panel orthonormalised by CholeskyQR2 (drivers.cu)
+//   z0 = Q^T b_sk                                                 :54
+//   Rinv = R^-1                                                   :55      blocked back-substitution (diagonal blocks in shared memory)
+//   z = cgls(A Rinv, b, eps, l, z0)                               :56-57   OPERATOR FORM: the reference forms the dense m x n
+//                                                                          product A Rinv; here every iteration applies Rinv
+//                                                                          (n x n, L2-resident) and streams A twice
+//   x = Rinv z                                                    :58
+//
+// Per CGLS iteration the HBM traffic is 2 x 8 m n bytes (A once for A t, once for A^T r): two HBM-bound matrix-vector
+// kernels below, written for a column-major tall A.  Row-sharded A: A t is local, A^T r is all-reduced (n doubles).
+#include "drivers.cuh"
+#include "gemm.cuh"
+#include "panel.cuh"
+#include "ptx.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace rnla {
+
+namespace {
+
+// y (m) = A (m x n) x (n): one thread per pair of rows, columns walked in order (coalesced 16-byte loads), x from shared memory
+constexpr int GV_T = 256;
+constexpr int GV_XCH = 2048;          // columns of x staged per pass
+__global__ void __launch_bounds__(GV_T)
+gemv_n_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, const double* __restrict__ x, double* __restrict__ y) {
+    __shared__ double xs[GV_XCH];
+    const int64_t i = ((int64_t)blockIdx.x * GV_T + threadIdx.x) * 2;
+    const bool vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0);
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t c0 = 0; c0 < n; c0 += GV_XCH) {
+        const int nc = (int)min((int64_t)GV_XCH, n - c0);
+        __syncthreads();
+        for (int c = threadIdx.x; c < nc; c += GV_T) xs[c] = x[c0 + c];
+        __syncthreads();
+        if (i + 1 < m && vec) {
+            const double* p = A + i + c0 * lda;
+#pragma unroll 8
+            for (int c = 0; c < nc; ++c) {
+                double2 v;
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + (int64_t)c * lda));
+                a0 = fma(v.x, xs[c], a0); a1 = fma(v.y, xs[c], a1);
+            }
+        } else if (i < m) {
+            const double* p = A + i + c0 * lda;
+            const bool two = i + 1 < m;
+#pragma unroll 4
+            for (int c = 0; c < nc; ++c) {
+                a0 = fma(ldg_stream(p + (int64_t)c * lda), xs[c], a0);
+                if (two) a1 = fma(ldg_stream(p + (int64_t)c * lda + 1), xs[c], a1);
+            }
+        }
+    }
+    if (i < m) y[i] = a0;
+    if (i + 1 < m) y[i + 1] = a1;
+}
+
+// partial u (n) = A(rows of this split, :)^T r: one CTA per (4 columns, row split); fixed-order reductions throughout
+constexpr int GT_CB = 4;
+__global__ void __launch_bounds__(GV_T)
+gemv_t_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, const double* __restrict__ r,
+              int64_t rows_per_split, double* __restrict__ part /* [nsplit][n] */) {
+    __shared__ double red[GV_T / 32][GT_CB];
+    const int64_t c0 = (int64_t)blockIdx.x * GT_CB;
+    const int64_t i0 = (int64_t)blockIdx.y * rows_per_split, i1 = min(m, i0 + rows_per_split);
+    double acc[GT_CB] = {0.0, 0.0, 0.0, 0.0};
+    const int ncv = (int)min((int64_t)GT_CB, n - c0);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += GV_T) {
+        const double ri = r[i];
+#pragma unroll
+        for (int c = 0; c < GT_CB; ++c)
+            if (c < ncv) acc[c] = fma(ldg_stream(A + i + (c0 + c) * lda), ri, acc[c]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < GT_CB; ++c) {
+        double v = acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < ncv) {
+        double s = 0.0;
+        for (int w = 0; w < GV_T / 32; ++w) s += red[w][threadIdx.x];
+        part[(int64_t)blockIdx.y * n + c0 + threadIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256)
+gemv_t_reduce_kernel(const double* __restrict__ part, int nsplit, int64_t n, double* __restrict__ u) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double s = 0.0;
+    for (int k = 0; k < nsplit; ++k) s += part[(int64_t)k * n + c];
+    u[c] = s;
+}
+
+// small dense mat-vec on an L2-resident n x n matrix: y = M x (trans = 0) or M^T x (trans = 1); one warp per output
+__global__ void __launch_bounds__(256)
+small_gemv_kernel(const double* __restrict__ M, int64_t ld, int n, int trans, const double* __restrict__ x, double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= n) return;
+    double s = 0.0;
+    if (trans) { for (int k = lane; k < n; k += 32) s = fma(M[k + (int64_t)o * ld], x[k], s); }
+    else { for (int k = lane; k < n; k += 32) s = fma(M[o + (int64_t)k * ld], x[k], s); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) y[o] = s;
+}
+
+// out[0] = x . y, deterministic two-stage reduction
+__global__ void __launch_bounds__(256)
+dot_partial_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n, double* __restrict__ scratch) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = fma(x[i], y[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w]; scratch[blockIdx.x] = t; }
+}
+__global__ void dot_final_kernel(const double* __restrict__ scratch, int nb, double* __restrict__ out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 32) s += scratch[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = s;
+}
+// y = a x + b y
+__global__ void __launch_bounds__(256)
+axpby_vec_kernel(double a, const double* __restrict__ x, double b, double* __restrict__ y, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = a * x[i] + b * y[i];
+}
+__global__ void __launch_bounds__(256)
+negate_kernel(double* __restrict__ X, int64_t ld, int64_t rows, int64_t cols) {
+    const int64_t total = rows * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / rows, r = idx - c * rows;
+        X[r + c * ld] = -X[r + c * ld];
+    }
+}
+
+inline int blocks_for(int64_t n, int cap = 148 * 8) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, cap)); }
+
+struct Solver {
+    Ctx& c;
+    DevBuf scratch, scal;
+    explicit Solver(Ctx& cc) : c(cc) {}
+    rnla_status init() { RNLA_CUDA(scratch.alloc(2048 * 8)); RNLA_CUDA(scal.alloc(8)); return RNLA_OK; }
+    // host value of x . y (all-reduced over the row shards when `sharded`)
+    rnla_status dot(const double* x, const double* y, int64_t n, bool sharded, double* out) {
+        const int nb = blocks_for(n, 1024);
+        dot_partial_kernel<<<nb, 256, 0, c.stream>>>(x, y, n, scratch.d());
+        dot_final_kernel<<<1, 32, 0, c.stream>>>(scratch.d(), nb, scal.d());
+        g_kernel_launches += 2;
+        RNLA_CUDA(cudaGetLastError());
+        if (sharded && c.nranks > 1) RNLA_TRY(allreduce_sum_f64(scal.d(), 1));
+        RNLA_CUDA(cudaMemcpyAsync(out, scal.p, 8, cudaMemcpyDeviceToHost, c.stream));
+        RNLA_CUDA(cudaStreamSynchronize(c.stream));
+        return RNLA_OK;
+    }
+    rnla_status axpby(double a, const double* x, double b, double* y, int64_t n) {
+        if (n <= 0) return RNLA_OK;
+        axpby_vec_kernel<<<blocks_for(n), 256, 0, c.stream>>>(a, x, b, y, n);
+        ++g_kernel_launches;
+        RNLA_CUDA(cudaGetLastError());
+        return RNLA_OK;
+    }
+    rnla_status small_gemv(const double* M, int64_t ld, int n, int trans, const double* x, double* y) {
+        small_gemv_kernel<<<(n + 7) / 8, 256, 0, c.stream>>>(M, ld, n, trans, x, y);
+        ++g_kernel_launches;
+        RNLA_CUDA(cudaGetLastError());
+        return RNLA_OK;
+    }
+};
+
+}  // namespace
+
+// y (m_local) = A x
+rnla_status dev_gemv_n(const double* A, int64_t lda, int64_t m, int64_t n, const double* x, double* y) {
+    Ctx& c = ctx();
+    if (m <= 0) return RNLA_OK;
+    gemv_n_kernel<<<(unsigned)((m + 2 * GV_T - 1) / (2 * GV_T)), GV_T, 0, c.stream>>>(A, lda, m, n, x, y);
+    ++g_kernel_launches;
+    RNLA_CUDA(cudaGetLastError());
+    return RNLA_OK;
+}
+// u (n) = A^T r, all-reduced over the row shards
+rnla_status dev_gemv_t(const double* A, int64_t lda, int64_t m, int64_t n, const double* r, double* u) {
+    Ctx& c = ctx();
+    const int ncg = (int)((n + GT_CB - 1) / GT_CB);
+    int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>((8LL * c.sms + ncg - 1) / ncg, std::max<int64_t>(1, m / 4096)));
+    const int64_t rps = ((std::max<int64_t>(m, 1) + nsplit - 1) / nsplit + 255) / 256 * 256;
+    nsplit = (int)std::max<int64_t>(1, (std::max<int64_t>(m, 1) + rps - 1) / rps);
+    DevBuf part;
+    RNLA_CUDA(part.alloc((size_t)nsplit * n * 8));
+    gemv_t_kernel<<<dim3((unsigned)ncg, (unsigned)nsplit), GV_T, 0, c.stream>>>(A, lda, m, n, r, rps, part.d());
+    gemv_t_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(part.d(), nsplit, n, u);
+    g_kernel_launches += 2;
+    RNLA_CUDA(cudaGetLastError());
+    if (c.nranks > 1) RNLA_TRY(allreduce_sum_f64(u, (size_t)n));
+    return RNLA_OK;
+}
+
+// X (rows x n, replicated) -> Q in place, R (n x n, ld n): block classical Gram-Schmidt with re-orthogonalisation over
+// panels of <= 128 columns; each panel finished by CholeskyQR2.  *deficient = number of dependent columns met.
+rnla_status dev_qr_blocked(double* X, int64_t ldx, int64_t rows, int n, double* R, int64_t* deficient) {
+    Ctx& c = ctx();
+    constexpr int PW = 128;
+    RNLA_CUDA(axpby_matrix(0.0, nullptr, 0, 0.0, nullptr, 0, R, n, n, n, c.stream));
+    DevBuf Cc, T, Rjj;
+    RNLA_CUDA(Cc.alloc((size_t)n * PW * 8)); RNLA_CUDA(T.alloc((size_t)rows * PW * 8)); RNLA_CUDA(Rjj.alloc((size_t)PW * PW * 8));
+    ShardInfo sh{rows, 0, rows};
+    int64_t def_total = 0;
+    for (int j0 = 0; j0 < n; j0 += PW) {
+        const int w = std::min(PW, n - j0);
+        double* XJ = X + (int64_t)j0 * ldx;
+        for (int rep = 0; rep < 2 && j0 > 0; ++rep) {
+            RNLA_TRY(dev_gemm_tn(X, ldx, rows, j0, XJ, ldx, w, Cc.d(), j0, false));                    // C = Q_prev^T X_J
+            RNLA_TRY(dev_gemm_nn(X, ldx, rows, j0, Cc.d(), j0, w, T.d(), rows));                       // T = Q_prev C
+            RNLA_CUDA(axpby_matrix(1.0, XJ, ldx, -1.0, T.d(), rows, XJ, ldx, rows, w, c.stream));      // X_J -= T
+            RNLA_CUDA(axpby_matrix(1.0, R + (int64_t)j0 * n, n, 1.0, Cc.d(), j0, R + (int64_t)j0 * n, n, j0, w, c.stream));   // R_{0:j0,J} += C
+        }
+        int64_t def = 0;
+        RNLA_TRY(orth_inplace(XJ, ldx, sh, w, false, Rjj.d(), &def));
+        def_total += def;
+        // the second projection's coefficients were taken before the panel was normalised: R_{0:j0,J} is exact as accumulated
+        RNLA_CUDA(copy_matrix(Rjj.d(), w, R + j0 + (int64_t)j0 * n, n, w, w, c.stream));
+    }
+    if (deficient) *deficient = def_total;
+    return RNLA_OK;
+}
+
+// Rinv = R^-1 for upper-triangular R (n x n): column panels left to right,
+// Rinv_JJ = inv(R_JJ) in shared memory, Rinv_{0:j0,J} = - Rinv_{0:j0,0:j0} R_{0:j0,J} Rinv_JJ (two GEMMs)
+rnla_status dev_tri_inv_blocked(const double* R, int64_t ldr, int n, double* Rinv, int64_t ldi) {
+    Ctx& c = ctx();
+    constexpr int PW = 128;
+    RNLA_CUDA(axpby_matrix(0.0, nullptr, 0, 0.0, nullptr, 0, Rinv, ldi, n, n, c.stream));
+    DevBuf T;
+    RNLA_CUDA(T.alloc((size_t)n * PW * 8));
+    for (int j0 = 0; j0 < n; j0 += PW) {
+        const int w = std::min(PW, n - j0);
+        double* XJJ = Rinv + j0 + (int64_t)j0 * ldi;
+        RNLA_CUDA(tri_inv_upper(R + j0 + (int64_t)j0 * ldr, ldr, w, XJJ, ldi, c.stream));
+        if (j0 > 0) {
+            RNLA_TRY(dev_gemm_nn(Rinv, ldi, j0, j0, R + (int64_t)j0 * ldr, ldr, w, T.d(), j0));           // T = Rinv_00 R_0J
+            RNLA_TRY(dev_gemm_nn(T.d(), j0, j0, w, XJJ, ldi, w, Rinv + (int64_t)j0 * ldi, ldi));          // Rinv_0J = T Rinv_JJ
+            negate_kernel<<<blocks_for((int64_t)j0 * w), 256, 0, c.stream>>>(Rinv + (int64_t)j0 * ldi, ldi, j0, w);
+            ++g_kernel_launches;
+            RNLA_CUDA(cudaGetLastError());
+        }
+    }
+    return RNLA_OK;
+}
+
+// blendenpik_overdetermined on device buffers.  A: m_local x n (row shard), b: m_local.  x: n (replicated).
+// iters_out: CGLS iterations used; converged_out: 1 if the reference's stopping rule ||s|| < epsilon fired.
+rnla_status dev_blendenpik(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double epsilon,
+                           int64_t maxit, double sampling_factor, int kind, int dist_or_width, int zeta, uint64_t seed,
+                           double* x, int64_t* iters_out, int32_t* converged_out) {
+    Ctx& c = ctx();
+    phases_reset();
+    ShardInfo sh;
+    RNLA_TRY(shard_layout(m_local, &sh));
+    const int64_t m = sh.rows_global;
+    if (n <= 0 || n > 16384) return fail(RNLA_ERR_INVALID_DIMENSIONS, "blendenpik (device): 1 <= n <= 16384");
+    const int64_t d = (sampling_factor * (double)n > (double)m) ? m : (int64_t)std::floor(sampling_factor * (double)n);   // :49
+    const int nn = (int)n;
+    Solver S(c);
+    RNLA_TRY(S.init());
+    DevBuf Ask, bsk, R, Rinv, z, r, s, p, t, ap, u;
+    RNLA_CUDA(Ask.alloc((size_t)d * n * 8)); RNLA_CUDA(bsk.alloc((size_t)d * 8));
+    RNLA_CUDA(R.alloc((size_t)n * n * 8)); RNLA_CUDA(Rinv.alloc((size_t)n * n * 8));
+    const int64_t mm = std::max<int64_t>(m_local, 1);
+    RNLA_CUDA(z.alloc((size_t)n * 8)); RNLA_CUDA(s.alloc((size_t)n * 8)); RNLA_CUDA(p.alloc((size_t)n * 8));
+    RNLA_CUDA(t.alloc((size_t)n * 8)); RNLA_CUDA(u.alloc((size_t)n * 8));
+    RNLA_CUDA(r.alloc((size_t)mm * 8)); RNLA_CUDA(ap.alloc((size_t)mm * 8));
+    {
+        // the sketch step: the same operator S for A and b                                                    :50-52
+        RNLA_TRY(dev_sketch_apply(kind, dist_or_width, seed, d, zeta, A, lda, m_local, n, sh.row_off, Ask.d(), d));
+        // dev_sketch_apply resets nothing: its own phase is recorded; b_sk silently (a d-vector)
+        RNLA_TRY(dev_sketch_apply(kind, dist_or_width, seed, d, zeta, b, mm, m_local, 1, sh.row_off, bsk.d(), d));
+    }
+    {
+        PhaseScope ph("precond:qr(A_sk)");
+        int64_t def = 0;
+        RNLA_TRY(dev_qr_blocked(Ask.d(), d, d, nn, R.d(), &def));                                             // :53
+        // the reference unwraps `solve_upper_triangular` (:55): a singular R is an error there too
+        std::vector<double> diag((size_t)n);
+        RNLA_CUDA(cudaMemcpy2DAsync(diag.data(), 8, R.d(), (size_t)(n + 1) * 8, 8, (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+        RNLA_CUDA(cudaStreamSynchronize(c.stream));
+        double dmax = 0.0, dmin = INFINITY;
+        for (double v : diag) { dmax = std::max(dmax, std::fabs(v)); dmin = std::min(dmin, std::fabs(v)); }
+        if (def || !(dmin > 1e-13 * dmax))
+            return fail(RNLA_ERR_SINGULAR_MATRIX, "blendenpik: the sketch of A is numerically rank deficient, R cannot be inverted");
+    }
+    {
+        PhaseScope ph("precond:z0,Rinv");
+        RNLA_TRY(dev_gemm_tn(Ask.d(), d, d, n, bsk.d(), d, 1, z.d(), n, false));                               // z0 = Q^T b_sk   :54
+        RNLA_TRY(dev_tri_inv_blocked(R.d(), n, nn, Rinv.d(), n));                                             // :55
+    }
+    int64_t it = 0; int32_t conv = 0;
+    {
+        PhaseScope ph("cgls");
+        // cgls(a = A Rinv, b, tolerance, num_iterations, x = z0)                                              cg.rs:18-61
+        RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 0, z.d(), t.d()));                                             // t = Rinv x
+        RNLA_TRY(dev_gemv_n(A, lda, m_local, n, t.d(), ap.d()));                                              // a x
+        RNLA_CUDA(cudaMemcpyAsync(r.p, b, (size_t)m_local * 8, cudaMemcpyDeviceToDevice, c.stream));
+        RNLA_TRY(S.axpby(-1.0, ap.d(), 1.0, r.d(), m_local));                                                 // r = b - a x       :30
+        RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), u.d()));
+        RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 1, u.d(), s.d()));                                             // s = a^T r          :31
+        RNLA_CUDA(cudaMemcpyAsync(p.p, s.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c.stream));              // p = s              :32
+        double norm_s = 0.0;
+        RNLA_TRY(S.dot(s.d(), s.d(), n, false, &norm_s));                                                     // :33
+        for (it = 0; it < maxit; ++it) {
+            RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 0, p.d(), t.d()));
+            RNLA_TRY(dev_gemv_n(A, lda, m_local, n, t.d(), ap.d()));                                          // ap = a p           :36
+            double apap = 0.0;
+            RNLA_TRY(S.dot(ap.d(), ap.d(), m_local, true, &apap));
+            const double alpha = norm_s / apap;                                                               // :37
+            RNLA_TRY(S.axpby(alpha, p.d(), 1.0, z.d(), n));                                                   // x += alpha p       :38
+            RNLA_TRY(S.axpby(-alpha, ap.d(), 1.0, r.d(), m_local));                                           // r -= alpha ap      :39
+            RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), u.d()));
+            RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 1, u.d(), s.d()));                                         // s_new = a^T r      :40
+            double norm_new = 0.0;
+            RNLA_TRY(S.dot(s.d(), s.d(), n, false, &norm_new));                                               // :41
+            if (std::sqrt(norm_new) < epsilon) { conv = 1; ++it; break; }                                     // :44-48
+            const double beta = norm_new / norm_s;                                                            // :50
+            norm_s = norm_new;
+            RNLA_TRY(S.axpby(1.0, s.d(), beta, p.d(), n));                                                    // p = s_new + beta p :52
+        }
+    }
+    RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 0, z.d(), x));                                                     // x = Rinv z         :58
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    if (iters_out) *iters_out = it;
+    if (converged_out) *converged_out = conv;
+    return RNLA_OK;
+}
+
+}  // namespace rnla

@@ -8,6 +8,8 @@ import numpy as np
 from . import _lib
 from ._lib import check
 from . import runtime
+import ctypes as C
+
 from .errors import InvalidParameters, NotOverdetermined
 
 SKETCH_DENSE, SKETCH_SASO, SKETCH_SASO_BLOCK = 0, 1, 2
@@ -71,3 +73,21 @@ def saddle_point_sketch(a, b, c, mu, epsilon, l, sampling_factor, kind=SKETCH_DE
     _validate(a, epsilon, l, sampling_factor)
     d = sketch_dim(a.shape[0], a.shape[1], sampling_factor, saddle=True)
     return sketch_apply(a, None, d, kind=kind, zeta=zeta, seed=runtime.get_options().seed)
+
+
+def blendenpik_overdetermined(a, b, epsilon, l, sampling_factor, kind=SKETCH_DENSE, zeta=8, width=0, info=None):
+    """`blendenpik_overdetermined` end to end (reference :26-59): sketch, QR of the sketch, CGLS on A R^-1 in operator
+    form, x = R^-1 z.  Same validation, same errors.  kind / zeta / width choose the sketch operator (the reference's own
+    is the dense Gaussian, the default here).  `info`, if a dict, receives the CGLS iteration count and convergence flag."""
+    lib = _lib.load()
+    a = runtime.as_f(a)
+    b = runtime.as_f(b)
+    m, n = a.shape
+    x = np.empty((n, 1), dtype=np.float64, order="F")
+    it = C.c_int64(0); conv = C.c_int32(0)
+    dist = width if kind == SKETCH_SASO_BLOCK else runtime.GAUSSIAN
+    check(lib.rnla_blendenpik_overdetermined(runtime.ptr(a), m, n, runtime.ptr(b), float(epsilon), int(l), float(sampling_factor),
+                                             kind, dist, zeta, runtime.ptr(x), C.byref(it), C.byref(conv)))
+    if info is not None:
+        info["iterations"] = int(it.value); info["converged"] = bool(conv.value)
+    return x

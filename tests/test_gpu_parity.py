@@ -574,6 +574,73 @@ def test_sketch_saso_block_errors_and_embedding(rb, orc):
         assert 0.25 < sv.min() and sv.max() < 1.8
 
 
+# ---------------------------------------------------------------- next row: blendenpik end to end
+@pytest.mark.parametrize("kind,zeta", [(0, 8), (2, 8), (1, 8)])
+@pytest.mark.parametrize("m,n,cond", [(6000, 40, 1e2), (9000, 300, 1e5)])
+def test_blendenpik_end_to_end(rb, orc, kind, zeta, m, n, cond):
+    """sketch -> QR -> z0 -> R^-1 -> CGLS (operator form on the device, dense product in the oracle as in the reference
+    src/sketch_and_precondition.rs:53-58) -> x.  Same sketch operator on both sides, so the preconditioner, the
+    iteration count and the solution agree; and x solves the least-squares problem."""
+    from randnla_b200 import sketch_and_precondition as sp
+    rng = np.random.default_rng(n)
+    U, _ = np.linalg.qr(rng.standard_normal((m, n))); V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = np.asfortranarray((U * np.logspace(0, -np.log10(cond), n)) @ V.T)
+    xt = rng.uniform(-100, 100, (n, 1))
+    b = A @ xt + 1e-2 * rng.standard_normal((m, 1))
+    info = {}
+    x = sp.blendenpik_overdetermined(A, b, 1e-10, 200, 4.0, kind=kind, zeta=zeta, info=info)
+    xo, ito, convo = orc.blendenpik(A, b, 1e-10, 200, 4.0, kind=kind, zeta=zeta)
+    xl = np.linalg.lstsq(A, b, rcond=None)[0]
+    nrm = np.linalg.norm(xl)
+    assert info["converged"] and convo
+    assert abs(info["iterations"] - ito) <= 2 and info["iterations"] < 80
+    assert np.linalg.norm(x - xo) <= 1e-8 * nrm
+    assert np.linalg.norm(x - xl) <= 1e-7 * nrm * max(1.0, cond * 1e-5)
+    # normal equations residual: A^T (b - A x) ~ 0
+    assert np.linalg.norm(A.T @ (b - A @ x)) <= 1e-8 * np.linalg.norm(A.T @ b)
+
+
+def test_blendenpik_reference_errors(rb):
+    """src/sketch_and_precondition.rs:229-290 test_blendenpik_overdetermined: Err for sampling_factor < 1, epsilon <= 0, l = 0,
+    and for an underdetermined system"""
+    from randnla_b200 import sketch_and_precondition as sp
+    from randnla_b200.errors import InvalidParameters, NotOverdetermined, SingularMatrix
+    A = random_matrix(50, 5, seed=1); b = random_matrix(50, 1, seed=2)
+    with pytest.raises(InvalidParameters):
+        sp.blendenpik_overdetermined(A, b, 1e-6, 10, 0.5)
+    with pytest.raises(InvalidParameters):
+        sp.blendenpik_overdetermined(A, b, 0.0, 10, 2.0)
+    with pytest.raises(InvalidParameters):
+        sp.blendenpik_overdetermined(A, b, 1e-6, 0, 2.0)
+    with pytest.raises(NotOverdetermined):
+        sp.blendenpik_overdetermined(A.T.copy(), random_matrix(5, 1, seed=3), 1e-6, 10, 2.0)
+    Z = A.copy(); Z[:, 3] = Z[:, 1]
+    with pytest.raises(SingularMatrix):
+        sp.blendenpik_overdetermined(Z, b, 1e-6, 10, 2.0)
+    x = sp.blendenpik_overdetermined(A, b, 1e-12, 50, 4.0)
+    assert np.linalg.norm(x - np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-9
+
+
+def test_gemv_kernels(rb, orc):
+    """the two HBM-bound matrix-vector kernels of the CGLS iteration against the oracle products (odd sizes and views)"""
+    import torch
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    for m, n in ((5001, 37), (4096, 2050), (3, 1), (70000, 5)):
+        A = random_matrix(m, n, seed=m % 13); xv = random_matrix(n, 1, seed=5); rv = random_matrix(m, 1, seed=6)
+        for pad in (0, 1):
+            big = rt.empty_colmajor(m + pad, n); dA = big[:m, :]
+            dA.copy_(torch.from_numpy(np.ascontiguousarray(A)))
+            dx = rt.to_device_colmajor(xv); dr = rt.to_device_colmajor(rv)
+            dy = rt.empty_colmajor(m, 1); du = rt.empty_colmajor(n, 1)
+            pA, lda = rt.dev_ptr_ld(dA)
+            _lib.check(lib.rnla_gemv_dev(pA, lda, m, n, 0, C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr())))
+            _lib.check(lib.rnla_gemv_dev(pA, lda, m, n, 1, C.c_void_p(dr.data_ptr()), C.c_void_p(du.data_ptr())))
+            rt.synchronize()
+            assert np.abs(dy.cpu().numpy() - A @ xv).max() <= 1e-13 * n * max(1, np.abs(A @ xv).max())
+            assert np.abs(du.cpu().numpy() - A.T @ rv).max() <= 1e-13 * m * max(1, np.abs(A.T @ rv).max())
+
+
 # ---------------------------------------------------------------- committed golden fixtures (oracle outputs)
 def test_golden_fixtures(rb):
     """tests/golden/*.npz were written by tests/golden/make_golden.py from the oracle; the GPU must reproduce them"""

@@ -387,3 +387,35 @@ def test_block_sparse_sign_embedding_quality(orc):
             b = sv(orc.sketch_apply_saso_block(Q, 400, zeta=8, seed=0, width=w))
             assert 0.25 < b.min() and b.max() < 1.8
     assert sv(orc.sketch_apply_saso_block(Qc, 400, zeta=8, seed=0, width=8)).min() < 0.1
+
+
+def test_cgls_and_blendenpik_restatement(orc):
+    """src/cg.rs:18-61 and src/sketch_and_precondition.rs:26-59 restated: CGLS reproduces a numpy transcription of the
+    reference loop iterate for iterate; blendenpik converges to the least-squares solution in a few dozen iterations for
+    every sketch operator, and reports the reference's validation errors"""
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((200, 12)); b = rng.standard_normal((200, 1))
+    x, it, conv = orc.cgls(a, b, 1e-12, 100)
+    xr = np.zeros((12, 1)); r = b - a @ xr; s = a.T @ r; p_ = s.copy(); ns = float(s.T @ s); itr = 0; cv = False
+    for i in range(100):
+        ap = a @ p_; alpha = ns / float(ap.T @ ap); xr += alpha * p_; r -= alpha * ap
+        sn = a.T @ r; nn = float(sn.T @ sn)
+        if np.sqrt(nn) < 1e-12:
+            cv = True; itr = i + 1; break
+        p_ = sn + (nn / ns) * p_; ns = nn
+    assert conv == cv and abs(it - itr) <= 1 and np.abs(x - xr).max() < 1e-12
+    assert np.abs(x - np.linalg.lstsq(a, b, rcond=None)[0]).max() < 1e-10
+    m, n = 3000, 40
+    A = rng.standard_normal((m, n)) * np.logspace(0, -4, n)
+    xt = rng.uniform(-100, 100, (n, 1)); bb = A @ xt + 1e-3 * rng.standard_normal((m, 1))
+    xl = np.linalg.lstsq(A, bb, rcond=None)[0]
+    for kind in (0, 1, 2):
+        xs, its, cvs = orc.blendenpik(A, bb, 1e-10, 200, 4.0, kind=kind)
+        assert cvs and its < 60 and np.linalg.norm(xs - xl) <= 1e-8 * np.linalg.norm(xl)
+    for bad in ((1e-6, 10, 0.5), (0.0, 10, 2.0), (1e-6, 0, 2.0)):
+        with pytest.raises(ValueError) as e:
+            orc.blendenpik(A, bb, bad[0], bad[1], bad[2])
+        assert e.value.args[0] == 1
+    with pytest.raises(ValueError) as e:
+        orc.blendenpik(A[:20].copy(), bb[:20], 1e-6, 10, 2.0)
+    assert e.value.args[0] == 4

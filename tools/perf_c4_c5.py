@@ -38,6 +38,29 @@ if which in ("c4", "both"):
     out["c4_dense_d4000"] = {"ms": t * 1e3, "tflops": 2.0 * d * m * n / t * 1e-12, "phases": rt.timings()}
     print(out["c4_dense_d4000"], flush=True)
     del dA, dS; torch.cuda.empty_cache()
+if which == "c4solve":
+    # BASELINE config 4 end to end: blendenpik on a 1M x 2000 least-squares problem (test_assist.rs:71-93 shape: hypothesis
+    # ~ U(-100, 100), Gaussian data with a 1e4 column scaling, small noise), block sparse-sign sketch, d = 4n
+    m, n = 1000000, 2000
+    dA = rt.empty_colmajor(m, n); pA, lda = rt.dev_ptr_ld(dA)
+    _lib.check(lib.rnla_sketch_fill_dev(0, 0, 77, 9, m, n, 0, pA, lda)); rt.synchronize()
+    dA.mul_(torch.logspace(0, -4, n, dtype=torch.float64, device="cuda"))
+    xt = (torch.rand(n, 1, dtype=torch.float64, device="cuda") * 200 - 100)
+    db = rt.empty_colmajor(m, 1); db.copy_(dA @ xt + 1e-4 * torch.randn(m, 1, dtype=torch.float64, device="cuda"))
+    dx = rt.empty_colmajor(n, 1)
+    it = C.c_int64(0); cv = C.c_int32(0)
+    for kind, zeta, sf, name in [(2, 8, 4.0, "saso_block_sf4"), (2, 8, 2.0, "saso_block_sf2"), (0, 0, 2.0, "dense_gaussian_sf2")]:
+        def run():
+            _lib.check(lib.rnla_blendenpik_overdetermined_dev(pA, lda, m, n, C.c_void_p(db.data_ptr()), 1e-8, 200, sf, kind, 0, zeta,
+                                                              C.c_void_p(dx.data_ptr()), C.byref(it), C.byref(cv)))
+        t = timed(run, reps=2)
+        res = dA.t() @ (db - dA @ dx)
+        out[f"c4_blendenpik_{name}"] = {"ms": t * 1e3, "iterations": int(it.value), "converged": bool(cv.value),
+                                        "rel_err_x": float(torch.linalg.vector_norm(dx - xt) / torch.linalg.vector_norm(xt)),
+                                        "normal_eq_residual": float(torch.linalg.vector_norm(res) / torch.linalg.vector_norm(dA.t() @ db)),
+                                        "phases": rt.timings()}
+        print(name, out[f"c4_blendenpik_{name}"], flush=True)
+    print(json.dumps(out)); sys.exit(0)
 if which in ("c5", "both"):
     n, r0, k, s = 50000, 400, 200, 10
     V0 = rt.empty_colmajor(n, r0); pV, ldv = rt.dev_ptr_ld(V0)
