@@ -207,6 +207,19 @@ inline std::pair<DMatrix, DMatrix> blendenpik_sketch(const DMatrix& a, const DMa
                                     b.as_ptr(), (int64_t)b.ncols(), a_sk.as_mut_ptr(), b_sk.as_mut_ptr()));
     return {std::move(a_sk), std::move(b_sk)};
 }
+// blendenpik_overdetermined end to end (:26-59): returns x (n x 1)
+inline DMatrix blendenpik_overdetermined(const DMatrix& a, const DMatrix& b, double epsilon, size_t l, double sampling_factor,
+                                         rnla_sketch_kind kind = RNLA_SKETCH_DENSE, int zeta = 8, int width = 0) {
+    validate(a, epsilon, l, sampling_factor);
+    DMatrix x(a.ncols(), 1);
+    int64_t iters = 0; int32_t conv = 0;
+    errors::check(rnla_blendenpik_overdetermined(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), b.as_ptr(), epsilon, (int64_t)l,
+                                                 sampling_factor, kind, kind == RNLA_SKETCH_SASO_BLOCK ? width : RNLA_GAUSSIAN, zeta,
+                                                 x.as_mut_ptr(), &iters, &conv));
+    if (conv) std::printf("CGLS converged after %lld iterations\n", (long long)iters);             // src/cg.rs:46
+    else std::printf("CGLS failed to converged after %zu iterations\n", l);                        // src/cg.rs:58
+    return x;
+}
 // sketch step of lsrn_overdetermined (:105-107) and sketch_saddle_point_precondition (:172-176, saddle = true)
 inline DMatrix sketch_only(const DMatrix& a, double epsilon, size_t l, double sampling_factor, bool saddle = false,
                            rnla_sketch_kind kind = RNLA_SKETCH_DENSE, int zeta = 8) {

@@ -62,6 +62,23 @@ int main() {
         auto [a_sk, b_sk] = sketch_and_precondition::blendenpik_sketch(DMatrix(200, 5, 1.0), DMatrix(200, 1, 1.0), 1e-6, 10, 4.0);
         CHECK(a_sk.nrows() == 20 && a_sk.ncols() == 5 && b_sk.nrows() == 20);
     }
+    // src/sketch_and_precondition.rs:229-290 test_blendenpik_overdetermined: the solve itself and its errors
+    {
+        const size_t m = 400, n = 6;
+        DMatrix A = DMatrix::from_fn(m, n, [](size_t i, size_t j) { return std::sin(0.37 * (double)(i + 1) * (double)(j + 1)) + (i % (j + 2) == 0 ? 1.0 : 0.0); });
+        DMatrix xt = DMatrix::from_fn(n, 1, [](size_t i, size_t) { return (double)i - 2.5; });
+        DMatrix b = A * xt;
+        auto x = sketch_and_precondition::blendenpik_overdetermined(A, b, 1e-12, 100, 4.0);
+        double err = 0.0;
+        for (size_t i = 0; i < n; ++i) err = std::fmax(err, std::fabs(x(i, 0) - xt(i, 0)));
+        CHECK(err < 1e-8);
+        auto x2 = sketch_and_precondition::blendenpik_overdetermined(A, b, 1e-12, 100, 4.0, RNLA_SKETCH_SASO_BLOCK, 8);
+        err = 0.0;
+        for (size_t i = 0; i < n; ++i) err = std::fmax(err, std::fabs(x2(i, 0) - xt(i, 0)));
+        CHECK(err < 1e-8);
+        try { sketch_and_precondition::blendenpik_overdetermined(A, b, 1e-6, 10, 0.5); CHECK(false); }
+        catch (const RandNLAError& e) { CHECK(e.kind == RandNLAError::InvalidParameters); }
+    }
     std::printf(failures ? "CPP MIRROR: %d FAILURES\n" : "CPP MIRROR: ALL OK\n", failures);
     return failures ? 1 : 0;
 }

@@ -17,6 +17,9 @@ extern "C" {
     pub fn rnla_sketch_dim(m: i64, n: i64, sampling_factor: c_double, rule: c_int) -> i64;
     pub fn rnla_sketch_apply(kind: c_int, dist: c_int, seed: u64, d: i64, zeta: c_int, a: *const c_double, m: i64, n: i64,
                              b: *const c_double, nrhs: i64, a_sk: *mut c_double, b_sk: *mut c_double) -> c_int;
+    pub fn rnla_blendenpik_overdetermined(a: *const c_double, m: i64, n: i64, b: *const c_double, epsilon: c_double, l: i64,
+                                          sampling_factor: c_double, kind: c_int, dist: c_int, zeta: c_int, x: *mut c_double,
+                                          iterations: *mut i64, converged: *mut c_int) -> c_int;
 }
 
 pub fn last_message() -> String {

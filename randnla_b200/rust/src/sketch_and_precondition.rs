@@ -6,7 +6,19 @@ use crate::ffi;
 use nalgebra::DMatrix;
 use std::error::Error;
 
-pub enum SketchKind { Dense, SparseSign { zeta: i32 } }
+/// Dense: i.i.d. Gaussian (what the reference draws).  SparseSign: textbook SASO.  BlockSparseSign: the block
+/// sparse-sign operator (include/rnla.h RNLA_SKETCH_SASO_BLOCK), `width` = 0 for the default block width.
+pub enum SketchKind { Dense, SparseSign { zeta: i32 }, BlockSparseSign { zeta: i32, width: i32 } }
+
+impl SketchKind {
+    fn abi(&self) -> (i32, i32, i32) {      // (kind, dist slot, zeta)
+        match *self {
+            SketchKind::Dense => (0, 0, 0),
+            SketchKind::SparseSign { zeta } => (1, 0, zeta),
+            SketchKind::BlockSparseSign { zeta, width } => (2, width, zeta),
+        }
+    }
+}
 
 /// d of :49 / :105 (`saddle = false`) or :172 (`saddle = true`)
 pub fn sketch_dim(m: usize, n: usize, sampling_factor: f64, saddle: bool) -> usize {
@@ -26,13 +38,34 @@ pub fn validate(a: &DMatrix<f64>, epsilon: f64, l: usize, sampling_factor: f64) 
 /// (S a, S b) for a d x m sketching operator S
 pub fn sketch_step(a: &DMatrix<f64>, b: Option<&DMatrix<f64>>, d: usize, kind: SketchKind) -> Result<(DMatrix<f64>, Option<DMatrix<f64>>), Box<dyn Error>> {
     let (m, n) = a.shape();
-    let (k, zeta) = match kind { SketchKind::Dense => (0, 0), SketchKind::SparseSign { zeta } => (1, zeta) };
+    let (k, dist, zeta) = kind.abi();
     let mut a_sk = DMatrix::<f64>::zeros(d, n);
     let mut b_sk = b.map(|bb| DMatrix::<f64>::zeros(d, bb.ncols()));
     let (bp, nrhs, bskp) = match (b, b_sk.as_mut()) {
         (Some(bb), Some(o)) => (bb.as_ptr(), bb.ncols() as i64, o.as_mut_ptr()),
         _ => (std::ptr::null(), 0, std::ptr::null_mut()),
     };
-    from_status(unsafe { ffi::rnla_sketch_apply(k, 0, 0, d as i64, zeta, a.as_ptr(), m as i64, n as i64, bp, nrhs, a_sk.as_mut_ptr(), bskp) })?;
+    from_status(unsafe { ffi::rnla_sketch_apply(k, dist, 0, d as i64, zeta, a.as_ptr(), m as i64, n as i64, bp, nrhs, a_sk.as_mut_ptr(), bskp) })?;
     Ok((a_sk, b_sk))
+}
+
+/// Drop-in for `blendenpik_overdetermined` (reference src/sketch_and_precondition.rs:26-59), end to end on the GPU:
+/// sketch, QR of the sketch, z0, R^-1, CGLS on A R^-1 in operator form, x = R^-1 z.  Same validation and errors.
+pub fn blendenpik_overdetermined(a: &DMatrix<f64>, b: &DMatrix<f64>, epsilon: f64, l: usize, sampling_factor: f64) -> Result<DMatrix<f64>, Box<dyn Error>> {
+    blendenpik_overdetermined_with(a, b, epsilon, l, sampling_factor, SketchKind::Dense)
+}
+
+pub fn blendenpik_overdetermined_with(a: &DMatrix<f64>, b: &DMatrix<f64>, epsilon: f64, l: usize, sampling_factor: f64, kind: SketchKind) -> Result<DMatrix<f64>, Box<dyn Error>> {
+    validate(a, epsilon, l, sampling_factor)?;
+    let (m, n) = a.shape();
+    let (k, dist, zeta) = kind.abi();
+    let mut x = DMatrix::<f64>::zeros(n, 1);
+    let (mut iters, mut converged) = (0i64, 0i32);
+    from_status(unsafe {
+        ffi::rnla_blendenpik_overdetermined(a.as_ptr(), m as i64, n as i64, b.as_ptr(), epsilon, l as i64, sampling_factor,
+                                            k, dist, zeta, x.as_mut_ptr(), &mut iters, &mut converged)
+    })?;
+    // src/cg.rs:46-59 prints the same two lines
+    if converged != 0 { println!("CGLS converged after {} iterations", iters); } else { println!("CGLS failed to converged after {} iterations", l); }
+    Ok(x)
 }
