@@ -205,6 +205,14 @@ rnla_status rnla_orth_dev(double* dX, int64_t ldx, int64_t rows_local, int64_t c
                           double* dR, int64_t* deficient);
 /* small dense core on one GPU: SVD of a (rows x cols) matrix with cols <= 512 columns... see DESIGN.md */
 rnla_status rnla_small_svd_dev(const double* dM, int64_t ldm, int64_t p, double* dU, double* dSigma, double* dV);
+/* planning decisions of the launches, computed on the host (no GPU needed; tests pin them):
+ * rnla_plan_gemm: out = {split-K parts of gemm_nn for (m x n) * (n x N), row chunks of gemm_tn for (m x n)^T (m x N), rows per
+ * chunk, tiles}.  rnla_plan_saso_block: the work list of the block sparse-sign kernel for `nchunks` chunks of 2048 rows:
+ * shape = {blocks per thread, columns per CTA, parts, column groups}, desc = (column group, first chunk, end chunk, slot) per
+ * CTA in launch order; returns the number of CTAs (-1: unsupported shape). */
+void rnla_plan_gemm(int64_t m, int64_t n, int64_t N, int32_t sms, int32_t* out);
+int32_t rnla_plan_saso_block(int64_t d, int32_t zeta, int32_t width, int64_t n, int64_t nchunks, int32_t sms, int32_t* shape,
+                             int32_t* desc, int32_t cap, int32_t* nslots);
 /* diagnostics: Jacobi sweeps used by the last small SVD (drivers and rnla_small_svd_dev) */
 int32_t rnla_last_jacobi_sweeps(void);
 rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double* dW, double* dLambda);

@@ -472,6 +472,25 @@ rnla_status rnla_blendenpik_overdetermined(const double* A, int64_t m, int64_t n
     return d2h(x, dx.d(), (size_t)n);
 }
 
+// ---- planning decisions, callable without a GPU (tests/test_host_logic.py) ---------------------------------------------
+void rnla_plan_gemm(int64_t m, int64_t n, int64_t N, int32_t sms, int32_t* out /* 4 */) {
+    int chunks = 0, tiles = 0; int64_t chunk_rows = 0;
+    gemm_tn_plan_info(m, n, N, sms, &chunks, &chunk_rows, &tiles);
+    out[0] = gemm_nn_ksplit(m, n, N, sms); out[1] = chunks; out[2] = (int32_t)chunk_rows; out[3] = tiles;
+}
+int32_t rnla_plan_saso_block(int64_t d, int32_t zeta, int32_t width, int64_t n, int64_t nchunks, int32_t sms, int32_t* shape /* 4 */,
+                             int32_t* desc /* 4 per CTA */, int32_t cap, int32_t* nslots) {
+    int bpt = 0, cb = 0, parts = 0;
+    if (!saso_block_shape(d, zeta, width, n, &bpt, &cb, &parts)) return -1;
+    const int ncg = (int)((n + cb - 1) / cb);
+    std::vector<SbFrag> work; std::vector<int> fix_cg, fix_off, fix_cnt, slots;
+    saso_block_worklist(ncg, nchunks, sms, work, fix_cg, fix_off, fix_cnt, slots);
+    shape[0] = bpt; shape[1] = cb; shape[2] = parts; shape[3] = ncg;
+    for (int i = 0; i < (int)work.size() && i < cap; ++i) { desc[4 * i] = work[i].cg; desc[4 * i + 1] = work[i].lo; desc[4 * i + 2] = work[i].hi; desc[4 * i + 3] = work[i].slot; }
+    if (nslots) *nslots = (int)slots.size();
+    return (int32_t)work.size();
+}
+
 rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int32_t trans, const double* dx, double* dy) {
     RNLA_TRY(ensure_ctx());
     return trans ? dev_gemv_t(dA, lda, m, n, dx, dy) : dev_gemv_n(dA, lda, m, n, dx, dy);

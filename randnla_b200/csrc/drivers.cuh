@@ -1,5 +1,6 @@
 #pragma once
 #include "context.cuh"
+#include <vector>
 
 namespace rnla {
 
@@ -30,6 +31,10 @@ rnla_status dev_rand_evd2(const double* A, int64_t lda, int64_t m_local, int64_t
                           const rnla_options& o, double* V, int64_t ldv, double* Lambda, int64_t* r_out);
 
 // saso_block.cu: block sparse-sign sketch, A_sk fully overwritten with S A_local
+struct SbFrag { int cg, lo, hi, slot; };     // work-list entry: column group, chunk range, partial slot (-1: writes A_sk)
+void saso_block_worklist(int ncg, int64_t nchunks, int sms, std::vector<SbFrag>& work, std::vector<int>& fix_cg,
+                         std::vector<int>& fix_off, std::vector<int>& fix_cnt, std::vector<int>& slots);
+bool saso_block_shape(int64_t d, int zeta, int w, int64_t n, int* bpt_out, int* cb_out, int* parts_out);
 rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const double* A, int64_t lda, int64_t m_local,
                              int64_t n, int64_t row_off, double* Ask, int64_t ldk);
 

@@ -530,6 +530,26 @@ static cudaError_t gemm_nn_dispatch(const GemmNN& p, int nblkN, int NT, cudaStre
     }
 }
 
+// host logic of gemm_nn's split-K choice, separated so that it can be checked without a GPU
+int gemm_nn_ksplit(int64_t m, int64_t K, int64_t N, int sms) {
+    const int nblkN = (int)((N + 127) / 128);
+    const int64_t tiles = ((m + BM - 1) / BM) * nblkN;
+    const int KT = (int)((K + NN_BK - 1) / NN_BK);
+    int best_s = 1;
+    double best = -1.0;
+    for (int s = 1; s <= 4; ++s) {
+        if (s > 1 && KT / s < 64) break;
+        const int64_t units = tiles * s, waves = (units + sms - 1) / sms;
+        const double eff = (double)units / (double)(waves * sms) - (s > 1 ? 42.0 * s / (double)K + 0.002 : 0.0);
+        if (eff > best + 1e-9) { best = eff; best_s = s; }
+    }
+    return best_s;
+}
+void gemm_tn_plan_info(int64_t m, int64_t n, int64_t N, int sms, int* chunks, int64_t* chunk_rows, int* tiles) {
+    const TNPlan pl = plan_tn(m, n, N, sms);
+    *chunks = pl.chunks; *chunk_rows = pl.chunk_rows; *tiles = pl.njb * pl.nblkN;
+}
+
 cudaError_t gemm_nn(const GemmNN& p0, cudaStream_t st) {
     if (p0.m <= 0 || p0.N <= 0) return cudaSuccess;
     if (p0.gen && (p0.k_off & 3)) return cudaErrorInvalidValue;
@@ -545,16 +565,8 @@ cudaError_t gemm_nn(const GemmNN& p0, cudaStream_t st) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
-    const int64_t tiles = ((p.m + BM - 1) / BM) * nblkN;
     const int KT = (int)((p.K + NN_BK - 1) / NN_BK);
-    int best_s = 1;
-    double best = -1.0;
-    for (int s = 1; s <= 4; ++s) {
-        if (s > 1 && KT / s < 64) break;
-        const int64_t units = tiles * s, waves = (units + sms - 1) / sms;
-        const double eff = (double)units / (double)(waves * sms) - (s > 1 ? 42.0 * s / (double)p.K + 0.002 : 0.0);
-        if (eff > best + 1e-9) { best = eff; best_s = s; }
-    }
+    const int best_s = gemm_nn_ksplit(p.m, p.K, p.N, sms);
     if (best_s == 1) return gemm_nn_dispatch(p, nblkN, NT, st);
     p.ksplit = best_s;
     p.kt_per = (KT + best_s - 1) / best_s;

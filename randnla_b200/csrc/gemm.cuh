@@ -30,6 +30,10 @@ cudaError_t gemm_nn(const GemmNN& p, cudaStream_t st);
 size_t gemm_tn_workspace_bytes(int64_t m, int64_t n, int64_t N, int sms);
 cudaError_t gemm_tn(const GemmTN& p, double* workspace, size_t workspace_bytes, int sms, cudaStream_t st);
 
+// planning decisions (host logic, exported through rnla_plan_* for CPU tests)
+int gemm_nn_ksplit(int64_t m, int64_t K, int64_t N, int sms);
+void gemm_tn_plan_info(int64_t m, int64_t n, int64_t N, int sms, int* chunks, int64_t* chunk_rows, int* tiles);
+
 // launch counter (bench.py reports gpu_launches from it)
 extern unsigned long long g_kernel_launches;
 

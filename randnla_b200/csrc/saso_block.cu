@@ -399,6 +399,53 @@ cudaError_t sb_dispatch_bpt(const SbArgs& a, int bpt, int cb, int grid, bool tma
 
 }  // namespace
 
+// host logic of the launch, separated so that it can be checked without a GPU (rnla_plan_saso_block, tests/test_host_logic.py)
+void saso_block_worklist(int ncg, int64_t nchunks, int sms_in, std::vector<SbFrag>& work, std::vector<int>& fix_cg,
+                         std::vector<int>& fix_off, std::vector<int>& fix_cnt, std::vector<int>& slots) {
+    const int sms = std::max(sms_in, 1);
+    const int nwhole = nchunks >= 16 ? (ncg / sms) * sms : ncg;      // short inputs are not worth fragmenting
+    for (int gidx = 0; gidx < nwhole; ++gidx) work.push_back({gidx, 0, (int)nchunks, -1});
+    const int64_t left = (int64_t)(ncg - nwhole) * nchunks;
+    std::vector<SbFrag> frags;
+    for (int k = 0; k < sms && left > 0; ++k) {
+        int64_t t = left * k / sms;
+        const int64_t t1 = left * (k + 1) / sms;
+        while (t < t1) {
+            const int64_t gl = t / nchunks, end = std::min(t1, (gl + 1) * nchunks);
+            const int cgi = nwhole + (int)gl, lo = (int)(t - gl * nchunks), hi = (int)(end - gl * nchunks);
+            if (lo == 0 && hi == (int)nchunks) frags.push_back({cgi, lo, hi, -1});
+            else {
+                const int slot = (int)slots.size();
+                if (fix_cg.empty() || fix_cg.back() != cgi) { fix_cg.push_back(cgi); fix_off.push_back(slot); fix_cnt.push_back(0); }
+                slots.push_back(slot); ++fix_cnt.back();
+                frags.push_back({cgi, lo, hi, slot});
+            }
+            t = end;
+        }
+    }
+    std::stable_sort(frags.begin(), frags.end(), [](const SbFrag& x, const SbFrag& y) { return x.hi - x.lo > y.hi - y.lo; });
+    work.insert(work.end(), frags.begin(), frags.end());
+}
+
+// shape decisions of saso_block_apply: returns false if (d, zeta, w) is not supported
+bool saso_block_shape(int64_t d, int zeta, int w, int64_t n, int* bpt_out, int* cb_out, int* parts_out) {
+    if (zeta != 1 && zeta != 2 && zeta != 4 && zeta != 8) return false;
+    if (w == 0) w = std::min(zeta, 4);
+    if ((w != 1 && w != 2 && w != 4) || w > zeta || d < zeta) return false;
+    const int g = zeta / w;
+    const int64_t nbt64 = (d / zeta) * g;
+    int bpt = 1;
+    while ((int64_t)bpt * SB_T < nbt64) bpt *= 2;
+    if ((int64_t)bpt * w > SB_MAXACC) return false;
+    int cb = SB_MAXACC / (bpt * w);
+    cb = cb >= 4 ? 4 : cb >= 2 ? 2 : 1;
+    if (bpt * w == 16 && w == 4 && n >= 3) cb = 3;   // w < 4 spills at 48 accumulators
+    while (cb > 1 && cb / 2 >= n) cb /= 2;
+    while (cb > 1 && SB_SMEM / (SB_R * 8 * cb + g * SB_TABW * (int)sizeof(sbtab_t)) < 2) cb /= 2;
+    *bpt_out = bpt; *cb_out = cb; *parts_out = nbt64 < SB_T ? (int)(SB_T / nbt64) : 1;
+    return true;
+}
+
 // A_sk (d x n, fully overwritten) = S A_local for the block sparse-sign operator with zeta = g * w non-zeros per column.
 // Rows [0, m_local) of A are global rows [row_off, row_off + m_local).  w = 0 selects the default width min(zeta, 4).
 rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const double* A, int64_t lda, int64_t m_local,
@@ -414,16 +461,9 @@ rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const do
     const int g = zeta / w;
     const int64_t nbs64 = d / zeta;               // blocks per stripe
     const int64_t nbt64 = nbs64 * g;              // blocks over all stripes
-    int bpt = 1;
-    while ((int64_t)bpt * SB_T < nbt64) bpt *= 2;
-    if ((int64_t)bpt * w > SB_MAXACC)
+    int bpt = 1, cb = 1, parts = 1;
+    if (!saso_block_shape(d, zeta, w, n, &bpt, &cb, &parts))
         return fail(RNLA_ERR_INVALID_DIMENSIONS, "block SASO: sketch dimension d must be <= 16384");
-    int cb = SB_MAXACC / (bpt * w);
-    cb = cb >= 4 ? 4 : cb >= 2 ? 2 : 1;
-    if (bpt * w == 16 && w == 4 && n >= 3) cb = 3;   // w < 4 spills at 48 accumulators
-    while (cb > 1 && cb / 2 >= n) cb /= 2;
-    while (cb > 1 && SB_SMEM / (SB_R * 8 * cb + g * SB_TABW * (int)sizeof(sbtab_t)) < 2) cb /= 2;
-    const int parts = nbt64 < SB_T ? (int)(SB_T / nbt64) : 1;
     const int ncg = (int)((n + cb - 1) / cb);
     const int64_t d_used = nbt64 * w;
 
@@ -450,34 +490,9 @@ rnla_status saso_block_apply(uint64_t seed, int64_t d, int zeta, int w, const do
     // fragments (column group, chunk range) with a partial-result slot.  Entries are ordered longest first, so the
     // hardware's in-order dispatch packs the fragments of the last wave tightly (longest-processing-time rule): every SM
     // streams nearly the same number of bytes, and only the fragments cost extra traffic (their slots).
-    struct Frag { int cg, lo, hi, slot; };
-    std::vector<Frag> work;
+    std::vector<SbFrag> work;
     std::vector<int> fix_cg, fix_off, fix_cnt, slots;
-    {
-        const int sms = std::max(c.sms, 1);
-        const int nwhole = nchunks >= 16 ? (ncg / sms) * sms : ncg;      // short inputs are not worth fragmenting
-        for (int gidx = 0; gidx < nwhole; ++gidx) work.push_back({gidx, 0, (int)nchunks, -1});
-        const int64_t left = (int64_t)(ncg - nwhole) * nchunks;
-        std::vector<Frag> frags;
-        for (int k = 0; k < sms && left > 0; ++k) {
-            int64_t t = left * k / sms;
-            const int64_t t1 = left * (k + 1) / sms;
-            while (t < t1) {
-                const int64_t gl = t / nchunks, end = std::min(t1, (gl + 1) * nchunks);
-                const int cgi = nwhole + (int)gl, lo = (int)(t - gl * nchunks), hi = (int)(end - gl * nchunks);
-                if (lo == 0 && hi == (int)nchunks) frags.push_back({cgi, lo, hi, -1});
-                else {
-                    const int slot = (int)slots.size();
-                    if (fix_cg.empty() || fix_cg.back() != cgi) { fix_cg.push_back(cgi); fix_off.push_back(slot); fix_cnt.push_back(0); }
-                    slots.push_back(slot); ++fix_cnt.back();
-                    frags.push_back({cgi, lo, hi, slot});
-                }
-                t = end;
-            }
-        }
-        std::stable_sort(frags.begin(), frags.end(), [](const Frag& x, const Frag& y) { return x.hi - x.lo > y.hi - y.lo; });
-        work.insert(work.end(), frags.begin(), frags.end());
-    }
+    saso_block_worklist(ncg, nchunks, c.sms, work, fix_cg, fix_off, fix_cnt, slots);
     const int nfix = (int)fix_cg.size(), nslots = (int)slots.size(), grid = (int)work.size();
     // one upload: descriptors (int4 per CTA), then the fix-up lists
     std::vector<int> host((size_t)4 * grid + 3 * (size_t)nfix + (size_t)nslots);

@@ -30,6 +30,16 @@ ev2 = np.concatenate([np.logspace(0.5, -0.5, 6), 1e-8 * np.abs(rng.standard_norm
 P = (Q * ev2) @ Q.T; P = 0.5 * (P + P.T)
 out["evd2_A"] = P
 out["evd2_lambda"] = orc.rand_evd2(P, 6, 4, orc.make_opts(mode=0))[1]
+# block sparse-sign operator: S itself (from S I) for two shapes of (zeta, width), and a sketch of a matrix
+out["sbs_S_z8w4"] = orc.sketch_apply_saso_block(np.eye(2100), 48, zeta=8, seed=11, width=4)[:, ::7].copy()
+out["sbs_S_z4w1"] = orc.sketch_apply_saso_block(np.eye(2100), 48, zeta=4, seed=11, width=1)[:, ::7].copy()
+T = random_matrix(2100, 5, seed=24)
+out["sbs_T"] = T; out["sbs_SA"] = orc.sketch_apply_saso_block(T, 48, zeta=8, seed=11)
+# blendenpik end to end (block sparse-sign sketch and dense Gaussian sketch)
+La = random_matrix(900, 12, seed=25) * np.logspace(0, -3, 12); Lb = random_matrix(900, 1, seed=26)
+out["lsq_A"] = La; out["lsq_b"] = Lb
+out["lsq_x_block"] = orc.blendenpik(La, Lb, 1e-12, 100, 4.0, kind=2, zeta=8)[0]
+out["lsq_x_dense"] = orc.blendenpik(La, Lb, 1e-12, 100, 4.0, kind=0)[0]
 X = random_matrix(40, 9, seed=23)
 out["stab_X"] = X; out["stab_L"] = orc.Stabilizer(X)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "path_golden.npz"), **out)

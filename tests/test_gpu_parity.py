@@ -660,6 +660,15 @@ def test_golden_fixtures(rb):
     assert (np.abs(np.array(lam) - g["evd2_lambda"]) / g["evd2_lambda"]).max() < 1e-9
     from randnla_b200.lora_helpers import Stabilizer
     assert Stabilizer(np.asfortranarray(g["stab_X"])).tobytes() == np.asfortranarray(g["stab_L"]).tobytes()
+    from randnla_b200 import sketch_and_precondition as sp
+    for key, zeta, width in (("sbs_S_z8w4", 8, 4), ("sbs_S_z4w1", 4, 1)):
+        Sg = sp.sketch_apply(np.eye(2100), None, 48, kind=sp.SKETCH_SASO_BLOCK, zeta=zeta, seed=11, width=width)[:, ::7]
+        assert np.asfortranarray(Sg).tobytes() == np.asfortranarray(g[key]).tobytes()
+    SA = sp.sketch_apply(np.asfortranarray(g["sbs_T"]), None, 48, kind=sp.SKETCH_SASO_BLOCK, zeta=8, seed=11)
+    assert np.abs(SA - g["sbs_SA"]).max() <= 1e-13 * np.abs(g["sbs_SA"]).max()
+    for key, kind in (("lsq_x_block", sp.SKETCH_SASO_BLOCK), ("lsq_x_dense", sp.SKETCH_DENSE)):
+        xg = sp.blendenpik_overdetermined(np.asfortranarray(g["lsq_A"]), np.asfortranarray(g["lsq_b"]), 1e-12, 100, 4.0, kind=kind, zeta=8)
+        assert np.linalg.norm(xg - g[key]) <= 1e-9 * np.linalg.norm(g[key])
 
 
 # ---------------------------------------------------------------- full size (BASELINE config 2), size-independent properties

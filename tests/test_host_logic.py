@@ -27,6 +27,70 @@ def test_shard_rows_partition():
                 assert all(s[0] % 4 == 0 for s in spans)       # Philox row-quads never straddle ranks
 
 
+def test_launch_planning_is_wave_aware():
+    """host logic of the launches (include/rnla.h rnla_plan_*), no GPU: split-K of gemm_nn and the chunk count of gemm_tn
+    fill whole waves of 148 one-CTA SMs at the BASELINE shapes; small problems are left alone"""
+    import ctypes as C
+    from randnla_b200 import _lib
+    lib = _lib.load()
+    out = (C.c_int32 * 4)()
+    lib.rnla_plan_gemm(200000, 20000, 110, 148, out)          # config 2
+    ksplit, chunks, chunk_rows, tiles = list(out)
+    assert ksplit == 3 and tiles == 157 and chunks == 16
+    waves = tiles * chunks / 148
+    assert 0.985 < waves / np.ceil(waves) <= 1.0
+    nn_waves = 1563 * ksplit / 148
+    assert nn_waves / np.ceil(nn_waves) > 0.985
+    lib.rnla_plan_gemm(50000, 50000, 210, 148, out)           # config 5
+    assert out[0] == 3 and (782 * out[1] / 148) / np.ceil(782 * out[1] / 148) > 0.98
+    lib.rnla_plan_gemm(2000, 1000, 60, 148, out)              # config 1: too short to split
+    assert out[0] == 1 and out[1] >= 1
+    lib.rnla_plan_gemm(200000, 110, 110, 148, out)            # Gram of a tall panel: K = 110 is never split
+    assert out[0] == 1 and out[1] * out[2] >= 200000
+
+
+@pytest.mark.parametrize("d,zeta,width,n,nchunks", [(8000, 8, 4, 2000, 489), (4000, 8, 4, 2000, 489), (8000, 8, 2, 2000, 489),
+                                                    (200, 8, 0, 37, 3), (16384, 1, 1, 5, 40), (64, 8, 4, 600, 1),
+                                                    (1200, 8, 0, 3000, 24), (8000, 4, 4, 301, 977), (2000, 8, 4, 1, 100)])
+def test_saso_block_work_list_covers_every_unit_once(d, zeta, width, n, nchunks):
+    """host logic of the block sparse-sign launch, no GPU: every (column group, chunk) unit is covered by exactly one CTA,
+    a column group is either written directly by one CTA or split into slot-carrying fragments in chunk order, slots are
+    unique, and the fragments are dispatched longest first"""
+    import ctypes as C
+    from randnla_b200 import _lib
+    lib = _lib.load()
+    shape = (C.c_int32 * 4)(); cap = 20000
+    desc = (C.c_int32 * (4 * cap))(); nslots = C.c_int32(0)
+    nctas = lib.rnla_plan_saso_block(d, zeta, width, n, nchunks, 148, shape, desc, cap, C.byref(nslots))
+    assert 0 < nctas <= cap
+    bpt, cb, parts, ncg = list(shape)
+    assert ncg == -(-n // cb) and bpt * (width or min(zeta, 4)) * cb <= 48
+    cover = np.zeros((ncg, nchunks), dtype=np.int32)
+    seen_slots = set(); direct = set(); last_len = None; in_frags = False
+    for i in range(nctas):
+        cg, lo, hi, slot = desc[4 * i:4 * i + 4]
+        assert 0 <= cg < ncg and 0 <= lo < hi <= nchunks
+        cover[cg, lo:hi] += 1
+        if slot < 0:
+            assert lo == 0 and hi == nchunks
+            direct.add(cg)
+        else:
+            assert slot not in seen_slots and not (lo == 0 and hi == nchunks)
+            seen_slots.add(slot)
+            if in_frags:
+                assert hi - lo <= last_len
+            in_frags = True; last_len = hi - lo
+    assert (cover == 1).all()
+    assert len(seen_slots) == nslots.value == max(seen_slots, default=-1) + 1
+    # work is balanced: no CTA-sized tail beyond the ideal share (whole groups fill complete waves)
+    whole = len(direct)
+    if nchunks >= 16 and ncg >= 148:
+        assert whole >= (ncg // 148) * 148
+    # unsupported shapes are refused
+    assert lib.rnla_plan_saso_block(20000, 8, 4, 10, 10, 148, shape, desc, cap, C.byref(nslots)) == -1
+    assert lib.rnla_plan_saso_block(100, 3, 0, 10, 10, 148, shape, desc, cap, C.byref(nslots)) == -1
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 

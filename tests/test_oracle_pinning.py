@@ -419,3 +419,23 @@ def test_cgls_and_blendenpik_restatement(orc):
     with pytest.raises(ValueError) as e:
         orc.blendenpik(A[:20].copy(), bb[:20], 1e-6, 10, 2.0)
     assert e.value.args[0] == 4
+
+
+def test_oracle_reproduces_committed_golden_vectors(orc):
+    """tests/golden/path_golden.npz (written by tests/golden/make_golden.py) is what the GPU tests are held to; the oracle
+    must keep reproducing it, so a change on either side is caught"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "path_golden.npz"))
+    A = np.asfortranarray(g["svd_A"])
+    for mode in (0, 1):
+        S = orc.rand_svd(A, int(g["svd_k"]), 1e-6, int(g["svd_s"]), orc.make_opts(mode=mode))[1]
+        assert np.abs(np.diag(S) - g[f"svd_sigma_mode{mode}"]).max() <= 1e-14
+    assert orc.omega_fill(0, 16, 5, seed=int(g["omega_seed"]), stream=1).tobytes() == np.asfortranarray(g["omega_gauss"]).tobytes()
+    assert np.abs(orc.rand_evd1(np.asfortranarray(g["evd1_A"]), 6, 0.1, 6, orc.make_opts(mode=0))[1] - g["evd1_lambda"]).max() <= 1e-13
+    assert np.abs(orc.rand_evd2(np.asfortranarray(g["evd2_A"]), 6, 4, orc.make_opts(mode=0))[1] - g["evd2_lambda"]).max() <= 1e-13
+    assert orc.Stabilizer(np.asfortranarray(g["stab_X"])).tobytes() == np.asfortranarray(g["stab_L"]).tobytes()
+    assert orc.sketch_apply_saso_block(np.eye(2100), 48, zeta=8, seed=11, width=4)[:, ::7].tobytes(order="F") == np.asfortranarray(g["sbs_S_z8w4"]).tobytes(order="F")
+    assert orc.sketch_apply_saso_block(np.eye(2100), 48, zeta=4, seed=11, width=1)[:, ::7].tobytes(order="F") == np.asfortranarray(g["sbs_S_z4w1"]).tobytes(order="F")
+    assert np.abs(orc.sketch_apply_saso_block(np.asfortranarray(g["sbs_T"]), 48, zeta=8, seed=11) - g["sbs_SA"]).max() <= 1e-14
+    x = orc.blendenpik(np.asfortranarray(g["lsq_A"]), np.asfortranarray(g["lsq_b"]), 1e-12, 100, 4.0, kind=2, zeta=8)[0]
+    assert np.linalg.norm(x - g["lsq_x_block"]) <= 1e-12 * np.linalg.norm(x)
