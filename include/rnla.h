@@ -147,7 +147,9 @@ rnla_status rnla_rand_evd2(const double* A, int64_t n, int64_t k, int64_t s,
                            double* V, double* lambda, int64_t* r);
 
 /* device-resident drivers: A is the LOCAL row shard (m_local x n, lda) when a communicator is active,
- * U is the matching local row shard; n-side outputs are replicated on every rank. */
+ * U is the matching local row shard; n-side outputs are replicated on every rank.  Unlike the host-buffer entry points
+ * these return as soon as the work is enqueued on the library stream (rnla_stream / rnla_set_stream): order your reads
+ * against that stream or call rnla_synchronize(). */
 rnla_status rnla_rand_svd_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t k, int64_t s,
                               const rnla_options* opt, double* dU, int64_t ldu, double* dSigma /* k */,
                               double* dVt, int64_t ldvt, int64_t* r);

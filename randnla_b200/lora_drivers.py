@@ -72,7 +72,8 @@ def rand_evd2(A, k, s):
 # ---- device-resident variants -------------------------------------------------------------------
 def rand_svd_dev(dA, k, s, opts=None, n=None):
     """Device-resident rand_svd.  `dA` is the LOCAL row shard (column-major torch CUDA tensor, m_local x n).
-    Returns (dU m_local x r, dSigma r, dVt r x n) as torch tensors."""
+    Returns (dU m_local x r, dSigma r, dVt r x n) as torch tensors.  Like the C entry point it returns once the work is
+    enqueued on the library stream: `runtime.synchronize()` (or `runtime.use_torch_stream()` beforehand) before torch reads them."""
     import torch
     lib = _lib.load()
     pA, lda = runtime.dev_ptr_ld(dA)

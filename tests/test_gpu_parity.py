@@ -354,7 +354,7 @@ def test_rand_svd_streamed_upload(rb, orc):
     assert np.abs(s - so).max() / so.max() < SIG_TOL and (np.abs(s - so) / so).max() < 1e-8
     assert subspace_angle(U, Uo) < 1e-6
     dA = rt.to_device_colmajor(A)
-    Ud, Sd, Vtd = ld.rand_svd_dev(dA, 20, 10)
+    Ud, Sd, Vtd = ld.rand_svd_dev(dA, 20, 10); rt.synchronize()      # the *_dev drivers return before their stream has drained
     assert np.abs(Sd.cpu().numpy() - s).max() <= 1e-13 * s.max()
     assert np.abs(np.abs(Ud.cpu().numpy()) - np.abs(U)).max() < 1e-9
 
