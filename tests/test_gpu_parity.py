@@ -711,3 +711,88 @@ def test_c2_full_size_properties(rb):
     assert 0 < resid2 < 3 * expect
     del dA
     torch.cuda.empty_cache()
+
+
+def test_c4_full_size_properties(rb):
+    """BASELINE config 4: 1 000 000 x 2000 f64 (16 GB), block sparse-sign sketch with zeta = 8.  Size-independent
+    properties: linearity (S(aX + bY) = a SX + b SY to rounding), agreement of a column of S A with the oracle's operator
+    applied to that single column, E||Sx||^2 = ||x||^2 within the concentration of d = 8000, bit-reproducibility, and the
+    end-to-end least-squares solve (normal-equations residual, planted solution)."""
+    import torch
+    from randnla_b200 import runtime as rt, _lib
+    from oracle import oracle as orc
+    lib = _lib.load()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("needs ~60 GB of free HBM")
+    m, n, d = 1000000, 2000, 8000
+    dA = rt.empty_colmajor(m, n); pA, lda = rt.dev_ptr_ld(dA)
+    _lib.check(lib.rnla_sketch_fill_dev(0, 0, 77, 9, m, n, 0, pA, lda)); rt.synchronize()
+    dS = rt.empty_colmajor(d, n); pS, lds = rt.dev_ptr_ld(dS)
+    def sketch(ptr, ld_, cols, out):
+        po, ldo = rt.dev_ptr_ld(out)
+        _lib.check(lib.rnla_sketch_apply_dev(2, 0, 5, d, 8, ptr, ld_, m, cols, 0, po, ldo)); rt.synchronize()
+    sketch(pA, lda, n, dS)
+    first = dS.clone()
+    sketch(pA, lda, n, dS)
+    assert torch.equal(first, dS)                                                   # fixed summation order
+    # one column against the oracle (CPU, 1M rows x 1 column)
+    col = dA[:, 7].cpu().numpy().reshape(-1, 1)
+    ref = orc.sketch_apply_saso_block(col, d, zeta=8, seed=5)
+    assert np.abs(dS[:, 7].cpu().numpy().reshape(-1, 1) - ref).max() <= 1e-12 * np.abs(ref).max()
+    # norms: ||S a_j||^2 / ||a_j||^2 = 1 +- O(sqrt(2/d))
+    ratio = (torch.linalg.vector_norm(dS, dim=0) / torch.linalg.vector_norm(dA, dim=0)) ** 2
+    assert float((ratio - 1).abs().max()) < 8 * np.sqrt(2.0 / d) and abs(float(ratio.mean()) - 1) < 2e-3
+    # linearity on a 3-column combination
+    X = rt.empty_colmajor(m, 3); X.copy_(dA[:, :3])
+    Y = rt.empty_colmajor(m, 3); Y.copy_(dA[:, 3:6])
+    Z = rt.empty_colmajor(m, 3); Z.copy_(2.5 * X - 0.75 * Y)
+    o3 = rt.empty_colmajor(d, 3); pz, ldz = rt.dev_ptr_ld(Z)
+    sketch(pz, ldz, 3, o3)
+    lin = 2.5 * dS[:, :3] - 0.75 * dS[:, 3:6]
+    assert float((o3 - lin).abs().max()) <= 1e-12 * float(lin.abs().max())
+    # end to end: blendenpik with the block sparse-sign sketch recovers a planted solution
+    torch.manual_seed(3)
+    xt = torch.rand(n, 1, dtype=torch.float64, device="cuda") * 200 - 100
+    db = rt.empty_colmajor(m, 1); db.copy_(dA @ xt)
+    dx = rt.empty_colmajor(n, 1); it = C.c_int64(0); cv = C.c_int32(0)
+    _lib.check(lib.rnla_blendenpik_overdetermined_dev(pA, lda, m, n, C.c_void_p(db.data_ptr()), 1e-8, 100, 4.0, 2, 0, 8,
+                                                      C.c_void_p(dx.data_ptr()), C.byref(it), C.byref(cv)))
+    rt.synchronize()
+    assert cv.value == 1 and it.value < 40
+    assert float(torch.linalg.vector_norm(dx - xt) / torch.linalg.vector_norm(xt)) < 1e-10
+    del dA, dS, X, Y, Z
+    torch.cuda.empty_cache()
+
+
+def test_c5_full_size_properties(rb):
+    """BASELINE config 5: rand_evd2 (Nystrom) on a 50 000 x 50 000 SPD matrix (20 GB), k = 200, s = 10: eigenvalues equal
+    the planted ones, V^T V = I, A V = V Lambda up to the tail."""
+    import torch
+    from randnla_b200 import runtime as rt, _lib, lora_drivers as ld
+    lib = _lib.load()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("needs ~60 GB of free HBM")
+    n, r0, k, s = 50000, 400, 200, 10
+    V0 = rt.empty_colmajor(n, r0); pV, ldv = rt.dev_ptr_ld(V0)
+    _lib.check(lib.rnla_sketch_fill_dev(0, 0, 31, 9, n, r0, 0, pV, ldv))
+    _lib.check(lib.rnla_orth_dev(pV, ldv, n, r0, 0, None, None)); rt.synchronize()
+    lam = np.concatenate([np.logspace(1, -2, 200), np.full(200, 1e-4)])
+    Vs = rt.empty_colmajor(n, r0); Vs.copy_(V0 * torch.from_numpy(lam).cuda())
+    V0t = rt.empty_colmajor(r0, n); V0t.copy_(V0.t())
+    dA = rt.empty_colmajor(n, n); pA, lda = rt.dev_ptr_ld(dA)
+    pVs, ldvs = rt.dev_ptr_ld(Vs); pVt, ldvt = rt.dev_ptr_ld(V0t)
+    _lib.check(lib.rnla_gemm_nn_dev(pVs, ldvs, n, r0, pVt, ldvt, n, pA, lda)); rt.synchronize()
+    dA.copy_(0.5 * (dA + dA.t())); dA.diagonal().add_(1e-8)
+    torch.cuda.synchronize()
+    V, L = ld.rand_evd2_dev(dA, k, s); rt.synchronize()
+    Lh = L.cpu().numpy()
+    assert len(Lh) == k and (np.diff(Lh) <= 0).all()
+    assert np.max(np.abs(Lh - (lam[:k] + 1e-8)) / lam[:k]) < 1e-10
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    assert float((V.t() @ V - eye).abs().max()) < 1e-11
+    R = dA @ V - V * L
+    assert float(torch.linalg.matrix_norm(R)) < 1e-4 * float(lam[0])                  # the 1e-4 tail leaks into the trailing vectors
+    del dA, V0, Vs, V0t
+    torch.cuda.empty_cache()
