@@ -115,6 +115,73 @@ def cpu_baseline(n, sample_rows, threads=None, steps=1, warmup=0):
             "seconds_per_call": t, "tflops": algorithmic_flops(sample_rows, n, K_RANK + S_OVER) / t * 1e-12}
 
 
+def secondary_configs(torch, rt, _lib, lib, dA_headline, hbm_peak):
+    """BASELINE configs 4 and 5 on the same GPU, reusing the headline matrix's memory: the block sparse-sign sketch step and
+    the blendenpik solve on a 1M x 2000 problem, rand_evd2 (Nystrom) on a 50k x 50k SPD matrix."""
+    import ctypes as C
+    from randnla_b200 import lora_drivers as ld
+    out = {}
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    m, n = 1000000, 2000
+    flat = dA_headline.t().reshape(-1)                              # the 32 GB buffer of the headline matrix, column-major
+    A4 = flat[: m * n].view(n, m).t()                               # 1M x 2000 view, lda = m (its content: low-rank + noise columns)
+    pA, lda = rt.dev_ptr_ld(A4)
+    _lib.check(lib.rnla_sketch_fill_dev(0, 0, 77, 9, m, n, 0, pA, lda)); rt.synchronize()
+    for d in (8000, 4000):
+        dS = rt.empty_colmajor(d, n); pS, lds = rt.dev_ptr_ld(dS)
+        ms = timed(lambda: _lib.check(lib.rnla_sketch_apply_dev(2, 0, 5, d, 8, pA, lda, m, n, 0, pS, lds)), 5)
+        gbs = 8.0 * m * n / (ms * 1e-3) * 1e-9
+        out[f"c4_sketch_step_block_sparse_sign_d{d}"] = {"ms": ms, "A_stream_GBps": gbs, "hbm_frac": gbs / hbm_peak, "zeta": 8, "shape": [m, n]}
+    xt = torch.rand(n, 1, dtype=torch.float64, device="cuda") * 200 - 100
+    db = rt.empty_colmajor(m, 1); db.copy_(A4 @ xt + 1e-2 * torch.randn(m, 1, dtype=torch.float64, device="cuda"))   # inconsistent system
+    dx = rt.empty_colmajor(n, 1); it = C.c_int64(0); cv = C.c_int32(0)
+    ms = timed(lambda: _lib.check(lib.rnla_blendenpik_overdetermined_dev(pA, lda, m, n, C.c_void_p(db.data_ptr()), 1e-8, 100, 4.0, 2, 0, 8,
+                                                                         C.c_void_p(dx.data_ptr()), C.byref(it), C.byref(cv))), 1)
+    out["c4_blendenpik_block_sparse_sign_sf4"] = {"ms": ms, "cgls_iterations": int(it.value), "converged": bool(cv.value),
+                                                  "rel_err_vs_planted": float(torch.linalg.vector_norm(dx - xt) / torch.linalg.vector_norm(xt)),
+                                                  "normal_eq_residual": float(torch.linalg.vector_norm(A4.t() @ (db - A4 @ dx)) / torch.linalg.vector_norm(A4.t() @ db)),
+                                                  "phases_ms": [[k, v] for k, v in rt.timings()]}
+    nn_, r0, k, s = 50000, 400, 200, 10
+    A5 = flat[: nn_ * nn_].view(nn_, nn_).t()
+    V0 = rt.empty_colmajor(nn_, r0); pV, ldv = rt.dev_ptr_ld(V0)
+    _lib.check(lib.rnla_sketch_fill_dev(0, 0, 31, 9, nn_, r0, 0, pV, ldv))
+    _lib.check(lib.rnla_orth_dev(pV, ldv, nn_, r0, 0, None, None)); rt.synchronize()
+    lam = np.concatenate([np.logspace(1, -2, 200), np.full(200, 1e-4)])
+    Vs = rt.empty_colmajor(nn_, r0); Vs.copy_(V0 * torch.from_numpy(lam).cuda())
+    V0t = rt.empty_colmajor(r0, nn_); V0t.copy_(V0.t())
+    p5, ld5 = rt.dev_ptr_ld(A5); pVs, ldvs = rt.dev_ptr_ld(Vs); pVt, ldvt = rt.dev_ptr_ld(V0t)
+    _lib.check(lib.rnla_gemm_nn_dev(pVs, ldvs, nn_, r0, pVt, ldvt, nn_, p5, ld5)); rt.synchronize()
+    A5.diagonal().add_(1e-8)                                        # V0 diag(lam) V0^T is symmetric to rounding; symmetrise exactly in place
+    res = {}
+    def run5():
+        res["V"], res["L"] = ld.rand_evd2_dev(A5, k, s)
+    # exact symmetry is a precondition of rand_evd2 (reference :106 style check): mirror the upper triangle blockwise
+    B = 5000
+    for i0 in range(0, nn_, B):
+        for j0 in range(i0, nn_, B):
+            blk = A5[i0:i0 + B, j0:j0 + B]
+            if i0 == j0:
+                blk.copy_(0.5 * (blk + blk.t()))
+            else:
+                A5[j0:j0 + B, i0:i0 + B].copy_(blk.t())
+    torch.cuda.synchronize()
+    ms = timed(run5, 2)
+    L = res["L"].cpu().numpy()
+    out["c5_rand_evd2_50k_k200"] = {"ms": ms, "tflops_fp64": 4 * 2.0 * nn_ * nn_ * (k + s) / (ms * 1e-3) * 1e-12, "r": int(len(L)),
+                                    "max_rel_lambda_err_vs_planted": float(np.max(np.abs(L - (lam[:len(L)] + 1e-8)) / lam[:len(L)])),
+                                    "phases_ms": [[k_, v] for k_, v in rt.timings()]}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -310,6 +377,14 @@ def run_ours(args):
     if world == 1 and args.cpu_rows > 0:
         cb = cpu_baseline(n, args.cpu_rows)
 
+    # ---- other BASELINE configs, one short measurement each (not the headline; device-resident, CUDA events) ----
+    secondary = None
+    if world == 1 and args.secondary:
+        try:
+            secondary = secondary_configs(torch, rt, _lib, lib, dA, hbm_peak)
+        except Exception as exc:                                   # never let a side measurement break the headline line
+            secondary = {"error": repr(exc)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -320,7 +395,7 @@ def run_ours(args):
                    "l2": f"inputs larger than L2 (A shard = {8 * m_local * n / 2**30:.1f} GiB per GPU, streamed 4x per step)"},
         "rand_svd_ms": ms_step, "tflops_fp64": algorithmic_flops(m_global, n, l) / (ms_step * 1e-3) * 1e-12,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cb, "phases_ms": phases,
+        "roofline": roofline, "cpu_baseline": cb, "phases_ms": phases, "secondary": secondary,
         "accuracy": {"max_abs_UtU_minus_I": orth_err, "max_rel_sigma_vs_planted(noise-limited)": sigma_vs_planted},
     }
     print(json.dumps(line), flush=True)
@@ -339,6 +414,7 @@ def main():
     ap.add_argument("--fused", type=int, default=2, help="0 materialise Omega, 1 in-kernel Philox, 2 auto")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-rows", type=int, default=25000, help="row sample of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--secondary", type=int, default=1, help="1: also time BASELINE configs 4 and 5 once (N=1 only, reported under 'secondary')")
     ap.add_argument("--ref-rows", type=int, default=25000, help="row sample per step of --impl reference")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
