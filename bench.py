@@ -131,6 +131,16 @@ def secondary_configs(torch, rt, _lib, lib, dA_headline, hbm_peak):
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    # the headline matrix once more with a sketch narrow enough (l = k + p = 16 < the FP64/HBM ridge of ~21 columns) that the
+    # four A-streaming passes are HBM-bound: this is the regime north_star's "70 % of HBM roofline" can physically refer to
+    mh, nh = dA_headline.shape
+    ms = timed(lambda: ld.rand_svd_dev(dA_headline, 10, 6), 3)
+    ph = rt.timings()
+    pass_ms = [v for k_, v in ph if k_.startswith("pass:")]
+    gbs = 8.0 * mh * nh / (float(np.mean(pass_ms)) * 1e-3) * 1e-9
+    out["c2_matrix_k10_p6_hbm_bound_regime"] = {"ms": ms, "mean_pass_ms": float(np.mean(pass_ms)), "A_stream_GBps_per_pass": gbs,
+                                                "hbm_frac": gbs / hbm_peak, "whole_call_A_stream_GBps": 4 * 8.0 * mh * nh / (ms * 1e-3) * 1e-9,
+                                                "phases_ms": [[k_, v] for k_, v in ph]}
     m, n = 1000000, 2000
     flat = dA_headline.t().reshape(-1)                              # the 32 GB buffer of the headline matrix, column-major
     A4 = flat[: m * n].view(n, m).t()                               # 1M x 2000 view, lda = m (its content: low-rank + noise columns)

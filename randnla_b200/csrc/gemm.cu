@@ -11,6 +11,7 @@
 //   warps 4-11 consumers: 4 (M) x 2 (N) warp grid over a 128 x (16*NT) tile, DMMA.8x8x4 from smem
 //   mbarrier full/empty ring between them.
 #include "gemm.cuh"
+#include <algorithm>
 #include "ptx.cuh"
 #include "rng.cuh"
 
@@ -419,6 +420,132 @@ tn_reduce_grouped_kernel(const double* __restrict__ P, int64_t ldp, int64_t pstr
     }
 }
 
+// ------------------------------------------------------------------------------------------
+//  NN, thin right operand (N <= 32): the HBM-bound regime (l = k + p below the ~21-column ridge).
+//  The 128 x 32 A tiles of the kernel above arrive as 1 KB pieces, one per column, 1.6 MB apart: measured 2.98 TB/s at
+//  l = 16 (36 % of DRAM peak, consumers starved at the full barrier).  DRAM wants long bursts, so this variant gives a CTA
+//  TBM = 1024 (N <= 16) or 512 (N <= 32) consecutive rows and stages A as column segments of 8 / 4 KB; a warp then owns
+//  128 / 64 rows, i.e. 16 / 8 DMMA row tiles x N/8 column tiles of accumulators.  A stage is ONE DMMA k-step (4 columns,
+//  32 KB) so that 6+ stages are in flight and a freed stage is refilled at once: the producer does nothing but issue
+//  copies, the thin B operand (K x N, L2-resident) is fetched by the consumers one stage ahead into registers.
+// ------------------------------------------------------------------------------------------
+constexpr int TBK = 4;                  // one DMMA k-step per stage: 32 KB stages, 6 of them in flight
+constexpr int THIN_CONS = 8;
+constexpr int THIN_THREADS = (THIN_CONS + 1) * 32;
+
+template <int MI /* 8-row tiles per warp */, int NI /* 8-column tiles */>
+struct ThinCfg {
+    static constexpr int TBM = THIN_CONS * 8 * MI;
+    static constexpr int TBMP = TBM + 4;
+    static constexpr int STAGE = TBK * TBMP;             // doubles: the A tile only, B comes straight from L2
+    static constexpr int STAGES = cmin(8, SMEM_BUDGET / (STAGE * 8));
+    static constexpr int SMEM = STAGES * STAGE * 8 + 2 * STAGES * 8;
+};
+
+template <int MI, int NI>
+__global__ void __launch_bounds__(THIN_THREADS, 1)
+gemm_nn_thin_kernel(const GemmNN p) {
+    using Cfg = ThinCfg<MI, NI>;
+    constexpr int TBM = Cfg::TBM, TBMP = Cfg::TBMP, STAGES = Cfg::STAGES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tiles = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * Cfg::STAGE * 8);
+    uint64_t* empty = full + STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i0 = (int64_t)blockIdx.x * TBM;
+    const int rows_valid = (int)min((int64_t)TBM, p.m - i0);
+    const int KT_all = (int)((p.K + TBK - 1) / TBK);
+    const int kt_lo = p.ksplit > 1 ? (int)blockIdx.z * p.kt_per : 0;
+    const int KT = p.ksplit > 1 ? max(0, min(KT_all - kt_lo, p.kt_per)) : KT_all;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], THIN_CONS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == THIN_CONS) {
+        // ================= producer warp: nothing but the copies, issued the moment a stage is free =================
+        const double* Ablk = p.A + i0;
+        const uint32_t bytes = (uint32_t)(rows_valid & ~1) * 8u;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            mbar_wait(&empty[s], ((uint32_t)(kt / STAGES) & 1u) ^ 1u);
+            double* As = tiles + (size_t)s * Cfg::STAGE;
+            const int64_t k0 = (int64_t)(kt_lo + kt) * TBK;
+            const int kv = (int)min((int64_t)TBK, p.K - k0);
+            if (kv == TBK && !(rows_valid & 1)) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[s], bytes * TBK);
+#pragma unroll
+                    for (int kk = 0; kk < TBK; ++kk) bulk_g2s(As + kk * TBMP, Ablk + (k0 + kk) * p.lda, bytes, &full[s]);
+                }
+            } else {
+                // last K step / odd last row: columns past K are zero (their B rows are zero too, but 0 * garbage is NaN)
+                for (int kk = kv; kk < TBK; ++kk)
+                    for (int r = lane; r < TBM; r += 32) As[kk * TBMP + r] = 0.0;
+                if (rows_valid & 1)
+                    for (int kk = lane; kk < kv; kk += 32) As[kk * TBMP + rows_valid - 1] = Ablk[rows_valid - 1 + (k0 + kk) * p.lda];
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[s], bytes * (uint32_t)kv);
+                    if (bytes)
+                        for (int kk = 0; kk < kv; ++kk) bulk_g2s(As + kk * TBMP, Ablk + (k0 + kk) * p.lda, bytes, &full[s]);
+                }
+            }
+        }
+    } else {
+        // ================= consumers: warp w owns rows [w * 8 MI, (w + 1) * 8 MI) of the tile =================
+        const int g = lane >> 2, t = lane & 3;
+        double acc[MI][NI][2];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+        const int a_off = t * TBMP + warp * 8 * MI + g;
+        // B fragment b[ni] = B(k0 + t, 8 ni + g): K x N is L2-resident, fetched one stage ahead into registers
+        auto load_b = [&](int kt, double* b) {
+            const int64_t k = (int64_t)(kt_lo + kt) * TBK + t;
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) {
+                const int col = ni * 8 + g;
+                b[ni] = (kt < KT && k < p.K && col < p.N) ? __ldg(p.B + k + (int64_t)col * p.ldb) : 0.0;
+            }
+        };
+        double bn[NI];
+        load_b(0, bn);
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            double b[NI];
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) b[ni] = bn[ni];
+            load_b(kt + 1, bn);
+            mbar_wait(&full[s], (uint32_t)(kt / STAGES) & 1u);
+            const double* As = tiles + (size_t)s * Cfg::STAGE + a_off;
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) {
+                const double a = As[mi * 8];
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a, b[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        double* Cout = p.ksplit > 1 ? p.P + (int64_t)blockIdx.z * p.pstride : p.C;
+        const int64_t ldo = p.ksplit > 1 ? p.m : p.ldc;
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) {
+            const int64_t row = i0 + warp * 8 * MI + mi * 8 + g;
+            if (row < p.m) {
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni) {
+                    const int64_t col = ni * 8 + 2 * t;
+                    if (col < p.N) Cout[row + col * ldo] = acc[mi][ni][0];
+                    if (col + 1 < p.N) Cout[row + (col + 1) * ldo] = acc[mi][ni][1];
+                }
+            }
+        }
+    }
+}
+
 // C = sum_z P[z] for the split-K partials of gemm_nn, fixed order
 __global__ void __launch_bounds__(256)
 nn_reduce_kernel(const double* __restrict__ P, int64_t pstride, int ksplit, int64_t m, int64_t N, double* __restrict__ C, int64_t ldc) {
@@ -530,6 +657,65 @@ static cudaError_t gemm_nn_dispatch(const GemmNN& p, int nblkN, int NT, cudaStre
     }
 }
 
+template <int MI, int NI>
+static cudaError_t launch_nn_thin(const GemmNN& p, cudaStream_t st) {
+    using Cfg = ThinCfg<MI, NI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_nn_thin_kernel<MI, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((p.m + Cfg::TBM - 1) / Cfg::TBM), 1, (unsigned)p.ksplit);
+    gemm_nn_thin_kernel<MI, NI><<<grid, THIN_THREADS, Cfg::SMEM, st>>>(p);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+// split-K for the thin kernel: few, tall tiles (196 at m = 200 000), so the parts are what fills the SMs
+int gemm_nn_thin_ksplit(int64_t m, int64_t K, int tbm, int sms) {
+    const int64_t tiles = (m + tbm - 1) / tbm;
+    const int KT = (int)((K + TBK - 1) / TBK);
+    int best_s = 1; double best = -1.0;
+    for (int s = 1; s <= 16; ++s) {
+        if (s > 1 && KT / s < 128) break;
+        const int64_t units = tiles * s, waves = (units + sms - 1) / sms;
+        const double eff = (double)units / (double)(waves * sms) - (s > 1 ? 8.0 * s / (double)K : 0.0);
+        if (eff > best + 1e-9) { best = eff; best_s = s; }
+    }
+    return best_s;
+}
+
+static cudaError_t gemm_nn_thin(GemmNN p, int sms, cudaStream_t st) {
+    const bool wide = p.N > 16;
+    const int tbm = wide ? ThinCfg<8, 4>::TBM : ThinCfg<16, 2>::TBM;
+    p.ksplit = gemm_nn_thin_ksplit(p.m, p.K, tbm, sms);
+    const int KT = (int)((p.K + TBK - 1) / TBK);
+    p.kt_per = (KT + p.ksplit - 1) / p.ksplit;
+    p.pstride = p.m * p.N;
+    cudaError_t e = cudaSuccess;
+    if (p.ksplit > 1) {
+        e = cudaMallocAsync(reinterpret_cast<void**>(&p.P), (size_t)p.ksplit * (size_t)p.pstride * sizeof(double), st);
+        if (e != cudaSuccess) return e;
+    }
+    if (p.N <= 8) e = launch_nn_thin<16, 1>(p, st);
+    else if (p.N <= 16) e = launch_nn_thin<16, 2>(p, st);
+    else if (p.N <= 24) e = launch_nn_thin<8, 3>(p, st);
+    else e = launch_nn_thin<8, 4>(p, st);
+    if (p.ksplit > 1) {
+        if (e == cudaSuccess) {
+            const int64_t total = p.m * p.N;
+            int blocks = (int)((total + 255) / 256);
+            if (blocks > sms * 8) blocks = sms * 8;
+            nn_reduce_kernel<<<blocks, 256, 0, st>>>(p.P, p.pstride, p.ksplit, p.m, p.N, p.C, p.ldc);
+            ++g_kernel_launches;
+            e = cudaGetLastError();
+        }
+        cudaFreeAsync(p.P, st);
+    }
+    return e;
+}
+
 // host logic of gemm_nn's split-K choice, separated so that it can be checked without a GPU
 int gemm_nn_ksplit(int64_t m, int64_t K, int64_t N, int sms) {
     const int nblkN = (int)((N + 127) / 128);
@@ -565,6 +751,7 @@ cudaError_t gemm_nn(const GemmNN& p0, cudaStream_t st) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
+    if (!p.gen && p.N <= 32 && p.K >= 1024 && p.m >= 8192 && aligned16(p.A) && (p.lda % 2 == 0)) return gemm_nn_thin(p, sms, st);
     const int KT = (int)((p.K + NN_BK - 1) / NN_BK);
     const int best_s = gemm_nn_ksplit(p.m, p.K, p.N, sms);
     if (best_s == 1) return gemm_nn_dispatch(p, nblkN, NT, st);
@@ -586,13 +773,186 @@ cudaError_t gemm_nn(const GemmNN& p0, cudaStream_t st) {
     return e;
 }
 
+// ------------------------------------------------------------------------------------------
+//  TN, thin right operand (N <= 32): the HBM-bound regime.  Same recipe as gemm_nn_thin_kernel: a CTA takes TCN = 32
+//  columns of A and a chunk of rows, stages A as 32 column segments of TRK = 256 rows (2 KB pieces, 64 KB per stage, 3
+//  stages), the producer warp only issues copies, and the thin operand Q (m x N, L2-resident) is fetched by the
+//  consumers one stage ahead into registers.  The 8 consumer warps split the rows of a stage (32 each); their 32 x N
+//  partial tiles are added in warp order through shared memory at the end, then the chunks by tn_reduce_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int TCN = 32;
+constexpr int TRK = 256;
+constexpr int TRKP = TRK + 4;
+constexpr int TN_THIN_STAGES = 3;
+constexpr int TN_THIN_SMEM = TN_THIN_STAGES * TCN * TRKP * 8 + 2 * TN_THIN_STAGES * 8;
+
+template <int NI>
+__global__ void __launch_bounds__(THIN_THREADS, 1)
+gemm_tn_thin_kernel(const GemmTN p, double* __restrict__ P, int64_t ldp, int64_t pstride, int ncg, int64_t chunk_rows) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tiles = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TN_THIN_STAGES * TCN * TRKP * 8);
+    uint64_t* empty = full + TN_THIN_STAGES;
+    constexpr int STAGE = TCN * TRKP;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = blockIdx.x % ncg, chunk = blockIdx.x / ncg;
+    const int64_t c0 = (int64_t)cg * TCN;
+    const int cols_valid = (int)min((int64_t)TCN, p.n - c0);
+    const int64_t r0 = (int64_t)chunk * chunk_rows, r1 = min(p.m, r0 + chunk_rows);
+    const int KT = (int)((r1 - r0 + TRK - 1) / TRK);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TN_THIN_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], THIN_CONS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == THIN_CONS) {
+        // ================= producer warp =================
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % TN_THIN_STAGES;
+            mbar_wait(&empty[s], ((uint32_t)(kt / TN_THIN_STAGES) & 1u) ^ 1u);
+            double* As = tiles + (size_t)s * STAGE;
+            const int64_t k0 = r0 + (int64_t)kt * TRK;
+            const int kv = (int)min((int64_t)TRK, r1 - k0);
+            const uint32_t bytes = (uint32_t)(kv & ~1) * 8u;
+            if (kv < TRK || cols_valid < TCN) {
+                // ragged end of the chunk / of the matrix: what the copies do not bring is zero (0 * garbage would be NaN)
+                for (int idx = lane; idx < TCN * TRK; idx += 32) {
+                    const int c = idx / TRK, k = idx - c * TRK;
+                    if (c >= cols_valid || k >= (kv & ~1)) As[c * TRKP + k] = (c < cols_valid && k < kv) ? p.A[k0 + k + (c0 + c) * p.lda] : 0.0;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes * (uint32_t)cols_valid);
+            __syncwarp();
+            if (bytes && lane < cols_valid) bulk_g2s(As + lane * TRKP, p.A + k0 + (c0 + lane) * p.lda, bytes, &full[s]);
+        }
+    } else {
+        // ================= consumers: warp w takes rows [32 w, 32 w + 32) of every stage =================
+        const int g = lane >> 2, t = lane & 3;
+        double acc[4][NI][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) { acc[mt][ni][0] = 0.0; acc[mt][ni][1] = 0.0; }
+        constexpr int KS = TRK / THIN_CONS / 4;           // k-steps per warp and stage
+        // b[ks][ni] = Q(k0 + 32 w + 4 ks + t, 8 ni + g), zero outside the chunk / the matrix
+        auto load_b = [&](int kt, double (*b)[NI]) {
+            const int64_t kb = r0 + (int64_t)kt * TRK + warp * (TRK / THIN_CONS) + t;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni) {
+                    const int64_t k = kb + 4 * ks;
+                    const int col = ni * 8 + g;
+                    b[ks][ni] = (kt < KT && k < r1 && col < p.N) ? __ldg(p.Q + k + (int64_t)col * p.ldq) : 0.0;
+                }
+        };
+        double bn[KS][NI];
+        load_b(0, bn);
+        const int a_off = g * TRKP + warp * (TRK / THIN_CONS) + t;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % TN_THIN_STAGES;
+            double b[KS][NI];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni) b[ks][ni] = bn[ks][ni];
+            load_b(kt + 1, bn);
+            mbar_wait(&full[s], (uint32_t)(kt / TN_THIN_STAGES) & 1u);
+            const double* As = tiles + (size_t)s * STAGE + a_off;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const double a = As[mt * 8 * TRKP + 4 * ks];          // A(k, c0 + 8 mt + g) = (A^T)(8 mt + g, k)
+#pragma unroll
+                    for (int ni = 0; ni < NI; ++ni) dmma884(acc[mt][ni][0], acc[mt][ni][1], a, b[ks][ni]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // add the warps' partial tiles in warp order (the ring is drained: every full barrier was waited on)
+        asm volatile("bar.sync 1, %0;" ::"n"(THIN_CONS * 32));
+        double* red = tiles;                               // [warp][32 x 8 NI]
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) {
+                red[(size_t)warp * TCN * 8 * NI + (mt * 8 + g) + (ni * 8 + 2 * t) * TCN] = acc[mt][ni][0];
+                red[(size_t)warp * TCN * 8 * NI + (mt * 8 + g) + (ni * 8 + 2 * t + 1) * TCN] = acc[mt][ni][1];
+            }
+        asm volatile("bar.sync 1, %0;" ::"n"(THIN_CONS * 32));
+        for (int idx = threadIdx.x; idx < TCN * 8 * NI; idx += THIN_CONS * 32) {
+            const int i = idx % TCN, j = idx / TCN;
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < THIN_CONS; ++w) sum += red[(size_t)w * TCN * 8 * NI + idx];
+            if (i < cols_valid && j < p.N) P[(int64_t)chunk * pstride + (c0 + i) + (int64_t)j * ldp] = sum;
+        }
+    }
+}
+
+struct TNThinPlan { int ncg, chunks; int64_t chunk_rows; };
+TNThinPlan plan_tn_thin(int64_t m, int64_t n, int sms) {
+    TNThinPlan pl;
+    pl.ncg = (int)((n + TCN - 1) / TCN);
+    const int64_t maxc = std::max<int64_t>(1, m / (8 * TRK));
+    int64_t want = std::min<int64_t>(maxc, std::max<int64_t>(1, (4LL * sms + pl.ncg - 1) / pl.ncg));
+    double best = -1.0; int64_t bestc = want;
+    for (int64_t cnd = std::max<int64_t>(1, want / 2); cnd <= std::min(maxc, want * 2 + 1); ++cnd) {
+        const int64_t units = (int64_t)pl.ncg * cnd, waves = (units + sms - 1) / sms;
+        const double eff = (double)units / (double)(waves * sms) - 0.0005 * (double)cnd;
+        if (eff > best + 1e-12) { best = eff; bestc = cnd; }
+    }
+    int64_t cr = (m + bestc - 1) / bestc;
+    cr = (cr + TRK - 1) / TRK * TRK;
+    pl.chunk_rows = cr;
+    pl.chunks = (int)((m + cr - 1) / cr);
+    return pl;
+}
+inline bool tn_thin_shape(int64_t m, int64_t n, int64_t N) { return N <= 32 && m >= 16384 && n >= 64; }
+
 size_t gemm_tn_workspace_bytes(int64_t m, int64_t n, int64_t N, int sms) {
     const TNPlan pl = plan_tn(m, n, N, sms);
-    return pl.chunks > 1 ? (size_t)pl.chunks * (size_t)pl.pstride * sizeof(double) : 0;
+    size_t bytes = pl.chunks > 1 ? (size_t)pl.chunks * (size_t)pl.pstride * sizeof(double) : 0;
+    if (tn_thin_shape(m, n, N)) bytes = std::max(bytes, (size_t)plan_tn_thin(m, n, sms).chunks * (size_t)(n * N) * sizeof(double));
+    return bytes;
 }
 
 cudaError_t gemm_tn(const GemmTN& p, double* workspace, size_t workspace_bytes, int sms, cudaStream_t st) {
     if (p.n <= 0 || p.N <= 0) return cudaSuccess;
+    if (tn_thin_shape(p.m, p.n, p.N) && aligned16(p.A) && (p.lda % 2 == 0)) {
+        const TNThinPlan tp = plan_tn_thin(p.m, p.n, sms);
+        const int64_t pstride = p.n * p.N;
+        if (workspace_bytes < (size_t)tp.chunks * (size_t)pstride * sizeof(double)) return cudaErrorInvalidValue;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(gemm_tn_thin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_THIN_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tn_thin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_THIN_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tn_thin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_THIN_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tn_thin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_THIN_SMEM);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        const unsigned grid = (unsigned)(tp.ncg * tp.chunks);
+        const int NI = (int)((p.N + 7) / 8);
+        switch (NI) {
+            case 1: gemm_tn_thin_kernel<1><<<grid, THIN_THREADS, TN_THIN_SMEM, st>>>(p, workspace, p.n, pstride, tp.ncg, tp.chunk_rows); break;
+            case 2: gemm_tn_thin_kernel<2><<<grid, THIN_THREADS, TN_THIN_SMEM, st>>>(p, workspace, p.n, pstride, tp.ncg, tp.chunk_rows); break;
+            case 3: gemm_tn_thin_kernel<3><<<grid, THIN_THREADS, TN_THIN_SMEM, st>>>(p, workspace, p.n, pstride, tp.ncg, tp.chunk_rows); break;
+            default: gemm_tn_thin_kernel<4><<<grid, THIN_THREADS, TN_THIN_SMEM, st>>>(p, workspace, p.n, pstride, tp.ncg, tp.chunk_rows); break;
+        }
+        ++g_kernel_launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const int64_t total = p.n * p.N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > sms * 8) blocks = sms * 8;
+        tn_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, p.n, pstride, tp.chunks, p.Z, p.ldz, p.n, p.N, p.accumulate);
+        ++g_kernel_launches;
+        return cudaGetLastError();
+    }
     const TNPlan pl = plan_tn(p.m, p.n, p.N, sms);
     if (pl.chunks > 1 && workspace_bytes < (size_t)pl.chunks * (size_t)pl.pstride * sizeof(double))
         return cudaErrorInvalidValue;

@@ -102,7 +102,9 @@ def _dev(rt, a):
 
 GEMM_SHAPES = [(1, 1, 1), (7, 5, 3), (128, 32, 16), (129, 33, 17), (300, 70, 9), (1025, 515, 110), (777, 333, 210),
                (4096, 2048, 128), (2000, 1000, 60), (513, 1, 40), (2, 4096, 5),
-               (300, 9001, 40), (2100, 6200, 130)]   # the last two are long enough for the split-K path of gemm_nn
+               (300, 9001, 40), (2100, 6200, 130),   # long enough for the split-K path of gemm_nn
+               (8200, 1030, 16), (9001, 2049, 5), (8192, 1024, 32), (10000, 1500, 24), (70000, 4099, 9),
+               (16400, 70, 17), (33002, 333, 32), (20001, 100, 8), (16384, 64, 1)]   # thin (HBM-bound regime) kernels, NN and TN
 
 
 @pytest.mark.parametrize("m,K,N", GEMM_SHAPES)
