@@ -541,7 +541,7 @@ rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double
     Ctx& c = ctx();
     if (p <= 0 || p > 1024) return fail(RNLA_ERR_INVALID_DIMENSIONS, "small_eigh: 1 <= p <= 1024");
     DevBuf work, info;
-    RNLA_CUDA(work.alloc((2 * (size_t)p * p + (size_t)p) * 8)); RNLA_CUDA(info.alloc(8));
+    RNLA_CUDA(work.alloc(jacobi_svd_work_doubles((int)p) * 8)); RNLA_CUDA(info.alloc(8));
     RNLA_CUDA(jacobi_eigh(dC, ldc, (int)p, dW, p, dLambda, 0, work.d(), info.as<int>(), c.stream));
     int h[2];
     RNLA_CUDA(cudaMemcpyAsync(h, info.p, 8, cudaMemcpyDeviceToHost, c.stream));

@@ -363,7 +363,7 @@ rnla_status dev_rand_evd1(const double* A, int64_t lda, int64_t m_local, int64_t
     DevBuf Q, Bt, C, W, lam, work, info;
     RNLA_CUDA(Q.alloc((size_t)mm * l * 8)); RNLA_CUDA(Bt.alloc((size_t)n * l * 8));
     RNLA_CUDA(C.alloc((size_t)l * l * 8)); RNLA_CUDA(W.alloc((size_t)l * l * 8)); RNLA_CUDA(lam.alloc((size_t)l * 8));
-    RNLA_CUDA(work.alloc((2 * (size_t)l * l + (size_t)l) * 8)); RNLA_CUDA(info.alloc(8));
+    RNLA_CUDA(work.alloc(jacobi_svd_work_doubles(l) * 8)); RNLA_CUDA(info.alloc(8));
     RNLA_TRY(dev_qb1(A, lda, sh, n, l, q, pps, o, Q.d(), mm, Bt.d()));
     {
         PhaseScope ph("core:eigh(BQ)");
@@ -396,7 +396,7 @@ rnla_status dev_rand_evd2(const double* A, int64_t lda, int64_t m_local, int64_t
         PhaseScope ph("check:psd");
         DevBuf W, lam, work, info;
         RNLA_CUDA(W.alloc((size_t)n * n * 8)); RNLA_CUDA(lam.alloc((size_t)n * 8));
-        RNLA_CUDA(work.alloc((2 * (size_t)n * n + (size_t)n) * 8)); RNLA_CUDA(info.alloc(8));
+        RNLA_CUDA(work.alloc(jacobi_svd_work_doubles((int)n) * 8)); RNLA_CUDA(info.alloc(8));
         RNLA_CUDA(jacobi_eigh(A, lda, (int)n, W.d(), n, lam.d(), 0, work.d(), info.as<int>(), c.stream));
         std::vector<double> hl((size_t)n);
         RNLA_CUDA(cudaMemcpyAsync(hl.data(), lam.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c.stream));

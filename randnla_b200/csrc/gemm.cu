@@ -421,7 +421,7 @@ tn_reduce_grouped_kernel(const double* __restrict__ P, int64_t ldp, int64_t pstr
 }
 
 // ------------------------------------------------------------------------------------------
-//  NN, thin right operand (N <= 32): the HBM-bound regime (l = k + p below the ~21-column ridge).
+//  NN, thin right operand (N <= 24): the HBM-bound regime (l = k + p below the ~21-column ridge).
 //  The 128 x 32 A tiles of the kernel above arrive as 1 KB pieces, one per column, 1.6 MB apart: measured 2.98 TB/s at
 //  l = 16 (36 % of DRAM peak, consumers starved at the full barrier).  DRAM wants long bursts, so this variant gives a CTA
 //  TBM = 1024 (N <= 16) or 512 (N <= 32) consecutive rows and stages A as column segments of 8 / 4 KB; a warp then owns
@@ -429,6 +429,9 @@ tn_reduce_grouped_kernel(const double* __restrict__ P, int64_t ldp, int64_t pstr
 //  32 KB) so that 6+ stages are in flight and a freed stage is refilled at once: the producer does nothing but issue
 //  copies, the thin B operand (K x N, L2-resident) is fetched by the consumers one stage ahead into registers.
 // ------------------------------------------------------------------------------------------
+// N <= 24: with four 8-column tiles the prefetched operand no longer fits the registers (measured at l = 32: 14.5 / 28 ms
+// per pass against 7.6 / 7.0 ms at l = 24); wider operands take the general kernels
+constexpr int THIN_MAX_N = 24;
 constexpr int TBK = 4;                  // one DMMA k-step per stage: 32 KB stages, 6 of them in flight
 constexpr int THIN_CONS = 8;
 constexpr int THIN_THREADS = (THIN_CONS + 1) * 32;
@@ -510,14 +513,15 @@ gemm_nn_thin_kernel(const GemmNN p) {
                 b[ni] = (kt < KT && k < p.K && col < p.N) ? __ldg(p.B + k + (int64_t)col * p.ldb) : 0.0;
             }
         };
-        double bn[NI];
-        load_b(0, bn);
+        // three stages of lookahead: a 16-32 KB stage is 700-1400 cycles of work, an L2 round trip under load is more
+        double b1[NI], b2[NI], b3[NI];
+        load_b(0, b1); load_b(1, b2); load_b(2, b3);
         for (int kt = 0; kt < KT; ++kt) {
             const int s = kt % STAGES;
             double b[NI];
 #pragma unroll
-            for (int ni = 0; ni < NI; ++ni) b[ni] = bn[ni];
-            load_b(kt + 1, bn);
+            for (int ni = 0; ni < NI; ++ni) { b[ni] = b1[ni]; b1[ni] = b2[ni]; b2[ni] = b3[ni]; }
+            load_b(kt + 3, b3);
             mbar_wait(&full[s], (uint32_t)(kt / STAGES) & 1u);
             const double* As = tiles + (size_t)s * Cfg::STAGE + a_off;
 #pragma unroll
@@ -688,7 +692,7 @@ int gemm_nn_thin_ksplit(int64_t m, int64_t K, int tbm, int sms) {
 
 static cudaError_t gemm_nn_thin(GemmNN p, int sms, cudaStream_t st) {
     const bool wide = p.N > 16;
-    const int tbm = wide ? ThinCfg<8, 4>::TBM : ThinCfg<16, 2>::TBM;
+    const int tbm = wide ? ThinCfg<8, 3>::TBM : ThinCfg<16, 2>::TBM;
     p.ksplit = gemm_nn_thin_ksplit(p.m, p.K, tbm, sms);
     const int KT = (int)((p.K + TBK - 1) / TBK);
     p.kt_per = (KT + p.ksplit - 1) / p.ksplit;
@@ -700,8 +704,7 @@ static cudaError_t gemm_nn_thin(GemmNN p, int sms, cudaStream_t st) {
     }
     if (p.N <= 8) e = launch_nn_thin<16, 1>(p, st);
     else if (p.N <= 16) e = launch_nn_thin<16, 2>(p, st);
-    else if (p.N <= 24) e = launch_nn_thin<8, 3>(p, st);
-    else e = launch_nn_thin<8, 4>(p, st);
+    else e = launch_nn_thin<8, 3>(p, st);
     if (p.ksplit > 1) {
         if (e == cudaSuccess) {
             const int64_t total = p.m * p.N;
@@ -751,7 +754,7 @@ cudaError_t gemm_nn(const GemmNN& p0, cudaStream_t st) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
-    if (!p.gen && p.N <= 32 && p.K >= 1024 && p.m >= 8192 && aligned16(p.A) && (p.lda % 2 == 0)) return gemm_nn_thin(p, sms, st);
+    if (!p.gen && p.N <= THIN_MAX_N && p.K >= 1024 && p.m >= 8192 && aligned16(p.A) && (p.lda % 2 == 0)) return gemm_nn_thin(p, sms, st);
     const int KT = (int)((p.K + NN_BK - 1) / NN_BK);
     const int best_s = gemm_nn_ksplit(p.m, p.K, p.N, sms);
     if (best_s == 1) return gemm_nn_dispatch(p, nblkN, NT, st);
@@ -774,7 +777,7 @@ cudaError_t gemm_nn(const GemmNN& p0, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
-//  TN, thin right operand (N <= 32): the HBM-bound regime.  Same recipe as gemm_nn_thin_kernel: a CTA takes TCN = 32
+//  TN, thin right operand (N <= 24): the HBM-bound regime.  Same recipe as gemm_nn_thin_kernel: a CTA takes TCN = 32
 //  columns of A and a chunk of rows, stages A as 32 column segments of TRK = 256 rows (2 KB pieces, 64 KB per stage, 3
 //  stages), the producer warp only issues copies, and the thin operand Q (m x N, L2-resident) is fetched by the
 //  consumers one stage ahead into registers.  The 8 consumer warps split the rows of a stage (32 each); their 32 x N
@@ -911,7 +914,7 @@ TNThinPlan plan_tn_thin(int64_t m, int64_t n, int sms) {
     pl.chunks = (int)((m + cr - 1) / cr);
     return pl;
 }
-inline bool tn_thin_shape(int64_t m, int64_t n, int64_t N) { return N <= 32 && m >= 16384 && n >= 64; }
+inline bool tn_thin_shape(int64_t m, int64_t n, int64_t N) { return N <= THIN_MAX_N && m >= 16384 && n >= 64; }
 
 size_t gemm_tn_workspace_bytes(int64_t m, int64_t n, int64_t N, int sms) {
     const TNPlan pl = plan_tn(m, n, N, sms);
@@ -931,7 +934,6 @@ cudaError_t gemm_tn(const GemmTN& p, double* workspace, size_t workspace_bytes, 
             cudaError_t e = cudaFuncSetAttribute(gemm_tn_thin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_THIN_SMEM);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tn_thin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_THIN_SMEM);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tn_thin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_THIN_SMEM);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tn_thin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_THIN_SMEM);
             if (e != cudaSuccess) return e;
             attr_set = true;
         }
@@ -940,8 +942,7 @@ cudaError_t gemm_tn(const GemmTN& p, double* workspace, size_t workspace_bytes, 
         switch (NI) {
             case 1: gemm_tn_thin_kernel<1><<<grid, THIN_THREADS, TN_THIN_SMEM, st>>>(p, workspace, p.n, pstride, tp.ncg, tp.chunk_rows); break;
             case 2: gemm_tn_thin_kernel<2><<<grid, THIN_THREADS, TN_THIN_SMEM, st>>>(p, workspace, p.n, pstride, tp.ncg, tp.chunk_rows); break;
-            case 3: gemm_tn_thin_kernel<3><<<grid, THIN_THREADS, TN_THIN_SMEM, st>>>(p, workspace, p.n, pstride, tp.ncg, tp.chunk_rows); break;
-            default: gemm_tn_thin_kernel<4><<<grid, THIN_THREADS, TN_THIN_SMEM, st>>>(p, workspace, p.n, pstride, tp.ncg, tp.chunk_rows); break;
+            default: gemm_tn_thin_kernel<3><<<grid, THIN_THREADS, TN_THIN_SMEM, st>>>(p, workspace, p.n, pstride, tp.ncg, tp.chunk_rows); break;
         }
         ++g_kernel_launches;
         cudaError_t e = cudaGetLastError();

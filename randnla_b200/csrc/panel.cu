@@ -570,6 +570,64 @@ jacobi_coop_kernel(double* __restrict__ W, double* __restrict__ V, int p, int b,
     if (blockIdx.x == 0 && threadIdx.x == 0) { flags[1] = sweeps; flags[2] = conv; }
 }
 
+// W = C + 1.01 ||C||_F I, V = I, flags cleared (single CTA; p <= 1024)
+__global__ void __launch_bounds__(1024)
+eigh_shift_kernel(const double* __restrict__ C, int64_t ldc, int p, double* __restrict__ W, double* __restrict__ V, int* flags) {
+    __shared__ double red[32];
+    __shared__ double s_shift;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double s = 0.0;
+    for (int idx = tid; idx < p * p; idx += blockDim.x) { const double v = C[(idx % p) + (int64_t)(idx / p) * ldc]; s = fma(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) s_shift = 1.01 * sqrt(t);
+    }
+    __syncthreads();
+    const double shift = s_shift;
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        // symmetrised read: the two triangles of C may differ in the last bit when C came out of a GEMM
+        const double v = 0.5 * (C[r + (int64_t)c * ldc] + C[c + (int64_t)r * ldc]);
+        W[idx] = v + (r == c ? shift : 0.0);
+        V[idx] = (r == c) ? 1.0 : 0.0;
+    }
+    for (int i = tid; i < 4 + JACOBI_MAX_SWEEPS; i += blockDim.x) flags[i] = 0;
+}
+
+// lambda_j = v_j^T C v_j, ordering (0: descending by value, 1: descending by |value|), W_out = sorted eigenvectors
+__global__ void __launch_bounds__(1024)
+eigh_finish_kernel(const double* __restrict__ C, int64_t ldc, int p, const double* __restrict__ V, double* __restrict__ Wout,
+                   int64_t ldw, double* __restrict__ lambda, int order, double* __restrict__ tmp /* p */, const int* __restrict__ flags,
+                   int* info) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < p; j += nwarps) {
+        const double* v = V + (size_t)j * p;
+        double num = 0.0, den = 0.0;
+        for (int k = lane; k < p; k += 32) {
+            double t = 0.0;                                     // (C v)_k with the symmetrised C
+            for (int i = 0; i < p; ++i) t = fma(0.5 * (C[k + (int64_t)i * ldc] + C[i + (int64_t)k * ldc]), v[i], t);
+            num = fma(v[k], t, num); den = fma(v[k], v[k], den);
+        }
+        num = warp_sum(num); den = warp_sum(den);
+        if (lane == 0) tmp[j] = den > 0.0 ? num / den : 0.0;
+    }
+    __syncthreads();
+    for (int j = warp; j < p; j += nwarps) {
+        const double lj = tmp[j];
+        const double kj = order ? fabs(lj) : lj;
+        int rank = 0;
+        for (int i = lane; i < p; i += 32) { const double li = tmp[i]; const double ki = order ? fabs(li) : li; rank += (ki > kj) || (ki == kj && i < j); }
+        rank = (int)(warp_sum((double)rank) + 0.5);
+        for (int k = lane; k < p; k += 32) Wout[k + (int64_t)rank * ldw] = V[(size_t)j * p + k];
+        if (lane == 0) lambda[rank] = lj;
+    }
+    if (tid == 0) { info[0] = flags[1]; info[1] = flags[2] ? 0 : 1; }
+}
+
 // sigma, ordering, U = W / sigma, orthonormal completion; W, V as left by the sweeps.  flags -> info
 __global__ void __launch_bounds__(1024)
 jacobi_svd_finish_kernel(int p, double* __restrict__ U, int64_t ldu, double* __restrict__ sigma, double* __restrict__ Vout,
@@ -637,102 +695,6 @@ jacobi_svd_finish_kernel(int p, double* __restrict__ U, int64_t ldu, double* __r
                 }
             }
         }
-    }
-    if (tid == 0) { info[0] = s_sweeps; info[1] = s_conv ? 0 : 1; }
-}
-
-constexpr int EIGH_MAX_PAIRS = 512;
-
-__global__ void __launch_bounds__(1024)
-jacobi_eigh_kernel(const double* __restrict__ C, int64_t ldc, int p, double* __restrict__ Wout, int64_t ldw,
-                   double* __restrict__ lambda, int order, double* __restrict__ work, int* info) {
-    double* A = work;                    // p x p
-    double* V = work + (size_t)p * p;    // p x p
-    double* lam_tmp = work + 2 * (size_t)p * p;
-    __shared__ double s_cs[EIGH_MAX_PAIRS], s_sn[EIGH_MAX_PAIRS];
-    __shared__ int s_a[EIGH_MAX_PAIRS], s_b[EIGH_MAX_PAIRS];
-    __shared__ int s_rot, s_sweeps, s_conv;
-    __shared__ double s_red[32];
-    __shared__ double s_floor;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    double fro = 0.0;
-    for (int idx = tid; idx < p * p; idx += blockDim.x) {
-        const int c = idx / p, r = idx - c * p;
-        // symmetrise defensively: use the average of the two triangles
-        const double v = 0.5 * (C[r + (int64_t)c * ldc] + C[c + (int64_t)r * ldc]);
-        A[idx] = v; fro += v * v;
-        V[idx] = (r == c) ? 1.0 : 0.0;
-    }
-    fro = warp_sum(fro);
-    if (lane == 0) s_red[warp] = fro;
-    if (tid == 0) { s_sweeps = 0; s_conv = 0; }
-    __syncthreads();
-    if (tid == 0) { double t = 0.0; for (int w = 0; w < nwarps; ++w) t += s_red[w]; s_floor = 1e-20 * sqrt(t); }
-    __syncthreads();
-    const double afloor = s_floor;
-    const int P = (p & 1) ? p + 1 : p;
-    const int npairs = P / 2;
-    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS && P >= 2; ++sweep) {
-        if (tid == 0) s_rot = 0;
-        __syncthreads();
-        for (int round = 0; round < P - 1; ++round) {
-            for (int pi = tid; pi < npairs; pi += blockDim.x) {
-                int a, b; rr_pair(round, pi, P, a, b);
-                double cs = 1.0, sn = 0.0;
-                if (b < p) {
-                    const double aa = A[a + (size_t)a * p], bb = A[b + (size_t)b * p], ab = A[a + (size_t)b * p];
-                    if (fabs(ab) > DBL_EPSILON * sqrt(fabs(aa * bb)) && fabs(ab) > afloor) {
-                        const double tau = (bb - aa) / (2.0 * ab);
-                        const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        cs = 1.0 / sqrt(1.0 + t * t); sn = t * cs;
-                        s_rot = 1;
-                    }
-                } else { a = -1; }
-                s_a[pi] = a; s_b[pi] = b; s_cs[pi] = cs; s_sn[pi] = sn;
-            }
-            __syncthreads();
-            // columns: A <- A J, V <- V J
-            for (int idx = tid; idx < npairs * p; idx += blockDim.x) {
-                const int pi = idx / p, k = idx - pi * p;
-                const int a = s_a[pi]; const double sn = s_sn[pi];
-                if (a < 0 || sn == 0.0) continue;
-                const int b = s_b[pi]; const double cs = s_cs[pi];
-                const double x = A[k + (size_t)a * p], y = A[k + (size_t)b * p];
-                A[k + (size_t)a * p] = cs * x - sn * y; A[k + (size_t)b * p] = sn * x + cs * y;
-                const double vx = V[k + (size_t)a * p], vy = V[k + (size_t)b * p];
-                V[k + (size_t)a * p] = cs * vx - sn * vy; V[k + (size_t)b * p] = sn * vx + cs * vy;
-            }
-            __syncthreads();
-            // rows: A <- J^T A
-            for (int idx = tid; idx < npairs * p; idx += blockDim.x) {
-                const int pi = idx / p, k = idx - pi * p;
-                const int a = s_a[pi]; const double sn = s_sn[pi];
-                if (a < 0 || sn == 0.0) continue;
-                const int b = s_b[pi]; const double cs = s_cs[pi];
-                const double x = A[a + (size_t)k * p], y = A[b + (size_t)k * p];
-                A[a + (size_t)k * p] = cs * x - sn * y; A[b + (size_t)k * p] = sn * x + cs * y;
-            }
-            __syncthreads();
-        }
-        const int rot = s_rot;
-        __syncthreads();
-        if (tid == 0) s_sweeps = sweep + 1;
-        if (!rot) { if (tid == 0) s_conv = 1; break; }
-    }
-    __syncthreads();
-    for (int j = tid; j < p; j += blockDim.x) lam_tmp[j] = A[j + (size_t)j * p];
-    __syncthreads();
-    for (int j = warp; j < p; j += nwarps) {
-        const double lj = lam_tmp[j];
-        const double kj = order ? fabs(lj) : lj;
-        int rank = 0;
-        for (int i = lane; i < p; i += 32) {
-            const double li = lam_tmp[i]; const double ki = order ? fabs(li) : li;
-            rank += (ki > kj) || (ki == kj && i < j);
-        }
-        rank = (int)(warp_sum((double)rank) + 0.5);
-        for (int k = lane; k < p; k += 32) Wout[k + (int64_t)rank * ldw] = V[k + (size_t)j * p];
-        if (lane == 0) lambda[rank] = lj;
     }
     if (tid == 0) { info[0] = s_sweeps; info[1] = s_conv ? 0 : 1; }
 }
@@ -865,12 +827,9 @@ cudaError_t scale_columns(double* X, int64_t ld, int64_t rows, int64_t cols, con
 }
 size_t jacobi_svd_work_doubles(int p) { return 2 * (size_t)p * p + (size_t)p + 8 + (4 + JACOBI_MAX_SWEEPS + 1) / 2; }
 
-cudaError_t jacobi_svd(const double* M, int64_t ldm, int p, double* U, int64_t ldu, double* sigma,
-                       double* V, int64_t ldv, double* work, int* info, cudaStream_t st, int transpose) {
+// the sweeps on W (p x p, ld p) with V accumulating the rotations: one CTA for small p, a cooperative grid otherwise
+static cudaError_t jacobi_run_sweeps(double* W, double* Vw, int p, int* flags, cudaStream_t st) {
     constexpr int JSMEM = 224 * 1024;
-    double* W = work;
-    double* Vw = work + (size_t)p * p;
-    int* flags = reinterpret_cast<int*>(work + 2 * (size_t)p * p + (size_t)p);     // 4 + JACOBI_MAX_SWEEPS ints
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(jacobi_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JSMEM);
@@ -878,8 +837,6 @@ cudaError_t jacobi_svd(const double* M, int64_t ldm, int p, double* U, int64_t l
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    jacobi_init_kernel<<<grid_for((int64_t)p * p, 256), 256, 0, st>>>(M, ldm, p, transpose, W, Vw, flags);
-    ++g_kernel_launches;
     if (p <= 72) {
         // small enough that one SM's shared-memory bandwidth is not the limit: every sweep inside one CTA
         jacobi_single_kernel<<<1, 1024, 16 * (size_t)p * p + 16, st>>>(W, Vw, p, JACOBI_MAX_SWEEPS, flags);
@@ -901,6 +858,17 @@ cudaError_t jacobi_svd(const double* M, int64_t ldm, int p, double* U, int64_t l
         if (e != cudaSuccess) return e;
         ++g_kernel_launches;
     }
+    return cudaSuccess;
+}
+
+cudaError_t jacobi_svd(const double* M, int64_t ldm, int p, double* U, int64_t ldu, double* sigma,
+                       double* V, int64_t ldv, double* work, int* info, cudaStream_t st, int transpose) {
+    double* W = work;
+    double* Vw = work + (size_t)p * p;
+    int* flags = reinterpret_cast<int*>(work + 2 * (size_t)p * p + (size_t)p);     // 4 + JACOBI_MAX_SWEEPS ints
+    jacobi_init_kernel<<<grid_for((int64_t)p * p, 256), 256, 0, st>>>(M, ldm, p, transpose, W, Vw, flags);
+    ++g_kernel_launches;
+    { cudaError_t e = jacobi_run_sweeps(W, Vw, p, flags, st); if (e != cudaSuccess) return e; }
     // the sweeps factor W0 = X diag(sigma) Y^T with X from the rotated columns and Y the accumulated rotations;
     // W0 = M^T swaps the roles of the two sides
     if (transpose) jacobi_svd_finish_kernel<<<1, 1024, 0, st>>>(p, V, ldv, sigma, U, ldu, work, flags, info);
@@ -909,8 +877,17 @@ cudaError_t jacobi_svd(const double* M, int64_t ldm, int p, double* U, int64_t l
 }
 cudaError_t jacobi_eigh(const double* C, int64_t ldc, int p, double* W, int64_t ldw, double* lambda,
                         int order, double* work, int* info, cudaStream_t st) {
-    if (p > 2 * EIGH_MAX_PAIRS) return cudaErrorInvalidValue;
-    jacobi_eigh_kernel<<<1, 1024, 0, st>>>(C, ldc, p, W, ldw, lambda, order, work, info);
+    // Symmetric eigen-decomposition through the one-sided sweeps above: M = C + shift I with shift = 1.01 ||C||_F is
+    // positive definite with condition number <= 201, its one-sided Jacobi factors M V = V diag(mu) give the eigenvectors of
+    // C, and the eigenvalues are the Rayleigh quotients v^T C v (absolute accuracy eps ||C||, as for any Jacobi method on an
+    // indefinite matrix).  The old two-sided kernel ran in one CTA on global memory: 11 ms at p = 110.
+    double* Wk = work;
+    double* Vw = work + (size_t)p * p;
+    int* flags = reinterpret_cast<int*>(work + 2 * (size_t)p * p + (size_t)p);
+    eigh_shift_kernel<<<1, 1024, 0, st>>>(C, ldc, p, Wk, Vw, flags);
+    ++g_kernel_launches;
+    { cudaError_t e = jacobi_run_sweeps(Wk, Vw, p, flags, st); if (e != cudaSuccess) return e; }
+    eigh_finish_kernel<<<1, 1024, 0, st>>>(C, ldc, p, Vw, W, ldw, lambda, order, work + 2 * (size_t)p * p, flags, info);
     return LAUNCHED();
 }
 
