@@ -396,10 +396,10 @@ def test_cgls_and_blendenpik_restatement(orc):
     rng = np.random.default_rng(3)
     a = rng.standard_normal((200, 12)); b = rng.standard_normal((200, 1))
     x, it, conv = orc.cgls(a, b, 1e-12, 100)
-    xr = np.zeros((12, 1)); r = b - a @ xr; s = a.T @ r; p_ = s.copy(); ns = float(s.T @ s); itr = 0; cv = False
+    xr = np.zeros((12, 1)); r = b - a @ xr; s = a.T @ r; p_ = s.copy(); ns = (s.T @ s).item(); itr = 0; cv = False
     for i in range(100):
-        ap = a @ p_; alpha = ns / float(ap.T @ ap); xr += alpha * p_; r -= alpha * ap
-        sn = a.T @ r; nn = float(sn.T @ sn)
+        ap = a @ p_; alpha = ns / (ap.T @ ap).item(); xr += alpha * p_; r -= alpha * ap
+        sn = a.T @ r; nn = (sn.T @ sn).item()
         if np.sqrt(nn) < 1e-12:
             cv = True; itr = i + 1; break
         p_ = sn + (nn / ns) * p_; ns = nn
