@@ -190,6 +190,16 @@ rnla_status rnla_blendenpik_overdetermined_dev(const double* dA, int64_t lda, in
                                                double epsilon, int64_t l, double sampling_factor, int32_t kind, int32_t dist,
                                                int32_t zeta, double* dx, int64_t* iterations, int32_t* converged);
 
+/* lsrn_overdetermined end to end (reference src/sketch_and_precondition.rs:82-119): sketch, SVD of the sketch, N = V Sigma^-1
+ * (0 where sigma == 0, :112), CGLS on A N in operator form from y = 0, x = N y.  Same arguments as blendenpik.  The on-device
+ * SVD core limits n to 1024 (RNLA_ERR_INVALID_DIMENSIONS beyond). */
+rnla_status rnla_lsrn_overdetermined(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l,
+                                     double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* x,
+                                     int64_t* iterations, int32_t* converged);
+rnla_status rnla_lsrn_overdetermined_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db, double epsilon,
+                                         int64_t l, double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* dx,
+                                         int64_t* iterations, int32_t* converged);
+
 /* ---- building blocks on device buffers (tests, benches, host mirrors) ---------------------------- */
 /* y (m) = A x (trans = 0) or y (n) = A^T x (trans != 0, all-reduced over the communicator): the two streaming kernels of CGLS */
 rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int32_t trans, const double* dx, double* dy);

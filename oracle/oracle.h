@@ -70,6 +70,8 @@ void orc_sketch_apply_saso(uint64_t seed, int64_t d, int zeta, const double* A, 
 int64_t orc_cgls(const double* a, int64_t m, int64_t n, const double* b, double tolerance, int64_t num_iterations, double* x, int* converged_out);
 int orc_blendenpik(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l, double sampling_factor,
                    int kind, int dist_or_width, int zeta, uint64_t seed, double* x, int64_t* iters_out, int* converged_out);
+int orc_lsrn(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l, double sampling_factor,
+             int kind, int dist_or_width, int zeta, uint64_t seed, double* x, int64_t* iters_out, int* converged_out);
 void orc_sketch_apply_saso_block(uint64_t seed, int64_t d, int zeta, int w, const double* A, int64_t m, int64_t n,
                                  int64_t row_off, double* A_sk);
 

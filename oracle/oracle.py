@@ -284,6 +284,19 @@ def blendenpik(A, b, epsilon, l, sampling_factor, kind=0, dist_or_width=0, zeta=
     return x, int(it.value), bool(conv.value)
 
 
+def lsrn(A, b, epsilon, l, sampling_factor, kind=0, dist_or_width=0, zeta=8, seed=0):
+    """src/sketch_and_precondition.rs:82-119 -> (x, iterations, converged)"""
+    A = F(A); m, n = A.shape
+    b = F(np.asarray(b, dtype=np.float64).reshape(-1, 1))
+    x = np.zeros((n, 1), order="F")
+    it = i64(0); conv = C.c_int(0)
+    rc = load().orc_lsrn(p(A), i64(m), i64(n), p(b), C.c_double(epsilon), i64(l), C.c_double(sampling_factor), C.c_int(kind),
+                         C.c_int(dist_or_width), C.c_int(zeta), u64(seed), p(x), C.byref(it), C.byref(conv))
+    if rc:
+        raise ValueError(rc)
+    return x, int(it.value), bool(conv.value)
+
+
 def set_threads(n):
     load().orc_set_threads(C.c_int(n))
 

@@ -763,3 +763,36 @@ int orc_blendenpik(const double* A, int64_t m, int64_t n, const double* b, doubl
     free(Ask); free(bsk); free(Q); free(R); free(z); free(Rinv);
     return rc;
 }
+
+/* src/sketch_and_precondition.rs:82-119 (sketch operator as in orc_blendenpik).  Returns 0, 4/1 for the validation errors
+ * (:85-104), 7 if the SVD fails. */
+int orc_lsrn(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l, double sampling_factor,
+             int kind, int dist_or_width, int zeta, uint64_t seed, double* x, int64_t* iters_out, int* converged_out) {
+    if (m < n) return 4;                                                                  /* :85-89 */
+    if (sampling_factor < 1.0 || epsilon <= 0.0 || l <= 0) return 1;                      /* :90-104 */
+    const int64_t d = orc_sketch_dim(m, n, sampling_factor, 0);                           /* :105 */
+    double* Ask = dalloc(d * n);
+    if (kind == 0) orc_sketch_apply_dense(dist_or_width, seed, d, A, m, n, Ask);          /* :106-107 */
+    else if (kind == 1) orc_sketch_apply_saso(seed, d, zeta, A, m, n, Ask);
+    else orc_sketch_apply_saso_block(seed, d, zeta, dist_or_width ? dist_or_width : (zeta < 4 ? zeta : 4), A, m, n, 0, Ask);
+    const int64_t r = imin(d, n);
+    double* U = dalloc(d * r); double* sg = dalloc(r); double* Vt = dalloc(r * n);
+    int rc = 0;
+    if (orc_svd(Ask, d, n, U, sg, Vt) != 0) rc = 7;                                       /* :109 svd(false, true) */
+    else {
+        double* N = dalloc(n * r);                                                        /* :110-113 n = v * sigma_inv */
+        for (int64_t j = 0; j < r; ++j)
+            for (int64_t i = 0; i < n; ++i) AT(N, n, i, j) = sg[j] != 0.0 ? AT(Vt, r, j, i) / sg[j] : 0.0;
+        double* Ap = dalloc(m * r);
+        orc_gemm_nn(A, m, m, n, N, n, r, Ap, m);                                          /* :114 */
+        double* y = dalloc(r);                                                            /* :115 zeros */
+        int conv = 0;
+        const int64_t it = orc_cgls(Ap, m, r, b, epsilon, l, y, &conv);                   /* :116 */
+        orc_gemm_nn(N, n, n, r, y, r, 1, x, n);                                           /* :117 */
+        if (iters_out) *iters_out = it;
+        if (converged_out) *converged_out = conv;
+        free(N); free(Ap); free(y);
+    }
+    free(Ask); free(U); free(sg); free(Vt);
+    return rc;
+}

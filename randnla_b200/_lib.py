@@ -64,6 +64,8 @@ SIGNATURES = {
     "rnla_orth_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, C.POINTER(c_i64)]),
     "rnla_small_svd_dev": (c_i32, [P, c_i64, c_i64, P, P, P]),
     "rnla_last_jacobi_sweeps": (c_i32, []),
+    "rnla_lsrn_overdetermined": (c_i32, [P, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
+    "rnla_lsrn_overdetermined_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
     "rnla_plan_gemm": (None, [c_i64, c_i64, c_i64, c_i32, P]),
     "rnla_plan_saso_block": (c_i32, [c_i64, c_i32, c_i32, c_i64, c_i64, c_i32, P, P, c_i32, P]),
     "rnla_gemv_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, P]),

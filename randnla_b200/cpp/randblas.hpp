@@ -220,6 +220,17 @@ inline DMatrix blendenpik_overdetermined(const DMatrix& a, const DMatrix& b, dou
     else std::printf("CGLS failed to converged after %zu iterations\n", l);                        // src/cg.rs:58
     return x;
 }
+// lsrn_overdetermined end to end (:82-119), n <= 1024: returns x (n x 1)
+inline DMatrix lsrn_overdetermined(const DMatrix& a, const DMatrix& b, double epsilon, size_t l, double sampling_factor,
+                                   rnla_sketch_kind kind = RNLA_SKETCH_DENSE, int zeta = 8, int width = 0) {
+    validate(a, epsilon, l, sampling_factor);
+    DMatrix x(a.ncols(), 1);
+    int64_t iters = 0; int32_t conv = 0;
+    errors::check(rnla_lsrn_overdetermined(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), b.as_ptr(), epsilon, (int64_t)l,
+                                           sampling_factor, kind, kind == RNLA_SKETCH_SASO_BLOCK ? width : RNLA_GAUSSIAN, zeta,
+                                           x.as_mut_ptr(), &iters, &conv));
+    return x;
+}
 // sketch step of lsrn_overdetermined (:105-107) and sketch_saddle_point_precondition (:172-176, saddle = true)
 inline DMatrix sketch_only(const DMatrix& a, double epsilon, size_t l, double sampling_factor, bool saddle = false,
                            rnla_sketch_kind kind = RNLA_SKETCH_DENSE, int zeta = 8) {

@@ -491,6 +491,28 @@ int32_t rnla_plan_saso_block(int64_t d, int32_t zeta, int32_t width, int64_t n, 
     return (int32_t)work.size();
 }
 
+rnla_status rnla_lsrn_overdetermined_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db, double epsilon,
+                                         int64_t l, double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* dx,
+                                         int64_t* iterations, int32_t* converged) {
+    RNLA_TRY(ensure_ctx());
+    ShardInfo sh;
+    RNLA_TRY(shard_layout(m_local, &sh));
+    RNLA_TRY(validate_lsq(sh.rows_global, n, epsilon, l, sampling_factor));                          // :85-104
+    return dev_lsrn(dA, lda, m_local, n, db, epsilon, l, sampling_factor, kind, dist, zeta, ctx().opts.seed, dx, iterations, converged);
+}
+rnla_status rnla_lsrn_overdetermined(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l,
+                                     double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* x,
+                                     int64_t* iterations, int32_t* converged) {
+    RNLA_TRY(validate_lsq(m, n, epsilon, l, sampling_factor));
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, db, dx;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_TRY(h2d(db, b, (size_t)m));
+    RNLA_CUDA(dx.alloc((size_t)n * 8));
+    RNLA_TRY(dev_lsrn(dA.d(), m, m, n, db.d(), epsilon, l, sampling_factor, kind, dist, zeta, ctx().opts.seed, dx.d(), iterations, converged));
+    return d2h(x, dx.d(), (size_t)n);
+}
+
 rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int32_t trans, const double* dx, double* dy) {
     RNLA_TRY(ensure_ctx());
     return trans ? dev_gemv_t(dA, lda, m, n, dx, dy) : dev_gemv_n(dA, lda, m, n, dx, dy);

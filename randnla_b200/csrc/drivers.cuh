@@ -51,6 +51,10 @@ rnla_status dev_blendenpik(const double* A, int64_t lda, int64_t m_local, int64_
                            int64_t maxit, double sampling_factor, int kind, int dist_or_width, int zeta, uint64_t seed,
                            double* x, int64_t* iters_out, int32_t* converged_out);
 
+rnla_status dev_lsrn(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double epsilon, int64_t maxit,
+                     double sampling_factor, int kind, int dist_or_width, int zeta, uint64_t seed, double* x,
+                     int64_t* iters_out, int32_t* converged_out);
+
 // literal.cu: bug-compatible pieces of the reference
 rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
                           const rnla_options& o, double* S);

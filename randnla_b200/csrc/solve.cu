@@ -263,6 +263,48 @@ rnla_status dev_tri_inv_blocked(const double* R, int64_t ldr, int n, double* Rin
     return RNLA_OK;
 }
 
+// cgls(a = A M, b, tolerance, num_iterations, x = z) of src/cg.rs:18-61 in operator form: M (n x n, ld n) is applied to
+// n-vectors, A is streamed twice per iteration.  z: initial guess in, solution of the preconditioned system out.
+static rnla_status cgls_operator(Solver& S, const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b,
+                                 const double* M, double* z, double epsilon, int64_t maxit, int64_t* it_out, int32_t* conv_out) {
+    Ctx& c = S.c;
+    PhaseScope ph("cgls");
+    const int nn = (int)n;
+    const int64_t mm = std::max<int64_t>(m_local, 1);
+    DevBuf r, s, p, t, ap, u;
+    RNLA_CUDA(s.alloc((size_t)n * 8)); RNLA_CUDA(p.alloc((size_t)n * 8)); RNLA_CUDA(t.alloc((size_t)n * 8)); RNLA_CUDA(u.alloc((size_t)n * 8));
+    RNLA_CUDA(r.alloc((size_t)mm * 8)); RNLA_CUDA(ap.alloc((size_t)mm * 8));
+    int64_t it = 0; int32_t conv = 0;
+    RNLA_TRY(S.small_gemv(M, n, nn, 0, z, t.d()));                                                        // t = M x
+    RNLA_TRY(dev_gemv_n(A, lda, m_local, n, t.d(), ap.d()));                                              // a x
+    RNLA_CUDA(cudaMemcpyAsync(r.p, b, (size_t)m_local * 8, cudaMemcpyDeviceToDevice, c.stream));
+    RNLA_TRY(S.axpby(-1.0, ap.d(), 1.0, r.d(), m_local));                                                 // r = b - a x       :30
+    RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), u.d()));
+    RNLA_TRY(S.small_gemv(M, n, nn, 1, u.d(), s.d()));                                                    // s = a^T r          :31
+    RNLA_CUDA(cudaMemcpyAsync(p.p, s.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c.stream));              // p = s              :32
+    double norm_s = 0.0;
+    RNLA_TRY(S.dot(s.d(), s.d(), n, false, &norm_s));                                                     // :33
+    for (it = 0; it < maxit; ++it) {
+        RNLA_TRY(S.small_gemv(M, n, nn, 0, p.d(), t.d()));
+        RNLA_TRY(dev_gemv_n(A, lda, m_local, n, t.d(), ap.d()));                                          // ap = a p           :36
+        double apap = 0.0;
+        RNLA_TRY(S.dot(ap.d(), ap.d(), m_local, true, &apap));
+        const double alpha = norm_s / apap;                                                               // :37
+        RNLA_TRY(S.axpby(alpha, p.d(), 1.0, z, n));                                                       // x += alpha p       :38
+        RNLA_TRY(S.axpby(-alpha, ap.d(), 1.0, r.d(), m_local));                                           // r -= alpha ap      :39
+        RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), u.d()));
+        RNLA_TRY(S.small_gemv(M, n, nn, 1, u.d(), s.d()));                                                // s_new = a^T r      :40
+        double norm_new = 0.0;
+        RNLA_TRY(S.dot(s.d(), s.d(), n, false, &norm_new));                                               // :41
+        if (std::sqrt(norm_new) < epsilon) { conv = 1; ++it; break; }                                     // :44-48
+        const double beta = norm_new / norm_s;                                                            // :50
+        norm_s = norm_new;
+        RNLA_TRY(S.axpby(1.0, s.d(), beta, p.d(), n));                                                    // p = s_new + beta p :52
+    }
+    *it_out = it; *conv_out = conv;
+    return RNLA_OK;
+}
+
 // blendenpik_overdetermined on device buffers.  A: m_local x n (row shard), b: m_local.  x: n (replicated).
 // iters_out: CGLS iterations used; converged_out: 1 if the reference's stopping rule ||s|| < epsilon fired.
 rnla_status dev_blendenpik(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double epsilon,
@@ -278,13 +320,11 @@ rnla_status dev_blendenpik(const double* A, int64_t lda, int64_t m_local, int64_
     const int nn = (int)n;
     Solver S(c);
     RNLA_TRY(S.init());
-    DevBuf Ask, bsk, R, Rinv, z, r, s, p, t, ap, u;
+    DevBuf Ask, bsk, R, Rinv, z;
     RNLA_CUDA(Ask.alloc((size_t)d * n * 8)); RNLA_CUDA(bsk.alloc((size_t)d * 8));
     RNLA_CUDA(R.alloc((size_t)n * n * 8)); RNLA_CUDA(Rinv.alloc((size_t)n * n * 8));
     const int64_t mm = std::max<int64_t>(m_local, 1);
-    RNLA_CUDA(z.alloc((size_t)n * 8)); RNLA_CUDA(s.alloc((size_t)n * 8)); RNLA_CUDA(p.alloc((size_t)n * 8));
-    RNLA_CUDA(t.alloc((size_t)n * 8)); RNLA_CUDA(u.alloc((size_t)n * 8));
-    RNLA_CUDA(r.alloc((size_t)mm * 8)); RNLA_CUDA(ap.alloc((size_t)mm * 8));
+    RNLA_CUDA(z.alloc((size_t)n * 8));
     {
         // the sketch step: the same operator S for A and b                                                    :50-52
         RNLA_TRY(dev_sketch_apply(kind, dist_or_width, seed, d, zeta, A, lda, m_local, n, sh.row_off, Ask.d(), d));
@@ -310,37 +350,64 @@ rnla_status dev_blendenpik(const double* A, int64_t lda, int64_t m_local, int64_
         RNLA_TRY(dev_tri_inv_blocked(R.d(), n, nn, Rinv.d(), n));                                             // :55
     }
     int64_t it = 0; int32_t conv = 0;
-    {
-        PhaseScope ph("cgls");
-        // cgls(a = A Rinv, b, tolerance, num_iterations, x = z0)                                              cg.rs:18-61
-        RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 0, z.d(), t.d()));                                             // t = Rinv x
-        RNLA_TRY(dev_gemv_n(A, lda, m_local, n, t.d(), ap.d()));                                              // a x
-        RNLA_CUDA(cudaMemcpyAsync(r.p, b, (size_t)m_local * 8, cudaMemcpyDeviceToDevice, c.stream));
-        RNLA_TRY(S.axpby(-1.0, ap.d(), 1.0, r.d(), m_local));                                                 // r = b - a x       :30
-        RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), u.d()));
-        RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 1, u.d(), s.d()));                                             // s = a^T r          :31
-        RNLA_CUDA(cudaMemcpyAsync(p.p, s.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c.stream));              // p = s              :32
-        double norm_s = 0.0;
-        RNLA_TRY(S.dot(s.d(), s.d(), n, false, &norm_s));                                                     // :33
-        for (it = 0; it < maxit; ++it) {
-            RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 0, p.d(), t.d()));
-            RNLA_TRY(dev_gemv_n(A, lda, m_local, n, t.d(), ap.d()));                                          // ap = a p           :36
-            double apap = 0.0;
-            RNLA_TRY(S.dot(ap.d(), ap.d(), m_local, true, &apap));
-            const double alpha = norm_s / apap;                                                               // :37
-            RNLA_TRY(S.axpby(alpha, p.d(), 1.0, z.d(), n));                                                   // x += alpha p       :38
-            RNLA_TRY(S.axpby(-alpha, ap.d(), 1.0, r.d(), m_local));                                           // r -= alpha ap      :39
-            RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), u.d()));
-            RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 1, u.d(), s.d()));                                         // s_new = a^T r      :40
-            double norm_new = 0.0;
-            RNLA_TRY(S.dot(s.d(), s.d(), n, false, &norm_new));                                               // :41
-            if (std::sqrt(norm_new) < epsilon) { conv = 1; ++it; break; }                                     // :44-48
-            const double beta = norm_new / norm_s;                                                            // :50
-            norm_s = norm_new;
-            RNLA_TRY(S.axpby(1.0, s.d(), beta, p.d(), n));                                                    // p = s_new + beta p :52
-        }
-    }
+    RNLA_TRY(cgls_operator(S, A, lda, m_local, n, b, Rinv.d(), z.d(), epsilon, maxit, &it, &conv));             // :56-57
     RNLA_TRY(S.small_gemv(Rinv.d(), n, nn, 0, z.d(), x));                                                     // x = Rinv z         :58
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    if (iters_out) *iters_out = it;
+    if (converged_out) *converged_out = conv;
+    return RNLA_OK;
+}
+
+// N(:, j) = V(:, j) / sigma_j, or 0 where sigma_j == 0                          src/sketch_and_precondition.rs:112-113
+__global__ void __launch_bounds__(256)
+scale_inv_columns_kernel(const double* __restrict__ V, int64_t ldv, int n, const double* __restrict__ sigma, double* __restrict__ N, int64_t ldn) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {
+        const int c = idx / n, r = idx - c * n;
+        const double sg = sigma[c];
+        N[r + (int64_t)c * ldn] = sg != 0.0 ? V[r + (int64_t)c * ldv] / sg : 0.0;
+    }
+}
+
+// lsrn_overdetermined on device buffers (reference src/sketch_and_precondition.rs:82-119): sketch, SVD of the sketch
+// (blocked QR, then one-sided Jacobi on R^T), N = V Sigma^-1, CGLS on A N in operator form from y = 0, x = N y.
+// The Jacobi core takes n <= 1024.
+rnla_status dev_lsrn(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double epsilon, int64_t maxit,
+                     double sampling_factor, int kind, int dist_or_width, int zeta, uint64_t seed, double* x,
+                     int64_t* iters_out, int32_t* converged_out) {
+    Ctx& c = ctx();
+    phases_reset();
+    ShardInfo sh;
+    RNLA_TRY(shard_layout(m_local, &sh));
+    const int64_t m = sh.rows_global;
+    if (n <= 0 || n > 1024) return fail(RNLA_ERR_INVALID_DIMENSIONS, "lsrn (device): 1 <= n <= 1024 (size of the on-device SVD core)");
+    const int64_t d = (sampling_factor * (double)n > (double)m) ? m : (int64_t)std::floor(sampling_factor * (double)n);   // :105
+    const int nn = (int)n;
+    Solver S(c);
+    RNLA_TRY(S.init());
+    DevBuf Ask, R, Ur, Vr, sig, Nm, y, work, info;
+    RNLA_CUDA(Ask.alloc((size_t)d * n * 8)); RNLA_CUDA(R.alloc((size_t)n * n * 8));
+    RNLA_CUDA(Ur.alloc((size_t)n * n * 8)); RNLA_CUDA(Vr.alloc((size_t)n * n * 8)); RNLA_CUDA(sig.alloc((size_t)n * 8));
+    RNLA_CUDA(Nm.alloc((size_t)n * n * 8)); RNLA_CUDA(y.alloc((size_t)n * 8));
+    RNLA_CUDA(work.alloc(jacobi_svd_work_doubles(nn) * 8)); RNLA_CUDA(info.alloc(8));
+    RNLA_TRY(dev_sketch_apply(kind, dist_or_width, seed, d, zeta, A, lda, m_local, n, sh.row_off, Ask.d(), d));   // :106-107
+    {
+        PhaseScope ph("precond:svd(A_sk)");
+        int64_t def = 0;
+        RNLA_TRY(dev_qr_blocked(Ask.d(), d, d, nn, R.d(), &def));
+        // A_sk = Q R, R = Ur diag(sigma) Vr^T  ->  the right singular vectors of A_sk are Vr                     :109-111
+        RNLA_CUDA(jacobi_svd(R.d(), n, nn, Ur.d(), n, sig.d(), Vr.d(), n, work.d(), info.as<int>(), c.stream, 1));
+        int hinfo[2];
+        RNLA_CUDA(cudaMemcpyAsync(hinfo, info.p, 8, cudaMemcpyDeviceToHost, c.stream));
+        RNLA_CUDA(cudaStreamSynchronize(c.stream));
+        if (hinfo[1]) return fail(RNLA_ERR_MATRIX_DECOMPOSITION, "lsrn: SVD of the sketch did not converge");
+        scale_inv_columns_kernel<<<blocks_for((int64_t)n * n), 256, 0, c.stream>>>(Vr.d(), n, nn, sig.d(), Nm.d(), n);   // :112-113
+        ++g_kernel_launches;
+        RNLA_CUDA(cudaGetLastError());
+    }
+    RNLA_CUDA(cudaMemsetAsync(y.p, 0, (size_t)n * 8, c.stream));                                              // y_hat = 0    :115
+    int64_t it = 0; int32_t conv = 0;
+    RNLA_TRY(cgls_operator(S, A, lda, m_local, n, b, Nm.d(), y.d(), epsilon, maxit, &it, &conv));             // :114-116
+    RNLA_TRY(S.small_gemv(Nm.d(), n, nn, 0, y.d(), x));                                                       // x = N y      :117
     RNLA_CUDA(cudaStreamSynchronize(c.stream));
     if (iters_out) *iters_out = it;
     if (converged_out) *converged_out = conv;

@@ -20,6 +20,9 @@ extern "C" {
     pub fn rnla_blendenpik_overdetermined(a: *const c_double, m: i64, n: i64, b: *const c_double, epsilon: c_double, l: i64,
                                           sampling_factor: c_double, kind: c_int, dist: c_int, zeta: c_int, x: *mut c_double,
                                           iterations: *mut i64, converged: *mut c_int) -> c_int;
+    pub fn rnla_lsrn_overdetermined(a: *const c_double, m: i64, n: i64, b: *const c_double, epsilon: c_double, l: i64,
+                                    sampling_factor: c_double, kind: c_int, dist: c_int, zeta: c_int, x: *mut c_double,
+                                    iterations: *mut i64, converged: *mut c_int) -> c_int;
 }
 
 pub fn last_message() -> String {

@@ -69,3 +69,18 @@ pub fn blendenpik_overdetermined_with(a: &DMatrix<f64>, b: &DMatrix<f64>, epsilo
     if converged != 0 { println!("CGLS converged after {} iterations", iters); } else { println!("CGLS failed to converged after {} iterations", l); }
     Ok(x)
 }
+
+/// Drop-in for `lsrn_overdetermined` (reference src/sketch_and_precondition.rs:82-119), end to end on the GPU
+/// (n <= 1024: size of the on-device SVD core).
+pub fn lsrn_overdetermined(a: &DMatrix<f64>, b: &DMatrix<f64>, epsilon: f64, l: usize, sampling_factor: f64) -> Result<DMatrix<f64>, Box<dyn Error>> {
+    validate(a, epsilon, l, sampling_factor)?;
+    let (m, n) = a.shape();
+    let mut x = DMatrix::<f64>::zeros(n, 1);
+    let (mut iters, mut converged) = (0i64, 0i32);
+    from_status(unsafe {
+        ffi::rnla_lsrn_overdetermined(a.as_ptr(), m as i64, n as i64, b.as_ptr(), epsilon, l as i64, sampling_factor,
+                                      0, 0, 0, x.as_mut_ptr(), &mut iters, &mut converged)
+    })?;
+    if converged != 0 { println!("CGLS converged after {} iterations", iters); } else { println!("CGLS failed to converged after {} iterations", l); }
+    Ok(x)
+}

@@ -91,3 +91,20 @@ def blendenpik_overdetermined(a, b, epsilon, l, sampling_factor, kind=SKETCH_DEN
     if info is not None:
         info["iterations"] = int(it.value); info["converged"] = bool(conv.value)
     return x
+
+
+def lsrn_overdetermined(a, b, epsilon, l, sampling_factor, kind=SKETCH_DENSE, zeta=8, width=0, info=None):
+    """`lsrn_overdetermined` end to end (reference :82-119): sketch, SVD of the sketch, N = V Sigma^-1, CGLS on A N in
+    operator form from y = 0, x = N y.  n <= 1024 (size of the on-device SVD core)."""
+    lib = _lib.load()
+    a = runtime.as_f(a)
+    b = runtime.as_f(b)
+    m, n = a.shape
+    x = np.empty((n, 1), dtype=np.float64, order="F")
+    it = C.c_int64(0); conv = C.c_int32(0)
+    dist = width if kind == SKETCH_SASO_BLOCK else runtime.GAUSSIAN
+    check(lib.rnla_lsrn_overdetermined(runtime.ptr(a), m, n, runtime.ptr(b), float(epsilon), int(l), float(sampling_factor),
+                                       kind, dist, zeta, runtime.ptr(x), C.byref(it), C.byref(conv)))
+    if info is not None:
+        info["iterations"] = int(it.value); info["converged"] = bool(conv.value)
+    return x

@@ -602,6 +602,31 @@ def test_blendenpik_end_to_end(rb, orc, kind, zeta, m, n, cond):
     assert np.linalg.norm(A.T @ (b - A @ x)) <= 1e-8 * np.linalg.norm(A.T @ b)
 
 
+@pytest.mark.parametrize("kind", [0, 2])
+@pytest.mark.parametrize("m,n,cond", [(6000, 40, 1e2), (9000, 300, 1e5)])
+def test_lsrn_end_to_end(rb, orc, kind, m, n, cond):
+    """src/sketch_and_precondition.rs:82-119: SVD-preconditioned CGLS from y = 0; same sketch on both sides"""
+    from randnla_b200 import sketch_and_precondition as sp
+    from randnla_b200.errors import InvalidParameters, InvalidDimensions
+    rng = np.random.default_rng(n + 1)
+    U, _ = np.linalg.qr(rng.standard_normal((m, n))); V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = np.asfortranarray((U * np.logspace(0, -np.log10(cond), n)) @ V.T)
+    xt = rng.uniform(-100, 100, (n, 1))
+    b = A @ xt + 1e-2 * rng.standard_normal((m, 1))
+    info = {}
+    x = sp.lsrn_overdetermined(A, b, 1e-10, 300, 4.0, kind=kind, info=info)
+    xo, ito, convo = orc.lsrn(A, b, 1e-10, 300, 4.0, kind=kind)
+    xl = np.linalg.lstsq(A, b, rcond=None)[0]
+    nrm = np.linalg.norm(xl)
+    assert info["converged"] and convo and abs(info["iterations"] - ito) <= 2 and info["iterations"] < 100
+    assert np.linalg.norm(x - xo) <= 1e-8 * nrm
+    assert np.linalg.norm(x - xl) <= 1e-7 * nrm * max(1.0, cond * 1e-5)
+    with pytest.raises(InvalidParameters):
+        sp.lsrn_overdetermined(A, b, 1e-6, 10, 0.5)
+    with pytest.raises(InvalidDimensions):
+        sp.lsrn_overdetermined(random_matrix(3000, 1100, seed=1), random_matrix(3000, 1, seed=2), 1e-6, 10, 2.0)
+
+
 def test_blendenpik_reference_errors(rb):
     """src/sketch_and_precondition.rs:229-290 test_blendenpik_overdetermined: Err for sampling_factor < 1, epsilon <= 0, l = 0,
     and for an underdetermined system"""

@@ -412,6 +412,9 @@ def test_cgls_and_blendenpik_restatement(orc):
     for kind in (0, 1, 2):
         xs, its, cvs = orc.blendenpik(A, bb, 1e-10, 200, 4.0, kind=kind)
         assert cvs and its < 60 and np.linalg.norm(xs - xl) <= 1e-8 * np.linalg.norm(xl)
+    for kind in (0, 2):                                      # src/sketch_and_precondition.rs:82-119
+        xs, its, cvs = orc.lsrn(A, bb, 1e-10, 300, 4.0, kind=kind)
+        assert cvs and its < 80 and np.linalg.norm(xs - xl) <= 1e-8 * np.linalg.norm(xl)
     for bad in ((1e-6, 10, 0.5), (0.0, 10, 2.0), (1e-6, 0, 2.0)):
         with pytest.raises(ValueError) as e:
             orc.blendenpik(A, bb, bad[0], bad[1], bad[2])
