@@ -64,6 +64,7 @@ extern "C" {
 
 // ------------------------------------------------------------------ RNG hooks
 rnla_status rnla_philox4x32_10(int64_t nblocks, const uint32_t* hctr, const uint32_t* hkey, uint32_t* hout) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     if (nblocks <= 0) return RNLA_OK;
     Ctx& c = ctx();
@@ -77,6 +78,7 @@ rnla_status rnla_philox4x32_10(int64_t nblocks, const uint32_t* hctr, const uint
     return RNLA_OK;
 }
 rnla_status rnla_threefry2x64_20(int64_t nblocks, const uint64_t* hctr, const uint64_t* hkey, uint64_t* hout) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     if (nblocks <= 0) return RNLA_OK;
     Ctx& c = ctx();
@@ -93,6 +95,7 @@ rnla_status rnla_threefry2x64_20(int64_t nblocks, const uint64_t* hctr, const ui
 // ------------------------------------------------------------------ sketch operators
 rnla_status rnla_sketch_fill_dev(int32_t generator, int32_t dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols,
                                  int64_t row_offset, double* d_out, int64_t ld) {
+    RNLA_API_GUARD;
     if (rows <= 0 || cols <= 0)   // src/sketch.rs:107-111
         return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
     if (dist < RNLA_GAUSSIAN || dist > RNLA_RADEMACHER) return fail(RNLA_ERR_INVALID_PARAMETERS, "unknown distribution");
@@ -114,6 +117,7 @@ rnla_status rnla_sketch_fill_dev(int32_t generator, int32_t dist, uint64_t seed,
 }
 rnla_status rnla_sketch_fill(int32_t generator, int32_t dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols,
                              int64_t row_offset, double* out, int64_t ld) {
+    RNLA_API_GUARD;
     if (rows <= 0 || cols <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
     if (ld < rows) return fail(RNLA_ERR_INVALID_DIMENSIONS, "leading dimension smaller than rows");
     RNLA_TRY(ensure_ctx());
@@ -125,12 +129,14 @@ rnla_status rnla_sketch_fill(int32_t generator, int32_t dist, uint64_t seed, uin
     return RNLA_OK;
 }
 rnla_status rnla_sketching_operator(int32_t dist, int64_t rows, int64_t cols, double* out) {
+    RNLA_API_GUARD;
     if (rows <= 0 || cols <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
     RNLA_TRY(ensure_ctx());
     return rnla_sketch_fill(RNLA_GEN_PHILOX, dist, ctx().opts.seed, 0, rows, cols, 0, out, rows);
 }
 
 rnla_status rnla_haar_sample(int64_t rows, int64_t cols, int32_t attr, double* out) {
+    RNLA_API_GUARD;
     // src/sketch.rs:45-85
     int64_t m, n;
     if (attr == RNLA_ROW) {
@@ -164,6 +170,7 @@ rnla_status rnla_haar_sample(int64_t rows, int64_t cols, int32_t attr, double* o
 
 // ------------------------------------------------------------------ helpers (host buffers)
 rnla_status rnla_orth(const double* X, int64_t rows, int64_t cols, double* Q, double* R, int64_t* qcols) {
+    RNLA_API_GUARD;
     if (rows <= 0 || cols <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
     RNLA_TRY(ensure_ctx());
     Ctx& c = ctx();
@@ -195,6 +202,7 @@ rnla_status rnla_orth(const double* X, int64_t rows, int64_t cols, double* Q, do
 }
 
 rnla_status rnla_stabilizer(const double* X, int64_t rows, int64_t cols, double* L, int64_t* lcols) {
+    RNLA_API_GUARD;
     if (rows <= 0 || cols <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
     RNLA_TRY(ensure_ctx());
     const int64_t mn = std::min(rows, cols);
@@ -213,6 +221,7 @@ static rnla_status check_range_args(int64_t m, int64_t n, int64_t k) {
 }
 
 rnla_status rnla_tsog1(const double* A, int64_t m, int64_t n, int64_t k, int32_t num_passes, int32_t passes_per_stab, double* S) {
+    RNLA_API_GUARD;
     RNLA_TRY(check_range_args(m, n, k));
     if (num_passes < 0 || passes_per_stab <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "num_passes must be >= 0 and passes_per_stab > 0");
     if (k > std::min(m, n)) return fail(RNLA_ERR_INVALID_DIMENSIONS, "tsog1: k must not exceed min(m, n)");
@@ -227,6 +236,7 @@ rnla_status rnla_tsog1(const double* A, int64_t m, int64_t n, int64_t k, int32_t
 }
 
 rnla_status rnla_rf1(const double* A, int64_t m, int64_t n, int64_t k, double* Q, int64_t* qcols) {
+    RNLA_API_GUARD;
     RNLA_TRY(check_range_args(m, n, k));
     RNLA_TRY(ensure_ctx());
     phases_reset();
@@ -242,6 +252,7 @@ rnla_status rnla_rf1(const double* A, int64_t m, int64_t n, int64_t k, double* Q
 }
 
 rnla_status rnla_qb1(const double* A, int64_t m, int64_t n, int64_t k, double epsilon, double* Q, double* B, int64_t* qcols) {
+    RNLA_API_GUARD;
     (void)epsilon;   // ignored, as in the reference (src/lora_helpers.rs:18-19)
     RNLA_TRY(check_range_args(m, n, k));
     RNLA_TRY(ensure_ctx());
@@ -263,6 +274,7 @@ rnla_status rnla_qb1(const double* A, int64_t m, int64_t n, int64_t k, double ep
 // ------------------------------------------------------------------ drivers (host buffers)
 rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, double epsilon, int64_t s,
                           double* U, double* S, double* Vt, int64_t* r_out) {
+    RNLA_API_GUARD;
     RNLA_TRY(validate_svd_like(k, epsilon, s));
     if (m <= 0 || n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
     RNLA_TRY(ensure_ctx());
@@ -325,6 +337,7 @@ rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, doub
 }
 
 rnla_status rnla_rand_evd1(const double* A, int64_t n, int64_t k, double epsilon, int64_t s, double* V, double* lambda, int64_t* r_out) {
+    RNLA_API_GUARD;
     RNLA_TRY(validate_svd_like(k, epsilon, s));
     if (n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
     RNLA_TRY(ensure_ctx());
@@ -343,6 +356,7 @@ rnla_status rnla_rand_evd1(const double* A, int64_t n, int64_t k, double epsilon
 }
 
 rnla_status rnla_rand_evd2(const double* A, int64_t n, int64_t k, int64_t s, double* V, double* lambda, int64_t* r_out) {
+    RNLA_API_GUARD;
     // src/lora_drivers.rs:169-173: only k is validated (s may be 0)
     if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, fmt("Rank k must be positive, current input is %lld", (long long)k));
     if (s < 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "Oversampling parameter s must be non-negative");
@@ -366,6 +380,7 @@ static const rnla_options& pick(const rnla_options* o) { return o ? *o : ctx().o
 
 rnla_status rnla_rand_svd_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t k, int64_t s,
                               const rnla_options* opt, double* dU, int64_t ldu, double* dSigma, double* dVt, int64_t ldvt, int64_t* r) {
+    RNLA_API_GUARD;
     RNLA_TRY(validate_svd_like(k, 1.0, s));
     RNLA_TRY(ensure_ctx());
     const rnla_options o = pick(opt);
@@ -373,6 +388,7 @@ rnla_status rnla_rand_svd_dev(const double* dA, int64_t lda, int64_t m_local, in
 }
 rnla_status rnla_rand_evd1_dev(const double* dA, int64_t lda, int64_t n, int64_t k, int64_t s, const rnla_options* opt,
                                double* dV, int64_t ldv, double* dLambda, int64_t* r) {
+    RNLA_API_GUARD;
     RNLA_TRY(validate_svd_like(k, 1.0, s));
     RNLA_TRY(ensure_ctx());
     const rnla_options o = pick(opt);
@@ -380,6 +396,7 @@ rnla_status rnla_rand_evd1_dev(const double* dA, int64_t lda, int64_t n, int64_t
 }
 rnla_status rnla_rand_evd2_dev(const double* dA, int64_t lda, int64_t n, int64_t k, int64_t s, const rnla_options* opt,
                                double* dV, int64_t ldv, double* dLambda, int64_t* r) {
+    RNLA_API_GUARD;
     if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, fmt("Rank k must be positive, current input is %lld", (long long)k));
     RNLA_TRY(ensure_ctx());
     const rnla_options o = pick(opt);
@@ -388,6 +405,7 @@ rnla_status rnla_rand_evd2_dev(const double* dA, int64_t lda, int64_t n, int64_t
 
 // ------------------------------------------------------------------ sketch step of sketch_and_precondition
 int64_t rnla_sketch_dim(int64_t m, int64_t n, double sampling_factor, int32_t rule) {
+    RNLA_API_GUARD;
     if (rule == 0) {
         // src/sketch_and_precondition.rs:49,105
         if (sampling_factor * (double)n > (double)m) return m;
@@ -402,12 +420,14 @@ int64_t rnla_sketch_dim(int64_t m, int64_t n, double sampling_factor, int32_t ru
 
 rnla_status rnla_sketch_apply_dev(int32_t kind, int32_t dist, uint64_t seed, int64_t d, int32_t zeta, const double* dA, int64_t lda,
                                   int64_t m_local, int64_t n, int64_t row_offset, double* dA_sk, int64_t ld_sk) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     return dev_sketch_apply(kind, dist, seed, d, zeta, dA, lda, m_local, n, row_offset, dA_sk, ld_sk);
 }
 
 rnla_status rnla_sketch_apply(int32_t kind, int32_t dist, uint64_t seed, int64_t d, int32_t zeta, const double* A, int64_t m, int64_t n,
                               const double* b, int64_t nrhs, double* A_sk, double* b_sk) {
+    RNLA_API_GUARD;
     if (m <= 0 || n <= 0 || d <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
     RNLA_TRY(ensure_ctx());
     DevBuf dA, dAsk, db, dbsk;
@@ -426,6 +446,7 @@ rnla_status rnla_sketch_apply(int32_t kind, int32_t dist, uint64_t seed, int64_t
 
 // ------------------------------------------------------------------ building blocks
 rnla_status rnla_gemm_nn_dev(const double* dA, int64_t lda, int64_t m, int64_t K, const double* dB, int64_t ldb, int64_t N, double* dC, int64_t ldc) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     return dev_gemm_nn(dA, lda, m, K, dB, ldb, N, dC, ldc);
 }
@@ -453,6 +474,7 @@ static rnla_status validate_lsq(int64_t m, int64_t n, double epsilon, int64_t l,
 rnla_status rnla_blendenpik_overdetermined_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db,
                                                double epsilon, int64_t l, double sampling_factor, int32_t kind, int32_t dist,
                                                int32_t zeta, double* dx, int64_t* iterations, int32_t* converged) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     ShardInfo sh;
     RNLA_TRY(shard_layout(m_local, &sh));
@@ -462,6 +484,7 @@ rnla_status rnla_blendenpik_overdetermined_dev(const double* dA, int64_t lda, in
 rnla_status rnla_blendenpik_overdetermined(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l,
                                            double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* x,
                                            int64_t* iterations, int32_t* converged) {
+    RNLA_API_GUARD;
     RNLA_TRY(validate_lsq(m, n, epsilon, l, sampling_factor));
     RNLA_TRY(ensure_ctx());
     DevBuf dA, db, dx;
@@ -474,12 +497,14 @@ rnla_status rnla_blendenpik_overdetermined(const double* A, int64_t m, int64_t n
 
 // ---- planning decisions, callable without a GPU (tests/test_host_logic.py) ---------------------------------------------
 void rnla_plan_gemm(int64_t m, int64_t n, int64_t N, int32_t sms, int32_t* out /* 4 */) {
+    RNLA_API_GUARD;
     int chunks = 0, tiles = 0; int64_t chunk_rows = 0;
     gemm_tn_plan_info(m, n, N, sms, &chunks, &chunk_rows, &tiles);
     out[0] = gemm_nn_ksplit(m, n, N, sms); out[1] = chunks; out[2] = (int32_t)chunk_rows; out[3] = tiles;
 }
 int32_t rnla_plan_saso_block(int64_t d, int32_t zeta, int32_t width, int64_t n, int64_t nchunks, int32_t sms, int32_t* shape /* 4 */,
                              int32_t* desc /* 4 per CTA */, int32_t cap, int32_t* nslots) {
+    RNLA_API_GUARD;
     int bpt = 0, cb = 0, parts = 0;
     if (!saso_block_shape(d, zeta, width, n, &bpt, &cb, &parts)) return -1;
     const int ncg = (int)((n + cb - 1) / cb);
@@ -494,6 +519,7 @@ int32_t rnla_plan_saso_block(int64_t d, int32_t zeta, int32_t width, int64_t n, 
 rnla_status rnla_lsrn_overdetermined_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db, double epsilon,
                                          int64_t l, double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* dx,
                                          int64_t* iterations, int32_t* converged) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     ShardInfo sh;
     RNLA_TRY(shard_layout(m_local, &sh));
@@ -503,6 +529,7 @@ rnla_status rnla_lsrn_overdetermined_dev(const double* dA, int64_t lda, int64_t 
 rnla_status rnla_lsrn_overdetermined(const double* A, int64_t m, int64_t n, const double* b, double epsilon, int64_t l,
                                      double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* x,
                                      int64_t* iterations, int32_t* converged) {
+    RNLA_API_GUARD;
     RNLA_TRY(validate_lsq(m, n, epsilon, l, sampling_factor));
     RNLA_TRY(ensure_ctx());
     DevBuf dA, db, dx;
@@ -514,27 +541,32 @@ rnla_status rnla_lsrn_overdetermined(const double* A, int64_t m, int64_t n, cons
 }
 
 rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int32_t trans, const double* dx, double* dy) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     return trans ? dev_gemv_t(dA, lda, m, n, dx, dy) : dev_gemv_n(dA, lda, m, n, dx, dy);
 }
 
 rnla_status rnla_sketch_gemm_dev(const double* dA, int64_t lda, int64_t m, int64_t K, int32_t dist, uint64_t seed, uint32_t stream,
                                  int64_t N, double* dC, int64_t ldc) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     return dev_sketch_gemm(dA, lda, m, K, dist, seed, stream, N, dC, ldc);
 }
 rnla_status rnla_gemm_tn_dev(const double* dA, int64_t lda, int64_t m, int64_t n, const double* dQ, int64_t ldq, int64_t N,
                              double* dZ, int64_t ldz, int32_t allreduce) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     return dev_gemm_tn(dA, lda, m, n, dQ, ldq, N, dZ, ldz, allreduce != 0);
 }
 rnla_status rnla_orth_dev(double* dX, int64_t ldx, int64_t rows_local, int64_t cols, int32_t sharded, double* dR, int64_t* deficient) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     ShardInfo sh{rows_local, 0, rows_local};
     if (sharded) RNLA_TRY(shard_layout(rows_local, &sh));
     return orth_inplace(dX, ldx, sh, (int)cols, sharded != 0, dR, deficient);
 }
 rnla_status rnla_small_svd_dev(const double* dM, int64_t ldm, int64_t p, double* dU, double* dSigma, double* dV) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     Ctx& c = ctx();
     if (p <= 0 || p > 1024) return fail(RNLA_ERR_INVALID_DIMENSIONS, "small_svd: 1 <= p <= 1024");
@@ -559,6 +591,7 @@ rnla_status rnla_small_svd_dev(const double* dM, int64_t ldm, int64_t p, double*
 int32_t rnla_last_jacobi_sweeps(void) { return g_last_jacobi_sweeps; }
 
 rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double* dW, double* dLambda) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     Ctx& c = ctx();
     if (p <= 0 || p > 1024) return fail(RNLA_ERR_INVALID_DIMENSIONS, "small_eigh: 1 <= p <= 1024");
@@ -574,6 +607,7 @@ rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double
 
 rnla_status rnla_generate_lowrank_dev(double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t row_offset, int64_t m_global,
                                       int64_t r0, const double* sigma_host, double eta, uint64_t seed) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     return dev_generate_lowrank(dA, lda, m_local, n, row_offset, m_global, r0, sigma_host, eta, seed);
 }

@@ -11,6 +11,8 @@ namespace rnla {
 static thread_local std::string t_err;
 static Ctx g_ctx;
 static std::mutex g_mu;
+static std::recursive_mutex g_api_mu;
+std::recursive_mutex& api_mutex() { return g_api_mu; }
 
 Ctx& ctx() { return g_ctx; }
 void set_error(const std::string& msg) { t_err = msg; }
@@ -162,10 +164,12 @@ int32_t rnla_version(void) { return 100; }
 const char* rnla_last_error_message(void) { return t_err.c_str(); }
 
 rnla_status rnla_init(int32_t device) {
+    RNLA_API_GUARD;
     std::lock_guard<std::mutex> lk(g_mu);
     return init_locked(device);
 }
 void rnla_shutdown(void) {
+    RNLA_API_GUARD;
     std::lock_guard<std::mutex> lk(g_mu);
     Ctx& c = g_ctx;
     if (!c.ready) return;
@@ -182,18 +186,21 @@ void rnla_shutdown(void) {
 }
 void* rnla_stream(void) { return ensure_ctx() == RNLA_OK ? (void*)g_ctx.stream : nullptr; }
 rnla_status rnla_set_stream(void* cuda_stream) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     RNLA_CUDA(cudaStreamSynchronize(g_ctx.stream));
     g_ctx.stream = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.own_stream;
     return RNLA_OK;
 }
 rnla_status rnla_synchronize(void) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     RNLA_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return RNLA_OK;
 }
 void rnla_default_options(rnla_options* opt) { if (opt) default_opts(opt); }
 rnla_status rnla_set_options(const rnla_options* opt) {
+    RNLA_API_GUARD;
     if (!opt) return fail(RNLA_ERR_INVALID_PARAMETERS, "rnla_set_options: null options");
     if (opt->mode != RNLA_MODE_INTENDED && opt->mode != RNLA_MODE_LITERAL)
         return fail(RNLA_ERR_INVALID_PARAMETERS, "rnla_set_options: unknown mode");
@@ -204,12 +211,14 @@ rnla_status rnla_set_options(const rnla_options* opt) {
     return RNLA_OK;
 }
 void rnla_get_options(rnla_options* opt) {
+    RNLA_API_GUARD;
     if (!opt) return;
     if (g_ctx.ready) *opt = g_ctx.opts; else default_opts(opt);
 }
 uint64_t rnla_kernel_launches(void) { return g_kernel_launches; }
 
 int32_t rnla_get_timings(const char** names, double* ms, int32_t cap) {
+    RNLA_API_GUARD;
     Ctx& c = g_ctx;
     if (!c.ready) return 0;
     cudaStreamSynchronize(c.stream);
@@ -226,6 +235,7 @@ int32_t rnla_get_timings(const char** names, double* ms, int32_t cap) {
 }
 
 rnla_status rnla_comm_unique_id(uint8_t id[128]) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     RNLA_TRY(load_nccl());
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
@@ -236,6 +246,7 @@ rnla_status rnla_comm_unique_id(uint8_t id[128]) {
     return RNLA_OK;
 }
 rnla_status rnla_comm_init(int32_t nranks, int32_t rank, const uint8_t id[128]) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(RNLA_ERR_INVALID_PARAMETERS, "rnla_comm_init: bad rank/nranks");
     Ctx& c = g_ctx;
@@ -251,6 +262,7 @@ rnla_status rnla_comm_init(int32_t nranks, int32_t rank, const uint8_t id[128]) 
     return RNLA_OK;
 }
 rnla_status rnla_comm_destroy(void) {
+    RNLA_API_GUARD;
     Ctx& c = g_ctx;
     if (c.comm) {
         cudaStreamSynchronize(c.stream);
@@ -264,23 +276,27 @@ int32_t rnla_comm_size(void) { return g_ctx.nranks; }
 int32_t rnla_comm_rank(void) { return g_ctx.rank; }
 
 rnla_status rnla_malloc(void** dptr, size_t bytes) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     RNLA_CUDA(cudaMalloc(dptr, bytes ? bytes : 8));
     return RNLA_OK;
 }
 rnla_status rnla_free(void* dptr) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     RNLA_CUDA(cudaStreamSynchronize(g_ctx.stream));
     RNLA_CUDA(cudaFree(dptr));
     return RNLA_OK;
 }
 rnla_status rnla_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     RNLA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
     RNLA_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return RNLA_OK;
 }
 rnla_status rnla_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+    RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
     RNLA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
     RNLA_CUDA(cudaStreamSynchronize(g_ctx.stream));

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -33,6 +34,11 @@ struct Ctx {
 };
 
 Ctx& ctx();
+// Every extern "C" entry point holds this lock for its whole duration: the context (stream, phase timings, workspace pool,
+// one-shot hooks) is process-global, so calls from several host threads are serialised.  Recursive: some entry points are
+// implemented on top of others.
+std::recursive_mutex& api_mutex();
+#define RNLA_API_GUARD std::lock_guard<std::recursive_mutex> rnla_api_guard_(::rnla::api_mutex())
 void set_error(const std::string& msg);
 rnla_status fail(rnla_status code, const std::string& msg);
 rnla_status cuda_fail(cudaError_t e, const char* what, const char* file, int line);

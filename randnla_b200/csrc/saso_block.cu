@@ -29,7 +29,7 @@
 // engine) into a ring of stages with one `full` mbarrier each; the last warp to finish a chunk refills its stage (a
 // dedicated producer warp would cap the kernel at 96 registers per thread); all 512 threads each own BPT blocks (BPT * w * CB f64 accumulators
 // in registers), walk their slots of the chunk, read A(x, c) from shared memory and apply the w signed updates as DFMAs.
-// HBM traffic: A exactly once (8 m n bytes) + d n 8 written; the slot tables (4 g bytes per row) are L2-resident.
+// HBM traffic: A exactly once (8 m n bytes) + d n 8 written; the slot tables (2 g bytes per row) are L2-resident.
 #include "drivers.cuh"
 #include "gemm.cuh"
 #include "panel.cuh"
