@@ -200,6 +200,70 @@ rnla_status rnla_lsrn_overdetermined_dev(const double* dA, int64_t lda, int64_t 
                                          int64_t l, double sampling_factor, int32_t kind, int32_t dist, int32_t zeta, double* dx,
                                          int64_t* iterations, int32_t* converged);
 
+/* ==== rows after the hot path: the callers and neighbours of the sketch ==================== */
+/* index vectors are int64 (the reference's Vec<usize>) */
+
+/* qrcp (reference src/pivot_decompositions.rs:105-180; steps = min(m, n)) and economic_qrcp(a, k) (:196-269; steps = k):
+ * Householder QR with column pivoting on exactly recomputed trailing column norms, first maximum wins.  R: m x n, the
+ * reference's work matrix `r` after `steps` reflections (`r_eco` = its first k rows); perm: n; Q (optional, NULL / qcols = 0
+ * to skip): the first qcols columns of the accumulated reflectors (qcols = k: `q_eco`; qcols = m: the full `q`).
+ * Errors (the reference asserts): "k must be positive", "k must be <= min(m,n)" -> INVALID_PARAMETERS. */
+rnla_status rnla_qrcp(const double* A, int64_t m, int64_t n, int64_t steps, int64_t qcols, double* Q, double* R, int64_t* perm);
+/* in place on the device: dR holds A on entry (m x n, ldr), R on exit */
+rnla_status rnla_qrcp_dev(double* dR, int64_t ldr, int64_t m, int64_t n, int64_t steps, int64_t* dperm, double* dQ, int64_t ldq,
+                          int64_t qcols);
+
+/* sap_chol_qrcp(a, d) (reference src/cqrrpt.rs:27-58; CQRRPT): sketch (d x m operator, kind/dist/zeta as in
+ * rnla_sketch_apply; the reference's own is DENSE GAUSSIAN), qrcp of the sketch, numerical rank k = #{|R_ii| > 1e-10},
+ * A_pre = A[:, J[:k]] R_k^-1, Cholesky QR of A_pre, R = R_pre R_sk[:k, :].  Q: m x n buffer, first *k columns valid (ld m);
+ * R: n x n buffer, holds the k x n factor packed with ld = *k; J: n.  Errors: "d must satisfy n <= d << m" (the reference's
+ * assert :29) -> INVALID_PARAMETERS; failed Cholesky (:51) -> MATRIX_DECOMPOSITION. */
+rnla_status rnla_sap_chol_qrcp(const double* A, int64_t m, int64_t n, int64_t d, int32_t kind, int32_t dist, int32_t zeta,
+                               double* Q, double* R, int64_t* J, int64_t* k);
+/* device buffers: dQ m x n (ldq), dR n x n (ldr; k x n valid, NOT repacked), dJ n */
+rnla_status rnla_sap_chol_qrcp_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int64_t d, int32_t kind, int32_t dist,
+                                   int32_t zeta, double* dQ, int64_t ldq, double* dR, int64_t ldr, int64_t* dJ, int64_t* k);
+
+/* sketched_least_squares_qr / _svd (reference src/sketch_and_solve.rs:24-33, :54-66): sketch with rows/4 rows, QR (or SVD)
+ * of the sketch, x = R^-1 Q^T b_sk with `solve_upper_triangular_system`'s rule for zero pivots (src/solvers.rs:22-41), or
+ * x = V Sigma^-1 U^T b_sk (`solve_diagonal_system` :57-69).  x: n.  The SVD variant needs n <= 1024 on the device.
+ * INVALID_DIMENSIONS when rows/4 < n (the reference then indexes out of bounds). */
+rnla_status rnla_sketched_least_squares_qr(const double* A, int64_t m, int64_t n, const double* b, int32_t kind, int32_t dist,
+                                           int32_t zeta, double* x);
+rnla_status rnla_sketched_least_squares_svd(const double* A, int64_t m, int64_t n, const double* b, int32_t kind, int32_t dist,
+                                            int32_t zeta, double* x);
+rnla_status rnla_sketched_least_squares_dev(int32_t which /* 0 QR, 1 SVD */, const double* dA, int64_t lda, int64_t m, int64_t n,
+                                            const double* db, int32_t kind, int32_t dist, int32_t zeta, double* dx);
+
+/* interpolative decompositions (reference src/id.rs).  attr: RNLA_COLUMN  Y ~ Y[:, J] X, X k x w;  RNLA_ROW  Y ~ X Y[J, :],
+ * X l x k.  J: k.  Errors: "k must be positive)", "k must be <= min(l,w)" (asserts :278-279) -> INVALID_PARAMETERS; a singular
+ * R1 (the reference unwraps :290) -> SINGULAR_MATRIX. */
+rnla_status rnla_osid_qrcp(const double* Y, int64_t l, int64_t w, int64_t k, int32_t attr, double* X, int64_t* J);        /* :272-318 */
+/* osid_randomised (:217-249): Column sketches with a k x m Gaussian; Row multiplies by tsog1(a, k, 2, 1)^T, which conforms
+ * only when a has k columns (INVALID_DIMENSIONS otherwise), as it is used by two_sided_id_randomised (:99) */
+rnla_status rnla_osid_randomised(const double* A, int64_t m, int64_t n, int64_t k, int32_t attr, double* X, int64_t* J);
+rnla_status rnla_osid_randomised_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int64_t k, int32_t attr,
+                                     const rnla_options* opt, double* dX, int64_t ldx, int64_t* dJ);
+/* two_sided_id (:118-129, randomised = 0) / two_sided_id_randomised (:94-101): A ~ Z A[I, J] X; Z m x k, I k, J k, X k x n */
+rnla_status rnla_two_sided_id(const double* A, int64_t m, int64_t n, int64_t k, int32_t randomised, double* Z, int64_t* I, int64_t* J,
+                              double* X);
+/* cur (:34-71, randomised = 0) / cur_randomised (:154-193): A ~ A[:, J] U A[I, :]; J k, U k x k, I k.  k <= 1024 on the device */
+rnla_status rnla_cur(const double* A, int64_t m, int64_t n, int64_t k, int32_t randomised, int64_t* J, double* U, int64_t* I);
+rnla_status rnla_cur_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int64_t k, int32_t randomised, const rnla_options* opt,
+                         int64_t* dJ, double* dU, int64_t ldu, int64_t* dI);
+
+/* sketch_saddle_point_precondition (reference src/sketch_and_precondition.rs:150-216), dense Gaussian operator (the
+ * reference's): SVD of the sketch, M = V (Sigma^2 + mu)^-1/2 (mu > 0) or V Sigma^-1, b_mod = b - S^T U diag(.) V^T c,
+ * z0 = U^T S b_mod, CGLS on A M in operator form, x = M z, y = b - A x.  c may be NULL (`c.is_empty()` :195).  x: n, y: m.
+ * Validation as blendenpik (:152-171).  n <= 1024 on the device; with mu = 0 a rank-deficient sketch is INVALID_DIMENSIONS
+ * (the reference's shapes do not conform at :211). */
+rnla_status rnla_sketch_saddle_point_precondition(const double* A, int64_t m, int64_t n, const double* b, const double* c, double mu,
+                                                  double epsilon, int64_t l, double sampling_factor, double* x, double* y,
+                                                  int64_t* iterations, int32_t* converged);
+rnla_status rnla_sketch_saddle_point_precondition_dev(const double* dA, int64_t lda, int64_t m, int64_t n, const double* db,
+                                                      const double* dc, double mu, double epsilon, int64_t l, double sampling_factor,
+                                                      double* dx, double* dy, int64_t* iterations, int32_t* converged);
+
 /* ---- building blocks on device buffers (tests, benches, host mirrors) ---------------------------- */
 /* y (m) = A x (trans = 0) or y (n) = A^T x (trans != 0, all-reduced over the communicator): the two streaming kernels of CGLS */
 rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int32_t trans, const double* dx, double* dy);

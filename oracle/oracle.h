@@ -75,6 +75,25 @@ int orc_lsrn(const double* A, int64_t m, int64_t n, const double* b, double epsi
 void orc_sketch_apply_saso_block(uint64_t seed, int64_t d, int zeta, int w, const double* A, int64_t m, int64_t n,
                                  int64_t row_off, double* A_sk);
 
+/* ---- next rows, oracle_next.c ------------------------------------------------ */
+/* src/pivot_decompositions.rs:105-180 (steps = min(m,n)) / :196-269 (steps = k).  R m x n, Q m x m or NULL, perm n */
+void orc_qrcp_steps(const double* A, int64_t m, int64_t n, int64_t steps, double* R, double* Q, int64_t* perm);
+/* src/cqrrpt.rs:27-58 */
+int orc_sap_chol_qrcp(const double* A, int64_t m, int64_t n, int64_t d, int kind, int dist_or_width, int zeta, uint64_t seed,
+                      double* Q, double* R, int64_t* J, int64_t* k_out);
+/* src/sketch_and_solve.rs:24-33 (which 0, QR) / :54-66 (which 1, SVD) */
+int orc_sketched_least_squares(int which, const double* A, int64_t m, int64_t n, const double* b, int kind, int dist_or_width,
+                               int zeta, uint64_t seed, double* x);
+/* src/id.rs */
+int orc_osid_qrcp(const double* Y, int64_t l, int64_t w, int64_t k, int attr, double* X, int64_t* J);
+int orc_osid_randomised(const double* A, int64_t m, int64_t n, int64_t k, int attr, const orc_opts* o, double* X, int64_t* J);
+int orc_two_sided_id(int randomised, const double* A, int64_t m, int64_t n, int64_t k, const orc_opts* o,
+                     double* Z, int64_t* I, int64_t* J, double* X);
+int orc_cur(int randomised, const double* A, int64_t m, int64_t n, int64_t k, const orc_opts* o, int64_t* J, double* U, int64_t* I);
+/* src/sketch_and_precondition.rs:150-216 */
+int orc_saddle_point(const double* A, int64_t m, int64_t n, const double* b, const double* c, double mu, double epsilon, int64_t l,
+                     double sampling_factor, int dist, uint64_t seed, double* x, double* y, int64_t* iters_out, int* converged_out);
+
 void orc_set_threads(int nthreads);
 int orc_get_threads(void);
 

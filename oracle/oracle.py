@@ -297,6 +297,111 @@ def lsrn(A, b, epsilon, l, sampling_factor, kind=0, dist_or_width=0, zeta=8, see
     return x, int(it.value), bool(conv.value)
 
 
+# ---- next rows: oracle_next.c ---------------------------------------------------
+def _ivec(n):
+    return np.zeros(max(int(n), 1), dtype=np.int64)
+
+
+def qrcp(A, steps=None, want_q=True):
+    """src/pivot_decompositions.rs:105-180 (steps None = min(m, n)) / economic_qrcp :196-269 (steps = k)
+    -> (Q m x m or None, R m x n work matrix, perm)"""
+    A = F(A); m, n = A.shape
+    steps = min(m, n) if steps is None else int(steps)
+    R = np.empty((m, n), order="F"); Q = np.empty((m, m), order="F") if want_q else None
+    perm = _ivec(n)
+    load().orc_qrcp_steps(p(A), i64(m), i64(n), i64(steps), p(R), p(Q) if want_q else None, p(perm))
+    return Q, R, perm[:n]
+
+
+def economic_qrcp(A, k):
+    Q, R, perm = qrcp(A, k, True)
+    return Q[:, :k].copy(order="F"), R[:k, :].copy(order="F"), perm
+
+
+def sap_chol_qrcp(A, d, kind=0, dist_or_width=0, zeta=8, seed=0):
+    """src/cqrrpt.rs:27-58 -> (Q m x k, R k x n, J)"""
+    A = F(A); m, n = A.shape
+    Q = np.zeros((m, n), order="F"); R = np.zeros(n * n); J = _ivec(n); k = i64(0)
+    rc = load().orc_sap_chol_qrcp(p(A), i64(m), i64(n), i64(d), C.c_int(kind), C.c_int(dist_or_width), C.c_int(zeta), u64(seed),
+                                  p(Q), p(R), p(J), C.byref(k))
+    if rc:
+        raise ValueError(rc)
+    k = int(k.value)
+    return Q[:, :k].copy(order="F"), R[:k * n].reshape((k, n), order="F").copy(order="F"), J[:n]
+
+
+def sketched_least_squares(which, A, b, kind=0, dist_or_width=0, zeta=8, seed=0):
+    """src/sketch_and_solve.rs: which 0 = QR (:24-33), 1 = SVD (:54-66)"""
+    A = F(A); m, n = A.shape
+    b = F(np.asarray(b, dtype=np.float64).reshape(-1, 1))
+    x = np.zeros((n, 1), order="F")
+    rc = load().orc_sketched_least_squares(C.c_int(which), p(A), i64(m), i64(n), p(b), C.c_int(kind), C.c_int(dist_or_width),
+                                           C.c_int(zeta), u64(seed), p(x))
+    if rc:
+        raise ValueError(rc)
+    return x
+
+
+ROW, COLUMN = 0, 1
+
+
+def osid_qrcp(Y, k, attr):
+    """src/id.rs:272-318 -> (X, J)"""
+    Y = F(Y); l, w = Y.shape
+    X = np.zeros((k, w) if attr == COLUMN else (l, k), order="F"); J = _ivec(k)
+    rc = load().orc_osid_qrcp(p(Y), i64(l), i64(w), i64(k), C.c_int(attr), p(X), p(J))
+    if rc:
+        raise ValueError(rc)
+    return X, J[:k]
+
+
+def osid_randomised(A, k, attr, opts=None):
+    """src/id.rs:217-249 -> (X, J)"""
+    A = F(A); m, n = A.shape
+    o = opts if opts is not None else make_opts()
+    X = np.zeros((k, n) if attr == COLUMN else (m, k), order="F"); J = _ivec(k)
+    rc = load().orc_osid_randomised(p(A), i64(m), i64(n), i64(k), C.c_int(attr), C.byref(o), p(X), p(J))
+    if rc:
+        raise ValueError(rc)
+    return X, J[:k]
+
+
+def two_sided_id(A, k, randomised=False, opts=None):
+    """src/id.rs:118-129 / :94-101 -> (Z, I, J, X)"""
+    A = F(A); m, n = A.shape
+    o = opts if opts is not None else make_opts()
+    Z = np.zeros((m, k), order="F"); X = np.zeros((k, n), order="F"); I = _ivec(k); J = _ivec(k)
+    rc = load().orc_two_sided_id(C.c_int(1 if randomised else 0), p(A), i64(m), i64(n), i64(k), C.byref(o), p(Z), p(I), p(J), p(X))
+    if rc:
+        raise ValueError(rc)
+    return Z, I[:k], J[:k], X
+
+
+def cur(A, k, randomised=False, opts=None):
+    """src/id.rs:34-71 / :154-193 -> (J, U, I)"""
+    A = F(A); m, n = A.shape
+    o = opts if opts is not None else make_opts()
+    U = np.zeros((k, k), order="F"); I = _ivec(k); J = _ivec(k)
+    rc = load().orc_cur(C.c_int(1 if randomised else 0), p(A), i64(m), i64(n), i64(k), C.byref(o), p(J), p(U), p(I))
+    if rc:
+        raise ValueError(rc)
+    return J[:k], U, I[:k]
+
+
+def saddle_point(A, b, c, mu, epsilon, l, sampling_factor, dist=0, seed=0):
+    """src/sketch_and_precondition.rs:150-216 -> (x, y, iterations, converged)"""
+    A = F(A); m, n = A.shape
+    b = F(np.asarray(b, dtype=np.float64).reshape(-1, 1))
+    cc = None if c is None or np.size(c) == 0 else F(np.asarray(c, dtype=np.float64).reshape(-1, 1))
+    x = np.zeros((n, 1), order="F"); y = np.zeros((m, 1), order="F")
+    it = i64(0); conv = C.c_int(0)
+    rc = load().orc_saddle_point(p(A), i64(m), i64(n), p(b), p(cc) if cc is not None else None, C.c_double(mu), C.c_double(epsilon),
+                                 i64(l), C.c_double(sampling_factor), C.c_int(dist), u64(seed), p(x), p(y), C.byref(it), C.byref(conv))
+    if rc:
+        raise ValueError(rc)
+    return x, y, int(it.value), bool(conv.value)
+
+
 def set_threads(n):
     load().orc_set_threads(C.c_int(n))
 

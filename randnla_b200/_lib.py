@@ -71,6 +71,21 @@ SIGNATURES = {
     "rnla_gemv_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, P]),
     "rnla_blendenpik_overdetermined": (c_i32, [P, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
     "rnla_blendenpik_overdetermined_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
+    "rnla_qrcp": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, P, P, P]),
+    "rnla_qrcp_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, P, P, c_i64, c_i64]),
+    "rnla_sap_chol_qrcp": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, P, P, P, C.POINTER(c_i64)]),
+    "rnla_sap_chol_qrcp_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, P, c_i64, P, c_i64, P, C.POINTER(c_i64)]),
+    "rnla_sketched_least_squares_qr": (c_i32, [P, c_i64, c_i64, P, c_i32, c_i32, c_i32, P]),
+    "rnla_sketched_least_squares_svd": (c_i32, [P, c_i64, c_i64, P, c_i32, c_i32, c_i32, P]),
+    "rnla_sketched_least_squares_dev": (c_i32, [c_i32, P, c_i64, c_i64, c_i64, P, c_i32, c_i32, c_i32, P]),
+    "rnla_osid_qrcp": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, P]),
+    "rnla_osid_randomised": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, P]),
+    "rnla_osid_randomised_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i32, C.POINTER(Options), P, c_i64, P]),
+    "rnla_two_sided_id": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, P, P, P]),
+    "rnla_cur": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, P, P]),
+    "rnla_cur_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i32, C.POINTER(Options), P, P, c_i64, P]),
+    "rnla_sketch_saddle_point_precondition": (c_i32, [P, c_i64, c_i64, P, P, c_f64, c_f64, c_i64, c_f64, P, P, P, P]),
+    "rnla_sketch_saddle_point_precondition_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, P, c_f64, c_f64, c_i64, c_f64, P, P, P, P]),
     "rnla_small_eigh_dev": (c_i32, [P, c_i64, c_i64, P, P]),
     "rnla_generate_lowrank_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, P, c_f64, c_u64]),
     "rnla_measure_roofs": (c_i32, [C.POINTER(c_f64), C.POINTER(c_f64), C.c_size_t]),

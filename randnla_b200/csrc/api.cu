@@ -613,3 +613,193 @@ rnla_status rnla_generate_lowrank_dev(double* dA, int64_t lda, int64_t m_local, 
 }
 
 }  // extern "C"
+
+// ================================================================================================================
+// SURVEY.md section 8(f) rows 2-4 and the saddle-point driver: pivoted QR, CQRRPT, sketch-and-solve, ID / CUR
+// ================================================================================================================
+static rnla_status d2h_idx(int64_t* host, const int64_t* dev, size_t count) {
+    if (count) RNLA_CUDA(cudaMemcpyAsync(host, dev, count * 8, cudaMemcpyDeviceToHost, ctx().stream));
+    RNLA_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RNLA_OK;
+}
+
+rnla_status rnla_qrcp_dev(double* dR, int64_t ldr, int64_t m, int64_t n, int64_t steps, int64_t* dperm, double* dQ, int64_t ldq,
+                          int64_t qcols) {
+    RNLA_API_GUARD;
+    RNLA_TRY(ensure_ctx());
+    if (m <= 0 || n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    if (steps <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be positive");                          // pivot_decompositions.rs:201
+    if (steps > std::min(m, n)) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be <= min(m,n)");            // :200
+    if (qcols < 0 || qcols > m) return fail(RNLA_ERR_INVALID_DIMENSIONS, "qrcp: 0 <= qcols <= m");
+    phases_reset();
+    RNLA_TRY(dev_qrcp(dR, ldr, m, n, steps, dperm, qcols ? dQ : nullptr, ldq, qcols));
+    RNLA_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RNLA_OK;
+}
+rnla_status rnla_qrcp(const double* A, int64_t m, int64_t n, int64_t steps, int64_t qcols, double* Q, double* R, int64_t* perm) {
+    RNLA_API_GUARD;
+    RNLA_TRY(ensure_ctx());
+    if (m <= 0 || n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    DevBuf dR, dQ, dp;
+    RNLA_TRY(h2d(dR, A, (size_t)m * n));
+    RNLA_CUDA(dp.alloc((size_t)n * 8));
+    const bool wantq = Q != nullptr && qcols > 0;
+    if (wantq) RNLA_CUDA(dQ.alloc((size_t)m * qcols * 8));
+    RNLA_TRY(rnla_qrcp_dev(dR.d(), m, m, n, steps, dp.as<int64_t>(), wantq ? dQ.d() : nullptr, m, wantq ? qcols : 0));
+    if (wantq) RNLA_TRY(d2h(Q, dQ.d(), (size_t)m * qcols));
+    RNLA_TRY(d2h(R, dR.d(), (size_t)m * n));
+    return d2h_idx(perm, dp.as<int64_t>(), (size_t)n);
+}
+
+rnla_status rnla_sap_chol_qrcp_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int64_t d, int32_t kind, int32_t dist,
+                                   int32_t zeta, double* dQ, int64_t ldq, double* dR, int64_t ldr, int64_t* dJ, int64_t* k) {
+    RNLA_API_GUARD;
+    RNLA_TRY(ensure_ctx());
+    int64_t kk = 0;
+    RNLA_TRY(dev_sap_chol_qrcp(dA, lda, m, n, d, kind, dist, zeta, ctx().opts.seed, dQ, ldq, dR, ldr, dJ, &kk));
+    if (k) *k = kk;
+    return RNLA_OK;
+}
+rnla_status rnla_sap_chol_qrcp(const double* A, int64_t m, int64_t n, int64_t d, int32_t kind, int32_t dist, int32_t zeta,
+                               double* Q, double* R, int64_t* J, int64_t* k) {
+    RNLA_API_GUARD;
+    if (!(n <= d && d <= m) || n <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "d must satisfy n \xe2\x89\xa4 d \xe2\x89\xaa m");   // cqrrpt.rs:29
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, dQ, dR, dJ;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_CUDA(dQ.alloc((size_t)m * n * 8)); RNLA_CUDA(dR.alloc((size_t)n * n * 8)); RNLA_CUDA(dJ.alloc((size_t)n * 8));
+    int64_t kk = 0;
+    RNLA_TRY(dev_sap_chol_qrcp(dA.d(), m, m, n, d, kind, dist, zeta, ctx().opts.seed, dQ.d(), m, dR.d(), n, dJ.as<int64_t>(), &kk));
+    if (k) *k = kk;
+    RNLA_TRY(d2h(Q, dQ.d(), (size_t)m * kk));
+    if (kk) RNLA_CUDA(cudaMemcpy2DAsync(R, (size_t)kk * 8, dR.p, (size_t)n * 8, (size_t)kk * 8, (size_t)n, cudaMemcpyDeviceToHost, ctx().stream));
+    return d2h_idx(J, dJ.as<int64_t>(), (size_t)n);
+}
+
+rnla_status rnla_sketched_least_squares_dev(int32_t which, const double* dA, int64_t lda, int64_t m, int64_t n, const double* db,
+                                            int32_t kind, int32_t dist, int32_t zeta, double* dx) {
+    RNLA_API_GUARD;
+    RNLA_TRY(ensure_ctx());
+    if (which != 0 && which != 1) return fail(RNLA_ERR_INVALID_PARAMETERS, "sketched_least_squares: which = 0 (QR) or 1 (SVD)");
+    return dev_sketched_least_squares(which, dA, lda, m, n, db, kind, dist, zeta, ctx().opts.seed, dx);
+}
+static rnla_status sketched_ls_host(int which, const double* A, int64_t m, int64_t n, const double* b, int32_t kind, int32_t dist,
+                                    int32_t zeta, double* x) {
+    RNLA_TRY(ensure_ctx());
+    if (m <= 0 || n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "Rows and columns must be greater than 0");
+    DevBuf dA, db, dx;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_TRY(h2d(db, b, (size_t)m));
+    RNLA_CUDA(dx.alloc((size_t)n * 8));
+    RNLA_TRY(dev_sketched_least_squares(which, dA.d(), m, m, n, db.d(), kind, dist, zeta, ctx().opts.seed, dx.d()));
+    return d2h(x, dx.d(), (size_t)n);
+}
+rnla_status rnla_sketched_least_squares_qr(const double* A, int64_t m, int64_t n, const double* b, int32_t kind, int32_t dist,
+                                           int32_t zeta, double* x) {
+    RNLA_API_GUARD;
+    return sketched_ls_host(0, A, m, n, b, kind, dist, zeta, x);
+}
+rnla_status rnla_sketched_least_squares_svd(const double* A, int64_t m, int64_t n, const double* b, int32_t kind, int32_t dist,
+                                            int32_t zeta, double* x) {
+    RNLA_API_GUARD;
+    return sketched_ls_host(1, A, m, n, b, kind, dist, zeta, x);
+}
+
+rnla_status rnla_osid_qrcp(const double* Y, int64_t l, int64_t w, int64_t k, int32_t attr, double* X, int64_t* J) {
+    RNLA_API_GUARD;
+    if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be positive)");                              // id.rs:278
+    if (k > std::min(l, w)) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be <= min(l,w)");                // id.rs:279
+    RNLA_TRY(ensure_ctx());
+    phases_reset();
+    DevBuf dY, dX, dJ;
+    RNLA_TRY(h2d(dY, Y, (size_t)l * w));
+    const bool col = attr == RNLA_COLUMN;
+    const int64_t xr = col ? k : l, xc = col ? w : k;
+    RNLA_CUDA(dX.alloc((size_t)xr * xc * 8)); RNLA_CUDA(dJ.alloc((size_t)k * 8));
+    RNLA_TRY(dev_osid_qrcp(dY.d(), l, l, w, k, attr, dX.d(), xr, dJ.as<int64_t>()));
+    RNLA_TRY(d2h(X, dX.d(), (size_t)xr * xc));
+    return d2h_idx(J, dJ.as<int64_t>(), (size_t)k);
+}
+rnla_status rnla_osid_randomised_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int64_t k, int32_t attr,
+                                     const rnla_options* opt, double* dX, int64_t ldx, int64_t* dJ) {
+    RNLA_API_GUARD;
+    RNLA_TRY(ensure_ctx());
+    phases_reset();
+    RNLA_TRY(dev_osid_randomised(dA, lda, m, n, k, attr, opt ? *opt : ctx().opts, dX, ldx, dJ));
+    RNLA_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RNLA_OK;
+}
+rnla_status rnla_osid_randomised(const double* A, int64_t m, int64_t n, int64_t k, int32_t attr, double* X, int64_t* J) {
+    RNLA_API_GUARD;
+    if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be positive)");                              // id.rs:223
+    if (k > std::min(m, n)) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be <= min(l,w)");                // id.rs:224
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, dX, dJ;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    const bool col = attr == RNLA_COLUMN;
+    const int64_t xr = col ? k : m, xc = col ? n : k;
+    RNLA_CUDA(dX.alloc((size_t)xr * xc * 8)); RNLA_CUDA(dJ.alloc((size_t)k * 8));
+    RNLA_TRY(rnla_osid_randomised_dev(dA.d(), m, m, n, k, attr, nullptr, dX.d(), xr, dJ.as<int64_t>()));
+    RNLA_TRY(d2h(X, dX.d(), (size_t)xr * xc));
+    return d2h_idx(J, dJ.as<int64_t>(), (size_t)k);
+}
+rnla_status rnla_two_sided_id(const double* A, int64_t m, int64_t n, int64_t k, int32_t randomised, double* Z, int64_t* I, int64_t* J,
+                              double* X) {
+    RNLA_API_GUARD;
+    if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be positive)");
+    if (k > std::min(m, n)) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be <= min(l,w)");
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, dZ, dX, dI, dJ;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_CUDA(dZ.alloc((size_t)m * k * 8)); RNLA_CUDA(dX.alloc((size_t)k * n * 8));
+    RNLA_CUDA(dI.alloc((size_t)k * 8)); RNLA_CUDA(dJ.alloc((size_t)k * 8));
+    RNLA_TRY(dev_two_sided_id(randomised, dA.d(), m, m, n, k, ctx().opts, dZ.d(), m, dI.as<int64_t>(), dJ.as<int64_t>(), dX.d(), k));
+    RNLA_TRY(d2h(Z, dZ.d(), (size_t)m * k));
+    RNLA_TRY(d2h(X, dX.d(), (size_t)k * n));
+    RNLA_TRY(d2h_idx(I, dI.as<int64_t>(), (size_t)k));
+    return d2h_idx(J, dJ.as<int64_t>(), (size_t)k);
+}
+rnla_status rnla_cur_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int64_t k, int32_t randomised, const rnla_options* opt,
+                         int64_t* dJ, double* dU, int64_t ldu, int64_t* dI) {
+    RNLA_API_GUARD;
+    RNLA_TRY(ensure_ctx());
+    return dev_cur(randomised, dA, lda, m, n, k, opt ? *opt : ctx().opts, dJ, dU, ldu, dI);
+}
+rnla_status rnla_cur(const double* A, int64_t m, int64_t n, int64_t k, int32_t randomised, int64_t* J, double* U, int64_t* I) {
+    RNLA_API_GUARD;
+    if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be positive)");
+    if (k > std::min(m, n)) return fail(RNLA_ERR_INVALID_PARAMETERS, "k must be <= min(l,w)");
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, dU, dI, dJ;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_CUDA(dU.alloc((size_t)k * k * 8)); RNLA_CUDA(dI.alloc((size_t)k * 8)); RNLA_CUDA(dJ.alloc((size_t)k * 8));
+    RNLA_TRY(dev_cur(randomised, dA.d(), m, m, n, k, ctx().opts, dJ.as<int64_t>(), dU.d(), k, dI.as<int64_t>()));
+    RNLA_TRY(d2h(U, dU.d(), (size_t)k * k));
+    RNLA_TRY(d2h_idx(I, dI.as<int64_t>(), (size_t)k));
+    return d2h_idx(J, dJ.as<int64_t>(), (size_t)k);
+}
+
+rnla_status rnla_sketch_saddle_point_precondition_dev(const double* dA, int64_t lda, int64_t m, int64_t n, const double* db,
+                                                      const double* dc, double mu, double epsilon, int64_t l, double sampling_factor,
+                                                      double* dx, double* dy, int64_t* iterations, int32_t* converged) {
+    RNLA_API_GUARD;
+    RNLA_TRY(ensure_ctx());
+    RNLA_TRY(validate_lsq(m, n, epsilon, l, sampling_factor));                                             // sketch_and_precondition.rs:152-171
+    return dev_saddle_point(dA, lda, m, n, db, dc, mu, epsilon, l, sampling_factor, RNLA_GAUSSIAN, ctx().opts.seed, dx, dy, iterations, converged);
+}
+rnla_status rnla_sketch_saddle_point_precondition(const double* A, int64_t m, int64_t n, const double* b, const double* c, double mu,
+                                                  double epsilon, int64_t l, double sampling_factor, double* x, double* y,
+                                                  int64_t* iterations, int32_t* converged) {
+    RNLA_API_GUARD;
+    RNLA_TRY(validate_lsq(m, n, epsilon, l, sampling_factor));
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, db, dc, dx, dy;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_TRY(h2d(db, b, (size_t)m));
+    if (c) RNLA_TRY(h2d(dc, c, (size_t)n));
+    RNLA_CUDA(dx.alloc((size_t)n * 8)); RNLA_CUDA(dy.alloc((size_t)m * 8));
+    RNLA_TRY(dev_saddle_point(dA.d(), m, m, n, db.d(), c ? dc.d() : nullptr, mu, epsilon, l, sampling_factor, RNLA_GAUSSIAN,
+                              ctx().opts.seed, dx.d(), dy.d(), iterations, converged));
+    RNLA_TRY(d2h(x, dx.d(), (size_t)n));
+    return d2h(y, dy.d(), (size_t)m);
+}

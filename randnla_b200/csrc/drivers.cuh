@@ -55,6 +55,38 @@ rnla_status dev_lsrn(const double* A, int64_t lda, int64_t m_local, int64_t n, c
                      double sampling_factor, int kind, int dist_or_width, int zeta, uint64_t seed, double* x,
                      int64_t* iters_out, int32_t* converged_out);
 
+rnla_status dev_small_gemv(const double* M, int64_t ld, int n, int trans, const double* x, double* y);
+rnla_status dev_axpby_vec(double a, const double* x, double b, double* y, int64_t n);
+rnla_status dev_cgls_operator(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, const double* M, double* z,
+                              double epsilon, int64_t maxit, int64_t* it_out, int32_t* conv_out);
+
+// pivot.cu: column-pivoted Householder QR (reference src/pivot_decompositions.rs:105-269) and index shuffles
+rnla_status dev_qrcp(double* R, int64_t ldr, int64_t m, int64_t n, int64_t steps, int64_t* dperm, double* Q, int64_t ldq, int64_t qcols);
+rnla_status dev_gather_columns(const double* A, int64_t lda, int64_t m, const int64_t* dJ, int64_t k, double* out, int64_t ldo);
+rnla_status dev_gather_rows(const double* A, int64_t lda, int64_t n, const int64_t* dI, int64_t k, double* out, int64_t ldo);
+rnla_status dev_scatter_rows(const double* M, int64_t ldm, int64_t k, const int64_t* dJ, double* W, int64_t ldw);
+rnla_status dev_build_interp(const double* T, int64_t ldt, int64_t k, int64_t w, const int64_t* dperm, double* X, int64_t ldx);
+rnla_status dev_backsolve_upper(const double* U, int64_t ldu, int n, double* y, double* x);
+rnla_status dev_diag_solve(const double* s, int n, double* z);
+rnla_status dev_saddle_weights(const double* s, int n, double mu, double* w);
+rnla_status dev_mul_vec(const double* w, int n, double* z);
+
+// next_rows.cu: SURVEY.md section 8f rows 2-4 and the saddle-point driver
+rnla_status dev_sap_chol_qrcp(const double* A, int64_t lda, int64_t m, int64_t n, int64_t d, int kind, int dist_or_width, int zeta,
+                              uint64_t seed, double* Q, int64_t ldq, double* R, int64_t ldr, int64_t* dJ, int64_t* k_out);
+rnla_status dev_sketched_least_squares(int which, const double* A, int64_t lda, int64_t m, int64_t n, const double* b, int kind,
+                                       int dist_or_width, int zeta, uint64_t seed, double* x);
+rnla_status dev_osid_qrcp(const double* Y, int64_t ldy, int64_t l, int64_t w, int64_t k, int attr, double* X, int64_t ldx, int64_t* dJ);
+rnla_status dev_osid_randomised(const double* A, int64_t lda, int64_t m, int64_t n, int64_t k, int attr, const rnla_options& o,
+                                double* X, int64_t ldx, int64_t* dJ);
+rnla_status dev_two_sided_id(int randomised, const double* A, int64_t lda, int64_t m, int64_t n, int64_t k, const rnla_options& o,
+                             double* Z, int64_t ldz, int64_t* dI, int64_t* dJ, double* X, int64_t ldx);
+rnla_status dev_cur(int randomised, const double* A, int64_t lda, int64_t m, int64_t n, int64_t k, const rnla_options& o,
+                    int64_t* dJ, double* U, int64_t ldu, int64_t* dI);
+rnla_status dev_saddle_point(const double* A, int64_t lda, int64_t m, int64_t n, const double* b, const double* cvec, double mu,
+                             double epsilon, int64_t maxit, double sampling_factor, int dist, uint64_t seed, double* x, double* y,
+                             int64_t* iters_out, int32_t* converged_out);
+
 // literal.cu: bug-compatible pieces of the reference
 rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
                           const rnla_options& o, double* S);

@@ -305,6 +305,22 @@ static rnla_status cgls_operator(Solver& S, const double* A, int64_t lda, int64_
     return RNLA_OK;
 }
 
+// building blocks of the other sketch-and-precondition / sketch-and-solve drivers (next_rows.cu)
+rnla_status dev_small_gemv(const double* M, int64_t ld, int n, int trans, const double* x, double* y) {
+    Solver S(ctx());
+    return S.small_gemv(M, ld, n, trans, x, y);
+}
+rnla_status dev_axpby_vec(double a, const double* x, double b, double* y, int64_t n) {
+    Solver S(ctx());
+    return S.axpby(a, x, b, y, n);
+}
+rnla_status dev_cgls_operator(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, const double* M, double* z,
+                              double epsilon, int64_t maxit, int64_t* it_out, int32_t* conv_out) {
+    Solver S(ctx());
+    RNLA_TRY(S.init());
+    return cgls_operator(S, A, lda, m_local, n, b, M, z, epsilon, maxit, it_out, conv_out);
+}
+
 // blendenpik_overdetermined on device buffers.  A: m_local x n (row shard), b: m_local.  x: n (replicated).
 // iters_out: CGLS iterations used; converged_out: 1 if the reference's stopping rule ||s|| < epsilon fired.
 rnla_status dev_blendenpik(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double epsilon,

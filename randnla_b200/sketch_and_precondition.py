@@ -108,3 +108,23 @@ def lsrn_overdetermined(a, b, epsilon, l, sampling_factor, kind=SKETCH_DENSE, ze
     if info is not None:
         info["iterations"] = int(it.value); info["converged"] = bool(conv.value)
     return x
+
+
+def sketch_saddle_point_precondition(a, b, c, mu, epsilon, l, sampling_factor, info=None):
+    """`sketch_saddle_point_precondition(a, b, c, mu, epsilon, l, sampling_factor) -> (x, y)` end to end (reference :150-216):
+    min ||a x - b||^2 + mu ||x||^2 + 2 <c, x> through the SVD of a dense Gaussian sketch and CGLS in operator form;
+    y = b - a x.  `c` may be None / empty (`c.is_empty()`, :195).  n <= 1024 (size of the on-device SVD core)."""
+    lib = _lib.load()
+    a = runtime.as_f(a)
+    b = runtime.as_f(b)
+    m, n = a.shape
+    cc = None if c is None or np.size(c) == 0 else runtime.as_f(c)
+    x = np.empty((n, 1), dtype=np.float64, order="F")
+    y = np.empty((m, 1), dtype=np.float64, order="F")
+    it = C.c_int64(0); conv = C.c_int32(0)
+    check(lib.rnla_sketch_saddle_point_precondition(runtime.ptr(a), m, n, runtime.ptr(b), runtime.ptr(cc) if cc is not None else None,
+                                                    float(mu), float(epsilon), int(l), float(sampling_factor), runtime.ptr(x),
+                                                    runtime.ptr(y), C.byref(it), C.byref(conv)))
+    if info is not None:
+        info["iterations"] = int(it.value); info["converged"] = bool(conv.value)
+    return x, y

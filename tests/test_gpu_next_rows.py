@@ -1,0 +1,292 @@
+"""Parity of the rows after the hot path (CQRRPT, sketch-and-solve, ID / CUR, saddle point) with the
+CPU oracle's restatement (oracle/oracle_next.c), through the C ABI, on a B200.  The test bodies follow the reference's own
+tests (src/pivot_decompositions.rs:318-395, src/cqrrpt.rs:72-133, src/sketch_and_solve.rs:80-158, src/id.rs:329-546,
+src/sketch_and_precondition.rs:277-337), with the assertions the reference only prints turned into bounds.
+
+Both sides draw the sketching operators from the same Philox map, so pivots, ranks and factors are comparable entry for
+entry.  Tolerances: factors and solutions to 1e-9 relative (f64, different summation orders); index vectors exact."""
+import numpy as np
+import pytest
+
+from conftest import rank_k_matrix, random_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def perm_matrix_t(p):
+    """src/test_assist.rs permutation_vector_to_transpose_matrix: P[i, p[i]] = 1"""
+    n = len(p)
+    P = np.zeros((n, n))
+    P[np.arange(n), p] = 1.0
+    return P
+
+
+# ------------------------------------------------------------------------------------------- pivot_decompositions
+@pytest.mark.parametrize("m,n", [(137, 23), (500, 29), (40, 40), (3000, 64), (20, 55)])
+def test_qrcp_matches_oracle_and_reference_properties(rb, orc, m, n):
+    """src/pivot_decompositions.rs:320-348 test_qrcp: orthonormal q, upper-triangular r, q r p^T = a; plus entry-wise
+    agreement with the oracle (same pivots, same reflectors)"""
+    from randnla_b200 import pivot_decompositions as pd
+    A = random_matrix(m, n, seed=m + n)
+    q, r, p = pd.qrcp(A)
+    Qo, Ro, po = orc.qrcp(A)
+    assert p == [int(v) for v in po]
+    assert sorted(p) == list(range(n))
+    scale = np.abs(A).max()
+    assert np.abs(r - Ro).max() <= 1e-12 * scale * np.sqrt(m)
+    assert np.abs(q - Qo).max() <= 1e-12 * np.sqrt(m)
+    assert np.abs(q.T @ q - np.eye(m)).max() < 1e-13 * m
+    assert np.abs(np.tril(r, -1)).max() <= 1e-13 * scale * np.sqrt(m)
+    assert np.abs(q @ r @ perm_matrix_t(p) - A).max() <= 1e-12 * scale * np.sqrt(m)
+    d = np.abs(np.diag(r))
+    assert (d[:-1] >= d[1:] * (1 - 1e-12)).all()          # rank revealing: non-increasing diagonal
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 25, 12), (64, 200, 30), (2500, 40, 40), (9, 7, 1)])
+def test_economic_qrcp(rb, orc, m, n, k):
+    """src/pivot_decompositions.rs:372-386 test_qrcp_economical + oracle parity; :389-395 bad input"""
+    from randnla_b200 import pivot_decompositions as pd
+    from randnla_b200.errors import InvalidParameters
+    A = random_matrix(m, n, seed=k)
+    q, r, p = pd.economic_qrcp(A, k)
+    Qo, Ro, po = orc.economic_qrcp(A, k)
+    assert q.shape == (m, k) and r.shape == (k, n)
+    assert p == [int(v) for v in po]
+    assert np.abs(r - Ro).max() <= 1e-12 * np.abs(A).max() * np.sqrt(m)
+    assert np.abs(q - Qo).max() <= 1e-12 * np.sqrt(m)
+    assert np.abs(q.T @ q - np.eye(k)).max() < 1e-13 * m
+    assert np.abs(np.tril(r[:, :k], -1)).max() <= 1e-13 * np.abs(A).max() * np.sqrt(m)
+    # the leading k columns are reproduced exactly by the truncated factorisation
+    assert np.abs(q @ r[:, :k] - A[:, p[:k]]).max() <= 1e-12 * np.abs(A).max() * np.sqrt(m)
+    with pytest.raises(InvalidParameters):
+        pd.economic_qrcp(A, 0)
+    with pytest.raises(InvalidParameters):
+        pd.economic_qrcp(A, min(m, n) + 1)
+
+
+def test_qrcp_rank_deficient_and_zero(rb, orc):
+    """zero trailing columns: |x| == 0 skips the reflection (:143); a zero matrix returns q = I, r = 0, p = identity"""
+    from randnla_b200 import pivot_decompositions as pd
+    A = rank_k_matrix(60, 20, 5, seed=3)
+    q, r, p = pd.qrcp(A)
+    assert np.abs(q @ r @ perm_matrix_t(p) - A).max() <= 1e-11 * np.abs(A).max()
+    assert np.abs(np.diag(r))[5:].max() <= 1e-10 * np.abs(np.diag(r))[0]
+    Z = np.zeros((12, 5), order="F")
+    q, r, p = pd.qrcp(Z)
+    assert p == list(range(5)) and np.array_equal(q, np.eye(12)) and not r.any()
+
+
+# ------------------------------------------------------------------------------------------------------- cqrrpt
+@pytest.mark.parametrize("m,n,d,kind", [(100, 10, 37, 0), (4000, 60, 240, 0), (20000, 130, 520, 2), (6000, 300, 600, 0)])
+def test_sap_chol_qrcp(rb, orc, m, n, d, kind):
+    """src/cqrrpt.rs:73-112 test_cqrrpt: unit, mutually orthogonal columns of q; upper-triangular r; q r p^T = a
+    (the reference compares against deterministic qrcp at 1e-4); plus parity with the oracle on the same sketch"""
+    from randnla_b200 import cqrrpt
+    A = np.asfortranarray(np.random.default_rng(d).uniform(-1, 1, (m, n)))
+    q, r, j = cqrrpt.sap_chol_qrcp(A, d, kind=kind)
+    Qo, Ro, Jo = orc.sap_chol_qrcp(A, d, kind=kind)
+    assert q.shape == (m, n) and r.shape == (n, n)
+    assert j == [int(v) for v in Jo]
+    assert np.abs(q.T @ q - np.eye(n)).max() < 1e-13 * n
+    assert np.abs(np.tril(r, -1)).max() <= 1e-12 * np.abs(r).max()
+    assert np.abs(q @ r @ perm_matrix_t(j) - A).max() <= 1e-12 * np.sqrt(m)
+    assert np.abs(r - Ro).max() <= 1e-10 * np.abs(Ro).max()
+    assert np.abs(q - Qo).max() <= 1e-10
+
+
+def test_sap_chol_qrcp_rank_deficient_and_errors(rb, orc):
+    """numerical rank k < n (:37-43): q has k columns, a[:, j[:k]] = q r[:, :k]; the reference's panics (:114-133)"""
+    from randnla_b200 import cqrrpt
+    from randnla_b200.errors import InvalidParameters
+    A = rank_k_matrix(500, 30, 11, seed=5)
+    q, r, j = cqrrpt.sap_chol_qrcp(A, 90)
+    Qo, Ro, Jo = orc.sap_chol_qrcp(A, 90)
+    assert q.shape == (500, 11) and r.shape == (11, 30) and Qo.shape == q.shape
+    assert j[:11] == [int(v) for v in Jo[:11]]
+    assert np.abs(q.T @ q - np.eye(11)).max() < 1e-12
+    assert np.abs(q @ r - A[:, j]).max() <= 1e-9 * np.abs(A).max()
+    data = random_matrix(100, 10, seed=1)
+    with pytest.raises(InvalidParameters, match="d must satisfy"):
+        cqrrpt.sap_chol_qrcp(data, 5)                     # test_cqrrpt_wrong_d
+    with pytest.raises(InvalidParameters, match="d must satisfy"):
+        cqrrpt.sap_chol_qrcp(data.T.copy(), 50)           # test_cqrrpt_wide_matrix
+
+
+# --------------------------------------------------------------------------------------------- sketch_and_solve
+@pytest.mark.parametrize("kind", [0, 2])
+@pytest.mark.parametrize("m,n", [(480, 25), (16000, 200)])
+def test_sketched_least_squares(rb, orc, m, n, kind):
+    """src/sketch_and_solve.rs:81-158: noisy data from a hypothesis; the sketched residual is within a small factor of the
+    optimal one (the reference prints both); parity with the oracle on the same sketch"""
+    from randnla_b200 import sketch_and_solve as ss
+    from randnla_b200.errors import InvalidDimensions
+    rng = np.random.default_rng(m)
+    hyp = rng.uniform(-100, 100, (n, 1))
+    A = rng.standard_normal((m, n))
+    y = A @ hyp
+    A = np.asfortranarray(A + 0.01 * rng.standard_normal((m, n)))
+    xl = np.linalg.lstsq(A, y, rcond=None)[0]
+    res_opt = np.linalg.norm(A @ xl - y)
+    for which, fn in ((0, ss.sketched_least_squares_qr), (1, ss.sketched_least_squares_svd)):
+        x = fn(A, y, kind=kind)
+        xo = orc.sketched_least_squares(which, A, y, kind=kind)
+        assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+        assert np.linalg.norm(A @ x - y) <= 2.0 * res_opt      # (1 + eps) distortion with d = m / 4 >= 4.8 n
+    with pytest.raises(InvalidDimensions):
+        ss.sketched_least_squares_qr(random_matrix(40, 20, seed=1), random_matrix(40, 1, seed=2))
+
+
+def test_sketched_least_squares_zero_pivot_rule(rb, orc):
+    """src/solvers.rs:22-41, :57-69: a zero column gives a zero pivot / zero singular value; that unknown stays 0.
+    (The zero column is the last one: for an interior zero column the reference's answer depends on which unit vector its
+    Householder QR happens to put into q, which no other QR reproduces.)"""
+    from randnla_b200 import sketch_and_solve as ss
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((400, 6)); A[:, 5] = 0.0
+    A = np.asfortranarray(A)
+    b = rng.standard_normal((400, 1))
+    for which, fn in ((0, ss.sketched_least_squares_qr), (1, ss.sketched_least_squares_svd)):
+        x = fn(A, b)
+        xo = orc.sketched_least_squares(which, A, b)
+        assert x[5, 0] == 0.0 and np.isfinite(x).all()
+        assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+
+
+# ----------------------------------------------------------------------------------------------------------- id
+@pytest.mark.parametrize("m,n,k", [(104, 107, 60), (300, 90, 45), (70, 400, 33)])
+def test_one_sided_id(rb, orc, m, n, k):
+    """src/id.rs:463-490 test_one_sided_id on rank_k_matrix: the ID of an exactly rank-k matrix is exact"""
+    from randnla_b200 import id as rid
+    from randnla_b200.sketch import MatrixAttribute as MA
+    A = rank_k_matrix(m, n, k, seed=k)
+    nrm = np.linalg.norm(A)
+    x, j = rid.osid_qrcp(A, k, MA.Column)
+    xo, jo = orc.osid_qrcp(A, k, orc.COLUMN)
+    assert j == [int(v) for v in jo] and x.shape == (k, n)
+    assert np.linalg.norm(A[:, j] @ x - A) <= 1e-10 * nrm
+    assert np.abs(x - xo).max() <= 1e-8 * max(1.0, np.abs(xo).max())
+    assert np.array_equal(x[:, j], np.eye(k))
+    x, i = rid.osid_qrcp(A, k, MA.Row)
+    xo, io = orc.osid_qrcp(A, k, orc.ROW)
+    assert i == [int(v) for v in io] and x.shape == (m, k)
+    assert np.linalg.norm(x @ A[i, :] - A) <= 1e-10 * nrm
+    x, j = rid.osid_randomised(A, k, MA.Column)
+    xo, jo = orc.osid_randomised(A, k, orc.COLUMN)
+    assert j == [int(v) for v in jo]
+    assert np.linalg.norm(A[:, j] @ x - A) <= 1e-8 * nrm
+    assert np.abs(x - xo).max() <= 1e-7 * max(1.0, np.abs(xo).max())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("m,n,k", [(106, 101, 52), (500, 64, 40)])
+def test_two_sided_id(rb, orc, m, n, k, mode):
+    """src/id.rs:492-517 test_two_sided_id, deterministic and randomised; in both tsog1 modes (the Row step of the randomised
+    variant calls tsog1(a, k, 2, 1), :230)"""
+    from randnla_b200 import id as rid, runtime as rt
+    A = rank_k_matrix(m, n, k, seed=k + 1)
+    nrm = np.linalg.norm(A)
+    z, i, j, x = rid.two_sided_id(A, k)
+    zo, io, jo, xo = orc.two_sided_id(A, k, False)
+    assert i == [int(v) for v in io] and j == [int(v) for v in jo]
+    assert np.linalg.norm(z @ A[np.ix_(i, j)] @ x - A) <= 1e-9 * nrm
+    with rt.options(mode=mode):
+        z, i, j, x = rid.two_sided_id_randomised(A, k)
+    zo, io, jo, xo = orc.two_sided_id(A, k, True, orc.make_opts(mode=mode))
+    assert j == [int(v) for v in jo]
+    assert np.linalg.norm(z @ A[np.ix_(i, j)] @ x - A) <= 1e-7 * nrm
+    if mode == 1:
+        # literal tsog1 is reproduced statement for statement (bit-identical Stabilizer): same row pivots, same Z.  In the
+        # intended mode the two sides stabilise differently (CholeskyQR vs Householder: same range, different basis), so the
+        # row pivots of a S^T may legitimately differ; the decomposition is still exact.
+        assert i == [int(v) for v in io]
+        assert np.abs(z - zo).max() <= 1e-6 * max(1.0, np.abs(zo).max())
+
+
+@pytest.mark.parametrize("m,n,k", [(108, 103, 55), (90, 240, 31), (2000, 150, 64)])
+def test_cur(rb, orc, m, n, k):
+    """src/id.rs:519-546 test_cur, tall and wide, deterministic and randomised"""
+    from randnla_b200 import id as rid
+    A = rank_k_matrix(m, n, k, seed=k + 2)
+    nrm = np.linalg.norm(A)
+    for randomised, fn in ((False, rid.cur), (True, rid.cur_randomised)):
+        j, u, i = fn(A, k)
+        jo, uo, io = orc.cur(A, k, randomised)
+        assert i == [int(v) for v in io] and j == [int(v) for v in jo]
+        assert u.shape == (k, k)
+        assert np.linalg.norm(A[:, j] @ u @ A[i, :] - A) <= 1e-7 * nrm
+        assert np.abs(u - uo).max() <= 1e-6 * max(1.0, np.abs(uo).max())
+
+
+def test_id_reference_panics(rb):
+    """src/id.rs:329-461: k = 0 and k > min(m, n) panic in the reference -> InvalidParameters with the same text"""
+    from randnla_b200 import id as rid
+    from randnla_b200.sketch import MatrixAttribute as MA
+    from randnla_b200.errors import InvalidParameters, InvalidDimensions
+    data = np.asfortranarray(np.random.default_rng(0).uniform(-1, 1, (100, 10)))
+    for k, msg in ((0, "k must be positive"), (11, "k must be <= min")):
+        for call in (lambda: rid.osid_qrcp(data, k, MA.Column), lambda: rid.osid_randomised(data, k, MA.Column),
+                     lambda: rid.cur(data, k), lambda: rid.cur_randomised(data, k),
+                     lambda: rid.two_sided_id(data, k), lambda: rid.two_sided_id_randomised(data, k)):
+            with pytest.raises(InvalidParameters, match=msg):
+                call()
+    with pytest.raises(InvalidDimensions):
+        rid.osid_randomised(data, 4, MA.Row)              # a * tsog1(a, k, 2, 1)^T does not conform (:230-233)
+
+
+def test_randomised_id_on_a_large_lowrank_matrix(rb):
+    """the randomised column ID at a size where only the k x n sketch is ever pivoted: 200 000 x 2 000, rank 40"""
+    import torch
+    import ctypes as C
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    m, n, k = 200_000, 2_000, 40
+    g = torch.Generator(device="cuda").manual_seed(1)
+    L = torch.randn((m, k), generator=g, device="cuda", dtype=torch.float64)
+    Rm = torch.randn((k, n), generator=g, device="cuda", dtype=torch.float64)
+    A = rt.empty_colmajor(m, n); A.copy_(L @ Rm)
+    X = rt.empty_colmajor(k, n)
+    J = torch.zeros(k, dtype=torch.int64, device="cuda")
+    pa, lda = rt.dev_ptr_ld(A); px, ldx = rt.dev_ptr_ld(X)
+    torch.cuda.synchronize()
+    _lib.check(lib.rnla_osid_randomised_dev(pa, lda, m, n, k, 1, None, px, ldx, C.c_void_p(J.data_ptr())))
+    torch.cuda.synchronize()
+    err = torch.linalg.norm(A[:, J] @ X - A) / torch.linalg.norm(A)
+    assert float(err) < 1e-9
+    assert len(set(J.tolist())) == k
+
+
+# ------------------------------------------------------------------------------------------------- saddle point
+@pytest.mark.parametrize("mu,with_c", [(0.0, False), (0.0, True), (3.7, False), (3.7, True)])
+@pytest.mark.parametrize("m,n", [(100, 10), (20000, 200)])
+def test_saddle_point(rb, orc, m, n, mu, with_c):
+    """src/sketch_and_precondition.rs:278-337 test_saddle_point (sampling factor 1.5 as there) + parity with the oracle.
+    With mu = 0 the solution is that of the normal equations A^T A x = A^T b - c."""
+    from randnla_b200 import sketch_and_precondition as sp
+    rng = np.random.default_rng(m + n)
+    A = np.asfortranarray(rng.standard_normal((m, n)))
+    b = A @ rng.uniform(-100, 100, (n, 1)) + 1e-2 * rng.standard_normal((m, 1))
+    c = rng.uniform(-10, 10, (n, 1)) if with_c else None
+    info = {}
+    x, y = sp.sketch_saddle_point_precondition(A, b, c, mu, 1e-9, 1000, 1.5, info=info)
+    xo, yo, ito, convo = orc.saddle_point(A, b, c, mu, 1e-9, 1000, 1.5)
+    nrm = np.linalg.norm(xo)
+    assert info["converged"] and convo and abs(info["iterations"] - ito) <= 2
+    assert np.linalg.norm(x - xo) <= 1e-8 * nrm
+    assert np.linalg.norm(y - (b - A @ x)) <= 1e-10 * np.linalg.norm(b)
+    assert np.linalg.norm(y - yo) <= 1e-8 * max(np.linalg.norm(yo), np.linalg.norm(b) * 1e-3)
+    if mu == 0.0:
+        cz = np.zeros((n, 1)) if c is None else c
+        xt = np.linalg.solve(A.T @ A, A.T @ b - cz)
+        assert np.linalg.norm(x - xt) <= 1e-8 * np.linalg.norm(xt)
+
+
+def test_saddle_point_reference_errors(rb):
+    """src/sketch_and_precondition.rs:320-330: Err for sampling_factor < 1, epsilon <= 0, l = 0; underdetermined systems"""
+    from randnla_b200 import sketch_and_precondition as sp
+    from randnla_b200.errors import InvalidParameters, NotOverdetermined
+    A = random_matrix(100, 10, seed=1); b = random_matrix(100, 1, seed=2); c = random_matrix(10, 1, seed=3)
+    for eps, l, sf in ((1e-4, 1000, 0.5), (-1e-4, 1000, 1.5), (0.0, 1000, 1.5), (1e-4, 0, 1.5)):
+        with pytest.raises(InvalidParameters):
+            sp.sketch_saddle_point_precondition(A, b, c, 1.0, eps, l, sf)
+    with pytest.raises(NotOverdetermined):
+        sp.sketch_saddle_point_precondition(A.T.copy(), random_matrix(10, 1, seed=4), random_matrix(100, 1, seed=5), 1.0, 1e-4, 10, 1.5)
