@@ -290,3 +290,40 @@ def test_saddle_point_reference_errors(rb):
             sp.sketch_saddle_point_precondition(A, b, c, 1.0, eps, l, sf)
     with pytest.raises(NotOverdetermined):
         sp.sketch_saddle_point_precondition(A.T.copy(), random_matrix(10, 1, seed=4), random_matrix(100, 1, seed=5), 1.0, 1e-4, 10, 1.5)
+
+
+# -------------------------------------------------------------------------------------------- committed fixtures
+def test_next_rows_golden_vectors(rb):
+    """tests/golden/next_rows_golden.npz: oracle outputs committed with their generating script; the CUDA path reproduces
+    them without the oracle in the loop"""
+    import os
+    from randnla_b200 import pivot_decompositions as pd, cqrrpt, sketch_and_solve as ss, id as rid, sketch_and_precondition as sp
+    from randnla_b200 import runtime as rt
+    from randnla_b200.sketch import MatrixAttribute as MA
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "next_rows_golden.npz"))
+    F = np.asfortranarray
+    q, r, p = pd.qrcp(F(g["qrcp_A"]))
+    assert p == g["qrcp_p"].tolist() and np.abs(r - g["qrcp_R"]).max() < 1e-13 and np.abs(q - g["qrcp_Q"]).max() < 1e-13
+    q, r, j = cqrrpt.sap_chol_qrcp(F(g["cq_A"]), int(g["cq_d"]))
+    assert j == g["cq_J"].tolist() and np.abs(r - g["cq_R"]).max() < 1e-11 and np.abs(q - g["cq_Q"]).max() < 1e-12
+    assert np.abs(ss.sketched_least_squares_qr(F(g["sas_A"]), F(g["sas_b"])) - g["sas_x_qr"]).max() < 1e-11
+    assert np.abs(ss.sketched_least_squares_svd(F(g["sas_A"]), F(g["sas_b"])) - g["sas_x_svd"]).max() < 1e-11
+    M = F(g["id_A"]); k = int(g["id_k"])
+    x, j = rid.osid_qrcp(M, k, MA.Column)
+    assert j == g["id_col_J"].tolist() and np.abs(x - g["id_col_X"]).max() < 1e-10
+    x, i = rid.osid_qrcp(M, k, MA.Row)
+    assert i == g["id_row_I"].tolist() and np.abs(x - g["id_row_X"]).max() < 1e-10
+    x, j = rid.osid_randomised(M, k, MA.Column)
+    assert j == g["id_rand_J"].tolist() and np.abs(x - g["id_rand_X"]).max() < 1e-8
+    for name, fn in (("det", rid.cur), ("rand", rid.cur_randomised)):
+        j, u, i = fn(M, k)
+        assert j == g[f"cur_{name}_J"].tolist() and i == g[f"cur_{name}_I"].tolist()
+        assert np.abs(u - g[f"cur_{name}_U"]).max() < 1e-7 * max(1.0, np.abs(g[f"cur_{name}_U"]).max())
+    with rt.options(mode=rt.MODE_LITERAL):
+        for name, fn in (("det", rid.two_sided_id), ("rand", rid.two_sided_id_randomised)):
+            z, i, j, x = fn(M, k)
+            assert i == g[f"tsid_{name}_I"].tolist() and j == g[f"tsid_{name}_J"].tolist()
+            assert np.abs(z - g[f"tsid_{name}_Z"]).max() < 1e-7 * max(1.0, np.abs(g[f"tsid_{name}_Z"]).max())
+    for mu, key in ((0.0, "sp_x_mu0"), (2.0, "sp_x_mu2")):
+        x, y = sp.sketch_saddle_point_precondition(F(g["sp_A"]), F(g["sp_b"]), F(g["sp_c"]), mu, 1e-12, 200, 2.0)
+        assert np.abs(x - g[key]).max() < 1e-10

@@ -1,0 +1,211 @@
+"""Pins the oracle's restatement of the rows after the hot path (oracle/oracle_next.c) before the CUDA
+path is compared against it (-m "not gpu").  What the reference's own tests hold for these functions are PROPERTIES
+(src/pivot_decompositions.rs:320-395, src/cqrrpt.rs:73-133, src/id.rs:329-546 -- orthonormal q, triangular r, exact
+reconstruction at 1e-4 / 1e-6, panics on bad k and d; the ID, CUR, sketch-and-solve and saddle-point tests only print), so
+they are asserted here on seeded restatements of the same fixtures, and everything LAPACK can decide independently (pivot
+order, |diag R|, least-squares solutions, pseudo-inverses) is cross-checked against numpy / scipy."""
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg as sl
+
+from conftest import rank_k_matrix, random_matrix
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "next_rows_golden.npz")
+
+
+def perm_t(p):
+    n = len(p)
+    P = np.zeros((n, n)); P[np.arange(n), p] = 1.0
+    return P
+
+
+@pytest.mark.parametrize("m,n", [(137, 23), (40, 40), (20, 55), (499, 29)])
+def test_qrcp_reference_properties_and_lapack_pivots(orc, m, n):
+    """test_qrcp (:320-348); LAPACK dgeqp3 picks the same pivots on generic data (norm downdating vs exact recomputation
+    only differ on near ties) and the same |diag R|"""
+    A = random_matrix(m, n, seed=m * n)
+    Q, R, p = orc.qrcp(A)
+    assert np.abs(Q.T @ Q - np.eye(m)).max() < 1e-13
+    assert np.abs(np.tril(R, -1)).max() < 1e-13 * np.abs(A).max() * np.sqrt(m)
+    assert np.abs(Q @ R @ perm_t(p) - A).max() < 1e-12
+    Qs, Rs, ps = sl.qr(A, pivoting=True)
+    assert np.array_equal(p, ps)
+    k = min(m, n)
+    assert np.abs(np.abs(np.diag(R))[:k] - np.abs(np.diag(Rs))[:k]).max() < 1e-12 * np.abs(Rs).max()
+
+
+def test_economic_qrcp_and_first_maximum_rule(orc):
+    """test_qrcp_economical (:372-386); ties go to the first column (strict `>`, :122-127)"""
+    A = random_matrix(64, 30, seed=4)
+    Q, R, p = orc.economic_qrcp(A, 11)
+    assert Q.shape == (64, 11) and R.shape == (11, 30)
+    assert np.abs(Q.T @ Q - np.eye(11)).max() < 1e-13
+    assert np.abs(np.tril(R[:, :11], -1)).max() < 1e-13
+    assert np.abs(Q @ R[:, :11] - A[:, p[:11]]).max() < 1e-12
+    T = np.zeros((6, 4)); T[0, 1] = T[1, 2] = T[2, 3] = 2.0; T[3, 0] = 2.0      # four columns of equal norm
+    _, _, p = orc.qrcp(T)
+    assert p[0] == 0
+    T[:, 0] *= 0.5
+    _, _, p = orc.qrcp(T)
+    assert p[0] == 1
+    Z = np.zeros((5, 3))
+    Q, R, p = orc.qrcp(Z)
+    assert list(p) == [0, 1, 2] and np.array_equal(Q, np.eye(5)) and not R.any()
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_sap_chol_qrcp_reference_properties(orc, kind):
+    """test_cqrrpt (:73-112): unit, orthogonal columns of q (1e-6 there), triangular r, q r p^T = a (1e-4 there);
+    its two panics (:114-133) come back as code 1"""
+    A = np.asfortranarray(np.random.default_rng(7).uniform(-1, 1, (2100, 10)))
+    for d in (16, 48, 120):
+        Q, R, J = orc.sap_chol_qrcp(A, d, kind=kind)
+        assert Q.shape == (2100, 10) and R.shape == (10, 10) and sorted(J) == list(range(10))
+        assert np.abs(Q.T @ Q - np.eye(10)).max() < 1e-13
+        assert np.abs(np.tril(R, -1)).max() < 1e-12
+        assert np.abs(Q @ R @ perm_t(J) - A).max() < 1e-12
+        # the QR factorisation of a[:, J] is unique up to the signs of diag(r) (r = r_pre r_sk inherits the signs of the
+        # Householder diagonal of the sketch's qrcp): compare with LAPACK's after normalising both
+        Ql, Rl = np.linalg.qr(A[:, J]); s = np.sign(np.diag(Rl)) * np.sign(np.diag(R))
+        assert np.abs(R - s[:, None] * Rl).max() < 1e-11 and np.abs(Q - Ql * s).max() < 1e-12
+    for bad in (9, 2101):
+        with pytest.raises(ValueError) as e:
+            orc.sap_chol_qrcp(A, bad)
+        assert e.value.args[0] == 1
+    with pytest.raises(ValueError):
+        orc.sap_chol_qrcp(A.T.copy(), 50)
+    B = rank_k_matrix(300, 20, 6, seed=2)
+    Q, R, J = orc.sap_chol_qrcp(B, 60)
+    assert Q.shape == (300, 6) and R.shape == (6, 20)                        # numerical rank of the sketch (:37-43)
+    assert np.abs(Q @ R - B[:, J]).max() < 1e-9 * np.abs(B).max()
+
+
+def test_sketched_least_squares_restatement(orc):
+    """test_least_squares_qr / _svd (:81-158): both variants solve the SKETCHED problem exactly -- x = lstsq(S a, S b) with S
+    recovered from the oracle's own sketch of the identity -- and land near the full solution"""
+    rng = np.random.default_rng(3)
+    A = np.asfortranarray(rng.standard_normal((480, 25))); hyp = rng.uniform(-100, 100, (25, 1))
+    b = A @ hyp + 0.01 * rng.standard_normal((480, 1))
+    d = 480 // 4
+    for kind in (0, 2):
+        S = orc.sketch_apply_dense(np.eye(480), d) if kind == 0 else orc.sketch_apply_saso_block(np.eye(480), d)
+        xs = np.linalg.lstsq(S @ A, S @ b, rcond=None)[0]
+        for which in (0, 1):
+            x = orc.sketched_least_squares(which, A, b, kind=kind)
+            assert np.linalg.norm(x - xs) < 1e-10 * np.linalg.norm(xs)
+            assert np.linalg.norm(x - hyp) < 1e-3 * np.linalg.norm(hyp)
+    with pytest.raises(ValueError) as e:
+        orc.sketched_least_squares(0, A[:60].copy(), b[:60])
+    assert e.value.args[0] == 2
+    # zero pivot / zero singular value: the unknown stays 0 (src/solvers.rs:29, :62)
+    A0 = A[:, :6].copy(); A0[:, 5] = 0.0
+    for which in (0, 1):
+        x = orc.sketched_least_squares(which, A0, b)
+        assert x[5, 0] == 0.0 and np.isfinite(x).all()
+
+
+@pytest.mark.parametrize("m,n,k", [(104, 107, 60), (70, 200, 20)])
+def test_id_restatement(orc, m, n, k):
+    """test_one_sided_id / test_two_sided_id / test_cur (:463-546) on rank_k_matrix: every decomposition of an exactly rank-k
+    matrix is exact; X restricted to the chosen columns is the identity (:297-301); indices are distinct"""
+    A = rank_k_matrix(m, n, k, seed=k)
+    nrm = np.linalg.norm(A)
+    X, J = orc.osid_qrcp(A, k, orc.COLUMN)
+    assert np.array_equal(X[:, J], np.eye(k)) and len(set(J)) == k
+    assert np.linalg.norm(A[:, J] @ X - A) < 1e-10 * nrm
+    _, _, ps = sl.qr(A, pivoting=True)
+    assert list(J) == list(ps[:k])
+    X, I = orc.osid_qrcp(A, k, orc.ROW)
+    assert X.shape == (m, k) and np.linalg.norm(X @ A[I, :] - A) < 1e-10 * nrm
+    X, J = orc.osid_randomised(A, k, orc.COLUMN)
+    assert np.linalg.norm(A[:, J] @ X - A) < 1e-8 * nrm
+    for rnd in (False, True):
+        for mode in (0, 1):
+            Z, I, J, X = orc.two_sided_id(A, k, rnd, orc.make_opts(mode=mode))
+            assert np.linalg.norm(Z @ A[np.ix_(I, J)] @ X - A) < 1e-7 * nrm
+        J, U, I = orc.cur(A, k, rnd)
+        assert U.shape == (k, k) and np.linalg.norm(A[:, J] @ U @ A[I, :] - A) < 1e-7 * nrm
+    for bad in (0, min(m, n) + 1):                                           # the reference's panics (:329-461)
+        for call in (lambda: orc.osid_qrcp(A, bad, orc.COLUMN), lambda: orc.osid_randomised(A, bad, orc.COLUMN),
+                     lambda: orc.cur(A, bad), lambda: orc.two_sided_id(A, bad)):
+            with pytest.raises(ValueError) as e:
+                call()
+            assert e.value.args[0] == 1
+    with pytest.raises(ValueError) as e:
+        orc.osid_randomised(A, k, orc.ROW)                                  # a * tsog1(a, k, 2, 1)^T conforms only if n == k
+    assert e.value.args[0] == 2
+
+
+def test_cur_core_is_the_pseudo_inverse_formula(orc):
+    """src/id.rs:49-52: u = x pinv(a[i, :]) -- checked against numpy's pinv with the oracle's own x, i"""
+    A = rank_k_matrix(60, 45, 9, seed=1)
+    J, U, I = orc.cur(A, 9)
+    X, J2 = orc.osid_qrcp(A, 9, orc.COLUMN)
+    assert list(J) == list(J2)
+    assert np.abs(U - X @ np.linalg.pinv(A[I, :])).max() < 1e-9 * np.abs(U).max()
+
+
+def test_saddle_point_restatement(orc):
+    """test_saddle_point (:278-337).  With mu = 0 the result solves a^T a x = a^T b - c.  With mu > 0 the reference
+    preconditions with (sigma^2 + mu)^-1/2 but iterates on a M alone, so its x is still the mu = 0 solution of the modified
+    right-hand side -- restated as written, and pinned as such."""
+    rng = np.random.default_rng(5)
+    A = np.asfortranarray(rng.standard_normal((300, 12))); b = rng.standard_normal((300, 1)); c = rng.uniform(-10, 10, (12, 1))
+    x, y, it, conv = orc.saddle_point(A, b, None, 0.0, 1e-12, 300, 1.5)
+    assert conv and np.linalg.norm(x - np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-10 * np.linalg.norm(x)
+    assert np.linalg.norm(y - (b - A @ x)) < 1e-12 * np.linalg.norm(b)
+    x, y, it, conv = orc.saddle_point(A, b, c, 0.0, 1e-12, 300, 1.5)
+    assert conv and np.linalg.norm(x - np.linalg.solve(A.T @ A, A.T @ b - c)) < 1e-10 * np.linalg.norm(x)
+    x2, _, _, conv = orc.saddle_point(A, b, None, 2.5, 1e-12, 300, 1.5)
+    assert conv and np.linalg.norm(x2 - np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-9 * np.linalg.norm(x2)
+    for bad, code in (((1e-4, 1000, 0.5), 1), ((-1e-4, 1000, 1.5), 1), ((0.0, 1000, 1.5), 1), ((1e-4, 0, 1.5), 1)):
+        with pytest.raises(ValueError) as e:
+            orc.saddle_point(A, b, c, 1.0, *bad)
+        assert e.value.args[0] == code
+    with pytest.raises(ValueError) as e:
+        orc.saddle_point(A[:8].copy(), b[:8], c, 1.0, 1e-4, 10, 1.5)
+    assert e.value.args[0] == 4
+
+
+def test_oracle_reproduces_next_rows_golden(orc):
+    """tests/golden/next_rows_golden.npz (tests/golden/make_golden_next_rows.py) is what the GPU tests are also held to"""
+    g = np.load(GOLD)
+    F = np.asfortranarray
+    Q, R, p = orc.qrcp(F(g["qrcp_A"]))
+    assert np.array_equal(p, g["qrcp_p"]) and np.abs(R - g["qrcp_R"]).max() < 1e-14 and np.abs(Q - g["qrcp_Q"]).max() < 1e-14
+    Q, R, J = orc.sap_chol_qrcp(F(g["cq_A"]), int(g["cq_d"]))
+    assert np.array_equal(J, g["cq_J"]) and np.abs(R - g["cq_R"]).max() < 1e-13 and np.abs(Q - g["cq_Q"]).max() < 1e-13
+    assert np.abs(orc.sketched_least_squares(0, F(g["sas_A"]), F(g["sas_b"])) - g["sas_x_qr"]).max() < 1e-13
+    assert np.abs(orc.sketched_least_squares(1, F(g["sas_A"]), F(g["sas_b"])) - g["sas_x_svd"]).max() < 1e-13
+    M = F(g["id_A"]); k = int(g["id_k"])
+    X, J = orc.osid_qrcp(M, k, orc.COLUMN)
+    assert np.array_equal(J, g["id_col_J"]) and np.abs(X - g["id_col_X"]).max() < 1e-12
+    J, U, I = orc.cur(M, k, True)
+    assert np.array_equal(J, g["cur_rand_J"]) and np.array_equal(I, g["cur_rand_I"]) and np.abs(U - g["cur_rand_U"]).max() < 1e-10
+    x = orc.saddle_point(F(g["sp_A"]), F(g["sp_b"]), F(g["sp_c"]), 2.0, 1e-12, 200, 2.0)[0]
+    assert np.abs(x - g["sp_x_mu2"]).max() < 1e-12
+
+
+def test_next_rows_validation_precedes_device_access():
+    """the reference's asserts / Errs of these rows are raised by the C ABI before any device work (no GPU here)"""
+    import randnla_b200 as rb
+    from randnla_b200.errors import InvalidParameters, NotOverdetermined
+    from randnla_b200.sketch import MatrixAttribute as MA
+    A = random_matrix(100, 10, seed=1); b = random_matrix(100, 1, seed=2); c = random_matrix(10, 1, seed=3)
+    with pytest.raises(InvalidParameters) as e:
+        rb.cqrrpt.sap_chol_qrcp(A, 5)
+    assert str(e.value) == "d must satisfy n ≤ d ≪ m"             # src/cqrrpt.rs:29
+    for k, msg in ((0, "k must be positive)"), (11, "k must be <= min(l,w)")):   # src/id.rs:278-279 (typo included)
+        for call in (lambda: rb.id.osid_qrcp(A, k, MA.Column), lambda: rb.id.osid_randomised(A, k, MA.Row),
+                     lambda: rb.id.cur(A, k), lambda: rb.id.cur_randomised(A, k), lambda: rb.id.two_sided_id(A, k),
+                     lambda: rb.id.two_sided_id_randomised(A, k)):
+            with pytest.raises(InvalidParameters) as e:
+                call()
+            assert str(e.value) == msg
+    with pytest.raises(InvalidParameters) as e:
+        rb.sketch_and_precondition.sketch_saddle_point_precondition(A, b, c, 1.0, 1e-4, 1000, 0.5)
+    assert str(e.value) == "Sampling factor must be greater than 1, current input is 0.5"
+    with pytest.raises(NotOverdetermined):
+        rb.sketch_and_precondition.sketch_saddle_point_precondition(A.T.copy(), c, b, 1.0, 1e-4, 10, 1.5)

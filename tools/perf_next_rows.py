@@ -1,6 +1,6 @@
 """Next rows at BASELINE config-4 scale on one B200, device-resident timing:
   cqrrpt:  sap_chol_qrcp of a 1M x 512 and a 1M x 2000 matrix, block sparse-sign sketch d = 2n
-  sas:     sketched_least_squares_qr on 1M x 2000 (d = 250 000 rows, block sparse-sign sketch)
+  sas:     sketched_least_squares_qr on 65536 x 2000 (d = rows / 4 = 16384, block sparse-sign sketch)
   id:      osid_randomised (Column) on 200k x 20k (the config-2 matrix), k = 100
   cur:     cur_randomised on 200k x 2000, k = 100
   saddle:  sketch_saddle_point_precondition on 1M x 1000, sf = 2
@@ -58,7 +58,7 @@ if "cqrrpt" in which:
         print(f"cqrrpt_{m}x{n}", out[f"cqrrpt_{m}x{n}"], flush=True)
         del dA, Q, R; torch.cuda.empty_cache()
 if "sas" in which:
-    m, n = 1000000, 2000
+    m, n = 65536, 2000          # d = rows / 4 = 16384, the largest block sparse-sign sketch
     dA, pA, lda = gauss(m, n, 78)
     xt = torch.rand(n, 1, dtype=torch.float64, device="cuda") * 200 - 100
     db = rt.empty_colmajor(m, 1); db.copy_(dA @ xt + 1e-2 * torch.randn(m, 1, dtype=torch.float64, device="cuda"))
@@ -67,8 +67,8 @@ if "sas" in which:
         def run():
             _lib.check(lib.rnla_sketched_least_squares_dev(which_s, pA, lda, m, n, P(db), 2, 0, 8, P(dx)))
         t = timed(run, reps=1)
-        out[f"sas_{name}_1Mx2000"] = {"ms": t * 1e3, "rel_err_x": float((dx - xt).norm() / xt.norm()), "phases": rt.timings()}
-        print(f"sas_{name}", out[f"sas_{name}_1Mx2000"], flush=True)
+        out[f"sas_{name}_65536x2000"] = {"ms": t * 1e3, "rel_err_x": float((dx - xt).norm() / xt.norm()), "phases": rt.timings()}
+        print(f"sas_{name}", out[f"sas_{name}_65536x2000"], flush=True)
     del dA, db; torch.cuda.empty_cache()
 if "id" in which:
     m, n, k = 200000, 20000, 100
