@@ -6,9 +6,15 @@
 //   randblas::lora_helpers::{QB1, RF1, tsog1, Orth, Stabilizer}                               <- src/lora_helpers.rs
 //   randblas::lora_drivers::{rand_svd, rand_evd1, rand_evd2}                                  <- src/lora_drivers.rs
 //   randblas::sketch_and_precondition::{blendenpik_sketch, lsrn_sketch, saddle_point_sketch} <- src/sketch_and_precondition.rs:26-52,82-107,150-176
+//   randblas::sketch_and_precondition::{blendenpik_overdetermined, lsrn_overdetermined, sketch_saddle_point_precondition}
+//   randblas::pivot_decompositions::{qrcp, economic_qrcp}                                    <- src/pivot_decompositions.rs
+//   randblas::cqrrpt::sap_chol_qrcp                                                          <- src/cqrrpt.rs
+//   randblas::sketch_and_solve::{sketched_least_squares_qr, sketched_least_squares_svd}      <- src/sketch_and_solve.rs
+//   randblas::id::{osid_qrcp, osid_randomised, two_sided_id(_randomised), cur(_randomised)}  <- src/id.rs
 //   randblas::errors::RandNLAError                                                           <- src/errors.rs
 // `Result<T, RandNLAError>` becomes "returns T or throws RandNLAError".  Header-only; link with -lrnla.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -243,5 +249,109 @@ inline DMatrix sketch_only(const DMatrix& a, double epsilon, size_t l, double sa
     return a_sk;
 }
 }  // namespace sketch_and_precondition
+
+// sketch_saddle_point_precondition end to end (src/sketch_and_precondition.rs:150-216), n <= 1024: returns (x, y).
+// `c` may be empty (0 x 0), as `c.is_empty()` at :195
+namespace sketch_and_precondition {
+inline std::pair<DMatrix, DMatrix> sketch_saddle_point_precondition(const DMatrix& a, const DMatrix& b, const DMatrix& c, double mu,
+                                                                    double epsilon, size_t l, double sampling_factor) {
+    validate(a, epsilon, l, sampling_factor);
+    DMatrix x(a.ncols(), 1), y(a.nrows(), 1);
+    int64_t iters = 0; int32_t conv = 0;
+    errors::check(rnla_sketch_saddle_point_precondition(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), b.as_ptr(),
+                                                        c.nrows() * c.ncols() ? c.as_ptr() : nullptr, mu, epsilon, (int64_t)l,
+                                                        sampling_factor, x.as_mut_ptr(), y.as_mut_ptr(), &iters, &conv));
+    return {std::move(x), std::move(y)};
+}
+}  // namespace sketch_and_precondition
+
+// ---- rows after the hot path --------------------------------------------------------------
+inline std::vector<size_t> to_usize(const std::vector<int64_t>& v, size_t k) { return std::vector<size_t>(v.begin(), v.begin() + (long)k); }
+
+namespace pivot_decompositions {
+// src/pivot_decompositions.rs:105-180: (q m x m, r m x n, p)
+inline std::tuple<DMatrix, DMatrix, std::vector<size_t>> qrcp(const DMatrix& a) {
+    const size_t m = a.nrows(), n = a.ncols();
+    DMatrix q(m, m), r(m, n);
+    std::vector<int64_t> p(std::max<size_t>(n, 1));
+    errors::check(rnla_qrcp(a.as_ptr(), (int64_t)m, (int64_t)n, (int64_t)std::min(m, n), (int64_t)m, q.as_mut_ptr(), r.as_mut_ptr(), p.data()));
+    return {std::move(q), std::move(r), to_usize(p, n)};
+}
+// :196-269: (q_eco m x k, r_eco k x n, p); the reference's asserts ("k must be positive", "k must be <= min(m,n)") throw
+inline std::tuple<DMatrix, DMatrix, std::vector<size_t>> economic_qrcp(const DMatrix& a, size_t k) {
+    const size_t m = a.nrows(), n = a.ncols();
+    DMatrix q(m, std::max<size_t>(k, 1)), r(m, n);
+    std::vector<int64_t> p(std::max<size_t>(n, 1));
+    errors::check(rnla_qrcp(a.as_ptr(), (int64_t)m, (int64_t)n, (int64_t)k, (int64_t)k, q.as_mut_ptr(), r.as_mut_ptr(), p.data()));
+    return {std::move(q), DMatrix::from_fn(k, n, [&](size_t i, size_t j) { return r(i, j); }), to_usize(p, n)};
+}
+}  // namespace pivot_decompositions
+
+namespace cqrrpt {
+// src/cqrrpt.rs:27-58: (q m x k, r k x n, j)
+inline std::tuple<DMatrix, DMatrix, std::vector<size_t>> sap_chol_qrcp(const DMatrix& a, size_t d) {
+    const size_t m = a.nrows(), n = a.ncols();
+    DMatrix q(m, n);
+    std::vector<double> r(std::max<size_t>(n * n, 1));
+    std::vector<int64_t> j(std::max<size_t>(n, 1));
+    int64_t k = 0;
+    errors::check(rnla_sap_chol_qrcp(a.as_ptr(), (int64_t)m, (int64_t)n, (int64_t)d, RNLA_SKETCH_DENSE, RNLA_GAUSSIAN, 0, q.as_mut_ptr(),
+                                     r.data(), j.data(), &k));
+    return {q.columns(0, (size_t)k), DMatrix::from_fn((size_t)k, n, [&](size_t i, size_t c) { return r[i + c * (size_t)k]; }), to_usize(j, n)};
+}
+}  // namespace cqrrpt
+
+namespace sketch_and_solve {
+// src/sketch_and_solve.rs:24-33
+inline DMatrix sketched_least_squares_qr(const DMatrix& a, const DMatrix& b) {
+    DMatrix x(a.ncols(), 1);
+    errors::check(rnla_sketched_least_squares_qr(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), b.as_ptr(), RNLA_SKETCH_DENSE, RNLA_GAUSSIAN, 0, x.as_mut_ptr()));
+    return x;
+}
+// :54-66
+inline DMatrix sketched_least_squares_svd(const DMatrix& a, const DMatrix& b) {
+    DMatrix x(a.ncols(), 1);
+    errors::check(rnla_sketched_least_squares_svd(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), b.as_ptr(), RNLA_SKETCH_DENSE, RNLA_GAUSSIAN, 0, x.as_mut_ptr()));
+    return x;
+}
+}  // namespace sketch_and_solve
+
+namespace id {
+using sketch::MatrixAttribute;
+// src/id.rs:272-318
+inline std::pair<DMatrix, std::vector<size_t>> osid_qrcp(const DMatrix& y, size_t k, MatrixAttribute attr) {
+    const bool col = attr == MatrixAttribute::Column;
+    DMatrix x(col ? std::max<size_t>(k, 1) : y.nrows(), col ? y.ncols() : std::max<size_t>(k, 1));
+    std::vector<int64_t> j(std::max<size_t>(k, 1));
+    errors::check(rnla_osid_qrcp(y.as_ptr(), (int64_t)y.nrows(), (int64_t)y.ncols(), (int64_t)k, (int32_t)attr, x.as_mut_ptr(), j.data()));
+    return {std::move(x), to_usize(j, k)};
+}
+// :217-249
+inline std::pair<DMatrix, std::vector<size_t>> osid_randomised(const DMatrix& a, size_t k, MatrixAttribute attr) {
+    const bool col = attr == MatrixAttribute::Column;
+    DMatrix x(col ? std::max<size_t>(k, 1) : a.nrows(), col ? a.ncols() : std::max<size_t>(k, 1));
+    std::vector<int64_t> j(std::max<size_t>(k, 1));
+    errors::check(rnla_osid_randomised(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), (int64_t)k, (int32_t)attr, x.as_mut_ptr(), j.data()));
+    return {std::move(x), to_usize(j, k)};
+}
+inline std::tuple<DMatrix, std::vector<size_t>, std::vector<size_t>, DMatrix> two_sided_impl(const DMatrix& a, size_t k, int randomised) {
+    DMatrix z(a.nrows(), std::max<size_t>(k, 1)), x(std::max<size_t>(k, 1), a.ncols());
+    std::vector<int64_t> i(std::max<size_t>(k, 1)), j(std::max<size_t>(k, 1));
+    errors::check(rnla_two_sided_id(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), (int64_t)k, randomised, z.as_mut_ptr(), i.data(), j.data(), x.as_mut_ptr()));
+    return {std::move(z), to_usize(i, k), to_usize(j, k), std::move(x)};
+}
+// :118-129 and :94-101
+inline auto two_sided_id(const DMatrix& a, size_t k) { return two_sided_impl(a, k, 0); }
+inline auto two_sided_id_randomised(const DMatrix& a, size_t k) { return two_sided_impl(a, k, 1); }
+inline std::tuple<std::vector<size_t>, DMatrix, std::vector<size_t>> cur_impl(const DMatrix& a, size_t k, int randomised) {
+    DMatrix u(std::max<size_t>(k, 1), std::max<size_t>(k, 1));
+    std::vector<int64_t> i(std::max<size_t>(k, 1)), j(std::max<size_t>(k, 1));
+    errors::check(rnla_cur(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), (int64_t)k, randomised, j.data(), u.as_mut_ptr(), i.data()));
+    return {to_usize(j, k), std::move(u), to_usize(i, k)};
+}
+// :34-71 and :154-193
+inline auto cur(const DMatrix& a, size_t k) { return cur_impl(a, k, 0); }
+inline auto cur_randomised(const DMatrix& a, size_t k) { return cur_impl(a, k, 1); }
+}  // namespace id
 
 }  // namespace randblas

@@ -79,6 +79,50 @@ int main() {
         try { sketch_and_precondition::blendenpik_overdetermined(A, b, 1e-6, 10, 0.5); CHECK(false); }
         catch (const RandNLAError& e) { CHECK(e.kind == RandNLAError::InvalidParameters); }
     }
+    // src/id.rs:463-546 on a rank-4 matrix: one-sided / two-sided ID and CUR reproduce it; :329-461 bad k throws
+    {
+        const size_t m = 60, n = 45, k = 4;
+        DMatrix L = DMatrix::from_fn(m, k, [](size_t i, size_t j) { return std::sin(0.7 * (double)(i + 1) * (double)(j + 1)); });
+        DMatrix Rr = DMatrix::from_fn(k, n, [](size_t i, size_t j) { return std::cos(0.3 * (double)(i + 2) * (double)(j + 1)); });
+        DMatrix A = L * Rr;
+        auto sel_cols = [&](const std::vector<size_t>& J) { return DMatrix::from_fn(m, J.size(), [&](size_t i, size_t c) { return A(i, J[c]); }); };
+        auto sel_rows = [&](const std::vector<size_t>& I) { return DMatrix::from_fn(I.size(), n, [&](size_t r, size_t j) { return A(I[r], j); }); };
+        auto rel = [&](const DMatrix& B) { double e = 0; for (size_t i = 0; i < m; ++i) for (size_t j = 0; j < n; ++j) e += (B(i, j) - A(i, j)) * (B(i, j) - A(i, j)); return std::sqrt(e) / A.norm(); };
+        auto [x, j] = id::osid_qrcp(A, k, sketch::MatrixAttribute::Column);
+        CHECK(rel(sel_cols(j) * x) < 1e-10);
+        auto [xr, jr] = id::osid_randomised(A, k, sketch::MatrixAttribute::Column);
+        CHECK(rel(sel_cols(jr) * xr) < 1e-9);
+        for (int rnd = 0; rnd < 2; ++rnd) {
+            auto [cj, u, ci] = rnd ? id::cur_randomised(A, k) : id::cur(A, k);
+            CHECK(rel(sel_cols(cj) * u * sel_rows(ci)) < 1e-8);
+            auto [z, ti, tj, tx] = rnd ? id::two_sided_id_randomised(A, k) : id::two_sided_id(A, k);
+            DMatrix core = DMatrix::from_fn(k, k, [&](size_t r, size_t c) { return A(ti[r], tj[c]); });
+            CHECK(rel(z * core * tx) < 1e-8);
+        }
+        try { id::osid_qrcp(A, 0, sketch::MatrixAttribute::Column); CHECK(false); }
+        catch (const RandNLAError& e) { CHECK(e.kind == RandNLAError::InvalidParameters && std::string(e.what()) == "k must be positive)"); }
+        // src/pivot_decompositions.rs:320-395 and src/cqrrpt.rs:73-133
+        auto [q, r, p] = pivot_decompositions::qrcp(L);
+        DMatrix qr = q * r;
+        double e = 0; for (size_t i = 0; i < m; ++i) for (size_t c = 0; c < k; ++c) e = std::fmax(e, std::fabs(qr(i, c) - L(i, p[c])));
+        CHECK(e < 1e-12 && approx_identity(q.transpose() * q, 1e-12));
+        auto [qc, rc, jc] = cqrrpt::sap_chol_qrcp(L, 12);
+        DMatrix qrc = qc * rc;
+        e = 0; for (size_t i = 0; i < m; ++i) for (size_t c = 0; c < k; ++c) e = std::fmax(e, std::fabs(qrc(i, c) - L(i, jc[c])));
+        CHECK(e < 1e-12 && approx_identity(qc.transpose() * qc, 1e-12));
+        try { cqrrpt::sap_chol_qrcp(L, 2); CHECK(false); } catch (const RandNLAError& e2) { CHECK(e2.kind == RandNLAError::InvalidParameters); }
+        // src/sketch_and_solve.rs:81-158 and src/sketch_and_precondition.rs:278-337 on a consistent system
+        DMatrix xt = DMatrix::from_fn(k, 1, [](size_t i, size_t) { return 1.5 - (double)i; });
+        DMatrix bb = L * xt;
+        for (int w = 0; w < 2; ++w) {
+            DMatrix xs = w ? sketch_and_solve::sketched_least_squares_svd(L, bb) : sketch_and_solve::sketched_least_squares_qr(L, bb);
+            double d = 0; for (size_t i = 0; i < k; ++i) d = std::fmax(d, std::fabs(xs(i, 0) - xt(i, 0)));
+            CHECK(d < 1e-9);
+        }
+        auto [sx, sy] = sketch_and_precondition::sketch_saddle_point_precondition(L, bb, DMatrix(), 0.0, 1e-12, 100, 2.0);
+        double d = 0; for (size_t i = 0; i < k; ++i) d = std::fmax(d, std::fabs(sx(i, 0) - xt(i, 0)));
+        CHECK(d < 1e-8 && sy.norm() < 1e-8 * bb.norm());
+    }
     std::printf(failures ? "CPP MIRROR: %d FAILURES\n" : "CPP MIRROR: ALL OK\n", failures);
     return failures ? 1 : 0;
 }

@@ -23,6 +23,19 @@ extern "C" {
     pub fn rnla_lsrn_overdetermined(a: *const c_double, m: i64, n: i64, b: *const c_double, epsilon: c_double, l: i64,
                                     sampling_factor: c_double, kind: c_int, dist: c_int, zeta: c_int, x: *mut c_double,
                                     iterations: *mut i64, converged: *mut c_int) -> c_int;
+    pub fn rnla_sketch_saddle_point_precondition(a: *const c_double, m: i64, n: i64, b: *const c_double, c: *const c_double, mu: c_double,
+                                                 epsilon: c_double, l: i64, sampling_factor: c_double, x: *mut c_double, y: *mut c_double,
+                                                 iterations: *mut i64, converged: *mut c_int) -> c_int;
+    // rows after the hot path: pivoted QR, CQRRPT, sketch-and-solve, ID / CUR
+    pub fn rnla_qrcp(a: *const c_double, m: i64, n: i64, steps: i64, qcols: i64, q: *mut c_double, r: *mut c_double, perm: *mut i64) -> c_int;
+    pub fn rnla_sap_chol_qrcp(a: *const c_double, m: i64, n: i64, d: i64, kind: c_int, dist: c_int, zeta: c_int,
+                              q: *mut c_double, r: *mut c_double, j: *mut i64, k: *mut i64) -> c_int;
+    pub fn rnla_sketched_least_squares_qr(a: *const c_double, m: i64, n: i64, b: *const c_double, kind: c_int, dist: c_int, zeta: c_int, x: *mut c_double) -> c_int;
+    pub fn rnla_sketched_least_squares_svd(a: *const c_double, m: i64, n: i64, b: *const c_double, kind: c_int, dist: c_int, zeta: c_int, x: *mut c_double) -> c_int;
+    pub fn rnla_osid_qrcp(y: *const c_double, l: i64, w: i64, k: i64, attr: c_int, x: *mut c_double, j: *mut i64) -> c_int;
+    pub fn rnla_osid_randomised(a: *const c_double, m: i64, n: i64, k: i64, attr: c_int, x: *mut c_double, j: *mut i64) -> c_int;
+    pub fn rnla_two_sided_id(a: *const c_double, m: i64, n: i64, k: i64, randomised: c_int, z: *mut c_double, i: *mut i64, j: *mut i64, x: *mut c_double) -> c_int;
+    pub fn rnla_cur(a: *const c_double, m: i64, n: i64, k: i64, randomised: c_int, j: *mut i64, u: *mut c_double, i: *mut i64) -> c_int;
 }
 
 pub fn last_message() -> String {

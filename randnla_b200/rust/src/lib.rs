@@ -7,3 +7,7 @@ pub mod lora_drivers;
 pub mod lora_helpers;
 pub mod sketch;
 pub mod sketch_and_precondition;
+pub mod pivot_decompositions;
+pub mod cqrrpt;
+pub mod sketch_and_solve;
+pub mod id;

@@ -84,3 +84,21 @@ pub fn lsrn_overdetermined(a: &DMatrix<f64>, b: &DMatrix<f64>, epsilon: f64, l: 
     if converged != 0 { println!("CGLS converged after {} iterations", iters); } else { println!("CGLS failed to converged after {} iterations", l); }
     Ok(x)
 }
+
+/// Drop-in for `sketch_saddle_point_precondition` (reference src/sketch_and_precondition.rs:150-216), end to end on the GPU
+/// (dense Gaussian sketch as in the reference; n <= 1024).  `c` may be empty (`c.is_empty()`, :195).
+pub fn sketch_saddle_point_precondition(a: &DMatrix<f64>, b: &DMatrix<f64>, c: &DMatrix<f64>, mu: f64, epsilon: f64, l: usize,
+                                        sampling_factor: f64) -> Result<(DMatrix<f64>, DMatrix<f64>), Box<dyn Error>> {
+    validate(a, epsilon, l, sampling_factor)?;
+    let (m, n) = a.shape();
+    let mut x = DMatrix::<f64>::zeros(n, 1);
+    let mut y = DMatrix::<f64>::zeros(m, 1);
+    let (mut iters, mut converged) = (0i64, 0i32);
+    let cp = if c.is_empty() { std::ptr::null() } else { c.as_ptr() };
+    from_status(unsafe {
+        ffi::rnla_sketch_saddle_point_precondition(a.as_ptr(), m as i64, n as i64, b.as_ptr(), cp, mu, epsilon, l as i64, sampling_factor,
+                                                   x.as_mut_ptr(), y.as_mut_ptr(), &mut iters, &mut converged)
+    })?;
+    if converged != 0 { println!("CGLS converged after {} iterations", iters); } else { println!("CGLS failed to converged after {} iterations", l); }
+    Ok((x, y))
+}
