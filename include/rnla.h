@@ -71,7 +71,10 @@ typedef struct rnla_options {
     int32_t passes_per_stab;  /* <=0: 1 (same lines) */
     int32_t fused_sketch;     /* 1: Omega is generated inside the A*Omega kernel and never materialised; 0: materialise (K0) then multiply;
                                * 2 (default): fuse iff the n x l operand would not stay L2-resident (> 48 MiB) */
-    int32_t reserved;
+    int32_t range_passes_int8; /* 1: the range-finder passes (A Omega, A^T Y, A S: results that only have to span a subspace) run on the INT8
+                               * tensor cores from a 4 x 7-bit fixed-point split of A (relative accuracy 2^-28 per product); the pass that
+                               * carries the singular values (Q^T A) stays FP64.  0 (default): every pass in FP64.  l <= 128, n <= 33280,
+                               * single pass structure of rand_svd / rand_evd1 (dev_qb1).  DESIGN.md section 5c */
 } rnla_options;
 
 /* ---- library / context ------------------------------------------------------------------------- */
@@ -292,6 +295,12 @@ int32_t rnla_plan_saso_block(int64_t d, int32_t zeta, int32_t width, int64_t n, 
 /* diagnostics: Jacobi sweeps used by the last small SVD (drivers and rnla_small_svd_dev) */
 int32_t rnla_last_jacobi_sweeps(void);
 rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double* dW, double* dLambda);
+
+/* the integer tensor-core products behind rnla_options.range_passes_int8 (csrc/i8gemm.cu), for tests and benches: one 4 x 7-bit
+ * split of A, then `reps` products.  trans = 0: C (m x N) = A B with B n x N;  trans != 0: C (n x N) = A^T B with B m x N.
+ * N <= 128, n <= 33280.  Relative accuracy about 2^-28 of (row maximum of A) x (column maximum of B) per product. */
+rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda, int64_t m, int64_t n, const double* dB, int64_t ldb,
+                                   int64_t N, double* dC, int64_t ldc, int32_t reps);
 
 /* synthetic inputs, generated on the device shard by shard: A = U0 diag(sigma) V0^T + eta G */
 rnla_status rnla_generate_lowrank_dev(double* dA, int64_t lda, int64_t m_local, int64_t n, int64_t row_offset,

@@ -16,7 +16,7 @@ P = C.c_void_p
 class Options(C.Structure):
     """`rnla_options` (include/rnla.h)."""
     _fields_ = [("mode", c_i32), ("dist", c_i32), ("seed", c_u64), ("num_passes", c_i32),
-                ("passes_per_stab", c_i32), ("fused_sketch", c_i32), ("reserved", c_i32)]
+                ("passes_per_stab", c_i32), ("fused_sketch", c_i32), ("range_passes_int8", c_i32)]
 
 
 # name -> (restype, argtypes); every symbol include/rnla.h declares
@@ -86,6 +86,7 @@ SIGNATURES = {
     "rnla_cur_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i32, C.POINTER(Options), P, P, c_i64, P]),
     "rnla_sketch_saddle_point_precondition": (c_i32, [P, c_i64, c_i64, P, P, c_f64, c_f64, c_i64, c_f64, P, P, P, P]),
     "rnla_sketch_saddle_point_precondition_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, P, c_f64, c_f64, c_i64, c_f64, P, P, P, P]),
+    "rnla_i8_range_gemm_dev": (c_i32, [c_i32, P, c_i64, c_i64, c_i64, P, c_i64, c_i64, P, c_i64, c_i32]),
     "rnla_small_eigh_dev": (c_i32, [P, c_i64, c_i64, P, P]),
     "rnla_generate_lowrank_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, P, c_f64, c_u64]),
     "rnla_measure_roofs": (c_i32, [C.POINTER(c_f64), C.POINTER(c_f64), C.c_size_t]),

@@ -803,3 +803,26 @@ rnla_status rnla_sketch_saddle_point_precondition(const double* A, int64_t m, in
     RNLA_TRY(d2h(x, dx.d(), (size_t)n));
     return d2h(y, dy.d(), (size_t)m);
 }
+
+// ---- INT8 tensor-core range-finder products (i8gemm.cu), exposed for tests and benches --------------------------------
+// trans = 0: C (m x N) = A (m x n) * B (n x N);  trans != 0: C (n x N) = A^T * B (m x N).  `reps` products with one split of A.
+rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda, int64_t m, int64_t n, const double* dB, int64_t ldb,
+                                   int64_t N, double* dC, int64_t ldc, int32_t reps) {
+    RNLA_API_GUARD;
+    RNLA_TRY(ensure_ctx());
+    if (N < 1 || N > 128 || ((n + 127) / 128) * 128 > 33280 || m < 1 || n < 1)
+        return fail(RNLA_ERR_INVALID_DIMENSIONS, "i8 range gemm: 1 <= N <= 128, n <= 33280");
+    phases_reset();
+    RNLA_TRY(i8_prepare(dA, lda, m, n));
+    rnla_status st = RNLA_OK;
+    for (int r = 0; r < std::max(reps, 1) && st == RNLA_OK; ++r) {
+        PhaseScope ph(trans ? "i8:At*B" : "i8:A*B");
+        st = trans ? i8_gemm_tn(dB, ldb, N, dC, ldc) : i8_gemm_nn(dB, ldb, N, dC, ldc);
+    }
+    i8_deactivate();
+    cudaError_t e = cudaStreamSynchronize(ctx().stream);
+    i8_release();
+    RNLA_TRY(st);
+    RNLA_CUDA(e);
+    return RNLA_OK;
+}

@@ -52,6 +52,7 @@ rnla_status shard_layout(int64_t rows_local, ShardInfo* out) {
 // ---------------------------------------------------------------- GEMM wrappers
 rnla_status dev_gemm_nn(const double* A, int64_t lda, int64_t m, int64_t K, const double* B, int64_t ldb, int64_t N,
                         double* C, int64_t ldc) {
+    if (i8_active_for(A, lda, m, K, N)) return i8_gemm_nn(B, ldb, N, C, ldc);      // range-finder pass on the INT8 tensor cores (i8gemm.cu)
     GemmNN p{};
     p.A = A; p.lda = lda; p.m = m; p.K = K; p.B = B; p.ldb = ldb; p.N = N; p.C = C; p.ldc = ldc; p.gen = 0;
     if (K == 0) { RNLA_CUDA(axpby_matrix(0.0, nullptr, 0, 0.0, nullptr, 0, C, ldc, m, N, ctx().stream)); return RNLA_OK; }
@@ -77,6 +78,8 @@ rnla_status dev_gemm_tn(const double* A, int64_t lda, int64_t m, int64_t n, cons
     if (need_ar && ldz != n) { RNLA_CUDA(packed.alloc((size_t)n * N * 8)); out = packed.d(); ldo = n; }
     if (m <= 0) {
         RNLA_CUDA(axpby_matrix(0.0, nullptr, 0, 0.0, nullptr, 0, out, ldo, n, N, c.stream));
+    } else if (i8_active_for(A, lda, m, n, N)) {
+        RNLA_TRY(i8_gemm_tn(Q, ldq, N, out, ldo));                                   // i8gemm.cu
     } else {
         const size_t wsb = gemm_tn_workspace_bytes(m, n, N, c.sms);
         DevBuf ws;
@@ -179,6 +182,7 @@ static inline bool use_fused(const rnla_options& o, int64_t n, int l) {
     if (o.fused_sketch == 1) return true;
     return (double)n * l * 8.0 > 48.0 * 1024 * 1024;
 }
+static inline bool use_fused_forced(const rnla_options& o) { return o.fused_sketch == 1; }
 static inline int eff_passes(const rnla_options& o, int dflt) { return o.num_passes > 0 ? o.num_passes : dflt; }
 static inline int eff_pps(const rnla_options& o) { return o.passes_per_stab > 0 ? o.passes_per_stab : 1; }
 
@@ -210,7 +214,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
                 auto hook = std::move(c.first_pass_hook);
                 c.first_pass_hook = nullptr;
                 RNLA_TRY(hook(S, Ytmp, std::max<int64_t>(m, 1)));
-            } else if (virt && use_fused(o, n, l)) {
+            } else if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
                 RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
             } else {
                 if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n, c.stream));
@@ -261,7 +265,7 @@ rnla_status dev_rf1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
         if (ldq != std::max<int64_t>(m, 1)) { RNLA_CUDA(Ytmp.alloc((size_t)std::max<int64_t>(m, 1) * l * 8)); ytmp = Ytmp.d(); }
         RNLA_TRY(tsog1_intended(A, lda, sh, n, l, q, pps, o, S.d(), ytmp, true, &virt));
         PhaseScope ph(virt ? (use_fused(o, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)") : "pass:A*S");
-        if (virt && use_fused(o, n, l)) {
+        if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
             RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Q, ldq));
         } else {
             if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S.d(), n, c.stream));
@@ -275,7 +279,15 @@ rnla_status dev_rf1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
 // QB1: Q = RF1(A, l); Bt = A^T Q  (n x l; the reference's B = Q^T A is its transpose)   lora_helpers.rs:17-23
 rnla_status dev_qb1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
                     const rnla_options& o, double* Q, int64_t ldq, double* Bt /* n x l, ld n */) {
-    RNLA_TRY(dev_rf1(A, lda, sh, n, l, q, pps, o, Q, ldq));
+    // range_passes_int8: the passes that only have to span the subspace run on the integer tensor cores (i8gemm.cu); the pass
+    // below, whose result carries the singular values, always runs in FP64
+    const bool i8 = o.range_passes_int8 == 1 && o.mode == RNLA_MODE_INTENDED && !use_fused_forced(o) && !ctx().first_pass_hook &&
+                    i8_supported(sh.rows_local, n, l);
+    if (i8) RNLA_TRY(i8_prepare(A, lda, sh.rows_local, n));
+    const rnla_status st = dev_rf1(A, lda, sh, n, l, q, pps, o, Q, ldq);
+    i8_deactivate();
+    if (i8) i8_release();
+    RNLA_TRY(st);
     PhaseScope ph("pass:At*Q");
     return dev_gemm_tn(A, lda, sh.rows_local, n, Q, ldq, l, Bt, n, true);
 }

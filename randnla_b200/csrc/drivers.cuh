@@ -87,6 +87,15 @@ rnla_status dev_saddle_point(const double* A, int64_t lda, int64_t m, int64_t n,
                              double epsilon, int64_t maxit, double sampling_factor, int dist, uint64_t seed, double* x, double* y,
                              int64_t* iters_out, int32_t* converged_out);
 
+// i8gemm.cu: range-finder passes on the INT8 tensor cores (tcgen05 kind::i8), opt-in through rnla_options.range_passes_int8
+bool i8_supported(int64_t m, int64_t n, int l);
+bool i8_active_for(const double* A, int64_t lda, int64_t m, int64_t n, int64_t N);
+void i8_deactivate();
+void i8_release();
+rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n);
+rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc);
+rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz);
+
 // literal.cu: bug-compatible pieces of the reference
 rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
                           const rnla_options& o, double* S);

@@ -1,0 +1,449 @@
+// Range-finder passes on the INT8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM): an Ozaki-style fixed-point
+// splitting of the FP64 operands, for the passes of the power iteration whose result only has to span the right subspace
+// (Y = A Omega, S = A^T Y, Y = A S; reference src/lora_helpers.rs:71-95 / :41).  The pass that determines the singular
+// values, B = Q^T A (src/lora_helpers.rs:21), stays on the FP64 DMMA kernels (gemm.cu).
+//
+//   a_ij = 2^{e_i} * sum_{t<4} d_t(i,j) 2^{-7(t+1)} + O(2^{e_i - 29}),   d_t in [-127, 127]   (e_i: exponent of the row maximum)
+//
+// A is split ONCE per driver call into four int8 digit planes, stored pre-tiled as the exact shared-memory images the MMA
+// descriptors expect (8 x 16-byte core matrices, no swizzle), in two arrangements: row-block major for A S (contraction over
+// columns) and column-block major for A^T Y (contraction over rows; the row scale 2^{e_i} is folded into Y before Y is split).
+// A stage of either pass is then ONE contiguous 32 KB bulk copy per operand (cp.async.bulk), 4 bytes of HBM traffic per element
+// of A instead of 8, and ten 128 x 128 x 32 integer MMAs per 32 columns: digit pairs (ta, tb) with ta + tb = g accumulate
+// exactly in int32 into accumulator g (4 x 128 TMEM columns = all 512), and the epilogue forms sum_g D_g 2^{-7(g+2)} exactly
+// in FP64.  Products with ta + tb >= 4 are dropped: relative accuracy 2^-28 of (row max) x (column max), enough for a basis.
+//
+// Accumulation bound: 4 pairs x 127^2 x K < 2^31  =>  K <= 33280 per accumulation (A S needs n <= 33280; A^T Y is chunked).
+#include "drivers.cuh"
+#include "gemm.cuh"
+#include "panel.cuh"
+#include "ptx.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace rnla {
+
+namespace {
+
+constexpr int PL = 4;                       // digit planes
+constexpr int BM = 128, BN = 128, BK = 64;  // CTA tile: 128 x 128 outputs, 64 contraction indices per stage
+constexpr int CHUNK = PL * BM * BK;         // 32 KB: one stage of one operand (all planes)
+constexpr int PLANE = BM * BK;              // 8 KB
+constexpr int STAGES = 3;
+constexpr int MMA_THREADS = 192;            // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr size_t MMA_SMEM = (size_t)STAGES * 2 * CHUNK + 1024 + 256;
+constexpr int64_t K_ACC_MAX = 33280;
+
+// ---------------------------------------------------------------------------------------------- tcgen05 wrappers
+__device__ __forceinline__ void tc_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], int8 x int8 -> int32
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, M = 128, N = 128
+__host__ __device__ constexpr uint32_t instr_desc(bool a_mn_major, bool b_mn_major) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------- splitting
+// |x| * scale -> 28-bit magnitude -> four signed 7-bit digits, most significant first
+__device__ __forceinline__ void digits4(double x, double scale, int (&d)[4]) {
+    const double ax = fabs(x) * scale;
+    unsigned v = __double2uint_rn(ax);
+    v = min(v, (1u << 28) - 1u);
+    const int s = x < 0.0 ? -1 : 1;
+    d[0] = s * (int)(v >> 21);
+    d[1] = s * (int)((v >> 14) & 127u);
+    d[2] = s * (int)((v >> 7) & 127u);
+    d[3] = s * (int)(v & 127u);
+}
+// exponent bookkeeping from the bit pattern of a maximum: up = 2^e with max < 2^e, down = 2^(28 - e); zero / tiny rows -> 0
+__device__ __forceinline__ void scales_from_max_bits(unsigned long long bits, double* up, double* down) {
+    const int E = (int)(bits >> 52) & 0x7ff;
+    if (E < 64 || E >= 2046) { *up = 0.0; *down = 0.0; return; }
+    *up = __longlong_as_double((long long)(E + 1) << 52);
+    *down = __longlong_as_double((long long)(2073 - E) << 52);
+}
+
+__global__ void __launch_bounds__(256)
+rowmax_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, int64_t cols_per, unsigned long long* __restrict__ bits) {
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+    if (i >= m) return;
+    const int64_t j0 = (int64_t)blockIdx.y * cols_per, j1 = min(n, j0 + cols_per);
+    const bool two = i + 1 < m;
+    const bool vec = two && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0);
+    double m0 = 0.0, m1 = 0.0;
+    if (vec) {
+#pragma unroll 8
+        for (int64_t j = j0; j < j1; ++j) {
+            double2 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(A + i + j * lda));
+            m0 = fmax(m0, fabs(v.x)); m1 = fmax(m1, fabs(v.y));
+        }
+    } else {
+        for (int64_t j = j0; j < j1; ++j) {
+            m0 = fmax(m0, fabs(ldg_stream(A + i + j * lda)));
+            if (two) m1 = fmax(m1, fabs(ldg_stream(A + i + 1 + j * lda)));
+        }
+    }
+    atomicMax(bits + i, (unsigned long long)__double_as_longlong(m0));
+    if (two) atomicMax(bits + i + 1, (unsigned long long)__double_as_longlong(m1));
+}
+__global__ void scales_kernel(const unsigned long long* __restrict__ bits, int64_t cnt, double* __restrict__ up, double* __restrict__ down) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) scales_from_max_bits(bits[i], up + i, down + i);
+}
+
+// One CTA per 128 x 128 block of A: two row-major-arranged images (NN: [plane][J 8][I 8][8 x 16 B], one per 64 columns) and two
+// column-major-arranged ones (TN: [plane][J 16][I 4][8 x 16 B], one per 64 rows).  A core matrix holds 16 rows x 8 columns of
+// A as 8 rows (columns of A) of 16 bytes (rows of A): the same 128 bytes serve as an MN-major core matrix of A S and as a
+// K-major one of A^T Y.
+__global__ void __launch_bounds__(256)
+slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, const double* __restrict__ down,
+               uint8_t* __restrict__ nn, int64_t kb_total, uint8_t* __restrict__ tn, int64_t kr_total, int64_t cblocks) {
+    extern __shared__ __align__(16) uint8_t img[];          // [0, 64K): NN images of the two column halves; [64K, 128K): TN images of the two row halves
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t rb = blockIdx.x / cblocks, cb = blockIdx.x % cblocks;
+    const int64_t R0 = rb * 128, C0 = cb * 128;
+    const bool vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int il = 64 * h + 2 * lane;                   // local rows il, il + 1
+        const int64_t i = R0 + il;
+        const double s0 = i < m ? down[i] : 0.0, s1 = i + 1 < m ? down[i + 1] : 0.0;
+#pragma unroll 4
+        for (int r = 0; r < 16; ++r) {
+            const int jl = warp + 8 * r;
+            const int64_t j = C0 + jl;
+            double x0 = 0.0, x1 = 0.0;
+            if (j < n) {
+                if (vec && i + 1 < m) {
+                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "l"(A + i + j * lda));
+                } else {
+                    if (i < m) x0 = ldg_stream(A + i + j * lda);
+                    if (i + 1 < m) x1 = ldg_stream(A + i + 1 + j * lda);
+                }
+            }
+            int d0[4], d1[4];
+            digits4(x0, s0, d0); digits4(x1, s1, d1);
+#pragma unroll
+            for (int t = 0; t < PL; ++t) {
+                const unsigned half = ((unsigned)d0[t] & 0xffu) | (((unsigned)d1[t] & 0xffu) << 8);
+                const unsigned other = __shfl_xor_sync(0xffffffffu, half, 1);
+                if ((lane & 1) == 0) {
+                    const unsigned word = half | (other << 16);             // rows il .. il + 3
+                    const int jj = jl & 63;
+                    const int off_nn = (jl >> 6) * CHUNK + t * PLANE + (jj >> 3) * 1024 + (il >> 4) * 128 + (jj & 7) * 16 + (il & 15);
+                    const int i64 = il & 63;
+                    const int off_tn = 2 * CHUNK + h * CHUNK + t * PLANE + (jl >> 3) * 512 + (i64 >> 4) * 128 + (jl & 7) * 16 + (i64 & 15);
+                    *reinterpret_cast<unsigned*>(img + off_nn) = word;
+                    *reinterpret_cast<unsigned*>(img + off_tn) = word;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(img);
+    uint4* dnn0 = reinterpret_cast<uint4*>(nn + (rb * kb_total + 2 * cb) * (int64_t)CHUNK);            // two consecutive column halves
+    uint4* dtn0 = reinterpret_cast<uint4*>(tn + (cb * kr_total + 2 * rb) * (int64_t)CHUNK);            // two consecutive row halves
+    for (int q = threadIdx.x; q < 2 * CHUNK / 16; q += 256) dnn0[q] = src[q];
+    for (int q = threadIdx.x; q < 2 * CHUNK / 16; q += 256) dtn0[q] = src[2 * CHUNK / 16 + q];
+}
+
+// per-column maxima of X (K x N), optionally with the row scale folded in (X(k, c) * rs[k])
+__global__ void __launch_bounds__(256)
+colmax_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, const double* __restrict__ rs, int64_t rows_per,
+              unsigned long long* __restrict__ bits) {
+    __shared__ double red[8];
+    const int c = blockIdx.x;
+    const int64_t k0 = (int64_t)blockIdx.y * rows_per, k1 = min(K, k0 + rows_per);
+    double mx = 0.0;
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) mx = fmax(mx, fabs(X[k + (int64_t)c * ldx] * (rs ? rs[k] : 1.0)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+        atomicMax(bits + c, (unsigned long long)__double_as_longlong(mx));
+    }
+}
+// B operand images: [k block of 64][plane][k group of 8][n block of 16][8 x 16 B]; columns >= N and rows >= K are zero
+__global__ void __launch_bounds__(256)
+slice_b_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, const double* __restrict__ rs, const double* __restrict__ cdown,
+               uint8_t* __restrict__ out) {
+    const int64_t kb = blockIdx.x;
+    const int kl = threadIdx.x & 63;
+    const int64_t k = kb * 64 + kl;
+    const double rsk = (k < K) ? (rs ? rs[k] : 1.0) : 0.0;
+    for (int cq = threadIdx.x >> 6; cq < 32; cq += 4) {
+        const int c0 = 4 * cq;
+        unsigned w[PL] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c0 + e;
+            int d[4] = {0, 0, 0, 0};
+            if (k < K && c < N) digits4(X[k + (int64_t)c * ldx] * rsk, cdown[c], d);
+#pragma unroll
+            for (int t = 0; t < PL; ++t) w[t] |= ((unsigned)d[t] & 0xffu) << (8 * e);
+        }
+#pragma unroll
+        for (int t = 0; t < PL; ++t)
+            *reinterpret_cast<unsigned*>(out + kb * (int64_t)CHUNK + t * PLANE + (kl >> 3) * 1024 + (c0 >> 4) * 128 + (kl & 7) * 16 + (c0 & 15)) = w[t];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- the MMA kernel
+// TN = false:  C(rows rb*128.., :) = rs_up(i) cs_up(c) * sum_g 2^{-7(g+2)} D_g,   contraction over all kb blocks of 64 columns
+// TN = true :  P[chunk](cols cb*128.., :) = sum_g 2^{-7(g+2)} D_g,                contraction over this chunk's blocks of 64 rows
+template <bool TN>
+__global__ void __launch_bounds__(MMA_THREADS, 1)
+i8_mma_kernel(const uint8_t* __restrict__ Aimg, int64_t a_blocks_per_tile, const uint8_t* __restrict__ Bimg, int64_t kblocks_total,
+              int64_t kblocks_per_chunk, double* __restrict__ C, int64_t ldc, int64_t rows, int ncols, const double* __restrict__ rs_up,
+              const double* __restrict__ cs_up, int64_t chunk_stride) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * 2 * CHUNK);
+    uint64_t* empty = full + STAGES;
+    uint64_t* accum = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.x;
+    const int64_t kb0 = (int64_t)blockIdx.y * kblocks_per_chunk;
+    const int64_t kb1 = min(kblocks_total, kb0 + kblocks_per_chunk);
+    const int nk = (int)(kb1 - kb0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(accum, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tc_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint8_t* a_src = Aimg + (tile * a_blocks_per_tile + kb0) * (int64_t)CHUNK;
+            const uint8_t* b_src = Bimg + kb0 * (int64_t)CHUNK;
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % STAGES;
+                if (it >= STAGES) mbar_wait(empty + s, ((it / STAGES) - 1) & 1);
+                mbar_arrive_expect_tx(full + s, 2 * CHUNK);
+                bulk_g2s(smem + (size_t)s * 2 * CHUNK, a_src + (int64_t)it * CHUNK, CHUNK, full + s);
+                bulk_g2s(smem + (size_t)s * 2 * CHUNK + CHUNK, b_src + (int64_t)it * CHUNK, CHUNK, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(!TN, true);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % STAGES;
+                mbar_wait(full + s, (it / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smem + (size_t)s * 2 * CHUNK);
+                const uint32_t b_base = a_base + CHUNK;
+#pragma unroll
+                for (int ks = 0; ks < BK / 32; ++ks) {
+#pragma unroll
+                    for (int ta = 0; ta < PL; ++ta) {
+#pragma unroll
+                        for (int tb = 0; tb + ta < PL; ++tb) {
+                            // A S: MN-major core matrices, 16-row blocks 128 B apart (SBO), 8-column groups 1024 B apart (LBO), 32 columns = 4096 B
+                            // A^T Y: K-major, 8-column blocks 512 B apart (SBO), the two 16-row halves 128 B apart (LBO), 32 rows = 256 B
+                            const uint64_t ad = TN ? smem_desc(a_base + ta * PLANE + ks * 256, 128, 512)
+                                                   : smem_desc(a_base + ta * PLANE + ks * 4096, 1024, 128);
+                            const uint64_t bd = smem_desc(b_base + tb * PLANE + ks * 4096, 1024, 128);
+                            const uint32_t acc = (it > 0 || ks > 0 || ta > 0) ? 1u : 0u;      // first pair of group g = tb is (0, g)
+                            tc_mma_i8(tmem + (uint32_t)(ta + tb) * BN, ad, bd, idesc, acc);
+                        }
+                    }
+                }
+                tc_commit(empty + s);
+            }
+            tc_commit(accum);
+        }
+    } else {
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
+        const int64_t r = tile * BM + quad * 32 + lane;     // output row (A S) / output row = column of A (A^T Y)
+        const double rsc = (!TN && r < rows) ? rs_up[r] : 1.0;
+        double* out = C + (TN ? (int64_t)blockIdx.y * chunk_stride : 0);
+        for (int c0 = 0; c0 < ncols; c0 += 16) {
+            uint32_t d[PL][16];
+#pragma unroll
+            for (int g = 0; g < PL; ++g) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * BN + c0), d[g]);
+            tc_wait_ld();
+            if (r < rows) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int c = c0 + e;
+                    if (c < ncols) {
+                        // exact in FP64: |D_g| < 2^31 and the four terms span 21 more bits
+                        double v = (double)(int)d[3][e];
+                        v = v * 0.0078125 + (double)(int)d[2][e];
+                        v = v * 0.0078125 + (double)(int)d[1][e];
+                        v = v * 0.0078125 + (double)(int)d[0][e];
+                        v *= 6.103515625e-05;               // 2^-14
+                        if (!TN) v *= rsc * cs_up[c];
+                        out[r + (int64_t)c * ldc] = v;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tc_dealloc(tmem, 512); }
+}
+
+// Z(j, c) = cs_up(c) * sum over chunks, fixed order
+__global__ void __launch_bounds__(256)
+i8_tn_reduce_kernel(const double* __restrict__ P, int nchunks, int64_t chunk_stride, int64_t n, int ncols, const double* __restrict__ cs_up,
+                    double* __restrict__ Z, int64_t ldz) {
+    const int64_t total = n * ncols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / n, j = idx - c * n;
+        double s = 0.0;
+        for (int k = 0; k < nchunks; ++k) s += P[(int64_t)k * chunk_stride + j + c * n];
+        Z[j + c * ldz] = s * cs_up[c];
+    }
+}
+
+struct Sliced {
+    const double* A = nullptr; int64_t lda = 0, m = 0, n = 0;
+    int64_t rblocks = 0, cblocks = 0, kb_total = 0, kr_total = 0;
+    DevBuf nn, tn, up, down, bits, bimg, cbits, cup, cdown;
+    bool ready = false;
+};
+Sliced g_sl;
+bool g_active = false;
+
+rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, const double* rs, int64_t kblocks) {
+    Ctx& c = ctx();
+    RNLA_CUDA(cudaMemsetAsync(g_sl.cbits.p, 0, 128 * 8, c.stream));
+    const int64_t rows_per = 32768;
+    colmax_kernel<<<dim3((unsigned)N, (unsigned)((K + rows_per - 1) / rows_per)), 256, 0, c.stream>>>(X, ldx, K, N, rs, rows_per,
+                                                                                                      g_sl.cbits.as<unsigned long long>());
+    scales_kernel<<<1, 128, 0, c.stream>>>(g_sl.cbits.as<unsigned long long>(), 128, g_sl.cup.d(), g_sl.cdown.d());
+    slice_b_kernel<<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, rs, g_sl.cdown.d(), g_sl.bimg.as<uint8_t>());
+    g_kernel_launches += 3;
+    RNLA_CUDA(cudaGetLastError());
+    return RNLA_OK;
+}
+
+}  // namespace
+
+bool i8_supported(int64_t m, int64_t n, int l) {
+    return l >= 1 && l <= BN && n >= 1 && m >= 1 && ((n + 127) / 128) * 128 <= K_ACC_MAX && m * n >= (int64_t)1 << 22;
+}
+bool i8_active_for(const double* A, int64_t lda, int64_t m, int64_t n, int64_t N) {
+    return g_active && g_sl.ready && g_sl.A == A && g_sl.lda == lda && g_sl.m == m && g_sl.n == n && N <= BN;
+}
+void i8_deactivate() { g_active = false; }
+void i8_release() { g_active = false; g_sl.ready = false; g_sl.nn.release(); g_sl.tn.release(); g_sl.bimg.release(); }
+
+// split A (m x n, lda) into the two tiled int8 images; afterwards dev_gemm_nn / dev_gemm_tn with this A and N <= 128 run on
+// the integer tensor cores until i8_deactivate()
+rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n) {
+    Ctx& c = ctx();
+    PhaseScope ph("i8:split(A)");
+    Sliced& s = g_sl;
+    s.ready = false; g_active = false;
+    s.A = A; s.lda = lda; s.m = m; s.n = n;
+    s.rblocks = (m + 127) / 128; s.cblocks = (n + 127) / 128;
+    s.kb_total = 2 * s.cblocks; s.kr_total = 2 * s.rblocks;
+    const size_t img_bytes = (size_t)s.rblocks * s.cblocks * 2 * CHUNK;
+    const int64_t kmax = std::max(s.kb_total, s.kr_total);
+    RNLA_CUDA(s.nn.alloc(img_bytes)); RNLA_CUDA(s.tn.alloc(img_bytes));
+    RNLA_CUDA(s.up.alloc((size_t)m * 8)); RNLA_CUDA(s.down.alloc((size_t)m * 8)); RNLA_CUDA(s.bits.alloc((size_t)m * 8));
+    RNLA_CUDA(s.bimg.alloc((size_t)kmax * CHUNK));
+    RNLA_CUDA(s.cbits.alloc(128 * 8)); RNLA_CUDA(s.cup.alloc(128 * 8)); RNLA_CUDA(s.cdown.alloc(128 * 8));
+    RNLA_CUDA(cudaMemsetAsync(s.bits.p, 0, (size_t)m * 8, c.stream));
+    const int64_t cols_per = std::max<int64_t>(256, (n + 7) / 8);
+    rowmax_kernel<<<dim3((unsigned)((m + 511) / 512), (unsigned)((n + cols_per - 1) / cols_per)), 256, 0, c.stream>>>(
+        A, lda, m, n, cols_per, s.bits.as<unsigned long long>());
+    scales_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(s.bits.as<unsigned long long>(), m, s.up.d(), s.down.d());
+    static bool attr = false;
+    if (!attr) {
+        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * CHUNK));
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
+        attr = true;
+    }
+    slice_a_kernel<<<(unsigned)(s.rblocks * s.cblocks), 256, 4 * CHUNK, c.stream>>>(A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total,
+                                                                                   s.tn.as<uint8_t>(), s.kr_total, s.cblocks);
+    g_kernel_launches += 3;
+    RNLA_CUDA(cudaGetLastError());
+    s.ready = true; g_active = true;
+    return RNLA_OK;
+}
+
+// C (m x N) = A * B (n x N) on the split A
+rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc) {
+    Ctx& c = ctx();
+    Sliced& s = g_sl;
+    RNLA_TRY(slice_b(B, ldb, s.n, (int)N, nullptr, s.kb_total));
+    i8_mma_kernel<false><<<dim3((unsigned)s.rblocks, 1), MMA_THREADS, MMA_SMEM, c.stream>>>(
+        s.nn.as<uint8_t>(), s.kb_total, s.bimg.as<uint8_t>(), s.kb_total, s.kb_total, C, ldc, s.m, (int)N, s.up.d(), s.cup.d(), 0);
+    ++g_kernel_launches;
+    RNLA_CUDA(cudaGetLastError());
+    return RNLA_OK;
+}
+
+// Z (n x N) = A^T * Q (m x N) on the split A (local rows only; the caller all-reduces)
+rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz) {
+    Ctx& c = ctx();
+    Sliced& s = g_sl;
+    RNLA_TRY(slice_b(Q, ldq, s.m, (int)N, s.up.d(), s.kr_total));
+    const int64_t max_per = K_ACC_MAX / 64 / 2 * 2;                      // blocks of 64 rows per accumulation
+    int64_t nchunks = std::max<int64_t>((s.kr_total + max_per - 1) / max_per, (4LL * c.sms + s.cblocks - 1) / s.cblocks);
+    nchunks = std::max<int64_t>(1, std::min<int64_t>(nchunks, s.kr_total));
+    const int64_t per = (s.kr_total + nchunks - 1) / nchunks;
+    nchunks = (s.kr_total + per - 1) / per;
+    const int64_t stride = s.n * N;
+    DevBuf P;
+    RNLA_CUDA(P.alloc((size_t)nchunks * stride * 8));
+    i8_mma_kernel<true><<<dim3((unsigned)s.cblocks, (unsigned)nchunks), MMA_THREADS, MMA_SMEM, c.stream>>>(
+        s.tn.as<uint8_t>(), s.kr_total, s.bimg.as<uint8_t>(), s.kr_total, per, P.d(), s.n, s.n, (int)N, nullptr, nullptr, stride);
+    i8_tn_reduce_kernel<<<(unsigned)std::min<int64_t>(148 * 8, (stride + 255) / 256), 256, 0, c.stream>>>(P.d(), (int)nchunks, stride, s.n, (int)N,
+                                                                                                           s.cup.d(), Z, ldz);
+    g_kernel_launches += 2;
+    RNLA_CUDA(cudaGetLastError());
+    return RNLA_OK;
+}
+
+}  // namespace rnla
