@@ -73,7 +73,7 @@ typedef struct rnla_options {
                                * 2 (default): fuse iff the n x l operand would not stay L2-resident (> 48 MiB) */
     int32_t range_passes_int8; /* 1: the range-finder passes (A Omega, A^T Y, A S: results that only have to span a subspace) run on the INT8
                                * tensor cores from a 4 x 7-bit fixed-point split of A (relative accuracy 2^-28 per product); the pass that
-                               * carries the singular values (Q^T A) stays FP64.  0 (default): every pass in FP64.  l <= 128, n <= 33280,
+                               * carries the singular values (Q^T A) stays FP64.  0 (default): every pass in FP64.  l <= 128, n <= 131072,
                                * single pass structure of rand_svd / rand_evd1 (dev_qb1).  DESIGN.md section 5c */
 } rnla_options;
 
@@ -298,7 +298,8 @@ rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double
 
 /* the integer tensor-core products behind rnla_options.range_passes_int8 (csrc/i8gemm.cu), for tests and benches: one 4 x 7-bit
  * split of A, then `reps` products.  trans = 0: C (m x N) = A B with B n x N;  trans != 0: C (n x N) = A^T B with B m x N.
- * N <= 128, n <= 33280.  Relative accuracy about 2^-28 of (row maximum of A) x (column maximum of B) per product. */
+ * N <= 128, n <= 131072.  reps < 0 (trans = 0 only): |reps| products with all 16 digit pairs (two sweeps), i.e. the exact
+ * product of the two 28-bit representations; otherwise the 10 leading pairs (accuracy about 2^-25 of row max x column max). */
 rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda, int64_t m, int64_t n, const double* dB, int64_t ldb,
                                    int64_t N, double* dC, int64_t ldc, int32_t reps);
 

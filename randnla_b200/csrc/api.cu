@@ -810,10 +810,12 @@ rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda,
                                    int64_t N, double* dC, int64_t ldc, int32_t reps) {
     RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
-    if (N < 1 || N > 128 || ((n + 127) / 128) * 128 > 33280 || m < 1 || n < 1)
-        return fail(RNLA_ERR_INVALID_DIMENSIONS, "i8 range gemm: 1 <= N <= 128, n <= 33280");
+    if (N < 1 || N > 128 || ((n + 127) / 128) * 128 > 131072 || m < 1 || n < 1)
+        return fail(RNLA_ERR_INVALID_DIMENSIONS, "i8 range gemm: 1 <= N <= 128, n <= 131072");
     phases_reset();
     RNLA_TRY(i8_prepare(dA, lda, m, n));
+    i8_set_precise(!trans && reps < 0);                    // reps < 0: A B with all 16 digit pairs (two sweeps)
+    reps = std::abs(reps);
     rnla_status st = RNLA_OK;
     for (int r = 0; r < std::max(reps, 1) && st == RNLA_OK; ++r) {
         PhaseScope ph(trans ? "i8:At*B" : "i8:A*B");

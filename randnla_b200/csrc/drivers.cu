@@ -269,7 +269,9 @@ rnla_status dev_rf1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
             RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Q, ldq));
         } else {
             if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S.d(), n, c.stream));
+            i8_set_precise(true);      // Y = A S is the product whose range becomes Q: all digit pairs (no-op on the FP64 path)
             RNLA_TRY(dev_gemm_nn(A, lda, m, n, S.d(), n, l, Q, ldq));
+            i8_set_precise(false);
         }
     }
     PhaseScope ph("orth:Y");

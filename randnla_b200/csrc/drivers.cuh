@@ -91,6 +91,7 @@ rnla_status dev_saddle_point(const double* A, int64_t lda, int64_t m, int64_t n,
 bool i8_supported(int64_t m, int64_t n, int l);
 bool i8_active_for(const double* A, int64_t lda, int64_t m, int64_t n, int64_t N);
 void i8_deactivate();
+void i8_set_precise(bool on);
 void i8_release();
 rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n);
 rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc);

@@ -3,7 +3,7 @@
 // (Y = A Omega, S = A^T Y, Y = A S; reference src/lora_helpers.rs:71-95 / :41).  The pass that determines the singular
 // values, B = Q^T A (src/lora_helpers.rs:21), stays on the FP64 DMMA kernels (gemm.cu).
 //
-//   a_ij = 2^{e_i} * sum_{t<4} d_t(i,j) 2^{-7(t+1)} + O(2^{e_i - 29}),   d_t in [-127, 127]   (e_i: exponent of the row maximum)
+//   a_ij = 2^{e_i} * sum_{t<4} d_t(i,j) 2^{-7(t+1)} + O(2^{e_i - 29}),   d_t in [-64, 64] (balanced digits)   (e_i: exponent of the row maximum)
 //
 // A is split ONCE per driver call into four int8 digit planes, stored pre-tiled as the exact shared-memory images the MMA
 // descriptors expect (8 x 16-byte core matrices, no swizzle), in two arrangements: row-block major for A S (contraction over
@@ -13,7 +13,7 @@
 // exactly in int32 into accumulator g (4 x 128 TMEM columns = all 512), and the epilogue forms sum_g D_g 2^{-7(g+2)} exactly
 // in FP64.  Products with ta + tb >= 4 are dropped: relative accuracy 2^-28 of (row max) x (column max), enough for a basis.
 //
-// Accumulation bound: 4 pairs x 127^2 x K < 2^31  =>  K <= 33280 per accumulation (A S needs n <= 33280; A^T Y is chunked).
+// Accumulation bound: 4 pairs x 64^2 x K < 2^31  =>  K <= 131072 per accumulation (A S needs n <= 131072; A^T Y is chunked).
 #include "drivers.cuh"
 #include "gemm.cuh"
 #include "panel.cuh"
@@ -33,7 +33,7 @@ constexpr int PLANE = BM * BK;              // 8 KB
 constexpr int STAGES = 3;
 constexpr int MMA_THREADS = 192;            // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
 constexpr size_t MMA_SMEM = (size_t)STAGES * 2 * CHUNK + 1024 + 256;
-constexpr int64_t K_ACC_MAX = 33280;
+constexpr int64_t K_ACC_MAX = 131072;      // 4 pairs x 64^2 x K < 2^31
 
 // ---------------------------------------------------------------------------------------------- tcgen05 wrappers
 __device__ __forceinline__ void tc_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -76,23 +76,24 @@ __host__ __device__ constexpr uint32_t instr_desc(bool a_mn_major, bool b_mn_maj
 }
 
 // ---------------------------------------------------------------------------------------------- splitting
-// |x| * scale -> 28-bit magnitude -> four signed 7-bit digits, most significant first
+// x * scale (|.| < 2^27) -> nearest integer v -> four BALANCED 7-bit digits, most significant first:
+// v = d0 2^21 + d1 2^14 + d2 2^7 + d3 with d1..d3 in [-64, 63] and |d0| <= 64.  Balanced digits halve the typical digit and
+// make the dropped cross terms zero-mean.
 __device__ __forceinline__ void digits4(double x, double scale, int (&d)[4]) {
-    const double ax = fabs(x) * scale;
-    unsigned v = __double2uint_rn(ax);
-    v = min(v, (1u << 28) - 1u);
-    const int s = x < 0.0 ? -1 : 1;
-    d[0] = s * (int)(v >> 21);
-    d[1] = s * (int)((v >> 14) & 127u);
-    d[2] = s * (int)((v >> 7) & 127u);
-    d[3] = s * (int)(v & 127u);
+    int v = __double2int_rn(x * scale);
+    v = max(-(1 << 27) + 1, min((1 << 27) - 1, v));
+    d[3] = ((v + 64) & 127) - 64; v = (v - d[3]) >> 7;
+    d[2] = ((v + 64) & 127) - 64; v = (v - d[2]) >> 7;
+    d[1] = ((v + 64) & 127) - 64; v = (v - d[1]) >> 7;
+    d[0] = v;
 }
-// exponent bookkeeping from the bit pattern of a maximum: up = 2^e with max < 2^e, down = 2^(28 - e); zero / tiny rows -> 0
+// exponent bookkeeping from the bit pattern of a maximum: up = 2^(e+1) with max < 2^e, down = 2^(28 - (e+1)), so that
+// |x * down| < 2^27; zero / tiny rows -> 0
 __device__ __forceinline__ void scales_from_max_bits(unsigned long long bits, double* up, double* down) {
     const int E = (int)(bits >> 52) & 0x7ff;
-    if (E < 64 || E >= 2046) { *up = 0.0; *down = 0.0; return; }
-    *up = __longlong_as_double((long long)(E + 1) << 52);
-    *down = __longlong_as_double((long long)(2073 - E) << 52);
+    if (E < 64 || E >= 2045) { *up = 0.0; *down = 0.0; return; }
+    *up = __longlong_as_double((long long)(E + 2) << 52);
+    *down = __longlong_as_double((long long)(2072 - E) << 52);
 }
 
 __global__ void __launch_bounds__(256)
@@ -124,60 +125,77 @@ __global__ void scales_kernel(const unsigned long long* __restrict__ bits, int64
     if (i < cnt) scales_from_max_bits(bits[i], up + i, down + i);
 }
 
-// One CTA per 128 x 128 block of A: two row-major-arranged images (NN: [plane][J 8][I 8][8 x 16 B], one per 64 columns) and two
-// column-major-arranged ones (TN: [plane][J 16][I 4][8 x 16 B], one per 64 rows).  A core matrix holds 16 rows x 8 columns of
-// A as 8 rows (columns of A) of 16 bytes (rows of A): the same 128 bytes serve as an MN-major core matrix of A S and as a
-// K-major one of A^T Y.
-__global__ void __launch_bounds__(256)
+// One CTA per 128 x 64 block of A (three resident CTAs per SM: while one forms digits the others keep loads in flight).  It
+// writes one complete row-block-major image (NN: [plane][J 8][I 8][8 x 16 B]) and, for each of its two 64-row halves, the matching
+// half (8 of 16 column groups) of a column-block-major image (TN: [plane][J 16][I 4][8 x 16 B]).  A core matrix holds 16 rows x 8
+// columns of A as 8 rows (columns of A) of 16 bytes (rows of A): the same 128 bytes serve as an MN-major core matrix of A S and
+// as a K-major one of A^T Y.
+// staging-buffer swizzle (the 16-byte row inside a core matrix is XORed with the index of the core matrix): lanes that write
+// the same row of neighbouring core matrices hit different banks; undone by the copy-out
+__device__ __forceinline__ int stage_swz(int off) { return off ^ (((off >> 7) & 7) << 4); }
+
+__global__ void __launch_bounds__(256, 3)
 slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, const double* __restrict__ down,
-               uint8_t* __restrict__ nn, int64_t kb_total, uint8_t* __restrict__ tn, int64_t kr_total, int64_t cblocks) {
-    extern __shared__ __align__(16) uint8_t img[];          // [0, 64K): NN images of the two column halves; [64K, 128K): TN images of the two row halves
+               uint8_t* __restrict__ nn, int64_t kb_total, uint8_t* __restrict__ tn, int64_t kr_total) {
+    extern __shared__ __align__(16) uint8_t img[];          // [0, 32K): NN image; [32K, 64K): TN pieces [half][plane][J 8][I 4][128 B]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t rb = blockIdx.x / cblocks, cb = blockIdx.x % cblocks;
-    const int64_t R0 = rb * 128, C0 = cb * 128;
+    const int64_t rb = blockIdx.x / kb_total, kb = blockIdx.x % kb_total;
+    const int64_t R0 = rb * 128, C0 = kb * 64;
     const bool vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0);
-#pragma unroll 1
+    double x0[16], x1[16], sc0[2], sc1[2];
+    // all 16 loads of the thread are in flight before the first digit is formed
+#pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int il = 64 * h + 2 * lane;                   // local rows il, il + 1
-        const int64_t i = R0 + il;
-        const double s0 = i < m ? down[i] : 0.0, s1 = i + 1 < m ? down[i + 1] : 0.0;
-#pragma unroll 4
-        for (int r = 0; r < 16; ++r) {
-            const int jl = warp + 8 * r;
-            const int64_t j = C0 + jl;
-            double x0 = 0.0, x1 = 0.0;
+        const int64_t i = R0 + 64 * h + 2 * lane;
+        sc0[h] = i < m ? down[i] : 0.0; sc1[h] = i + 1 < m ? down[i + 1] : 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int64_t j = C0 + warp + 8 * r;
+            double a0 = 0.0, a1 = 0.0;
             if (j < n) {
                 if (vec && i + 1 < m) {
-                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "l"(A + i + j * lda));
+                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(a0), "=d"(a1) : "l"(A + i + j * lda));
                 } else {
-                    if (i < m) x0 = ldg_stream(A + i + j * lda);
-                    if (i + 1 < m) x1 = ldg_stream(A + i + 1 + j * lda);
+                    if (i < m) a0 = ldg_stream(A + i + j * lda);
+                    if (i + 1 < m) a1 = ldg_stream(A + i + 1 + j * lda);
                 }
             }
+            x0[h * 8 + r] = a0; x1[h * 8 + r] = a1;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int il = 64 * h + 2 * lane;                   // local rows il, il + 1
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int jl = warp + 8 * r;
             int d0[4], d1[4];
-            digits4(x0, s0, d0); digits4(x1, s1, d1);
+            digits4(x0[h * 8 + r], sc0[h], d0); digits4(x1[h * 8 + r], sc1[h], d1);
 #pragma unroll
             for (int t = 0; t < PL; ++t) {
                 const unsigned half = ((unsigned)d0[t] & 0xffu) | (((unsigned)d1[t] & 0xffu) << 8);
                 const unsigned other = __shfl_xor_sync(0xffffffffu, half, 1);
                 if ((lane & 1) == 0) {
                     const unsigned word = half | (other << 16);             // rows il .. il + 3
-                    const int jj = jl & 63;
-                    const int off_nn = (jl >> 6) * CHUNK + t * PLANE + (jj >> 3) * 1024 + (il >> 4) * 128 + (jj & 7) * 16 + (il & 15);
+                    const int off_nn = t * PLANE + (jl >> 3) * 1024 + (il >> 4) * 128 + (jl & 7) * 16 + (il & 15);
                     const int i64 = il & 63;
-                    const int off_tn = 2 * CHUNK + h * CHUNK + t * PLANE + (jl >> 3) * 512 + (i64 >> 4) * 128 + (jl & 7) * 16 + (i64 & 15);
-                    *reinterpret_cast<unsigned*>(img + off_nn) = word;
-                    *reinterpret_cast<unsigned*>(img + off_tn) = word;
+                    const int off_tn = CHUNK + h * (CHUNK / 2) + t * (PLANE / 2) + (jl >> 3) * 512 + (i64 >> 4) * 128 + (jl & 7) * 16 + (i64 & 15);
+                    *reinterpret_cast<unsigned*>(img + stage_swz(off_nn)) = word;
+                    *reinterpret_cast<unsigned*>(img + stage_swz(off_tn)) = word;
                 }
             }
         }
     }
     __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(img);
-    uint4* dnn0 = reinterpret_cast<uint4*>(nn + (rb * kb_total + 2 * cb) * (int64_t)CHUNK);            // two consecutive column halves
-    uint4* dtn0 = reinterpret_cast<uint4*>(tn + (cb * kr_total + 2 * rb) * (int64_t)CHUNK);            // two consecutive row halves
-    for (int q = threadIdx.x; q < 2 * CHUNK / 16; q += 256) dnn0[q] = src[q];
-    for (int q = threadIdx.x; q < 2 * CHUNK / 16; q += 256) dtn0[q] = src[2 * CHUNK / 16 + q];
+    uint4* dnn = reinterpret_cast<uint4*>(nn + (rb * kb_total + kb) * (int64_t)CHUNK);
+    for (int q = threadIdx.x; q < CHUNK / 16; q += 256) dnn[q] = src[stage_swz(q * 16) >> 4];
+    // TN: block (cb = kb / 2, kr = 2 rb + h); this CTA owns column groups J = 8 (kb & 1) .. + 7 of every plane: 4 KB per plane
+    for (int q = threadIdx.x; q < CHUNK / 16; q += 256) {
+        const int h = q >> 10, t = (q >> 8) & 3, w = q & 255;              // 1024 uint4 per half, 256 per plane piece
+        uint4* dst = reinterpret_cast<uint4*>(tn + ((kb >> 1) * kr_total + 2 * rb + h) * (int64_t)CHUNK + t * PLANE + (kb & 1) * (PLANE / 2));
+        dst[w] = src[stage_swz(CHUNK + q * 16) >> 4];
+    }
 }
 
 // per-column maxima of X (K x N), optionally with the row scale folded in (X(k, c) * rs[k])
@@ -226,7 +244,9 @@ slice_b_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, cons
 // ---------------------------------------------------------------------------------------------- the MMA kernel
 // TN = false:  C(rows rb*128.., :) = rs_up(i) cs_up(c) * sum_g 2^{-7(g+2)} D_g,   contraction over all kb blocks of 64 columns
 // TN = true :  P[chunk](cols cb*128.., :) = sum_g 2^{-7(g+2)} D_g,                contraction over this chunk's blocks of 64 rows
-template <bool TN>
+// HI = true: second sweep of A S, digit pairs with ta + tb in {4, 5, 6} into accumulators 0..2, ADDED to C: together with the
+// first sweep all 16 pairs, i.e. the exact product of the two 28-bit representations.
+template <bool TN, bool HI>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 i8_mma_kernel(const uint8_t* __restrict__ Aimg, int64_t a_blocks_per_tile, const uint8_t* __restrict__ Bimg, int64_t kblocks_total,
               int64_t kblocks_per_chunk, double* __restrict__ C, int64_t ldc, int64_t rows, int ncols, const double* __restrict__ rs_up,
@@ -280,14 +300,18 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int64_t a_blocks_per_tile, const
 #pragma unroll
                     for (int ta = 0; ta < PL; ++ta) {
 #pragma unroll
-                        for (int tb = 0; tb + ta < PL; ++tb) {
+                        for (int tb = 0; tb < PL; ++tb) {
+                            constexpr int G0 = HI ? 4 : 0;
+                            const int g = ta + tb;
+                            if (g < G0 || g >= G0 + 4) continue;
                             // A S: MN-major core matrices, 16-row blocks 128 B apart (SBO), 8-column groups 1024 B apart (LBO), 32 columns = 4096 B
                             // A^T Y: K-major, 8-column blocks 512 B apart (SBO), the two 16-row halves 128 B apart (LBO), 32 rows = 256 B
                             const uint64_t ad = TN ? smem_desc(a_base + ta * PLANE + ks * 256, 128, 512)
                                                    : smem_desc(a_base + ta * PLANE + ks * 4096, 1024, 128);
                             const uint64_t bd = smem_desc(b_base + tb * PLANE + ks * 4096, 1024, 128);
-                            const uint32_t acc = (it > 0 || ks > 0 || ta > 0) ? 1u : 0u;      // first pair of group g = tb is (0, g)
-                            tc_mma_i8(tmem + (uint32_t)(ta + tb) * BN, ad, bd, idesc, acc);
+                            const int ta_first = g > PL - 1 ? g - (PL - 1) : 0;                // first pair of group g in this loop order
+                            const uint32_t acc = (it > 0 || ks > 0 || ta > ta_first) ? 1u : 0u;
+                            tc_mma_i8(tmem + (uint32_t)(g - G0) * BN, ad, bd, idesc, acc);
                         }
                     }
                 }
@@ -305,7 +329,7 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int64_t a_blocks_per_tile, const
         for (int c0 = 0; c0 < ncols; c0 += 16) {
             uint32_t d[PL][16];
 #pragma unroll
-            for (int g = 0; g < PL; ++g) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * BN + c0), d[g]);
+            for (int g = 0; g < (HI ? 3 : PL); ++g) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * BN + c0), d[g]);
             tc_wait_ld();
             if (r < rows) {
 #pragma unroll
@@ -313,13 +337,22 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int64_t a_blocks_per_tile, const
                     const int c = c0 + e;
                     if (c < ncols) {
                         // exact in FP64: |D_g| < 2^31 and the four terms span 21 more bits
-                        double v = (double)(int)d[3][e];
-                        v = v * 0.0078125 + (double)(int)d[2][e];
-                        v = v * 0.0078125 + (double)(int)d[1][e];
-                        v = v * 0.0078125 + (double)(int)d[0][e];
-                        v *= 6.103515625e-05;               // 2^-14
-                        if (!TN) v *= rsc * cs_up[c];
-                        out[r + (int64_t)c * ldc] = v;
+                        double v;
+                        if (HI) {
+                            v = (double)(int)d[2][e];
+                            v = v * 0.0078125 + (double)(int)d[1][e];
+                            v = v * 0.0078125 + (double)(int)d[0][e];
+                            v *= 2.2737367544323206e-13;        // 2^-42: groups 4, 5, 6
+                            out[r + (int64_t)c * ldc] += v * (rsc * cs_up[c]);
+                        } else {
+                            v = (double)(int)d[3][e];
+                            v = v * 0.0078125 + (double)(int)d[2][e];
+                            v = v * 0.0078125 + (double)(int)d[1][e];
+                            v = v * 0.0078125 + (double)(int)d[0][e];
+                            v *= 6.103515625e-05;               // 2^-14
+                            if (!TN) v *= rsc * cs_up[c];
+                            out[r + (int64_t)c * ldc] = v;
+                        }
                     }
                 }
             }
@@ -351,6 +384,7 @@ struct Sliced {
 };
 Sliced g_sl;
 bool g_active = false;
+bool g_precise = false;       // A S with all 16 digit pairs (two sweeps)
 
 rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, const double* rs, int64_t kblocks) {
     Ctx& c = ctx();
@@ -373,14 +407,14 @@ bool i8_supported(int64_t m, int64_t n, int l) {
 bool i8_active_for(const double* A, int64_t lda, int64_t m, int64_t n, int64_t N) {
     return g_active && g_sl.ready && g_sl.A == A && g_sl.lda == lda && g_sl.m == m && g_sl.n == n && N <= BN;
 }
-void i8_deactivate() { g_active = false; }
+void i8_deactivate() { g_active = false; g_precise = false; }
+void i8_set_precise(bool on) { g_precise = on; }
 void i8_release() { g_active = false; g_sl.ready = false; g_sl.nn.release(); g_sl.tn.release(); g_sl.bimg.release(); }
 
 // split A (m x n, lda) into the two tiled int8 images; afterwards dev_gemm_nn / dev_gemm_tn with this A and N <= 128 run on
 // the integer tensor cores until i8_deactivate()
 rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n) {
     Ctx& c = ctx();
-    PhaseScope ph("i8:split(A)");
     Sliced& s = g_sl;
     s.ready = false; g_active = false;
     s.A = A; s.lda = lda; s.m = m; s.n = n;
@@ -392,20 +426,24 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n) {
     RNLA_CUDA(s.up.alloc((size_t)m * 8)); RNLA_CUDA(s.down.alloc((size_t)m * 8)); RNLA_CUDA(s.bits.alloc((size_t)m * 8));
     RNLA_CUDA(s.bimg.alloc((size_t)kmax * CHUNK));
     RNLA_CUDA(s.cbits.alloc(128 * 8)); RNLA_CUDA(s.cup.alloc(128 * 8)); RNLA_CUDA(s.cdown.alloc(128 * 8));
+    phase_begin("i8:rowmax(A)");
     RNLA_CUDA(cudaMemsetAsync(s.bits.p, 0, (size_t)m * 8, c.stream));
     const int64_t cols_per = std::max<int64_t>(256, (n + 7) / 8);
     rowmax_kernel<<<dim3((unsigned)((m + 511) / 512), (unsigned)((n + cols_per - 1) / cols_per)), 256, 0, c.stream>>>(
         A, lda, m, n, cols_per, s.bits.as<unsigned long long>());
     scales_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(s.bits.as<unsigned long long>(), m, s.up.d(), s.down.d());
+    phase_end();
+    PhaseScope ph("i8:split(A)");
     static bool attr = false;
     if (!attr) {
-        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * CHUNK));
-        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
-        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
+        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CHUNK));
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
         attr = true;
     }
-    slice_a_kernel<<<(unsigned)(s.rblocks * s.cblocks), 256, 4 * CHUNK, c.stream>>>(A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total,
-                                                                                   s.tn.as<uint8_t>(), s.kr_total, s.cblocks);
+    slice_a_kernel<<<(unsigned)(s.rblocks * s.kb_total), 256, 2 * CHUNK, c.stream>>>(A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total,
+                                                                                    s.tn.as<uint8_t>(), s.kr_total);
     g_kernel_launches += 3;
     RNLA_CUDA(cudaGetLastError());
     s.ready = true; g_active = true;
@@ -417,9 +455,15 @@ rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64
     Ctx& c = ctx();
     Sliced& s = g_sl;
     RNLA_TRY(slice_b(B, ldb, s.n, (int)N, nullptr, s.kb_total));
-    i8_mma_kernel<false><<<dim3((unsigned)s.rblocks, 1), MMA_THREADS, MMA_SMEM, c.stream>>>(
+    i8_mma_kernel<false, false><<<dim3((unsigned)s.rblocks, 1), MMA_THREADS, MMA_SMEM, c.stream>>>(
         s.nn.as<uint8_t>(), s.kb_total, s.bimg.as<uint8_t>(), s.kb_total, s.kb_total, C, ldc, s.m, (int)N, s.up.d(), s.cup.d(), 0);
     ++g_kernel_launches;
+    if (g_precise) {
+        // second sweep over the same images: the digit pairs the first one dropped
+        i8_mma_kernel<false, true><<<dim3((unsigned)s.rblocks, 1), MMA_THREADS, MMA_SMEM, c.stream>>>(
+            s.nn.as<uint8_t>(), s.kb_total, s.bimg.as<uint8_t>(), s.kb_total, s.kb_total, C, ldc, s.m, (int)N, s.up.d(), s.cup.d(), 0);
+        ++g_kernel_launches;
+    }
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;
 }
@@ -437,7 +481,7 @@ rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64
     const int64_t stride = s.n * N;
     DevBuf P;
     RNLA_CUDA(P.alloc((size_t)nchunks * stride * 8));
-    i8_mma_kernel<true><<<dim3((unsigned)s.cblocks, (unsigned)nchunks), MMA_THREADS, MMA_SMEM, c.stream>>>(
+    i8_mma_kernel<true, false><<<dim3((unsigned)s.cblocks, (unsigned)nchunks), MMA_THREADS, MMA_SMEM, c.stream>>>(
         s.tn.as<uint8_t>(), s.kr_total, s.bimg.as<uint8_t>(), s.kr_total, per, P.d(), s.n, s.n, (int)N, nullptr, nullptr, stride);
     i8_tn_reduce_kernel<<<(unsigned)std::min<int64_t>(148 * 8, (stride + 255) / 256), 256, 0, c.stream>>>(P.d(), (int)nchunks, stride, s.n, (int)N,
                                                                                                            s.cup.d(), Z, ldz);
