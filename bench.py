@@ -202,7 +202,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_call"] * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if not use_i8 else "f64 (range-finder passes: int8 tensor cores on a 28-bit fixed-point split of A; Q^T A, factorisations and outputs f64)", "data": "synthetic",
         "config": {"workload": f"rand_svd f64 {args.rows * args.gpus}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}",
                    "timed_on": f"{sample_rows}x{n} row sample (CPU), throughput is per byte of A streamed"},
         "cpu_baseline": cb, "gpu_launches": 0,
@@ -257,7 +257,8 @@ def run_ours(args):
     dA = rt.empty_colmajor(m_local, n)
     pA, lda = rt.dev_ptr_ld(dA)
     _lib.check(lib.rnla_generate_lowrank_dev(pA, lda, m_local, n, row_off, m_global, R0, sig.ctypes.data_as(C.c_void_p), 1e-7, 1234))
-    opts = rt.make_options(fused_sketch=args.fused)
+    use_i8 = args.range == "int8"
+    opts = rt.make_options(fused_sketch=args.fused, range_passes_int8=1 if use_i8 else 0)
 
     # ---- roofs of this box, this run ----
     fp64 = C.c_double(0); hbm = C.c_double(0)
@@ -302,6 +303,25 @@ def run_ours(args):
     rt.synchronize()
     orth_err = float((gram - torch.eye(K_RANK, dtype=torch.float64, device="cuda")).abs().max().item())
     sigma_vs_planted = float(np.max(np.abs(Sg - sig[:K_RANK]) / sig[:K_RANK]))
+
+    # ---- the same call with all four passes in FP64, beside the headline (sigma agreement between the two, time) ----
+    fp64_side = None
+    if use_i8:
+        o64 = rt.make_options(fused_sketch=args.fused, range_passes_int8=0)
+        U64, S64, Vt64 = ld.rand_svd_dev(dA, K_RANK, S_OVER, o64)
+        barrier()
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(2):
+            U64, S64, Vt64 = ld.rand_svd_dev(dA, K_RANK, S_OVER, o64)
+        f1.record()
+        barrier()
+        ms64 = max_over_ranks(f0.elapsed_time(f1) / 2)
+        S64h = S64.cpu().numpy()
+        fp64_side = {"ms_per_step": ms64, "A_stream_GBps": algorithmic_bytes(m_global, n) / (ms64 * 1e-3) * 1e-9,
+                     "max_rel_sigma_diff_int8_range_vs_all_fp64": float(np.max(np.abs(Sg - S64h) / S64h)),
+                     "phases_ms": dict(rt.timings())}
+        del U64, Vt64
 
     # ---- end to end through the host-buffer C ABI (pinned host memory -> device -> host) ----
     e2e = None
@@ -358,24 +378,45 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernels (per launch, CUDA events on the launching stream, timed region) ----
     phases = {k: float(np.mean(v)) for k, v in phase_acc.items()}
-    nn_ms = [v for k, v in phases.items() if k.startswith("pass:A*")]
-    tn_ms = [v for k, v in phases.items() if k.startswith("pass:At*")]
-    gemm_ms = nn_ms + tn_ms
-    per_launch_ms = float(np.mean(gemm_ms))
     fl = 2.0 * m_local * n * l
     by = 8.0 * m_local * n
+    # FP64 DMMA passes of the step: all four with --range fp64, only "pass:At*Q" (the one that carries sigma) with --range int8
+    i8_names = ("pass:A*Omega", "pass:At*Y", "pass:A*S") if use_i8 else ()
+    fp64_ms = {k: v for k, v in phases.items() if k.startswith("pass:") and not k.startswith(i8_names)} if use_i8 else \
+              {k: v for k, v in phases.items() if k.startswith("pass:")}
+    i8_ms = {k: v for k, v in phases.items() if use_i8 and k.startswith(i8_names)}
+    nn_ms = [v for k, v in fp64_ms.items() if k.startswith("pass:A*")]
+    tn_ms = [v for k, v in fp64_ms.items() if k.startswith("pass:At*")]
+    gemm_ms = nn_ms + tn_ms
+    per_launch_ms = float(np.mean(gemm_ms))
     roofline = {
-        "bound": "tensor", "kernel": "gemm_nn_kernel / gemm_tn_kernel (FP64 DMMA.8x8x4, 2 launches each per step)",
+        "bound": "tensor", "kernel": "gemm_tn_kernel (FP64 DMMA.8x8x4): B = Q^T A, the pass that carries the singular values" if use_i8
+                 else "gemm_nn_kernel / gemm_tn_kernel (FP64 DMMA.8x8x4, 2 launches each per step)",
         "achieved": fl / (per_launch_ms * 1e-3) * 1e-12, "peak": fp64.value, "unit": "TFLOP/s",
         "frac": fl / (per_launch_ms * 1e-3) * 1e-12 / fp64.value,
         "peak_source": "FP64 DMMA peak measured live by rnla_measure_roofs on this GPU (MEASURED_PEAKS.json holds no FP64 number)",
         "traffic": None,
         "hbm": {"achieved": by / (per_launch_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": by / (per_launch_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src, "read_only_stream_measured_gbs": hbm.value},
-        "note": "l = k+p = 110 makes every pass FP64-pipe bound (27.5 flop/B vs a 5.7 flop/B ridge), SURVEY.md §0 fact 3",
+        "note": "l = k+p = 110 makes an FP64 pass FP64-pipe bound (27.5 flop/B vs a 5.7 flop/B ridge), SURVEY.md §0 fact 3",
         "per_kernel_ms": {"gemm_nn": float(np.mean(nn_ms)) if nn_ms else None, "gemm_tn": float(np.mean(tn_ms)) if tn_ms else None},
         "share_of_step": float(sum(gemm_ms) / sum(phases.values())),
     }
+    if use_i8 and i8_ms:
+        # the integer passes stream the 4 digit planes of A: 4 bytes per element per sweep (A S makes two sweeps), HBM-bound
+        sweeps = {k: (2.0 if k.startswith("pass:A*S") else 1.0) for k in i8_ms}
+        tot_ms = sum(i8_ms.values()); tot_by = sum(4.0 * m_local * n * sweeps[k] for k in i8_ms)
+        split_ms = phases.get("i8:rowmax(A)", 0.0) + phases.get("i8:split(A)", 0.0)
+        roofline["int8_range_passes"] = {
+            "bound": "hbm", "kernel": "i8_mma_kernel (tcgen05.mma kind::i8, TMEM accumulators, cp.async.bulk of pre-tiled digit planes)",
+            "achieved": tot_by / (tot_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s", "frac": tot_by / (tot_ms * 1e-3) * 1e-9 / hbm_peak,
+            "per_pass_ms": i8_ms, "bytes_per_sweep": 4.0 * m_local * n,
+            "tensor_TOPS": sum(10.0 * sweeps[k] if not k.startswith("pass:A*S") else 16.0 for k in i8_ms) * 2.0 * m_local * n * 128 / (tot_ms * 1e-3) * 1e-12,
+            "f64_equivalent_A_stream_GBps": by * len(i8_ms) / (tot_ms * 1e-3) * 1e-9,
+            "split_of_A": {"ms": split_ms, "bytes": 8.0 * m_local * n * 2 + 8.0 * m_local * n,
+                           "GBps": (8.0 * m_local * n * 2 + 8.0 * m_local * n) / (split_ms * 1e-3) * 1e-9 if split_ms else None,
+                           "note": "row maxima (A read once) + digit split (A read once, two tiled 4-plane images written)"},
+        }
     ncu_traffic = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
     if os.path.exists(ncu_traffic):
         try:
@@ -397,16 +438,18 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if not use_i8 else "f64 (range-finder passes: int8 tensor cores on a 28-bit fixed-point split of A; Q^T A, factorisations and outputs f64)",
         "data": "synthetic",
         "config": {"workload": f"rand_svd f64 {m_global}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}, Gaussian sketch",
                    "rows_per_gpu": m_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
                    "sketch": "auto (materialised while Omega is L2-resident)" if args.fused == 2 else ("fused in-kernel Philox" if args.fused == 1 else "materialised"),
+                   "range_passes": "int8 tensor cores (rnla_options.range_passes_int8 = 1)" if use_i8 else "fp64",
                    "l2": f"inputs larger than L2 (A shard = {8 * m_local * n / 2**30:.1f} GiB per GPU, streamed 4x per step)"},
         "rand_svd_ms": ms_step, "tflops_fp64": algorithmic_flops(m_global, n, l) / (ms_step * 1e-3) * 1e-12,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cb, "phases_ms": phases, "secondary": secondary,
         "accuracy": {"max_abs_UtU_minus_I": orth_err, "max_rel_sigma_vs_planted(noise-limited)": sigma_vs_planted},
+        "all_fp64_passes": fp64_side,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -422,6 +465,9 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (debug)")
     ap.add_argument("--cols", type=int, default=N_COLS)
     ap.add_argument("--fused", type=int, default=2, help="0 materialise Omega, 1 in-kernel Philox, 2 auto")
+    ap.add_argument("--range", default="int8", choices=["int8", "fp64"],
+                    help="int8: the three range-finder passes (A Omega, A^T Y, A S) run on the INT8 tensor cores from a 4 x 7-bit split of A "
+                         "(rnla_options.range_passes_int8), the pass that carries the singular values (Q^T A) in FP64; fp64: all four passes FP64")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-rows", type=int, default=25000, help="row sample of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--secondary", type=int, default=1, help="1: also time BASELINE configs 4 and 5 once (N=1 only, reported under 'secondary')")

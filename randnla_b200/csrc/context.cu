@@ -33,6 +33,8 @@ static void default_opts(rnla_options* o) {
     o->num_passes = 0;
     o->passes_per_stab = 0;
     o->fused_sketch = 2;
+    const char* r8 = getenv("RNLA_RANGE_INT8");
+    if (r8 && !strcmp(r8, "1")) o->range_passes_int8 = 1;
     const char* m = getenv("RNLA_MODE");
     if (m && (!strcmp(m, "literal") || !strcmp(m, "LITERAL") || !strcmp(m, "1"))) o->mode = RNLA_MODE_LITERAL;
 }

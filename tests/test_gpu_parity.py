@@ -823,3 +823,68 @@ def test_c5_full_size_properties(rb):
     assert float(torch.linalg.matrix_norm(R)) < 1e-4 * float(lam[0])                  # the 1e-4 tail leaks into the trailing vectors
     del dA, V0, Vs, V0t
     torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------- range-finder passes on the INT8 tensor cores (csrc/i8gemm.cu)
+@pytest.mark.parametrize("trans,m,n,N,precise", [(0, 128, 64, 128, False), (0, 300, 200, 110, False), (0, 300, 200, 110, True),
+                                                 (1, 300, 200, 110, False), (0, 4100, 1030, 7, True), (1, 70001, 515, 60, False),
+                                                 (0, 2000, 40000, 33, False)])
+def test_i8_range_gemm_accuracy(rb, trans, m, n, N, precise):
+    """tcgen05 kind::i8 products of a 4 x 7-bit fixed-point split against torch FP64: the error is bounded relative to
+    (row maximum of A) x (column maximum of B) x K, i.e. componentwise against |A| |B| it stays at the 2^-25 (ten leading digit
+    pairs) / 2^-28 (all sixteen) level; ragged sizes, rows scaled over 12 decades, a zero row and a zero column included"""
+    import torch
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(m + 3 * n + N)
+    A = rt.empty_colmajor(m, n); A.copy_(torch.randn((m, n), generator=g, device="cuda", dtype=torch.float64))
+    A.mul_(torch.logspace(-6, 6, m, dtype=torch.float64, device="cuda").reshape(-1, 1))
+    A[m // 2, :] = 0.0
+    kb = m if trans else n
+    B = rt.empty_colmajor(kb, N); B.copy_(torch.randn((kb, N), generator=g, device="cuda", dtype=torch.float64))
+    B[:, N - 1] = 0.0
+    Cm = rt.empty_colmajor(n if trans else m, N); Cm.fill_(float("nan"))
+    pa, lda = rt.dev_ptr_ld(A); pb, ldb = rt.dev_ptr_ld(B); pc, ldc = rt.dev_ptr_ld(Cm)
+    torch.cuda.synchronize()
+    _lib.check(lib.rnla_i8_range_gemm_dev(trans, pa, lda, m, n, pb, ldb, N, pc, ldc, -1 if precise else 1))
+    torch.cuda.synchronize()
+    assert torch.isfinite(Cm).all()
+    if trans:
+        ref = A.t() @ B
+        bound = (A.abs().max(dim=1).values.reshape(-1, 1) * B.abs()).max(dim=0).values.reshape(1, -1) * m     # folded row scale
+        err = ((Cm - ref).abs() / bound.clamp_min(1e-300)).max()
+    else:
+        ref = A @ B
+        bound = A.abs().max(dim=1).values.reshape(-1, 1) * B.abs().max(dim=0).values.reshape(1, -1) * n
+        err = ((Cm - ref).abs() / bound.clamp_min(1e-300)).max()
+    assert float(err) < (2.0 ** -27 if precise else 2.0 ** -24)
+    assert float((Cm - ref).norm() / ref.norm()) < (1e-7 if precise else 1e-6)
+    assert float(Cm[:, N - 1].abs().max()) == 0.0
+    if not trans:
+        assert float(Cm[m // 2].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("m,n,k,s", [(6000, 1500, 20, 10), (3000, 4000, 30, 6), (9000, 1200, 25, 8)])
+def test_rand_svd_int8_range_passes_match_the_oracle(rb, orc, m, n, k, s):
+    """rnla_options.range_passes_int8: A Omega, A^T Y and A S on the integer tensor cores, Q^T A in FP64.  The singular values
+    still agree with the all-FP64 oracle to the north_star tolerance (the range only has to capture the dominant subspace), U is
+    orthonormal, and the library really took the integer path (its phases are in the timings)."""
+    from randnla_b200 import runtime as rt, lora_drivers as ld
+    A, sig = lowrank_plus_noise(m, n, seed=m % 97, k=k)
+    with rt.options(range_passes_int8=1):
+        U, S, Vt = ld.rand_svd(A, k, 1e-6, s)
+        names = [nm for nm, _ in rt.timings()]
+    assert "i8:split(A)" in names and "pass:At*Q" in names
+    Uo, So, Vto = orc.rand_svd(A, k, 1e-6, s, orc.make_opts(mode=0))
+    sg, so = np.diag(S), np.diag(So)
+    assert np.max(np.abs(sg - so) / so) < SIG_TOL
+    assert np.abs(U.T @ U - np.eye(k)).max() < 1e-12
+    assert np.linalg.norm(U @ S @ Vt - A) <= np.linalg.norm(Uo @ So @ Vto - A) * (1 + 1e-6) + 1e-12 * np.linalg.norm(A)
+    assert subspace_angle(np.linalg.qr(U)[0], np.linalg.qr(Uo)[0]) < 1e-4
+    # off by default, and small inputs keep the FP64 path even when it is on
+    U2, S2, Vt2 = ld.rand_svd(A, k, 1e-6, s)
+    assert "i8:split(A)" not in [nm for nm, _ in rt.timings()]
+    assert np.max(np.abs(np.diag(S2) - so) / so) < SIG_TOL
+    with rt.options(range_passes_int8=1):
+        ld.rand_svd(random_matrix(300, 200, seed=1), 10, 1e-6, 5)
+        assert "i8:split(A)" not in [nm for nm, _ in rt.timings()]
