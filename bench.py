@@ -202,7 +202,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_call"] * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if not use_i8 else "f64 (range-finder passes: int8 tensor cores on a 28-bit fixed-point split of A; Q^T A, factorisations and outputs f64)", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": ["f64", "f64 (range-finder passes: int8 tensor cores on a 28-bit fixed-point split of A; Q^T A, factorisations and outputs f64)",
+                                        "f64 results; every pass over A on the int8 tensor cores with exact int32 accumulation: 28-bit balanced-digit split for the "
+                                        "range-finder passes, 49-bit split (28 digit pairs) for Q^T A; factorisations, small products and outputs f64"][i8_level], "data": "synthetic",
         "config": {"workload": f"rand_svd f64 {args.rows * args.gpus}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}",
                    "timed_on": f"{sample_rows}x{n} row sample (CPU), throughput is per byte of A streamed"},
         "cpu_baseline": cb, "gpu_launches": 0,
@@ -257,8 +259,9 @@ def run_ours(args):
     dA = rt.empty_colmajor(m_local, n)
     pA, lda = rt.dev_ptr_ld(dA)
     _lib.check(lib.rnla_generate_lowrank_dev(pA, lda, m_local, n, row_off, m_global, R0, sig.ctypes.data_as(C.c_void_p), 1e-7, 1234))
-    use_i8 = args.range == "int8"
-    opts = rt.make_options(fused_sketch=args.fused, range_passes_int8=1 if use_i8 else 0)
+    use_i8 = args.range != "fp64"
+    i8_level = {"fp64": 0, "int8": 1, "int8-all": 2}[args.range]
+    opts = rt.make_options(fused_sketch=args.fused, range_passes_int8=i8_level)
 
     # ---- roofs of this box, this run ----
     fp64 = C.c_double(0); hbm = C.c_double(0)
@@ -307,21 +310,23 @@ def run_ours(args):
     # ---- the same call with all four passes in FP64, beside the headline (sigma agreement between the two, time) ----
     fp64_side = None
     if use_i8:
-        o64 = rt.make_options(fused_sketch=args.fused, range_passes_int8=0)
-        U64, S64, Vt64 = ld.rand_svd_dev(dA, K_RANK, S_OVER, o64)
-        barrier()
-        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(2):
-            U64, S64, Vt64 = ld.rand_svd_dev(dA, K_RANK, S_OVER, o64)
-        f1.record()
-        barrier()
-        ms64 = max_over_ranks(f0.elapsed_time(f1) / 2)
-        S64h = S64.cpu().numpy()
-        fp64_side = {"ms_per_step": ms64, "A_stream_GBps": algorithmic_bytes(m_global, n) / (ms64 * 1e-3) * 1e-9,
-                     "max_rel_sigma_diff_int8_range_vs_all_fp64": float(np.max(np.abs(Sg - S64h) / S64h)),
-                     "phases_ms": dict(rt.timings())}
-        del U64, Vt64
+        def side(level):
+            oo = rt.make_options(fused_sketch=args.fused, range_passes_int8=level)
+            Ux, Sx, Vx = ld.rand_svd_dev(dA, K_RANK, S_OVER, oo)
+            barrier()
+            f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(2):
+                Ux, Sx, Vx = ld.rand_svd_dev(dA, K_RANK, S_OVER, oo)
+            f1.record()
+            barrier()
+            msx = max_over_ranks(f0.elapsed_time(f1) / 2)
+            Sxh = Sx.cpu().numpy()
+            return {"ms_per_step": msx, "A_stream_GBps": algorithmic_bytes(m_global, n) / (msx * 1e-3) * 1e-9,
+                    "max_rel_sigma_diff_vs_headline": float(np.max(np.abs(Sg - Sxh) / Sxh)), "phases_ms": dict(rt.timings())}
+        fp64_side = {"all_fp64": side(0)}
+        if i8_level == 2:
+            fp64_side["int8_range_passes_fp64_QtA"] = side(1)
 
     # ---- end to end through the host-buffer C ABI (pinned host memory -> device -> host) ----
     e2e = None
@@ -381,44 +386,63 @@ def run_ours(args):
     fl = 2.0 * m_local * n * l
     by = 8.0 * m_local * n
     # FP64 DMMA passes of the step: all four with --range fp64, only "pass:At*Q" (the one that carries sigma) with --range int8
-    i8_names = ("pass:A*Omega", "pass:At*Y", "pass:A*S") if use_i8 else ()
+    i8_names = (("pass:A*Omega", "pass:At*Y", "pass:A*S", "pass:At*Q") if i8_level == 2 else ("pass:A*Omega", "pass:At*Y", "pass:A*S")) if use_i8 else ()
     fp64_ms = {k: v for k, v in phases.items() if k.startswith("pass:") and not k.startswith(i8_names)} if use_i8 else \
               {k: v for k, v in phases.items() if k.startswith("pass:")}
     i8_ms = {k: v for k, v in phases.items() if use_i8 and k.startswith(i8_names)}
     nn_ms = [v for k, v in fp64_ms.items() if k.startswith("pass:A*")]
     tn_ms = [v for k, v in fp64_ms.items() if k.startswith("pass:At*")]
     gemm_ms = nn_ms + tn_ms
-    per_launch_ms = float(np.mean(gemm_ms))
-    roofline = {
-        "bound": "tensor", "kernel": "gemm_tn_kernel (FP64 DMMA.8x8x4): B = Q^T A, the pass that carries the singular values" if use_i8
-                 else "gemm_nn_kernel / gemm_tn_kernel (FP64 DMMA.8x8x4, 2 launches each per step)",
-        "achieved": fl / (per_launch_ms * 1e-3) * 1e-12, "peak": fp64.value, "unit": "TFLOP/s",
-        "frac": fl / (per_launch_ms * 1e-3) * 1e-12 / fp64.value,
-        "peak_source": "FP64 DMMA peak measured live by rnla_measure_roofs on this GPU (MEASURED_PEAKS.json holds no FP64 number)",
-        "traffic": None,
-        "hbm": {"achieved": by / (per_launch_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": by / (per_launch_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src, "read_only_stream_measured_gbs": hbm.value},
-        "note": "l = k+p = 110 makes an FP64 pass FP64-pipe bound (27.5 flop/B vs a 5.7 flop/B ridge), SURVEY.md §0 fact 3",
-        "per_kernel_ms": {"gemm_nn": float(np.mean(nn_ms)) if nn_ms else None, "gemm_tn": float(np.mean(tn_ms)) if tn_ms else None},
-        "share_of_step": float(sum(gemm_ms) / sum(phases.values())),
-    }
+    step_ms = sum(phases.values())
+    fp64_block = None
+    if gemm_ms:
+        per_launch_ms = float(np.mean(gemm_ms))
+        fp64_block = {
+            "bound": "tensor", "kernel": "gemm_tn_kernel (FP64 DMMA.8x8x4): B = Q^T A, the pass that carries the singular values" if use_i8
+                     else "gemm_nn_kernel / gemm_tn_kernel (FP64 DMMA.8x8x4, 2 launches each per step)",
+            "achieved": fl / (per_launch_ms * 1e-3) * 1e-12, "peak": fp64.value, "unit": "TFLOP/s",
+            "frac": fl / (per_launch_ms * 1e-3) * 1e-12 / fp64.value,
+            "peak_source": "FP64 DMMA peak measured live by rnla_measure_roofs on this GPU (MEASURED_PEAKS.json holds no FP64 number)",
+            "traffic": None,
+            "hbm": {"achieved": by / (per_launch_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": by / (per_launch_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src, "read_only_stream_measured_gbs": hbm.value},
+            "note": "l = k+p = 110 makes an FP64 pass FP64-pipe bound (27.5 flop/B vs a 5.7 flop/B ridge), SURVEY.md §0 fact 3",
+            "per_kernel_ms": {"gemm_nn": float(np.mean(nn_ms)) if nn_ms else None, "gemm_tn": float(np.mean(tn_ms)) if tn_ms else None},
+            "share_of_step": float(sum(gemm_ms) / step_ms),
+        }
+    if i8_level == 2:
+        # no FP64 pass left: the longest single launch of the step is the digit split of A (HBM-bound: A read once, the two tiled
+        # 4-plane images and the 3-plane image of the trailing digits written: 8 + 4 + 4 + 3 = 19 bytes per element)
+        sp_ms = phases.get("i8:split(A)", float("nan"))
+        sp_by = 19.0 * m_local * n
+        roofline = {"bound": "hbm", "kernel": "slice_a_kernel<7 digits> (FP64 -> seven balanced 7-bit digit planes, pre-tiled MMA images)",
+                    "achieved": sp_by / (sp_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s", "frac": sp_by / (sp_ms * 1e-3) * 1e-9 / hbm_peak,
+                    "peak_source": hbm_src, "traffic": None, "bytes_per_launch": sp_by, "share_of_step": float(sp_ms / step_ms),
+                    "note": "with --range int8-all no FP64 GEMM is left in the step; per-kernel blocks for the integer passes below, "
+                            "the FP64 DMMA kernels are measured in all_fp64_passes / --range fp64 (95 % of the DMMA peak)"}
+    else:
+        roofline = fp64_block
     if use_i8 and i8_ms:
         # the integer passes stream the 4 digit planes of A: 4 bytes per element per sweep (A S makes two sweeps), HBM-bound
-        sweeps = {k: (2.0 if k.startswith("pass:A*S") else 1.0) for k in i8_ms}
+        # bytes of digit planes streamed: 4 per element per sweep; A S makes two sweeps; the 49-bit Q^T A reads 4 + 7
+        sweeps = {k: (2.0 if k.startswith("pass:A*S") else (2.75 if k.startswith("pass:At*Q") else 1.0)) for k in i8_ms}
+        pairs = {k: (16.0 if k.startswith("pass:A*S") else (28.0 if k.startswith("pass:At*Q") else 10.0)) for k in i8_ms}
         tot_ms = sum(i8_ms.values()); tot_by = sum(4.0 * m_local * n * sweeps[k] for k in i8_ms)
         split_ms = phases.get("i8:rowmax(A)", 0.0) + phases.get("i8:split(A)", 0.0)
-        roofline["int8_range_passes"] = {
+        roofline["int8_passes"] = {
             "bound": "hbm", "kernel": "i8_mma_kernel (tcgen05.mma kind::i8, TMEM accumulators, cp.async.bulk of pre-tiled digit planes)",
             "achieved": tot_by / (tot_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s", "frac": tot_by / (tot_ms * 1e-3) * 1e-9 / hbm_peak,
             "per_pass_ms": i8_ms, "bytes_per_sweep": 4.0 * m_local * n,
-            "tensor_TOPS": sum(10.0 * sweeps[k] if not k.startswith("pass:A*S") else 16.0 for k in i8_ms) * 2.0 * m_local * n * 128 / (tot_ms * 1e-3) * 1e-12,
+            "tensor_TOPS": sum(pairs.values()) * 2.0 * m_local * n * 128 / (tot_ms * 1e-3) * 1e-12, "digit_pair_mmas": pairs,
             "f64_equivalent_A_stream_GBps": by * len(i8_ms) / (tot_ms * 1e-3) * 1e-9,
-            "split_of_A": {"ms": split_ms, "bytes": 8.0 * m_local * n * 2 + 8.0 * m_local * n,
-                           "GBps": (8.0 * m_local * n * 2 + 8.0 * m_local * n) / (split_ms * 1e-3) * 1e-9 if split_ms else None,
-                           "note": "row maxima (A read once) + digit split (A read once, two tiled 4-plane images written)"},
+            "split_of_A": {"ms": split_ms, "bytes": (16.0 + (11.0 if i8_level == 2 else 8.0)) * m_local * n,
+                           "GBps": (16.0 + (11.0 if i8_level == 2 else 8.0)) * m_local * n / (split_ms * 1e-3) * 1e-9 if split_ms else None,
+                           "note": "row maxima (A read once) + digit split (A read once, tiled digit-plane images written)"},
         }
+    if i8_level == 2 and fp64_block is None:
+        roofline["fp64_dmma_kernels"] = "see all_fp64_passes"
     ncu_traffic = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(ncu_traffic):
+    if os.path.exists(ncu_traffic) and i8_level != 2:
         try:
             roofline["traffic"] = json.load(open(ncu_traffic)).get("gemm_bytes_per_launch")
         except Exception:
@@ -438,12 +462,15 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if not use_i8 else "f64 (range-finder passes: int8 tensor cores on a 28-bit fixed-point split of A; Q^T A, factorisations and outputs f64)",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": ["f64", "f64 (range-finder passes: int8 tensor cores on a 28-bit fixed-point split of A; Q^T A, factorisations and outputs f64)",
+                                        "f64 results; every pass over A on the int8 tensor cores with exact int32 accumulation: 28-bit balanced-digit split for the "
+                                        "range-finder passes, 49-bit split (28 digit pairs) for Q^T A; factorisations, small products and outputs f64"][i8_level],
         "data": "synthetic",
         "config": {"workload": f"rand_svd f64 {m_global}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}, Gaussian sketch",
                    "rows_per_gpu": m_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
                    "sketch": "auto (materialised while Omega is L2-resident)" if args.fused == 2 else ("fused in-kernel Philox" if args.fused == 1 else "materialised"),
-                   "range_passes": "int8 tensor cores (rnla_options.range_passes_int8 = 1)" if use_i8 else "fp64",
+                   "range_passes": ["fp64", "int8 tensor cores, Q^T A in FP64 (rnla_options.range_passes_int8 = 1)",
+                                    "int8 tensor cores, Q^T A on a 49-bit split (rnla_options.range_passes_int8 = 2)"][i8_level],
                    "l2": f"inputs larger than L2 (A shard = {8 * m_local * n / 2**30:.1f} GiB per GPU, streamed 4x per step)"},
         "rand_svd_ms": ms_step, "tflops_fp64": algorithmic_flops(m_global, n, l) / (ms_step * 1e-3) * 1e-12,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -465,9 +492,10 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (debug)")
     ap.add_argument("--cols", type=int, default=N_COLS)
     ap.add_argument("--fused", type=int, default=2, help="0 materialise Omega, 1 in-kernel Philox, 2 auto")
-    ap.add_argument("--range", default="int8", choices=["int8", "fp64"],
+    ap.add_argument("--range", default="int8-all", choices=["int8-all", "int8", "fp64"],
                     help="int8: the three range-finder passes (A Omega, A^T Y, A S) run on the INT8 tensor cores from a 4 x 7-bit split of A "
-                         "(rnla_options.range_passes_int8), the pass that carries the singular values (Q^T A) in FP64; fp64: all four passes FP64")
+                         "(rnla_options.range_passes_int8 = 1), the pass that carries the singular values (Q^T A) in FP64; int8-all: Q^T A too, "
+                         "on a 49-bit split with exact int32 accumulation (= 2); fp64: all four passes on the FP64 DMMA kernels")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-rows", type=int, default=25000, help="row sample of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--secondary", type=int, default=1, help="1: also time BASELINE configs 4 and 5 once (N=1 only, reported under 'secondary')")

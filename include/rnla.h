@@ -71,10 +71,13 @@ typedef struct rnla_options {
     int32_t passes_per_stab;  /* <=0: 1 (same lines) */
     int32_t fused_sketch;     /* 1: Omega is generated inside the A*Omega kernel and never materialised; 0: materialise (K0) then multiply;
                                * 2 (default): fuse iff the n x l operand would not stay L2-resident (> 48 MiB) */
-    int32_t range_passes_int8; /* 1: the range-finder passes (A Omega, A^T Y, A S: results that only have to span a subspace) run on the INT8
-                               * tensor cores from a 4 x 7-bit fixed-point split of A (relative accuracy 2^-28 per product); the pass that
-                               * carries the singular values (Q^T A) stays FP64.  0 (default): every pass in FP64.  l <= 128, n <= 131072,
-                               * single pass structure of rand_svd / rand_evd1 (dev_qb1).  DESIGN.md section 5c */
+    int32_t range_passes_int8; /* 0 (default): every pass over A in FP64 (DMMA).
+                               * 1: the range-finder passes (A Omega, A^T Y, A S: results that only have to span a subspace) run on the INT8
+                               *    tensor cores (tcgen05 kind::i8) from a 4 x 7-bit balanced-digit split of A, exact int32 accumulation,
+                               *    2^-25 .. 2^-28 of (row max) x (column max) per product; Q^T A, which carries the singular values, stays FP64.
+                               * 2: Q^T A as well, on a 7 x 7-bit (49-bit) split: 28 digit pairs, exact int32 accumulation, FP64-grade result.
+                               * Applies to rand_svd / rand_evd1 (dev_qb1) in the intended mode, l <= 128, n <= 131072, m n >= 2^22; other
+                               * shapes keep FP64.  Also RNLA_RANGE_INT8=1|2 in the environment.  DESIGN.md section 5c */
 } rnla_options;
 
 /* ---- library / context ------------------------------------------------------------------------- */
@@ -88,6 +91,9 @@ void* rnla_stream(void);
 /* run on a caller-owned cudaStream_t instead (e.g. torch's current stream); NULL restores the library stream */
 rnla_status rnla_set_stream(void* cuda_stream);
 rnla_status rnla_synchronize(void);
+/* the int8 passes (rnla_options.range_passes_int8) keep their digit-plane workspace (about 4 to 11 bytes per element of the
+ * largest A seen) across calls; this frees it (rnla_shutdown does too) */
+rnla_status rnla_release_workspace(void);
 void rnla_default_options(rnla_options* opt);
 /* process-wide defaults used by the reference-signature entry points */
 rnla_status rnla_set_options(const rnla_options* opt);

@@ -28,6 +28,7 @@ SIGNATURES = {
     "rnla_stream": (P, []),
     "rnla_set_stream": (c_i32, [P]),
     "rnla_synchronize": (c_i32, []),
+    "rnla_release_workspace": (c_i32, []),
     "rnla_default_options": (None, [C.POINTER(Options)]),
     "rnla_set_options": (c_i32, [C.POINTER(Options)]),
     "rnla_get_options": (None, [C.POINTER(Options)]),

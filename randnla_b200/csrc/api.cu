@@ -813,8 +813,9 @@ rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda,
     if (N < 1 || N > 128 || ((n + 127) / 128) * 128 > 131072 || m < 1 || n < 1)
         return fail(RNLA_ERR_INVALID_DIMENSIONS, "i8 range gemm: 1 <= N <= 128, n <= 131072");
     phases_reset();
-    RNLA_TRY(i8_prepare(dA, lda, m, n));
+    RNLA_TRY(i8_prepare(dA, lda, m, n, trans && reps < 0));
     i8_set_precise(!trans && reps < 0);                    // reps < 0: A B with all 16 digit pairs (two sweeps)
+    i8_set_full(trans && reps < 0);                        // reps < 0, trans: A^T B on the 49-bit split (28 digit pairs)
     reps = std::abs(reps);
     rnla_status st = RNLA_OK;
     for (int r = 0; r < std::max(reps, 1) && st == RNLA_OK; ++r) {
@@ -826,5 +827,14 @@ rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda,
     i8_release();
     RNLA_TRY(st);
     RNLA_CUDA(e);
+    return RNLA_OK;
+}
+
+// the digit-plane workspace of the int8 passes persists across calls (tens of GB at the headline size); give it back
+rnla_status rnla_release_workspace(void) {
+    RNLA_API_GUARD;
+    if (ensure_ctx() != RNLA_OK) return RNLA_OK;
+    cudaStreamSynchronize(ctx().stream);
+    i8_free_workspace();
     return RNLA_OK;
 }

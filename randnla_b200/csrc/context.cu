@@ -1,4 +1,5 @@
 #include "context.cuh"
+#include "drivers.cuh"
 #include "gemm.cuh"
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is dlopen'ed so librnla.so has no link-time NCCL dependency
@@ -34,7 +35,7 @@ static void default_opts(rnla_options* o) {
     o->passes_per_stab = 0;
     o->fused_sketch = 2;
     const char* r8 = getenv("RNLA_RANGE_INT8");
-    if (r8 && !strcmp(r8, "1")) o->range_passes_int8 = 1;
+    if (r8 && (!strcmp(r8, "1") || !strcmp(r8, "2"))) o->range_passes_int8 = r8[0] - '0';
     const char* m = getenv("RNLA_MODE");
     if (m && (!strcmp(m, "literal") || !strcmp(m, "LITERAL") || !strcmp(m, "1"))) o->mode = RNLA_MODE_LITERAL;
 }
@@ -176,6 +177,7 @@ void rnla_shutdown(void) {
     Ctx& c = g_ctx;
     if (!c.ready) return;
     cudaStreamSynchronize(c.stream);
+    i8_free_workspace();
     if (c.comm) { g_nccl.CommDestroy((ncclComm_t)c.comm); c.comm = nullptr; c.nranks = 1; c.rank = 0; }
     phases_reset();
     for (auto e : c.event_pool) cudaEventDestroy(e);

@@ -182,7 +182,7 @@ static inline bool use_fused(const rnla_options& o, int64_t n, int l) {
     if (o.fused_sketch == 1) return true;
     return (double)n * l * 8.0 > 48.0 * 1024 * 1024;
 }
-static bool g_i8_deferred = false;
+static bool g_i8_deferred = false, g_i8_p7 = false;
 static inline bool use_fused_forced(const rnla_options& o) { return o.fused_sketch == 1; }
 static inline int eff_passes(const rnla_options& o, int dflt) { return o.num_passes > 0 ? o.num_passes : dflt; }
 static inline int eff_pps(const rnla_options& o) { return o.passes_per_stab > 0 ? o.passes_per_stab : 1; }
@@ -215,7 +215,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
                 auto hook = std::move(c.first_pass_hook);
                 c.first_pass_hook = nullptr;
                 RNLA_TRY(hook(S, Ytmp, std::max<int64_t>(m, 1)));
-                if (g_i8_deferred) { g_i8_deferred = false; phase_end(); RNLA_TRY(i8_prepare(A, lda, m, n)); phase_begin("i8:(split done)"); }
+                if (g_i8_deferred) { g_i8_deferred = false; phase_end(); RNLA_TRY(i8_prepare(A, lda, m, n, g_i8_p7)); phase_begin("i8:(split done)"); }
             } else if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
                 RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
             } else {
@@ -285,17 +285,22 @@ rnla_status dev_qb1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
                     const rnla_options& o, double* Q, int64_t ldq, double* Bt /* n x l, ld n */) {
     // range_passes_int8: the passes that only have to span the subspace run on the integer tensor cores (i8gemm.cu); the pass
     // below, whose result carries the singular values, always runs in FP64
-    const bool i8 = o.range_passes_int8 == 1 && o.mode == RNLA_MODE_INTENDED && !use_fused_forced(o) && i8_supported(sh.rows_local, n, l);
+    const bool i8 = (o.range_passes_int8 == 1 || o.range_passes_int8 == 2) && o.mode == RNLA_MODE_INTENDED && !use_fused_forced(o) && i8_supported(sh.rows_local, n, l);
     // host-buffer entry point: A is still arriving when the first pass runs (first_pass_hook); the split waits for that pass
     g_i8_deferred = i8 && (bool)ctx().first_pass_hook;
-    if (i8 && !g_i8_deferred) RNLA_TRY(i8_prepare(A, lda, sh.rows_local, n));
-    const rnla_status st = dev_rf1(A, lda, sh, n, l, q, pps, o, Q, ldq);
+    const bool all8 = i8 && o.range_passes_int8 == 2;     // 2: Q^T A too, on a 49-bit (7-digit) split
+    g_i8_p7 = all8;
+    if (i8 && !g_i8_deferred) RNLA_TRY(i8_prepare(A, lda, sh.rows_local, n, all8));
+    rnla_status st = dev_rf1(A, lda, sh, n, l, q, pps, o, Q, ldq);
     g_i8_deferred = false;
+    if (st == RNLA_OK) {
+        if (!all8) i8_deactivate(); else i8_set_full(true);
+        PhaseScope ph("pass:At*Q");
+        st = dev_gemm_tn(A, lda, sh.rows_local, n, Q, ldq, l, Bt, n, true);
+    }
     i8_deactivate();
     if (i8) i8_release();
-    RNLA_TRY(st);
-    PhaseScope ph("pass:At*Q");
-    return dev_gemm_tn(A, lda, sh.rows_local, n, Q, ldq, l, Bt, n, true);
+    return st;
 }
 
 // SVD of a tall replicated-or-sharded panel X (rows x p) = Uo diag(sigma) Vo^T through CholeskyQR + Jacobi on R.

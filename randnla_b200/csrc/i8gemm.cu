@@ -30,9 +30,13 @@ constexpr int PL = 4;                       // digit planes
 constexpr int BM = 128, BN = 128, BK = 64;  // CTA tile: 128 x 128 outputs, 64 contraction indices per stage
 constexpr int CHUNK = PL * BM * BK;         // 32 KB: one stage of one operand (all planes)
 constexpr int PLANE = BM * BK;              // 8 KB
+constexpr int PLH = 3;                      // extra digit planes of the 49-bit split
+constexpr int CHUNK_HI = PLH * PLANE;       // 24 KB
 constexpr int STAGES = 3;
 constexpr int MMA_THREADS = 192;            // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
 constexpr size_t MMA_SMEM = (size_t)STAGES * 2 * CHUNK + 1024 + 256;
+constexpr int STAGE_HI = 2 * CHUNK + 2 * CHUNK_HI;                          // 112 KB: both operands, all seven planes
+constexpr size_t MMA_SMEM_HI = (size_t)2 * STAGE_HI + 1024 + 256;
 constexpr int64_t K_ACC_MAX = 131072;      // 4 pairs x 64^2 x K < 2^31
 
 // ---------------------------------------------------------------------------------------------- tcgen05 wrappers
@@ -87,6 +91,22 @@ __device__ __forceinline__ void digits4(double x, double scale, int (&d)[4]) {
     d[1] = ((v + 64) & 127) - 64; v = (v - d[1]) >> 7;
     d[0] = v;
 }
+// seven balanced digits of a 49-bit fixed-point value, in 32-bit arithmetic: y = x * scale (|y| < 2^27), vh = rint(y) gives
+// the four leading digits exactly as digits4 does, the remainder y - vh (exact in FP64, |.| <= 1/2) times 2^21 gives the three
+// trailing ones: x * scale * 2^21 = vh 2^21 + d4 2^14 + d5 2^7 + d6 (+- 1/2)
+__device__ __forceinline__ void digits7(double x, double scale, int (&d)[7]) {
+    const double y = x * scale;
+    int vh = __double2int_rn(y);
+    int vl = __double2int_rn((y - (double)vh) * 2097152.0);
+    vh = max(-(1 << 27) + 1, min((1 << 27) - 1, vh));
+    d[6] = ((vl + 64) & 127) - 64; vl = (vl - d[6]) >> 7;
+    d[5] = ((vl + 64) & 127) - 64; vl = (vl - d[5]) >> 7;
+    d[4] = vl;
+    d[3] = ((vh + 64) & 127) - 64; vh = (vh - d[3]) >> 7;
+    d[2] = ((vh + 64) & 127) - 64; vh = (vh - d[2]) >> 7;
+    d[1] = ((vh + 64) & 127) - 64; vh = (vh - d[1]) >> 7;
+    d[0] = vh;
+}
 // exponent bookkeeping from the bit pattern of a maximum: up = 2^(e+1) with max < 2^e, down = 2^(28 - (e+1)), so that
 // |x * down| < 2^27; zero / tiny rows -> 0
 __device__ __forceinline__ void scales_from_max_bits(unsigned long long bits, double* up, double* down) {
@@ -134,9 +154,11 @@ __global__ void scales_kernel(const unsigned long long* __restrict__ bits, int64
 // the same row of neighbouring core matrices hit different banks; undone by the copy-out
 __device__ __forceinline__ int stage_swz(int off) { return off ^ (((off >> 7) & 7) << 4); }
 
-__global__ void __launch_bounds__(256, 3)
+// P7: seven digits per element; planes 4..6 go to a third image (column-block major only: [plane 3][J 16][I 4][8 x 16 B])
+template <bool P7>
+__global__ void __launch_bounds__(256, P7 ? 2 : 3)
 slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, const double* __restrict__ down,
-               uint8_t* __restrict__ nn, int64_t kb_total, uint8_t* __restrict__ tn, int64_t kr_total) {
+               uint8_t* __restrict__ nn, int64_t kb_total, uint8_t* __restrict__ tn, int64_t kr_total, uint8_t* __restrict__ tnhi) {
     extern __shared__ __align__(16) uint8_t img[];          // [0, 32K): NN image; [32K, 64K): TN pieces [half][plane][J 8][I 4][128 B]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t rb = blockIdx.x / kb_total, kb = blockIdx.x % kb_total;
@@ -169,19 +191,27 @@ slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, 
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int jl = warp + 8 * r;
-            int d0[4], d1[4];
-            digits4(x0[h * 8 + r], sc0[h], d0); digits4(x1[h * 8 + r], sc1[h], d1);
+            constexpr int ND = P7 ? 7 : 4;
+            int d0[ND], d1[ND];
+            if (P7) { digits7(x0[h * 8 + r], sc0[h], reinterpret_cast<int (&)[7]>(d0)); digits7(x1[h * 8 + r], sc1[h], reinterpret_cast<int (&)[7]>(d1)); }
+            else { digits4(x0[h * 8 + r], sc0[h], reinterpret_cast<int (&)[4]>(d0)); digits4(x1[h * 8 + r], sc1[h], reinterpret_cast<int (&)[4]>(d1)); }
 #pragma unroll
-            for (int t = 0; t < PL; ++t) {
+            for (int t = 0; t < ND; ++t) {
                 const unsigned half = ((unsigned)d0[t] & 0xffu) | (((unsigned)d1[t] & 0xffu) << 8);
                 const unsigned other = __shfl_xor_sync(0xffffffffu, half, 1);
                 if ((lane & 1) == 0) {
                     const unsigned word = half | (other << 16);             // rows il .. il + 3
-                    const int off_nn = t * PLANE + (jl >> 3) * 1024 + (il >> 4) * 128 + (jl & 7) * 16 + (il & 15);
                     const int i64 = il & 63;
-                    const int off_tn = CHUNK + h * (CHUNK / 2) + t * (PLANE / 2) + (jl >> 3) * 512 + (i64 >> 4) * 128 + (jl & 7) * 16 + (i64 & 15);
-                    *reinterpret_cast<unsigned*>(img + stage_swz(off_nn)) = word;
-                    *reinterpret_cast<unsigned*>(img + stage_swz(off_tn)) = word;
+                    const int intra_tn = (jl >> 3) * 512 + (i64 >> 4) * 128 + (jl & 7) * 16 + (i64 & 15);
+                    if (t < PL) {
+                        const int off_nn = t * PLANE + (jl >> 3) * 1024 + (il >> 4) * 128 + (jl & 7) * 16 + (il & 15);
+                        const int off_tn = CHUNK + h * (CHUNK / 2) + t * (PLANE / 2) + intra_tn;
+                        *reinterpret_cast<unsigned*>(img + stage_swz(off_nn)) = word;
+                        *reinterpret_cast<unsigned*>(img + stage_swz(off_tn)) = word;
+                    } else {
+                        const int off_hi = 2 * CHUNK + h * (CHUNK_HI / 2) + (t - PL) * (PLANE / 2) + intra_tn;
+                        *reinterpret_cast<unsigned*>(img + stage_swz(off_hi)) = word;
+                    }
                 }
             }
         }
@@ -195,6 +225,13 @@ slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, 
         const int h = q >> 10, t = (q >> 8) & 3, w = q & 255;              // 1024 uint4 per half, 256 per plane piece
         uint4* dst = reinterpret_cast<uint4*>(tn + ((kb >> 1) * kr_total + 2 * rb + h) * (int64_t)CHUNK + t * PLANE + (kb & 1) * (PLANE / 2));
         dst[w] = src[stage_swz(CHUNK + q * 16) >> 4];
+    }
+    if (P7) {
+        for (int q = threadIdx.x; q < CHUNK_HI / 16; q += 256) {
+            const int h = q / 768, t = (q % 768) >> 8, w = q & 255;        // 768 uint4 per half, 256 per plane piece
+            uint4* dst = reinterpret_cast<uint4*>(tnhi + ((kb >> 1) * kr_total + 2 * rb + h) * (int64_t)CHUNK_HI + t * PLANE + (kb & 1) * (PLANE / 2));
+            dst[w] = src[stage_swz(2 * CHUNK + q * 16) >> 4];
+        }
     }
 }
 
@@ -217,27 +254,39 @@ colmax_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, const
     }
 }
 // B operand images: [k block of 64][plane][k group of 8][n block of 16][8 x 16 B]; columns >= N and rows >= K are zero
+template <bool P7>
 __global__ void __launch_bounds__(256)
 slice_b_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, const double* __restrict__ rs, const double* __restrict__ cdown,
-               uint8_t* __restrict__ out) {
+               uint8_t* __restrict__ out, uint8_t* __restrict__ out_hi) {
     const int64_t kb = blockIdx.x;
     const int kl = threadIdx.x & 63;
     const int64_t k = kb * 64 + kl;
     const double rsk = (k < K) ? (rs ? rs[k] : 1.0) : 0.0;
     for (int cq = threadIdx.x >> 6; cq < 32; cq += 4) {
         const int c0 = 4 * cq;
-        unsigned w[PL] = {0u, 0u, 0u, 0u};
+        constexpr int ND = P7 ? 7 : 4;
+        unsigned w[ND];
+#pragma unroll
+        for (int t = 0; t < ND; ++t) w[t] = 0u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int c = c0 + e;
-            int d[4] = {0, 0, 0, 0};
-            if (k < K && c < N) digits4(X[k + (int64_t)c * ldx] * rsk, cdown[c], d);
+            int d[ND];
 #pragma unroll
-            for (int t = 0; t < PL; ++t) w[t] |= ((unsigned)d[t] & 0xffu) << (8 * e);
+            for (int t = 0; t < ND; ++t) d[t] = 0;
+            if (k < K && c < N) {
+                if (P7) digits7(X[k + (int64_t)c * ldx] * rsk, cdown[c], reinterpret_cast<int (&)[7]>(d));
+                else digits4(X[k + (int64_t)c * ldx] * rsk, cdown[c], reinterpret_cast<int (&)[4]>(d));
+            }
+#pragma unroll
+            for (int t = 0; t < ND; ++t) w[t] |= ((unsigned)d[t] & 0xffu) << (8 * e);
         }
+        const int intra = (kl >> 3) * 1024 + (c0 >> 4) * 128 + (kl & 7) * 16 + (c0 & 15);
 #pragma unroll
-        for (int t = 0; t < PL; ++t)
-            *reinterpret_cast<unsigned*>(out + kb * (int64_t)CHUNK + t * PLANE + (kl >> 3) * 1024 + (c0 >> 4) * 128 + (kl & 7) * 16 + (c0 & 15)) = w[t];
+        for (int t = 0; t < ND; ++t) {
+            if (t < PL) *reinterpret_cast<unsigned*>(out + kb * (int64_t)CHUNK + t * PLANE + intra) = w[t];
+            else *reinterpret_cast<unsigned*>(out_hi + kb * (int64_t)CHUNK_HI + (t - PL) * PLANE + intra) = w[t];
+        }
     }
 }
 
@@ -363,37 +412,159 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int64_t a_blocks_per_tile, const
     if (warp == 1) { tc_fence_after(); tc_dealloc(tmem, 512); }
 }
 
+// Second sweep of the 49-bit A^T Q: digit pairs with ta + tb in {4, 5, 6} (18 of them, all seven planes of both operands) into
+// accumulators 0..2; P2[chunk] = sum_g 2^{-7(g+2)} D_g.  A stage holds both operands' seven planes (112 KB), two stages.
+__global__ void __launch_bounds__(MMA_THREADS, 1)
+i8_mma_tn_hi_kernel(const uint8_t* __restrict__ Alo, const uint8_t* __restrict__ Ahi, const uint8_t* __restrict__ Blo,
+                    const uint8_t* __restrict__ Bhi, int64_t kr_total, int64_t kblocks_per_chunk, double* __restrict__ P2, int64_t ldc,
+                    int64_t rows, int ncols, int64_t chunk_stride) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)2 * STAGE_HI);
+    uint64_t* empty = full + 2;
+    uint64_t* accum = empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.x;
+    const int64_t kb0 = (int64_t)blockIdx.y * kblocks_per_chunk;
+    const int64_t kb1 = min(kr_total, kb0 + kblocks_per_chunk);
+    const int nk = (int)(kb1 - kb0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(accum, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tc_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nk; ++it) {
+                const int s = it & 1;
+                if (it >= 2) mbar_wait(empty + s, ((it >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(full + s, STAGE_HI);
+                uint8_t* st = smem + (size_t)s * STAGE_HI;
+                bulk_g2s(st, Alo + (tile * kr_total + kb0 + it) * (int64_t)CHUNK, CHUNK, full + s);
+                bulk_g2s(st + CHUNK, Blo + (kb0 + it) * (int64_t)CHUNK, CHUNK, full + s);
+                bulk_g2s(st + 2 * CHUNK, Ahi + (tile * kr_total + kb0 + it) * (int64_t)CHUNK_HI, CHUNK_HI, full + s);
+                bulk_g2s(st + 2 * CHUNK + CHUNK_HI, Bhi + (kb0 + it) * (int64_t)CHUNK_HI, CHUNK_HI, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(false, true);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it & 1;
+                mbar_wait(full + s, (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + (size_t)s * STAGE_HI);
+#pragma unroll
+                for (int ks = 0; ks < BK / 32; ++ks) {
+#pragma unroll
+                    for (int ta = 0; ta < PL + PLH; ++ta) {
+#pragma unroll
+                        for (int tb = 0; tb < PL + PLH; ++tb) {
+                            const int g = ta + tb;
+                            if (g < 4 || g > 6) continue;
+                            const uint32_t a_plane = ta < PL ? base + ta * PLANE : base + 2 * CHUNK + (ta - PL) * PLANE;
+                            const uint32_t b_plane = tb < PL ? base + CHUNK + tb * PLANE : base + 2 * CHUNK + CHUNK_HI + (tb - PL) * PLANE;
+                            const uint64_t ad = smem_desc(a_plane + ks * 256, 128, 512);
+                            const uint64_t bd = smem_desc(b_plane + ks * 4096, 1024, 128);
+                            const uint32_t acc = (it > 0 || ks > 0 || ta > 0) ? 1u : 0u;      // first pair of group g is (0, g)
+                            tc_mma_i8(tmem + (uint32_t)(g - 4) * BN, ad, bd, idesc, acc);
+                        }
+                    }
+                }
+                tc_commit(empty + s);
+            }
+            tc_commit(accum);
+        }
+    } else {
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        const int quad = warp & 3;
+        const int64_t r = tile * BM + quad * 32 + lane;
+        double* out = P2 + (int64_t)blockIdx.y * chunk_stride;
+        for (int c0 = 0; c0 < ncols; c0 += 16) {
+            uint32_t d[3][16];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * BN + c0), d[g]);
+            tc_wait_ld();
+            if (r < rows) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int c = c0 + e;
+                    if (c < ncols) {
+                        double v = (double)(int)d[2][e];
+                        v = v * 0.0078125 + (double)(int)d[1][e];
+                        v = v * 0.0078125 + (double)(int)d[0][e];
+                        out[r + (int64_t)c * ldc] = v * 2.2737367544323206e-13;       // 2^-42
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tc_dealloc(tmem, 512); }
+}
+
 // Z(j, c) = cs_up(c) * sum over chunks, fixed order
 __global__ void __launch_bounds__(256)
-i8_tn_reduce_kernel(const double* __restrict__ P, int nchunks, int64_t chunk_stride, int64_t n, int ncols, const double* __restrict__ cs_up,
-                    double* __restrict__ Z, int64_t ldz) {
+i8_tn_reduce_kernel(const double* __restrict__ P, const double* __restrict__ P2, int nchunks, int64_t chunk_stride, int64_t n, int ncols,
+                    const double* __restrict__ cs_up, double* __restrict__ Z, int64_t ldz) {
     const int64_t total = n * ncols;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = idx / n, j = idx - c * n;
         double s = 0.0;
         for (int k = 0; k < nchunks; ++k) s += P[(int64_t)k * chunk_stride + j + c * n];
+        if (P2) {
+            double s2 = 0.0;                  // the low-order digit pairs, summed separately and added last
+            for (int k = 0; k < nchunks; ++k) s2 += P2[(int64_t)k * chunk_stride + j + c * n];
+            s += s2;
+        }
         Z[j + c * ldz] = s * cs_up[c];
     }
 }
 
+// The digit-plane images are tens of GB: they live in a workspace that persists across driver calls (grown on demand, released
+// by rnla_release_workspace / rnla_shutdown) instead of going through the stream-ordered pool on every call -- re-carving 44 GB
+// out of the pool per call cost 60 ms to 1 s of host time (measured), more than all the passes together.
+struct Persist {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    double* d() const { return static_cast<double*>(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
 struct Sliced {
     const double* A = nullptr; int64_t lda = 0, m = 0, n = 0;
     int64_t rblocks = 0, cblocks = 0, kb_total = 0, kr_total = 0;
-    DevBuf nn, tn, up, down, bits, bimg, cbits, cup, cdown;
-    bool ready = false;
+    Persist nn, tn, tnhi, up, down, bits, bimg, bimg_hi, cbits, cup, cdown, part, part2;
+    bool ready = false, p7 = false;
 };
 Sliced g_sl;
 bool g_active = false;
 bool g_precise = false;       // A S with all 16 digit pairs (two sweeps)
+bool g_full = false;          // A^T Q on the 49-bit split (two sweeps, 28 digit pairs)
 
-rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, const double* rs, int64_t kblocks) {
+rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, const double* rs, int64_t kblocks, bool p7 = false) {
     Ctx& c = ctx();
     RNLA_CUDA(cudaMemsetAsync(g_sl.cbits.p, 0, 128 * 8, c.stream));
     const int64_t rows_per = 32768;
     colmax_kernel<<<dim3((unsigned)N, (unsigned)((K + rows_per - 1) / rows_per)), 256, 0, c.stream>>>(X, ldx, K, N, rs, rows_per,
                                                                                                       g_sl.cbits.as<unsigned long long>());
     scales_kernel<<<1, 128, 0, c.stream>>>(g_sl.cbits.as<unsigned long long>(), 128, g_sl.cup.d(), g_sl.cdown.d());
-    slice_b_kernel<<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, rs, g_sl.cdown.d(), g_sl.bimg.as<uint8_t>());
+    if (p7) slice_b_kernel<true><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, rs, g_sl.cdown.d(), g_sl.bimg.as<uint8_t>(), g_sl.bimg_hi.as<uint8_t>());
+    else slice_b_kernel<false><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, rs, g_sl.cdown.d(), g_sl.bimg.as<uint8_t>(), nullptr);
     g_kernel_launches += 3;
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;
@@ -407,25 +578,33 @@ bool i8_supported(int64_t m, int64_t n, int l) {
 bool i8_active_for(const double* A, int64_t lda, int64_t m, int64_t n, int64_t N) {
     return g_active && g_sl.ready && g_sl.A == A && g_sl.lda == lda && g_sl.m == m && g_sl.n == n && N <= BN;
 }
-void i8_deactivate() { g_active = false; g_precise = false; }
+void i8_deactivate() { g_active = false; g_precise = false; g_full = false; }
+void i8_set_full(bool on) { g_full = on; }
 void i8_set_precise(bool on) { g_precise = on; }
-void i8_release() { g_active = false; g_sl.ready = false; g_sl.nn.release(); g_sl.tn.release(); g_sl.bimg.release(); }
+void i8_release() { g_active = false; g_sl.ready = false; }      // the workspace persists (see Persist)
+void i8_free_workspace() {
+    g_active = false; g_sl.ready = false;
+    Persist* all[] = {&g_sl.nn, &g_sl.tn, &g_sl.tnhi, &g_sl.up, &g_sl.down, &g_sl.bits, &g_sl.bimg, &g_sl.bimg_hi, &g_sl.cbits, &g_sl.cup, &g_sl.cdown,
+                      &g_sl.part, &g_sl.part2};
+    for (Persist* b : all) b->release();
+}
 
 // split A (m x n, lda) into the two tiled int8 images; afterwards dev_gemm_nn / dev_gemm_tn with this A and N <= 128 run on
 // the integer tensor cores until i8_deactivate()
-rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n) {
+rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool p7) {
     Ctx& c = ctx();
     Sliced& s = g_sl;
     s.ready = false; g_active = false;
-    s.A = A; s.lda = lda; s.m = m; s.n = n;
+    s.A = A; s.lda = lda; s.m = m; s.n = n; s.p7 = p7;
     s.rblocks = (m + 127) / 128; s.cblocks = (n + 127) / 128;
     s.kb_total = 2 * s.cblocks; s.kr_total = 2 * s.rblocks;
     const size_t img_bytes = (size_t)s.rblocks * s.cblocks * 2 * CHUNK;
     const int64_t kmax = std::max(s.kb_total, s.kr_total);
-    RNLA_CUDA(s.nn.alloc(img_bytes)); RNLA_CUDA(s.tn.alloc(img_bytes));
-    RNLA_CUDA(s.up.alloc((size_t)m * 8)); RNLA_CUDA(s.down.alloc((size_t)m * 8)); RNLA_CUDA(s.bits.alloc((size_t)m * 8));
-    RNLA_CUDA(s.bimg.alloc((size_t)kmax * CHUNK));
-    RNLA_CUDA(s.cbits.alloc(128 * 8)); RNLA_CUDA(s.cup.alloc(128 * 8)); RNLA_CUDA(s.cdown.alloc(128 * 8));
+    RNLA_CUDA(s.nn.ensure(img_bytes)); RNLA_CUDA(s.tn.ensure(img_bytes));
+    RNLA_CUDA(s.up.ensure((size_t)m * 8)); RNLA_CUDA(s.down.ensure((size_t)m * 8)); RNLA_CUDA(s.bits.ensure((size_t)m * 8));
+    RNLA_CUDA(s.bimg.ensure((size_t)kmax * CHUNK));
+    if (p7) { RNLA_CUDA(s.tnhi.ensure(img_bytes / PL * PLH)); RNLA_CUDA(s.bimg_hi.ensure((size_t)kmax * CHUNK_HI)); }
+    RNLA_CUDA(s.cbits.ensure(128 * 8)); RNLA_CUDA(s.cup.ensure(128 * 8)); RNLA_CUDA(s.cdown.ensure(128 * 8));
     phase_begin("i8:rowmax(A)");
     RNLA_CUDA(cudaMemsetAsync(s.bits.p, 0, (size_t)m * 8, c.stream));
     const int64_t cols_per = std::max<int64_t>(256, (n + 7) / 8);
@@ -436,14 +615,20 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n) {
     PhaseScope ph("i8:split(A)");
     static bool attr = false;
     if (!attr) {
-        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CHUNK));
+        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CHUNK));
+        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CHUNK + CHUNK_HI));
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_tn_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM_HI));
         RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
         RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
         RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
         attr = true;
     }
-    slice_a_kernel<<<(unsigned)(s.rblocks * s.kb_total), 256, 2 * CHUNK, c.stream>>>(A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total,
-                                                                                    s.tn.as<uint8_t>(), s.kr_total);
+    if (p7)
+        slice_a_kernel<true><<<(unsigned)(s.rblocks * s.kb_total), 256, 2 * CHUNK + CHUNK_HI, c.stream>>>(
+            A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total, s.tn.as<uint8_t>(), s.kr_total, s.tnhi.as<uint8_t>());
+    else
+        slice_a_kernel<false><<<(unsigned)(s.rblocks * s.kb_total), 256, 2 * CHUNK, c.stream>>>(
+            A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total, s.tn.as<uint8_t>(), s.kr_total, nullptr);
     g_kernel_launches += 3;
     RNLA_CUDA(cudaGetLastError());
     s.ready = true; g_active = true;
@@ -472,19 +657,26 @@ rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64
 rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz) {
     Ctx& c = ctx();
     Sliced& s = g_sl;
-    RNLA_TRY(slice_b(Q, ldq, s.m, (int)N, s.up.d(), s.kr_total));
-    const int64_t max_per = K_ACC_MAX / 64 / 2 * 2;                      // blocks of 64 rows per accumulation
+    const bool full = g_full && s.p7;
+    RNLA_TRY(slice_b(Q, ldq, s.m, (int)N, s.up.d(), s.kr_total, full));
+    const int64_t max_per = full ? 1024 : K_ACC_MAX / 64 / 2 * 2;        // blocks of 64 rows per accumulation (7 pairs x 64^2 x K < 2^31 when full)
     int64_t nchunks = std::max<int64_t>((s.kr_total + max_per - 1) / max_per, (4LL * c.sms + s.cblocks - 1) / s.cblocks);
     nchunks = std::max<int64_t>(1, std::min<int64_t>(nchunks, s.kr_total));
     const int64_t per = (s.kr_total + nchunks - 1) / nchunks;
     nchunks = (s.kr_total + per - 1) / per;
     const int64_t stride = s.n * N;
-    DevBuf P;
-    RNLA_CUDA(P.alloc((size_t)nchunks * stride * 8));
+    Persist& P = s.part; Persist& P2 = s.part2;
+    RNLA_CUDA(P.ensure((size_t)nchunks * stride * 8));
+    if (full) RNLA_CUDA(P2.ensure((size_t)nchunks * stride * 8));
     i8_mma_kernel<true, false><<<dim3((unsigned)s.cblocks, (unsigned)nchunks), MMA_THREADS, MMA_SMEM, c.stream>>>(
         s.tn.as<uint8_t>(), s.kr_total, s.bimg.as<uint8_t>(), s.kr_total, per, P.d(), s.n, s.n, (int)N, nullptr, nullptr, stride);
-    i8_tn_reduce_kernel<<<(unsigned)std::min<int64_t>(148 * 8, (stride + 255) / 256), 256, 0, c.stream>>>(P.d(), (int)nchunks, stride, s.n, (int)N,
-                                                                                                           s.cup.d(), Z, ldz);
+    if (full) {
+        i8_mma_tn_hi_kernel<<<dim3((unsigned)s.cblocks, (unsigned)nchunks), MMA_THREADS, MMA_SMEM_HI, c.stream>>>(
+            s.tn.as<uint8_t>(), s.tnhi.as<uint8_t>(), s.bimg.as<uint8_t>(), s.bimg_hi.as<uint8_t>(), s.kr_total, per, P2.d(), s.n, s.n, (int)N, stride);
+        ++g_kernel_launches;
+    }
+    i8_tn_reduce_kernel<<<(unsigned)std::min<int64_t>(148 * 8, (stride + 255) / 256), 256, 0, c.stream>>>(P.d(), full ? P2.d() : nullptr, (int)nchunks,
+                                                                                                           stride, s.n, (int)N, s.cup.d(), Z, ldz);
     g_kernel_launches += 2;
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;

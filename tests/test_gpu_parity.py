@@ -828,7 +828,8 @@ def test_c5_full_size_properties(rb):
 # ---------------------------------------------------------------- range-finder passes on the INT8 tensor cores (csrc/i8gemm.cu)
 @pytest.mark.parametrize("trans,m,n,N,precise", [(0, 128, 64, 128, False), (0, 300, 200, 110, False), (0, 300, 200, 110, True),
                                                  (1, 300, 200, 110, False), (0, 4100, 1030, 7, True), (1, 70001, 515, 60, False),
-                                                 (0, 2000, 40000, 33, False)])
+                                                 (0, 2000, 40000, 33, False), (1, 300, 200, 110, True), (1, 140001, 515, 60, True),
+                                                 (1, 4100, 1030, 128, True)])
 def test_i8_range_gemm_accuracy(rb, trans, m, n, N, precise):
     """tcgen05 kind::i8 products of a 4 x 7-bit fixed-point split against torch FP64: the error is bounded relative to
     (row maximum of A) x (column maximum of B) x K, i.e. componentwise against |A| |B| it stays at the 2^-25 (ten leading digit
@@ -857,21 +858,25 @@ def test_i8_range_gemm_accuracy(rb, trans, m, n, N, precise):
         ref = A @ B
         bound = A.abs().max(dim=1).values.reshape(-1, 1) * B.abs().max(dim=0).values.reshape(1, -1) * n
         err = ((Cm - ref).abs() / bound.clamp_min(1e-300)).max()
-    assert float(err) < (2.0 ** -27 if precise else 2.0 ** -24)
-    assert float((Cm - ref).norm() / ref.norm()) < (1e-7 if precise else 1e-6)
+    # precise: A B with all 16 pairs of the 28-bit split; A^T B on the 49-bit split (28 pairs: the pass that carries sigma)
+    tol = (2.0 ** -46 if trans else 2.0 ** -27) if precise else 2.0 ** -24
+    assert float(err) < tol
+    assert float((Cm - ref).norm() / ref.norm()) < ((1e-12 if trans else 1e-7) if precise else 1e-6)
     assert float(Cm[:, N - 1].abs().max()) == 0.0
     if not trans:
         assert float(Cm[m // 2].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("level", [1, 2])
 @pytest.mark.parametrize("m,n,k,s", [(6000, 1500, 20, 10), (3000, 4000, 30, 6), (9000, 1200, 25, 8)])
-def test_rand_svd_int8_range_passes_match_the_oracle(rb, orc, m, n, k, s):
-    """rnla_options.range_passes_int8: A Omega, A^T Y and A S on the integer tensor cores, Q^T A in FP64.  The singular values
+def test_rand_svd_int8_range_passes_match_the_oracle(rb, orc, m, n, k, s, level):
+    """rnla_options.range_passes_int8: A Omega, A^T Y and A S on the integer tensor cores, Q^T A in FP64 (level 1) or on a
+    49-bit split with exact integer accumulation (level 2).  The singular values
     still agree with the all-FP64 oracle to the north_star tolerance (the range only has to capture the dominant subspace), U is
     orthonormal, and the library really took the integer path (its phases are in the timings)."""
     from randnla_b200 import runtime as rt, lora_drivers as ld
     A, sig = lowrank_plus_noise(m, n, seed=m % 97, k=k)
-    with rt.options(range_passes_int8=1):
+    with rt.options(range_passes_int8=level):        # 2: Q^T A too, on a 49-bit split
         U, S, Vt = ld.rand_svd(A, k, 1e-6, s)
         names = [nm for nm, _ in rt.timings()]
     assert "i8:split(A)" in names and "pass:At*Q" in names

@@ -23,7 +23,7 @@ def run(trans, m, n, N, reps=1, scale_rows=False):
     err = float(((Cm - ref).abs() / den).max())
     fro = float((Cm - ref).norm() / ref.norm())
     return err, fro, rt.timings()
-cases = [(0, 300, 200, 110, False, -1), (0, 5000, 3000, 60, False, -1), (0, 1000, 500, 110, True, -1), (0, 128, 64, 128), (0, 256, 128, 16), (0, 300, 200, 110), (1, 128, 128, 128), (1, 300, 200, 110), (0, 5000, 3000, 60), (1, 70000, 1000, 110), (0, 1000, 500, 110, True), (1, 1000, 500, 110, True)]
+cases = [(1, 300, 200, 110, False, -1), (1, 70000, 1000, 110, False, -1), (1, 1000, 500, 110, True, -1), (0, 300, 200, 110, False, -1), (0, 5000, 3000, 60, False, -1), (0, 1000, 500, 110, True, -1), (0, 128, 64, 128), (0, 256, 128, 16), (0, 300, 200, 110), (1, 128, 128, 128), (1, 300, 200, 110), (0, 5000, 3000, 60), (1, 70000, 1000, 110), (0, 1000, 500, 110, True), (1, 1000, 500, 110, True)]
 if big:
     cases = []
 for cs in cases:
@@ -33,7 +33,7 @@ for cs in cases:
     out[f"{trans}_{m}x{n}_{N}_{len(cs)}"] = [err, fro]
 if big:
     m, n, N = 200000, 20000, 110
-    for trans, rp in ((0, 3), (1, 3), (0, -3)):
+    for trans, rp in ((0, 3), (1, 3), (0, -3), (1, -3)):
         err, fro, ph = run(trans, m, n, N, rp)
         print(f"trans={trans} {m}x{n} N={N}: err {err:.3e} fro {fro:.3e} phases {ph}", flush=True)
         out[f"big_{trans}_{rp}"] = {"err": err, "fro": fro, "phases": ph}

@@ -14,7 +14,7 @@ dA = rt.empty_colmajor(m, n); pA, lda = rt.dev_ptr_ld(dA)
 _lib.check(lib.rnla_generate_lowrank_dev(pA, lda, m, n, 0, m, bench.R0, sig.ctypes.data_as(C.c_void_p), 1e-7, 1234))
 out = {"m": m, "n": n}
 res = {}
-for name, flag in (("fp64", 0), ("int8_range", 1)):
+for name, flag in (("fp64", 0), ("int8_range", 1), ("int8_all", 2)):
     opts = rt.make_options(range_passes_int8=flag)
     U, S, Vt = ld.rand_svd_dev(dA, 100, 10, opts); rt.synchronize()
     best = 1e30
@@ -25,7 +25,13 @@ for name, flag in (("fp64", 0), ("int8_range", 1)):
     res[name] = (U.clone(), S.clone(), Vt.clone())
     out[name] = {"ms": best * 1e3, "phases": rt.timings()}
     print(name, f"{best*1e3:.2f} ms", rt.timings(), flush=True)
-S0 = res["fp64"][1].cpu().numpy(); S1 = res["int8_range"][1].cpu().numpy()
+S0 = res["fp64"][1].cpu().numpy(); S1 = res["int8_range"][1].cpu().numpy(); S2 = res["int8_all"][1].cpu().numpy()
+out["max_rel_sigma_diff_all"] = float(np.max(np.abs(S0 - S2) / S0))
+out["rel_sigma_diff_all_last5"] = [float(x) for x in (np.abs(S0 - S2) / S0)[-5:]]
+U2, V2 = res["int8_all"][0], res["int8_all"][2]
+out["orth_err_all"] = float((U2.t() @ U2 - torch.eye(100, dtype=torch.float64, device="cuda")).abs().max())
+out["VtV_err_all"] = float((V2 @ V2.t() - torch.eye(100, dtype=torch.float64, device="cuda")).abs().max())
+out["sigma_vs_planted_all"] = float(np.max(np.abs(S2 - sig[:100]) / sig[:100]))
 out["max_rel_sigma_diff"] = float(np.max(np.abs(S0 - S1) / S0))
 out["rel_sigma_diff_last10"] = [float(x) for x in (np.abs(S0 - S1) / S0)[-10:]]
 U0, U1 = res["fp64"][0], res["int8_range"][0]
