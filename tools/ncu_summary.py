@@ -12,6 +12,10 @@ W = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), ("la
      ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "DMMA pipe active % (while SM active)"),
      ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (elapsed)"),
      ("sm__ops_path_tensor_src_fp64.sum.per_second", "fp64 tensor ops/ns (x2 = GFLOP/s)"),
+     ("sm__ops_path_tensor_src_int8.sum.per_second", "int8 tensor ops/ns"),
+     ("sm__inst_executed_pipe_tc.sum", "tcgen05 (UTC*) instructions"),
+     ("sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active", "uniform pipe %"),
+     ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2 -> SM bytes"),
      ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
      ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
      ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
