@@ -74,37 +74,46 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, M = 128, N = 128
-__host__ __device__ constexpr uint32_t instr_desc(bool a_mn_major, bool b_mn_major) {
+// N = nmma (a multiple of 16, <= 128): only the thin operand's columns that exist are multiplied
+__host__ __device__ constexpr uint32_t instr_desc(bool a_mn_major, bool b_mn_major, int nmma) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
-           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------- splitting
-// x * scale (|.| < 2^27) -> nearest integer v -> four BALANCED 7-bit digits, most significant first:
-// v = d0 2^21 + d1 2^14 + d2 2^7 + d3 with d1..d3 in [-64, 63] and |d0| <= 64.  Balanced digits halve the typical digit and
-// make the dropped cross terms zero-mean.
+// Balanced 7-bit digits without a single conversion instruction: y + 1.5 * 2^52 holds rint(y) in the low mantissa bits
+// (|y| < 2^27), subtracting the magic number again gives rint(y) as a double, and the low 7 bits of an integer, sign-extended,
+// are its balanced digit in [-64, 63] (v - d is then divisible by 128).
+__device__ __forceinline__ int sext7(int v) { return (v << 25) >> 25; }
+__device__ __forceinline__ int rint_bits(double y, double* r) {
+    const double MAGIC = 6755399441055744.0;                // 1.5 * 2^52
+    const double t = y + MAGIC;
+    *r = t - MAGIC;
+    return (int)(unsigned)__double_as_longlong(t);          // low 32 bits: two's complement of rint(y)
+}
+// x * scale (|.| < 2^27) -> v = rint -> v = d0 2^21 + d1 2^14 + d2 2^7 + d3, d1..d3 in [-64, 63], |d0| <= 64
 __device__ __forceinline__ void digits4(double x, double scale, int (&d)[4]) {
-    int v = __double2int_rn(x * scale);
-    v = max(-(1 << 27) + 1, min((1 << 27) - 1, v));
-    d[3] = ((v + 64) & 127) - 64; v = (v - d[3]) >> 7;
-    d[2] = ((v + 64) & 127) - 64; v = (v - d[2]) >> 7;
-    d[1] = ((v + 64) & 127) - 64; v = (v - d[1]) >> 7;
+    double r;
+    int v = rint_bits(x * scale, &r);
+    d[3] = sext7(v); v = (v - d[3]) >> 7;
+    d[2] = sext7(v); v = (v - d[2]) >> 7;
+    d[1] = sext7(v); v = (v - d[1]) >> 7;
     d[0] = v;
 }
-// seven balanced digits of a 49-bit fixed-point value, in 32-bit arithmetic: y = x * scale (|y| < 2^27), vh = rint(y) gives
-// the four leading digits exactly as digits4 does, the remainder y - vh (exact in FP64, |.| <= 1/2) times 2^21 gives the three
-// trailing ones: x * scale * 2^21 = vh 2^21 + d4 2^14 + d5 2^7 + d6 (+- 1/2)
+// seven digits of a 49-bit fixed-point value, in 32-bit arithmetic: vh = rint(y) gives the four leading digits exactly as
+// digits4 does, the remainder y - vh (exact in FP64, |.| <= 1/2) times 2^21 the three trailing ones:
+// x * scale * 2^21 = vh 2^21 + d4 2^14 + d5 2^7 + d6 (+- 1/2)
 __device__ __forceinline__ void digits7(double x, double scale, int (&d)[7]) {
     const double y = x * scale;
-    int vh = __double2int_rn(y);
-    int vl = __double2int_rn((y - (double)vh) * 2097152.0);
-    vh = max(-(1 << 27) + 1, min((1 << 27) - 1, vh));
-    d[6] = ((vl + 64) & 127) - 64; vl = (vl - d[6]) >> 7;
-    d[5] = ((vl + 64) & 127) - 64; vl = (vl - d[5]) >> 7;
+    double yr, r2;
+    int vh = rint_bits(y, &yr);
+    int vl = rint_bits((y - yr) * 2097152.0, &r2);
+    d[6] = sext7(vl); vl = (vl - d[6]) >> 7;
+    d[5] = sext7(vl); vl = (vl - d[5]) >> 7;
     d[4] = vl;
-    d[3] = ((vh + 64) & 127) - 64; vh = (vh - d[3]) >> 7;
-    d[2] = ((vh + 64) & 127) - 64; vh = (vh - d[2]) >> 7;
-    d[1] = ((vh + 64) & 127) - 64; vh = (vh - d[1]) >> 7;
+    d[3] = sext7(vh); vh = (vh - d[3]) >> 7;
+    d[2] = sext7(vh); vh = (vh - d[2]) >> 7;
+    d[1] = sext7(vh); vh = (vh - d[1]) >> 7;
     d[0] = vh;
 }
 // exponent bookkeeping from the bit pattern of a maximum: up = 2^(e+1) with max < 2^e, down = 2^(28 - (e+1)), so that
@@ -152,67 +161,63 @@ __global__ void scales_kernel(const unsigned long long* __restrict__ bits, int64
 // as a K-major one of A^T Y.
 // staging-buffer swizzle (the 16-byte row inside a core matrix is XORed with the index of the core matrix): lanes that write
 // the same row of neighbouring core matrices hit different banks; undone by the copy-out
-__device__ __forceinline__ int stage_swz(int off) { return off ^ (((off >> 7) & 7) << 4); }
+__device__ __forceinline__ int stage_swz(int off) { return off ^ ((((off >> 7) ^ (off >> 12)) & 7) << 4); }
+__device__ __forceinline__ unsigned pack4(int a, int b, int c, int d) {
+    return __byte_perm(__byte_perm((unsigned)a, (unsigned)b, 0x0040), __byte_perm((unsigned)c, (unsigned)d, 0x0040), 0x5410);
+}
 
 // P7: seven digits per element; planes 4..6 go to a third image (column-block major only: [plane 3][J 16][I 4][8 x 16 B])
 template <bool P7>
 __global__ void __launch_bounds__(256, P7 ? 2 : 3)
 slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, const double* __restrict__ down,
                uint8_t* __restrict__ nn, int64_t kb_total, uint8_t* __restrict__ tn, int64_t kr_total, uint8_t* __restrict__ tnhi) {
-    extern __shared__ __align__(16) uint8_t img[];          // [0, 32K): NN image; [32K, 64K): TN pieces [half][plane][J 8][I 4][128 B]
+    extern __shared__ __align__(16) uint8_t img[];          // [0, 32K): NN image; [32K, 64K): TN pieces [half][plane][J 8][I 4][128 B]; then the trailing planes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t rb = blockIdx.x / kb_total, kb = blockIdx.x % kb_total;
     const int64_t R0 = rb * 128, C0 = kb * 64;
-    const bool vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0);
-    double x0[16], x1[16], sc0[2], sc1[2];
-    // all 16 loads of the thread are in flight before the first digit is formed
+    const int il = 4 * lane;                                // local rows il .. il + 3: a warp covers the 128 rows of one column
+    const int64_t i = R0 + il;
+    const bool vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0) && i + 3 < m;
+    double x[8][4], sc[4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int64_t i = R0 + 64 * h + 2 * lane;
-        sc0[h] = i < m ? down[i] : 0.0; sc1[h] = i + 1 < m ? down[i + 1] : 0.0;
+    for (int e = 0; e < 4; ++e) sc[e] = i + e < m ? down[i + e] : 0.0;
+    // all loads of the thread are in flight before the first digit is formed
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int64_t j = C0 + warp + 8 * r;
-            double a0 = 0.0, a1 = 0.0;
-            if (j < n) {
-                if (vec && i + 1 < m) {
-                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(a0), "=d"(a1) : "l"(A + i + j * lda));
-                } else {
-                    if (i < m) a0 = ldg_stream(A + i + j * lda);
-                    if (i + 1 < m) a1 = ldg_stream(A + i + 1 + j * lda);
-                }
+    for (int r = 0; r < 8; ++r) {
+        const int64_t j = C0 + warp + 8 * r;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[r][e] = 0.0;
+        if (j < n) {
+            if (vec) {
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(x[r][0]), "=d"(x[r][1]) : "l"(A + i + j * lda));
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(x[r][2]), "=d"(x[r][3]) : "l"(A + i + 2 + j * lda));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (i + e < m) x[r][e] = ldg_stream(A + i + e + j * lda);
             }
-            x0[h * 8 + r] = a0; x1[h * 8 + r] = a1;
         }
     }
+    const int h = il >> 6, i64 = il & 63;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int il = 64 * h + 2 * lane;                   // local rows il, il + 1
+    for (int r = 0; r < 8; ++r) {
+        const int jl = warp + 8 * r;
+        constexpr int ND = P7 ? 7 : 4;
+        int d[4][ND];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int jl = warp + 8 * r;
-            constexpr int ND = P7 ? 7 : 4;
-            int d0[ND], d1[ND];
-            if (P7) { digits7(x0[h * 8 + r], sc0[h], reinterpret_cast<int (&)[7]>(d0)); digits7(x1[h * 8 + r], sc1[h], reinterpret_cast<int (&)[7]>(d1)); }
-            else { digits4(x0[h * 8 + r], sc0[h], reinterpret_cast<int (&)[4]>(d0)); digits4(x1[h * 8 + r], sc1[h], reinterpret_cast<int (&)[4]>(d1)); }
+        for (int e = 0; e < 4; ++e) {
+            if (P7) digits7(x[r][e], sc[e], reinterpret_cast<int (&)[7]>(d[e]));
+            else digits4(x[r][e], sc[e], reinterpret_cast<int (&)[4]>(d[e]));
+        }
+        const int intra_nn = (jl >> 3) * 1024 + (il >> 4) * 128 + (jl & 7) * 16 + (il & 15);
+        const int intra_tn = (jl >> 3) * 512 + (i64 >> 4) * 128 + (jl & 7) * 16 + (i64 & 15);
 #pragma unroll
-            for (int t = 0; t < ND; ++t) {
-                const unsigned half = ((unsigned)d0[t] & 0xffu) | (((unsigned)d1[t] & 0xffu) << 8);
-                const unsigned other = __shfl_xor_sync(0xffffffffu, half, 1);
-                if ((lane & 1) == 0) {
-                    const unsigned word = half | (other << 16);             // rows il .. il + 3
-                    const int i64 = il & 63;
-                    const int intra_tn = (jl >> 3) * 512 + (i64 >> 4) * 128 + (jl & 7) * 16 + (i64 & 15);
-                    if (t < PL) {
-                        const int off_nn = t * PLANE + (jl >> 3) * 1024 + (il >> 4) * 128 + (jl & 7) * 16 + (il & 15);
-                        const int off_tn = CHUNK + h * (CHUNK / 2) + t * (PLANE / 2) + intra_tn;
-                        *reinterpret_cast<unsigned*>(img + stage_swz(off_nn)) = word;
-                        *reinterpret_cast<unsigned*>(img + stage_swz(off_tn)) = word;
-                    } else {
-                        const int off_hi = 2 * CHUNK + h * (CHUNK_HI / 2) + (t - PL) * (PLANE / 2) + intra_tn;
-                        *reinterpret_cast<unsigned*>(img + stage_swz(off_hi)) = word;
-                    }
-                }
+        for (int t = 0; t < ND; ++t) {
+            const unsigned word = pack4(d[0][t], d[1][t], d[2][t], d[3][t]);
+            if (t < PL) {
+                *reinterpret_cast<unsigned*>(img + stage_swz(t * PLANE + intra_nn)) = word;
+                *reinterpret_cast<unsigned*>(img + stage_swz(CHUNK + h * (CHUNK / 2) + t * (PLANE / 2) + intra_tn)) = word;
+            } else {
+                *reinterpret_cast<unsigned*>(img + stage_swz(2 * CHUNK + h * (CHUNK_HI / 2) + (t - PL) * (PLANE / 2) + intra_tn)) = word;
             }
         }
     }
@@ -222,14 +227,14 @@ slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, 
     for (int q = threadIdx.x; q < CHUNK / 16; q += 256) dnn[q] = src[stage_swz(q * 16) >> 4];
     // TN: block (cb = kb / 2, kr = 2 rb + h); this CTA owns column groups J = 8 (kb & 1) .. + 7 of every plane: 4 KB per plane
     for (int q = threadIdx.x; q < CHUNK / 16; q += 256) {
-        const int h = q >> 10, t = (q >> 8) & 3, w = q & 255;              // 1024 uint4 per half, 256 per plane piece
-        uint4* dst = reinterpret_cast<uint4*>(tn + ((kb >> 1) * kr_total + 2 * rb + h) * (int64_t)CHUNK + t * PLANE + (kb & 1) * (PLANE / 2));
+        const int hh = q >> 10, t = (q >> 8) & 3, w = q & 255;             // 1024 uint4 per half, 256 per plane piece
+        uint4* dst = reinterpret_cast<uint4*>(tn + ((kb >> 1) * kr_total + 2 * rb + hh) * (int64_t)CHUNK + t * PLANE + (kb & 1) * (PLANE / 2));
         dst[w] = src[stage_swz(CHUNK + q * 16) >> 4];
     }
     if (P7) {
         for (int q = threadIdx.x; q < CHUNK_HI / 16; q += 256) {
-            const int h = q / 768, t = (q % 768) >> 8, w = q & 255;        // 768 uint4 per half, 256 per plane piece
-            uint4* dst = reinterpret_cast<uint4*>(tnhi + ((kb >> 1) * kr_total + 2 * rb + h) * (int64_t)CHUNK_HI + t * PLANE + (kb & 1) * (PLANE / 2));
+            const int hh = q / 768, t = (q % 768) >> 8, w = q & 255;       // 768 uint4 per half, 256 per plane piece
+            uint4* dst = reinterpret_cast<uint4*>(tnhi + ((kb >> 1) * kr_total + 2 * rb + hh) * (int64_t)CHUNK_HI + t * PLANE + (kb & 1) * (PLANE / 2));
             dst[w] = src[stage_swz(2 * CHUNK + q * 16) >> 4];
         }
     }
@@ -337,7 +342,7 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int64_t a_blocks_per_tile, const
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(!TN, true);
+            const uint32_t idesc = instr_desc(!TN, true, (ncols + 15) & ~15);
             for (int it = 0; it < nk; ++it) {
                 const int s = it % STAGES;
                 mbar_wait(full + s, (it / STAGES) & 1);
@@ -454,7 +459,7 @@ i8_mma_tn_hi_kernel(const uint8_t* __restrict__ Alo, const uint8_t* __restrict__
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(false, true);
+            const uint32_t idesc = instr_desc(false, true, (ncols + 15) & ~15);
             for (int it = 0; it < nk; ++it) {
                 const int s = it & 1;
                 mbar_wait(full + s, (it >> 1) & 1);

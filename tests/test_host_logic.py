@@ -152,3 +152,73 @@ def test_row_sharded_dataflow_matches_single_process_oracle(tmp_path, orc, q):
     A = np.asfortranarray(rng.standard_normal((m, 12)) @ rng.standard_normal((12, n)) + 1e-3 * rng.standard_normal((m, n)))
     _, S, _ = orc.rand_svd(A, k, 0.1, s, orc.make_opts(mode=0, num_passes=q))
     assert (np.abs(sig - np.diag(S)) / np.diag(S)).max() < 1e-10
+
+
+# ---- the fixed-point split behind the INT8 tensor-core passes (randnla_b200/csrc/i8gemm.cu: digits4 / digits7 / scales_from_max_bits) ----
+def _scales(rowmax):
+    """2^(e+1) and 2^(27-e) with rowmax < 2^e, from the exponent field of the maximum (scales_from_max_bits)"""
+    E = (np.float64(rowmax).view(np.uint64) >> np.uint64(52)) & np.uint64(0x7ff)
+    E = int(E)
+    if E < 64 or E >= 2045:
+        return 0.0, 0.0
+    return float(np.ldexp(1.0, E + 2 - 1023)), float(np.ldexp(1.0, 2072 - E - 1023))
+
+
+def _digits(x, down, seven):
+    """numpy restatement of digits4 / digits7: balanced 7-bit digits, most significant first"""
+    y = x * down
+    vh = int(np.rint(y))
+    vl = int(np.rint((y - vh) * 2097152.0)) if seven else 0
+    vh = max(-(1 << 27) + 1, min((1 << 27) - 1, vh))
+    d = [0] * (7 if seven else 4)
+    if seven:
+        d[6] = ((vl + 64) & 127) - 64; vl = (vl - d[6]) >> 7
+        d[5] = ((vl + 64) & 127) - 64; vl = (vl - d[5]) >> 7
+        d[4] = vl
+    d[3] = ((vh + 64) & 127) - 64; vh = (vh - d[3]) >> 7
+    d[2] = ((vh + 64) & 127) - 64; vh = (vh - d[2]) >> 7
+    d[1] = ((vh + 64) & 127) - 64; vh = (vh - d[1]) >> 7
+    d[0] = vh
+    return d
+
+
+def test_int8_digit_split_is_exact_bounded_and_accumulates_in_int32():
+    """every digit fits int8 with |d| <= 64 (so 4 pairs x 64^2 x 131072 and 7 pairs x 64^2 x 65536 stay below 2^31), the digits
+    reproduce the rounded fixed-point value exactly, and the representation error is 2^-28 (4 digits) / 2^-49 (7 digits) of the
+    row scale; the weights are the ones the epilogues use: x = up * sum_t d_t 2^{-7(t+1)}"""
+    rng = np.random.default_rng(0)
+    for scale in (1.0, 3e-7, 9.1e11):
+        row = rng.standard_normal(4000) * scale
+        row[:4] = [np.abs(row).max() * (1 - 2 ** -52), -np.abs(row).max(), 0.0, scale * 2 ** -60]
+        up, down = _scales(np.abs(row).max())
+        assert up > np.abs(row).max() and up <= 4 * np.abs(row).max()
+        for seven in (False, True):
+            worst = 0.0
+            for x in row[:600]:
+                d = _digits(float(x), down, seven)
+                assert all(-64 <= t <= 64 for t in d)
+                rec = up * sum(t * 2.0 ** (-7 * (i + 1)) for i, t in enumerate(d))
+                worst = max(worst, abs(rec - x) / up)
+            assert worst <= (2.0 ** -49 if seven else 2.0 ** -28) * 0.51
+    assert 4 * 64 * 64 * 131072 <= 2 ** 31 and 7 * 64 * 64 * 65536 < 2 ** 31
+    assert _scales(0.0) == (0.0, 0.0) and _scales(1e-300) == (0.0, 0.0)
+
+
+def test_int8_digit_pair_groups_cover_the_product():
+    """sum over digit pairs grouped by g = ta + tb with weight 2^{-7(g+2)} is the product of the two representations: 10 pairs
+    (g <= 3) for a range-finder pass, 16 for A S, 28 of the 49 pairs (g <= 6) for Q^T A -- and the dropped groups are below
+    2^-25 / 2^-46 of the scales"""
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal(64); b = rng.standard_normal(64)
+    ua, da = _scales(np.abs(a).max()); ub, db = _scales(np.abs(b).max())
+    for seven, gmax, tol in ((False, 3, 2.0 ** -24), (False, 6, 2.0 ** -27), (True, 6, 2.0 ** -45)):
+        A = np.array([_digits(float(x), da, seven) for x in a]); B = np.array([_digits(float(x), db, seven) for x in b])
+        nd = A.shape[1]
+        acc = {}
+        for ta in range(nd):
+            for tb in range(nd):
+                if ta + tb <= gmax:
+                    acc[ta + tb] = acc.get(ta + tb, 0) + int(A[:, ta] @ B[:, tb])          # exact integer accumulation
+        got = ua * ub * sum(v * 2.0 ** (-7 * (g + 2)) for g, v in acc.items())
+        assert abs(got - a @ b) <= tol * ua * ub * len(a)
+        assert len([1 for ta in range(nd) for tb in range(nd) if ta + tb <= gmax]) == {(False, 3): 10, (False, 6): 16, (True, 6): 28}[(seven, gmax)]
