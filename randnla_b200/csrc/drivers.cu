@@ -215,7 +215,11 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
                 auto hook = std::move(c.first_pass_hook);
                 c.first_pass_hook = nullptr;
                 RNLA_TRY(hook(S, Ytmp, std::max<int64_t>(m, 1)));
-                if (g_i8_deferred) { g_i8_deferred = false; phase_end(); RNLA_TRY(i8_prepare(A, lda, m, n, g_i8_p7)); phase_begin("i8:(split done)"); }
+                if (g_i8_deferred) {
+                    g_i8_deferred = false; phase_end();
+                    if (i8_prepare(A, lda, m, n, g_i8_p7) != RNLA_OK) { cudaGetLastError(); i8_deactivate(); }
+                    phase_begin("i8:(split done)");
+                }
             } else if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
                 RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
             } else {
@@ -290,11 +294,14 @@ rnla_status dev_qb1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
     g_i8_deferred = i8 && (bool)ctx().first_pass_hook;
     const bool all8 = i8 && o.range_passes_int8 == 2;     // 2: Q^T A too, on a 49-bit (7-digit) split
     g_i8_p7 = all8;
-    if (i8 && !g_i8_deferred) RNLA_TRY(i8_prepare(A, lda, sh.rows_local, n, all8));
+    if (i8 && !g_i8_deferred && i8_prepare(A, lda, sh.rows_local, n, all8) != RNLA_OK) {
+        // e.g. no room for the digit-plane workspace: the FP64 kernels need none
+        cudaGetLastError(); i8_deactivate();
+    }
     rnla_status st = dev_rf1(A, lda, sh, n, l, q, pps, o, Q, ldq);
     g_i8_deferred = false;
     if (st == RNLA_OK) {
-        if (!all8) i8_deactivate(); else i8_set_full(true);
+        if (!all8 || !i8_active_for(A, lda, sh.rows_local, n, l)) i8_deactivate(); else i8_set_full(true);
         PhaseScope ph("pass:At*Q");
         st = dev_gemm_tn(A, lda, sh.rows_local, n, Q, ldq, l, Bt, n, true);
     }

@@ -605,7 +605,11 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool 
     s.kb_total = 2 * s.cblocks; s.kr_total = 2 * s.rblocks;
     const size_t img_bytes = (size_t)s.rblocks * s.cblocks * 2 * CHUNK;
     const int64_t kmax = std::max(s.kb_total, s.kr_total);
-    RNLA_CUDA(s.nn.ensure(img_bytes)); RNLA_CUDA(s.tn.ensure(img_bytes));
+    if (s.nn.ensure(img_bytes) != cudaSuccess || s.tn.ensure(img_bytes) != cudaSuccess || (p7 && s.tnhi.ensure(img_bytes / PL * PLH) != cudaSuccess)) {
+        cudaGetLastError();
+        i8_free_workspace();
+        return fail(RNLA_ERR_COMPUTATION, "int8 passes: no room for the digit-plane workspace");
+    }
     RNLA_CUDA(s.up.ensure((size_t)m * 8)); RNLA_CUDA(s.down.ensure((size_t)m * 8)); RNLA_CUDA(s.bits.ensure((size_t)m * 8));
     RNLA_CUDA(s.bimg.ensure((size_t)kmax * CHUNK));
     if (p7) { RNLA_CUDA(s.tnhi.ensure(img_bytes / PL * PLH)); RNLA_CUDA(s.bimg_hi.ensure((size_t)kmax * CHUNK_HI)); }

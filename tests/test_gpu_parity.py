@@ -893,3 +893,24 @@ def test_rand_svd_int8_range_passes_match_the_oracle(rb, orc, m, n, k, s, level)
     with rt.options(range_passes_int8=1):
         ld.rand_svd(random_matrix(300, 200, seed=1), 10, 1e-6, 5)
         assert "i8:split(A)" not in [nm for nm, _ in rt.timings()]
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_rand_evd1_int8_passes_match_the_oracle(rb, orc, level):
+    """rand_evd1 (reference src/lora_drivers.rs:87-151) goes through QB1 as well: with the passes on the integer tensor cores
+    its eigenvalues still agree with the all-FP64 oracle to the north_star tolerance"""
+    from randnla_b200 import runtime as rt, lora_drivers as ld
+    n, k, s = 2304, 12, 8
+    rng = np.random.default_rng(5)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, 40)))
+    ev = np.concatenate([[9.0, -7.5, 6.0, 5.0, -4.0, 3.5, 3.0, -2.5, 2.0, 1.5, -1.2, 1.0], 1e-6 * rng.standard_normal(28)])
+    A = (Q * ev) @ Q.T
+    A = np.asfortranarray(0.5 * (A + A.T))
+    with rt.options(range_passes_int8=level):
+        V, lam = ld.rand_evd1(A, k, 0.1, s)
+        assert "i8:split(A)" in [nm for nm, _ in rt.timings()]
+    Vo, lamo = orc.rand_evd1(A, k, 0.1, s, orc.make_opts(mode=0))
+    lam, lamo = np.asarray(lam, dtype=np.float64), np.asarray(lamo, dtype=np.float64)
+    assert np.max(np.abs(lam - lamo) / np.abs(lamo)) < SIG_TOL
+    assert np.abs(V.T @ V - np.eye(k)).max() < 1e-12
+    assert np.linalg.norm(A @ V - V * lam) <= 1e-8 * np.abs(lam).max()
