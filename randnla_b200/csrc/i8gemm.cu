@@ -154,9 +154,8 @@ __global__ void scales_kernel(const unsigned long long* __restrict__ bits, int64
     if (i < cnt) scales_from_max_bits(bits[i], up + i, down + i);
 }
 
-// One CTA per 128 x 64 block of A (three resident CTAs per SM: while one forms digits the others keep loads in flight).  It
-// writes one complete row-block-major image (NN: [plane][J 8][I 8][8 x 16 B]) and, for each of its two 64-row halves, the matching
-// half (8 of 16 column groups) of a column-block-major image (TN: [plane][J 16][I 4][8 x 16 B]).  A core matrix holds 16 rows x 8
+// The digit split of A.  It writes row-block-major images (NN: [plane][J 8][I 8][8 x 16 B] per 128 rows x 64 columns) and
+// column-block-major images (TN: [plane][J 16][I 4][8 x 16 B] per 128 columns x 64 rows).  A core matrix holds 16 rows x 8
 // columns of A as 8 rows (columns of A) of 16 bytes (rows of A): the same 128 bytes serve as an MN-major core matrix of A S and
 // as a K-major one of A^T Y.
 // staging-buffer swizzle (the 16-byte row inside a core matrix is XORed with the index of the core matrix): lanes that write
@@ -166,24 +165,32 @@ __device__ __forceinline__ unsigned pack4(int a, int b, int c, int d) {
     return __byte_perm(__byte_perm((unsigned)a, (unsigned)b, 0x0040), __byte_perm((unsigned)c, (unsigned)d, 0x0040), 0x5410);
 }
 
-// P7: seven digits per element; planes 4..6 go to a third image (column-block major only: [plane 3][J 16][I 4][8 x 16 B])
+// P7: seven digits per element; planes 4..6 go to a third image (column-block major only: [plane 3][J 16][I 4][8 x 16 B]).
+// One CTA per 128 rows x 32 columns (half of a 64-column image block): 16 elements per thread keep the register count low
+// enough for three or four resident CTAs per SM, which is what keeps loads in flight while other CTAs form digits and store.
+constexpr int SL_COLS = 32;
+constexpr int SL_NN = PL * 128 * SL_COLS;          // 16 KB: [plane][J 4][I 8][128 B]
+constexpr int SL_TN = PL * 128 * SL_COLS;          // 16 KB: [half][plane][J 4][I 4][128 B]
+constexpr int SL_HI = PLH * 128 * SL_COLS;         // 12 KB: [half][plane 3][J 4][I 4][128 B]
 template <bool P7>
-__global__ void __launch_bounds__(256, P7 ? 2 : 3)
+__global__ void __launch_bounds__(256, P7 ? 3 : 4)
 slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, const double* __restrict__ down,
                uint8_t* __restrict__ nn, int64_t kb_total, uint8_t* __restrict__ tn, int64_t kr_total, uint8_t* __restrict__ tnhi) {
-    extern __shared__ __align__(16) uint8_t img[];          // [0, 32K): NN image; [32K, 64K): TN pieces [half][plane][J 8][I 4][128 B]; then the trailing planes
+    extern __shared__ __align__(16) uint8_t img[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t rb = blockIdx.x / kb_total, kb = blockIdx.x % kb_total;
-    const int64_t R0 = rb * 128, C0 = kb * 64;
+    const int64_t hb_total = 2 * kb_total;
+    const int64_t rb = blockIdx.x / hb_total, hb = blockIdx.x % hb_total;
+    const int64_t kb = hb >> 1;
+    const int half = (int)(hb & 1);                         // which 32 columns of the 64-column image block
+    const int64_t R0 = rb * 128, C0 = hb * SL_COLS;
     const int il = 4 * lane;                                // local rows il .. il + 3: a warp covers the 128 rows of one column
     const int64_t i = R0 + il;
     const bool vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0) && i + 3 < m;
-    double x[8][4], sc[4];
+    double x[4][4], sc[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) sc[e] = i + e < m ? down[i + e] : 0.0;
-    // all loads of the thread are in flight before the first digit is formed
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < 4; ++r) {
         const int64_t j = C0 + warp + 8 * r;
 #pragma unroll
         for (int e = 0; e < 4; ++e) x[r][e] = 0.0;
@@ -199,8 +206,8 @@ slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, 
     }
     const int h = il >> 6, i64 = il & 63;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int jl = warp + 8 * r;
+    for (int r = 0; r < 4; ++r) {
+        const int jl = warp + 8 * r;                        // 0 .. 31
         constexpr int ND = P7 ? 7 : 4;
         int d[4][ND];
 #pragma unroll
@@ -214,28 +221,34 @@ slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, 
         for (int t = 0; t < ND; ++t) {
             const unsigned word = pack4(d[0][t], d[1][t], d[2][t], d[3][t]);
             if (t < PL) {
-                *reinterpret_cast<unsigned*>(img + stage_swz(t * PLANE + intra_nn)) = word;
-                *reinterpret_cast<unsigned*>(img + stage_swz(CHUNK + h * (CHUNK / 2) + t * (PLANE / 2) + intra_tn)) = word;
+                *reinterpret_cast<unsigned*>(img + stage_swz(t * (SL_NN / PL) + intra_nn)) = word;
+                *reinterpret_cast<unsigned*>(img + stage_swz(SL_NN + h * (SL_TN / 2) + t * (SL_TN / 2 / PL) + intra_tn)) = word;
             } else {
-                *reinterpret_cast<unsigned*>(img + stage_swz(2 * CHUNK + h * (CHUNK_HI / 2) + (t - PL) * (PLANE / 2) + intra_tn)) = word;
+                *reinterpret_cast<unsigned*>(img + stage_swz(SL_NN + SL_TN + h * (SL_HI / 2) + (t - PL) * (SL_HI / 2 / PLH) + intra_tn)) = word;
             }
         }
     }
     __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(img);
-    uint4* dnn = reinterpret_cast<uint4*>(nn + (rb * kb_total + kb) * (int64_t)CHUNK);
-    for (int q = threadIdx.x; q < CHUNK / 16; q += 256) dnn[q] = src[stage_swz(q * 16) >> 4];
-    // TN: block (cb = kb / 2, kr = 2 rb + h); this CTA owns column groups J = 8 (kb & 1) .. + 7 of every plane: 4 KB per plane
-    for (int q = threadIdx.x; q < CHUNK / 16; q += 256) {
-        const int hh = q >> 10, t = (q >> 8) & 3, w = q & 255;             // 1024 uint4 per half, 256 per plane piece
-        uint4* dst = reinterpret_cast<uint4*>(tn + ((kb >> 1) * kr_total + 2 * rb + hh) * (int64_t)CHUNK + t * PLANE + (kb & 1) * (PLANE / 2));
-        dst[w] = src[stage_swz(CHUNK + q * 16) >> 4];
+    // NN: block (rb, kb), column groups J = 4 half .. + 3 of every plane: 4 KB per plane
+    for (int q = threadIdx.x; q < SL_NN / 16; q += 256) {
+        const int t = q >> 8, w = q & 255;
+        uint4* dst = reinterpret_cast<uint4*>(nn + (rb * kb_total + kb) * (int64_t)CHUNK + t * PLANE + half * (PLANE / 2));
+        dst[w] = src[stage_swz(q * 16) >> 4];
+    }
+    // TN: block (cb = kb / 2, kr = 2 rb + hh), column groups J = 8 (kb & 1) + 4 half .. + 3 of every plane: 2 KB per plane
+    for (int q = threadIdx.x; q < SL_TN / 16; q += 256) {
+        const int hh = q >> 9, t = (q >> 7) & 3, w = q & 127;              // 512 uint4 per half, 128 per plane piece
+        uint4* dst = reinterpret_cast<uint4*>(tn + ((kb >> 1) * kr_total + 2 * rb + hh) * (int64_t)CHUNK + t * PLANE +
+                                              ((kb & 1) * 8 + half * 4) * 512);
+        dst[w] = src[stage_swz(SL_NN + q * 16) >> 4];
     }
     if (P7) {
-        for (int q = threadIdx.x; q < CHUNK_HI / 16; q += 256) {
-            const int hh = q / 768, t = (q % 768) >> 8, w = q & 255;       // 768 uint4 per half, 256 per plane piece
-            uint4* dst = reinterpret_cast<uint4*>(tnhi + ((kb >> 1) * kr_total + 2 * rb + hh) * (int64_t)CHUNK_HI + t * PLANE + (kb & 1) * (PLANE / 2));
-            dst[w] = src[stage_swz(2 * CHUNK + q * 16) >> 4];
+        for (int q = threadIdx.x; q < SL_HI / 16; q += 256) {
+            const int hh = q / 384, t = (q % 384) >> 7, w = q & 127;       // 384 uint4 per half, 128 per plane piece
+            uint4* dst = reinterpret_cast<uint4*>(tnhi + ((kb >> 1) * kr_total + 2 * rb + hh) * (int64_t)CHUNK_HI + t * PLANE +
+                                                  ((kb & 1) * 8 + half * 4) * 512);
+            dst[w] = src[stage_swz(SL_NN + SL_TN + q * 16) >> 4];
         }
     }
 }
@@ -624,8 +637,8 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool 
     PhaseScope ph("i8:split(A)");
     static bool attr = false;
     if (!attr) {
-        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CHUNK));
-        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CHUNK + CHUNK_HI));
+        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_NN + SL_TN));
+        RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_NN + SL_TN + SL_HI));
         RNLA_CUDA(cudaFuncSetAttribute(i8_mma_tn_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM_HI));
         RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
         RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
@@ -633,10 +646,10 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool 
         attr = true;
     }
     if (p7)
-        slice_a_kernel<true><<<(unsigned)(s.rblocks * s.kb_total), 256, 2 * CHUNK + CHUNK_HI, c.stream>>>(
+        slice_a_kernel<true><<<(unsigned)(s.rblocks * s.kb_total * 2), 256, SL_NN + SL_TN + SL_HI, c.stream>>>(
             A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total, s.tn.as<uint8_t>(), s.kr_total, s.tnhi.as<uint8_t>());
     else
-        slice_a_kernel<false><<<(unsigned)(s.rblocks * s.kb_total), 256, 2 * CHUNK, c.stream>>>(
+        slice_a_kernel<false><<<(unsigned)(s.rblocks * s.kb_total * 2), 256, SL_NN + SL_TN, c.stream>>>(
             A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total, s.tn.as<uint8_t>(), s.kr_total, nullptr);
     g_kernel_launches += 3;
     RNLA_CUDA(cudaGetLastError());
