@@ -445,6 +445,12 @@ def run_ours(args):
         }
     if i8_level == 2 and fp64_block is None:
         roofline["fp64_dmma_kernels"] = "see all_fp64_passes"
+        ncu8 = os.path.join(ROOT, "profiles", "r01_ncu_traffic_int8.json")
+        if os.path.exists(ncu8) and m_local == ROWS_PER_GPU and n == N_COLS:
+            try:
+                roofline["traffic"] = json.load(open(ncu8)).get("split_bytes_per_launch")     # dram read + write of the split kernel (ncu)
+            except Exception:
+                pass
     ncu_traffic = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
     if os.path.exists(ncu_traffic) and i8_level != 2:
         try:
