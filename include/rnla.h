@@ -273,6 +273,31 @@ rnla_status rnla_sketch_saddle_point_precondition_dev(const double* dA, int64_t 
                                                       const double* dc, double mu, double epsilon, int64_t l, double sampling_factor,
                                                       double* dx, double* dy, int64_t* iterations, int32_t* converged);
 
+/* lsqr(a, b, damp, atol, btol, conlim, iter_lim, calc_var, x0) (reference src/solvers.rs:115-278, its translation of scipy
+ * 1.14.1 sparse.linalg.lsqr; called by no driver of the reference, SURVEY.md section 8f row 1 "wire lsqr").  The
+ * Golub-Kahan bidiagonalisation runs on the device (A streamed twice per iteration), the scalar recurrences on the host.
+ * iter_lim < 0: the reference's `None` (2 n).  x0 may be NULL.  x: n.  var: n (zeros unless calc_var; may be NULL when
+ * calc_var == 0).  arnorms: the reference's history of ||A^T r|| estimates (its 8th return value), the first
+ * min(n_arnorms, arnorms_cap) entries are written; may be NULL.  The other return values arrive in *result in the
+ * reference's order.  No validation in the reference (shape mismatches panic inside nalgebra): m >= 1, n >= 1 here. */
+typedef struct rnla_lsqr_result {
+    int64_t istop;      /* reason for termination, 0..7 as scipy */
+    int64_t itn;        /* iterations performed */
+    double r1norm;      /* norm(r) */
+    double r2norm;      /* sqrt(norm(r)^2 + damp^2 norm(x - x0)^2) */
+    double anorm;       /* estimate of the Frobenius norm of Abar */
+    double acond;       /* estimate of cond(Abar) */
+    double xnorm;       /* norm(x) */
+    int64_t n_arnorms;  /* length of the arnorm history */
+} rnla_lsqr_result;
+rnla_status rnla_lsqr(const double* A, int64_t m, int64_t n, const double* b, double damp, double atol, double btol, double conlim,
+                      int64_t iter_lim, int32_t calc_var, const double* x0, double* x, rnla_lsqr_result* result, double* arnorms,
+                      int64_t arnorms_cap, double* var);
+/* device buffers: dA / db the caller's row shard when a communicator is active; dx0, dx, dvar replicated; arnorms on the HOST */
+rnla_status rnla_lsqr_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db, double damp, double atol,
+                          double btol, double conlim, int64_t iter_lim, int32_t calc_var, const double* dx0, double* dx,
+                          rnla_lsqr_result* result, double* arnorms, int64_t arnorms_cap, double* dvar);
+
 /* ---- building blocks on device buffers (tests, benches, host mirrors) ---------------------------- */
 /* y (m) = A x (trans = 0) or y (n) = A^T x (trans != 0, all-reduced over the communicator): the two streaming kernels of CGLS */
 rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int32_t trans, const double* dx, double* dy);

@@ -93,6 +93,11 @@ int orc_cur(int randomised, const double* A, int64_t m, int64_t n, int64_t k, co
 /* src/sketch_and_precondition.rs:150-216 */
 int orc_saddle_point(const double* A, int64_t m, int64_t n, const double* b, const double* c, double mu, double epsilon, int64_t l,
                      double sampling_factor, int dist, uint64_t seed, double* x, double* y, int64_t* iters_out, int* converged_out);
+/* src/solvers.rs:115-278 (translation of scipy 1.14.1 lsqr).  iter_lim < 0: 2 n.  Returns the length of the arnorms history. */
+int64_t orc_lsqr(const double* a, int64_t m, int64_t n, const double* b, double damp, double atol, double btol, double conlim,
+                 int64_t iter_lim, int calc_var, const double* x0, double* x, int64_t* istop_out, int64_t* itn_out,
+                 double* r1norm_out, double* r2norm_out, double* anorm_out, double* acond_out, double* arnorms, double* xnorm_out,
+                 double* var);
 
 void orc_set_threads(int nthreads);
 int orc_get_threads(void);

@@ -402,6 +402,24 @@ def saddle_point(A, b, c, mu, epsilon, l, sampling_factor, dist=0, seed=0):
     return x, y, int(it.value), bool(conv.value)
 
 
+def lsqr(a, b, damp=0.0, atol=1e-6, btol=1e-6, conlim=1e8, iter_lim=None, calc_var=False, x0=None):
+    """src/solvers.rs:115-278 -> (x, istop, itn, r1norm, r2norm, anorm, acond, arnorms, xnorm, var), scipy's return order
+    with the arnorm history in place of the last arnorm, as the reference returns it"""
+    a = F(a); m, n = a.shape
+    b = F(np.asarray(b, dtype=np.float64).reshape(-1, 1))
+    lim = 2 * n if iter_lim is None else int(iter_lim)
+    x = np.zeros((n, 1), order="F"); var = np.zeros(n); hist = np.zeros(max(lim, 1))
+    x0f = None if x0 is None else F(np.asarray(x0, dtype=np.float64).reshape(-1, 1))
+    istop = i64(0); itn = i64(0)
+    r1 = C.c_double(0); r2 = C.c_double(0); an = C.c_double(0); ac = C.c_double(0); xn = C.c_double(0)
+    lib = load()
+    lib.orc_lsqr.restype = i64
+    nh = lib.orc_lsqr(p(a), i64(m), i64(n), p(b), C.c_double(damp), C.c_double(atol), C.c_double(btol), C.c_double(conlim), i64(lim),
+                      C.c_int(1 if calc_var else 0), p(x0f) if x0f is not None else None, p(x), C.byref(istop), C.byref(itn),
+                      C.byref(r1), C.byref(r2), C.byref(an), C.byref(ac), p(hist), C.byref(xn), p(var))
+    return x, int(istop.value), int(itn.value), r1.value, r2.value, an.value, ac.value, hist[:int(nh)].copy(), xn.value, var
+
+
 def set_threads(n):
     load().orc_set_threads(C.c_int(n))
 

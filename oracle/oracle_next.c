@@ -354,3 +354,109 @@ int orc_saddle_point(const double* A, int64_t m, int64_t n, const double* b, con
     free(St); free(Ask); free(U); free(sg); free(Vt);
     return rc;
 }
+
+/* ======================================================================== src/solvers.rs:65-98 sym_ortho, :115-278 lsqr
+ * (the reference's translation of scipy 1.14.1 sparse.linalg.lsqr), statement for statement on a dense a (m x n).
+ * x0 may be NULL.  arnorms: iter_lim doubles (history of ||A^T r|| estimates); returns its length.  var: n doubles. */
+static double sgn(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
+static void sym_ortho(double a, double b, double* c, double* s, double* r) {
+    if (b == 0.0) { *c = sgn(a); *s = 0.0; *r = fabs(a); }
+    else if (a == 0.0) { *c = 0.0; *s = sgn(b); *r = fabs(b); }
+    else if (fabs(b) > fabs(a)) { const double tau = a / b; *s = sgn(b) / sqrt(1.0 + tau * tau); *c = *s * tau; *r = b / *s; }
+    else { const double tau = b / a; *c = sgn(a) / sqrt(1.0 + tau * tau); *s = *c * tau; *r = a / *c; }
+}
+static double nrm2(const double* v, int64_t n) { double s = 0.0; for (int64_t i = 0; i < n; ++i) s += v[i] * v[i]; return sqrt(s); }
+
+int64_t orc_lsqr(const double* a, int64_t m, int64_t n, const double* b, double damp, double atol, double btol, double conlim,
+                 int64_t iter_lim, int calc_var, const double* x0, double* x, int64_t* istop_out, int64_t* itn_out,
+                 double* r1norm_out, double* r2norm_out, double* anorm_out, double* acond_out, double* arnorms, double* xnorm_out,
+                 double* var) {
+    const double eps = 2.220446049250313e-16;
+    if (iter_lim < 0) iter_lim = 2 * n;                                                  /* :140 */
+    for (int64_t i = 0; i < n; ++i) { var[i] = 0.0; x[i] = x0 ? x0[i] : 0.0; }
+    double* u = dalloc(m); double* v = dalloc(n); double* w = dalloc(n); double* t = dalloc(m > n ? m : n);
+    memcpy(u, b, (size_t)m * sizeof(double));
+    const double bnorm = nrm2(b, m);
+    double beta;
+    if (x0) { orc_gemm_nn(a, m, m, n, x, n, 1, t, m); for (int64_t i = 0; i < m; ++i) u[i] -= t[i]; beta = nrm2(u, m); }   /* :148-153 */
+    else beta = bnorm;
+    { const double sc = beta > 0.0 ? 1.0 / beta : 0.0; for (int64_t i = 0; i < m; ++i) u[i] *= sc; }                       /* :156 */
+    orc_gemm_tn(a, m, m, n, u, m, 1, v, n);                                              /* :157 */
+    double alfa = nrm2(v, n);
+    { const double sc = alfa > 0.0 ? 1.0 / alfa : 0.0; for (int64_t i = 0; i < n; ++i) v[i] *= sc; }
+    memcpy(w, v, (size_t)n * sizeof(double));
+    double rhobar = alfa, phibar = beta, rnorm = beta, r1norm = rnorm, r2norm = rnorm;
+    double anorm = 0.0, acond = 0.0, ddnorm = 0.0, res2 = 0.0, xnorm = 0.0, xxnorm = 0.0, z = 0.0, cs2 = -1.0, sn2 = 0.0;
+    const double dampsq = damp * damp;
+    double arnorm = alfa * beta;
+    int64_t itn = 0, istop = 0, nhist = 0;
+    if (arnorm == 0.0) {                                                                 /* :181-183 */
+        arnorms[0] = 0.0; nhist = 1;
+        *istop_out = 0; *itn_out = 0; *r1norm_out = beta; *r2norm_out = beta; *anorm_out = 0.0; *acond_out = 0.0; *xnorm_out = 0.0;
+        free(u); free(v); free(w); free(t);
+        return nhist;
+    }
+    const double ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
+    while (itn < iter_lim) {
+        arnorms[itn] = arnorm; nhist = itn + 1;
+        ++itn;
+        orc_gemm_nn(a, m, m, n, v, n, 1, t, m);
+        for (int64_t i = 0; i < m; ++i) u[i] = t[i] - alfa * u[i];                       /* :195 */
+        beta = nrm2(u, m);
+        if (beta > 0.0) {
+            for (int64_t i = 0; i < m; ++i) u[i] *= 1.0 / beta;
+            anorm = sqrt(anorm * anorm + alfa * alfa + beta * beta + dampsq);
+            orc_gemm_tn(a, m, m, n, u, m, 1, t, n);
+            for (int64_t i = 0; i < n; ++i) v[i] = t[i] - beta * v[i];                   /* :202 */
+            alfa = nrm2(v, n);
+            { const double sc = alfa > 0.0 ? 1.0 / alfa : 0.0; for (int64_t i = 0; i < n; ++i) v[i] *= sc; }
+        }
+        const double rhobar1 = sqrt(rhobar * rhobar + dampsq);
+        const double cs1 = rhobar / rhobar1, sn1 = damp / rhobar1;
+        const double psi = sn1 * phibar;
+        phibar *= cs1;
+        double cs, sn, rho;
+        sym_ortho(rhobar1, beta, &cs, &sn, &rho);
+        const double theta = sn * alfa;
+        rhobar = -cs * alfa;
+        const double phi = cs * phibar;
+        phibar *= sn;
+        const double tau = sn * phi;
+        const double t1 = phi / rho, t2 = -theta / rho;
+        double dkn = 0.0;
+        for (int64_t i = 0; i < n; ++i) {
+            const double dk = w[i] * (1.0 / rho);                                        /* :227 */
+            x[i] += t1 * w[i];
+            w[i] = v[i] + t2 * w[i];
+            dkn += dk * dk;
+            if (calc_var) var[i] += dk * dk;
+        }
+        ddnorm += dkn;
+        const double delta = sn2 * rho, gambar = -cs2 * rho, rhs = phi - delta * z, zbar = rhs / gambar;
+        xnorm = sqrt(xxnorm + zbar * zbar);
+        const double gamma = sqrt(gambar * gambar + theta * theta);
+        cs2 = gambar / gamma; sn2 = theta / gamma; z = rhs / gamma;
+        xxnorm += z * z;
+        acond = anorm * sqrt(ddnorm);
+        const double res1 = phibar * phibar;
+        res2 += psi * psi;
+        rnorm = sqrt(res1 + res2);
+        arnorm = alfa * fabs(tau);
+        const double r1sq = rnorm * rnorm - dampsq * xxnorm;
+        r1norm = sqrt(fabs(r1sq));
+        r2norm = rnorm;
+        const double test1 = rnorm / bnorm, test2 = arnorm / (anorm * rnorm + eps), test3 = 1.0 / (acond + eps);
+        const double tt1 = test1 / (1.0 + anorm * xnorm / bnorm), rtol = atol + btol * (anorm * xnorm / bnorm);
+        if (itn >= iter_lim) istop = 7;
+        if (1.0 + test3 <= 1.0) istop = 6;
+        if (1.0 + test2 <= 1.0) istop = 5;
+        if (1.0 + tt1 <= 1.0) istop = 4;
+        if (test3 <= ctol) istop = 3;
+        if (test2 <= atol) istop = 2;
+        if (test1 <= rtol) istop = 1;
+        if (istop != 0) break;
+    }
+    *istop_out = istop; *itn_out = itn; *r1norm_out = r1norm; *r2norm_out = r2norm; *anorm_out = anorm; *acond_out = acond; *xnorm_out = xnorm;
+    free(u); free(v); free(w); free(t);
+    return nhist;
+}

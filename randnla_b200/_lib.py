@@ -19,6 +19,12 @@ class Options(C.Structure):
                 ("passes_per_stab", c_i32), ("fused_sketch", c_i32), ("range_passes_int8", c_i32)]
 
 
+class LsqrResult(C.Structure):
+    """`rnla_lsqr_result` (include/rnla.h)."""
+    _fields_ = [("istop", c_i64), ("itn", c_i64), ("r1norm", c_f64), ("r2norm", c_f64), ("anorm", c_f64), ("acond", c_f64),
+                ("xnorm", c_f64), ("n_arnorms", c_i64)]
+
+
 # name -> (restype, argtypes); every symbol include/rnla.h declares
 SIGNATURES = {
     "rnla_version": (c_i32, []),
@@ -67,6 +73,9 @@ SIGNATURES = {
     "rnla_last_jacobi_sweeps": (c_i32, []),
     "rnla_lsrn_overdetermined": (c_i32, [P, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
     "rnla_lsrn_overdetermined_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
+    "rnla_lsqr": (c_i32, [P, c_i64, c_i64, P, c_f64, c_f64, c_f64, c_f64, c_i64, c_i32, P, P, C.POINTER(LsqrResult), P, c_i64, P]),
+    "rnla_lsqr_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, c_f64, c_f64, c_f64, c_f64, c_i64, c_i32, P, P, C.POINTER(LsqrResult), P,
+                      c_i64, P]),
     "rnla_plan_gemm": (None, [c_i64, c_i64, c_i64, c_i32, P]),
     "rnla_plan_saso_block": (c_i32, [c_i64, c_i32, c_i32, c_i64, c_i64, c_i32, P, P, c_i32, P]),
     "rnla_gemv_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, P]),

@@ -10,6 +10,7 @@
 //   randblas::pivot_decompositions::{qrcp, economic_qrcp}                                    <- src/pivot_decompositions.rs
 //   randblas::cqrrpt::sap_chol_qrcp                                                          <- src/cqrrpt.rs
 //   randblas::sketch_and_solve::{sketched_least_squares_qr, sketched_least_squares_svd}      <- src/sketch_and_solve.rs
+//   randblas::solvers::lsqr                                                                 <- src/solvers.rs:115-278
 //   randblas::id::{osid_qrcp, osid_randomised, two_sided_id(_randomised), cur(_randomised)}  <- src/id.rs
 //   randblas::errors::RandNLAError                                                           <- src/errors.rs
 // `Result<T, RandNLAError>` becomes "returns T or throws RandNLAError".  Header-only; link with -lrnla.
@@ -315,6 +316,34 @@ inline DMatrix sketched_least_squares_svd(const DMatrix& a, const DMatrix& b) {
     return x;
 }
 }  // namespace sketch_and_solve
+
+namespace solvers {
+// src/solvers.rs:115-278: the reference's 10-tuple, in its order
+struct LsqrOutput {
+    DMatrix x;                     // solution vector (n x 1)
+    size_t istop, itn;             // reason for termination, iterations performed
+    double r1norm, r2norm, anorm, acond;
+    std::vector<double> arnorms;   // history of the ||A^T r|| estimates
+    double xnorm;
+    DMatrix var;                   // variance estimate (n x 1), zeros unless calc_var
+};
+// iter_lim < 0 is the reference's `None` (2 n); x0 == nullptr its `None`
+inline LsqrOutput lsqr(const DMatrix& a, const DMatrix& b, double damp, double atol, double btol, double conlim, long iter_lim,
+                       bool calc_var, const DMatrix* x0) {
+    const size_t n = a.ncols();
+    if (b.nrows() != a.nrows() || (x0 && x0->nrows() != n)) throw std::invalid_argument("lsqr: shapes do not conform");   // nalgebra panics
+    LsqrOutput o{DMatrix(n, 1), 0, 0, 0, 0, 0, 0, {}, 0, DMatrix(n, 1)};
+    o.arnorms.assign((size_t)std::max<long>(iter_lim < 0 ? 2 * (long)n : iter_lim, 1), 0.0);
+    rnla_lsqr_result r{};
+    errors::check(rnla_lsqr(a.as_ptr(), (int64_t)a.nrows(), (int64_t)n, b.as_ptr(), damp, atol, btol, conlim, (int64_t)iter_lim,
+                            calc_var ? 1 : 0, x0 ? x0->as_ptr() : nullptr, o.x.as_mut_ptr(), &r, o.arnorms.data(),
+                            (int64_t)o.arnorms.size(), o.var.as_mut_ptr()));
+    o.istop = (size_t)r.istop; o.itn = (size_t)r.itn; o.r1norm = r.r1norm; o.r2norm = r.r2norm; o.anorm = r.anorm; o.acond = r.acond;
+    o.xnorm = r.xnorm;
+    o.arnorms.resize((size_t)std::min<int64_t>(r.n_arnorms, (int64_t)o.arnorms.size()));
+    return o;
+}
+}  // namespace solvers
 
 namespace id {
 using sketch::MatrixAttribute;

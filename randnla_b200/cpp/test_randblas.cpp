@@ -122,6 +122,16 @@ int main() {
         auto [sx, sy] = sketch_and_precondition::sketch_saddle_point_precondition(L, bb, DMatrix(), 0.0, 1e-12, 100, 2.0);
         double d = 0; for (size_t i = 0; i < k; ++i) d = std::fmax(d, std::fabs(sx(i, 0) - xt(i, 0)));
         CHECK(d < 1e-8 && sy.norm() < 1e-8 * bb.norm());
+        // src/solvers.rs:391-410 (test_simple_system) and a consistent tall system through lsqr
+        DMatrix a3 = DMatrix::from_fn(3, 2, [](size_t i, size_t j) { return (i == j || i == j + 1) ? 1.0 : 0.0; });
+        DMatrix b0(3, 1), b1 = DMatrix::from_fn(3, 1, [](size_t i, size_t) { return i == 0 ? 1.0 : (i == 2 ? -1.0 : 0.0); });
+        auto z0 = solvers::lsqr(a3, b0, 0.0, 1e-8, 1e-8, 1e8, -1, false, nullptr);
+        CHECK(z0.istop == 0 && z0.itn == 0 && z0.x.norm() == 0.0 && z0.arnorms.size() == 1 && z0.arnorms[0] == 0.0);
+        auto z1 = solvers::lsqr(a3, b1, 0.0, 1e-8, 1e-8, 1e8, -1, false, nullptr);
+        CHECK(std::fabs(z1.x(0, 0) - 1.0) < 1e-2 && std::fabs(z1.x(1, 0) + 1.0) < 1e-2);
+        auto z2 = solvers::lsqr(L, bb, 0.0, 1e-13, 1e-13, 1e8, -1, true, nullptr);
+        d = 0; for (size_t i = 0; i < k; ++i) d = std::fmax(d, std::fabs(z2.x(i, 0) - xt(i, 0)));
+        CHECK(d < 1e-8 && z2.istop >= 1 && z2.istop <= 2 && z2.arnorms.size() == z2.itn && z2.var(0, 0) > 0.0);
     }
     std::printf(failures ? "CPP MIRROR: %d FAILURES\n" : "CPP MIRROR: ALL OK\n", failures);
     return failures ? 1 : 0;

@@ -540,6 +540,36 @@ rnla_status rnla_lsrn_overdetermined(const double* A, int64_t m, int64_t n, cons
     return d2h(x, dx.d(), (size_t)n);
 }
 
+// ---- lsqr (reference src/solvers.rs:115-278)
+rnla_status rnla_lsqr_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db, double damp, double atol,
+                          double btol, double conlim, int64_t iter_lim, int32_t calc_var, const double* dx0, double* dx,
+                          rnla_lsqr_result* result, double* arnorms, int64_t arnorms_cap, double* dvar) {
+    RNLA_API_GUARD;
+    if (!result || !dx || !dA || !db) return fail(RNLA_ERR_INVALID_PARAMETERS, "lsqr: null argument");
+    if (m_local < 0 || n < 1) return fail(RNLA_ERR_INVALID_DIMENSIONS, "lsqr: a must have at least one row and one column");
+    RNLA_TRY(ensure_ctx());
+    return dev_lsqr(dA, lda, m_local, n, db, damp, atol, btol, conlim, iter_lim, calc_var, dx0, dx, result, arnorms, arnorms_cap, dvar);
+}
+rnla_status rnla_lsqr(const double* A, int64_t m, int64_t n, const double* b, double damp, double atol, double btol, double conlim,
+                      int64_t iter_lim, int32_t calc_var, const double* x0, double* x, rnla_lsqr_result* result, double* arnorms,
+                      int64_t arnorms_cap, double* var) {
+    RNLA_API_GUARD;
+    if (!result || !x || !A || !b) return fail(RNLA_ERR_INVALID_PARAMETERS, "lsqr: null argument");
+    if (calc_var && !var) return fail(RNLA_ERR_INVALID_PARAMETERS, "lsqr: calc_var needs a var buffer");
+    if (m < 1 || n < 1) return fail(RNLA_ERR_INVALID_DIMENSIONS, "lsqr: a must have at least one row and one column");
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, db, dx0, dx, dvar;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_TRY(h2d(db, b, (size_t)m));
+    if (x0) RNLA_TRY(h2d(dx0, x0, (size_t)n));
+    RNLA_CUDA(dx.alloc((size_t)n * 8));
+    if (var) RNLA_CUDA(dvar.alloc((size_t)n * 8));
+    RNLA_TRY(dev_lsqr(dA.d(), m, m, n, db.d(), damp, atol, btol, conlim, iter_lim, calc_var, x0 ? dx0.d() : nullptr, dx.d(), result,
+                      arnorms, arnorms_cap, var ? dvar.d() : nullptr));
+    if (var) RNLA_TRY(d2h(var, dvar.d(), (size_t)n));
+    return d2h(x, dx.d(), (size_t)n);
+}
+
 rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int32_t trans, const double* dx, double* dy) {
     RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());

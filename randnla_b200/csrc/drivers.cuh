@@ -55,6 +55,11 @@ rnla_status dev_lsrn(const double* A, int64_t lda, int64_t m_local, int64_t n, c
                      double sampling_factor, int kind, int dist_or_width, int zeta, uint64_t seed, double* x,
                      int64_t* iters_out, int32_t* converged_out);
 
+// lsqr of src/solvers.rs:115-278 on device buffers (u row-sharded with A; v, w, x, var replicated); arnorms is a HOST array
+rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double damp, double atol, double btol,
+                     double conlim, int64_t iter_lim, int calc_var, const double* x0, double* x, rnla_lsqr_result* res,
+                     double* arnorms, int64_t arnorms_cap, double* var);
+
 rnla_status dev_small_gemv(const double* M, int64_t ld, int n, int trans, const double* x, double* y);
 rnla_status dev_axpby_vec(double a, const double* x, double b, double* y, int64_t n);
 rnla_status dev_cgls_operator(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, const double* M, double* z,

@@ -430,4 +430,197 @@ rnla_status dev_lsrn(const double* A, int64_t lda, int64_t m_local, int64_t n, c
     return RNLA_OK;
 }
 
+// ======================================================================================================================
+// lsqr(a, b, damp, atol, btol, conlim, iter_lim, calc_var, x0) of src/solvers.rs:115-278 (the reference's translation of
+// scipy 1.14.1 sparse.linalg.lsqr; sym_ortho :84-103), statement for statement on the device.  The Golub-Kahan vectors stay
+// in HBM: u (m_local, row-sharded with A) and v, w, x, var (n, replicated); the scalar recurrences (plane rotations, norm
+// estimates, stopping tests) run on the host from the two norms each iteration reads back.  Per iteration A is streamed
+// twice (A v and A^T u, 2 x 8 m n bytes, the two HBM-bound kernels of CGLS above); the vector updates are fused with their
+// norms: u = A v - alfa u with ||u||, v = A^T u - beta v with ||v||, and the x / w / var update with ||dk||^2.
+
+namespace {
+
+// y = a x + b y, block partials of sum y_i^2 (fixed order) -> scratch
+__global__ void __launch_bounds__(256)
+axpby_sumsq_kernel(double a, const double* __restrict__ x, double b, double* __restrict__ y, int64_t n, double* __restrict__ scratch) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = a * x[i] + b * y[i];
+        y[i] = v;
+        s = fma(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w]; scratch[blockIdx.x] = t; }
+}
+// :224-232  dk = w / rho;  x += t1 w;  w = v + t2 w;  var += dk .* dk;  block partials of ||dk||^2 -> scratch
+__global__ void __launch_bounds__(256)
+lsqr_update_kernel(double t1, double t2, double inv_rho, const double* __restrict__ v, double* __restrict__ w, double* __restrict__ x,
+                   double* __restrict__ var, int64_t n, double* __restrict__ scratch) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double wi = w[i], dk = wi * inv_rho;
+        x[i] += t1 * wi;
+        w[i] = v[i] + t2 * wi;
+        s = fma(dk, dk, s);
+        if (var) var[i] += dk * dk;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int k = 0; k < 8; ++k) t += red[k]; scratch[blockIdx.x] = t; }
+}
+
+inline double sgn(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }                          // :77-81
+inline void sym_ortho(double a, double b, double* c, double* s, double* r) {                               // :84-103
+    if (b == 0.0) { *c = sgn(a); *s = 0.0; *r = std::fabs(a); }
+    else if (a == 0.0) { *c = 0.0; *s = sgn(b); *r = std::fabs(b); }
+    else if (std::fabs(b) > std::fabs(a)) { const double tau = a / b; *s = sgn(b) / std::sqrt(1.0 + tau * tau); *c = *s * tau; *r = b / *s; }
+    else { const double tau = b / a; *c = sgn(a) / std::sqrt(1.0 + tau * tau); *s = *c * tau; *r = a / *c; }
+}
+
+// host value of the sum the last *_sumsq / update kernel left in scratch (all-reduced over the row shards when `sharded`)
+rnla_status finish_sum(Solver& S, int nb, bool sharded, double* out) {
+    Ctx& c = S.c;
+    dot_final_kernel<<<1, 32, 0, c.stream>>>(S.scratch.d(), nb, S.scal.d());
+    ++g_kernel_launches;
+    RNLA_CUDA(cudaGetLastError());
+    if (sharded && c.nranks > 1) RNLA_TRY(allreduce_sum_f64(S.scal.d(), 1));
+    RNLA_CUDA(cudaMemcpyAsync(out, S.scal.p, 8, cudaMemcpyDeviceToHost, c.stream));
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    return RNLA_OK;
+}
+// y = a x + b y; *nrm = ||y||_2
+rnla_status axpby_nrm2(Solver& S, double a, const double* x, double b, double* y, int64_t n, bool sharded, double* nrm) {
+    const int nb = blocks_for(n, 1024);
+    axpby_sumsq_kernel<<<nb, 256, 0, S.c.stream>>>(a, x, b, y, n, S.scratch.d());
+    ++g_kernel_launches;
+    RNLA_CUDA(cudaGetLastError());
+    double ss = 0.0;
+    RNLA_TRY(finish_sum(S, nb, sharded, &ss));
+    *nrm = std::sqrt(ss);
+    return RNLA_OK;
+}
+
+}  // namespace
+
+rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double damp, double atol, double btol,
+                     double conlim, int64_t iter_lim, int calc_var, const double* x0, double* x, rnla_lsqr_result* res,
+                     double* arnorms, int64_t arnorms_cap, double* var) {
+    Ctx& c = ctx();
+    phases_reset();
+    PhaseScope ph("lsqr");
+    if (n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "lsqr: a needs at least one column");
+    Solver S(c);
+    RNLA_TRY(S.init());
+    const double eps = 2.220446049250313e-16;
+    if (iter_lim < 0) iter_lim = 2 * n;                                                                   // :140
+    const int64_t mm = std::max<int64_t>(m_local, 1);
+    DevBuf u, v, w, tm, tn, varb;
+    RNLA_CUDA(u.alloc((size_t)mm * 8)); RNLA_CUDA(tm.alloc((size_t)mm * 8));
+    RNLA_CUDA(v.alloc((size_t)n * 8)); RNLA_CUDA(w.alloc((size_t)n * 8)); RNLA_CUDA(tn.alloc((size_t)n * 8));
+    double* dvar = nullptr;
+    if (calc_var) {
+        dvar = var;
+        if (!dvar) { RNLA_CUDA(varb.alloc((size_t)n * 8)); dvar = varb.d(); }
+    }
+    if (var) RNLA_CUDA(cudaMemsetAsync(var, 0, (size_t)n * 8, c.stream));                                 // :142
+    if (dvar && dvar != var) RNLA_CUDA(cudaMemsetAsync(dvar, 0, (size_t)n * 8, c.stream));
+    if (x0) { if (x0 != x) RNLA_CUDA(cudaMemcpyAsync(x, x0, (size_t)n * 8, cudaMemcpyDeviceToDevice, c.stream)); }
+    else RNLA_CUDA(cudaMemsetAsync(x, 0, (size_t)n * 8, c.stream));                                       // :143
+    RNLA_CUDA(cudaMemcpyAsync(u.p, b, (size_t)m_local * 8, cudaMemcpyDeviceToDevice, c.stream));          // :144
+    double bb = 0.0;
+    RNLA_TRY(S.dot(b, b, m_local, true, &bb));
+    const double bnorm = std::sqrt(bb);                                                                   // :145
+    double beta = bnorm;
+    if (x0) {                                                                                             // :148-153
+        RNLA_TRY(dev_gemv_n(A, lda, m_local, n, x, tm.d()));
+        RNLA_TRY(axpby_nrm2(S, -1.0, tm.d(), 1.0, u.d(), m_local, true, &beta));
+    }
+    RNLA_TRY(S.axpby(0.0, u.d(), beta > 0.0 ? 1.0 / beta : 0.0, u.d(), m_local));                         // :156
+    RNLA_TRY(dev_gemv_t(A, lda, m_local, n, u.d(), v.d()));                                               // :157
+    double vv = 0.0;
+    RNLA_TRY(S.dot(v.d(), v.d(), n, false, &vv));
+    double alfa = std::sqrt(vv);                                                                          // :158
+    RNLA_TRY(S.axpby(0.0, v.d(), alfa > 0.0 ? 1.0 / alfa : 0.0, v.d(), n));                               // :160
+    RNLA_CUDA(cudaMemcpyAsync(w.p, v.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c.stream));              // :161
+    double rhobar = alfa, phibar = beta, rnorm = beta, r1norm = rnorm, r2norm = rnorm;
+    double anorm = 0.0, acond = 0.0, ddnorm = 0.0, res2 = 0.0, xnorm = 0.0, xxnorm = 0.0, z = 0.0, cs2 = -1.0, sn2 = 0.0;
+    const double dampsq = damp * damp;
+    double arnorm = alfa * beta;
+    int64_t itn = 0, istop = 0, nhist = 0;
+    if (arnorm == 0.0) {                                                                                  // :181-183
+        if (arnorms && arnorms_cap > 0) arnorms[0] = 0.0;
+        RNLA_CUDA(cudaStreamSynchronize(c.stream));
+        *res = rnla_lsqr_result{0, 0, beta, beta, 0.0, 0.0, 0.0, 1};
+        return RNLA_OK;
+    }
+    const double ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
+    while (itn < iter_lim) {
+        if (arnorms && itn < arnorms_cap) arnorms[itn] = arnorm;                                          // :191
+        nhist = ++itn;
+        RNLA_TRY(dev_gemv_n(A, lda, m_local, n, v.d(), tm.d()));
+        RNLA_TRY(axpby_nrm2(S, 1.0, tm.d(), -alfa, u.d(), m_local, true, &beta));                         // :195-196
+        if (beta > 0.0) {
+            RNLA_TRY(S.axpby(0.0, u.d(), 1.0 / beta, u.d(), m_local));                                    // :199
+            anorm = std::sqrt(anorm * anorm + alfa * alfa + beta * beta + dampsq);                        // :200
+            RNLA_TRY(dev_gemv_t(A, lda, m_local, n, u.d(), tn.d()));
+            RNLA_TRY(axpby_nrm2(S, 1.0, tn.d(), -beta, v.d(), n, false, &alfa));                          // :202-203
+            RNLA_TRY(S.axpby(0.0, v.d(), alfa > 0.0 ? 1.0 / alfa : 0.0, v.d(), n));                       // :204
+        }
+        const double rhobar1 = std::sqrt(rhobar * rhobar + dampsq);                                       // :208-212
+        const double cs1 = rhobar / rhobar1, sn1 = damp / rhobar1;
+        const double psi = sn1 * phibar;
+        phibar *= cs1;
+        double cs, sn, rho;
+        sym_ortho(rhobar1, beta, &cs, &sn, &rho);                                                         // :214
+        const double theta = sn * alfa;
+        rhobar = -cs * alfa;
+        const double phi = cs * phibar;
+        phibar *= sn;
+        const double tau = sn * phi;
+        const double t1 = phi / rho, t2 = -theta / rho;                                                   // :222-223
+        {
+            const int nb = blocks_for(n, 1024);
+            lsqr_update_kernel<<<nb, 256, 0, c.stream>>>(t1, t2, 1.0 / rho, v.d(), w.d(), x, dvar, n, S.scratch.d());   // :224-232
+            ++g_kernel_launches;
+            RNLA_CUDA(cudaGetLastError());
+            double dkn = 0.0;
+            RNLA_TRY(finish_sum(S, nb, false, &dkn));
+            ddnorm += dkn;
+        }
+        const double delta = sn2 * rho, gambar = -cs2 * rho, rhs = phi - delta * z, zbar = rhs / gambar;  // :235-244
+        xnorm = std::sqrt(xxnorm + zbar * zbar);
+        const double gamma = std::sqrt(gambar * gambar + theta * theta);
+        cs2 = gambar / gamma; sn2 = theta / gamma; z = rhs / gamma;
+        xxnorm += z * z;
+        acond = anorm * std::sqrt(ddnorm);                                                                // :247-251
+        const double res1 = phibar * phibar;
+        res2 += psi * psi;
+        rnorm = std::sqrt(res1 + res2);
+        arnorm = alfa * std::fabs(tau);
+        const double r1sq = rnorm * rnorm - dampsq * xxnorm;                                              // :253-255
+        r1norm = std::sqrt(std::fabs(r1sq));
+        r2norm = rnorm;
+        const double test1 = rnorm / bnorm, test2 = arnorm / (anorm * rnorm + eps), test3 = 1.0 / (acond + eps);   // :257-261
+        const double tt1 = test1 / (1.0 + anorm * xnorm / bnorm), rtol = atol + btol * (anorm * xnorm / bnorm);
+        if (itn >= iter_lim) istop = 7;                                                                   // :264-270
+        if (1.0 + test3 <= 1.0) istop = 6;
+        if (1.0 + test2 <= 1.0) istop = 5;
+        if (1.0 + tt1 <= 1.0) istop = 4;
+        if (test3 <= ctol) istop = 3;
+        if (test2 <= atol) istop = 2;
+        if (test1 <= rtol) istop = 1;
+        if (istop != 0) break;
+    }
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    *res = rnla_lsqr_result{istop, itn, r1norm, r2norm, anorm, acond, xnorm, nhist};
+    return RNLA_OK;
+}
+
 }  // namespace rnla

@@ -43,4 +43,22 @@ pub fn last_message() -> String {
         let p = rnla_last_error_message();
         if p.is_null() { String::new() } else { std::ffi::CStr::from_ptr(p).to_string_lossy().into_owned() }
     }
+    // lsqr (reference src/solvers.rs:115-278)
+    pub fn rnla_lsqr(a: *const c_double, m: i64, n: i64, b: *const c_double, damp: c_double, atol: c_double, btol: c_double,
+                     conlim: c_double, iter_lim: i64, calc_var: c_int, x0: *const c_double, x: *mut c_double,
+                     result: *mut RnlaLsqrResult, arnorms: *mut c_double, arnorms_cap: i64, var: *mut c_double) -> c_int;
+}
+
+/// `rnla_lsqr_result` (include/rnla.h)
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct RnlaLsqrResult {
+    pub istop: i64,
+    pub itn: i64,
+    pub r1norm: c_double,
+    pub r2norm: c_double,
+    pub anorm: c_double,
+    pub acond: c_double,
+    pub xnorm: c_double,
+    pub n_arnorms: i64,
 }

@@ -11,3 +11,4 @@ pub mod pivot_decompositions;
 pub mod cqrrpt;
 pub mod sketch_and_solve;
 pub mod id;
+pub mod solvers;

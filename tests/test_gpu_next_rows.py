@@ -292,6 +292,109 @@ def test_saddle_point_reference_errors(rb):
         sp.sketch_saddle_point_precondition(A.T.copy(), random_matrix(10, 1, seed=4), random_matrix(100, 1, seed=5), 1.0, 1e-4, 10, 1.5)
 
 
+# ---------------------------------------------------------------------------------------------------------- lsqr
+def _lsq_problem(m, n, cond, seed, consistent=False):
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = np.asfortranarray((U * np.logspace(0, -np.log10(cond), n)) @ V.T)
+    x = rng.uniform(-100, 100, n)
+    b = A @ x + (0.0 if consistent else 1e-2) * rng.standard_normal(m)
+    return A, b
+
+
+@pytest.mark.parametrize("m,n,cond,damp,calc_var,use_x0,consistent", [
+    (200, 100, 10.0, 0.0, False, False, False),       # test_overdetermined_system's shape (src/solvers.rs:413-468)
+    (3001, 257, 1e3, 0.0, True, False, False),        # odd sizes: scalar tails of both streaming kernels
+    (3000, 40, 1e3, 0.5, True, True, False),
+    (120, 120, 50.0, 0.0, False, True, True),
+    (20000, 300, 1e6, 1e-3, False, False, False),
+])
+def test_lsqr_matches_oracle(rb, orc, m, n, cond, damp, calc_var, use_x0, consistent):
+    """src/solvers.rs:115-278.  (1) six iterations with the stopping tests off: every return value to 1e-10 (summation orders
+    differ; beyond ~8 iterations the unorthogonalised recurrences amplify rounding, see tests/test_oracle_next_rows.py);
+    (2) to convergence: same stopping reason, iteration count within a few, residual norm to 1e-6 / 1e-3."""
+    from randnla_b200 import solvers
+    A, b = _lsq_problem(m, n, cond, seed=m + n, consistent=consistent)
+    x0 = np.random.default_rng(9).standard_normal(n) if use_x0 else None
+    got = solvers.lsqr(A, b, damp, 0.0, 0.0, 0.0, 6, calc_var, x0)
+    ref = orc.lsqr(A, b, damp, 0.0, 0.0, 0.0, 6, calc_var, x0)
+    assert got[1] == ref[1] == 7 and got[2] == ref[2] == 6
+    assert np.abs(got[0] - ref[0]).max() <= 1e-10 * np.abs(ref[0]).max()
+    for i in (3, 4, 5, 6, 8):
+        assert abs(got[i] - ref[i]) <= 1e-10 * abs(ref[i]), i
+    assert len(got[7]) == 6 and np.abs(got[7] - ref[7]).max() <= 1e-10 * ref[7].max()
+    if calc_var:
+        assert np.abs(got[9] - ref[9]).max() <= 1e-10 * ref[9].max()
+    else:
+        assert not got[9].any()
+    got = solvers.lsqr(A, b, damp, 1e-8, 1e-8, 1e8, None, calc_var, x0)
+    ref = orc.lsqr(A, b, damp, 1e-8, 1e-8, 1e8, None, calc_var, x0)
+    assert got[1] == ref[1] and abs(got[2] - ref[2]) <= max(2, ref[2] // 20)
+    assert len(got[7]) == got[2]
+    if cond <= 50.0:
+        assert np.abs(got[0] - ref[0]).max() <= 1e-6 * np.abs(ref[0]).max()
+    assert abs(got[3] - ref[3]) <= (1e-6 if cond <= 50.0 else 1e-3) * abs(ref[3]) + 1e-7 * np.linalg.norm(b)
+
+
+def test_lsqr_reference_cases(rb):
+    """test_simple_system (src/solvers.rs:391-410) and test_overdetermined_system (:413-468, against LAPACK instead of
+    nalgebra's SVD solve); early return on b = 0 (:181-183); iter_lim (istop = 7); scipy's lsqr, which the reference
+    translates, gives the same answer"""
+    from scipy.sparse.linalg import lsqr as sp_lsqr
+    from randnla_b200 import solvers
+    A = np.asfortranarray(np.array([[1.0, 0.0], [1.0, 1.0], [0.0, 1.0]]))
+    x, istop, itn, r1, r2, an, ac, hist, xn, var = solvers.lsqr(A, np.zeros(3), 0.0, 1e-8, 1e-8, 1e8, None, False, None)
+    assert not x.any() and istop == 0 and itn == 0 and list(hist) == [0.0] and r1 == 0.0 and an == 0.0
+    x, istop, itn, *_ = solvers.lsqr(A, np.array([1.0, 0.0, -1.0]), 0.0, 1e-8, 1e-8, 1e8, None, False, None)
+    assert abs(x[0, 0] - 1.0) < 1e-12 and abs(x[1, 0] + 1.0) < 1e-12 and istop in (1, 2) and itn <= 2
+    A, b = _lsq_problem(200, 100, 10.0, seed=2)
+    x, istop, itn, r1, *_ = solvers.lsqr(A, b, 0.0, 1e-12, 1e-12, 1e8, None, False, None)
+    xs = np.linalg.lstsq(A, b, rcond=None)[0]
+    assert np.abs(x[:, 0] - xs).max() <= 1e-8 * np.abs(xs).max()
+    assert abs(r1 - np.linalg.norm(A @ xs - b)) <= 1e-8 * r1
+    ref = sp_lsqr(A, b, atol=1e-12, btol=1e-12, conlim=1e8, iter_lim=200)
+    assert istop == ref[1] and abs(itn - ref[2]) <= 2 and np.abs(x[:, 0] - ref[0]).max() <= 1e-8 * np.abs(xs).max()
+    x, istop, itn, *_, hist, xn, var = solvers.lsqr(A, b, 0.0, 1e-14, 1e-14, 1e8, 7, False, None)
+    assert istop == 7 and itn == 7 and len(hist) == 7
+    with pytest.raises(ValueError):
+        solvers.lsqr(A, b[:-1])
+
+
+def test_lsqr_at_scale_on_device_buffers(rb):
+    """rnla_lsqr_dev on a 1 000 000 x 500 system (4 GB) resident in HBM: planted solution recovered, the normal-equations
+    residual is at rounding level, and the running estimates (r1norm, xnorm, anorm <= ||A||_F) agree with the true values"""
+    import ctypes as C
+    import torch
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    m, n = 1_000_000, 500
+    dA = rt.empty_colmajor(m, n); pA, lda = rt.dev_ptr_ld(dA)
+    _lib.check(lib.rnla_sketch_fill_dev(0, 0, 31, 4, m, n, 0, pA, lda)); rt.synchronize()
+    torch.manual_seed(5)
+    xt = torch.rand(n, 1, dtype=torch.float64, device="cuda") * 200 - 100
+    noise = torch.randn(m, 1, dtype=torch.float64, device="cuda") * 1e-2
+    db = rt.empty_colmajor(m, 1); db.copy_(dA @ xt + noise)
+    dx = rt.empty_colmajor(n, 1); dvar = torch.zeros(n, dtype=torch.float64, device="cuda")
+    res = _lib.LsqrResult(); hist = np.zeros(2 * n)
+    before = rt.kernel_launches()
+    _lib.check(lib.rnla_lsqr_dev(pA, lda, m, n, C.c_void_p(db.data_ptr()), 0.0, 1e-13, 1e-13, 1e8, -1, 1, None,
+                                 C.c_void_p(dx.data_ptr()), C.byref(res), C.c_void_p(hist.ctypes.data), hist.size,
+                                 C.c_void_p(dvar.data_ptr())))
+    rt.synchronize()
+    assert rt.kernel_launches() > before
+    assert res.istop in (1, 2) and 0 < res.itn < 60 and res.n_arnorms == res.itn
+    r = db - dA @ dx
+    assert float(torch.linalg.vector_norm(dA.T @ r)) <= 1e-9 * float(torch.linalg.vector_norm(dA)) * float(torch.linalg.vector_norm(r))
+    assert float(torch.linalg.vector_norm(dx - xt) / torch.linalg.vector_norm(xt)) < 1e-6        # noise 1e-2 / sqrt(m) per entry
+    assert abs(res.r1norm - float(torch.linalg.vector_norm(r))) <= 1e-8 * res.r1norm
+    assert abs(res.xnorm - float(torch.linalg.vector_norm(dx))) <= 1e-8 * res.xnorm
+    assert res.anorm <= 1.001 * float(torch.linalg.vector_norm(dA)) * np.sqrt(res.itn)
+    assert float(dvar.min()) > 0.0
+    del dA, db, r
+    torch.cuda.empty_cache()
+
+
 # -------------------------------------------------------------------------------------------- committed fixtures
 def test_next_rows_golden_vectors(rb):
     """tests/golden/next_rows_golden.npz: oracle outputs committed with their generating script; the CUDA path reproduces

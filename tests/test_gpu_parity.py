@@ -914,3 +914,31 @@ def test_rand_evd1_int8_passes_match_the_oracle(rb, orc, level):
     assert np.max(np.abs(lam - lamo) / np.abs(lamo)) < SIG_TOL
     assert np.abs(V.T @ V - np.eye(k)).max() < 1e-12
     assert np.linalg.norm(A @ V - V * lam) <= 1e-8 * np.abs(lam).max()
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_int8_passes_on_degenerate_inputs(rb, orc, level):
+    """exactly rank-deficient panels (rank 30 < l = 60), a zero matrix and rows of wildly different scale with the passes on
+    the integer tensor cores: same answers as the oracle, Orth(0) = I semantics preserved (src/lora_drivers.rs:341-357)"""
+    from randnla_b200 import runtime as rt, lora_drivers as ld
+    A = rank_k_matrix(4200, 1100, 30, seed=8)
+    with rt.options(range_passes_int8=level):
+        U, S, Vt = ld.rand_svd(A, 50, 1e-6, 10)
+        assert "i8:split(A)" in [nm for nm, _ in rt.timings()]
+    so = np.linalg.svd(A, compute_uv=False)
+    sg = np.diag(S)
+    assert np.max(np.abs(sg[:30] - so[:30]) / so[:30]) < SIG_TOL
+    assert sg[30:].max() <= 1e-9 * so[0]
+    assert np.abs(U.T @ U - np.eye(50)).max() < 1e-11
+    assert np.linalg.norm(U @ S @ Vt - A) <= 1e-9 * np.linalg.norm(A)
+    with rt.options(range_passes_int8=level):
+        U, S, Vt = ld.rand_svd(np.zeros((4096, 1024), order="F"), 5, 0.1, 5)
+    assert not S.any() and np.abs(U[:5, :5] - np.eye(5)).max() < 1e-12 and np.abs(Vt[:5, :5] - np.eye(5)).max() < 1e-12
+    # rows scaled over 16 decades: the split is relative to each row's own maximum
+    rng = np.random.default_rng(3)
+    B = rank_k_matrix(4100, 1050, 12, seed=9) * np.logspace(-8, 8, 4100).reshape(-1, 1)
+    B = np.asfortranarray(B)
+    with rt.options(range_passes_int8=level):
+        U, S, Vt = ld.rand_svd(B, 12, 1e-6, 8)
+    so = np.linalg.svd(B, compute_uv=False)[:12]
+    assert np.max(np.abs(np.diag(S) - so) / so) < 1e-9

@@ -209,3 +209,72 @@ def test_next_rows_validation_precedes_device_access():
     assert str(e.value) == "Sampling factor must be greater than 1, current input is 0.5"
     with pytest.raises(NotOverdetermined):
         rb.sketch_and_precondition.sketch_saddle_point_precondition(A.T.copy(), c, b, 1.0, 1e-4, 10, 1.5)
+
+
+# ---- lsqr (src/solvers.rs:115-278): the reference says it is a translation of scipy 1.14.1's lsqr, so scipy's own lsqr is the
+# ---- known-answer generator: same iterates, same stopping rule, same estimates on the same inputs
+def _lsq_problem(m, n, cond, seed, consistent=False):
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = np.asfortranarray((U * np.logspace(0, -np.log10(cond), n)) @ V.T)
+    x = rng.uniform(-100, 100, n)
+    b = A @ x + (0.0 if consistent else 1e-2) * rng.standard_normal(m)
+    return A, b
+
+
+@pytest.mark.parametrize("m,n,cond,damp,calc_var,use_x0,consistent", [
+    (200, 100, 10.0, 0.0, False, False, False),     # test_overdetermined_system's shape (:413-468)
+    (300, 40, 1e3, 0.0, True, False, False),
+    (300, 40, 1e3, 0.5, True, True, False),
+    (120, 120, 50.0, 0.0, False, True, True),
+    (500, 30, 1e6, 1e-3, False, False, False),
+    (64, 90, 20.0, 0.1, True, False, False),         # underdetermined with damping
+])
+def test_lsqr_matches_scipy(orc, m, n, cond, damp, calc_var, use_x0, consistent):
+    from scipy.sparse.linalg import lsqr as sp_lsqr
+    A, b = _lsq_problem(max(m, n), min(m, n), cond, seed=m + n, consistent=consistent)
+    if m < n:
+        A = np.asfortranarray(A.T); b = np.random.default_rng(5).standard_normal(m)
+    x0 = np.random.default_rng(9).standard_normal(A.shape[1]) if use_x0 else None
+    # (1) a fixed number of iterations with the stopping tests switched off: every return value agrees to rounding
+    # (short: without reorthogonalisation the Golub-Kahan recurrences amplify rounding differences once Ritz values converge --
+    # measured here: 1e-15 up to 8 iterations, 1e-8 at 12, 1e-5 at 16 on the cond 1e3 case)
+    K = 6
+    got = orc.lsqr(A, b, damp=damp, atol=0.0, btol=0.0, conlim=0.0, iter_lim=K, calc_var=calc_var, x0=x0)
+    ref = sp_lsqr(A, b, damp=damp, atol=0.0, btol=0.0, conlim=0.0, iter_lim=K, calc_var=calc_var, x0=x0)
+    x, istop, itn, r1, r2, an, ac, hist, xn, var = got
+    assert istop == ref[1] == 7 and itn == ref[2] == K
+    assert np.abs(x[:, 0] - ref[0]).max() <= 1e-10 * np.abs(ref[0]).max()
+    for g, r in zip((r1, r2, an, ac, xn), (ref[3], ref[4], ref[5], ref[6], ref[8])):
+        assert abs(g - r) <= 1e-10 * abs(r)
+    assert len(hist) == itn and np.all(hist >= 0)
+    if calc_var:
+        assert np.abs(var - ref[9]).max() <= 1e-10 * np.abs(ref[9]).max()
+    else:
+        assert not var.any()
+    # (2) run to convergence: same stopping reason, the iteration count may differ slightly where a test sits on its threshold
+    got = orc.lsqr(A, b, damp=damp, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, calc_var=calc_var, x0=x0)
+    ref = sp_lsqr(A, b, damp=damp, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=2 * A.shape[1], calc_var=calc_var, x0=x0)
+    assert got[1] == ref[1] and abs(got[2] - ref[2]) <= max(2, ref[2] // 20)
+    if cond <= 50.0:                              # x itself is only determined to about cond * atol
+        assert np.abs(got[0][:, 0] - ref[0]).max() <= 1e-6 * np.abs(ref[0]).max()
+    assert abs(got[3] - ref[3]) <= (1e-6 if cond <= 50.0 else 1e-3) * abs(ref[3]) + 1e-7 * np.linalg.norm(b)
+
+
+def test_lsqr_reference_cases(orc):
+    """test_simple_system (:391-410): b = 0 returns x = 0 at once with the single-entry history [0.0] (:181-183); the 3 x 2
+    system with b = (1, 0, -1) has the solution (1, -1) (1e-2 there).  iter_lim is honoured (istop = 7)."""
+    A = np.asfortranarray(np.array([[1.0, 0.0], [1.0, 1.0], [0.0, 1.0]]))
+    x, istop, itn, r1, r2, an, ac, hist, xn, var = orc.lsqr(A, np.zeros(3), atol=1e-8, btol=1e-8)
+    assert not x.any() and istop == 0 and itn == 0 and list(hist) == [0.0] and r1 == 0.0 and an == 0.0
+    x, istop, itn, *_ = orc.lsqr(A, np.array([1.0, 0.0, -1.0]), atol=1e-8, btol=1e-8)
+    assert np.abs(x[:, 0] - [1.0, -1.0]).max() < 1e-12 and istop in (1, 2) and itn <= 2
+    A, b = _lsq_problem(200, 100, 1e4, seed=1)
+    x, istop, itn, *_, hist, xn, var = orc.lsqr(A, b, atol=1e-14, btol=1e-14, iter_lim=7)
+    assert istop == 7 and itn == 7 and len(hist) == 7
+    # the least-squares solution against LAPACK (test_overdetermined_system compares with nalgebra's SVD solve)
+    A, b = _lsq_problem(200, 100, 10.0, seed=2)
+    x, *_ = orc.lsqr(A, b, atol=1e-12, btol=1e-12)
+    xs = np.linalg.lstsq(A, b, rcond=None)[0]
+    assert np.abs(x[:, 0] - xs).max() <= 1e-8 * np.abs(xs).max()
