@@ -930,7 +930,7 @@ def test_int8_passes_on_degenerate_inputs(rb, orc, level):
     assert np.max(np.abs(sg[:30] - so[:30]) / so[:30]) < SIG_TOL
     assert sg[30:].max() <= 1e-9 * so[0]
     assert np.abs(U.T @ U - np.eye(50)).max() < 1e-11
-    assert np.linalg.norm(U @ S @ Vt - A) <= 1e-9 * np.linalg.norm(A)
+    assert np.linalg.norm(U @ S @ Vt - A) <= 1e-8 * np.linalg.norm(A)      # the range comes from 28-bit products (2^-25 accuracy)
     with rt.options(range_passes_int8=level):
         U, S, Vt = ld.rand_svd(np.zeros((4096, 1024), order="F"), 5, 0.1, 5)
     assert not S.any() and np.abs(U[:5, :5] - np.eye(5)).max() < 1e-12 and np.abs(Vt[:5, :5] - np.eye(5)).max() < 1e-12
