@@ -273,6 +273,25 @@ rnla_status rnla_sketch_saddle_point_precondition_dev(const double* dA, int64_t 
                                                       const double* dc, double mu, double epsilon, int64_t l, double sampling_factor,
                                                       double* dx, double* dy, int64_t* iterations, int32_t* converged);
 
+/* ---- reference src/cg.rs: the iterative solvers the drivers above are built on, under their own names ----
+ * cgls(a, b, tolerance, num_iterations, x) (:18-61) on a dense m x n system: x0 may be NULL (the reference's `None`: zeros).
+ * x: n.  iterations / converged (may be NULL): what the reference prints (:46, :58).  No validation in the reference. */
+rnla_status rnla_cgls(const double* A, int64_t m, int64_t n, const double* b, double tolerance, int64_t num_iterations,
+                      const double* x0, double* x, int64_t* iterations, int32_t* converged);
+/* device buffers; dA / db the caller's row shard when a communicator is active, dx replicated (in: initial guess, out: solution) */
+rnla_status rnla_cgls_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db, double tolerance,
+                          int64_t num_iterations, double* dx, int64_t* iterations, int32_t* converged);
+/* conjugate_grad(a, b, x) (:77-112): a n x n symmetric positive semi-definite, at most 2 n iterations, stops when r.r < 1e-10.
+ * x0 may be NULL (the reference's `None`: the vector of ones).  NOT_POSITIVE_SEMI_DEFINITE from the reference's eigenvalue
+ * check (:80-86), which is run for n <= 512 only (an O(n^3) decomposition in front of an O(n^2) iteration; same policy as
+ * rnla_rand_evd2).  iterations: the loop index the reference prints when it converges (2 n otherwise). */
+rnla_status rnla_conjugate_grad(const double* A, int64_t n, const double* b, const double* x0, double* x, int64_t* iterations,
+                                int32_t* converged);
+rnla_status rnla_conjugate_grad_dev(const double* dA, int64_t lda, int64_t n, const double* db, double* dx, int64_t* iterations,
+                                    int32_t* converged);
+/* verify_solution(a, b, x) = ||a x - b||_2 (:115-117) */
+rnla_status rnla_verify_solution(const double* A, int64_t m, int64_t n, const double* b, const double* x, double* residual_norm);
+
 /* lsqr(a, b, damp, atol, btol, conlim, iter_lim, calc_var, x0) (reference src/solvers.rs:115-278, its translation of scipy
  * 1.14.1 sparse.linalg.lsqr; called by no driver of the reference, SURVEY.md section 8f row 1 "wire lsqr").  The
  * Golub-Kahan bidiagonalisation runs on the device (A streamed twice per iteration), the scalar recurrences on the host.

@@ -99,6 +99,9 @@ int64_t orc_lsqr(const double* a, int64_t m, int64_t n, const double* b, double 
                  double* r1norm_out, double* r2norm_out, double* anorm_out, double* acond_out, double* arnorms, double* xnorm_out,
                  double* var);
 
+/* src/cg.rs:77-112; returns 0 or 9 (NotPositiveSemiDefinite) */
+int orc_conjugate_grad(const double* a, int64_t n, const double* b, double* x, int64_t* iters_out, int* converged_out);
+
 void orc_set_threads(int nthreads);
 int orc_get_threads(void);
 

@@ -420,6 +420,23 @@ def lsqr(a, b, damp=0.0, atol=1e-6, btol=1e-6, conlim=1e8, iter_lim=None, calc_v
     return x, int(istop.value), int(itn.value), r1.value, r2.value, an.value, ac.value, hist[:int(nh)].copy(), xn.value, var
 
 
+def conjugate_grad(a, b, x0=None):
+    """src/cg.rs:77-112 -> (x, iterations, converged); raises ValueError(9) for NotPositiveSemiDefinite"""
+    a = F(a); n = a.shape[0]
+    b = F(np.asarray(b, dtype=np.float64).reshape(-1, 1))
+    x = F(np.ones((n, 1)) if x0 is None else np.array(x0, dtype=np.float64).reshape(-1, 1))
+    it = i64(0); conv = C.c_int(0)
+    rc = load().orc_conjugate_grad(p(a), i64(n), p(b), p(x), C.byref(it), C.byref(conv))
+    if rc:
+        raise ValueError(rc)
+    return x[:, 0].copy(), int(it.value), bool(conv.value)
+
+
+def verify_solution(a, b, x):
+    """src/cg.rs:115-117"""
+    return float(np.linalg.norm(np.asarray(a) @ np.asarray(x).reshape(-1) - np.asarray(b).reshape(-1)))
+
+
 def set_threads(n):
     load().orc_set_threads(C.c_int(n))
 

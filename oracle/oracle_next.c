@@ -460,3 +460,39 @@ int64_t orc_lsqr(const double* a, int64_t m, int64_t n, const double* b, double 
     free(u); free(v); free(w); free(t);
     return nhist;
 }
+
+/* ======================================================================== src/cg.rs:77-112 conjugate_grad, statement for
+ * statement.  x: in the initial guess (the reference's default is ones), out the solution.  Returns 0, or 9
+ * (NotPositiveSemiDefinite) when an eigenvalue of a is negative (:80-86; beyond rounding noise of the Jacobi solver here).
+ * iters_out: the loop index printed at convergence (2 n when the loop runs out). */
+int orc_conjugate_grad(const double* a, int64_t n, const double* b, double* x, int64_t* iters_out, int* converged_out) {
+    {
+        double* W = dalloc(n * n); double* lam = dalloc(n);
+        orc_symmetric_eigen(a, n, W, lam);
+        double amax = 0.0; int bad = 0;
+        for (int64_t i = 0; i < n; ++i) if (fabs(lam[i]) > amax) amax = fabs(lam[i]);
+        for (int64_t i = 0; i < n; ++i) if (lam[i] < -1e-12 * (amax > 1e-300 ? amax : 1e-300) * (double)n) bad = 1;
+        free(W); free(lam);
+        if (bad) return 9;
+    }
+    double* r = dalloc(n); double* p = dalloc(n); double* ap = dalloc(n);
+    orc_gemm_nn(a, n, n, n, x, n, 1, r, n);
+    for (int64_t i = 0; i < n; ++i) { r[i] -= b[i]; p[i] = -r[i]; }                       /* :89-90 */
+    double rk = 0.0; for (int64_t i = 0; i < n; ++i) rk += r[i] * r[i];                   /* :91 */
+    int64_t it; int conv = 0;
+    for (it = 0; it < 2 * n; ++it) {                                                      /* :93 */
+        orc_gemm_nn(a, n, n, n, p, n, 1, ap, n);                                          /* :94 */
+        double pap = 0.0; for (int64_t i = 0; i < n; ++i) pap += p[i] * ap[i];
+        const double alpha = rk / pap;                                                    /* :95 */
+        for (int64_t i = 0; i < n; ++i) { x[i] += alpha * p[i]; r[i] += alpha * ap[i]; }  /* :96-97 */
+        double rk1 = 0.0; for (int64_t i = 0; i < n; ++i) rk1 += r[i] * r[i];             /* :98 */
+        if (rk1 < 1e-10) { conv = 1; break; }                                             /* :100-103 */
+        const double beta = rk1 / rk;                                                     /* :105 */
+        rk = rk1;
+        for (int64_t i = 0; i < n; ++i) p[i] = beta * p[i] - r[i];                        /* :107 */
+    }
+    if (iters_out) *iters_out = it;
+    if (converged_out) *converged_out = conv;
+    free(r); free(p); free(ap);
+    return 0;
+}

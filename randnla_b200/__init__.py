@@ -11,6 +11,7 @@ Python mirror of the reference's Rust modules over the C ABI in include/rnla.h:
     randnla_b200.sketch_and_solve         <- reference src/sketch_and_solve.rs
     randnla_b200.id                       <- reference src/id.rs
     randnla_b200.solvers                  <- reference src/solvers.rs (lsqr)
+    randnla_b200.cg                       <- reference src/cg.rs (cgls, conjugate_grad, verify_solution)
     randnla_b200.errors                   <- reference src/errors.rs
 
 All arithmetic runs in hand-written CUDA inside librnla.so; this package only marshals numpy / torch
@@ -21,7 +22,7 @@ from .errors import RandNLAError  # noqa: F401
 from . import _lib  # noqa: F401
 from . import runtime  # noqa: F401
 from . import sketch, lora_helpers, lora_drivers, sketch_and_precondition  # noqa: F401
-from . import pivot_decompositions, cqrrpt, sketch_and_solve, id, solvers  # noqa: F401
+from . import pivot_decompositions, cqrrpt, sketch_and_solve, id, solvers, cg  # noqa: F401
 
 __all__ = ["errors", "RandNLAError", "runtime", "sketch", "lora_helpers", "lora_drivers", "sketch_and_precondition",
-           "pivot_decompositions", "cqrrpt", "sketch_and_solve", "id", "solvers"]
+           "pivot_decompositions", "cqrrpt", "sketch_and_solve", "id", "solvers", "cg"]

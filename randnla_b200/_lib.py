@@ -73,6 +73,11 @@ SIGNATURES = {
     "rnla_last_jacobi_sweeps": (c_i32, []),
     "rnla_lsrn_overdetermined": (c_i32, [P, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
     "rnla_lsrn_overdetermined_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
+    "rnla_cgls": (c_i32, [P, c_i64, c_i64, P, c_f64, c_i64, P, P, C.POINTER(c_i64), C.POINTER(c_i32)]),
+    "rnla_cgls_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, c_f64, c_i64, P, C.POINTER(c_i64), C.POINTER(c_i32)]),
+    "rnla_conjugate_grad": (c_i32, [P, c_i64, P, P, P, C.POINTER(c_i64), C.POINTER(c_i32)]),
+    "rnla_conjugate_grad_dev": (c_i32, [P, c_i64, c_i64, P, P, C.POINTER(c_i64), C.POINTER(c_i32)]),
+    "rnla_verify_solution": (c_i32, [P, c_i64, c_i64, P, P, C.POINTER(c_f64)]),
     "rnla_lsqr": (c_i32, [P, c_i64, c_i64, P, c_f64, c_f64, c_f64, c_f64, c_i64, c_i32, P, P, C.POINTER(LsqrResult), P, c_i64, P]),
     "rnla_lsqr_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, c_f64, c_f64, c_f64, c_f64, c_i64, c_i32, P, P, C.POINTER(LsqrResult), P,
                       c_i64, P]),

@@ -10,6 +10,7 @@
 //   randblas::pivot_decompositions::{qrcp, economic_qrcp}                                    <- src/pivot_decompositions.rs
 //   randblas::cqrrpt::sap_chol_qrcp                                                          <- src/cqrrpt.rs
 //   randblas::sketch_and_solve::{sketched_least_squares_qr, sketched_least_squares_svd}      <- src/sketch_and_solve.rs
+//   randblas::cg::{cgls, conjugate_grad, verify_solution}                                    <- src/cg.rs
 //   randblas::solvers::lsqr                                                                 <- src/solvers.rs:115-278
 //   randblas::id::{osid_qrcp, osid_randomised, two_sided_id(_randomised), cur(_randomised)}  <- src/id.rs
 //   randblas::errors::RandNLAError                                                           <- src/errors.rs
@@ -316,6 +317,36 @@ inline DMatrix sketched_least_squares_svd(const DMatrix& a, const DMatrix& b) {
     return x;
 }
 }  // namespace sketch_and_solve
+
+namespace cg {
+// src/cg.rs:18-61; x == nullptr is the reference's `None` (zeros).  Prints what the reference prints.
+inline DMatrix cgls(const DMatrix& a, const DMatrix& b, double tolerance, size_t num_iterations, const DMatrix* x = nullptr) {
+    if (b.nrows() != a.nrows() || (x && x->nrows() != a.ncols())) throw std::invalid_argument("cgls: shapes do not conform");
+    DMatrix out(a.ncols(), 1);
+    int64_t iters = 0; int32_t conv = 0;
+    errors::check(rnla_cgls(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), b.as_ptr(), tolerance, (int64_t)num_iterations,
+                            x ? x->as_ptr() : nullptr, out.as_mut_ptr(), &iters, &conv));
+    if (conv) std::printf("CGLS converged after %lld iterations\n", (long long)iters);               // :46
+    else std::printf("CGLS failed to converged after %zu iterations\n", num_iterations);             // :58
+    return out;
+}
+// :77-112; x == nullptr: the vector of ones (:88).  Throws RandNLAError::NotPositiveSemiDefinite (:80-86).
+inline DMatrix conjugate_grad(const DMatrix& a, const DMatrix& b, const DMatrix* x = nullptr) {
+    const size_t n = a.nrows();
+    if (a.ncols() != n || b.nrows() != n || (x && x->nrows() != n)) throw std::invalid_argument("conjugate_grad: shapes do not conform");
+    DMatrix out(n, 1);
+    int64_t iters = 0; int32_t conv = 0;
+    errors::check(rnla_conjugate_grad(a.as_ptr(), (int64_t)n, b.as_ptr(), x ? x->as_ptr() : nullptr, out.as_mut_ptr(), &iters, &conv));
+    if (conv) std::printf("Converged after %lld iterations\n", (long long)iters);                    // :101
+    return out;
+}
+// :115-117
+inline double verify_solution(const DMatrix& a, const DMatrix& b, const DMatrix& x) {
+    double r = 0.0;
+    errors::check(rnla_verify_solution(a.as_ptr(), (int64_t)a.nrows(), (int64_t)a.ncols(), b.as_ptr(), x.as_ptr(), &r));
+    return r;
+}
+}  // namespace cg
 
 namespace solvers {
 // src/solvers.rs:115-278: the reference's 10-tuple, in its order

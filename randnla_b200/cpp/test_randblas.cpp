@@ -122,6 +122,18 @@ int main() {
         auto [sx, sy] = sketch_and_precondition::sketch_saddle_point_precondition(L, bb, DMatrix(), 0.0, 1e-12, 100, 2.0);
         double d = 0; for (size_t i = 0; i < k; ++i) d = std::fmax(d, std::fabs(sx(i, 0) - xt(i, 0)));
         CHECK(d < 1e-8 && sy.norm() < 1e-8 * bb.norm());
+        // src/cg.rs:130-197
+        DMatrix ca = DMatrix::from_fn(3, 3, [](size_t i, size_t j) { const double v[9] = {4, 1, 2, 1, 3, 0, 2, 0, 1}; return v[i * 3 + j]; });
+        DMatrix cb = DMatrix::from_fn(3, 1, [](size_t i, size_t) { return i == 0 ? 4.0 : 2.0; });
+        DMatrix ones3(3, 1, 1.0);
+        CHECK(cg::cgls(ca, cb, 3.0, 100).norm() < 3.0);
+        CHECK(cg::cgls(ca, cb, 3.0, 100, &ones3).norm() < 3.0);
+        CHECK(cg::cgls(ca, cb, 1e-20, 1).norm() > 1e-20);
+        DMatrix sa = DMatrix::from_fn(3, 3, [](size_t i, size_t j) { const double v[9] = {4, 1, 2, 1, 3, 1, 2, 1, 3}; return v[i * 3 + j]; });
+        DMatrix sb = DMatrix::from_fn(3, 1, [](size_t i, size_t) { return 1.0 + (double)i; });
+        CHECK(cg::verify_solution(sa, sb, cg::conjugate_grad(sa, sb, &ones3)) < 1e-10);
+        try { DMatrix ind = DMatrix::identity(3, 3); ind(1, 1) = -2.0; cg::conjugate_grad(ind, sb); CHECK(false); }
+        catch (const RandNLAError& e3) { CHECK(e3.kind == RandNLAError::NotPositiveSemiDefinite); }
         // src/solvers.rs:391-410 (test_simple_system) and a consistent tall system through lsqr
         DMatrix a3 = DMatrix::from_fn(3, 2, [](size_t i, size_t j) { return (i == j || i == j + 1) ? 1.0 : 0.0; });
         DMatrix b0(3, 1), b1 = DMatrix::from_fn(3, 1, [](size_t i, size_t) { return i == 0 ? 1.0 : (i == 2 ? -1.0 : 0.0); });

@@ -540,6 +540,71 @@ rnla_status rnla_lsrn_overdetermined(const double* A, int64_t m, int64_t n, cons
     return d2h(x, dx.d(), (size_t)n);
 }
 
+// ---- reference src/cg.rs: cgls, conjugate_grad, verify_solution
+rnla_status rnla_cgls_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db, double tolerance,
+                          int64_t num_iterations, double* dx, int64_t* iterations, int32_t* converged) {
+    RNLA_API_GUARD;
+    if (!dA || !db || !dx) return fail(RNLA_ERR_INVALID_PARAMETERS, "cgls: null argument");
+    if (m_local < 0 || n < 1) return fail(RNLA_ERR_INVALID_DIMENSIONS, "cgls: a must have at least one column");
+    RNLA_TRY(ensure_ctx());
+    phases_reset();
+    int64_t it = 0; int32_t conv = 0;
+    RNLA_TRY(dev_cgls_operator(dA, lda, m_local, n, db, nullptr, dx, tolerance, num_iterations, &it, &conv));
+    RNLA_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (iterations) *iterations = it;
+    if (converged) *converged = conv;
+    return RNLA_OK;
+}
+rnla_status rnla_cgls(const double* A, int64_t m, int64_t n, const double* b, double tolerance, int64_t num_iterations,
+                      const double* x0, double* x, int64_t* iterations, int32_t* converged) {
+    RNLA_API_GUARD;
+    if (!A || !b || !x) return fail(RNLA_ERR_INVALID_PARAMETERS, "cgls: null argument");
+    if (m < 1 || n < 1) return fail(RNLA_ERR_INVALID_DIMENSIONS, "cgls: a must have at least one row and one column");
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, db, dx;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_TRY(h2d(db, b, (size_t)m));
+    if (x0) RNLA_TRY(h2d(dx, x0, (size_t)n));
+    else { RNLA_CUDA(dx.alloc((size_t)n * 8)); RNLA_CUDA(cudaMemsetAsync(dx.p, 0, (size_t)n * 8, ctx().stream)); }        // :29
+    RNLA_TRY(rnla_cgls_dev(dA.d(), m, m, n, db.d(), tolerance, num_iterations, dx.d(), iterations, converged));
+    return d2h(x, dx.d(), (size_t)n);
+}
+rnla_status rnla_conjugate_grad_dev(const double* dA, int64_t lda, int64_t n, const double* db, double* dx, int64_t* iterations,
+                                    int32_t* converged) {
+    RNLA_API_GUARD;
+    if (!dA || !db || !dx) return fail(RNLA_ERR_INVALID_PARAMETERS, "conjugate_grad: null argument");
+    RNLA_TRY(ensure_ctx());
+    return dev_conjugate_grad(dA, lda, n, db, dx, iterations, converged);
+}
+rnla_status rnla_conjugate_grad(const double* A, int64_t n, const double* b, const double* x0, double* x, int64_t* iterations,
+                                int32_t* converged) {
+    RNLA_API_GUARD;
+    if (!A || !b || !x) return fail(RNLA_ERR_INVALID_PARAMETERS, "conjugate_grad: null argument");
+    if (n < 1) return fail(RNLA_ERR_INVALID_DIMENSIONS, "conjugate_grad: empty system");
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, db, dx;
+    RNLA_TRY(h2d(dA, A, (size_t)n * n));
+    RNLA_TRY(h2d(db, b, (size_t)n));
+    if (x0) RNLA_TRY(h2d(dx, x0, (size_t)n));
+    else {                                                                                         // DVector::from_element(n, 1.0)  :88
+        std::vector<double> ones((size_t)n, 1.0);
+        RNLA_TRY(h2d(dx, ones.data(), (size_t)n));
+    }
+    RNLA_TRY(dev_conjugate_grad(dA.d(), n, n, db.d(), dx.d(), iterations, converged));
+    return d2h(x, dx.d(), (size_t)n);
+}
+rnla_status rnla_verify_solution(const double* A, int64_t m, int64_t n, const double* b, const double* x, double* residual_norm) {
+    RNLA_API_GUARD;
+    if (!A || !b || !x || !residual_norm) return fail(RNLA_ERR_INVALID_PARAMETERS, "verify_solution: null argument");
+    if (m < 1 || n < 1) return fail(RNLA_ERR_INVALID_DIMENSIONS, "verify_solution: empty system");
+    RNLA_TRY(ensure_ctx());
+    DevBuf dA, db, dx;
+    RNLA_TRY(h2d(dA, A, (size_t)m * n));
+    RNLA_TRY(h2d(db, b, (size_t)m));
+    RNLA_TRY(h2d(dx, x, (size_t)n));
+    return dev_verify_solution(dA.d(), m, m, n, db.d(), dx.d(), residual_norm);
+}
+
 // ---- lsqr (reference src/solvers.rs:115-278)
 rnla_status rnla_lsqr_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* db, double damp, double atol,
                           double btol, double conlim, int64_t iter_lim, int32_t calc_var, const double* dx0, double* dx,

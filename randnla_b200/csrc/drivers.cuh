@@ -55,6 +55,10 @@ rnla_status dev_lsrn(const double* A, int64_t lda, int64_t m_local, int64_t n, c
                      double sampling_factor, int kind, int dist_or_width, int zeta, uint64_t seed, double* x,
                      int64_t* iters_out, int32_t* converged_out);
 
+// src/cg.rs:77-117 on device buffers
+rnla_status dev_conjugate_grad(const double* A, int64_t lda, int64_t n, const double* b, double* x, int64_t* iterations_out,
+                               int32_t* converged_out);
+rnla_status dev_verify_solution(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, const double* x, double* out);
 // lsqr of src/solvers.rs:115-278 on device buffers (u row-sharded with A; v, w, x, var replicated); arnorms is a HOST array
 rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double damp, double atol, double btol,
                      double conlim, int64_t iter_lim, int calc_var, const double* x0, double* x, rnla_lsqr_result* res,

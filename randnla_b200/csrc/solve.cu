@@ -275,25 +275,27 @@ static rnla_status cgls_operator(Solver& S, const double* A, int64_t lda, int64_
     RNLA_CUDA(s.alloc((size_t)n * 8)); RNLA_CUDA(p.alloc((size_t)n * 8)); RNLA_CUDA(t.alloc((size_t)n * 8)); RNLA_CUDA(u.alloc((size_t)n * 8));
     RNLA_CUDA(r.alloc((size_t)mm * 8)); RNLA_CUDA(ap.alloc((size_t)mm * 8));
     int64_t it = 0; int32_t conv = 0;
-    RNLA_TRY(S.small_gemv(M, n, nn, 0, z, t.d()));                                                        // t = M x
-    RNLA_TRY(dev_gemv_n(A, lda, m_local, n, t.d(), ap.d()));                                              // a x
+    // M == nullptr: plain cgls(a = A, ...), the mat-vecs take the n-vectors directly
+    auto apply_m = [&](const double* in) -> const double* { if (!M) return in; S.small_gemv(M, n, nn, 0, in, t.d()); return t.d(); };
+    auto apply_mt = [&](double* out) -> rnla_status { return M ? S.small_gemv(M, n, nn, 1, u.d(), out) : RNLA_OK; };
+    double* const at_out = M ? u.d() : s.d();                                                             // where A^T r lands
+    RNLA_TRY(dev_gemv_n(A, lda, m_local, n, apply_m(z), ap.d()));                                         // a x
     RNLA_CUDA(cudaMemcpyAsync(r.p, b, (size_t)m_local * 8, cudaMemcpyDeviceToDevice, c.stream));
     RNLA_TRY(S.axpby(-1.0, ap.d(), 1.0, r.d(), m_local));                                                 // r = b - a x       :30
-    RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), u.d()));
-    RNLA_TRY(S.small_gemv(M, n, nn, 1, u.d(), s.d()));                                                    // s = a^T r          :31
+    RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), at_out));
+    RNLA_TRY(apply_mt(s.d()));                                                                            // s = a^T r          :31
     RNLA_CUDA(cudaMemcpyAsync(p.p, s.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c.stream));              // p = s              :32
     double norm_s = 0.0;
     RNLA_TRY(S.dot(s.d(), s.d(), n, false, &norm_s));                                                     // :33
     for (it = 0; it < maxit; ++it) {
-        RNLA_TRY(S.small_gemv(M, n, nn, 0, p.d(), t.d()));
-        RNLA_TRY(dev_gemv_n(A, lda, m_local, n, t.d(), ap.d()));                                          // ap = a p           :36
+        RNLA_TRY(dev_gemv_n(A, lda, m_local, n, apply_m(p.d()), ap.d()));                                 // ap = a p           :36
         double apap = 0.0;
         RNLA_TRY(S.dot(ap.d(), ap.d(), m_local, true, &apap));
         const double alpha = norm_s / apap;                                                               // :37
         RNLA_TRY(S.axpby(alpha, p.d(), 1.0, z, n));                                                       // x += alpha p       :38
         RNLA_TRY(S.axpby(-alpha, ap.d(), 1.0, r.d(), m_local));                                           // r -= alpha ap      :39
-        RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), u.d()));
-        RNLA_TRY(S.small_gemv(M, n, nn, 1, u.d(), s.d()));                                                // s_new = a^T r      :40
+        RNLA_TRY(dev_gemv_t(A, lda, m_local, n, r.d(), at_out));
+        RNLA_TRY(apply_mt(s.d()));                                                                        // s_new = a^T r      :40
         double norm_new = 0.0;
         RNLA_TRY(S.dot(s.d(), s.d(), n, false, &norm_new));                                               // :41
         if (std::sqrt(norm_new) < epsilon) { conv = 1; ++it; break; }                                     // :44-48
@@ -620,6 +622,76 @@ rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, c
     }
     RNLA_CUDA(cudaStreamSynchronize(c.stream));
     *res = rnla_lsqr_result{istop, itn, r1norm, r2norm, anorm, acond, xnorm, nhist};
+    return RNLA_OK;
+}
+
+// conjugate_grad(a, b, x) of src/cg.rs:77-112 on device buffers: a n x n (symmetric positive semi-definite), b n, x n (in:
+// the initial guess -- the reference's default is the vector of ones, set by the caller-facing wrappers; out: the solution).
+// The O(n^3) symmetric_eigen the reference runs as a PSD check (:80-86) is kept where it is affordable (n <= 512, the policy of
+// rand_evd2); one streamed pass over a per iteration.  iterations_out: loop index at which r.r < 1e-10 fired (what the reference
+// prints), or 2 n; converged_out: whether it fired.
+rnla_status dev_conjugate_grad(const double* A, int64_t lda, int64_t n, const double* b, double* x, int64_t* iterations_out,
+                               int32_t* converged_out) {
+    Ctx& c = ctx();
+    phases_reset();
+    if (n <= 0) return fail(RNLA_ERR_INVALID_DIMENSIONS, "conjugate_grad: empty system");
+    if (n <= 512) {
+        PhaseScope ph("check:psd");
+        DevBuf W, lam, work, info;
+        RNLA_CUDA(W.alloc((size_t)n * n * 8)); RNLA_CUDA(lam.alloc((size_t)n * 8));
+        RNLA_CUDA(work.alloc(jacobi_svd_work_doubles((int)n) * 8)); RNLA_CUDA(info.alloc(8));
+        RNLA_CUDA(jacobi_eigh(A, lda, (int)n, W.d(), n, lam.d(), 0, work.d(), info.as<int>(), c.stream));
+        std::vector<double> hl((size_t)n);
+        RNLA_CUDA(cudaMemcpyAsync(hl.data(), lam.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c.stream));
+        RNLA_CUDA(cudaStreamSynchronize(c.stream));
+        double amax = 0.0;                                               // strict `x < 0.0` beyond rounding noise, as in rand_evd2
+        for (double v : hl) amax = std::max(amax, std::fabs(v));
+        for (double v : hl)
+            if (v < -1e-12 * std::max(amax, 1e-300) * (double)n) return fail(RNLA_ERR_NOT_PSD, "Matrix is not positive semi-definite");
+    }
+    PhaseScope ph("cg");
+    Solver S(c);
+    RNLA_TRY(S.init());
+    DevBuf r, p, ap;
+    RNLA_CUDA(r.alloc((size_t)n * 8)); RNLA_CUDA(p.alloc((size_t)n * 8)); RNLA_CUDA(ap.alloc((size_t)n * 8));
+    RNLA_TRY(dev_gemv_n(A, lda, n, n, x, r.d()));
+    RNLA_TRY(S.axpby(-1.0, b, 1.0, r.d(), n));                                                            // r = a x - b        :89
+    RNLA_CUDA(cudaMemsetAsync(p.p, 0, (size_t)n * 8, c.stream));
+    RNLA_TRY(S.axpby(-1.0, r.d(), 1.0, p.d(), n));                                                        // p = -r             :90
+    double rk = 0.0;
+    RNLA_TRY(S.dot(r.d(), r.d(), n, false, &rk));                                                         // :91
+    int64_t i = 0; int32_t conv = 0;
+    for (i = 0; i < 2 * n; ++i) {                                                                         // :93
+        RNLA_TRY(dev_gemv_n(A, lda, n, n, p.d(), ap.d()));                                                // :94
+        double pap = 0.0;
+        RNLA_TRY(S.dot(p.d(), ap.d(), n, false, &pap));
+        const double alpha = rk / pap;                                                                    // :95
+        RNLA_TRY(S.axpby(alpha, p.d(), 1.0, x, n));                                                       // :96
+        RNLA_TRY(S.axpby(alpha, ap.d(), 1.0, r.d(), n));                                                  // :97
+        double rk1 = 0.0;
+        RNLA_TRY(S.dot(r.d(), r.d(), n, false, &rk1));                                                    // :98
+        if (rk1 < 1e-10) { conv = 1; break; }                                                             // :100-103
+        const double beta = rk1 / rk;                                                                     // :105
+        rk = rk1;
+        RNLA_TRY(S.axpby(-1.0, r.d(), beta, p.d(), n));                                                   // p = beta p - r     :107
+    }
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    if (iterations_out) *iterations_out = i;
+    if (converged_out) *converged_out = conv;
+    return RNLA_OK;
+}
+
+// verify_solution(a, b, x) = ||a x - b|| (src/cg.rs:115-117); a m_local x n (row shard), b m_local, x n
+rnla_status dev_verify_solution(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, const double* x, double* out) {
+    Ctx& c = ctx();
+    Solver S(c);
+    RNLA_TRY(S.init());
+    DevBuf r;
+    RNLA_CUDA(r.alloc((size_t)std::max<int64_t>(m_local, 1) * 8));
+    RNLA_TRY(dev_gemv_n(A, lda, m_local, n, x, r.d()));
+    double nr = 0.0;
+    RNLA_TRY(axpby_nrm2(S, -1.0, b, 1.0, r.d(), m_local, true, &nr));
+    *out = nr;
     return RNLA_OK;
 }
 

@@ -43,6 +43,13 @@ pub fn last_message() -> String {
         let p = rnla_last_error_message();
         if p.is_null() { String::new() } else { std::ffi::CStr::from_ptr(p).to_string_lossy().into_owned() }
     }
+    // reference src/cg.rs
+    pub fn rnla_cgls(a: *const c_double, m: i64, n: i64, b: *const c_double, tolerance: c_double, num_iterations: i64,
+                     x0: *const c_double, x: *mut c_double, iterations: *mut i64, converged: *mut c_int) -> c_int;
+    pub fn rnla_conjugate_grad(a: *const c_double, n: i64, b: *const c_double, x0: *const c_double, x: *mut c_double,
+                               iterations: *mut i64, converged: *mut c_int) -> c_int;
+    pub fn rnla_verify_solution(a: *const c_double, m: i64, n: i64, b: *const c_double, x: *const c_double,
+                                residual_norm: *mut c_double) -> c_int;
     // lsqr (reference src/solvers.rs:115-278)
     pub fn rnla_lsqr(a: *const c_double, m: i64, n: i64, b: *const c_double, damp: c_double, atol: c_double, btol: c_double,
                      conlim: c_double, iter_lim: i64, calc_var: c_int, x0: *const c_double, x: *mut c_double,

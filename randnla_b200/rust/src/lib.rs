@@ -12,3 +12,4 @@ pub mod cqrrpt;
 pub mod sketch_and_solve;
 pub mod id;
 pub mod solvers;
+pub mod cg;

@@ -400,6 +400,69 @@ def test_lsqr_at_scale_on_device_buffers(rb):
     torch.cuda.empty_cache()
 
 
+# ------------------------------------------------------------------------------------------------------ src/cg.rs
+def _spd(n, cond, seed):
+    rng = np.random.default_rng(seed)
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    return np.asfortranarray((V * np.logspace(0, -np.log10(cond), n)) @ V.T), rng.standard_normal(n)
+
+
+def test_cg_reference_cases(rb, orc):
+    """src/cg.rs:130-197: the three cgls cases and test_conjugate_gradient, same assertions"""
+    from randnla_b200 import cg
+    a = np.asfortranarray(np.array([[4.0, 1.0, 2.0], [1.0, 3.0, 0.0], [2.0, 0.0, 1.0]]))
+    b = np.array([4.0, 2.0, 2.0])
+    assert np.linalg.norm(cg.cgls(a, b, 3.0, 100, None)) < 3.0
+    assert np.linalg.norm(cg.cgls(a, b, 3.0, 100, np.ones(3))) < 3.0
+    info = {}
+    assert np.linalg.norm(cg.cgls(a, b, 1e-20, 1, None, info=info)) > 1e-20 and not info["converged"] and info["iterations"] == 1
+    a2 = np.asfortranarray(np.array([[4.0, 1.0, 2.0], [1.0, 3.0, 1.0], [2.0, 1.0, 3.0]]))
+    b2 = np.array([1.0, 2.0, 3.0])
+    x = cg.conjugate_grad(a2, b2, np.ones(3))
+    assert cg.verify_solution(a2, b2, x) < 1e-10
+    from randnla_b200.errors import NotPositiveSemiDefinite
+    with pytest.raises(NotPositiveSemiDefinite, match="Matrix is not positive semi-definite"):
+        cg.conjugate_grad(np.asfortranarray(np.diag([1.0, -2.0, 3.0])), np.ones(3))
+
+
+@pytest.mark.parametrize("m,n,cond", [(200, 100, 10.0), (3001, 257, 30.0), (20000, 300, 100.0)])
+def test_cgls_matches_oracle(rb, orc, m, n, cond):
+    """plain cgls (src/cg.rs:18-61) on a dense system, with and without an initial guess: same iteration count (within 5 %: the
+    stopping test sits on its threshold after hundreds of steps), same solution to 1e-6; five steps agree to rounding"""
+    from randnla_b200 import cg
+    A, b = _lsq_problem(m, n, cond, seed=m + n)
+    for x0 in (None, np.random.default_rng(3).standard_normal(n)):
+        info = {}
+        x = cg.cgls(A, b, 1e-9, 4 * n, x0, info=info)
+        xo, ito, convo = orc.cgls(A, b, 1e-9, 4 * n, x0)
+        assert info["converged"] == convo and abs(info["iterations"] - ito) <= max(1, ito // 20)
+        assert np.abs(x - xo).max() <= 1e-6 * np.abs(xo).max()
+        assert abs(cg.verify_solution(A, b, x) - orc.verify_solution(A, b, xo)) <= 1e-9 * np.linalg.norm(b)
+    # a fixed number of steps, no convergence: iterates agree to rounding
+    info = {}
+    x = cg.cgls(A, b, 1e-300, 5, None, info=info)
+    xo, ito, convo = orc.cgls(A, b, 1e-300, 5)
+    assert info["iterations"] == ito == 5 and not info["converged"] and np.abs(x - xo).max() <= 1e-12 * np.abs(xo).max()
+
+
+@pytest.mark.parametrize("n,cond", [(50, 10.0), (300, 1e3), (2000, 50.0)])
+def test_conjugate_grad_matches_oracle(rb, orc, n, cond):
+    """conjugate_grad (src/cg.rs:77-112), default start (ones) and a given start; n = 2000 is beyond the size the PSD check
+    is run for on the device (the oracle always runs it)"""
+    from randnla_b200 import cg
+    A, b = _spd(n, cond, seed=n)
+    for x0 in (None, np.random.default_rng(4).standard_normal(n)):
+        info = {}
+        x = cg.conjugate_grad(A, b, x0, info=info)
+        xo, ito, convo = orc.conjugate_grad(A, b, x0)
+        assert info["converged"] == convo and abs(info["iterations"] - ito) <= max(1, ito // 20)
+        # both stop at ||r|| < 1e-5, i.e. within cond * 1e-5 of the solution (lambda_max = 1); long runs decorrelate in rounding
+        assert np.linalg.norm(x - xo) <= 2.5e-5 * cond
+        if info["iterations"] == ito and ito <= 40:
+            assert np.abs(x - xo).max() <= 1e-9 * max(1.0, np.abs(xo).max())
+        assert cg.verify_solution(A, b, x) < 1e-5
+
+
 # -------------------------------------------------------------------------------------------- committed fixtures
 def test_next_rows_golden_vectors(rb):
     """tests/golden/next_rows_golden.npz: oracle outputs committed with their generating script; the CUDA path reproduces

@@ -278,3 +278,53 @@ def test_lsqr_reference_cases(orc):
     x, *_ = orc.lsqr(A, b, atol=1e-12, btol=1e-12)
     xs = np.linalg.lstsq(A, b, rcond=None)[0]
     assert np.abs(x[:, 0] - xs).max() <= 1e-8 * np.abs(xs).max()
+
+
+# ---- src/cg.rs: conjugate_grad (:77-112) and the reference's own cases (:130-197)
+def _spd(n, cond, seed):
+    rng = np.random.default_rng(seed)
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    return np.asfortranarray((V * np.logspace(0, -np.log10(cond), n)) @ V.T), rng.standard_normal(n)
+
+
+def test_conjugate_grad_reference_case_and_lapack(orc):
+    """test_conjugate_gradient (:187-196): residual below 1e-10 on the 3 x 3 system; LAPACK's solution on larger SPD systems
+    (the stopping rule r.r < 1e-10 bounds the residual by 1e-5); NotPositiveSemiDefinite for an indefinite matrix (:80-86);
+    the iterates are those of textbook CG (scipy's cg with the same start takes the same steps)."""
+    a = np.asfortranarray(np.array([[4.0, 1.0, 2.0], [1.0, 3.0, 1.0], [2.0, 1.0, 3.0]]))
+    b = np.array([1.0, 2.0, 3.0])
+    x, it, conv = orc.conjugate_grad(a, b, np.ones(3))
+    assert conv and it <= 2 and orc.verify_solution(a, b, x) < 1e-10
+    for n, cond in ((50, 10.0), (200, 1e3)):
+        A, rhs = _spd(n, cond, seed=n)
+        x, it, conv = orc.conjugate_grad(A, rhs)
+        assert conv and it < 2 * n
+        assert np.linalg.norm(A @ x - rhs) < 1e-5
+        xs = np.linalg.solve(A, rhs)
+        assert np.linalg.norm(x - xs) <= cond * 1e-5
+    with pytest.raises(ValueError, match="9"):
+        orc.conjugate_grad(np.asfortranarray(np.diag([1.0, -2.0, 3.0])), np.ones(3))
+    # a fixed number of steps against scipy's cg from the same starting vector
+    from scipy.sparse.linalg import cg as sp_cg
+    A, rhs = _spd(60, 30.0, seed=7)
+    iterates = []
+    sp_cg(A, rhs, x0=np.ones(60), rtol=0.0, atol=0.0, maxiter=5, callback=lambda xk: iterates.append(xk.copy()))
+    # the oracle stops on r.r < 1e-10 only, so replay 5 steps by hand with its own update rule
+    x = np.ones(60); r = A @ x - rhs; p = -r; rk = r @ r
+    for _ in range(5):
+        ap = A @ p; alpha = rk / (p @ ap); x = x + alpha * p; r = r + alpha * ap; rk1 = r @ r; p = (rk1 / rk) * p - r; rk = rk1
+    assert np.abs(x - iterates[4]).max() <= 1e-12 * np.abs(x).max()
+
+
+def test_cgls_reference_cases(orc):
+    """test_cgls_converges / _with_initial_guess / _does_not_converge (:130-184)"""
+    a = np.asfortranarray(np.array([[4.0, 1.0, 2.0], [1.0, 3.0, 0.0], [2.0, 0.0, 1.0]]))
+    b = np.array([4.0, 2.0, 2.0])
+    x, it, conv = orc.cgls(a, b, 3.0, 100)
+    assert conv and np.linalg.norm(x) < 3.0
+    x, it, conv = orc.cgls(a, b, 3.0, 100, np.ones(3))
+    assert np.linalg.norm(x) < 3.0
+    x, it, conv = orc.cgls(a, b, 1e-20, 1)
+    assert not conv and it == 1 and np.linalg.norm(x) > 1e-20
+    x, it, conv = orc.cgls(a, b, 1e-12, 100)
+    assert conv and np.abs(x[:, 0] - np.linalg.solve(a, b)).max() < 1e-10
