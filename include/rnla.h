@@ -222,6 +222,16 @@ rnla_status rnla_qrcp(const double* A, int64_t m, int64_t n, int64_t steps, int6
 rnla_status rnla_qrcp_dev(double* dR, int64_t ldr, int64_t m, int64_t n, int64_t steps, int64_t* dperm, double* dQ, int64_t ldq,
                           int64_t qcols);
 
+/* lupp(matrix) (reference src/pivot_decompositions.rs:21-86): LU with partial row pivoting, first maximum wins, the
+ * reference's elimination order with separately rounded multiply and subtract -- L, U and perm are bit-identical to that
+ * arithmetic.  L: n x n unit lower triangular, U: n x n upper triangular, perm: n (`p[k]` = original index of row k).
+ * Errors: rows != cols -> NOT_SQUARE "Matrix must be square, found matrix with {} rows and {} columns" (:23-27); a zero pivot
+ * column -> SINGULAR_MATRIX "Matrix must be nonsingular for an LU decomposition" (:44-48; like the reference, the last
+ * diagonal entry is not examined). */
+rnla_status rnla_lupp(const double* A, int64_t rows, int64_t cols, double* L, double* U, int64_t* perm);
+/* device buffers: dW n x n holds the matrix on entry and is destroyed; dL, dU n x n; dperm n */
+rnla_status rnla_lupp_dev(double* dW, int64_t ldw, int64_t n, double* dL, int64_t ldl, double* dU, int64_t ldu, int64_t* dperm);
+
 /* sap_chol_qrcp(a, d) (reference src/cqrrpt.rs:27-58; CQRRPT): sketch (d x m operator, kind/dist/zeta as in
  * rnla_sketch_apply; the reference's own is DENSE GAUSSIAN), qrcp of the sketch, numerical rank k = #{|R_ii| > 1e-10},
  * A_pre = A[:, J[:k]] R_k^-1, Cholesky QR of A_pre, R = R_pre R_sk[:k, :].  Q: m x n buffer, first *k columns valid (ld m);

@@ -102,6 +102,9 @@ int64_t orc_lsqr(const double* a, int64_t m, int64_t n, const double* b, double 
 /* src/cg.rs:77-112; returns 0 or 9 (NotPositiveSemiDefinite) */
 int orc_conjugate_grad(const double* a, int64_t n, const double* b, double* x, int64_t* iters_out, int* converged_out);
 
+/* src/pivot_decompositions.rs:21-86; returns 0 or 6 (SingularMatrix) */
+int orc_lupp(const double* a, int64_t n, double* L, double* U, int64_t* perm);
+
 void orc_set_threads(int nthreads);
 int orc_get_threads(void);
 

@@ -437,6 +437,19 @@ def verify_solution(a, b, x):
     return float(np.linalg.norm(np.asarray(a) @ np.asarray(x).reshape(-1) - np.asarray(b).reshape(-1)))
 
 
+def lupp(a):
+    """src/pivot_decompositions.rs:21-86 -> (l, u, p); raises ValueError(5) for a non-square input, ValueError(6) for a singular one"""
+    a = F(a)
+    if a.shape[0] != a.shape[1]:
+        raise ValueError(5)
+    n = a.shape[0]
+    L = np.zeros((n, n), order="F"); U = np.zeros((n, n), order="F"); perm = np.zeros(n, dtype=np.int64)
+    rc = load().orc_lupp(p(a), i64(n), p(L), p(U), p(perm))
+    if rc:
+        raise ValueError(rc)
+    return L, U, perm
+
+
 def set_threads(n):
     load().orc_set_threads(C.c_int(n))
 

@@ -496,3 +496,37 @@ int orc_conjugate_grad(const double* a, int64_t n, const double* b, double* x, i
     free(r); free(p); free(ap);
     return 0;
 }
+
+/* ======================================================================== src/pivot_decompositions.rs:21-86 lupp, statement
+ * for statement (this file is compiled with -ffp-contract=off: multiply and subtract round separately, as in the reference).
+ * a: n x n column-major.  L, U: n x n.  perm: n.  Returns 0, or 6 (SingularMatrix) on an exactly zero pivot column (:44-48). */
+int orc_lupp(const double* a, int64_t n, double* L, double* U, int64_t* perm) {
+    double* lu = dalloc(n * n);
+    memcpy(lu, a, (size_t)(n * n) * sizeof(double));
+    for (int64_t i = 0; i < n; ++i) perm[i] = i;                                          /* :30 */
+    for (int64_t k = 0; k + 1 < n; ++k) {                                                 /* :32 */
+        int64_t pivot_row = k;
+        double pivot_val = fabs(lu[k + k * n]);
+        for (int64_t i = k + 1; i < n; ++i) {                                             /* :36-42 */
+            const double val = fabs(lu[i + k * n]);
+            if (val > pivot_val) { pivot_val = val; pivot_row = i; }
+        }
+        if (pivot_val == 0.0) { free(lu); return 6; }                                     /* :44-48 */
+        if (pivot_row != k) {                                                             /* :50-60 */
+            for (int64_t j = 0; j < n; ++j) { const double t = lu[k + j * n]; lu[k + j * n] = lu[pivot_row + j * n]; lu[pivot_row + j * n] = t; }
+            const int64_t t = perm[k]; perm[k] = perm[pivot_row]; perm[pivot_row] = t;
+        }
+        for (int64_t i = k + 1; i < n; ++i) {                                             /* :62-70 */
+            const double multiplier = lu[i + k * n] / lu[k + k * n];
+            lu[i + k * n] = multiplier;
+            for (int64_t j = k + 1; j < n; ++j) lu[i + j * n] -= multiplier * lu[k + j * n];
+        }
+    }
+    for (int64_t j = 0; j < n; ++j)                                                       /* :73-84 */
+        for (int64_t i = 0; i < n; ++i) {
+            L[i + j * n] = i > j ? lu[i + j * n] : (i == j ? 1.0 : 0.0);
+            U[i + j * n] = i > j ? 0.0 : lu[i + j * n];
+        }
+    free(lu);
+    return 0;
+}

@@ -88,6 +88,8 @@ SIGNATURES = {
     "rnla_blendenpik_overdetermined_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
     "rnla_qrcp": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, P, P, P]),
     "rnla_qrcp_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, P, P, c_i64, c_i64]),
+    "rnla_lupp": (c_i32, [P, c_i64, c_i64, P, P, P]),
+    "rnla_lupp_dev": (c_i32, [P, c_i64, c_i64, P, c_i64, P, c_i64, P]),
     "rnla_sap_chol_qrcp": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, P, P, P, C.POINTER(c_i64)]),
     "rnla_sap_chol_qrcp_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, P, c_i64, P, c_i64, P, C.POINTER(c_i64)]),
     "rnla_sketched_least_squares_qr": (c_i32, [P, c_i64, c_i64, P, c_i32, c_i32, c_i32, P]),

@@ -7,7 +7,7 @@
 //   randblas::lora_drivers::{rand_svd, rand_evd1, rand_evd2}                                  <- src/lora_drivers.rs
 //   randblas::sketch_and_precondition::{blendenpik_sketch, lsrn_sketch, saddle_point_sketch} <- src/sketch_and_precondition.rs:26-52,82-107,150-176
 //   randblas::sketch_and_precondition::{blendenpik_overdetermined, lsrn_overdetermined, sketch_saddle_point_precondition}
-//   randblas::pivot_decompositions::{qrcp, economic_qrcp}                                    <- src/pivot_decompositions.rs
+//   randblas::pivot_decompositions::{lupp, qrcp, economic_qrcp}                                    <- src/pivot_decompositions.rs
 //   randblas::cqrrpt::sap_chol_qrcp                                                          <- src/cqrrpt.rs
 //   randblas::sketch_and_solve::{sketched_least_squares_qr, sketched_least_squares_svd}      <- src/sketch_and_solve.rs
 //   randblas::cg::{cgls, conjugate_grad, verify_solution}                                    <- src/cg.rs
@@ -286,6 +286,14 @@ inline std::tuple<DMatrix, DMatrix, std::vector<size_t>> economic_qrcp(const DMa
     std::vector<int64_t> p(std::max<size_t>(n, 1));
     errors::check(rnla_qrcp(a.as_ptr(), (int64_t)m, (int64_t)n, (int64_t)k, (int64_t)k, q.as_mut_ptr(), r.as_mut_ptr(), p.data()));
     return {std::move(q), DMatrix::from_fn(k, n, [&](size_t i, size_t j) { return r(i, j); }), to_usize(p, n)};
+}
+// src/pivot_decompositions.rs:21-86; throws NotSquare / SingularMatrix as the reference returns them
+inline std::tuple<DMatrix, DMatrix, std::vector<size_t>> lupp(const DMatrix& matrix) {
+    const size_t n = std::max<size_t>(matrix.nrows(), 1);
+    DMatrix l(n, n), u(n, n);
+    std::vector<int64_t> p(n);
+    errors::check(rnla_lupp(matrix.as_ptr(), (int64_t)matrix.nrows(), (int64_t)matrix.ncols(), l.as_mut_ptr(), u.as_mut_ptr(), p.data()));
+    return {std::move(l), std::move(u), to_usize(p, n)};
 }
 }  // namespace pivot_decompositions
 

@@ -122,6 +122,21 @@ int main() {
         auto [sx, sy] = sketch_and_precondition::sketch_saddle_point_precondition(L, bb, DMatrix(), 0.0, 1e-12, 100, 2.0);
         double d = 0; for (size_t i = 0; i < k; ++i) d = std::fmax(d, std::fabs(sx(i, 0) - xt(i, 0)));
         CHECK(d < 1e-8 && sy.norm() < 1e-8 * bb.norm());
+        // src/pivot_decompositions.rs:351-369 (test_lupp) on a 60 x 60 Gaussian matrix
+        {
+            DMatrix g = sketch::sketching_operator(sketch::DistributionType::Gaussian, 60, 60);
+            auto [ll, uu, pp] = pivot_decompositions::lupp(g);
+            DMatrix lu = ll * uu;
+            double e2 = 0, lo = 0, up = 0;
+            for (size_t i = 0; i < 60; ++i) for (size_t c = 0; c < 60; ++c) {
+                e2 = std::fmax(e2, std::fabs(lu(i, c) - g(pp[i], c)));
+                if (i < c) up = std::fmax(up, std::fabs(ll(i, c)));
+                if (i > c) lo = std::fmax(lo, std::fabs(uu(i, c)));
+            }
+            CHECK(e2 < 1e-12 && up == 0.0 && lo == 0.0);
+            try { pivot_decompositions::lupp(DMatrix(3, 4)); CHECK(false); } catch (const RandNLAError& e4) { CHECK(e4.kind == RandNLAError::NotSquare); }
+            try { pivot_decompositions::lupp(DMatrix(3, 3)); CHECK(false); } catch (const RandNLAError& e4) { CHECK(e4.kind == RandNLAError::SingularMatrix); }
+        }
         // src/cg.rs:130-197
         DMatrix ca = DMatrix::from_fn(3, 3, [](size_t i, size_t j) { const double v[9] = {4, 1, 2, 1, 3, 0, 2, 0, 1}; return v[i * 3 + j]; });
         DMatrix cb = DMatrix::from_fn(3, 1, [](size_t i, size_t) { return i == 0 ? 4.0 : 2.0; });

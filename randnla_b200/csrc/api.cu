@@ -746,6 +746,38 @@ rnla_status rnla_qrcp(const double* A, int64_t m, int64_t n, int64_t steps, int6
     return d2h_idx(perm, dp.as<int64_t>(), (size_t)n);
 }
 
+// ---- lupp (reference src/pivot_decompositions.rs:21-86)
+rnla_status rnla_lupp_dev(double* dW, int64_t ldw, int64_t n, double* dL, int64_t ldl, double* dU, int64_t ldu, int64_t* dperm) {
+    RNLA_API_GUARD;
+    if (!dW || !dL || !dU || !dperm) return fail(RNLA_ERR_INVALID_PARAMETERS, "lupp: null argument");
+    if (n < 1) return fail(RNLA_ERR_INVALID_DIMENSIONS, "lupp: empty matrix");          // the reference underflows `n - 1` (:32)
+    RNLA_TRY(ensure_ctx());
+    phases_reset();
+    int64_t sing = -1;
+    RNLA_TRY(dev_lupp(dW, ldw, n, dL, ldl, dU, ldu, dperm, &sing));
+    if (sing >= 0) return fail(RNLA_ERR_SINGULAR_MATRIX, "Matrix must be nonsingular for an LU decomposition");   // :44-48
+    return RNLA_OK;
+}
+rnla_status rnla_lupp(const double* A, int64_t rows, int64_t cols, double* L, double* U, int64_t* perm) {
+    RNLA_API_GUARD;
+    if (rows != cols) {                                                                            // :23-27
+        char buf[160];
+        snprintf(buf, sizeof buf, "Matrix must be square, found matrix with %lld rows and %lld columns", (long long)rows, (long long)cols);
+        return fail(RNLA_ERR_NOT_SQUARE, buf);
+    }
+    if (!A || !L || !U || !perm) return fail(RNLA_ERR_INVALID_PARAMETERS, "lupp: null argument");
+    if (rows < 1) return fail(RNLA_ERR_INVALID_DIMENSIONS, "lupp: empty matrix");
+    RNLA_TRY(ensure_ctx());
+    const int64_t n = rows;
+    DevBuf dW, dL, dU, dp;
+    RNLA_TRY(h2d(dW, A, (size_t)n * n));
+    RNLA_CUDA(dL.alloc((size_t)n * n * 8)); RNLA_CUDA(dU.alloc((size_t)n * n * 8)); RNLA_CUDA(dp.alloc((size_t)n * 8));
+    RNLA_TRY(rnla_lupp_dev(dW.d(), n, n, dL.d(), n, dU.d(), n, dp.as<int64_t>()));
+    RNLA_TRY(d2h(L, dL.d(), (size_t)n * n));
+    RNLA_TRY(d2h(U, dU.d(), (size_t)n * n));
+    return d2h_idx(perm, dp.as<int64_t>(), (size_t)n);
+}
+
 rnla_status rnla_sap_chol_qrcp_dev(const double* dA, int64_t lda, int64_t m, int64_t n, int64_t d, int32_t kind, int32_t dist,
                                    int32_t zeta, double* dQ, int64_t ldq, double* dR, int64_t ldr, int64_t* dJ, int64_t* k) {
     RNLA_API_GUARD;

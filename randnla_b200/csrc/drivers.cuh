@@ -71,6 +71,8 @@ rnla_status dev_cgls_operator(const double* A, int64_t lda, int64_t m_local, int
 
 // pivot.cu: column-pivoted Householder QR (reference src/pivot_decompositions.rs:105-269) and index shuffles
 rnla_status dev_qrcp(double* R, int64_t ldr, int64_t m, int64_t n, int64_t steps, int64_t* dperm, double* Q, int64_t ldq, int64_t qcols);
+rnla_status dev_lupp(double* W, int64_t ld, int64_t n, double* L, int64_t ldl, double* U, int64_t ldu, int64_t* dperm,
+                     int64_t* singular_step);
 rnla_status dev_gather_columns(const double* A, int64_t lda, int64_t m, const int64_t* dJ, int64_t k, double* out, int64_t ldo);
 rnla_status dev_gather_rows(const double* A, int64_t lda, int64_t n, const int64_t* dI, int64_t k, double* out, int64_t ldo);
 rnla_status dev_scatter_rows(const double* M, int64_t ldm, int64_t k, const int64_t* dJ, double* W, int64_t ldw);

@@ -324,4 +324,115 @@ rnla_status dev_mul_vec(const double* w, int n, double* z) {
     return RNLA_OK;
 }
 
+// ======================================================================================================================
+// lupp(matrix) of src/pivot_decompositions.rs:21-86: LU with partial (row) pivoting, first maximum wins (strict `>`, :36-42),
+// Gaussian elimination with separately rounded multiply and subtract (:63-70) -- kept operation for operation
+// (__ddiv_rn / __dmul_rn / __dsub_rn, no FMA contraction), so L, U and p are BIT-IDENTICAL to the reference's arithmetic.
+// One launch per elimination step: every CTA owns LU_CPB trailing columns and redundantly finds the pivot of column k (an
+// L2-resident column), takes the swapped values of rows k / pivot_row of its own columns into registers, and applies the
+// rank-1 update to them; CTA 0 also records the multipliers (L), the pivot (U_kk), the permutation and swaps the two rows of
+// the earlier L columns.  Column k of the work matrix is never written during its own step (the other CTAs are reading it):
+// L and U are separate outputs.  flag[0] = 1 + k marks a zero pivot at step k (SingularMatrix, :44-48).
+namespace {
+constexpr int LU_T = 256;
+constexpr int LU_CPB = 4;
+__global__ void __launch_bounds__(LU_T)
+lupp_step_kernel(double* __restrict__ W, int64_t ld, int64_t n, int64_t k, double* __restrict__ L, int64_t ldl,
+                 double* __restrict__ U, int64_t ldu, int64_t* __restrict__ perm, int* __restrict__ flag) {
+    __shared__ double bval[LU_T / 32];
+    __shared__ long long bidx[LU_T / 32];
+    __shared__ long long s_pr;
+    __shared__ double s_pv;
+    if (flag[0] != 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* colk = W + k * ld;
+    double best = -1.0; long long bi = n;
+    for (int64_t i = k + tid; i < n; i += LU_T) { const double v = fabs(colk[i]); if (v > best) { best = v; bi = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { bval[warp] = best; bidx[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        double b = bval[0]; long long i = bidx[0];
+        for (int w = 1; w < LU_T / 32; ++w) if (bval[w] > b || (bval[w] == b && bidx[w] < i)) { b = bval[w]; i = bidx[w]; }
+        if (i >= n) { i = k; b = fabs(colk[k]); }           // all NaN: `val > pivot_val` never fires, the diagonal stays
+        s_pr = i; s_pv = b;
+    }
+    __syncthreads();
+    const int64_t pr = s_pr;
+    if (s_pv == 0.0) { if (blockIdx.x == 0 && tid == 0) flag[0] = 1 + (int)k; return; }
+    const double pivot = colk[pr];                           // lu[(k, k)] after the swap
+    const double okk = colk[k];                              // what row pr holds in column k after the swap
+    const int64_t j0 = k + 1 + (int64_t)blockIdx.x * LU_CPB;
+    const int nc = (int)min((int64_t)LU_CPB, n - j0);
+    double ukj[LU_CPB], okj[LU_CPB];
+#pragma unroll
+    for (int c = 0; c < LU_CPB; ++c) {
+        ukj[c] = c < nc ? W[pr + (j0 + c) * ld] : 0.0;      // row k of column j after the swap
+        okj[c] = c < nc ? W[k + (j0 + c) * ld] : 0.0;       // row pr of column j after the swap
+    }
+    __syncthreads();                                         // every thread holds both rows before anyone overwrites them
+    for (int64_t i = k + 1 + tid; i < n; i += LU_T) {
+        const double mult = __ddiv_rn(i == pr ? okk : colk[i], pivot);                             // :64
+#pragma unroll
+        for (int c = 0; c < LU_CPB; ++c)
+            if (c < nc) {
+                double* w = W + i + (j0 + c) * ld;
+                *w = __dsub_rn(i == pr ? okj[c] : *w, __dmul_rn(mult, ukj[c]));                     // :67-69
+            }
+        if (blockIdx.x == 0) L[i + k * ldl] = mult;                                                // :65
+    }
+    if (tid < nc) { W[k + (j0 + tid) * ld] = ukj[tid]; U[k + (j0 + tid) * ldu] = ukj[tid]; }
+    if (blockIdx.x == 0) {
+        if (tid == 0) {
+            U[k + k * ldu] = pivot;
+            if (pr != k) { const int64_t t = perm[k]; perm[k] = perm[pr]; perm[pr] = t; }          // :57-59
+        }
+        if (pr != k)                                                                               // :51-56 on the stored multipliers
+            for (int64_t j = tid; j < k; j += LU_T) { const double t = L[k + j * ldl]; L[k + j * ldl] = L[pr + j * ldl]; L[pr + j * ldl] = t; }
+    }
+}
+__global__ void lupp_init_kernel(double* __restrict__ L, int64_t ldl, double* __restrict__ U, int64_t ldu, int64_t n,
+                                 int64_t* __restrict__ perm, int* __restrict__ flag) {
+    const int64_t total = n * n;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / n, r = idx - c * n;
+        L[r + c * ldl] = r == c ? 1.0 : 0.0;                                                      // :74
+        U[r + c * ldu] = 0.0;                                                                     // :75
+        if (c == 0) perm[r] = r;                                                                  // :30
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) flag[0] = 0;
+}
+}  // namespace
+
+// W: n x n, holds the matrix on entry and is destroyed.  L, U: n x n outputs.  dperm: n.  *singular_step = -1, or the step
+// at which the pivot was exactly zero (the reference's SingularMatrix error).
+rnla_status dev_lupp(double* W, int64_t ld, int64_t n, double* L, int64_t ldl, double* U, int64_t ldu, int64_t* dperm,
+                     int64_t* singular_step) {
+    Ctx& c = ctx();
+    PhaseScope ph("lupp");
+    DevBuf flag;
+    RNLA_CUDA(flag.alloc(8));
+    lupp_init_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n * n + 255) / 256, 148 * 8)), 256, 0, c.stream>>>(
+        L, ldl, U, ldu, n, dperm, flag.as<int>());
+    ++g_kernel_launches;
+    for (int64_t k = 0; k + 1 < n; ++k) {                                                         // :32
+        const unsigned grid = (unsigned)((n - k - 1 + LU_CPB - 1) / LU_CPB);
+        lupp_step_kernel<<<grid, LU_T, 0, c.stream>>>(W, ld, n, k, L, ldl, U, ldu, dperm, flag.as<int>());
+        ++g_kernel_launches;
+    }
+    RNLA_CUDA(cudaGetLastError());
+    // the last diagonal entry is never a pivot (:32 stops at n - 2): it is what the eliminations left
+    RNLA_CUDA(cudaMemcpyAsync(U + (n - 1) + (n - 1) * ldu, W + (n - 1) + (n - 1) * ld, 8, cudaMemcpyDeviceToDevice, c.stream));
+    int hflag = 0;
+    RNLA_CUDA(cudaMemcpyAsync(&hflag, flag.p, 4, cudaMemcpyDeviceToHost, c.stream));
+    RNLA_CUDA(cudaStreamSynchronize(c.stream));
+    *singular_step = hflag ? hflag - 1 : -1;
+    return RNLA_OK;
+}
+
 }  // namespace rnla

@@ -43,6 +43,7 @@ pub fn last_message() -> String {
         let p = rnla_last_error_message();
         if p.is_null() { String::new() } else { std::ffi::CStr::from_ptr(p).to_string_lossy().into_owned() }
     }
+    pub fn rnla_lupp(a: *const c_double, rows: i64, cols: i64, l: *mut c_double, u: *mut c_double, perm: *mut i64) -> c_int;
     // reference src/cg.rs
     pub fn rnla_cgls(a: *const c_double, m: i64, n: i64, b: *const c_double, tolerance: c_double, num_iterations: i64,
                      x0: *const c_double, x: *mut c_double, iterations: *mut i64, converged: *mut c_int) -> c_int;

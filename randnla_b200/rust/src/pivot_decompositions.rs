@@ -1,6 +1,7 @@
-//! Drop-ins for `qrcp` and `economic_qrcp` of reference src/pivot_decompositions.rs (:105-180, :196-269) on the GPU.
-//! (`lupp` :21-86 is not on any sketch path and stays as it is.)
+//! Drop-ins for `lupp`, `qrcp` and `economic_qrcp` of reference src/pivot_decompositions.rs (:21-86, :105-180, :196-269) on
+//! the GPU.
 use crate::errors::from_status;
+use std::error::Error;
 use crate::ffi;
 use nalgebra::DMatrix;
 
@@ -26,4 +27,15 @@ pub fn economic_qrcp(a: &DMatrix<f64>, k: usize) -> (DMatrix<f64>, DMatrix<f64>,
     assert!(k > 0, "k must be positive");
     let (q, r, p) = run(a, k, k);
     (q, r.rows(0, k).into_owned(), p)
+}
+
+/// `lupp` (reference :21-86): same errors, and the same bits in l, u, p (first-maximum pivot, the reference's operation order).
+pub fn lupp(matrix: &DMatrix<f64>) -> Result<(DMatrix<f64>, DMatrix<f64>, Vec<usize>), Box<dyn Error>> {
+    let (rows, cols) = matrix.shape();
+    let n = rows.max(1);
+    let mut l = DMatrix::<f64>::zeros(n, n);
+    let mut u = DMatrix::<f64>::zeros(n, n);
+    let mut p = vec![0i64; n];
+    from_status(unsafe { ffi::rnla_lupp(matrix.as_ptr(), rows as i64, cols as i64, l.as_mut_ptr(), u.as_mut_ptr(), p.as_mut_ptr()) })?;
+    Ok((l, u, p.iter().map(|&v| v as usize).collect()))
 }

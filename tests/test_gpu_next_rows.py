@@ -400,6 +400,39 @@ def test_lsqr_at_scale_on_device_buffers(rb):
     torch.cuda.empty_cache()
 
 
+# ----------------------------------------------------------------------------------------------------------- lupp
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 257, 500, 1500])
+def test_lupp_is_bit_identical_to_the_oracle(rb, orc, n):
+    """src/pivot_decompositions.rs:21-86: same pivots, and -- the elimination being kept operation for operation -- the same
+    bits in L and U; test_lupp's own assertions (:351-369) on top"""
+    from randnla_b200 import pivot_decompositions as pd
+    A = random_matrix(n, n, seed=n + 1)
+    l, u, p = pd.lupp(A)
+    Lo, Uo, po = orc.lupp(A)
+    assert p == po.tolist()
+    assert np.array_equal(l, Lo) and np.array_equal(u, Uo)
+    assert np.abs(l @ u - A[p, :]).max() <= 1e-10 * n * max(1.0, np.abs(A).max())
+    assert not np.triu(l, 1).any() and not np.tril(u, -1).any()
+
+
+def test_lupp_errors_ties_and_structured_inputs(rb, orc):
+    from randnla_b200 import pivot_decompositions as pd
+    from randnla_b200.errors import NotSquare, SingularMatrix
+    with pytest.raises(NotSquare, match="Matrix must be square, found matrix with 3 rows and 4 columns"):
+        pd.lupp(np.zeros((3, 4), order="F"))
+    with pytest.raises(SingularMatrix, match="Matrix must be nonsingular for an LU decomposition"):
+        pd.lupp(np.asfortranarray(np.array([[0.0, 1.0, 2.0], [0.0, 3.0, 4.0], [0.0, 5.0, 6.0]])))
+    l, u, p = pd.lupp(np.asfortranarray(np.array([[1.0, 2.0], [2.0, 4.0]])))          # the last diagonal entry is never examined (:32)
+    assert u[1, 1] == 0.0 and p == [1, 0]
+    # ties: rows of equal magnitude, the first wins; a matrix that needs no pivoting; one that pivots at every step
+    for A in (np.array([[2.0, 1.0, 0.0], [-2.0, 0.0, 1.0], [2.0, 3.0, 5.0]]), np.eye(9) * 3 + np.triu(np.ones((9, 9))),
+              np.flipud(np.eye(33)) + 1e-3 * random_matrix(33, 33, seed=2), rank_k_matrix(40, 40, 12, seed=3) + 1e-9 * np.eye(40)):
+        A = np.asfortranarray(A)
+        l, u, p = pd.lupp(A)
+        Lo, Uo, po = orc.lupp(A)
+        assert p == po.tolist() and np.array_equal(l, Lo) and np.array_equal(u, Uo)
+
+
 # ------------------------------------------------------------------------------------------------------ src/cg.rs
 def _spd(n, cond, seed):
     rng = np.random.default_rng(seed)

@@ -328,3 +328,32 @@ def test_cgls_reference_cases(orc):
     assert not conv and it == 1 and np.linalg.norm(x) > 1e-20
     x, it, conv = orc.cgls(a, b, 1e-12, 100)
     assert conv and np.abs(x[:, 0] - np.linalg.solve(a, b)).max() < 1e-10
+
+
+# ---- lupp (src/pivot_decompositions.rs:21-86)
+@pytest.mark.parametrize("n", [1, 2, 7, 64, 500])
+def test_lupp_reference_properties_and_lapack(orc, n):
+    """test_lupp (:351-369; n = 500 there): triangular factors, P L U = A at 1e-4 (1e-10 here), and agreement with LAPACK's
+    dgetrf -- the same pivot rule (first maximum of |.|) gives the same permutation, factors equal to rounding"""
+    A = random_matrix(n, n, seed=n)
+    L, U, p = orc.lupp(A)
+    assert np.array_equal(np.triu(L, 1), np.zeros((n, n))) and np.array_equal(np.diag(L), np.ones(n))
+    assert np.array_equal(np.tril(U, -1), np.zeros((n, n)))
+    assert np.abs((L @ U) - A[p, :]).max() <= 1e-10 * max(1.0, np.abs(A).max()) * n
+    P, Ls, Us = sl.lu(A)
+    assert np.array_equal(P.T @ A, A[p, :])
+    assert np.abs(L - Ls).max() <= 1e-9 * n and np.abs(U - Us).max() <= 1e-9 * n * np.abs(Us).max()
+    assert np.abs(L).max() <= 1.0
+
+
+def test_lupp_errors_and_ties(orc):
+    """NotSquare (:23-27), SingularMatrix on a zero pivot column (:44-48) -- but not for a zero LAST diagonal entry, which the
+    loop never examines (:32); ties go to the first row (strict `>`)"""
+    with pytest.raises(ValueError, match="5"):
+        orc.lupp(np.zeros((3, 4)))
+    with pytest.raises(ValueError, match="6"):
+        orc.lupp(np.asfortranarray(np.array([[0.0, 1.0, 2.0], [0.0, 3.0, 4.0], [0.0, 5.0, 6.0]])))
+    L, U, p = orc.lupp(np.asfortranarray(np.array([[1.0, 2.0], [2.0, 4.0]])))         # singular, but only U[1, 1] shows it
+    assert U[1, 1] == 0.0 and list(p) == [1, 0]
+    L, U, p = orc.lupp(np.asfortranarray(np.array([[2.0, 1.0, 0.0], [-2.0, 0.0, 1.0], [2.0, 3.0, 5.0]])))
+    assert p[0] == 0
