@@ -202,10 +202,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_call"] * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": ["f64", "f64 (range-finder passes: int8 tensor cores on a 28-bit fixed-point split of A; Q^T A, factorisations and outputs f64)",
-                                        "f64 results; every pass over A on the int8 tensor cores with exact int32 accumulation: 28-bit balanced-digit split for the "
-                                        "range-finder passes, 49-bit split (28 digit pairs) for Q^T A; factorisations, small products and outputs f64"][i8_level], "data": "synthetic",
-        "config": {"workload": f"rand_svd f64 {args.rows * args.gpus}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"rand_svd f64 {args.rows * args.gpus}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}, Gaussian sketch",
                    "timed_on": f"{sample_rows}x{n} row sample (CPU), throughput is per byte of A streamed"},
         "cpu_baseline": cb, "gpu_launches": 0,
         "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -222,3 +222,19 @@ def test_int8_digit_pair_groups_cover_the_product():
         got = ua * ub * sum(v * 2.0 ** (-7 * (g + 2)) for g, v in acc.items())
         assert abs(got - a @ b) <= tol * ua * ub * len(a)
         assert len([1 for ta in range(nd) for tb in range(nd) if ta + tb <= gmax]) == {(False, 3): 10, (False, 6): 16, (True, 6): 28}[(seven, gmax)]
+
+
+def test_bench_reference_arm_prints_its_json_line():
+    """`bench.py --impl reference` (the oracle's literal-mode rand_svd on host cores, no GPU) keeps the contract's keys"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-rows", "600", "--cols", "400"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "rand_svd_A_stream_GBps" and line["unit"] == "GB/s"
+    assert line["value"] > 0 and line["dtype"] == "f64" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
