@@ -531,3 +531,29 @@ def test_next_rows_golden_vectors(rb):
     for mu, key in ((0.0, "sp_x_mu0"), (2.0, "sp_x_mu2")):
         x, y = sp.sketch_saddle_point_precondition(F(g["sp_A"]), F(g["sp_b"]), F(g["sp_c"]), mu, 1e-12, 200, 2.0)
         assert np.abs(x - g[key]).max() < 1e-10
+
+
+def test_solvers_golden_vectors(rb):
+    """tests/golden/solvers_golden.npz: scipy's lsqr (six iterations, stopping tests off), LAPACK solutions and pivots, the
+    oracle's bit-exact LU factors -- reproduced by the CUDA path without the oracle in the loop"""
+    import os
+    from randnla_b200 import solvers, cg, pivot_decompositions as pd
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "solvers_golden.npz"))
+    A, b = np.asfortranarray(g["lsqr_A"]), g["lsqr_b"]
+    for tag, damp, x0 in (("plain", 0.0, None), ("damped_x0", 0.3, g["lsqr_x0"])):
+        x, istop, itn, r1, r2, an, ac, hist, xn, var = solvers.lsqr(A, b, damp, 0.0, 0.0, 0.0, 6, True, x0)
+        sc = g[f"lsqr_{tag}_scalars"]
+        assert (istop, itn) == (int(sc[0]), int(sc[1]))
+        assert np.abs(x[:, 0] - g[f"lsqr_{tag}_x"]).max() <= 1e-11 * np.abs(g[f"lsqr_{tag}_x"]).max()
+        assert np.allclose([r1, r2, an, ac, xn], sc[2:], rtol=1e-11, atol=0)
+        assert np.allclose(var, g[f"lsqr_{tag}_var"], rtol=1e-10, atol=0)
+    x, *_ = solvers.lsqr(A, b, 0.0, 1e-14, 1e-14, 1e8, None, False, None)
+    assert np.abs(x[:, 0] - g["lsqr_lstsq_x"]).max() <= 1e-9 * np.abs(g["lsqr_lstsq_x"]).max()
+    info = {}
+    xs = cg.cgls(A, b, 1e-11, 500, None, info=info)
+    assert abs(info["iterations"] - int(g["cgls_iterations"][0])) <= 1 and info["converged"] and np.abs(xs[:, 0] - g["lsqr_lstsq_x"]).max() <= 1e-9
+    info = {}
+    xo = cg.conjugate_grad(np.asfortranarray(g["cg_A"]), g["cg_b"], None, info=info)
+    assert abs(info["iterations"] - int(g["cg_iterations"][0])) <= 1 and info["converged"] and np.abs(xo - g["cg_x_lapack"]).max() < 1e-6
+    l, u, p = pd.lupp(np.asfortranarray(g["lupp_A"]))
+    assert np.array_equal(l, g["lupp_L"]) and np.array_equal(u, g["lupp_U"]) and p == g["lupp_p"].tolist()

@@ -357,3 +357,26 @@ def test_lupp_errors_and_ties(orc):
     assert U[1, 1] == 0.0 and list(p) == [1, 0]
     L, U, p = orc.lupp(np.asfortranarray(np.array([[2.0, 1.0, 0.0], [-2.0, 0.0, 1.0], [2.0, 3.0, 5.0]])))
     assert p[0] == 0
+
+
+def test_solvers_golden_vectors(orc):
+    """tests/golden/solvers_golden.npz (scipy lsqr / LAPACK / oracle outputs with their generating script): the oracle
+    reproduces them; the same file is the target of the CUDA path in tests/test_gpu_next_rows.py"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "solvers_golden.npz"))
+    A, b = np.asfortranarray(g["lsqr_A"]), g["lsqr_b"]
+    for tag, damp, x0 in (("plain", 0.0, None), ("damped_x0", 0.3, g["lsqr_x0"])):
+        x, istop, itn, r1, r2, an, ac, hist, xn, var = orc.lsqr(A, b, damp, 0.0, 0.0, 0.0, 6, True, x0)
+        sc = g[f"lsqr_{tag}_scalars"]
+        assert (istop, itn) == (int(sc[0]), int(sc[1]))
+        assert np.abs(x[:, 0] - g[f"lsqr_{tag}_x"]).max() <= 1e-11 * np.abs(g[f"lsqr_{tag}_x"]).max()
+        assert np.allclose([r1, r2, an, ac, xn], sc[2:], rtol=1e-11, atol=0)
+        assert np.allclose(var, g[f"lsqr_{tag}_var"], rtol=1e-10, atol=0)
+    x, *_ = orc.lsqr(A, b, 0.0, 1e-14, 1e-14, 1e8, None, False, None)
+    assert np.abs(x[:, 0] - g["lsqr_lstsq_x"]).max() <= 1e-9 * np.abs(g["lsqr_lstsq_x"]).max()
+    xs, it, conv = orc.cgls(A, b, 1e-11, 500)
+    assert [it, int(conv)] == g["cgls_iterations"].tolist() and np.abs(xs[:, 0] - g["lsqr_lstsq_x"]).max() <= 1e-9
+    xo, ito, convo = orc.conjugate_grad(np.asfortranarray(g["cg_A"]), g["cg_b"])
+    assert [ito, int(convo)] == g["cg_iterations"].tolist() and np.abs(xo - g["cg_x_lapack"]).max() < 1e-6
+    L, U, p = orc.lupp(np.asfortranarray(g["lupp_A"]))
+    assert np.array_equal(L, g["lupp_L"]) and np.array_equal(U, g["lupp_U"]) and np.array_equal(p, g["lupp_p"])
+    assert np.abs(L - g["lupp_L_lapack"]).max() < 1e-12 and np.abs(U - g["lupp_U_lapack"]).max() < 1e-12
