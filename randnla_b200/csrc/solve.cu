@@ -72,7 +72,33 @@ gemv_t_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, c
     const int64_t i0 = (int64_t)blockIdx.y * rows_per_split, i1 = min(m, i0 + rows_per_split);
     double acc[GT_CB] = {0.0, 0.0, 0.0, 0.0};
     const int ncv = (int)min((int64_t)GT_CB, n - c0);
-    for (int64_t i = i0 + threadIdx.x; i < i1; i += GV_T) {
+    int64_t i_scalar = i0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 2 == 0) && ((reinterpret_cast<uintptr_t>(r) & 15) == 0) &&
+                     (i0 % 2 == 0) && ncv == GT_CB;
+    if (vec) {
+        // two rows per thread and two such steps per trip: eight 16-byte loads of A in flight per thread (128 B), which is what
+        // an HBM-bound stream needs at 8 CTAs per SM; rows walked in a fixed order (deterministic sums)
+        const int64_t span = 4 * GV_T;                                      // rows per trip of the whole CTA
+        const int64_t full = i0 + (i1 - i0) / span * span;
+        const double* a0 = A + c0 * lda;
+        for (int64_t ib = i0; ib < full; ib += span) {
+            const int64_t ia = ib + 2 * threadIdx.x, ic = ia + 2 * GV_T;
+            double2 va[GT_CB], vc[GT_CB];
+#pragma unroll
+            for (int c = 0; c < GT_CB; ++c) {
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(va[c].x), "=d"(va[c].y) : "l"(a0 + ia + c * lda));
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(vc[c].x), "=d"(vc[c].y) : "l"(a0 + ic + c * lda));
+            }
+            const double2 ra = *reinterpret_cast<const double2*>(r + ia), rc = *reinterpret_cast<const double2*>(r + ic);
+#pragma unroll
+            for (int c = 0; c < GT_CB; ++c) {
+                acc[c] = fma(va[c].x, ra.x, acc[c]); acc[c] = fma(va[c].y, ra.y, acc[c]);
+                acc[c] = fma(vc[c].x, rc.x, acc[c]); acc[c] = fma(vc[c].y, rc.y, acc[c]);
+            }
+        }
+        i_scalar = full;
+    }
+    for (int64_t i = i_scalar + threadIdx.x; i < i1; i += GV_T) {
         const double ri = r[i];
 #pragma unroll
         for (int c = 0; c < GT_CB; ++c)
