@@ -366,6 +366,27 @@ def test_lsqr_reference_cases(rb):
         solvers.lsqr(A, b[:-1])
 
 
+def test_lsqr_underdetermined_damped_and_zero_rhs(rb, orc):
+    """a wide system (64 x 90) with damping, against the oracle over six iterations and against the regularised normal equations at
+    convergence; b = 0 with a non-zero x0 (the early return of :181-183 does not apply: u = -A x0)"""
+    from randnla_b200 import solvers
+    A = random_matrix(64, 90, seed=12)
+    b = np.random.default_rng(13).standard_normal(64)
+    got = solvers.lsqr(A, b, 0.1, 0.0, 0.0, 0.0, 6, True, None)
+    ref = orc.lsqr(A, b, 0.1, 0.0, 0.0, 0.0, 6, True, None)
+    assert got[1] == ref[1] == 7 and np.abs(got[0] - ref[0]).max() <= 1e-11 * np.abs(ref[0]).max()
+    for i in (3, 4, 5, 6, 8):
+        assert abs(got[i] - ref[i]) <= 1e-11 * abs(ref[i])
+    assert np.abs(got[9] - ref[9]).max() <= 1e-11 * ref[9].max()
+    x, istop, *_ = solvers.lsqr(A, b, 0.1, 1e-13, 1e-13, 1e8, None, False, None)
+    xs = np.linalg.solve(A.T @ A + 0.01 * np.eye(90), A.T @ b)
+    assert istop in (1, 2) and np.abs(x[:, 0] - xs).max() <= 1e-8 * np.abs(xs).max()
+    x0 = np.random.default_rng(14).standard_normal(90)
+    got = solvers.lsqr(A, np.zeros(64), 0.0, 0.0, 0.0, 0.0, 4, False, x0)
+    ref = orc.lsqr(A, np.zeros(64), 0.0, 0.0, 0.0, 0.0, 4, False, x0)
+    assert got[2] == ref[2] and np.abs(got[0] - ref[0]).max() <= 1e-11 * np.abs(ref[0]).max()
+
+
 def test_lsqr_at_scale_on_device_buffers(rb):
     """rnla_lsqr_dev on a 1 000 000 x 500 system (4 GB) resident in HBM: planted solution recovered, the normal-equations
     residual is at rounding level, and the running estimates (r1norm, xnorm, anorm <= ||A||_F) agree with the true values"""
