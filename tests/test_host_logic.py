@@ -238,3 +238,61 @@ def test_bench_reference_arm_prints_its_json_line():
     assert line["value"] > 0 and line["dtype"] == "f64" and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+# ---- the row-sharded dataflow of the iterative solvers (csrc/solve.cu: dev_lsqr, cgls_operator): u / r sharded with A, the n-vectors
+# ---- replicated, A^T u all-reduced, every norm of an m-vector an all-reduced scalar -- over world_size-2 gloo
+def _solver_worker(rank, world, port, m, n, out):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from randnla_b200.runtime import shard_rows
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((m, n)) * np.logspace(0, -1, n); b = rng.standard_normal(m)
+    r0, r1 = shard_rows(m, world, rank)
+    Al, bl = A[r0:r1], b[r0:r1]
+
+    def allsum(x):
+        t = torch.from_numpy(np.atleast_1d(np.asarray(x, dtype=np.float64)).copy()); dist.all_reduce(t); return t.numpy()
+
+    # LSQR, damp = 0 (src/solvers.rs:140-232), six iterations, local arithmetic on the shard + the collectives of dev_lsqr
+    x = np.zeros(n); u = bl.copy()
+    beta = float(np.sqrt(allsum(u @ u)[0])); u /= beta
+    v = allsum(Al.T @ u); alfa = float(np.linalg.norm(v)); v /= alfa
+    w = v.copy(); rhobar, phibar = alfa, beta
+    for _ in range(6):
+        u = Al @ v - alfa * u
+        beta = float(np.sqrt(allsum(u @ u)[0])); u /= beta
+        v = allsum(Al.T @ u) - beta * v
+        alfa = float(np.linalg.norm(v)); v /= alfa
+        rho = np.hypot(rhobar, beta); cs, sn = rhobar / rho, beta / rho
+        theta = sn * alfa; rhobar = -cs * alfa; phi = cs * phibar; phibar = sn * phibar
+        x = x + (phi / rho) * w
+        w = v - (theta / rho) * w
+    # CGLS (src/cg.rs:29-52), five iterations
+    xc = np.zeros(n); r = bl - Al @ xc
+    s = allsum(Al.T @ r); p = s.copy(); ns = float(s @ s)
+    for _ in range(5):
+        ap = Al @ p
+        alpha = ns / float(allsum(ap @ ap)[0])
+        xc = xc + alpha * p; r = r - alpha * ap
+        s = allsum(Al.T @ r); nn = float(s @ s)
+        p = s + (nn / ns) * p; ns = nn
+    if rank == 0:
+        np.savez(out, x=x, xc=xc)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_solver_dataflow_matches_single_process_oracle(tmp_path, orc):
+    import torch.multiprocessing as mp
+    m, n = 157, 23
+    out = str(tmp_path / "solvers.npz")
+    mp.spawn(_solver_worker, args=(2, _free_port(), m, n, out), nprocs=2, join=True)
+    got = np.load(out)
+    rng = np.random.default_rng(5)
+    A = np.asfortranarray(rng.standard_normal((m, n)) * np.logspace(0, -1, n)); b = rng.standard_normal(m)
+    xl = orc.lsqr(A, b, 0.0, 0.0, 0.0, 0.0, 6, False, None)[0][:, 0]
+    xc, it, conv = orc.cgls(A, b, 1e-300, 5)
+    assert np.abs(got["x"] - xl).max() <= 1e-12 * np.abs(xl).max()
+    assert np.abs(got["xc"] - xc[:, 0]).max() <= 1e-12 * np.abs(xc).max()
