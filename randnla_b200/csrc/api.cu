@@ -313,6 +313,7 @@ rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, doub
                 if (e != cudaSuccess) { rc = cuda_fail(e, "streamed upload of A", __FILE__, __LINE__); break; }
                 rc = fused ? dev_sketch_gemm(dAp + r0, m, rows, n, o.dist, o.seed, 1 /* STREAM_RANGE_N */, l, Y + r0, ldy)
                            : dev_gemm_nn(dAp + r0, m, rows, n, S, n, l, Y + r0, ldy);
+                if (rc == RNLA_OK && c.block_landed_hook) rc = c.block_landed_hook(r0, rows);     // int8 passes: split this block now
             }
             cudaEventDestroy(ready); cudaEventDestroy(landed);
             return rc;

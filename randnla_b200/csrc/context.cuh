@@ -31,6 +31,8 @@ struct Ctx {
     // Y = A * Omega of the power iteration by "upload a row block, multiply it" (the pass hides behind the PCIe copy)
     cudaStream_t copy_stream = nullptr;
     std::function<rnla_status(double* S, double* Y, int64_t ldy)> first_pass_hook;
+    // called by that hook after each row block [r0, r0 + rows) of A has landed and been multiplied (the int8 split of the block)
+    std::function<rnla_status(int64_t r0, int64_t rows)> block_landed_hook;
 };
 
 Ctx& ctx();

@@ -209,17 +209,27 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
     }
     while (q - done >= 2) {
         {
-            PhaseScope ph(virt ? (c.first_pass_hook ? "upload+pass:A*Omega" : use_fused(o, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)") : "pass:A*S");
+            PhaseScope ph(virt ? (c.first_pass_hook ? (g_i8_deferred ? "upload+pass:A*Omega+i8:split(A)" : "upload+pass:A*Omega") : use_fused(o, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)") : "pass:A*S");
             if (virt && c.first_pass_hook) {
                 // host-buffer entry point: A is still arriving over PCIe, row block by row block (api.cu)
                 auto hook = std::move(c.first_pass_hook);
                 c.first_pass_hook = nullptr;
-                RNLA_TRY(hook(S, Ytmp, std::max<int64_t>(m, 1)));
+                // int8 passes: every row block is split (row maxima, digits) right after it has landed and been multiplied, so the
+                // split of A hides behind the PCIe transfer as well; only the last block's is exposed
+                bool split_ok = false;
                 if (g_i8_deferred) {
-                    g_i8_deferred = false; phase_end();
-                    if (i8_prepare(A, lda, m, n, g_i8_p7) != RNLA_OK) { cudaGetLastError(); i8_deactivate(); }
-                    phase_begin("i8:(split done)");
+                    g_i8_deferred = false;
+                    split_ok = i8_prepare_begin(A, lda, m, n, g_i8_p7) == RNLA_OK;
+                    if (!split_ok) { cudaGetLastError(); i8_deactivate(); }
+                    else c.block_landed_hook = [&split_ok](int64_t r0, int64_t rows) -> rnla_status {
+                        if (split_ok && i8_prepare_rows(r0, rows) != RNLA_OK) { cudaGetLastError(); split_ok = false; }
+                        return RNLA_OK;                         // a failed split only means the FP64 kernels run the remaining passes
+                    };
                 }
+                const rnla_status hst = hook(S, Ytmp, std::max<int64_t>(m, 1));
+                c.block_landed_hook = nullptr;
+                RNLA_TRY(hst);
+                if (split_ok) i8_prepare_end(); else i8_deactivate();
             } else if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
                 RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
             } else {

@@ -106,6 +106,9 @@ void i8_set_precise(bool on);
 void i8_release();
 void i8_free_workspace();
 rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool p7 = false);
+rnla_status i8_prepare_begin(const double* A, int64_t lda, int64_t m, int64_t n, bool p7);
+rnla_status i8_prepare_rows(int64_t r0, int64_t count, bool phases = false);
+void i8_prepare_end();
 void i8_set_full(bool on);
 rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc);
 rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz);

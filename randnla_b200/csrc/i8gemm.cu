@@ -175,11 +175,12 @@ constexpr int SL_HI = PLH * 128 * SL_COLS;         // 12 KB: [half][plane 3][J 4
 template <bool P7>
 __global__ void __launch_bounds__(256, P7 ? 3 : 4)
 slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, const double* __restrict__ down,
-               uint8_t* __restrict__ nn, int64_t kb_total, uint8_t* __restrict__ tn, int64_t kr_total, uint8_t* __restrict__ tnhi) {
+               uint8_t* __restrict__ nn, int64_t kb_total, uint8_t* __restrict__ tn, int64_t kr_total, uint8_t* __restrict__ tnhi,
+               int64_t rb0 /* first 128-row block of this launch */) {
     extern __shared__ __align__(16) uint8_t img[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t hb_total = 2 * kb_total;
-    const int64_t rb = blockIdx.x / hb_total, hb = blockIdx.x % hb_total;
+    const int64_t rb = rb0 + blockIdx.x / hb_total, hb = blockIdx.x % hb_total;
     const int64_t kb = hb >> 1;
     const int half = (int)(hb & 1);                         // which 32 columns of the 64-column image block
     const int64_t R0 = rb * 128, C0 = hb * SL_COLS;
@@ -608,8 +609,9 @@ void i8_free_workspace() {
 }
 
 // split A (m x n, lda) into the two tiled int8 images; afterwards dev_gemm_nn / dev_gemm_tn with this A and N <= 128 run on
-// the integer tensor cores until i8_deactivate()
-rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool p7) {
+// the integer tensor cores until i8_deactivate().  Three steps so that the host-buffer entry point can split each row block of A
+// as it lands over PCIe (row maxima are per row: a block of whole rows is self-contained): begin, rows(r0, count)*, end.
+rnla_status i8_prepare_begin(const double* A, int64_t lda, int64_t m, int64_t n, bool p7) {
     Ctx& c = ctx();
     Sliced& s = g_sl;
     s.ready = false; g_active = false;
@@ -627,14 +629,7 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool 
     RNLA_CUDA(s.bimg.ensure((size_t)kmax * CHUNK));
     if (p7) { RNLA_CUDA(s.tnhi.ensure(img_bytes / PL * PLH)); RNLA_CUDA(s.bimg_hi.ensure((size_t)kmax * CHUNK_HI)); }
     RNLA_CUDA(s.cbits.ensure(128 * 8)); RNLA_CUDA(s.cup.ensure(128 * 8)); RNLA_CUDA(s.cdown.ensure(128 * 8));
-    phase_begin("i8:rowmax(A)");
     RNLA_CUDA(cudaMemsetAsync(s.bits.p, 0, (size_t)m * 8, c.stream));
-    const int64_t cols_per = std::max<int64_t>(256, (n + 7) / 8);
-    rowmax_kernel<<<dim3((unsigned)((m + 511) / 512), (unsigned)((n + cols_per - 1) / cols_per)), 256, 0, c.stream>>>(
-        A, lda, m, n, cols_per, s.bits.as<unsigned long long>());
-    scales_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(s.bits.as<unsigned long long>(), m, s.up.d(), s.down.d());
-    phase_end();
-    PhaseScope ph("i8:split(A)");
     static bool attr = false;
     if (!attr) {
         RNLA_CUDA(cudaFuncSetAttribute(slice_a_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_NN + SL_TN));
@@ -645,15 +640,38 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool 
         RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
         attr = true;
     }
-    if (p7)
-        slice_a_kernel<true><<<(unsigned)(s.rblocks * s.kb_total * 2), 256, SL_NN + SL_TN + SL_HI, c.stream>>>(
-            A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total, s.tn.as<uint8_t>(), s.kr_total, s.tnhi.as<uint8_t>());
+    return RNLA_OK;
+}
+// rows [r0, r0 + count) of the matrix given to i8_prepare_begin; r0 must be a multiple of 128 (whole image row blocks)
+rnla_status i8_prepare_rows(int64_t r0, int64_t count, bool phases) {
+    Ctx& c = ctx();
+    Sliced& s = g_sl;
+    if (count <= 0) return RNLA_OK;
+    if (r0 % 128 != 0 || r0 + count > s.m) return fail(RNLA_ERR_COMPUTATION, "int8 split: row block must start on a multiple of 128");
+    const double* A = s.A; const int64_t lda = s.lda, m = s.m, n = s.n;
+    if (phases) phase_begin("i8:rowmax(A)");
+    const int64_t cols_per = std::max<int64_t>(256, (n + 7) / 8);
+    rowmax_kernel<<<dim3((unsigned)((count + 511) / 512), (unsigned)((n + cols_per - 1) / cols_per)), 256, 0, c.stream>>>(
+        A + r0, lda, count, n, cols_per, s.bits.as<unsigned long long>() + r0);
+    scales_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c.stream>>>(s.bits.as<unsigned long long>() + r0, count, s.up.d() + r0, s.down.d() + r0);
+    if (phases) { phase_end(); phase_begin("i8:split(A)"); }
+    const int64_t rb0 = r0 / 128, nrb = (count + 127) / 128;
+    if (s.p7)
+        slice_a_kernel<true><<<(unsigned)(nrb * s.kb_total * 2), 256, SL_NN + SL_TN + SL_HI, c.stream>>>(
+            A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total, s.tn.as<uint8_t>(), s.kr_total, s.tnhi.as<uint8_t>(), rb0);
     else
-        slice_a_kernel<false><<<(unsigned)(s.rblocks * s.kb_total * 2), 256, SL_NN + SL_TN, c.stream>>>(
-            A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total, s.tn.as<uint8_t>(), s.kr_total, nullptr);
+        slice_a_kernel<false><<<(unsigned)(nrb * s.kb_total * 2), 256, SL_NN + SL_TN, c.stream>>>(
+            A, lda, m, n, s.down.d(), s.nn.as<uint8_t>(), s.kb_total, s.tn.as<uint8_t>(), s.kr_total, nullptr, rb0);
+    if (phases) phase_end();
     g_kernel_launches += 3;
     RNLA_CUDA(cudaGetLastError());
-    s.ready = true; g_active = true;
+    return RNLA_OK;
+}
+void i8_prepare_end() { g_sl.ready = true; g_active = true; }
+rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool p7) {
+    RNLA_TRY(i8_prepare_begin(A, lda, m, n, p7));
+    RNLA_TRY(i8_prepare_rows(0, m, true));
+    i8_prepare_end();
     return RNLA_OK;
 }
 

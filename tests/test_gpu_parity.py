@@ -879,7 +879,8 @@ def test_rand_svd_int8_range_passes_match_the_oracle(rb, orc, m, n, k, s, level)
     with rt.options(range_passes_int8=level):        # 2: Q^T A too, on a 49-bit split
         U, S, Vt = ld.rand_svd(A, k, 1e-6, s)
         names = [nm for nm, _ in rt.timings()]
-    assert "i8:split(A)" in names and "pass:At*Q" in names
+    # (host buffers of >= 8192 rows are uploaded in row blocks and split block by block inside the upload phase)
+    assert any("i8:split(A)" in nm for nm in names) and "pass:At*Q" in names
     Uo, So, Vto = orc.rand_svd(A, k, 1e-6, s, orc.make_opts(mode=0))
     sg, so = np.diag(S), np.diag(So)
     assert np.max(np.abs(sg - so) / so) < SIG_TOL
@@ -888,11 +889,11 @@ def test_rand_svd_int8_range_passes_match_the_oracle(rb, orc, m, n, k, s, level)
     assert subspace_angle(np.linalg.qr(U)[0], np.linalg.qr(Uo)[0]) < 1e-4
     # off by default, and small inputs keep the FP64 path even when it is on
     U2, S2, Vt2 = ld.rand_svd(A, k, 1e-6, s)
-    assert "i8:split(A)" not in [nm for nm, _ in rt.timings()]
+    assert not any("i8:split(A)" in nm for nm, _ in rt.timings())
     assert np.max(np.abs(np.diag(S2) - so) / so) < SIG_TOL
     with rt.options(range_passes_int8=1):
         ld.rand_svd(random_matrix(300, 200, seed=1), 10, 1e-6, 5)
-        assert "i8:split(A)" not in [nm for nm, _ in rt.timings()]
+        assert not any("i8:split(A)" in nm for nm, _ in rt.timings())
 
 
 @pytest.mark.parametrize("level", [1, 2])
@@ -924,7 +925,7 @@ def test_int8_passes_on_degenerate_inputs(rb, orc, level):
     A = rank_k_matrix(4200, 1100, 30, seed=8)
     with rt.options(range_passes_int8=level):
         U, S, Vt = ld.rand_svd(A, 50, 1e-6, 10)
-        assert "i8:split(A)" in [nm for nm, _ in rt.timings()]
+        assert any("i8:split(A)" in nm for nm, _ in rt.timings())
     so = np.linalg.svd(A, compute_uv=False)
     sg = np.diag(S)
     assert np.max(np.abs(sg[:30] - so[:30]) / so[:30]) < SIG_TOL
