@@ -458,11 +458,38 @@ rnla_status dev_rand_evd2(const double* A, int64_t lda, int64_t m_local, int64_t
     RNLA_CUDA(SY.alloc((size_t)l * l * 8)); RNLA_CUDA(Rinv.alloc((size_t)l * l * 8));
     RNLA_CUDA(Ur.alloc((size_t)l * l * 8)); RNLA_CUDA(Vr.alloc((size_t)l * l * 8)); RNLA_CUDA(sig.alloc((size_t)l * 8));
     RNLA_CUDA(flags.alloc((size_t)l * 4)); RNLA_CUDA(info.alloc(16)); RNLA_CUDA(scal.alloc(8)); RNLA_CUDA(scratch.alloc(1024 * 8));
-    RNLA_TRY(dev_tsog1(A, lda, sh, n, l, q, pps, o, S.d()));
-    {
-        PhaseScope ph("pass:A*S");
-        RNLA_TRY(dev_gemm_nn(A, lda, m_local, n, S.d(), n, l, Y.d(), mm));                 // Y = A S        :187
+    // range_passes_int8 (single GPU, exactly symmetric A -- which PSD-ness presupposes; checked in one pass over A): the
+    // power-iteration products, which only have to span the range, run on the integer tensor cores from the 28-bit split of A;
+    // Y = A S carries the eigenvalues and needs FP64-grade accuracy: level 2 forms it as A^T S on the 49-bit split (the
+    // transposed kernel is the one that has it; A = A^T), level 1 falls back to the FP64 kernel for this one product
+    bool i8 = (o.range_passes_int8 == 1 || o.range_passes_int8 == 2) && o.mode == RNLA_MODE_INTENDED && c.nranks == 1 && m_local == n &&
+              i8_supported(n, n, l);
+    if (i8) {
+        DevBuf sflag;
+        RNLA_CUDA(sflag.alloc(4));
+        RNLA_CUDA(cudaMemsetAsync(sflag.p, 0, 4, c.stream));
+        RNLA_CUDA(check_symmetric(A, lda, n, sflag.as<int>(), c.stream));
+        int h = 0;
+        RNLA_CUDA(cudaMemcpyAsync(&h, sflag.p, 4, cudaMemcpyDeviceToHost, c.stream));
+        RNLA_TRY(sync_stream());
+        if (h) i8 = false;
     }
+    const bool all8 = i8 && o.range_passes_int8 == 2;
+    if (i8 && i8_prepare(A, lda, n, n, all8) != RNLA_OK) { cudaGetLastError(); i8_deactivate(); i8 = false; }
+    rnla_status st = dev_tsog1(A, lda, sh, n, l, q, pps, o, S.d());
+    if (st == RNLA_OK) {
+        PhaseScope ph("pass:A*S");
+        if (all8 && i8_active_for(A, lda, n, n, l)) {
+            i8_set_full(true);
+            st = dev_gemm_tn(A, lda, n, n, S.d(), n, l, Y.d(), mm, false);                  // Y = A^T S = A S on 49 bits
+        } else {
+            i8_deactivate();
+            st = dev_gemm_nn(A, lda, m_local, n, S.d(), n, l, Y.d(), mm);                  // Y = A S        :187
+        }
+    }
+    i8_deactivate();
+    if (i8) i8_release();
+    RNLA_TRY(st);
     double nu;
     {
         PhaseScope ph("nystrom:shift+gram");

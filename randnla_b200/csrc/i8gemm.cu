@@ -591,11 +591,13 @@ rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, const double
 
 }  // namespace
 
+// thin operands wider than one 128-column MMA tile are processed tile by tile (each tile is another sweep over the planes of A)
+constexpr int I8_MAX_N = 256;
 bool i8_supported(int64_t m, int64_t n, int l) {
-    return l >= 1 && l <= BN && n >= 1 && m >= 1 && ((n + 127) / 128) * 128 <= K_ACC_MAX && m * n >= (int64_t)1 << 22;
+    return l >= 1 && l <= I8_MAX_N && n >= 1 && m >= 1 && ((n + 127) / 128) * 128 <= K_ACC_MAX && m * n >= (int64_t)1 << 22;
 }
 bool i8_active_for(const double* A, int64_t lda, int64_t m, int64_t n, int64_t N) {
-    return g_active && g_sl.ready && g_sl.A == A && g_sl.lda == lda && g_sl.m == m && g_sl.n == n && N <= BN;
+    return g_active && g_sl.ready && g_sl.A == A && g_sl.lda == lda && g_sl.m == m && g_sl.n == n && N <= I8_MAX_N;
 }
 void i8_deactivate() { g_active = false; g_precise = false; g_full = false; }
 void i8_set_full(bool on) { g_full = on; }
@@ -676,7 +678,7 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool 
 }
 
 // C (m x N) = A * B (n x N) on the split A
-rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc) {
+static rnla_status i8_gemm_nn_tile(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc) {
     Ctx& c = ctx();
     Sliced& s = g_sl;
     RNLA_TRY(slice_b(B, ldb, s.n, (int)N, nullptr, s.kb_total));
@@ -692,9 +694,14 @@ rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;
 }
+rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc) {
+    for (int64_t c0 = 0; c0 < N; c0 += BN)
+        RNLA_TRY(i8_gemm_nn_tile(B + c0 * ldb, ldb, std::min<int64_t>(BN, N - c0), C + c0 * ldc, ldc));
+    return RNLA_OK;
+}
 
 // Z (n x N) = A^T * Q (m x N) on the split A (local rows only; the caller all-reduces)
-rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz) {
+static rnla_status i8_gemm_tn_tile(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz) {
     Ctx& c = ctx();
     Sliced& s = g_sl;
     const bool full = g_full && s.p7;
@@ -719,6 +726,11 @@ rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64
                                                                                                            stride, s.n, (int)N, s.cup.d(), Z, ldz);
     g_kernel_launches += 2;
     RNLA_CUDA(cudaGetLastError());
+    return RNLA_OK;
+}
+rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz) {
+    for (int64_t c0 = 0; c0 < N; c0 += BN)
+        RNLA_TRY(i8_gemm_tn_tile(Q + c0 * ldq, ldq, std::min<int64_t>(BN, N - c0), Z + c0 * ldz, ldz));
     return RNLA_OK;
 }
 

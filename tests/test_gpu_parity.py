@@ -943,3 +943,37 @@ def test_int8_passes_on_degenerate_inputs(rb, orc, level):
         U, S, Vt = ld.rand_svd(B, 12, 1e-6, 8)
     so = np.linalg.svd(B, compute_uv=False)[:12]
     assert np.max(np.abs(np.diag(S) - so) / so) < 1e-9
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_rand_evd2_int8_passes_match_the_oracle(rb, orc, level):
+    """rand_evd2 (reference src/lora_drivers.rs:167-224) with the power-iteration products on the integer tensor cores and l = 160
+    columns (two 128-column MMA tiles); Y = A S, which carries the eigenvalues, on the 49-bit split (level 2, as A^T S: A is
+    symmetric) or in FP64 (level 1).  Eigenvalues agree with the all-FP64 path to the north_star tolerance; a matrix that is not
+    exactly symmetric keeps the FP64 kernels."""
+    from randnla_b200 import runtime as rt, lora_drivers as ld
+    n, k, s = 2304, 150, 10
+    rng = np.random.default_rng(15)
+    Qm, _ = np.linalg.qr(rng.standard_normal((n, 220)))
+    ev = np.concatenate([np.logspace(1, -2, 150), np.full(70, 1e-6)])
+    A = (Qm * ev) @ Qm.T
+    A = np.asfortranarray(0.5 * (A + A.T))
+    with rt.options(range_passes_int8=level):
+        V, lam = ld.rand_evd2(A, k, s)
+        names = [nm for nm, _ in rt.timings()]
+    assert "i8:split(A)" in names
+    # against the all-FP64 path of the library (itself held to the oracle in test_rand_evd2_reference_cases; the oracle's literal
+    # O(n^3) PSD pre-check makes it unusable at a size where the integer path engages)
+    Vf, lamf = ld.rand_evd2(A, k, s)
+    assert "i8:split(A)" not in [nm for nm, _ in rt.timings()]
+    lam, lamf = np.asarray(lam, dtype=np.float64), np.asarray(lamf, dtype=np.float64)
+    assert len(lam) == len(lamf) == k
+    assert np.max(np.abs(lam - lamf) / lamf) < SIG_TOL
+    assert np.max(np.abs(lam - ev[:k]) / ev[:k]) < 1e-6                     # Nystrom bias from the 1e-6 tail
+    assert np.abs(V.T @ V - np.eye(k)).max() < 1e-11
+    assert np.linalg.norm(A @ V - V * lam) <= 1e-5 * lam.max()
+    assert subspace_angle(np.linalg.qr(V)[0], np.linalg.qr(Vf)[0]) < 1e-4
+    B = A.copy(order="F"); B[3, 7] += 1e-9                                  # not exactly symmetric: no integer passes
+    with rt.options(range_passes_int8=level):
+        ld.rand_evd2(B, k, s)
+        assert "i8:split(A)" not in [nm for nm, _ in rt.timings()]
