@@ -189,6 +189,20 @@ def secondary_configs(torch, rt, _lib, lib, dA_headline, hbm_peak):
     out["c5_rand_evd2_50k_k200"] = {"ms": ms, "tflops_fp64": 4 * 2.0 * nn_ * nn_ * (k + s) / (ms * 1e-3) * 1e-12, "r": int(len(L)),
                                     "max_rel_lambda_err_vs_planted": float(np.max(np.abs(L - (lam[:len(L)] + 1e-8)) / lam[:len(L)])),
                                     "phases_ms": [[k_, v] for k_, v in rt.timings()]}
+    # the same call with every pass over A on the integer tensor cores (range_passes_int8 = 2: power iteration on the 28-bit
+    # split, Y = A S as A^T S on the 49-bit split; l = 210 columns = two 128-column MMA tiles)
+    try:
+        o8 = rt.make_options(range_passes_int8=2)
+        def run5i():
+            res["V8"], res["L8"] = ld.rand_evd2_dev(A5, k, s, o8)
+        ms8 = timed(run5i, 2)
+        L8 = res["L8"].cpu().numpy()
+        out["c5_rand_evd2_50k_k200_int8"] = {"ms": ms8, "r": int(len(L8)),
+                                             "max_rel_lambda_diff_vs_fp64_path": float(np.max(np.abs(L8 - L[:len(L8)]) / L[:len(L8)])),
+                                             "max_rel_lambda_err_vs_planted": float(np.max(np.abs(L8 - (lam[:len(L8)] + 1e-8)) / lam[:len(L8)])),
+                                             "phases_ms": [[k_, v] for k_, v in rt.timings()]}
+    except Exception as exc:
+        out["c5_rand_evd2_50k_k200_int8"] = {"error": repr(exc)[:200]}
     return out
 
 
