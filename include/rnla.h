@@ -76,8 +76,11 @@ typedef struct rnla_options {
                                *    tensor cores (tcgen05 kind::i8) from a 4 x 7-bit balanced-digit split of A, exact int32 accumulation,
                                *    2^-25 .. 2^-28 of (row max) x (column max) per product; Q^T A, which carries the singular values, stays FP64.
                                * 2: Q^T A as well, on a 7 x 7-bit (49-bit) split: 28 digit pairs, exact int32 accumulation, FP64-grade result.
-                               * Applies to rand_svd / rand_evd1 (dev_qb1) in the intended mode, l <= 128, n <= 131072, m n >= 2^22; other
-                               * shapes keep FP64.  Also RNLA_RANGE_INT8=1|2 in the environment.  DESIGN.md section 5c */
+                               * Applies to rand_svd / rand_evd1 (dev_qb1) in the intended mode, l <= 256 (thin operands wider than 128
+                               * columns go through the MMA kernels in 128-column tiles), n <= 131072, m n >= 2^22; other shapes keep FP64.
+                               * rand_evd2 (one GPU, A verified exactly symmetric): the power-iteration products on the 28-bit split;
+                               * Y = A S, which carries the eigenvalues, as A^T S on the 49-bit split (2) or in FP64 (1).
+                               * Also RNLA_RANGE_INT8=1|2 in the environment.  DESIGN.md section 5c */
 } rnla_options;
 
 /* ---- library / context ------------------------------------------------------------------------- */
