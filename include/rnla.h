@@ -71,16 +71,23 @@ typedef struct rnla_options {
     int32_t passes_per_stab;  /* <=0: 1 (same lines) */
     int32_t fused_sketch;     /* 1: Omega is generated inside the A*Omega kernel and never materialised; 0: materialise (K0) then multiply;
                                * 2 (default): fuse iff the n x l operand would not stay L2-resident (> 48 MiB) */
-    int32_t range_passes_int8; /* 0 (default): every pass over A in FP64 (DMMA).
-                               * 1: the range-finder passes (A Omega, A^T Y, A S: results that only have to span a subspace) run on the INT8
-                               *    tensor cores (tcgen05 kind::i8) from a 4 x 7-bit balanced-digit split of A, exact int32 accumulation,
-                               *    2^-25 .. 2^-28 of (row max) x (column max) per product; Q^T A, which carries the singular values, stays FP64.
-                               * 2: Q^T A as well, on a 7 x 7-bit (49-bit) split: 28 digit pairs, exact int32 accumulation, FP64-grade result.
-                               * Applies to rand_svd / rand_evd1 (dev_qb1) in the intended mode, l <= 256 (thin operands wider than 128
-                               * columns go through the MMA kernels in 128-column tiles), n <= 131072, m n >= 2^22; other shapes keep FP64.
-                               * rand_evd2 (one GPU, A verified exactly symmetric): the power-iteration products on the 28-bit split;
-                               * Y = A S, which carries the eigenvalues, as A^T S on the 49-bit split (2) or in FP64 (1).
-                               * Also RNLA_RANGE_INT8=1|2 in the environment.  DESIGN.md section 5c */
+    int32_t range_passes_int8; /* which passes over A run on the INT8 tensor cores (tcgen05 kind::i8) from a balanced-digit fixed-point
+                               * split of A with EXACT int32 accumulation (csrc/i8gemm.cu):
+                               * -1 (default, "auto"): level 3 where the shape is supported, else 0.
+                               *  0: every pass in FP64 (DMMA).
+                               *  3: every pass FP64-grade on the integer pipe: all four products on a 55-bit split (7 digit planes of widths
+                               *     7, 8, ..., 8 bits; 28 digit pairs): the error of a product is below 2^-53 of (row max of A) x (column max of
+                               *     the thin operand) x (contraction length)^(1/2), the normwise error model of an FP64 GEMM, independent of
+                               *     the spectrum of A; singular values agree with the FP64 kernels' like two FP64 GEMMs with different
+                               *     summation orders do.
+                               *  1: A Omega, A^T Y on 31-bit operands (4 planes, 10 pairs), A S with all 16 pairs; Q^T A stays FP64.
+                               *  2: as 1, Q^T A on the 55-bit split.  Levels 1 and 2 are SPECTRUM-CONDITIONAL: they reproduce the FP64 result
+                               *     to 1e-10 only when the part of A outside the captured range is small against sigma_k and
+                               *     sigma_1 / sigma_k <~ 1e4 (DESIGN.md 5c has the measured sweep); opt-in, never chosen by auto.
+                               * Applies to rand_svd / rand_evd1 (dev_qb1) and rand_evd2 in the intended mode, l <= 256 (thin operands wider than
+                               * 128 columns go through the MMA kernels in 128-column tiles), m n >= 2^22; other shapes keep FP64.  A matrix
+                               * with Inf / NaN entries, or with a non-zero row below 2^-959, keeps the FP64 kernels too.
+                               * Also RNLA_RANGE_INT8=0|1|2|3|auto in the environment. */
 } rnla_options;
 
 /* ---- library / context ------------------------------------------------------------------------- */
@@ -359,10 +366,16 @@ int32_t rnla_plan_saso_block(int64_t d, int32_t zeta, int32_t width, int64_t n, 
 int32_t rnla_last_jacobi_sweeps(void);
 rnla_status rnla_small_eigh_dev(const double* dC, int64_t ldc, int64_t p, double* dW, double* dLambda);
 
-/* the integer tensor-core products behind rnla_options.range_passes_int8 (csrc/i8gemm.cu), for tests and benches: one 4 x 7-bit
- * split of A, then `reps` products.  trans = 0: C (m x N) = A B with B n x N;  trans != 0: C (n x N) = A^T B with B m x N.
- * N <= 128, n <= 131072.  reps < 0 (trans = 0 only): |reps| products with all 16 digit pairs (two sweeps), i.e. the exact
- * product of the two 28-bit representations; otherwise the 10 leading pairs (accuracy about 2^-25 of row max x column max). */
+/* the integer tensor-core products behind rnla_options.range_passes_int8 (csrc/i8gemm.cu), for tests and benches: one split of A
+ * into `planes` digit planes (4: 31-bit operands -- all_pairs != 0 adds the sweep over digit-pair groups 4..6; 6: 47-bit; 7: 55-bit),
+ * then `reps` products.  trans = 0: C (m x N) = A B with B n x N;  trans != 0: C (n x N) = A^T B with B m x N.  N <= 256. */
+rnla_status rnla_i8_gemm_dev(int32_t trans, int32_t planes, int32_t all_pairs, const double* dA, int64_t lda, int64_t m, int64_t n,
+                             const double* dB, int64_t ldb, int64_t N, double* dC, int64_t ldc, int32_t reps);
+/* test hook: drain the int32 accumulators of the integer kernels every `stages` stages of 64 contraction indices instead of at the
+ * exactness bound (340 stages for 7 planes); 0 restores the bound.  Results do not change (the drains are exact). */
+rnla_status rnla_debug_i8_flush(int32_t stages);
+/* round-1 form of the same: reps > 0: 4 planes, ten leading pairs; reps < 0: |reps| products, A B with all 16 pairs of the 31-bit
+ * split, A^T B on the 55-bit split */
 rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda, int64_t m, int64_t n, const double* dB, int64_t ldb,
                                    int64_t N, double* dC, int64_t ldc, int32_t reps);
 

@@ -51,6 +51,8 @@ int orc_symmetric_eigen(const double* A, int64_t n, double* W, double* lambda);
 typedef struct orc_opts {
     int mode; int dist; uint64_t seed; int num_passes; int passes_per_stab;
     const double* omega_n; const double* omega_m;
+    int skip_psd_check;   /* rand_evd2 only: skip the O(n^3) eigen-decomposition of src/lora_drivers.rs:178-184 (tests at sizes where
+                           * it would take minutes; the inputs of those tests are PSD by construction) */
 } orc_opts;
 void orc_tsog1(const double* A, int64_t m, int64_t n, int64_t k, int num_passes, int passes_per_stab, const orc_opts* o, double* S);
 void orc_rf1(const double* A, int64_t m, int64_t n, int64_t k, const orc_opts* o, double* Q);

@@ -17,7 +17,7 @@ i32, i64, u32, u64, f64, P = C.c_int, C.c_int64, C.c_uint32, C.c_uint64, C.c_dou
 
 class Opts(C.Structure):
     _fields_ = [("mode", C.c_int), ("dist", C.c_int), ("seed", u64), ("num_passes", C.c_int),
-                ("passes_per_stab", C.c_int), ("omega_n", P), ("omega_m", P)]
+                ("passes_per_stab", C.c_int), ("omega_n", P), ("omega_m", P), ("skip_psd_check", C.c_int)]
 
 
 def build():
@@ -56,8 +56,8 @@ def p(a):
 MODE_INTENDED, MODE_LITERAL = 0, 1
 
 
-def make_opts(mode=MODE_INTENDED, dist=0, seed=0, num_passes=0, passes_per_stab=0, omega_n=None, omega_m=None):
-    o = Opts(mode, dist, seed, num_passes, passes_per_stab, None, None)
+def make_opts(mode=MODE_INTENDED, dist=0, seed=0, num_passes=0, passes_per_stab=0, omega_n=None, omega_m=None, skip_psd_check=False):
+    o = Opts(mode, dist, seed, num_passes, passes_per_stab, None, None, int(bool(skip_psd_check)))
     keep = []
     if omega_n is not None:
         on = F(omega_n); keep.append(on); o.omega_n = on.ctypes.data

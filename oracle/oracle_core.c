@@ -554,7 +554,7 @@ int orc_rand_evd1(const double* A, int64_t n, int64_t k, double epsilon, int64_t
 int orc_rand_evd2(const double* A, int64_t n, int64_t k, int64_t s, const orc_opts* o, double* V, double* lambda, int64_t* r_out) {
     if (k <= 0) return 1;                                                  /* :169-173 */
     if (r_out) *r_out = 0;
-    {   /* :178-184 PSD check through a full symmetric eigen-decomposition */
+    if (!o || !o->skip_psd_check) {   /* :178-184 PSD check through a full symmetric eigen-decomposition */
         double* W = dalloc(n * n); double* lam = dalloc(n);
         orc_symmetric_eigen(A, n, W, lam);
         int neg = 0; double amax = 0;

@@ -103,6 +103,8 @@ SIGNATURES = {
     "rnla_cur_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i32, C.POINTER(Options), P, P, c_i64, P]),
     "rnla_sketch_saddle_point_precondition": (c_i32, [P, c_i64, c_i64, P, P, c_f64, c_f64, c_i64, c_f64, P, P, P, P]),
     "rnla_sketch_saddle_point_precondition_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, P, c_f64, c_f64, c_i64, c_f64, P, P, P, P]),
+    "rnla_i8_gemm_dev": (c_i32, [c_i32, c_i32, c_i32, P, c_i64, c_i64, c_i64, P, c_i64, c_i64, P, c_i64, c_i32]),
+    "rnla_debug_i8_flush": (c_i32, [c_i32]),
     "rnla_i8_range_gemm_dev": (c_i32, [c_i32, P, c_i64, c_i64, c_i64, P, c_i64, c_i64, P, c_i64, c_i32]),
     "rnla_small_eigh_dev": (c_i32, [P, c_i64, c_i64, P, P]),
     "rnla_generate_lowrank_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, P, c_f64, c_u64]),

@@ -932,22 +932,23 @@ rnla_status rnla_sketch_saddle_point_precondition(const double* A, int64_t m, in
     return d2h(y, dy.d(), (size_t)m);
 }
 
-// ---- INT8 tensor-core range-finder products (i8gemm.cu), exposed for tests and benches --------------------------------
-// trans = 0: C (m x N) = A (m x n) * B (n x N);  trans != 0: C (n x N) = A^T * B (m x N).  `reps` products with one split of A.
-rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda, int64_t m, int64_t n, const double* dB, int64_t ldb,
-                                   int64_t N, double* dC, int64_t ldc, int32_t reps) {
+// ---- INT8 tensor-core products (i8gemm.cu), exposed for tests and benches -------------------------------------------------------
+// trans = 0: C (m x N) = A (m x n) * B (n x N);  trans != 0: C (n x N) = A^T * B (m x N).  `reps` products with one split of A into
+// `planes` digit planes (4: 31-bit operands, all_pairs != 0 adds the digit pairs of groups 4..6; 6: 47-bit; 7: 55-bit, FP64-grade).
+rnla_status rnla_i8_gemm_dev(int32_t trans, int32_t planes, int32_t all_pairs, const double* dA, int64_t lda, int64_t m, int64_t n,
+                             const double* dB, int64_t ldb, int64_t N, double* dC, int64_t ldc, int32_t reps) {
     RNLA_API_GUARD;
     RNLA_TRY(ensure_ctx());
-    if (N < 1 || N > 128 || ((n + 127) / 128) * 128 > 131072 || m < 1 || n < 1)
-        return fail(RNLA_ERR_INVALID_DIMENSIONS, "i8 range gemm: 1 <= N <= 128, n <= 131072");
+    if (N < 1 || N > 256 || m < 1 || n < 1) return fail(RNLA_ERR_INVALID_DIMENSIONS, "i8 gemm: 1 <= N <= 256");
+    if (planes != 4 && planes != 6 && planes != 7) return fail(RNLA_ERR_INVALID_PARAMETERS, "i8 gemm: planes must be 4, 6 or 7");
     phases_reset();
-    RNLA_TRY(i8_prepare(dA, lda, m, n, trans && reps < 0));
-    i8_set_precise(!trans && reps < 0);                    // reps < 0: A B with all 16 digit pairs (two sweeps)
-    i8_set_full(trans && reps < 0);                        // reps < 0, trans: A^T B on the 49-bit split (28 digit pairs)
-    reps = std::abs(reps);
+    bool usable = false;
+    RNLA_TRY(i8_prepare(dA, lda, m, n, planes, &usable));
+    if (!usable) { i8_release(); return fail(RNLA_ERR_COMPUTATION, "i8 gemm: A holds non-finite values or rows too small to scale"); }
     rnla_status st = RNLA_OK;
     for (int r = 0; r < std::max(reps, 1) && st == RNLA_OK; ++r) {
         PhaseScope ph(trans ? "i8:At*B" : "i8:A*B");
+        i8_set_precision(planes, all_pairs != 0);
         st = trans ? i8_gemm_tn(dB, ldb, N, dC, ldc) : i8_gemm_nn(dB, ldb, N, dC, ldc);
     }
     i8_deactivate();
@@ -956,6 +957,19 @@ rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda,
     RNLA_TRY(st);
     RNLA_CUDA(e);
     return RNLA_OK;
+}
+// tests: drain the int32 accumulators every `stages` stages of 64 contraction indices (0 restores the exactness bound)
+rnla_status rnla_debug_i8_flush(int32_t stages) {
+    RNLA_API_GUARD;
+    i8_debug_flush(stages);
+    return RNLA_OK;
+}
+// round-1 entry point, kept: reps > 0: the ten leading digit pairs of the 31-bit split; reps < 0: A B with all 16 pairs, A^T B on
+// the 55-bit split
+rnla_status rnla_i8_range_gemm_dev(int32_t trans, const double* dA, int64_t lda, int64_t m, int64_t n, const double* dB, int64_t ldb,
+                                   int64_t N, double* dC, int64_t ldc, int32_t reps) {
+    if (reps >= 0) return rnla_i8_gemm_dev(trans, 4, 0, dA, lda, m, n, dB, ldb, N, dC, ldc, reps);
+    return rnla_i8_gemm_dev(trans, trans ? 7 : 4, 1, dA, lda, m, n, dB, ldb, N, dC, ldc, -reps);
 }
 
 // the digit-plane workspace of the int8 passes persists across calls (tens of GB at the headline size); give it back

@@ -34,8 +34,10 @@ static void default_opts(rnla_options* o) {
     o->num_passes = 0;
     o->passes_per_stab = 0;
     o->fused_sketch = 2;
+    o->range_passes_int8 = -1;          // auto: FP64-grade passes on the integer tensor cores where the shape is supported
     const char* r8 = getenv("RNLA_RANGE_INT8");
-    if (r8 && (!strcmp(r8, "1") || !strcmp(r8, "2"))) o->range_passes_int8 = r8[0] - '0';
+    if (r8 && r8[0] >= '0' && r8[0] <= '3' && !r8[1]) o->range_passes_int8 = r8[0] - '0';
+    if (r8 && !strcmp(r8, "auto")) o->range_passes_int8 = -1;
     const char* m = getenv("RNLA_MODE");
     if (m && (!strcmp(m, "literal") || !strcmp(m, "LITERAL") || !strcmp(m, "1"))) o->mode = RNLA_MODE_LITERAL;
 }

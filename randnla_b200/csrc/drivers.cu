@@ -182,8 +182,24 @@ static inline bool use_fused(const rnla_options& o, int64_t n, int l) {
     if (o.fused_sketch == 1) return true;
     return (double)n * l * 8.0 > 48.0 * 1024 * 1024;
 }
-static bool g_i8_deferred = false, g_i8_p7 = false;
+static bool g_i8_deferred = false;
+static I8Plan g_plan;          // how the current driver call spends the integer tensor cores (dev_qb1 / dev_rand_evd2 set it)
 static inline bool use_fused_forced(const rnla_options& o) { return o.fused_sketch == 1; }
+// rnla_options.range_passes_int8 -> which passes run on the integer tensor cores and at which precision:
+//   0  every pass in FP64 (DMMA)
+//   1  A Omega, A^T Y on 31-bit operands (10 digit pairs), A S with all 16 pairs; Q^T A in FP64        (spectrum-conditional)
+//   2  as 1, Q^T A on the 55-bit split                                                                 (spectrum-conditional)
+//   3  every pass FP64-grade: all four products on the 55-bit split (7 digit planes, 28 digit pairs)
+//  <0  auto (default): 3 where the shape is supported, else 0
+I8Plan i8_plan(const rnla_options& o, int64_t m_local, int64_t n, int l) {
+    I8Plan p;
+    int lvl = o.range_passes_int8 < 0 ? 3 : o.range_passes_int8;
+    if (lvl == 0 || lvl > 3 || o.mode != RNLA_MODE_INTENDED || use_fused_forced(o) || !i8_supported(m_local, n, l)) return p;
+    if (lvl == 1) { p.stored = 4; p.carry = 0; }
+    else if (lvl == 2) { p.stored = 7; p.carry = 7; }
+    else { p.stored = 7; p.early = 7; p.early_all = true; p.last = 7; p.last_all = true; p.carry = 7; }
+    return p;
+}
 static inline int eff_passes(const rnla_options& o, int dflt) { return o.num_passes > 0 ? o.num_passes : dflt; }
 static inline int eff_pps(const rnla_options& o) { return o.passes_per_stab > 0 ? o.passes_per_stab : 1; }
 
@@ -203,6 +219,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
         PhaseScope ph("tsog1:At_Omega");
         // S = A^T * Omega(m x l)                                                    lora_helpers.rs:74-76
         RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_M, m, l, sh.row_off, Ytmp, std::max<int64_t>(m, 1), c.stream));
+        i8_set_precision(g_plan.early, g_plan.early_all);
         RNLA_TRY(dev_gemm_tn(A, lda, m, n, Ytmp, std::max<int64_t>(m, 1), l, S, n, true));
         done = 1;
         if (done % pps == 0) RNLA_TRY(orth_inplace(S, n, nside, l, false, nullptr, nullptr, 1));
@@ -219,7 +236,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
                 bool split_ok = false;
                 if (g_i8_deferred) {
                     g_i8_deferred = false;
-                    split_ok = i8_prepare_begin(A, lda, m, n, g_i8_p7) == RNLA_OK;
+                    split_ok = i8_prepare_begin(A, lda, m, n, g_plan.stored) == RNLA_OK;
                     if (!split_ok) { cudaGetLastError(); i8_deactivate(); }
                     else c.block_landed_hook = [&split_ok](int64_t r0, int64_t rows) -> rnla_status {
                         if (split_ok && i8_prepare_rows(r0, rows) != RNLA_OK) { cudaGetLastError(); split_ok = false; }
@@ -229,11 +246,13 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
                 const rnla_status hst = hook(S, Ytmp, std::max<int64_t>(m, 1));
                 c.block_landed_hook = nullptr;
                 RNLA_TRY(hst);
-                if (split_ok) i8_prepare_end(); else i8_deactivate();
+                if (split_ok) RNLA_TRY(i8_prepare_end(&split_ok));
+                if (!split_ok) i8_deactivate();
             } else if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
                 RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
             } else {
                 if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n, c.stream));
+                i8_set_precision(g_plan.early, g_plan.early_all);
                 RNLA_TRY(dev_gemm_nn(A, lda, m, n, S, n, l, Ytmp, std::max<int64_t>(m, 1)));
             }
             virt = false;
@@ -242,6 +261,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
         if (done % pps == 0) { PhaseScope ph("stab:Y"); RNLA_TRY(orth_inplace(Ytmp, std::max<int64_t>(m, 1), sh, l, true, nullptr, nullptr, 1)); }
         {
             PhaseScope ph("pass:At*Y");
+            i8_set_precision(g_plan.early, g_plan.early_all);
             RNLA_TRY(dev_gemm_tn(A, lda, m, n, Ytmp, std::max<int64_t>(m, 1), l, S, n, true));
         }
         ++done;
@@ -285,9 +305,8 @@ rnla_status dev_rf1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
             RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Q, ldq));
         } else {
             if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S.d(), n, c.stream));
-            i8_set_precise(true);      // Y = A S is the product whose range becomes Q: all digit pairs (no-op on the FP64 path)
+            i8_set_precision(g_plan.last, g_plan.last_all);      // Y = A S is the product whose range becomes Q (no-op on the FP64 path)
             RNLA_TRY(dev_gemm_nn(A, lda, m, n, S.d(), n, l, Q, ldq));
-            i8_set_precise(false);
         }
     }
     PhaseScope ph("orth:Y");
@@ -297,26 +316,28 @@ rnla_status dev_rf1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
 // QB1: Q = RF1(A, l); Bt = A^T Q  (n x l; the reference's B = Q^T A is its transpose)   lora_helpers.rs:17-23
 rnla_status dev_qb1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,
                     const rnla_options& o, double* Q, int64_t ldq, double* Bt /* n x l, ld n */) {
-    // range_passes_int8: the passes that only have to span the subspace run on the integer tensor cores (i8gemm.cu); the pass
-    // below, whose result carries the singular values, always runs in FP64
-    const bool i8 = (o.range_passes_int8 == 1 || o.range_passes_int8 == 2) && o.mode == RNLA_MODE_INTENDED && !use_fused_forced(o) && i8_supported(sh.rows_local, n, l);
+    // rnla_options.range_passes_int8 (i8_plan): which passes over A run on the integer tensor cores, and at which precision
+    g_plan = i8_plan(o, sh.rows_local, n, l);
+    const bool i8 = g_plan.stored > 0;
     // host-buffer entry point: A is still arriving when the first pass runs (first_pass_hook); the split waits for that pass
     g_i8_deferred = i8 && (bool)ctx().first_pass_hook;
-    const bool all8 = i8 && o.range_passes_int8 == 2;     // 2: Q^T A too, on a 49-bit (7-digit) split
-    g_i8_p7 = all8;
-    if (i8 && !g_i8_deferred && i8_prepare(A, lda, sh.rows_local, n, all8) != RNLA_OK) {
-        // e.g. no room for the digit-plane workspace: the FP64 kernels need none
-        cudaGetLastError(); i8_deactivate();
+    if (i8 && !g_i8_deferred) {
+        bool usable = false;
+        if (i8_prepare(A, lda, sh.rows_local, n, g_plan.stored, &usable) != RNLA_OK || !usable) {
+            // no room for the digit-plane workspace, or A holds Inf / NaN / unscalable rows: the FP64 kernels need neither
+            cudaGetLastError(); i8_deactivate();
+        }
     }
     rnla_status st = dev_rf1(A, lda, sh, n, l, q, pps, o, Q, ldq);
     g_i8_deferred = false;
     if (st == RNLA_OK) {
-        if (!all8 || !i8_active_for(A, lda, sh.rows_local, n, l)) i8_deactivate(); else i8_set_full(true);
+        if (g_plan.carry == 0 || !i8_active_for(A, lda, sh.rows_local, n, l)) i8_deactivate(); else i8_set_precision(g_plan.carry, true);
         PhaseScope ph("pass:At*Q");
         st = dev_gemm_tn(A, lda, sh.rows_local, n, Q, ldq, l, Bt, n, true);
     }
     i8_deactivate();
     if (i8) i8_release();
+    g_plan = I8Plan();
     return st;
 }
 
@@ -458,37 +479,23 @@ rnla_status dev_rand_evd2(const double* A, int64_t lda, int64_t m_local, int64_t
     RNLA_CUDA(SY.alloc((size_t)l * l * 8)); RNLA_CUDA(Rinv.alloc((size_t)l * l * 8));
     RNLA_CUDA(Ur.alloc((size_t)l * l * 8)); RNLA_CUDA(Vr.alloc((size_t)l * l * 8)); RNLA_CUDA(sig.alloc((size_t)l * 8));
     RNLA_CUDA(flags.alloc((size_t)l * 4)); RNLA_CUDA(info.alloc(16)); RNLA_CUDA(scal.alloc(8)); RNLA_CUDA(scratch.alloc(1024 * 8));
-    // range_passes_int8 (single GPU, exactly symmetric A -- which PSD-ness presupposes; checked in one pass over A): the
-    // power-iteration products, which only have to span the range, run on the integer tensor cores from the 28-bit split of A;
-    // Y = A S carries the eigenvalues and needs FP64-grade accuracy: level 2 forms it as A^T S on the 49-bit split (the
-    // transposed kernel is the one that has it; A = A^T), level 1 falls back to the FP64 kernel for this one product
-    bool i8 = (o.range_passes_int8 == 1 || o.range_passes_int8 == 2) && o.mode == RNLA_MODE_INTENDED && c.nranks == 1 && m_local == n &&
-              i8_supported(n, n, l);
+    // rnla_options.range_passes_int8 (i8_plan): the power-iteration products on the integer tensor cores at the plan's `early`
+    // precision; Y = A S carries the eigenvalues: on the 55-bit split (levels 2, 3) or in FP64 (level 1)
+    g_plan = i8_plan(o, m_local, n, l);
+    bool i8 = g_plan.stored > 0;
     if (i8) {
-        DevBuf sflag;
-        RNLA_CUDA(sflag.alloc(4));
-        RNLA_CUDA(cudaMemsetAsync(sflag.p, 0, 4, c.stream));
-        RNLA_CUDA(check_symmetric(A, lda, n, sflag.as<int>(), c.stream));
-        int h = 0;
-        RNLA_CUDA(cudaMemcpyAsync(&h, sflag.p, 4, cudaMemcpyDeviceToHost, c.stream));
-        RNLA_TRY(sync_stream());
-        if (h) i8 = false;
+        bool usable = false;
+        if (i8_prepare(A, lda, m_local, n, g_plan.stored, &usable) != RNLA_OK || !usable) { cudaGetLastError(); i8_deactivate(); }
     }
-    const bool all8 = i8 && o.range_passes_int8 == 2;
-    if (i8 && i8_prepare(A, lda, n, n, all8) != RNLA_OK) { cudaGetLastError(); i8_deactivate(); i8 = false; }
     rnla_status st = dev_tsog1(A, lda, sh, n, l, q, pps, o, S.d());
     if (st == RNLA_OK) {
         PhaseScope ph("pass:A*S");
-        if (all8 && i8_active_for(A, lda, n, n, l)) {
-            i8_set_full(true);
-            st = dev_gemm_tn(A, lda, n, n, S.d(), n, l, Y.d(), mm, false);                  // Y = A^T S = A S on 49 bits
-        } else {
-            i8_deactivate();
-            st = dev_gemm_nn(A, lda, m_local, n, S.d(), n, l, Y.d(), mm);                  // Y = A S        :187
-        }
+        if (g_plan.carry && i8_active_for(A, lda, m_local, n, l)) i8_set_precision(g_plan.carry, true); else i8_deactivate();
+        st = dev_gemm_nn(A, lda, m_local, n, S.d(), n, l, Y.d(), mm);                      // Y = A S        :187
     }
     i8_deactivate();
     if (i8) i8_release();
+    g_plan = I8Plan();
     RNLA_TRY(st);
     double nu;
     {

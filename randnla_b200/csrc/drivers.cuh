@@ -98,20 +98,31 @@ rnla_status dev_saddle_point(const double* A, int64_t lda, int64_t m, int64_t n,
                              double epsilon, int64_t maxit, double sampling_factor, int dist, uint64_t seed, double* x, double* y,
                              int64_t* iters_out, int32_t* converged_out);
 
-// i8gemm.cu: range-finder passes on the INT8 tensor cores (tcgen05 kind::i8), opt-in through rnla_options.range_passes_int8
+// i8gemm.cu: the passes over A on the INT8 tensor cores (tcgen05 kind::i8), rnla_options.range_passes_int8
 bool i8_supported(int64_t m, int64_t n, int l);
 bool i8_active_for(const double* A, int64_t lda, int64_t m, int64_t n, int64_t N);
 void i8_deactivate();
-void i8_set_precise(bool on);
+// precision of the products that follow: 4 digit planes (31-bit operands; all_pairs adds the sweep over groups 4..6),
+// 6 (47-bit) or 7 (55-bit, FP64-grade)
+void i8_set_precision(int planes, bool all_pairs);
 void i8_release();
+void i8_debug_flush(int stages);
 void i8_free_workspace();
-rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, bool p7 = false);
-rnla_status i8_prepare_begin(const double* A, int64_t lda, int64_t m, int64_t n, bool p7);
+// usable = false: A holds Inf / NaN or rows too small to scale -> the caller keeps the FP64 kernels
+rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, int planes, bool* usable);
+rnla_status i8_prepare_begin(const double* A, int64_t lda, int64_t m, int64_t n, int planes);
 rnla_status i8_prepare_rows(int64_t r0, int64_t count, bool phases = false);
-void i8_prepare_end();
-void i8_set_full(bool on);
+rnla_status i8_prepare_end(bool* usable);
 rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc);
 rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz);
+// how a driver spends the integer tensor cores (resolved from rnla_options.range_passes_int8 and the shape)
+struct I8Plan {
+    int stored = 0;                       // digit planes of the split of A (0: FP64 kernels everywhere)
+    int early = 4; bool early_all = false;  // A Omega, A^T Y: products that shape the sketch
+    int last = 4;  bool last_all = true;    // the last A S, whose range becomes Q
+    int carry = 0;                        // the product that carries the values (Q^T A, Nystrom Y = A S): planes, 0 = FP64
+};
+I8Plan i8_plan(const rnla_options& o, int64_t m_local, int64_t n, int l);
 
 // literal.cu: bug-compatible pieces of the reference
 rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,

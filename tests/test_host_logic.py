@@ -154,74 +154,84 @@ def test_row_sharded_dataflow_matches_single_process_oracle(tmp_path, orc, q):
     assert (np.abs(sig - np.diag(S)) / np.diag(S)).max() < 1e-10
 
 
-# ---- the fixed-point split behind the INT8 tensor-core passes (randnla_b200/csrc/i8gemm.cu: digits4 / digits7 / scales_from_max_bits) ----
-def _scales(rowmax):
-    """2^(e+1) and 2^(27-e) with rowmax < 2^e, from the exponent field of the maximum (scales_from_max_bits)"""
-    E = (np.float64(rowmax).view(np.uint64) >> np.uint64(52)) & np.uint64(0x7ff)
-    E = int(E)
-    if E < 64 or E >= 2045:
-        return 0.0, 0.0
-    return float(np.ldexp(1.0, E + 2 - 1023)), float(np.ldexp(1.0, 2072 - E - 1023))
-
-
-def _digits(x, down, seven):
-    """numpy restatement of digits4 / digits7: balanced 7-bit digits, most significant first"""
-    y = x * down
-    vh = int(np.rint(y))
-    vl = int(np.rint((y - vh) * 2097152.0)) if seven else 0
-    vh = max(-(1 << 27) + 1, min((1 << 27) - 1, vh))
-    d = [0] * (7 if seven else 4)
-    if seven:
-        d[6] = ((vl + 64) & 127) - 64; vl = (vl - d[6]) >> 7
-        d[5] = ((vl + 64) & 127) - 64; vl = (vl - d[5]) >> 7
-        d[4] = vl
-    d[3] = ((vh + 64) & 127) - 64; vh = (vh - d[3]) >> 7
-    d[2] = ((vh + 64) & 127) - 64; vh = (vh - d[2]) >> 7
-    d[1] = ((vh + 64) & 127) - 64; vh = (vh - d[1]) >> 7
-    d[0] = vh
-    return d
-
-
+# ---- the fixed-point split behind the INT8 tensor-core passes (randnla_b200/csrc/i8gemm.cu), emulated in tests/i8_emulation.py ----
 def test_int8_digit_split_is_exact_bounded_and_accumulates_in_int32():
-    """every digit fits int8 with |d| <= 64 (so 4 pairs x 64^2 x 131072 and 7 pairs x 64^2 x 65536 stay below 2^31), the digits
-    reproduce the rounded fixed-point value exactly, and the representation error is 2^-28 (4 digits) / 2^-49 (7 digits) of the
-    row scale; the weights are the ones the epilogues use: x = up * sum_t d_t 2^{-7(t+1)}"""
+    """digits<P> of i8gemm.cu: plane 0 holds 7 bits (|d_0| <= 64), the others balanced 8-bit digits in [-128, 127] (int8 without
+    slack, hence the carry out of the trailing part); the digits reproduce the rounded fixed-point value exactly; the
+    representation error is 2^-(8P) of the row scale `up`; and every digit-pair group of every sweep stays below 2^31 over the
+    stages between two drains of the accumulators (FLUSH_P*)."""
+    from fractions import Fraction
+    import i8_emulation as em
     rng = np.random.default_rng(0)
     for scale in (1.0, 3e-7, 9.1e11):
         row = rng.standard_normal(4000) * scale
-        row[:4] = [np.abs(row).max() * (1 - 2 ** -52), -np.abs(row).max(), 0.0, scale * 2 ** -60]
-        up, down = _scales(np.abs(row).max())
-        assert up > np.abs(row).max() and up <= 4 * np.abs(row).max()
-        for seven in (False, True):
-            worst = 0.0
-            for x in row[:600]:
-                d = _digits(float(x), down, seven)
-                assert all(-64 <= t <= 64 for t in d)
-                rec = up * sum(t * 2.0 ** (-7 * (i + 1)) for i, t in enumerate(d))
-                worst = max(worst, abs(rec - x) / up)
-            assert worst <= (2.0 ** -49 if seven else 2.0 ** -28) * 0.51
-    assert 4 * 64 * 64 * 131072 <= 2 ** 31 and 7 * 64 * 64 * 65536 < 2 ** 31
-    assert _scales(0.0) == (0.0, 0.0) and _scales(1e-300) == (0.0, 0.0)
+        mx = np.abs(row).max()
+        row[:4] = [mx * (1 - 2 ** -52), -mx, 0.0, scale * 2 ** -60]
+        up, down = em.scales(np.array([mx]))
+        up, down = float(up[0]), float(down[0])
+        assert mx < up / 2 <= 2 * mx and up * down == 2.0 ** 31
+        # entries whose scaled value sits exactly half-way between two integers: the trailing part rounds to +-2^(8(P-4)-1), whose
+        # top digit would be +128 without the carry
+        row[4:8] = [(12345 + 0.5) / down, -(777 + 0.5) / down, 0.5 / down, (2 ** 29 - 0.5) / down]
+        for P in (4, 6, 7):
+            pl = em.planes(row[:600], down, P)
+            assert np.abs(pl[0]).max() <= 64
+            for t in range(1, P):
+                assert pl[t].min() >= -128 and pl[t].max() <= 127
+            for i in range(600):
+                v = sum(int(pl[t][i]) << (8 * (P - 1 - t)) for t in range(P))              # exact integer value of the digits
+                exact = Fraction(float(row[i])) * Fraction(2) ** (8 * P - 1) / Fraction(up)
+                assert abs(Fraction(v) - exact) <= Fraction(1, 2)
+    bound = lambda t: 64 if t == 0 else 128
+    for P, all_pairs in ((4, False), (4, True), (6, True), (7, True)):
+        for pu, g0, ng in em.sweeps(P, all_pairs):
+            for g in range(g0, g0 + ng):
+                per_index = sum(bound(ta) * bound(tb) for ta, tb in em.pairs(pu, g0, ng) if ta + tb == g)
+                assert per_index * 64 * em.FLUSH_STAGES[pu] < 2 ** 31
+    assert [len(em.pairs(pu, g0, ng)) for pu, g0, ng in em.sweeps(7, True)] == [10, 18]
+    assert [len(em.pairs(pu, g0, ng)) for pu, g0, ng in em.sweeps(6, True)] == [10, 11]
+    assert [len(em.pairs(pu, g0, ng)) for pu, g0, ng in em.sweeps(4, True)] == [10, 6]
+    u0, d0 = em.scales(np.array([0.0, 1e-300, np.inf]))
+    assert not u0.any() and not d0.any()
 
 
-def test_int8_digit_pair_groups_cover_the_product():
-    """sum over digit pairs grouped by g = ta + tb with weight 2^{-7(g+2)} is the product of the two representations: 10 pairs
-    (g <= 3) for a range-finder pass, 16 for A S, 28 of the 49 pairs (g <= 6) for Q^T A -- and the dropped groups are below
-    2^-25 / 2^-46 of the scales"""
+def test_int8_products_reach_their_stated_accuracy():
+    """emulated products (same digits, same pair groups, exact integer accumulation) against numpy: 4 planes / 10 pairs 2^-27,
+    all 16 pairs 2^-30, 6 planes 2^-43, 7 planes 2^-50.5 (numpy's own FP64 product is no better) -- relative to (row max) x
+    (column max) x sqrt(K); the scales `up` are 2 to 4 times the maxima, which is where the bits below 31 / 47 / 55 go"""
+    import i8_emulation as em
     rng = np.random.default_rng(1)
-    a = rng.standard_normal(64); b = rng.standard_normal(64)
-    ua, da = _scales(np.abs(a).max()); ub, db = _scales(np.abs(b).max())
-    for seven, gmax, tol in ((False, 3, 2.0 ** -24), (False, 6, 2.0 ** -27), (True, 6, 2.0 ** -45)):
-        A = np.array([_digits(float(x), da, seven) for x in a]); B = np.array([_digits(float(x), db, seven) for x in b])
-        nd = A.shape[1]
-        acc = {}
-        for ta in range(nd):
-            for tb in range(nd):
-                if ta + tb <= gmax:
-                    acc[ta + tb] = acc.get(ta + tb, 0) + int(A[:, ta] @ B[:, tb])          # exact integer accumulation
-        got = ua * ub * sum(v * 2.0 ** (-7 * (g + 2)) for g, v in acc.items())
-        assert abs(got - a @ b) <= tol * ua * ub * len(a)
-        assert len([1 for ta in range(nd) for tb in range(nd) if ta + tb <= gmax]) == {(False, 3): 10, (False, 6): 16, (True, 6): 28}[(seven, gmax)]
+    A = rng.standard_normal((300, 500)) * np.logspace(-6, 6, 300)[:, None]
+    B = rng.standard_normal((500, 24)); Q = rng.standard_normal((300, 24))
+    for P, all_pairs, tol in ((4, False, 2.0 ** -25), (4, True, 2.0 ** -28), (6, True, 2.0 ** -41), (7, True, 2.0 ** -49)):
+        C = em.i8_nn(A, B, P, all_pairs)
+        bound = np.abs(A).max(axis=1)[:, None] * np.abs(B).max(axis=0)[None, :] * np.sqrt(A.shape[1])
+        assert (np.abs(C - A @ B) / bound).max() < tol
+        Z = em.i8_tn(A, Q, P, all_pairs)
+        bound = (np.abs(A).max(axis=1)[:, None] * np.abs(Q)).max(axis=0)[None, :] * np.sqrt(A.shape[0])
+        assert (np.abs(Z - A.T @ Q) / bound).max() < tol
+
+
+@pytest.mark.parametrize("kappa", [1e2, 1e4, 1e6])
+def test_int8_accuracy_contract_on_the_emulated_sweep(kappa):
+    """The accuracy contract of rnla_options.range_passes_int8 (include/rnla.h), on the CPU emulation with the same
+    Omega as the all-FP64 run: level 3 (every pass on the 55-bit split; what `auto` selects) reproduces the FP64 singular values to
+    the north_star tolerance whatever the tail of the spectrum does; levels 1 and 2 (31-bit range passes) only when the part of A
+    outside the captured range is small -- with a flat tail at sigma_k they are off by far more than 1e-10, which is why `auto`
+    never selects them."""
+    import i8_emulation as em
+    m, n, k, s = 1500, 600, 20, 8
+    Om = np.random.default_rng(1).standard_normal((n, k + s))
+    for gap in (1e-2, 1.0, None):
+        A, sig = em.spectrum_matrix(m, n, k, kappa, gap)
+        s0 = em.rand_svd_emulated(A, Om, k, 0)
+        d3 = np.max(np.abs(em.rand_svd_emulated(A, Om, k, 3) - s0) / s0)
+        assert d3 < 1e-10, (kappa, gap, d3)
+        d2 = np.max(np.abs(em.rand_svd_emulated(A, Om, k, 2) - s0) / s0)
+        if gap == 1e-2 and kappa <= 1e4:
+            assert d2 < 1e-10, (kappa, gap, d2)
+        if gap == 1.0:
+            assert d2 > 1e-10, (kappa, gap, d2)
 
 
 def test_bench_reference_arm_prints_its_json_line():
