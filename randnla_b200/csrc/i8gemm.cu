@@ -16,9 +16,10 @@
 // both passes: a stage of A^T Y is one contiguous 8 KB bulk copy per plane, a stage of A S eight 1 KB copies per plane.
 //
 // TMEM holds four 128-column int32 accumulators, so a product is at most two sweeps over the images:
-//   LO  planes 0..3 of both operands, groups g = 0..3 (10 pairs)                       -> 31-bit operands, result to ~2^-29
-//   HI4 planes 0..3, g = 4..6 (6 pairs)     HI6 planes 0..5, g = 4, 5 (11 pairs)      HI7 planes 0..6, g = 4..6 (18 pairs)
-// LO + HI7 is the product of the 55-bit representations up to 2^-54 of (row max) x (column max): FP64-grade.
+//   4 planes: groups 0..3 (10 pairs; 31-bit operands, result to ~2^-27), optionally groups 4..6 (6 pairs)
+//   6 planes: groups 0..3 on planes 0..3 + groups 4, 5 on planes 0..5 (11 pairs)
+//   7 planes: groups 0..2 on planes 0..2 (6 pairs) + groups 3..6 on all seven planes (22 pairs): the product of the 55-bit
+//             representations up to 2^-54 of (row max) x (column max): FP64-grade.
 // Accumulation bound: the largest group (g = 6: 2 x 64*128 + 5 x 128^2 per index) stays below 2^31 for 21845 contraction indices;
 // the kernels drain the accumulators into the FP64 output every `flush` stages, so n and m are unlimited.
 #include "drivers.cuh"
@@ -36,7 +37,7 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 64;   // CTA tile: 128 x (<= 128) outputs, 64 contraction indices per stage
 constexpr int APLANE = 16384;                // one digit plane of a 128 x 128 block of A
 constexpr int ASTAGE = 8192;                 // one digit plane of a stage (128 x 64)
-constexpr int MMA_THREADS = 192;             // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int MMA_THREADS = 224;             // warp 0 A producer, warp 1 MMA issuer, warps 2-5 epilogue, warp 6 B producer
 // stages of 64 contraction indices per int32 accumulation (worst group of the sweep, |d_0| <= 64, |d_t| <= 128)
 constexpr int FLUSH_P4 = 682, FLUSH_P6 = 408, FLUSH_P7 = 340;
 
@@ -233,17 +234,18 @@ colmax_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, const
         atomicMax(bits + c, (unsigned long long)__double_as_longlong(mx));
     }
 }
-// thin-operand images: [k block of 64][plane P][k group 8][n block nb][8 x 16 B]; columns >= N and rows >= K are zero
+// thin-operand images: [k block of 32][k group 4][plane P][n block nb][8 x 16 B]; columns >= N and rows >= K are zero.  The planes of a
+// k group are adjacent so that ONE MMA of width 2 x 16 nb can multiply a plane of A by two neighbouring planes tb, tb + 1 at once.
 template <int P>
 __global__ void __launch_bounds__(256)
 slice_b_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int nb, const double* __restrict__ rs, const double* __restrict__ cdown,
                uint8_t* __restrict__ out) {
-    const int64_t kb = blockIdx.x;
+    const int64_t kb = blockIdx.x;                          // 64 contraction indices = two image blocks
     const int kl = threadIdx.x & 63;
     const int64_t k = kb * 64 + kl;
     const double rsk = (k < K) ? (rs ? rs[k] : 1.0) : 0.0;
-    const int plane = nb * 1024;
-    uint8_t* dst = out + kb * (int64_t)(P * plane);
+    const int plane = nb * 128;                             // one plane of one k group
+    uint8_t* dst = out + (kb * 2 + (kl >> 5)) * (int64_t)(P * nb * 512);
     for (int cq = threadIdx.x >> 6; cq < 4 * nb; cq += 4) {
         const int c0 = 4 * cq;
         unsigned w[P];
@@ -259,7 +261,7 @@ slice_b_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int 
 #pragma unroll
             for (int t = 0; t < P; ++t) w[t] |= ((unsigned)d[t] & 0xffu) << (8 * e);
         }
-        const int intra = (kl >> 3) * (nb * 128) + (c0 >> 4) * 128 + (kl & 7) * 16 + (c0 & 15);
+        const int intra = ((kl & 31) >> 3) * (P * plane) + (c0 >> 4) * 128 + (kl & 7) * 16 + (c0 & 15);
 #pragma unroll
         for (int t = 0; t < P; ++t) *reinterpret_cast<unsigned*>(dst + t * plane + intra) = w[t];
     }
@@ -271,19 +273,68 @@ slice_b_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int 
 // TN = true :  P[chunk](cols tile*128.., :) (+)= 2^{-(14+8 G0)} sum_g ...,                          contraction over this chunk's blocks of 64 rows
 // ADD: the sweep adds to what an earlier sweep of the same product wrote.  Every `flush` stages the accumulators are drained into
 // the output (the first drain stores unless ADD), which keeps the int32 sums exact for any contraction length.
+//
+// Two decoupled shared-memory rings.  The planes of A come from HBM: what hides its latency is bytes in flight, so A gets a deep ring
+// of `na` stages of 64 contraction indices (PU x 8 KB each).  The thin operand comes from L2 and is as large per stage as A (l ~ 128):
+// it gets a shallow ring of `nbs` half-stages of 32 indices, so that it costs 2-3 x PU x nb x 512 B of shared memory instead of
+// doubling every stage of A.  Warp 0 feeds the A ring, warp 6 the B ring, one lane of warp 1 issues the MMAs, warps 2-5 drain TMEM.
+constexpr int MAX_RING = 16;
+// The MMAs of one K step of a sweep, decided at compile time: for every plane ta of A the planes tb of the thin operand whose group
+// g = ta + tb the sweep owns; neighbouring planes tb, tb + 1 go into ONE MMA of double width (accumulators g and g + 1 are
+// neighbours in TMEM) whenever both accumulators are in the same state (both already written in this accumulation, or both not):
+// A is then read from shared memory 6 instead of 10 times per K step in the LO sweep, 12 instead of 18 times in HI7.
+// FRESH: the first K step of an accumulation, where the first MMA into an accumulator overwrites it.
+template <int PU, int G0, int NG, bool FRESH>
+struct Sched {
+    int n = 0;
+    int ta[32], tb[32], wide[32], acc[32];
+    constexpr Sched() : ta{}, tb{}, wide{}, acc{} {
+        unsigned touched = FRESH ? 0u : 0xffu;
+        for (int a = 0; a < PU; ++a)
+            for (int b = 0; b < PU; ++b) {
+                const int g = a + b;
+                if (g < G0 || g >= G0 + NG) continue;
+                const unsigned m1 = 1u << (g - G0), m2 = 3u << (g - G0);
+                const bool can2 = b + 1 < PU && g + 1 < G0 + NG && ((touched & m2) == 0u || (touched & m2) == m2);
+                const unsigned mk = can2 ? m2 : m1;
+                ta[n] = a; tb[n] = b; wide[n] = can2 ? 1 : 0; acc[n] = (touched & mk) ? 1 : 0;
+                touched |= mk;
+                ++n;
+                if (can2) ++b;
+            }
+    }
+};
+template <bool TN, class S>
+__device__ __forceinline__ void issue_kstep(uint32_t tmem, uint32_t a_base, uint32_t b_base, int ks, int nb, int pu, int g0, uint32_t idesc1,
+                                            uint32_t idesc2) {
+    constexpr S sc{};
+    const uint32_t aw = (uint32_t)nb * 16;                      // TMEM columns per accumulator
+#pragma unroll
+    for (int i = 0; i < sc.n; ++i) {
+        // A S:   MN-major, stage plane [I 8][J 8][128 B]:  32 columns = 4 J = 512 B;  K stride (J) 128, M stride (I) 1024
+        // A^T Y: K-major,  stage plane [I 4][J 16][128 B]: 32 rows = 2 I = 4096 B;   K stride (I) 2048, M stride (J) 128
+        const uint64_t ad = TN ? smem_desc(a_base + sc.ta[i] * ASTAGE + ks * 4096, 2048, 128)
+                               : smem_desc(a_base + sc.ta[i] * ASTAGE + ks * 512, 128, 1024);
+        // thin operand: MN-major, half-stage [k group 4][plane PU][n block nb][128 B]: planes tb, tb + 1 are adjacent along N
+        const uint64_t bd = smem_desc(b_base + sc.tb[i] * nb * 128, pu * nb * 128, 128);
+        tc_mma_i8(tmem + (uint32_t)(sc.ta[i] + sc.tb[i] - g0) * aw, ad, bd, sc.wide[i] ? idesc2 : idesc1, (uint32_t)sc.acc[i]);
+    }
+}
 template <bool TN, int PU, int G0, int NG, bool ADD>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
-i8_mma_kernel(const uint8_t* __restrict__ Aimg, int pst, int64_t cblocks, const uint8_t* __restrict__ Bimg, int pb, int nb,
+i8_mma_kernel(const uint8_t* __restrict__ Aimg, int pst, int64_t cblocks, const uint8_t* __restrict__ Bimg, int pb, int nb, int na, int nbs,
               int64_t kblocks_total, int64_t kblocks_per_chunk, int flush, double* __restrict__ C, int64_t ldc, int64_t rows, int ncols,
               const double* __restrict__ rs_up, const double* __restrict__ cs_up, int64_t chunk_stride) {
-    constexpr int STAGES = PU <= 4 ? 3 : 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int bplane = nb * 1024;
-    const uint32_t a_bytes = PU * ASTAGE, b_bytes = (uint32_t)(PU * bplane), stage = a_bytes + b_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage);
-    uint64_t* empty = full + STAGES;
-    uint64_t* accum = empty + STAGES;
+    const int bplane = nb * 512;                               // one plane of a half-stage of the thin operand
+    const uint32_t a_bytes = PU * ASTAGE, b_bytes = (uint32_t)(PU * bplane);
+    uint8_t* bring = smem + (size_t)na * a_bytes;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(bring + (size_t)nbs * b_bytes);
+    uint64_t* emptyA = fullA + MAX_RING;
+    uint64_t* fullB = emptyA + MAX_RING;
+    uint64_t* emptyB = fullB + 4;
+    uint64_t* accum = emptyB + 4;
     uint64_t* drained = accum + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -294,7 +345,8 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int pst, int64_t cblocks, const 
     const int nflush = (nk + flush - 1) / flush;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < na; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); }
+        for (int s = 0; s < nbs; ++s) { mbar_init(fullB + s, 1); mbar_init(emptyB + s, 1); }
         mbar_init(accum, 1);
         mbar_init(drained, 4);
         mbar_fence_init();
@@ -306,62 +358,70 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int pst, int64_t cblocks, const 
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
+        int s = 0; uint32_t ph = 1;                            // parity of the `empty` phase to wait for: the first lap passes at once
         for (int it = 0; it < nk; ++it) {
-            const int s = it % STAGES;
-            if (it >= STAGES) mbar_wait(empty + s, ((it / STAGES) - 1) & 1);
+            mbar_wait(emptyA + s, ph);
             const int64_t kb = kb0 + it, blk2 = kb >> 1;
             const int h = (int)(kb & 1);
-            uint8_t* st = smem + (size_t)s * stage;
-            if (lane == 0) mbar_arrive_expect_tx(full + s, stage);
+            uint8_t* st = smem + (size_t)s * a_bytes;
+            if (lane == 0) mbar_arrive_expect_tx(fullA + s, a_bytes);
             __syncwarp();
             if (TN) {
                 // stage = 128 columns (tile) x 64 rows (half h of row block blk2): [I 4][J 16][128 B] = 8 KB contiguous per plane
                 const uint8_t* src = Aimg + ((blk2 * cblocks + tile) * pst) * (int64_t)APLANE + h * ASTAGE;
-                if (lane < PU) bulk_g2s(st + lane * ASTAGE, src + (int64_t)lane * APLANE, ASTAGE, full + s);
+                if (lane < PU) bulk_g2s(st + lane * ASTAGE, src + (int64_t)lane * APLANE, ASTAGE, fullA + s);
             } else {
                 // stage = 128 rows (tile) x 64 columns (half h of column block blk2): per plane and 16-row group I one 1 KB run
                 const uint8_t* src = Aimg + ((tile * cblocks + blk2) * pst) * (int64_t)APLANE + h * 1024;
                 for (int q = lane; q < PU * 8; q += 32)
-                    bulk_g2s(st + (q >> 3) * ASTAGE + (q & 7) * 1024, src + (int64_t)(q >> 3) * APLANE + (q & 7) * 2048, 1024, full + s);
+                    bulk_g2s(st + (q >> 3) * ASTAGE + (q & 7) * 1024, src + (int64_t)(q >> 3) * APLANE + (q & 7) * 2048, 1024, fullA + s);
             }
-            if (lane == 31) bulk_g2s(st + a_bytes, Bimg + kb * (int64_t)(pb * bplane), b_bytes, full + s);
+            if (++s == na) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 1;
+            const uint8_t* src = Bimg + 2 * kb0 * (int64_t)(pb * bplane);
+            for (int j = 0; j < 2 * nk; ++j) {
+                mbar_wait(emptyB + s, ph);
+                mbar_arrive_expect_tx(fullB + s, b_bytes);
+                uint8_t* dst = bring + (size_t)s * b_bytes;
+                const uint8_t* blk = src + (int64_t)j * (pb * bplane);
+                if (pb == PU) bulk_g2s(dst, blk, b_bytes, fullB + s);
+                else                                            // the leading PU planes of each of the four k groups
+                    for (int kg = 0; kg < 4; ++kg) bulk_g2s(dst + kg * (PU * nb * 128), blk + kg * (pb * nb * 128), PU * nb * 128, fullB + s);
+                if (++s == nbs) { s = 0; ph ^= 1; }
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = instr_desc(!TN, true, nb * 16);
+            const uint32_t idesc1 = instr_desc(!TN, true, nb * 16), idesc2 = instr_desc(!TN, true, 2 * nb * 16);
+            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+            int since = 0, drains = 0;                          // stages since the last drain of the accumulators
             for (int it = 0; it < nk; ++it) {
-                const int s = it % STAGES;
-                const bool fresh = (it % flush) == 0;           // first stage of an accumulation: overwrite the accumulators
+                const bool fresh = since == 0;                  // first stage of an accumulation: overwrite the accumulators
                 if (fresh && it > 0) {
                     tc_commit(accum);                           // everything issued so far -> the epilogue warps drain
-                    mbar_wait(drained, ((it / flush) - 1) & 1);
+                    mbar_wait(drained, drains & 1);
+                    ++drains;
                     tc_fence_after();
                 }
-                mbar_wait(full + s, (it / STAGES) & 1);
+                if (++since == flush) since = 0;
+                mbar_wait(fullA + sa, pha);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(smem + (size_t)s * stage);
-                const uint32_t b_base = a_base + a_bytes;
+                const uint32_t a_base = smem_u32(smem + (size_t)sa * a_bytes);
 #pragma unroll
                 for (int ks = 0; ks < BK / 32; ++ks) {
-#pragma unroll
-                    for (int ta = 0; ta < PU; ++ta) {
-#pragma unroll
-                        for (int tb = 0; tb < PU; ++tb) {
-                            const int g = ta + tb;
-                            if (g < G0 || g >= G0 + NG) continue;
-                            // A S:   MN-major, stage plane [I 8][J 8][128 B]:  32 columns = 4 J = 512 B;  K stride (J) 128, M stride (I) 1024
-                            // A^T Y: K-major,  stage plane [I 4][J 16][128 B]: 32 rows = 2 I = 4096 B;   K stride (I) 2048, M stride (J) 128
-                            const uint64_t ad = TN ? smem_desc(a_base + ta * ASTAGE + ks * 4096, 2048, 128)
-                                                   : smem_desc(a_base + ta * ASTAGE + ks * 512, 128, 1024);
-                            // thin operand: MN-major, plane [k group 8][n block nb][128 B]: 32 k = 4 groups
-                            const uint64_t bd = smem_desc(b_base + tb * bplane + ks * 4 * nb * 128, nb * 128, 128);
-                            const int ta_first = g > PU - 1 ? g - (PU - 1) : 0;                // first pair of group g in this loop order
-                            const uint32_t acc = (!fresh || ks > 0 || ta > ta_first) ? 1u : 0u;
-                            tc_mma_i8(tmem + (uint32_t)(g - G0) * BN, ad, bd, idesc, acc);
-                        }
-                    }
+                    mbar_wait(fullB + sb, phb);
+                    tc_fence_after();
+                    const uint32_t b_base = smem_u32(bring + (size_t)sb * b_bytes);
+                    if (fresh && ks == 0) issue_kstep<TN, Sched<PU, G0, NG, true>>(tmem, a_base, b_base, ks, nb, PU, G0, idesc1, idesc2);
+                    else issue_kstep<TN, Sched<PU, G0, NG, false>>(tmem, a_base, b_base, ks, nb, PU, G0, idesc1, idesc2);
+                    tc_commit(emptyB + sb);
+                    if (++sb == nbs) { sb = 0; phb ^= 1; }
                 }
-                tc_commit(empty + s);
+                tc_commit(emptyA + sa);
+                if (++sa == na) { sa = 0; pha ^= 1; }
             }
             tc_commit(accum);
         }
@@ -377,7 +437,7 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int pst, int64_t cblocks, const 
             for (int c0 = 0; c0 < ncols; c0 += 16) {
                 uint32_t d[NG][16];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * BN + c0), d[g]);
+                for (int g = 0; g < NG; ++g) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * nb * 16 + c0), d[g]);
                 tc_wait_ld();
                 if (r < rows) {
 #pragma unroll
@@ -387,7 +447,7 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int pst, int64_t cblocks, const 
                             double v = (double)(int)d[NG - 1][e];
 #pragma unroll
                             for (int g = NG - 2; g >= 0; --g) v = v * 0.00390625 + (double)(int)d[g][e];
-                            v *= G0 == 0 ? 6.103515625e-05 : 1.4210854715202004e-14;           // 2^-14, 2^-46 (G0 = 4)
+                            v *= 1.0 / (double)(1ull << (14 + 8 * G0));                         // 2^-(14 + 8 G0): weight of the sweep's first group
                             if (!TN) v *= rsc * cs_up[c];
                             double* o = out + r + (int64_t)c * ldc;
                             if (ADD || f > 0) *o += v; else *o = v;
@@ -451,7 +511,7 @@ void launch_slice_b(const double* X, int64_t ldx, int64_t K, int N, int nb, cons
 }
 rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, int nb, const double* rs, int64_t kblocks, int planes) {
     Ctx& c = ctx();
-    RNLA_CUDA(g_sl.bimg.ensure((size_t)kblocks * planes * nb * 1024));
+    RNLA_CUDA(g_sl.bimg.ensure((size_t)kblocks * planes * nb * 1024));      // kblocks blocks of 64 = 2 kblocks image blocks of 32
     RNLA_CUDA(cudaMemsetAsync(g_sl.cbits.p, 0, 128 * 8, c.stream));
     const int64_t rows_per = 32768;
     colmax_kernel<<<dim3((unsigned)N, (unsigned)((K + rows_per - 1) / rows_per)), 256, 0, c.stream>>>(X, ldx, K, N, rs, rows_per,
@@ -465,21 +525,37 @@ rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, int nb, cons
     return RNLA_OK;
 }
 
-inline size_t mma_smem(int pu, int nb) { return (size_t)(pu <= 4 ? 3 : 2) * pu * (ASTAGE + nb * 1024) + 1024 + 256; }
+// ring sizes: the thin operand gets `nbs` half-stages (3 when the A ring still gets at least 3 stages, else 2), A the rest of the
+// 227 KB of dynamic shared memory
+constexpr size_t SMEM_MAX = 232448, SMEM_FIXED = 1024 + 1024;      // alignment slack + barriers
+inline void mma_rings(int pu, int nb, int* na, int* nbs) {
+    const size_t a = (size_t)pu * ASTAGE, b = (size_t)pu * nb * 512;
+    int s = 3;
+    if ((SMEM_MAX - SMEM_FIXED - 3 * b) / a < 3) s = 2;
+    *nbs = s;
+    *na = (int)std::min<size_t>(MAX_RING, (SMEM_MAX - SMEM_FIXED - s * b) / a);
+}
+inline size_t mma_smem(int pu, int nb) {
+    int na, nbs;
+    mma_rings(pu, nb, &na, &nbs);
+    return (size_t)na * pu * ASTAGE + (size_t)nbs * pu * nb * 512 + SMEM_FIXED;
+}
 
 template <bool TN, int PU, int G0, int NG, bool ADD>
 rnla_status launch_mma(dim3 grid, int nb, int64_t kblocks_total, int64_t per, int flush, double* C, int64_t ldc, int64_t rows, int ncols,
                        const double* rs_up, int64_t chunk_stride) {
     Ctx& c = ctx();
     Sliced& s = g_sl;
-    static int attr_nb = 0;                                  // largest dynamic shared memory size this instance was configured for
-    if (nb > attr_nb) {
-        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<TN, PU, G0, NG, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem(PU, nb)));
-        attr_nb = nb;
+    static bool attr = false;
+    if (!attr) {
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<TN, PU, G0, NG, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        attr = true;
     }
+    int na, nbs;
+    mma_rings(PU, nb, &na, &nbs);
     i8_mma_kernel<TN, PU, G0, NG, ADD><<<grid, MMA_THREADS, mma_smem(PU, nb), c.stream>>>(
-        s.img.as<uint8_t>(), s.planes, s.cblocks, s.bimg.as<uint8_t>(), g_planes, nb, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up,
-        s.cup.d(), chunk_stride);
+        s.img.as<uint8_t>(), s.planes, s.cblocks, s.bimg.as<uint8_t>(), g_planes, nb, na, nbs, kblocks_total, per, flush, C, ldc, rows, ncols,
+        rs_up, s.cup.d(), chunk_stride);
     ++g_kernel_launches;
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;
@@ -490,8 +566,13 @@ rnla_status run_sweeps(dim3 grid, int nb, int64_t kblocks_total, int64_t per, do
                        const double* rs_up, int64_t chunk_stride) {
     const int f4 = g_flush_override ? g_flush_override : FLUSH_P4, f6 = g_flush_override ? g_flush_override : FLUSH_P6,
               f7 = g_flush_override ? g_flush_override : FLUSH_P7;
+    if (g_planes == 7) {
+        // 28 pairs: groups 0..2 need planes 0..2 only (6 pairs), groups 3..6 all seven (22 pairs): 3 + 7 planes of each operand enter
+        // the SMs per product instead of 4 + 7 -- the kernels are bound by the L2 -> SM traffic
+        RNLA_TRY((launch_mma<TN, 3, 0, 3, false>(grid, nb, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
+        return launch_mma<TN, 7, 3, 4, true>(grid, nb, kblocks_total, per, f7, C, ldc, rows, ncols, rs_up, chunk_stride);
+    }
     RNLA_TRY((launch_mma<TN, 4, 0, 4, false>(grid, nb, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
-    if (g_planes == 7) return launch_mma<TN, 7, 4, 3, true>(grid, nb, kblocks_total, per, f7, C, ldc, rows, ncols, rs_up, chunk_stride);
     if (g_planes == 6) return launch_mma<TN, 6, 4, 2, true>(grid, nb, kblocks_total, per, f6, C, ldc, rows, ncols, rs_up, chunk_stride);
     if (g_all_pairs) return launch_mma<TN, 4, 4, 3, true>(grid, nb, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride);
     return RNLA_OK;

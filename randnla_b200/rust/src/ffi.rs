@@ -36,13 +36,6 @@ extern "C" {
     pub fn rnla_osid_randomised(a: *const c_double, m: i64, n: i64, k: i64, attr: c_int, x: *mut c_double, j: *mut i64) -> c_int;
     pub fn rnla_two_sided_id(a: *const c_double, m: i64, n: i64, k: i64, randomised: c_int, z: *mut c_double, i: *mut i64, j: *mut i64, x: *mut c_double) -> c_int;
     pub fn rnla_cur(a: *const c_double, m: i64, n: i64, k: i64, randomised: c_int, j: *mut i64, u: *mut c_double, i: *mut i64) -> c_int;
-}
-
-pub fn last_message() -> String {
-    unsafe {
-        let p = rnla_last_error_message();
-        if p.is_null() { String::new() } else { std::ffi::CStr::from_ptr(p).to_string_lossy().into_owned() }
-    }
     pub fn rnla_lupp(a: *const c_double, rows: i64, cols: i64, l: *mut c_double, u: *mut c_double, perm: *mut i64) -> c_int;
     // reference src/cg.rs
     pub fn rnla_cgls(a: *const c_double, m: i64, n: i64, b: *const c_double, tolerance: c_double, num_iterations: i64,
@@ -55,6 +48,13 @@ pub fn last_message() -> String {
     pub fn rnla_lsqr(a: *const c_double, m: i64, n: i64, b: *const c_double, damp: c_double, atol: c_double, btol: c_double,
                      conlim: c_double, iter_lim: i64, calc_var: c_int, x0: *const c_double, x: *mut c_double,
                      result: *mut RnlaLsqrResult, arnorms: *mut c_double, arnorms_cap: i64, var: *mut c_double) -> c_int;
+}
+
+pub fn last_message() -> String {
+    unsafe {
+        let p = rnla_last_error_message();
+        if p.is_null() { String::new() } else { std::ffi::CStr::from_ptr(p).to_string_lossy().into_owned() }
+    }
 }
 
 /// `rnla_lsqr_result` (include/rnla.h)

@@ -4,7 +4,7 @@ Test helper, numpy only: pins the digit arithmetic on CPU and carries the accura
 (tests/test_host_logic.py); tools/i8_emulate.py prints the sweep tables quoted in DESIGN.md section 5c."""
 import numpy as np
 
-FLUSH_STAGES = {4: 682, 6: 408, 7: 340}      # stages of 64 contraction indices per int32 accumulation (i8gemm.cu FLUSH_P*)
+FLUSH_STAGES = {3: 682, 4: 682, 6: 408, 7: 340}      # stages of 64 contraction indices per int32 accumulation (i8gemm.cu FLUSH_P*)
 
 
 def scales(mx):
@@ -47,9 +47,10 @@ def pairs(P, g0, ng):
 
 def sweeps(P, all_pairs):
     """(planes used, first group, groups) of the sweeps of one product at precision (P, all_pairs): run_sweeps of i8gemm.cu"""
+    if P == 7:
+        return [(3, 0, 3), (7, 3, 4)]
     out = [(4, 0, 4)]
-    if P == 7: out.append((7, 4, 3))
-    elif P == 6: out.append((6, 4, 2))
+    if P == 6: out.append((6, 4, 2))
     elif all_pairs: out.append((4, 4, 3))
     return out
 

@@ -140,3 +140,90 @@ def test_sketch_and_precondition_validation():
 def test_options_struct_layout():
     from randnla_b200 import _lib
     assert C.sizeof(_lib.Options) == 32
+
+
+# ---- static agreement of the three bindings with include/rnla.h (the Rust crate cannot be compiled here: no toolchain) ----
+def _c_prototypes():
+    """name -> (return type, [parameter types]) of every function include/rnla.h declares, types normalised"""
+    src = open(os.path.join(ROOT, "include", "rnla.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = {}
+    for ret, name, args in re.findall(r"\b([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(rnla_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src):
+        params = []
+        for a in [x.strip() for x in args.replace("\n", " ").split(",")]:
+            if a in ("void", ""):
+                continue
+            a = re.sub(r"\s+", " ", a)
+            m = re.match(r"^(.*?)([A-Za-z_][A-Za-z0-9_]*)?$", a)       # drop the parameter name
+            ty = m.group(1).strip() if m.group(2) and m.group(1).strip() else a
+            params.append(re.sub(r"\s*\*\s*", "*", ty).strip())
+        protos[name] = (re.sub(r"\s*\*\s*", "*", ret.strip()), params)
+    return protos
+
+
+_C_TO_RUST = {"double": "c_double", "const double*": "*const c_double", "double*": "*mut c_double", "int64_t": "i64", "int64_t*": "*mut i64",
+              "const int64_t*": "*const i64", "int32_t": "c_int", "int32_t*": "*mut c_int", "uint64_t": "u64", "uint32_t": "u32",
+              "rnla_status": "c_int", "const char*": "*const c_char", "rnla_lsqr_result*": "*mut RnlaLsqrResult"}
+_C_TO_CTYPES = {"double": "c_double", "int64_t": "c_long", "int32_t": "c_int", "uint64_t": "c_ulong", "uint32_t": "c_uint", "rnla_status": "c_int",
+                "size_t": "c_ulong", "void": None}
+
+
+def _rust_externs():
+    src = open(os.path.join(ROOT, "randnla_b200", "rust", "src", "ffi.rs")).read()
+    src = re.sub(r"//[^\n]*", "", src)
+    blocks = re.findall(r'extern\s+"C"\s*\{(.*?)\n\}', src, flags=re.S)
+    decls = {}
+    for blk in blocks:
+        for name, args, ret in re.findall(r"pub\s+fn\s+(rnla_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->\s*([^;]+?))?\s*;", blk, flags=re.S):
+            params = [re.sub(r"\s+", " ", a.split(":", 1)[1].strip()) for a in args.replace("\n", " ").split(",") if ":" in a]
+            decls[name] = ((ret or "()").strip(), params)
+    return src, blocks, decls
+
+
+def test_rust_ffi_matches_the_header():
+    """randnla_b200/rust/src/ffi.rs cannot be compiled in this image (no rustc / cargo): check statically that it is well formed
+    (every bodiless `fn` sits inside an `extern "C"` block, braces balance), that each declaration agrees with include/rnla.h in
+    name, arity and parameter / return types, that every `ffi::rnla_*` the other modules call is declared, and that the
+    #[repr(C)] mirror of rnla_lsqr_result has the header's fields in the header's order."""
+    protos = _c_prototypes()
+    src, blocks, decls = _rust_externs()
+    assert src.count("{") == src.count("}")
+    outside = src
+    for blk in blocks:
+        outside = outside.replace(blk, "")
+    assert not re.search(r"\bfn\s+\w+\s*\([^)]*\)\s*(->\s*[^;{]+)?;", outside), "bodiless fn outside the extern block"
+    assert len(decls) >= 29
+    for name, (ret, params) in decls.items():
+        assert name in protos, f"{name} is not declared in include/rnla.h"
+        cret, cparams = protos[name]
+        assert _C_TO_RUST[cret] == ret, (name, cret, ret)
+        assert len(cparams) == len(params), (name, cparams, params)
+        for cp, rp in zip(cparams, params):
+            assert _C_TO_RUST[cp] == rp, (name, cp, rp)
+    rust_dir = os.path.join(ROOT, "randnla_b200", "rust", "src")
+    for f in os.listdir(rust_dir):
+        for used in re.findall(r"ffi::(rnla_[a-z0-9_]+)", open(os.path.join(rust_dir, f)).read()):
+            assert used in decls, f"{f} calls ffi::{used}, which ffi.rs does not declare"
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rnla.h")).read(), flags=re.S)
+    cfields = re.findall(r"(int64_t|double)\s+(\w+)\s*;", re.search(r"typedef struct[^{]*\{([^}]*)\}\s*rnla_lsqr_result", hdr).group(1))
+    rfields = re.findall(r"pub\s+(\w+)\s*:\s*(\w+)", re.search(r"pub struct RnlaLsqrResult\s*\{(.*?)\}", src, flags=re.S).group(1))
+    assert [(n, {"int64_t": "i64", "double": "c_double"}[t]) for t, n in cfields] == rfields
+
+
+def test_ctypes_prototypes_match_the_header():
+    """randnla_b200/_lib.py: arity and scalar parameter types of every prototype against include/rnla.h (pointers are void*)"""
+    from randnla_b200 import _lib
+    protos = _c_prototypes()
+    for name, (res, args) in _lib.SIGNATURES.items():
+        cret, cparams = protos[name]
+        assert len(cparams) == len(args), (name, cparams, args)
+        for cp, a in zip(cparams, args):
+            if cp.endswith("*"):
+                assert a is _lib.P or a is C.c_char_p or hasattr(a, "contents") or getattr(a, "_type_", None) is not None, (name, cp, a)
+            else:
+                assert _C_TO_CTYPES[cp] == a.__name__, (name, cp, a)
+        if cret.endswith("*"):
+            assert res in (_lib.P, C.c_char_p)
+        else:
+            assert (res.__name__ if res is not None else None) == _C_TO_CTYPES[cret], (name, cret, res)
