@@ -36,6 +36,8 @@ void orc_gemm_nn(const double* A, int64_t lda, int64_t m, int64_t K, const doubl
 void orc_gemm_tn(const double* A, int64_t lda, int64_t m, int64_t n, const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz);
 /* X.qr(): thin Q (rows x p), R (p x cols), p = min(rows, cols), R diag >= 0.  R may be NULL. */
 void orc_qr(const double* X, int64_t rows, int64_t cols, double* Q, double* R);
+/* src/sketch.rs:45-85; attr 0 = Row, 1 = Column; returns 0 or 2 (InvalidDimensions) */
+int orc_haar_sample(int64_t rows, int64_t cols, int attr, uint64_t seed, double* out);
 /* X.full_piv_lu().l(): rows x min(rows, cols) */
 void orc_stabilizer(const double* X, int64_t rows, int64_t cols, double* L);
 /* lower Cholesky; returns 0 on success, -1 if not positive definite */

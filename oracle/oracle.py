@@ -144,6 +144,15 @@ def Orth(X):
     return qr(X)[0]
 
 
+def haar_sample(rows, cols, attr, seed=0):
+    """src/sketch.rs:45-85; attr 0 = Row, 1 = Column"""
+    out = np.empty((rows, cols), dtype=np.float64, order="F")
+    rc = load().orc_haar_sample(i64(rows), i64(cols), C.c_int(attr), u64(seed), p(out))
+    if rc:
+        raise OracleError(rc)
+    return out
+
+
 def Stabilizer(X):
     X = F(X); rows, cols = X.shape
     L = np.empty((rows, min(rows, cols)), dtype=np.float64, order="F")

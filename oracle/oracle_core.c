@@ -596,6 +596,30 @@ int orc_rand_evd2(const double* A, int64_t n, int64_t k, int64_t s, const orc_op
     return 0;
 }
 
+/* ======================================================================== haar_sample  (src/sketch.rs:45-85) */
+/* rows x cols matrix with orthonormal rows (attr 0 = Row, rows <= cols) or columns (attr 1 = Column, cols <= rows): Q factor of the
+ * Householder QR of an m x n Gaussian matrix (m >= n; :68-73), each column multiplied by signum(R_ii) (:74-80), transposed for Row
+ * (:81-84).  The Gaussian entries are Omega(seed, stream 0) of this build (the reference's ziggurat values are parity-unpinned,
+ * oracle.h); column-major fill as DMatrix::from_vec (:72).  Returns 2 (InvalidDimensions) as :49-63 do. */
+int orc_haar_sample(int64_t rows, int64_t cols, int attr, uint64_t seed, double* out) {
+    int64_t m, n;
+    if (attr == 0) { if (rows > cols) return 2; m = cols; n = rows; }          /* :48-56 */
+    else { if (cols > rows) return 2; m = rows; n = cols; }                     /* :57-65 */
+    if (m <= 0 || n <= 0) return 2;
+    double* G = dalloc(m * n); double* Q = dalloc(m * n); double* R = dalloc(n * n);
+    orc_omega_fill(0, seed, 0u, m, n, 0, G, m);                                 /* :68-72 */
+    orc_qr(G, m, n, Q, R);                                                      /* :73 */
+    for (int64_t j = 0; j < n; ++j) {                                           /* :74-80 */
+        const double d = AT(R, n, j, j);
+        const double sg = (d > 0.0) ? 1.0 : (d < 0.0 ? -1.0 : (d == 0.0 ? (signbit(d) ? -1.0 : 1.0) : d));   /* f64::signum */
+        for (int64_t i = 0; i < m; ++i) AT(Q, m, i, j) *= sg;
+    }
+    if (attr == 0) { for (int64_t j = 0; j < n; ++j) for (int64_t i = 0; i < m; ++i) AT(out, n, j, i) = AT(Q, m, i, j); }   /* :82 */
+    else memcpy(out, Q, (size_t)(m * n) * sizeof(double));                      /* :83 */
+    free(G); free(Q); free(R);
+    return 0;
+}
+
 /* ======================================================================== sketch step */
 int64_t orc_sketch_dim(int64_t m, int64_t n, double sf, int rule) {
     if (rule == 0) return (sf * (double)n > (double)m) ? m : (int64_t)floor(sf * (double)n);   /* sketch_and_precondition.rs:49,105 */

@@ -155,6 +155,8 @@ def _c_prototypes():
             if a in ("void", ""):
                 continue
             a = re.sub(r"\s+", " ", a)
+            if "[" in a:                                               # array parameter (`uint8_t id[128]`) decays to a pointer
+                a = a[:a.index("[")].rsplit(" ", 1)[0] + "* x"
             m = re.match(r"^(.*?)([A-Za-z_][A-Za-z0-9_]*)?$", a)       # drop the parameter name
             ty = m.group(1).strip() if m.group(2) and m.group(1).strip() else a
             params.append(re.sub(r"\s*\*\s*", "*", ty).strip())

@@ -86,13 +86,20 @@ def test_reference_threefry_stream(rb, orc, dist):
         rb.sketch.sketch_fill(0, 4, 4, generator=rt.GEN_THREEFRY)
 
 
-def test_haar_sample(rb):
-    """src/sketch.rs:140-214 test_row_attribute / test_column_attribute"""
+def test_haar_sample(rb, orc):
+    """src/sketch.rs:140-214 test_row_attribute / test_column_attribute, and parity with the oracle's restatement of :45-85
+    (Householder Q of the same Gaussian matrix, sign-fixed): the device's CholeskyQR2 Q has R_ii > 0, i.e. it is that matrix"""
     from randnla_b200.sketch import MatrixAttribute as M
     Q = rb.sketch.haar_sample(3, 6, M.Row)
     assert Q.shape == (3, 6) and np.abs(Q @ Q.T - np.eye(3)).max() < 1e-6
     Q = rb.sketch.haar_sample(6, 3, M.Column)
     assert Q.shape == (6, 3) and np.abs(Q.T @ Q - np.eye(3)).max() < 1e-6
+    for rows, cols, attr in [(3, 6, M.Row), (6, 3, M.Column), (4, 4, M.Row), (4, 4, M.Column), (50, 200, M.Row), (300, 40, M.Column),
+                             (1, 5, M.Row), (5, 1, M.Column), (110, 20000, M.Row)]:
+        got = rb.sketch.haar_sample(rows, cols, attr)
+        want = orc.haar_sample(rows, cols, int(attr), seed=0)
+        assert got.shape == want.shape == (rows, cols)
+        assert np.abs(got - want).max() < 1e-12, (rows, cols, attr)
 
 
 # ---------------------------------------------------------------- K1 / K1' / K2 streaming GEMMs

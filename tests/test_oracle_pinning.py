@@ -167,6 +167,27 @@ def _fullpiv_l_numpy(X):
     return L
 
 
+def test_haar_sample_restatement(orc):
+    """orc_haar_sample follows src/sketch.rs:45-85: Q of the Householder QR of a Gaussian matrix, columns multiplied by
+    signum(R_ii), transposed for Row.  Pinned on the reference's own tests (`test_row_attribute` / `test_column_attribute`,
+    :140-214: shapes, Q Q^T = I or Q^T Q = I to 1e-6; the dimension errors of :49-63) and against LAPACK: the same Gaussian matrix
+    through numpy's QR, sign-fixed the same way, gives the same Q to rounding."""
+    from oracle.oracle import OracleError
+    for rows, cols, attr in [(3, 6, 0), (6, 3, 1), (4, 4, 0), (4, 4, 1), (50, 200, 0), (300, 40, 1), (1, 5, 0), (5, 1, 1)]:
+        Q = orc.haar_sample(rows, cols, attr, seed=7)
+        assert Q.shape == (rows, cols)
+        G = orc.omega_fill(0, max(rows, cols), min(rows, cols), seed=7, stream=0)      # m x n with m >= n, column-major fill (:68-72)
+        Qn, Rn = np.linalg.qr(G)
+        Qn = Qn * np.sign(np.diag(Rn))                  # the factorisation with R_ii > 0: nalgebra's Q (R_ii >= 0), whose signum fix is +1
+        want = Qn.T if attr == 0 else Qn
+        assert np.abs(Q - want).max() < 1e-12
+        eye = np.eye(min(rows, cols))
+        assert np.abs((Q @ Q.T if attr == 0 else Q.T @ Q) - eye).max() < 1e-13
+    for rows, cols, attr in [(5, 3, 0), (3, 5, 1)]:
+        with pytest.raises(OracleError):
+            orc.haar_sample(rows, cols, attr)
+
+
 @pytest.mark.parametrize("shape", [(30, 6), (6, 6), (5, 9), (64, 17)])
 def test_stabilizer_matches_numpy_restatement(orc, shape):
     X = random_matrix(*shape, seed=7)
