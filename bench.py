@@ -87,32 +87,77 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(n, sample_rows, threads=None, steps=1, warmup=0):
-    """The reference's CPU dataflow (oracle `literal` mode: src/lora_helpers.rs:17-146 + src/lora_drivers.rs:30-69
-    statement for statement) timed on the host cores, on a bounded row sample of the same workload."""
+def host_threads():
+    """all host cores this process may use, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _blas_threads(n):
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=n)
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
+def workload_matrix(rows, n, seed=1234):
+    """the bench workload on the host: planted low-rank part of the device generator's matrix (same spectrum)"""
+    rng = np.random.default_rng(seed)
+    sig = planted_sigma()
+    with _blas_threads(host_threads()):
+        U0, _ = np.linalg.qr(rng.standard_normal((rows, R0)))
+        V0, _ = np.linalg.qr(rng.standard_normal((n, R0)))
+        A = np.empty((rows, n), order="F")
+        np.matmul(U0 * sig, V0.T, out=A)
+    return A
+
+
+def cpu_rand_svd_seconds(A, k, s, threads, steps=1, warmup=0):
+    """The reference's CPU dataflow (oracle `literal` mode: src/lora_helpers.rs:17-146 + src/lora_drivers.rs:30-69 statement for
+    statement, every product a real GEMM, the transpose materialised) on `threads` host threads; mean seconds per call."""
     from oracle import oracle as orc
     orc.load()
-    if threads:
-        orc.set_threads(threads)
-    rng = np.random.default_rng(1234)
-    sig = planted_sigma()
-    U0, _ = np.linalg.qr(rng.standard_normal((sample_rows, R0)))
-    V0, _ = np.linalg.qr(rng.standard_normal((n, R0)))
-    A = np.asfortranarray((U0 * sig) @ V0.T)
-    del U0
+    orc.set_threads(int(threads))
     o = orc.make_opts(mode=orc.MODE_LITERAL)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        U, S, Vt = orc.rand_svd(A, K_RANK, 1e-6, S_OVER, o)
+        orc.rand_svd(A, k, 1e-6, s, o)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    t = float(np.mean(times))
-    return {"value": algorithmic_bytes(sample_rows, n) / t * 1e-9, "unit": "GB/s", "cores": orc.get_threads(), "kind": "port",
-            "sample": f"oracle literal-mode rand_svd (k={K_RANK}, s={S_OVER}) on {sample_rows} x {n} rows-sample of the workload, "
-                      f"{t:.2f} s per call, all products are real GEMMs as in the reference",
-            "seconds_per_call": t, "tflops": algorithmic_flops(sample_rows, n, K_RANK + S_OVER) / t * 1e-12}
+    return float(np.mean(times)), times
+
+
+def cpu_baseline(n, sample_rows):
+    """cpu_baseline leg of the GPU arm (rank 0, N = 1): the oracle port on a bounded row sample of the workload with ALL host cores
+    (`value`), the same on ONE thread (faithful to the reference: nalgebra / matrixmultiply are single-threaded, Cargo.lock:618-619,
+    644-645) on a smaller sample, and BASELINE config 1 (2000 x 1000 rank-50, k = 50, s = 10) in full, both ways."""
+    cores = host_threads()
+    A = workload_matrix(sample_rows, n)
+    t_all, _ = cpu_rand_svd_seconds(A, K_RANK, S_OVER, cores)
+    rows1 = max(1024, sample_rows // 8)
+    t_one, _ = cpu_rand_svd_seconds(A[:rows1].copy(order="F"), K_RANK, S_OVER, 1)
+    del A
+    rng = np.random.default_rng(0)
+    C1 = np.zeros((2000, 1000), order="F")
+    for _ in range(50):                                        # src/test_assist.rs:7-31 rank_k_matrix
+        C1 += np.outer(rng.standard_normal(2000), rng.standard_normal(1000))
+    c1_all = float(np.median(cpu_rand_svd_seconds(C1, 50, 10, cores, steps=5, warmup=1)[1]))
+    c1_one = float(np.median(cpu_rand_svd_seconds(C1, 50, 10, 1, steps=5, warmup=1)[1]))
+    return {"value": algorithmic_bytes(sample_rows, n) / t_all * 1e-9, "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"oracle literal-mode rand_svd (k={K_RANK}, s={S_OVER}) on a {sample_rows} x {n} row sample of the workload, "
+                      f"{t_all:.2f} s per call on {cores} threads, all products are real GEMMs as in the reference",
+            "seconds_per_call": t_all, "tflops": algorithmic_flops(sample_rows, n, K_RANK + S_OVER) / t_all * 1e-12,
+            "one_thread": {"value": algorithmic_bytes(rows1, n) / t_one * 1e-9, "unit": "GB/s", "cores": 1, "sample_rows": rows1,
+                           "seconds_per_call": t_one, "tflops": algorithmic_flops(rows1, n, K_RANK + S_OVER) / t_one * 1e-12,
+                           "note": "the reference itself is single-threaded (nalgebra 0.33 / matrixmultiply 0.3.9 without the threading feature)"},
+            "config1_2000x1000_k50": {"ms_all_cores": c1_all * 1e3, "ms_one_thread": c1_one * 1e3, "cores": cores,
+                                      "note": "BASELINE config 1 timed in full (median of 5), oracle literal mode"}}
 
 
 def secondary_configs(torch, rt, _lib, lib, dA_headline, hbm_peak):
@@ -134,11 +179,14 @@ def secondary_configs(torch, rt, _lib, lib, dA_headline, hbm_peak):
     # the headline matrix once more with a sketch narrow enough (l = k + p = 16 < the FP64/HBM ridge of ~21 columns) that the
     # four A-streaming passes are HBM-bound: this is the regime north_star's "70 % of HBM roofline" can physically refer to
     mh, nh = dA_headline.shape
-    ms = timed(lambda: ld.rand_svd_dev(dA_headline, 10, 6), 3)
+    o_fp64 = rt.make_options(range_passes_int8=0)
+    o_auto = rt.make_options(range_passes_int8=-1)
+    ms = timed(lambda: ld.rand_svd_dev(dA_headline, 10, 6, o_fp64), 3)
     ph = rt.timings()
     pass_ms = [v for k_, v in ph if k_.startswith("pass:")]
     gbs = 8.0 * mh * nh / (float(np.mean(pass_ms)) * 1e-3) * 1e-9
-    out["c2_matrix_k10_p6_hbm_bound_regime"] = {"ms": ms, "mean_pass_ms": float(np.mean(pass_ms)), "A_stream_GBps_per_pass": gbs,
+    assert not any(k_.startswith("i8:") for k_, _ in ph), "the HBM-bound FP64 leg ran integer passes"
+    out["c2_matrix_k10_p6_hbm_bound_regime"] = {"mode": "fp64 (thin FP64 kernels, l = 16)", "ms": ms, "mean_pass_ms": float(np.mean(pass_ms)), "A_stream_GBps_per_pass": gbs,
                                                 "hbm_frac": gbs / hbm_peak, "whole_call_A_stream_GBps": 4 * 8.0 * mh * nh / (ms * 1e-3) * 1e-9,
                                                 "phases_ms": [[k_, v] for k_, v in ph]}
     m, n = 1000000, 2000
@@ -172,8 +220,6 @@ def secondary_configs(torch, rt, _lib, lib, dA_headline, hbm_peak):
     _lib.check(lib.rnla_gemm_nn_dev(pVs, ldvs, nn_, r0, pVt, ldvt, nn_, p5, ld5)); rt.synchronize()
     A5.diagonal().add_(1e-8)                                        # V0 diag(lam) V0^T is symmetric to rounding; symmetrise exactly in place
     res = {}
-    def run5():
-        res["V"], res["L"] = ld.rand_evd2_dev(A5, k, s)
     # exact symmetry is a precondition of rand_evd2 (reference :106 style check): mirror the upper triangle blockwise
     B = 5000
     for i0 in range(0, nn_, B):
@@ -184,52 +230,107 @@ def secondary_configs(torch, rt, _lib, lib, dA_headline, hbm_peak):
             else:
                 A5[j0:j0 + B, i0:i0 + B].copy_(blk.t())
     torch.cuda.synchronize()
-    ms = timed(run5, 2)
-    L = res["L"].cpu().numpy()
-    out["c5_rand_evd2_50k_k200"] = {"ms": ms, "tflops_fp64": 4 * 2.0 * nn_ * nn_ * (k + s) / (ms * 1e-3) * 1e-12, "r": int(len(L)),
-                                    "max_rel_lambda_err_vs_planted": float(np.max(np.abs(L - (lam[:len(L)] + 1e-8)) / lam[:len(L)])),
-                                    "phases_ms": [[k_, v] for k_, v in rt.timings()]}
-    # the same call with every pass over A on the integer tensor cores (range_passes_int8 = 2: power iteration on the 28-bit
-    # split, Y = A S as A^T S on the 49-bit split; l = 210 columns = two 128-column MMA tiles)
-    try:
-        o8 = rt.make_options(range_passes_int8=2)
-        def run5i():
-            res["V8"], res["L8"] = ld.rand_evd2_dev(A5, k, s, o8)
-        ms8 = timed(run5i, 2)
-        L8 = res["L8"].cpu().numpy()
-        out["c5_rand_evd2_50k_k200_int8"] = {"ms": ms8, "r": int(len(L8)),
-                                             "max_rel_lambda_diff_vs_fp64_path": float(np.max(np.abs(L8 - L[:len(L8)]) / L[:len(L8)])),
-                                             "max_rel_lambda_err_vs_planted": float(np.max(np.abs(L8 - (lam[:len(L8)] + 1e-8)) / lam[:len(L8)])),
-                                             "phases_ms": [[k_, v] for k_, v in rt.timings()]}
-    except Exception as exc:
-        out["c5_rand_evd2_50k_k200_int8"] = {"error": repr(exc)[:200]}
+    for tag, oo in (("fp64", o_fp64), ("auto", o_auto)):
+        def run5():
+            res["V"], res["L"] = ld.rand_evd2_dev(A5, k, s, oo)
+        ms = timed(run5, 2)
+        L = res["L"].cpu().numpy()
+        ph5 = rt.timings()
+        assert any(k_.startswith("i8:") for k_, _ in ph5) == (tag == "auto"), f"config 5 leg {tag}: phases {ph5}"
+        res["L_" + tag] = L
+        out["c5_rand_evd2_50k_k200_" + tag] = {"ms": ms, "tflops_fp64_equivalent": 4 * 2.0 * nn_ * nn_ * (k + s) / (ms * 1e-3) * 1e-12, "r": int(len(L)),
+                                               "max_rel_lambda_err_vs_planted": float(np.max(np.abs(L - (lam[:len(L)] + 1e-8)) / lam[:len(L)])),
+                                               "phases_ms": [[k_, v] for k_, v in ph5]}
+    La, Lf = res["L_auto"], res["L_fp64"]
+    out["c5_rand_evd2_50k_k200_auto"]["max_rel_lambda_diff_vs_fp64_path"] = float(np.max(np.abs(La - Lf[:len(La)]) / Lf[:len(La)]))
     return out
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port: the Rust reference cannot be built in
+    this image) on all host cores, on the GPU arm's config.  Every step is one full `rand_svd` of the N = 1 workload (200 000 x 20 000)
+    when the host has the memory for it (A + the transposed copy the reference makes + panels: ~70 GB) and the whole run fits a few
+    minutes; otherwise a bounded row sample, and the line says which."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import psutil
     n = args.cols
-    sample_rows = args.ref_rows
-    cb = cpu_baseline(n, sample_rows, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
+    cores = host_threads()
+    rows_full = args.rows
+    # calibrate on a small sample, then take the largest row count whose (warmup + steps) calls stay within the time budget
+    cal_rows = 6250
+    t_cal, _ = cpu_rand_svd_seconds(workload_matrix(cal_rows, n), K_RANK, S_OVER, cores)
+    per_row = t_cal / cal_rows
+    calls = max(args.steps, 1) + max(args.warmup, 0)
+    fit_rows = int(args.ref_budget_s / (calls * per_row))
+    mem_rows = int(0.55 * psutil.virtual_memory().available / (2.2 * 8 * n))
+    rows = rows_full if args.ref_rows <= 0 else args.ref_rows
+    rows = max(1000, min(rows, fit_rows, mem_rows))
+    rows -= rows % 8
+    A = workload_matrix(rows, n)
+    t, times = cpu_rand_svd_seconds(A, K_RANK, S_OVER, cores, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
+    value = algorithmic_bytes(rows, n) / t * 1e-9
+    sample = (f"oracle literal-mode rand_svd (k={K_RANK}, s={S_OVER}) on {rows} x {n}"
+              + (" = the full N = 1 workload" if rows == rows_full else f" row sample of the {rows_full} x {n} workload (time budget {args.ref_budget_s:.0f} s, "
+                 f"host RAM {psutil.virtual_memory().total >> 30} GiB)") + f", {t:.2f} s per call on {cores} threads")
+    cb = {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample, "seconds_per_call": t,
+          "tflops": algorithmic_flops(rows, n, K_RANK + S_OVER) / t * 1e-12, "rows_timed": rows, "full_workload": rows == rows_full}
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_call"] * 1e3,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"rand_svd f64 {args.rows * args.gpus}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}, Gaussian sketch",
-                   "timed_on": f"{sample_rows}x{n} row sample (CPU), throughput is per byte of A streamed"},
+                   "timed_on": f"{rows}x{n} (CPU, {cores} threads), throughput is per byte of A streamed"},
         "cpu_baseline": cb, "gpu_launches": 0,
-        "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+MODES = {"auto": -1, "fp64": 0, "level1": 1, "level2": 2, "level3": 3}
+MODE_DTYPE = {
+    "auto": "f64 operands and results; every pass over A FP64-grade on the int8 tensor cores: 55-bit balanced-digit fixed-point split, "
+            "exact int32 accumulation in TMEM (rnla_options.range_passes_int8 = -1 'auto', the library default)",
+    "level3": "f64 operands and results; every pass over A FP64-grade on the int8 tensor cores: 55-bit balanced-digit fixed-point split, "
+              "exact int32 accumulation in TMEM (rnla_options.range_passes_int8 = 3)",
+    "fp64": "f64 (every pass on the FP64 DMMA kernels, rnla_options.range_passes_int8 = 0)",
+    "level1": "f64 results; A Omega, A^T Y, A S on 31-bit int8 digit planes, Q^T A in FP64 (opt-in, spectrum-conditional: range_passes_int8 = 1)",
+    "level2": "f64 results; A Omega, A^T Y, A S on 31-bit int8 digit planes, Q^T A on the 55-bit split (opt-in, spectrum-conditional: range_passes_int8 = 2)",
+}
+
+
+def gpu_numa_cpus(local_rank, policy):
+    """CPUs of the NUMA node a rank's pinned staging buffer should live on.  'gpu': the node the GPU hangs off (sysfs); 'spread':
+    node = rank mod nodes (used when every GPU reports the same node, so that one socket's memory does not feed all uploads)"""
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if len(nodes) < 2 or policy == "none":
+            return None, None
+        bdf = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        node = -1
+        if bdf:
+            bdf = bdf[-12:] if len(bdf) > 12 else bdf              # sysfs uses a 4-digit domain
+            f = f"/sys/bus/pci/devices/{bdf}/numa_node"
+            if os.path.exists(f):
+                node = int(open(f).read().strip())
+        if policy == "spread" or node < 0:
+            node = nodes[local_rank % len(nodes)]
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return node, cpus
+    except Exception:
+        return None, None
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import ctypes as C
-    import randnla_b200 as rb
+    import randnla_b200 as rb  # noqa: F401
     from randnla_b200 import runtime as rt, _lib, lora_drivers as ld
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -249,9 +350,15 @@ def run_ours(args):
     rt.use_torch_stream()
 
     n = args.cols
-    m_local = args.rows
-    m_global = m_local * world
-    row_off = rank * m_local
+    strong = args.scaling == "strong"
+    if strong:
+        m_global = args.rows_total
+        r_start, r_stop = rt.shard_rows(m_global, world, rank)
+        m_local, row_off = r_stop - r_start, r_start
+    else:
+        m_local = args.rows
+        m_global = m_local * world
+        row_off = rank * m_local
     l = K_RANK + S_OVER
     sig = planted_sigma()
 
@@ -271,44 +378,60 @@ def run_ours(args):
     dA = rt.empty_colmajor(m_local, n)
     pA, lda = rt.dev_ptr_ld(dA)
     _lib.check(lib.rnla_generate_lowrank_dev(pA, lda, m_local, n, row_off, m_global, R0, sig.ctypes.data_as(C.c_void_p), 1e-7, 1234))
-    use_i8 = args.range != "fp64"
-    i8_level = {"fp64": 0, "int8": 1, "int8-all": 2}[args.range]
-    opts = rt.make_options(fused_sketch=args.fused, range_passes_int8=i8_level)
+
+    def make_opts(mode):
+        return rt.make_options(fused_sketch=args.fused, range_passes_int8=MODES[mode])
 
     # ---- roofs of this box, this run ----
-    fp64 = C.c_double(0); hbm = C.c_double(0)
+    fp64 = C.c_double(0); hbm = C.c_double(0); i8_burst = C.c_double(0); i8_sust = C.c_double(0)
     _lib.check(lib.rnla_measure_roofs(C.byref(fp64), C.byref(hbm), 4 << 30))
+    _lib.check(lib.rnla_measure_int8_roof(C.byref(i8_burst), C.byref(i8_sust)))
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    hbm_peak, hbm_src, bf16_sust = 6650.0, "fallback (B200_PROFILING.md)", None
     if os.path.exists(peaks_file):
         try:
-            hbm_peak = float(json.load(open(peaks_file))["hbm_gbs"]); hbm_src = "MEASURED_PEAKS.json (driver copy benchmark)"
+            pk = json.load(open(peaks_file))
+            hbm_peak = float(pk["hbm_gbs"]); hbm_src = "MEASURED_PEAKS.json (driver copy benchmark)"
+            bf16_sust = float(pk.get("bf16_tflops_sustained", 0.0)) or None
         except Exception:
             pass
 
-    # ---- device-resident timing ----
-    for _ in range(args.warmup):
-        U, S, Vt = ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
-    barrier()
+    def timed_steps(opts, warmup, steps, collect=False):
+        """`steps` calls bracketed by CUDA events on the launching stream (barrier + synchronize on both sides), max over ranks"""
+        for _ in range(warmup):
+            out = ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
+        barrier()
+        acc = {}
+        launches0 = rt.kernel_launches()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            out = ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
+            if collect:
+                for name, ms in rt.timings():     # library-side CUDA events of this step (stream already drained by the call)
+                    acc.setdefault(name, []).append(ms)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+        return ms, out, {k_: float(np.mean(v)) for k_, v in acc.items()}, rt.kernel_launches() - launches0
+
+    # ---- device-resident timing of the headline mode ----
+    opts = make_opts(args.mode)
+    _lib.check(lib.rnla_set_kernel_timing(1))
     sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):                                   # warm-up outside the clock sampling window
+        ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
+    barrier()
     if rank == 0:
         sampler.start()
-    launches0 = rt.kernel_launches()
-    phase_acc = {}
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        U, S, Vt = ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
-        for name, ms in rt.timings():             # library-side CUDA events of this step (stream already drained by the call)
-            phase_acc.setdefault(name, []).append(ms)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = rt.kernel_launches() - launches0
+    ms_step, (U, S, Vt), phases_all, launches = timed_steps(opts, 0, args.steps, collect=True)
     clocks = sampler.stop() if rank == 0 else None
-    ms_step = max_over_ranks(ms_total / args.steps)
+    _lib.check(lib.rnla_set_kernel_timing(0))
+    kernels = {k_: v for k_, v in phases_all.items() if k_.startswith("k:")}
+    phases = {k_: v for k_, v in phases_all.items() if not k_.startswith("k:")}
     value = algorithmic_bytes(m_global, n) / (ms_step * 1e-3) * 1e-9
+    int8_ran = any(k_.startswith("i8:") for k_ in phases)
 
     # ---- accuracy of the timed result (size-independent properties) ----
     Sg = S.cpu().numpy()
@@ -319,156 +442,151 @@ def run_ours(args):
     orth_err = float((gram - torch.eye(K_RANK, dtype=torch.float64, device="cuda")).abs().max().item())
     sigma_vs_planted = float(np.max(np.abs(Sg - sig[:K_RANK]) / sig[:K_RANK]))
 
-    # ---- the same call with all four passes in FP64, beside the headline (sigma agreement between the two, time) ----
-    fp64_side = None
-    if use_i8:
-        def side(level):
-            oo = rt.make_options(fused_sketch=args.fused, range_passes_int8=level)
-            for _ in range(2):
-                Ux, Sx, Vx = ld.rand_svd_dev(dA, K_RANK, S_OVER, oo)
-            per = []
-            for _ in range(3):
-                barrier()
-                f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
-                f0.record()
-                Ux, Sx, Vx = ld.rand_svd_dev(dA, K_RANK, S_OVER, oo)
-                f1.record()
-                barrier()
-                per.append(max_over_ranks(f0.elapsed_time(f1)))
-            msx = float(np.median(per))
-            Sxh = Sx.cpu().numpy()
-            return {"ms_per_step": msx, "A_stream_GBps": algorithmic_bytes(m_global, n) / (msx * 1e-3) * 1e-9,
-                    "max_rel_sigma_diff_vs_headline": float(np.max(np.abs(Sg - Sxh) / Sxh)), "phases_ms": dict(rt.timings())}
-        fp64_side = {"all_fp64": side(0)}
-        if i8_level == 2:
-            fp64_side["int8_range_passes_fp64_QtA"] = side(1)
+    # ---- the other modes beside the headline: all-FP64 is a first-class second value; levels 1 / 2 are the opt-in fast modes ----
+    def side(mode, steps):
+        oo = make_opts(mode)
+        msx, (Ux, Sx, Vx), ph, _ = timed_steps(oo, 2, steps, collect=True)
+        Sxh = Sx.cpu().numpy()
+        ph = {k_: v for k_, v in ph.items() if not k_.startswith("k:")}
+        has_i8 = any(k_.startswith("i8:") for k_ in ph)
+        assert has_i8 == (mode != "fp64") or not int8_ran, f"mode {mode}: phases {list(ph)} do not match the requested arithmetic"
+        return {"ms_per_step": msx, "value": algorithmic_bytes(m_global, n) / (msx * 1e-3) * 1e-9, "unit": "GB/s", "steps": steps,
+                "max_rel_sigma_diff_vs_headline": float(np.max(np.abs(Sg - Sxh) / Sxh)), "phases_ms": ph,
+                "dtype": MODE_DTYPE[mode]}
+    sides = {}
+    for mode in ("fp64", "level1", "level2") if args.mode in ("auto", "level3") else ("fp64",):
+        if mode != args.mode:
+            sides[mode] = side(mode, min(args.steps, 5) if mode == "fp64" else 3)
 
-    # ---- end to end through the host-buffer C ABI (pinned host memory -> device -> host) ----
+    # ---- end to end through the host-buffer C ABI (pinned host memory -> device -> host), headline mode and all-FP64 ----
     e2e = None
+    e2e_fp64 = None
     if args.e2e_steps > 0:
-        rt.set_options(range_passes_int8=i8_level)          # the host-buffer entry point reads the process-wide options
         host_bytes = 8 * m_local * n
         import psutil
         avail = psutil.virtual_memory().available
-        full = host_bytes * world < 0.7 * avail if world > 1 else host_bytes < 0.7 * avail
+        full = host_bytes * world < 0.7 * avail
+        numa_node = None
         if full:
+            numa_node, cpus = gpu_numa_cpus(local_rank, args.pin_numa) if world > 1 else (None, None)
+            old_aff = None
+            if cpus:
+                try:
+                    old_aff = os.sched_getaffinity(0); os.sched_setaffinity(0, cpus)       # first-touch: the pinned pages land on this node
+                except Exception:
+                    old_aff = None
             hA = torch.empty((n, m_local), dtype=torch.float64, pin_memory=True)      # column-major m_local x n
             hA.copy_(dA.t())
-            hAn = hA.numpy().T
+            if old_aff:
+                os.sched_setaffinity(0, old_aff)
             kk = K_RANK
             hU = np.empty((m_local, kk), order="F"); hS = np.empty((kk, kk), order="F"); hVt = np.empty((kk, n), order="F")
             r = C.c_int64(0)
 
             def e2e_step():
                 _lib.check(lib.rnla_rand_svd(C.c_void_p(hA.data_ptr()), m_local, n, kk, 1e-6, S_OVER, rt.ptr(hU), rt.ptr(hS), rt.ptr(hVt), C.byref(r)))
-            staging = "full shard in pinned host memory"
-            d2h = (m_local * kk + kk + kk * n) * 8
+            staging = "full shard in pinned host memory" + (f" on NUMA node {numa_node} ({args.pin_numa})" if numa_node is not None else "")
         else:
             win_rows = 25000
             hW = torch.empty((n, win_rows), dtype=torch.float64, pin_memory=True)
             hW.copy_(dA[:win_rows].t())
             dB = rt.empty_colmajor(m_local, n)
+            cur = {"opts": opts}
 
             def e2e_step():
                 for r0 in range(0, m_local, win_rows):
                     rr = min(win_rows, m_local - r0)
                     dB[r0:r0 + rr].t().copy_(hW[:, :rr], non_blocking=True)
-                Ue, Se, Vte = ld.rand_svd_dev(dB, K_RANK, S_OVER, opts)
+                Ue, Se, Vte = ld.rand_svd_dev(dB, K_RANK, S_OVER, cur["opts"])
                 Ue.cpu(); Se.cpu(); Vte.cpu()
             staging = f"pinned {win_rows}-row window reused cyclically (host RAM cannot hold {world} x {host_bytes >> 30} GiB)"
-            d2h = (m_local * K_RANK + K_RANK + K_RANK * n) * 8
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
-        e2e = {"value": algorithmic_bytes(m_global, n) / dt * 1e-9, "unit": "GB/s", "h2d_bytes_per_step": int(host_bytes),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "staging": staging,
-               "api": "rnla_rand_svd (host buffers, include/rnla.h)" if full else "runtime copy + lora_drivers.rand_svd_dev"}
+        d2h = (m_local * K_RANK + K_RANK + K_RANK * n) * 8
+
+        def run_e2e(mode):
+            # the host-buffer entry point reads the process-wide options: set them for this leg only, restored on exit
+            with rt.options(fused_sketch=args.fused, range_passes_int8=MODES[mode]):
+                if not full:
+                    cur["opts"] = make_opts(mode)
+                e2e_step()
+                names = [nm for nm, _ in rt.timings()]
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    e2e_step()
+                barrier()
+                dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+            assert any("i8:" in nm for nm in names) == (mode != "fp64") or not int8_ran, f"e2e leg {mode}: phases {names}"
+            return {"value": algorithmic_bytes(m_global, n) / dt * 1e-9, "unit": "GB/s", "h2d_bytes_per_step": int(host_bytes),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "staging": staging, "mode": mode,
+                    "api": "rnla_rand_svd (host buffers, include/rnla.h)" if full else "runtime copy + lora_drivers.rand_svd_dev"}
+        e2e = run_e2e(args.mode)
+        if args.mode != "fp64":
+            e2e_fp64 = run_e2e("fp64")
         if full:
             del hA
         else:
             del dB
+    assert rt.get_options().range_passes_int8 == -1 or os.environ.get("RNLA_RANGE_INT8"), "process-wide options were not restored"
 
     if rank != 0:
         if world > 1:
             dist.barrier()
         return
 
-    # ---- roofline of the dominant kernels (per launch, CUDA events on the launching stream, timed region) ----
-    phases = {k: float(np.mean(v)) for k, v in phase_acc.items()}
-    fl = 2.0 * m_local * n * l
-    by = 8.0 * m_local * n
-    # FP64 DMMA passes of the step: all four with --range fp64, only "pass:At*Q" (the one that carries sigma) with --range int8
-    i8_names = (("pass:A*Omega", "pass:At*Y", "pass:A*S", "pass:At*Q") if i8_level == 2 else ("pass:A*Omega", "pass:At*Y", "pass:A*S")) if use_i8 else ()
-    fp64_ms = {k: v for k, v in phases.items() if k.startswith("pass:") and not k.startswith(i8_names)} if use_i8 else \
-              {k: v for k, v in phases.items() if k.startswith("pass:")}
-    i8_ms = {k: v for k, v in phases.items() if use_i8 and k.startswith(i8_names)}
-    nn_ms = [v for k, v in fp64_ms.items() if k.startswith("pass:A*")]
-    tn_ms = [v for k, v in fp64_ms.items() if k.startswith("pass:At*")]
-    gemm_ms = nn_ms + tn_ms
+    # ---- roofline of the dominant kernel (per launch, CUDA events on the launching stream, timed region) ----
     step_ms = sum(phases.values())
-    fp64_block = None
-    if gemm_ms:
-        per_launch_ms = float(np.mean(gemm_ms))
-        fp64_block = {
-            "bound": "tensor", "kernel": "gemm_tn_kernel (FP64 DMMA.8x8x4): B = Q^T A, the pass that carries the singular values" if use_i8
-                     else "gemm_nn_kernel / gemm_tn_kernel (FP64 DMMA.8x8x4, 2 launches each per step)",
-            "achieved": fl / (per_launch_ms * 1e-3) * 1e-12, "peak": fp64.value, "unit": "TFLOP/s",
-            "frac": fl / (per_launch_ms * 1e-3) * 1e-12 / fp64.value,
-            "peak_source": "FP64 DMMA peak measured live by rnla_measure_roofs on this GPU (MEASURED_PEAKS.json holds no FP64 number)",
-            "traffic": None,
-            "hbm": {"achieved": by / (per_launch_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": by / (per_launch_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src, "read_only_stream_measured_gbs": hbm.value},
-            "note": "l = k+p = 110 makes an FP64 pass FP64-pipe bound (27.5 flop/B vs a 5.7 flop/B ridge), SURVEY.md §0 fact 3",
-            "per_kernel_ms": {"gemm_nn": float(np.mean(nn_ms)) if nn_ms else None, "gemm_tn": float(np.mean(tn_ms)) if tn_ms else None},
-            "share_of_step": float(sum(gemm_ms) / step_ms),
-        }
-    if i8_level == 2:
-        # no FP64 pass left: the longest single launch of the step is the digit split of A (HBM-bound: A read once, the two tiled
-        # 4-plane images and the 3-plane image of the trailing digits written: 8 + 4 + 4 + 3 = 19 bytes per element)
-        sp_ms = phases.get("i8:split(A)", float("nan"))
-        sp_by = 19.0 * m_local * n
-        roofline = {"bound": "hbm", "kernel": "slice_a_kernel<7 digits> (FP64 -> seven balanced 7-bit digit planes, pre-tiled MMA images)",
-                    "achieved": sp_by / (sp_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s", "frac": sp_by / (sp_ms * 1e-3) * 1e-9 / hbm_peak,
-                    "peak_source": hbm_src, "traffic": None, "bytes_per_launch": sp_by, "share_of_step": float(sp_ms / step_ms),
-                    "note": "with --range int8-all no FP64 GEMM is left in the step; per-kernel blocks for the integer passes below, "
-                            "the FP64 DMMA kernels are measured in all_fp64_passes / --range fp64 (95 % of the DMMA peak)"}
-    else:
-        roofline = fp64_block
-    if use_i8 and i8_ms:
-        # the integer passes stream the 4 digit planes of A: 4 bytes per element per sweep (A S makes two sweeps), HBM-bound
-        # bytes of digit planes streamed: 4 per element per sweep; A S makes two sweeps; the 49-bit Q^T A reads 4 + 7
-        sweeps = {k: (2.0 if k.startswith("pass:A*S") else (2.75 if k.startswith("pass:At*Q") else 1.0)) for k in i8_ms}
-        pairs = {k: (16.0 if k.startswith("pass:A*S") else (28.0 if k.startswith("pass:At*Q") else 10.0)) for k in i8_ms}
-        tot_ms = sum(i8_ms.values()); tot_by = sum(4.0 * m_local * n * sweeps[k] for k in i8_ms)
-        split_ms = phases.get("i8:rowmax(A)", 0.0) + phases.get("i8:split(A)", 0.0)
-        roofline["int8_passes"] = {
-            "bound": "hbm", "kernel": "i8_mma_kernel (tcgen05.mma kind::i8, TMEM accumulators, cp.async.bulk of pre-tiled digit planes)",
-            "achieved": tot_by / (tot_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s", "frac": tot_by / (tot_ms * 1e-3) * 1e-9 / hbm_peak,
-            "per_pass_ms": i8_ms, "bytes_per_sweep": 4.0 * m_local * n,
-            "tensor_TOPS": sum(pairs.values()) * 2.0 * m_local * n * 128 / (tot_ms * 1e-3) * 1e-12, "digit_pair_mmas": pairs,
-            "f64_equivalent_A_stream_GBps": by * len(i8_ms) / (tot_ms * 1e-3) * 1e-9,
-            "split_of_A": {"ms": split_ms, "bytes": (16.0 + (11.0 if i8_level == 2 else 8.0)) * m_local * n,
-                           "GBps": (16.0 + (11.0 if i8_level == 2 else 8.0)) * m_local * n / (split_ms * 1e-3) * 1e-9 if split_ms else None,
-                           "note": "row maxima (A read once) + digit split (A read once, tiled digit-plane images written)"},
-        }
-    if i8_level == 2 and fp64_block is None:
-        roofline["fp64_dmma_kernels"] = "see all_fp64_passes"
-        ncu8 = os.path.join(ROOT, "profiles", "r01_ncu_traffic_int8.json")
-        if os.path.exists(ncu8) and m_local == ROWS_PER_GPU and n == N_COLS:
-            try:
-                roofline["traffic"] = json.load(open(ncu8)).get("split_bytes_per_launch")     # dram read + write of the split kernel (ncu)
-            except Exception:
-                pass
-    ncu_traffic = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(ncu_traffic) and i8_level != 2:
+    fl_pass = 2.0 * m_local * n * l
+    by_pass = 8.0 * m_local * n
+    pass_ms = {k_: v for k_, v in phases.items() if k_.startswith("pass:")}
+    ncu = {}
+    ncu_file = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if os.path.exists(ncu_file) and m_local == ROWS_PER_GPU and n == N_COLS:
         try:
-            roofline["traffic"] = json.load(open(ncu_traffic)).get("gemm_bytes_per_launch")
+            ncu = json.load(open(ncu_file))
         except Exception:
-            pass
+            ncu = {}
+    step_block = {"algorithmic_bytes": algorithmic_bytes(m_local, n), "ms": ms_step, "achieved_GBps": algorithmic_bytes(m_local, n) / (ms_step * 1e-3) * 1e-9,
+                  "frac_hbm": algorithmic_bytes(m_local, n) / (ms_step * 1e-3) * 1e-9 / hbm_peak, "dram_bytes": ncu.get("step_dram_bytes_" + args.mode),
+                  "note": "4 passes x 8 m n bytes (SURVEY 8d) over the whole step; dram_bytes = ncu dram read + write summed over the step's kernels"}
+    hbm_block = lambda t_ms: {"achieved": by_pass / (t_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s", "frac": by_pass / (t_ms * 1e-3) * 1e-9 / hbm_peak,
+                              "peak_source": hbm_src, "read_only_stream_measured_gbs": hbm.value, "bytes": by_pass,
+                              "note": "algorithmic bytes of one pass (8 m n: A read once, SURVEY 8d) over the duration of the pass"}
+    if int8_ran and kernels:
+        # the dominant launch: the sweep over all seven digit planes (groups 3..6, 22 digit-pair MMAs per 32 contraction indices)
+        dom = max(kernels, key=lambda k_: kernels[k_])
+        pairs = 22 if "planes 7" in dom else (6 if "planes 3" in dom else (11 if "planes 6" in dom else (10 if "groups 0..3" in dom else 6)))
+        nmma = 16 * ((l + 15) // 16)
+        ops = 2.0 * m_local * n * nmma * pairs
+        t_ms = kernels[dom]
+        mean_pass = float(np.mean(list(pass_ms.values())))
+        roofline = {
+            "bound": "tensor", "kernel": dom[2:] + " (tcgen05.mma kind::i8, TMEM int32 accumulators, cp.async.bulk of pre-tiled digit planes)",
+            "achieved": ops / (t_ms * 1e-3) * 1e-12, "peak": i8_sust.value, "unit": "TFLOP/s", "frac": ops / (t_ms * 1e-3) * 1e-12 / i8_sust.value,
+            "peak_source": "int8 tensor-core rate measured live by rnla_measure_int8_roof on this GPU, 0.25 s back-to-back under the power cap "
+                           "(MEASURED_PEAKS.json holds bf16 only; int8 dense = 2 x bf16 on this part)",
+            "peak_burst": i8_burst.value, "measured_peaks_bf16_sustained_x2": 2.0 * bf16_sust if bf16_sust else None,
+            "ops_note": "int8 multiply-accumulates executed by the launch, 2 ops each: 2 m n x 112 columns x digit pairs",
+            "launch_ms": t_ms, "digit_pairs": pairs, "share_of_step": float(4 * t_ms / step_ms) if "planes 7" in dom else None,
+            "traffic": ncu.get("dominant_kernel_dram_bytes_per_launch"),
+            "hbm": hbm_block(mean_pass), "fp64_equivalent_tflops_per_pass": fl_pass / (mean_pass * 1e-3) * 1e-12,
+            "fp64_dmma_peak_tflops": fp64.value, "per_kernel_ms": kernels, "per_pass_ms": pass_ms,
+            "split_of_A": {"rowmax_ms": phases.get("i8:rowmax(A)"), "split_ms": phases.get("i8:split(A)"),
+                           "bytes": (8.0 + 8.0 + 7.0) * m_local * n,
+                           "note": "row maxima (A read once) + digit split (A read once, seven tiled digit planes written once)"},
+            "step": step_block,
+        }
+    else:
+        gemm_ms = list(pass_ms.values())
+        per_launch_ms = float(np.mean(gemm_ms)) if gemm_ms else float("nan")
+        roofline = {
+            "bound": "tensor", "kernel": "gemm_nn_kernel / gemm_tn_kernel (FP64 DMMA.8x8x4, 2 launches each per step)",
+            "achieved": fl_pass / (per_launch_ms * 1e-3) * 1e-12, "peak": fp64.value, "unit": "TFLOP/s",
+            "frac": fl_pass / (per_launch_ms * 1e-3) * 1e-12 / fp64.value,
+            "peak_source": "FP64 DMMA peak measured live by rnla_measure_roofs on this GPU (MEASURED_PEAKS.json holds no FP64 number)",
+            "traffic": ncu.get("fp64_gemm_dram_bytes_per_launch"), "hbm": hbm_block(per_launch_ms),
+            "note": "l = k+p = 110 makes an FP64 pass FP64-pipe bound (27.5 flop/B vs a 5.7 flop/B ridge), SURVEY.md section 0 fact 3",
+            "per_pass_ms": pass_ms, "share_of_step": float(sum(gemm_ms) / step_ms), "step": step_block,
+        }
 
     cb = None
     if world == 1 and args.cpu_rows > 0:
@@ -476,29 +594,33 @@ def run_ours(args):
 
     # ---- other BASELINE configs, one short measurement each (not the headline; device-resident, CUDA events) ----
     secondary = None
-    if world == 1 and args.secondary:
+    if world == 1 and args.secondary and not strong:
         try:
             secondary = secondary_configs(torch, rt, _lib, lib, dA, hbm_peak)
         except Exception as exc:                                   # never let a side measurement break the headline line
-            secondary = {"error": repr(exc)[:200]}
+            secondary = {"error": repr(exc)[:300]}
 
+    fp64_first_class = None
+    if "fp64" in sides:
+        f = sides["fp64"]
+        fp64_first_class = {"value": f["value"], "unit": "GB/s", "ms_per_step": f["ms_per_step"], "dtype": f["dtype"], "steps": f["steps"],
+                            "e2e": e2e_fp64, "max_rel_sigma_diff_vs_headline": f["max_rel_sigma_diff_vs_headline"], "phases_ms": f["phases_ms"],
+                            "fp64_dmma_frac_of_peak": fl_pass / (float(np.mean([v for k_, v in f["phases_ms"].items() if k_.startswith("pass:")])) * 1e-3) * 1e-12 / fp64.value}
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": ["f64", "f64 (range-finder passes: int8 tensor cores on a 28-bit fixed-point split of A; Q^T A, factorisations and outputs f64)",
-                                        "f64 results; every pass over A on the int8 tensor cores with exact int32 accumulation: 28-bit balanced-digit split for the "
-                                        "range-finder passes, 49-bit split (28 digit pairs) for Q^T A; factorisations, small products and outputs f64"][i8_level],
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": MODE_DTYPE[args.mode] if int8_ran or args.mode == "fp64" else MODE_DTYPE["fp64"] + " [the int8 workspace did not fit: FP64 fallback]",
         "data": "synthetic",
         "config": {"workload": f"rand_svd f64 {m_global}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}, Gaussian sketch",
                    "rows_per_gpu": m_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
                    "sketch": "auto (materialised while Omega is L2-resident)" if args.fused == 2 else ("fused in-kernel Philox" if args.fused == 1 else "materialised"),
-                   "range_passes": ["fp64", "int8 tensor cores, Q^T A in FP64 (rnla_options.range_passes_int8 = 1)",
-                                    "int8 tensor cores, Q^T A on a 49-bit split (rnla_options.range_passes_int8 = 2)"][i8_level],
+                   "mode": args.mode, "range_passes_int8": MODES[args.mode],
                    "l2": f"inputs larger than L2 (A shard = {8 * m_local * n / 2**30:.1f} GiB per GPU, streamed 4x per step)"},
-        "rand_svd_ms": ms_step, "tflops_fp64": algorithmic_flops(m_global, n, l) / (ms_step * 1e-3) * 1e-12,
+        "rand_svd_ms": ms_step, "tflops_fp64_equivalent": algorithmic_flops(m_global, n, l) / (ms_step * 1e-3) * 1e-12,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cb, "phases_ms": phases, "secondary": secondary,
         "accuracy": {"max_abs_UtU_minus_I": orth_err, "max_rel_sigma_vs_planted(noise-limited)": sigma_vs_planted},
-        "all_fp64_passes": fp64_side,
+        "fp64": fp64_first_class, "other_modes": {k_: v for k_, v in sides.items() if k_ != "fp64"},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -514,14 +636,18 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (debug)")
     ap.add_argument("--cols", type=int, default=N_COLS)
     ap.add_argument("--fused", type=int, default=2, help="0 materialise Omega, 1 in-kernel Philox, 2 auto")
-    ap.add_argument("--range", default="int8-all", choices=["int8-all", "int8", "fp64"],
-                    help="int8: the three range-finder passes (A Omega, A^T Y, A S) run on the INT8 tensor cores from a 4 x 7-bit split of A "
-                         "(rnla_options.range_passes_int8 = 1), the pass that carries the singular values (Q^T A) in FP64; int8-all: Q^T A too, "
-                         "on a 49-bit split with exact int32 accumulation (= 2); fp64: all four passes on the FP64 DMMA kernels")
+    ap.add_argument("--mode", default="auto", choices=sorted(MODES),
+                    help="rnla_options.range_passes_int8 of the headline: auto = the library default (every pass FP64-grade on the int8 tensor cores, "
+                         "55-bit split); fp64 = the FP64 DMMA kernels; level1 / level2 = the opt-in, spectrum-conditional 31-bit range passes")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --rows per GPU; strong: --rows-total sharded over the ranks")
+    ap.add_argument("--rows-total", type=int, default=2000000, help="global rows of --scaling strong (BASELINE config 3: 2M x 20k)")
+    ap.add_argument("--pin-numa", default="gpu", choices=["gpu", "spread", "none"],
+                    help="N > 1: NUMA node of each rank's pinned staging buffer (gpu: the node its GPU hangs off; spread: rank mod nodes)")
+    ap.add_argument("--ref-budget-s", type=float, default=300.0, help="time budget of --impl reference; the rows per step shrink to fit it")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-rows", type=int, default=25000, help="row sample of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--secondary", type=int, default=1, help="1: also time BASELINE configs 4 and 5 once (N=1 only, reported under 'secondary')")
-    ap.add_argument("--ref-rows", type=int, default=25000, help="row sample per step of --impl reference")
+    ap.add_argument("--ref-rows", type=int, default=0, help="rows per step of --impl reference (0: the full N = 1 workload, memory and budget permitting)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

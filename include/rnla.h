@@ -110,6 +110,9 @@ rnla_status rnla_set_options(const rnla_options* opt);
 void rnla_get_options(rnla_options* opt);
 /* kernels launched by this library since load (bench.py `gpu_launches`) */
 uint64_t rnla_kernel_launches(void);
+/* on != 0: the integer tensor-core kernels of the passes also record kernel-level entries, named "k:...", nested inside the
+ * driver-level phases (bench.py's roofline block reads per-launch durations from them); off by default */
+rnla_status rnla_set_kernel_timing(int32_t on);
 /* per-phase device timings of the last driver call: names[i] / ms[i]; returns the number of phases */
 int32_t rnla_get_timings(const char** names, double* ms, int32_t cap);
 
@@ -386,6 +389,9 @@ rnla_status rnla_generate_lowrank_dev(double* dA, int64_t lda, int64_t m_local, 
 /* live roof measurement for bench.py (same box, same run): peak DMMA.8x8x4 rate of all SMs in TFLOP/s (register-resident
  * chains, no memory) and a read-only HBM stream over `hbm_bytes` (>= 1 GiB recommended) in GB/s.  Either pointer may be NULL. */
 rnla_status rnla_measure_roofs(double* fp64_dmma_tflops, double* hbm_read_gbs, size_t hbm_bytes);
+/* int8 tensor-core rate (tcgen05.mma kind::i8, M = N = 128, K = 32, operands resident in shared memory, every SM) in TOP/s:
+ * best short launch (`burst`) and a 0.25 s back-to-back run under the box's power cap (`sustained`); either pointer may be NULL */
+rnla_status rnla_measure_int8_roof(double* burst_tops, double* sustained_tops);
 
 /* raw device memory helpers for hosts without a CUDA runtime binding (Rust shim, ctypes) */
 rnla_status rnla_malloc(void** dptr, size_t bytes);

@@ -39,6 +39,7 @@ SIGNATURES = {
     "rnla_set_options": (c_i32, [C.POINTER(Options)]),
     "rnla_get_options": (None, [C.POINTER(Options)]),
     "rnla_kernel_launches": (c_u64, []),
+    "rnla_set_kernel_timing": (c_i32, [c_i32]),
     "rnla_get_timings": (c_i32, [C.POINTER(C.c_char_p), C.POINTER(c_f64), c_i32]),
     "rnla_comm_unique_id": (c_i32, [P]),
     "rnla_comm_init": (c_i32, [c_i32, c_i32, P]),
@@ -108,6 +109,7 @@ SIGNATURES = {
     "rnla_i8_range_gemm_dev": (c_i32, [c_i32, P, c_i64, c_i64, c_i64, P, c_i64, c_i64, P, c_i64, c_i32]),
     "rnla_small_eigh_dev": (c_i32, [P, c_i64, c_i64, P, P]),
     "rnla_generate_lowrank_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, P, c_f64, c_u64]),
+    "rnla_measure_int8_roof": (c_i32, [C.POINTER(c_f64), C.POINTER(c_f64)]),
     "rnla_measure_roofs": (c_i32, [C.POINTER(c_f64), C.POINTER(c_f64), C.c_size_t]),
     "rnla_malloc": (c_i32, [C.POINTER(P), C.c_size_t]),
     "rnla_free": (c_i32, [P]),

@@ -147,17 +147,26 @@ void phases_reset() {
     Ctx& c = g_ctx;
     for (auto& p : c.phases) { c.event_pool.push_back(p.e0); c.event_pool.push_back(p.e1); }
     c.phases.clear();
+    c.open_phases.clear();
 }
+// Phases nest: a kernel-level entry ("k:..." names, recorded only while kernel timing is on, rnla_set_kernel_timing) may sit inside
+// a driver-level phase; phase_end closes the innermost open one.
 void phase_begin(const char* name) {
     Ctx& c = g_ctx;
     PhaseTiming p; p.name = name; p.e0 = get_event(); p.e1 = get_event();
     cudaEventRecord(p.e0, c.stream);
     c.phases.push_back(p);
+    c.open_phases.push_back((int)c.phases.size() - 1);
 }
 void phase_end() {
     Ctx& c = g_ctx;
-    if (!c.phases.empty()) cudaEventRecord(c.phases.back().e1, c.stream);
+    if (c.open_phases.empty()) return;
+    const int i = c.open_phases.back();
+    c.open_phases.pop_back();
+    if (i < (int)c.phases.size()) cudaEventRecord(c.phases[(size_t)i].e1, c.stream);
 }
+void kernel_phase_begin(const char* name) { if (g_ctx.kernel_timing) phase_begin(name); }
+void kernel_phase_end() { if (g_ctx.kernel_timing) phase_end(); }
 
 }  // namespace rnla
 
@@ -223,6 +232,11 @@ void rnla_get_options(rnla_options* opt) {
 }
 uint64_t rnla_kernel_launches(void) { return g_kernel_launches; }
 
+rnla_status rnla_set_kernel_timing(int32_t on) {
+    RNLA_API_GUARD;
+    g_ctx.kernel_timing = on != 0;
+    return RNLA_OK;
+}
 int32_t rnla_get_timings(const char** names, double* ms, int32_t cap) {
     RNLA_API_GUARD;
     Ctx& c = g_ctx;

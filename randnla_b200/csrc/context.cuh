@@ -25,6 +25,8 @@ struct Ctx {
     int nranks = 1, rank = 0;
     // timings of the last driver call
     std::vector<PhaseTiming> phases;
+    std::vector<int> open_phases;            // indices of the phases begun and not yet ended (phases nest)
+    bool kernel_timing = false;              // also record kernel-level entries ("k:..."), rnla_set_kernel_timing
     std::vector<cudaEvent_t> event_pool;
     std::vector<std::string> timing_names;   // storage handed out by rnla_get_timings
     // host-buffer entry points: copy stream for the upload of A, and a one-shot hook that replaces the first product
@@ -84,6 +86,8 @@ rnla_status allgather_i64(const int64_t* send_dev, int64_t* recv_dev, size_t cou
 
 void phase_begin(const char* name);
 void phase_end();
+void kernel_phase_begin(const char* name);   // no-ops unless kernel timing is on
+void kernel_phase_end();
 void phases_reset();
 
 struct PhaseScope {

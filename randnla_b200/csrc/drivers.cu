@@ -195,6 +195,9 @@ I8Plan i8_plan(const rnla_options& o, int64_t m_local, int64_t n, int l) {
     I8Plan p;
     int lvl = o.range_passes_int8 < 0 ? 3 : o.range_passes_int8;
     if (lvl == 0 || lvl > 3 || o.mode != RNLA_MODE_INTENDED || use_fused_forced(o) || !i8_supported(m_local, n, l)) return p;
+    // auto: a narrow sketch keeps the FP64 kernels -- below l ~ 40 an FP64 pass is HBM-bound or close to it (5 .. 11 ms at the
+    // headline size) and beats an integer pass plus its share of the split of A
+    if (o.range_passes_int8 < 0 && l < 40) return p;
     if (lvl == 1) { p.stored = 4; p.carry = 0; }
     else if (lvl == 2) { p.stored = 7; p.carry = 7; }
     else { p.stored = 7; p.early = 7; p.early_all = true; p.last = 7; p.last_all = true; p.carry = 7; }

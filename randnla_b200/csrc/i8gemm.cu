@@ -28,6 +28,7 @@
 #include "ptx.cuh"
 #include <algorithm>
 #include <cmath>
+#include <string>
 #include <vector>
 
 namespace rnla {
@@ -553,9 +554,13 @@ rnla_status launch_mma(dim3 grid, int nb, int64_t kblocks_total, int64_t per, in
     }
     int na, nbs;
     mma_rings(PU, nb, &na, &nbs);
+    static const std::string kname = std::string("k:i8_mma<") + (TN ? "A^T B" : "A B") + ", planes " + std::to_string(PU) + ", groups " +
+                                     std::to_string(G0) + ".." + std::to_string(G0 + NG - 1) + ">";
+    kernel_phase_begin(kname.c_str());
     i8_mma_kernel<TN, PU, G0, NG, ADD><<<grid, MMA_THREADS, mma_smem(PU, nb), c.stream>>>(
         s.img.as<uint8_t>(), s.planes, s.cblocks, s.bimg.as<uint8_t>(), g_planes, nb, na, nbs, kblocks_total, per, flush, C, ldc, rows, ncols,
         rs_up, s.cup.d(), chunk_stride);
+    kernel_phase_end();
     ++g_kernel_launches;
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;

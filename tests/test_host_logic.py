@@ -240,13 +240,15 @@ def test_bench_reference_arm_prints_its_json_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")               # what torch.distributed.run exports: the arm must not inherit it
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--ref-rows", "600", "--cols", "400"], capture_output=True, text=True, timeout=300)
+                          "--ref-rows", "1200", "--cols", "400"], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "rand_svd_A_stream_GBps" and line["unit"] == "GB/s"
     assert line["value"] > 0 and line["dtype"] == "f64" and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["rows_timed"] == 1200 and line["cpu_baseline"]["full_workload"] is False
     assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
