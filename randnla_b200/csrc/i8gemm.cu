@@ -28,6 +28,7 @@
 #include "ptx.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -526,13 +527,17 @@ rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, int nb, cons
     return RNLA_OK;
 }
 
-// ring sizes: the thin operand gets `nbs` half-stages (3 when the A ring still gets at least 3 stages, else 2), A the rest of the
-// 227 KB of dynamic shared memory
+// ring sizes: the thin operand gets `nbs` half-stages -- 4 while the A ring still gets at least 3 stages (measured on the
+// 3-plane sweep at the headline size: 3.7 / 4.9 ms with 2, 3.0 / 3.8 with 3, 3.0 / 3.2 with 4), else 3, else 2 -- and A the rest of
+// the 227 KB of dynamic shared memory.  The 7-plane sweep is insensitive (7.9 ms with 2, 3 or 4): it is bound by what one SM can
+// take in from L2.
 constexpr size_t SMEM_MAX = 232448, SMEM_FIXED = 1024 + 1024;      // alignment slack + barriers
 inline void mma_rings(int pu, int nb, int* na, int* nbs) {
     const size_t a = (size_t)pu * ASTAGE, b = (size_t)pu * nb * 512;
-    int s = 3;
-    if ((SMEM_MAX - SMEM_FIXED - 3 * b) / a < 3) s = 2;
+    int s = 4;
+    while (s > 2 && (SMEM_MAX - SMEM_FIXED - (size_t)s * b) / a < 3) --s;
+    static const char* ov = getenv("RNLA_I8_NBS");           // experiments: force the depth of the thin-operand ring
+    if (ov && ov[0] >= '2' && ov[0] <= '4' && (SMEM_MAX - SMEM_FIXED - (size_t)(ov[0] - '0') * b) / a >= 1) s = ov[0] - '0';
     *nbs = s;
     *na = (int)std::min<size_t>(MAX_RING, (SMEM_MAX - SMEM_FIXED - s * b) / a);
 }
