@@ -125,6 +125,11 @@ def dev_ptr_ld(t):
     ld = t.stride(1) if cols > 1 else max(rows, 1)
     if ld < max(rows, 1):
         raise ValueError("bad leading dimension")
+    # The library launches on its own (non-blocking) stream unless use_torch_stream() was called: work torch has queued on ITS
+    # stream for this tensor (a fill, an upload's transpose kernel) must have finished before the library reads or writes it.
+    cur = torch.cuda.current_stream(t.device)
+    if (_lib.load().rnla_stream() or 0) != cur.cuda_stream:
+        cur.synchronize()
     return C.c_void_p(t.data_ptr()), int(ld)
 
 
