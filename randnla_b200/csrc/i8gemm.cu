@@ -622,6 +622,30 @@ rnla_status i8_prepare_begin(const double* A, int64_t lda, int64_t m, int64_t n,
     s.A = A; s.lda = lda; s.m = m; s.n = n; s.planes = planes;
     s.rblocks = (m + 127) / 128; s.cblocks = (n + 127) / 128;
     const size_t img_bytes = (size_t)s.rblocks * s.cblocks * planes * APLANE;
+    if (img_bytes > s.img.cap) {
+        // Look before allocating: a failed 100 GB cudaMalloc (and the pool churn after it) costs hundreds of milliseconds per call
+        // (measured on the 2-GPU shard of BASELINE config 3: 160 GB of A per GPU, no room for 140 GB of planes).  The images need
+        // their own size plus headroom for the panels of the passes; cached blocks of the stream-ordered pool are given back first.
+        const size_t headroom = (size_t)2 << 30;
+        size_t freeb = 0, total = 0;
+        RNLA_CUDA(cudaMemGetInfo(&freeb, &total));
+        static size_t refused_bytes = 0, refused_free = 0;     // the last request that did not fit, and the free memory it saw after trimming
+        if (img_bytes >= refused_bytes && refused_bytes && freeb <= refused_free + ((size_t)1 << 30))
+            return fail(RNLA_ERR_COMPUTATION, "int8 passes: no room for the digit-plane workspace");
+        if (freeb + s.img.cap < img_bytes + headroom) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
+                cudaStreamSynchronize(c.stream);
+                cudaMemPoolTrimTo(pool, 0);
+            }
+            RNLA_CUDA(cudaMemGetInfo(&freeb, &total));
+        }
+        if (freeb + s.img.cap < img_bytes + headroom) {
+            refused_bytes = img_bytes; refused_free = freeb;
+            return fail(RNLA_ERR_COMPUTATION, "int8 passes: no room for the digit-plane workspace");
+        }
+        refused_bytes = 0;
+    }
     if (s.img.ensure(img_bytes) != cudaSuccess) {
         cudaGetLastError();
         i8_free_workspace();
