@@ -374,6 +374,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(x):
+        """the value of every rank, in rank order"""
+        if world == 1:
+            return [float(x)]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = float(x)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     # ---- synthetic input, generated on the device shard by shard ----
     dA = rt.empty_colmajor(m_local, n)
     pA, lda = rt.dev_ptr_ld(dA)
@@ -432,6 +441,9 @@ def run_ours(args):
     phases = {k_: v for k_, v in phases_all.items() if not k_.startswith("k:")}
     value = algorithmic_bytes(m_global, n) / (ms_step * 1e-3) * 1e-9
     int8_ran = any(k_.startswith("i8:") for k_ in phases)
+    per_rank = {"int8_ran": all_ranks(1.0 if int8_ran else 0.0), "sum_of_phases_ms": all_ranks(sum(phases.values())),
+                "free_hbm_gib": all_ranks(torch.cuda.mem_get_info()[0] / 2**30)}
+    int8_ran = all(v > 0.5 for v in per_rank["int8_ran"])
 
     # ---- accuracy of the timed result (size-independent properties) ----
     Sg = S.cpu().numpy()
@@ -522,6 +534,20 @@ def run_ours(args):
         e2e = run_e2e(args.mode)
         if args.mode != "fp64":
             e2e_fp64 = run_e2e("fp64")
+        if full:
+            # what the host can feed: the same pinned shard uploaded by every rank at once, no compute (the floor of e2e)
+            dUp = rt.empty_colmajor(m_local, n)
+            dUp.t().copy_(hA, non_blocking=True); barrier()
+            t0 = time.perf_counter()
+            dUp.t().copy_(hA, non_blocking=True)
+            barrier()
+            up = max_over_ranks(time.perf_counter() - t0)
+            for blk in (e2e, e2e_fp64):
+                if blk:
+                    blk["upload_only_ms"] = up * 1e3
+                    blk["upload_only_GBps_per_gpu"] = host_bytes / up * 1e-9
+                    blk["upload_only_GBps_all_gpus"] = host_bytes * world / up * 1e-9
+            del dUp
         if full:
             del hA
         else:
@@ -621,6 +647,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cb, "phases_ms": phases, "secondary": secondary,
         "accuracy": {"max_abs_UtU_minus_I": orth_err, "max_rel_sigma_vs_planted(noise-limited)": sigma_vs_planted},
         "fp64": fp64_first_class, "other_modes": {k_: v for k_, v in sides.items() if k_ != "fp64"},
+        "per_rank": per_rank,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -12,6 +12,8 @@ print({k: d[k] for k in ("value", "ms_per_step", "scaling", "n_gpus")}, d["dtype
 print("   e2e", d["e2e"] and (round(d["e2e"]["ms_per_step"], 1), round(d["e2e"]["value"], 1), d["e2e"]["staging"]))
 print("   phases", {k: round(v, 2) for k, v in d["phases_ms"].items()})
 print("   fp64", d["fp64"] and (round(d["fp64"]["ms_per_step"], 2), d["fp64"]["e2e"] and round(d["fp64"]["e2e"]["ms_per_step"], 1)))
+print("   per_rank", d.get("per_rank"))
+print("   upload_only", d["e2e"] and d["e2e"].get("upload_only_ms"), d["e2e"] and d["e2e"].get("upload_only_GBps_all_gpus"))
 PY
 }
 if [ "$WHAT" != "strong" ]; then
@@ -21,6 +23,6 @@ if [ "$WHAT" != "strong" ]; then
 fi
 if [ "$WHAT" != "weak" ]; then
   timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --scaling strong \
-      --rows-total 2000000 --steps 3 --warmup 2 --e2e-steps 0 > gpurun_out/bench_r2_strong_n$N.json 2> gpurun_out/bench_r2_strong_n$N.err
+      --rows-total ${ROWS_TOTAL:-2000000} --steps 3 --warmup 2 --e2e-steps 0 > gpurun_out/bench_r2_strong_n$N.json 2> gpurun_out/bench_r2_strong_n$N.err
   tail -c 300 gpurun_out/bench_r2_strong_n$N.err; show gpurun_out/bench_r2_strong_n$N.json
 fi
