@@ -285,6 +285,9 @@ rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, doub
     const rnla_options& o = c.opts;
     const int q = o.num_passes > 0 ? o.num_passes : 2;
     const bool streamed = o.mode == RNLA_MODE_INTENDED && q >= 2 && q % 2 == 0 && m >= 8192;
+    // outputs first: nothing below may return between arming the one-shot upload hook and the driver call that consumes it
+    RNLA_CUDA(dU.alloc((size_t)m * r * 8)); RNLA_CUDA(dS.alloc((size_t)r * 8)); RNLA_CUDA(dVt.alloc((size_t)r * n * 8));
+    struct HookGuard { Ctx& c; ~HookGuard() { c.first_pass_hook = nullptr; c.block_landed_hook = nullptr; } } hook_guard{c};
     if (!streamed) {
         RNLA_TRY(h2d(dA, A, (size_t)m * n));
     } else {
@@ -294,9 +297,13 @@ rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, doub
         RNLA_CUDA(dA.alloc((size_t)m * n * 8));
         double* dAp = dA.d();
         c.first_pass_hook = [&c, A, dAp, m, n, l, o](double* S, double* Y, int64_t ldy) -> rnla_status {
-            cudaEvent_t ready, landed;
-            RNLA_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-            RNLA_CUDA(cudaEventCreateWithFlags(&landed, cudaEventDisableTiming));
+            struct Ev {                                         // destroyed on every return path
+                cudaEvent_t e = nullptr;
+                ~Ev() { if (e) cudaEventDestroy(e); }
+            } ev_ready, ev_landed;
+            RNLA_CUDA(cudaEventCreateWithFlags(&ev_ready.e, cudaEventDisableTiming));
+            RNLA_CUDA(cudaEventCreateWithFlags(&ev_landed.e, cudaEventDisableTiming));
+            cudaEvent_t ready = ev_ready.e, landed = ev_landed.e;
             const bool fused = o.fused_sketch == 1 || (o.fused_sketch == 2 && (double)n * l * 8.0 > 48.0 * 1024 * 1024);
             if (!fused) RNLA_CUDA(fill_philox(o.dist, o.seed, 1 /* STREAM_RANGE_N */, n, l, 0, S, n, c.stream));
             RNLA_CUDA(cudaEventRecord(ready, c.stream));                    // dA is allocated stream-ordered on c.stream
@@ -315,11 +322,9 @@ rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, doub
                            : dev_gemm_nn(dAp + r0, m, rows, n, S, n, l, Y + r0, ldy);
                 if (rc == RNLA_OK && c.block_landed_hook) rc = c.block_landed_hook(r0, rows);     // int8 passes: split this block now
             }
-            cudaEventDestroy(ready); cudaEventDestroy(landed);
             return rc;
         };
     }
-    RNLA_CUDA(dU.alloc((size_t)m * r * 8)); RNLA_CUDA(dS.alloc((size_t)r * 8)); RNLA_CUDA(dVt.alloc((size_t)r * n * 8));
     int64_t rr = 0;
     {
         const rnla_status st = dev_rand_svd(dA.d(), m, m, n, k, s, c.opts, dU.d(), m, dS.d(), dVt.d(), r, &rr);

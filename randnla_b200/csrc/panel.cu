@@ -815,6 +815,18 @@ cudaError_t sumsq(const double* X, int64_t ld, int64_t rows, int64_t cols, doubl
     sumsq_final_kernel<<<1, 32, 0, st>>>(scratch, blocks, out);
     return LAUNCHED();
 }
+// flag[0] = 1 if any diagonal entry A(i, col_off + i) of the local row block is negative (or NaN): a negative diagonal entry
+// proves a negative eigenvalue (e_i^T A e_i < 0)
+__global__ void negative_diag_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int64_t col_off, int* flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows && !(A[i + (col_off + i) * lda] >= 0.0)) atomicExch(flag, 1);
+}
+cudaError_t check_negative_diag(const double* A, int64_t lda, int64_t rows, int64_t col_off, int* flag, cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    negative_diag_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(A, lda, rows, col_off, flag);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
 cudaError_t check_symmetric(const double* A, int64_t lda, int64_t n, int* flag, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     check_symmetric_kernel<<<grid_for(n * n, 256), 256, 0, st>>>(A, lda, n, flag);

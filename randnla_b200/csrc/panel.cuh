@@ -45,6 +45,8 @@ cudaError_t axpby_matrix(double a, const double* x, int64_t ldx, double b, const
 cudaError_t sumsq(const double* X, int64_t ld, int64_t rows, int64_t cols, double* out, double* scratch, int nscratch, cudaStream_t st);
 // exact symmetry test: flag[0] = 1 if any A(i,j) != A(j,i)   (reference lora_drivers.rs:106)
 cudaError_t check_symmetric(const double* A, int64_t lda, int64_t n, int* flag, cudaStream_t st);
+// flag[0] = 1 if a diagonal entry A(i, col_off + i), i < rows, is negative or NaN (necessary condition of PSD-ness, O(n))
+cudaError_t check_negative_diag(const double* A, int64_t lda, int64_t rows, int64_t col_off, int* flag, cudaStream_t st);
 // scale column j of X by s[j]
 cudaError_t scale_columns(double* X, int64_t ld, int64_t rows, int64_t cols, const double* s, cudaStream_t st);
 
