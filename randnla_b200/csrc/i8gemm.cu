@@ -26,6 +26,7 @@
 #include "gemm.cuh"
 #include "panel.cuh"
 #include "ptx.cuh"
+#include <cuda.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -72,6 +73,56 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pair (tcgen05 cta_group::2): two CTAs of a cluster on the two SMs of a TPC run ONE MMA of M = 256; each CTA supplies its own
+// 128 rows of the A operand and HALF of the columns of the B operand from its own shared memory, and holds the accumulators of its
+// own 128 rows in its own TMEM.  The leader (cluster rank 0) issues; commits are multicast to the same barrier in both CTAs.
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+// address of the barrier at the same offset in the leader's (rank 0) shared memory
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(ra) : "r"(smem_u32(p)));
+    return ra;
+}
+// tiled TMA loads of the pair: the bytes land in the executing CTA's shared memory, the transaction count is reported to a barrier
+// that may live in the peer (the leader's `full` barrier expects the bytes of both CTAs)
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_alloc2(uint32_t* smem_dst, uint32_t ncols) {         // the same warp of BOTH CTAs executes this
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {                               // arrives in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46)
 // LBO: stride between core matrices along the contraction dimension, SBO: along the M / N dimension
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -79,9 +130,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, M = 128, N = nmma (a multiple of 16)
-__host__ __device__ constexpr uint32_t instr_desc(bool a_mn_major, bool b_mn_major, int nmma) {
+__host__ __device__ constexpr uint32_t instr_desc(bool a_mn_major, bool b_mn_major, int nmma, int mmma = BM) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
-           ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(mmma >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------- splitting
@@ -280,7 +331,7 @@ slice_b_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int 
 // of `na` stages of 64 contraction indices (PU x 8 KB each).  The thin operand comes from L2 and is as large per stage as A (l ~ 128):
 // it gets a shallow ring of `nbs` half-stages of 32 indices, so that it costs 2-3 x PU x nb x 512 B of shared memory instead of
 // doubling every stage of A.  Warp 0 feeds the A ring, warp 6 the B ring, one lane of warp 1 issues the MMAs, warps 2-5 drain TMEM.
-constexpr int MAX_RING = 16;
+constexpr int MAX_RING = 16, MAX_RING2 = 24;
 // The MMAs of one K step of a sweep, decided at compile time: for every plane ta of A the planes tb of the thin operand whose group
 // g = ta + tb the sweep owns; neighbouring planes tb, tb + 1 go into ONE MMA of double width (accumulators g and g + 1 are
 // neighbours in TMEM) whenever both accumulators are in the same state (both already written in this accumulation, or both not):
@@ -465,6 +516,227 @@ i8_mma_kernel(const uint8_t* __restrict__ Aimg, int pst, int64_t cblocks, const 
     if (warp == 1) { tc_fence_after(); tc_dealloc(tmem, 512); }
 }
 
+// ---------------------------------------------------------------------------------------------- the CTA-pair MMA kernel
+// The single-CTA sweeps above are bound by what the SMs can take in from L2, and half of that traffic is the thin
+// operand: every 128-row tile of A re-reads all of it.  Here two CTAs of a cluster (the two SMs of a TPC) work on two neighbouring
+// tiles with ONE tcgen05.mma.cta_group::2 of M = 256 per digit pair: each CTA loads the planes of its own tile and only HALF of the
+// columns of the thin operand (23 % fewer bytes into the SMs per product at l = 110).
+//
+// Thin-operand images for the pair, K-major: [block of 32 k][rank 2][plane P][n group w8/8][k chunk 2][8 columns x 16 B of k].
+// Rank 0 holds columns [0, w8), rank 1 columns [w8, N), w8 = 8 ceil(N / 16).  A plane is w8 x 32 bytes, the MMA reads w = N_mma / 2 >= w8
+// columns of it (N_mma a multiple of 32): the n groups beyond w8 overlap the next plane -- whatever they hold only reaches the
+// accumulator columns [w8, w) and [w + w8, 2 w), which nobody reads.
+template <int P>
+__global__ void __launch_bounds__(256)
+slice_b2_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int w8, const double* __restrict__ rs, const double* __restrict__ cdown,
+                uint8_t* __restrict__ out) {
+    const int64_t kb = blockIdx.x;                          // 64 contraction indices = two image blocks
+    const int kq = threadIdx.x & 15;                        // four consecutive k: one 4-byte piece of a 16-byte row of a core matrix
+    const int kk = 4 * kq;
+    const int64_t k0 = kb * 64 + kk;
+    double rsk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) rsk[e] = (k0 + e < K) ? (rs ? rs[k0 + e] : 1.0) : 0.0;
+    const int plane = w8 * 32;
+    for (int c = threadIdx.x >> 4; c < 2 * w8; c += 16) {
+        const int rank = c >= w8 ? 1 : 0, lc = c - rank * w8;
+        unsigned wd[P];
+#pragma unroll
+        for (int t = 0; t < P; ++t) wd[t] = 0u;
+        if (c < N) {
+            const double cd = cdown[c];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int d[P];
+#pragma unroll
+                for (int t = 0; t < P; ++t) d[t] = 0;
+                if (k0 + e < K) digits<P>(X[k0 + e + (int64_t)c * ldx] * rsk[e], cd, d);
+#pragma unroll
+                for (int t = 0; t < P; ++t) wd[t] |= ((unsigned)d[t] & 0xffu) << (8 * e);
+            }
+        }
+        uint8_t* dst = out + (((kb * 2 + (kk >> 5)) * 2 + rank) * P) * (int64_t)plane + (lc >> 3) * 256 + ((kk & 31) >> 4) * 128 + (lc & 7) * 16 + (kk & 15);
+#pragma unroll
+        for (int t = 0; t < P; ++t) *reinterpret_cast<unsigned*>(dst + t * plane) = wd[t];
+    }
+}
+
+// all digit pairs of a sweep, one MMA each, on one step of 32 contraction indices; FRESH: the first step of an accumulation (the
+// first MMA into an accumulator overwrites it)
+constexpr int ASTEP = 4096;                  // one digit plane of a step (128 x 32)
+template <bool TN, int PU, int G0, int NG, bool FRESH>
+__device__ __forceinline__ void issue_step2(uint32_t tmem, uint32_t a_base, uint32_t b_base, uint32_t acc_cols, uint32_t bplane, uint32_t idesc) {
+    unsigned touched = FRESH ? 0u : 0xffu;
+#pragma unroll
+    for (int ta = 0; ta < PU; ++ta) {
+        // A S:   MN-major, step plane [I 8][J 4][128 B]:  K stride (J) 128, M stride (I) 512
+        // A^T Y: K-major,  step plane [I 2][J 16][128 B]: K stride (I) 2048, M stride (J) 128
+        const uint64_t ad = TN ? smem_desc(a_base + ta * ASTEP, 2048, 128) : smem_desc(a_base + ta * ASTEP, 128, 512);
+#pragma unroll
+        for (int tb = 0; tb < PU; ++tb) {
+            const int g = ta + tb - G0;
+            if (g < 0 || g >= NG) continue;
+            const uint64_t bd = smem_desc(b_base + tb * bplane, 128, 256);     // thin operand, K-major: k chunks 128 B apart, n groups 256 B apart
+            tc_mma2_i8(tmem + (uint32_t)g * acc_cols, ad, bd, idesc, (touched >> g) & 1u);
+            touched |= 1u << g;
+        }
+    }
+}
+// grid.x = 2 x pairs of tiles (cluster = blockIdx.x {2p, 2p + 1}); `tiles` = valid tiles (an odd count leaves a phantom that loads
+// the last tile again and stores nothing); w = columns of the thin operand each CTA feeds to the MMA (N_mma = 2 w), w8 = columns per
+// rank in the images.  Both operands advance in steps of 32 contraction indices (one MMA K step) through their own rings: what covers
+// the latency of a refill is the number of bytes in flight, (depth - 1) / depth of a ring, so the steps are as small as the MMA allows.
+// Barriers: the LEADER's fullA / fullB count the bytes of both CTAs' tiled TMA loads (cp.async.bulk.tensor with cta_group::2 may
+// report to a barrier in the peer); emptyA / emptyB / accum are committed by the leader's MMAs in both CTAs; the leader's `drained`
+// collects the epilogue warps of both.
+template <bool TN, int PU, int G0, int NG, bool ADD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMA_THREADS, 1)
+i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t cblocks, int64_t tiles, int w, int w8,
+               int na, int nbs, int pfd, int64_t kblocks_total, int64_t kblocks_per_chunk, int flush, double* __restrict__ C, int64_t ldc, int64_t rows,
+               int ncols, const double* __restrict__ rs_up, const double* __restrict__ cs_up, int64_t chunk_stride) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t bplane = (uint32_t)w8 * 32;                 // one plane of a step of this rank's columns
+    const uint32_t a_bytes = PU * ASTEP, b_bytes = PU * bplane;
+    uint8_t* bring = smem + (size_t)na * a_bytes;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(bring + (size_t)nbs * b_bytes + 512);     // 512: what the last plane's MMA window overlaps
+    uint64_t* emptyA = fullA + MAX_RING2;
+    uint64_t* fullB = emptyA + MAX_RING2;
+    uint64_t* emptyB = fullB + MAX_RING2;
+    uint64_t* accum = emptyB + MAX_RING2;
+    uint64_t* drained = accum + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int64_t tile_raw = blockIdx.x, tile = min(tile_raw, tiles - 1);
+    const int64_t kb0 = (int64_t)blockIdx.y * kblocks_per_chunk;
+    const int64_t kb1 = min(kblocks_total, kb0 + kblocks_per_chunk);
+    const int nk = (int)max((int64_t)0, kb1 - kb0);            // blocks of 64 contraction indices (the unit of the work split and of `flush`)
+    const int ns = 2 * nk;                                     // steps of 32
+    const int64_t gs0 = 2 * kb0;                               // first step
+    const int nflush = (nk + flush - 1) / flush;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < na; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); }
+        for (int s = 0; s < nbs; ++s) { mbar_init(fullB + s, 1); mbar_init(emptyB + s, 1); }
+        mbar_init(accum, 1);
+        mbar_init(drained, 8);
+        mbar_fence_init();
+    }
+    if (warp == 1) tc_alloc2(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                        // the peer's barriers exist before anything is signalled across
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // one tiled TMA load per step: all PU planes of this CTA's tile (A S: eight 512-byte runs per plane, A^T Y: 4 KB per plane)
+            int s = 0; uint32_t ph = 1;                         // parity of the `empty` phase to wait for: the first lap passes at once
+            for (int j = 0; j < ns; ++j) {
+                mbar_wait(emptyA + s, ph);
+                const int64_t gs = gs0 + j, blk2 = gs >> 2;
+                const int q = (int)(gs & 3);
+                if (rank == 0) mbar_arrive_expect_tx(fullA + s, 2 * a_bytes);         // the leader's barrier counts both CTAs' bytes
+                uint8_t* st = smem + (size_t)s * a_bytes;
+                if (TN) tma2_load_5d(st, &tmA, leader_addr(fullA + s), 0, 0, 2 * q, 0, (int)(blk2 * cblocks + tile));
+                else tma2_load_5d(st, &tmA, leader_addr(fullA + s), 0, q, 0, 0, (int)(tile * cblocks + blk2));
+                if (j + pfd < ns) {
+                    // experiments (RNLA_I8_PFD): ask L2 for the step `pfd` ahead
+                    const int64_t gp = gs + pfd, bp = gp >> 2;
+                    const int qp = (int)(gp & 3);
+                    if (TN) tma_prefetch_l2_5d(&tmA, 0, 0, 2 * qp, 0, (int)(bp * cblocks + tile));
+                    else tma_prefetch_l2_5d(&tmA, 0, qp, 0, 0, (int)(tile * cblocks + bp));
+                }
+                if (++s == na) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 1;
+            for (int j = 0; j < ns; ++j) {
+                mbar_wait(emptyB + s, ph);
+                if (rank == 0) mbar_arrive_expect_tx(fullB + s, 2 * b_bytes);
+                tma2_load_3d(bring + (size_t)s * b_bytes, &tmB, leader_addr(fullB + s), 0, 0, (int)((gs0 + j) * 2 + rank));   // the leading PU planes
+                if (++s == nbs) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = instr_desc(!TN, false, 2 * w, 2 * BM);
+            const uint32_t acc_cols = 2u * (uint32_t)w;
+            const int fsteps = 2 * flush;
+            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+            int since = 0, drains = 0;                          // steps since the last drain of the accumulators
+            for (int j = 0; j < ns; ++j) {
+                const bool fresh = since == 0;                  // first step of an accumulation: overwrite the accumulators
+                if (fresh && j > 0) {
+                    tc_commit2(accum);                          // everything issued so far -> the epilogue warps of both CTAs drain
+                    mbar_wait(drained, drains & 1);
+                    ++drains;
+                    tc_fence_after();
+                }
+                if (++since == fsteps) since = 0;
+                mbar_wait(fullA + sa, pha);
+                mbar_wait(fullB + sb, phb);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smem + (size_t)sa * a_bytes), b_base = smem_u32(bring + (size_t)sb * b_bytes);
+                if (fresh) issue_step2<TN, PU, G0, NG, true>(tmem, a_base, b_base, acc_cols, bplane, idesc);
+                else issue_step2<TN, PU, G0, NG, false>(tmem, a_base, b_base, acc_cols, bplane, idesc);
+                tc_commit2(emptyA + sa);
+                tc_commit2(emptyB + sb);
+                if (++sa == na) { sa = 0; pha ^= 1; }
+                if (++sb == nbs) { sb = 0; phb ^= 1; }
+            }
+            tc_commit2(accum);
+        }
+    } else {
+        const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
+        const int64_t r = tile_raw * BM + quad * 32 + lane;     // output row (A S) / output row = column of A (A^T Y)
+        const double rsc = (!TN && r < rows) ? rs_up[r] : 1.0;
+        double* out = C + (TN ? (int64_t)blockIdx.y * chunk_stride : 0);
+        if (nk <= 0 && !ADD && r < rows) for (int c = 0; c < ncols; ++c) out[r + (int64_t)c * ldc] = 0.0;
+        for (int f = 0; f < nflush; ++f) {
+            mbar_wait(accum, f & 1);
+            tc_fence_after();
+            for (int seg = 0; seg < 2; ++seg) {
+                const int cbase = seg * w8, cnt = min(ncols - cbase, w8);     // output columns [cbase, cbase + cnt) <- accumulator columns seg * w + ..
+                for (int c0 = 0; c0 < cnt; c0 += 16) {
+                    uint32_t d[NG][16];
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 2 * w + seg * w + c0), d[g]);
+                    tc_wait_ld();
+                    if (r < rows) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            if (c0 + e < cnt) {
+                                const int c = cbase + c0 + e;
+                                double v = (double)(int)d[NG - 1][e];
+#pragma unroll
+                                for (int g = NG - 2; g >= 0; --g) v = v * 0.00390625 + (double)(int)d[g][e];
+                                v *= 1.0 / (double)(1ull << (14 + 8 * G0));                     // 2^-(14 + 8 G0): weight of the sweep's first group
+                                if (!TN) v *= rsc * cs_up[c];
+                                double* o = out + r + (int64_t)c * ldc;
+                                if (ADD || f > 0) *o += v; else *o = v;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            if (f + 1 < nflush) {
+                __syncwarp();
+                if (lane == 0) { if (rank == 0) mbar_arrive(drained); else mbar_arrive_remote(drained, 0); }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                        // nobody leaves (or frees TMEM) while the pair's MMAs can still touch it
+    if (warp == 1) { tc_fence_after(); tc_dealloc2(tmem, 512); }
+}
+
 // Z(j, c) = cs_up(c) * sum over chunks, fixed order
 __global__ void __launch_bounds__(256)
 i8_tn_reduce_kernel(const double* __restrict__ P, int nchunks, int64_t chunk_stride, int64_t n, int ncols,
@@ -507,6 +779,19 @@ int g_planes = 4;             // precision of the next products: digit planes of
 bool g_all_pairs = false;     // ... and, for 4 planes, whether the second sweep (groups 4..6) runs
 int g_flush_override = 0;     // tests: drain the accumulators every this many stages (0: the exactness bound FLUSH_P*)
 
+// The CTA-pair kernels (tcgen05 cta_group::2) are the product path; RNLA_I8_PAIR=0 keeps the single-CTA sweeps for comparison runs.
+inline bool pair_enabled() {
+    static const bool on = [] { const char* e = getenv("RNLA_I8_PAIR"); return !(e && e[0] == '0'); }();
+    return on;
+}
+inline int pair_w8(int N) { return 8 * ((N + 15) / 16); }                 // thin-operand columns per rank in the images
+// columns per rank the MMA reads (N_mma = 2 w).  tcgen05.mma.cta_group::2.kind::i8 takes N in steps of 16 (w = w8: N_mma = 112 at
+// l = 110; CuTe's static_assert of N % 32 is a library limit -- all products are bit-identical to the CPU emulation at N_mma = 16, 48,
+// 80, 112, ... on the B200, tests/test_gpu_parity.py); RNLA_I8_N32=1 pads to a multiple of 32 (measured: 7.55 instead of 7.1 ms).
+inline int pair_w(int N) {
+    static const bool n32 = [] { const char* e = getenv("RNLA_I8_N32"); return e && e[0] == '1'; }();
+    return n32 ? 16 * ((pair_w8(N) + 15) / 16) : pair_w8(N);
+}
 template <int P>
 void launch_slice_b(const double* X, int64_t ldx, int64_t K, int N, int nb, const double* rs, int64_t kblocks, cudaStream_t st) {
     slice_b_kernel<P><<<(unsigned)kblocks, 256, 0, st>>>(X, ldx, K, N, nb, rs, g_sl.cdown.d(), g_sl.bimg.as<uint8_t>());
@@ -519,7 +804,13 @@ rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, int nb, cons
     colmax_kernel<<<dim3((unsigned)N, (unsigned)((K + rows_per - 1) / rows_per)), 256, 0, c.stream>>>(X, ldx, K, N, rs, rows_per,
                                                                                                       g_sl.cbits.as<unsigned long long>());
     scales_kernel<<<1, 128, 0, c.stream>>>(g_sl.cbits.as<unsigned long long>(), 128, g_sl.cup.d(), g_sl.cdown.d(), g_sl.flags.as<int>() + 1);
-    if (planes == 4) launch_slice_b<4>(X, ldx, K, N, nb, rs, kblocks, c.stream);
+    if (pair_enabled()) {
+        const int w8 = pair_w8(N);
+        uint8_t* out = g_sl.bimg.as<uint8_t>();
+        if (planes == 4) slice_b2_kernel<4><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
+        else if (planes == 6) slice_b2_kernel<6><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
+        else slice_b2_kernel<7><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
+    } else if (planes == 4) launch_slice_b<4>(X, ldx, K, N, nb, rs, kblocks, c.stream);
     else if (planes == 6) launch_slice_b<6>(X, ldx, K, N, nb, rs, kblocks, c.stream);
     else launch_slice_b<7>(X, ldx, K, N, nb, rs, kblocks, c.stream);
     g_kernel_launches += 3;
@@ -570,6 +861,85 @@ rnla_status launch_mma(dim3 grid, int nb, int64_t kblocks_total, int64_t per, in
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;
 }
+// ring sizes of the pair kernel: the thin operand's half-stages are PU x w8 x 32 bytes; four of them, A takes the rest
+constexpr size_t SMEM_FIXED2 = 1024 + 512 + 1024;                  // alignment slack + the MMA window past the last plane + barriers
+inline void mma2_rings(int pu, int w8, int* na, int* nbs) {
+    const size_t a = (size_t)pu * ASTEP, b = (size_t)pu * w8 * 32;
+    int s = 4;
+    if (const char* ov = getenv("RNLA_I8_NBS2")) { const int v = atoi(ov); if (v >= 2 && v <= MAX_RING2 && (SMEM_MAX - SMEM_FIXED2 - (size_t)v * b) / a >= 2) s = v; }
+    *nbs = s;
+    *na = (int)std::min<size_t>(MAX_RING2, (SMEM_MAX - SMEM_FIXED2 - (size_t)s * b) / a);
+}
+// Tensor maps over the images (elements: 8-byte words).  A: [block][plane][I 8][quarter 4][512 B]; a step (32 contraction indices) of
+// A S is the box (512 B, one quarter, all I, PU planes), a step of A^T Y the box (512 B, all quarters, two I, PU planes): ONE copy
+// instruction per step either way (separate 1 KB bulk copies are limited to 30 GB/s per SM by their per-instruction cost,
+// profiles/r02_ingest_rate.json).
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+inline rnla_status make_tensor_map(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return fail(RNLA_ERR_COMPUTATION, "int8 passes: cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, base, dims, strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RNLA_ERR_COMPUTATION, "int8 passes: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return RNLA_OK;
+}
+template <bool TN, int PU, int G0, int NG, bool ADD>
+rnla_status launch_mma2(dim3 grid, int N, int64_t kblocks_total, int64_t per, int flush, double* C, int64_t ldc, int64_t rows, int ncols,
+                        const double* rs_up, int64_t chunk_stride) {
+    Ctx& c = ctx();
+    Sliced& s = g_sl;
+    static bool attr = false;
+    if (!attr) {
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma2_kernel<TN, PU, G0, NG, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        attr = true;
+    }
+    const int w8 = pair_w8(N), w = pair_w(N);
+    int na, nbs;
+    mma2_rings(PU, w8, &na, &nbs);
+    const size_t smem = (size_t)na * PU * ASTEP + (size_t)nbs * PU * w8 * 32 + SMEM_FIXED2;
+    static const std::string kname = std::string("k:i8_mma<") + (TN ? "A^T B" : "A B") + ", planes " + std::to_string(PU) + ", groups " +
+                                     std::to_string(G0) + ".." + std::to_string(G0 + NG - 1) + ">";
+    const int64_t tiles = grid.x;
+    grid.x = (unsigned)(2 * ((tiles + 1) / 2));
+    CUtensorMap tmA, tmB;
+    {
+        const cuuint64_t dims[5] = {64, 4, 8, (cuuint64_t)s.planes, (cuuint64_t)(s.rblocks * s.cblocks)};
+        const cuuint64_t strides[4] = {512, 2048, (cuuint64_t)APLANE, (cuuint64_t)s.planes * APLANE};
+        const cuuint32_t box_nn[5] = {64, 1, 8, (cuuint32_t)PU, 1}, box_tn[5] = {64, 4, 2, (cuuint32_t)PU, 1};
+        RNLA_TRY(make_tensor_map(&tmA, s.img.p, 5, dims, strides, TN ? box_tn : box_nn));
+        // thin operand: [block of 32 k x rank][plane][w8 x 32 bytes]
+        const cuuint64_t bdims[3] = {(cuuint64_t)w8 * 4, (cuuint64_t)g_planes, (cuuint64_t)(4 * kblocks_total)};
+        const cuuint64_t bstrides[2] = {(cuuint64_t)w8 * 32, (cuuint64_t)g_planes * w8 * 32};
+        const cuuint32_t bbox[3] = {(cuuint32_t)w8 * 4, (cuuint32_t)PU, 1};
+        RNLA_TRY(make_tensor_map(&tmB, s.bimg.p, 3, bdims, bstrides, bbox));
+    }
+    int pfd = 1 << 30;                                          // L2 prefetch distance in stages (none)
+    if (const char* e = getenv("RNLA_I8_PFD")) { const int v = atoi(e); if (v > 0) pfd = v; }
+    kernel_phase_begin(kname.c_str());
+    i8_mma2_kernel<TN, PU, G0, NG, ADD><<<grid, MMA_THREADS, smem, c.stream>>>(
+        tmA, tmB, s.cblocks, tiles, w, w8, na, nbs, pfd, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, s.cup.d(), chunk_stride);
+    kernel_phase_end();
+    ++g_kernel_launches;
+    RNLA_CUDA(cudaGetLastError());
+    return RNLA_OK;
+}
+template <bool TN, int PU, int G0, int NG, bool ADD>
+rnla_status launch_sweep(dim3 grid, int nb, int N, int64_t kblocks_total, int64_t per, int flush, double* C, int64_t ldc, int64_t rows, int ncols,
+                         const double* rs_up, int64_t chunk_stride) {
+    if (pair_enabled()) return launch_mma2<TN, PU, G0, NG, ADD>(grid, N, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, chunk_stride);
+    return launch_mma<TN, PU, G0, NG, ADD>(grid, nb, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, chunk_stride);
+}
 // the sweeps of one product at the current precision
 template <bool TN>
 rnla_status run_sweeps(dim3 grid, int nb, int64_t kblocks_total, int64_t per, double* C, int64_t ldc, int64_t rows, int ncols,
@@ -579,12 +949,12 @@ rnla_status run_sweeps(dim3 grid, int nb, int64_t kblocks_total, int64_t per, do
     if (g_planes == 7) {
         // 28 pairs: groups 0..2 need planes 0..2 only (6 pairs), groups 3..6 all seven (22 pairs): 3 + 7 planes of each operand enter
         // the SMs per product instead of 4 + 7 -- the kernels are bound by the L2 -> SM traffic
-        RNLA_TRY((launch_mma<TN, 3, 0, 3, false>(grid, nb, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
-        return launch_mma<TN, 7, 3, 4, true>(grid, nb, kblocks_total, per, f7, C, ldc, rows, ncols, rs_up, chunk_stride);
+        RNLA_TRY((launch_sweep<TN, 3, 0, 3, false>(grid, nb, ncols, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
+        return launch_sweep<TN, 7, 3, 4, true>(grid, nb, ncols, kblocks_total, per, f7, C, ldc, rows, ncols, rs_up, chunk_stride);
     }
-    RNLA_TRY((launch_mma<TN, 4, 0, 4, false>(grid, nb, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
-    if (g_planes == 6) return launch_mma<TN, 6, 4, 2, true>(grid, nb, kblocks_total, per, f6, C, ldc, rows, ncols, rs_up, chunk_stride);
-    if (g_all_pairs) return launch_mma<TN, 4, 4, 3, true>(grid, nb, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride);
+    RNLA_TRY((launch_sweep<TN, 4, 0, 4, false>(grid, nb, ncols, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
+    if (g_planes == 6) return launch_sweep<TN, 6, 4, 2, true>(grid, nb, ncols, kblocks_total, per, f6, C, ldc, rows, ncols, rs_up, chunk_stride);
+    if (g_all_pairs) return launch_sweep<TN, 4, 4, 3, true>(grid, nb, ncols, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride);
     return RNLA_OK;
 }
 
@@ -722,6 +1092,22 @@ rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64
     return RNLA_OK;
 }
 
+// Row chunks of A^T Q for the pair kernel: (pairs of column tiles) x chunks units run on sms / 2 pair slots, every wave as long as one
+// chunk; pick the chunk count whose last wave is fullest, net of a per-chunk cost of about six stages (pipeline fill, epilogue).
+// Headline shape: 79 pairs x 14 chunks = 1106 units = 14.95 waves of 74.
+static int64_t pair_chunks(int64_t pairs, int64_t kblocks, int sms) {
+    const int64_t slots = std::max(1, sms / 2);
+    int64_t best = 1;
+    double best_eff = 0.0;
+    for (int64_t nc = 1; nc <= std::min<int64_t>(kblocks, 64); ++nc) {
+        const int64_t per = (kblocks + nc - 1) / nc;
+        if ((kblocks + per - 1) / per != nc) continue;
+        const int64_t waves = (pairs * nc + slots - 1) / slots;
+        const double eff = (double)(pairs * kblocks) / ((double)waves * (double)per * (double)slots) * (double)per / ((double)per + 6.0);
+        if (eff > best_eff * 1.005) { best_eff = eff; best = nc; }
+    }
+    return best;
+}
 // Z (n x N) = A^T * Q (m x N) on the split A (local rows only; the caller all-reduces)
 static rnla_status i8_gemm_tn_tile(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz) {
     Ctx& c = ctx();
@@ -731,6 +1117,7 @@ static rnla_status i8_gemm_tn_tile(const double* Q, int64_t ldq, int64_t N, doub
     RNLA_TRY(slice_b(Q, ldq, s.m, (int)N, nb, s.up.d(), kblocks, g_planes));
     // row chunks: enough (column block, chunk) units to fill the SMs a few times over; the partials are summed in chunk order
     int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>((4LL * c.sms + s.cblocks - 1) / s.cblocks, kblocks));
+    if (pair_enabled()) nchunks = pair_chunks((s.cblocks + 1) / 2, kblocks, c.sms);
     const int64_t per = (kblocks + nchunks - 1) / nchunks;
     nchunks = (kblocks + per - 1) / per;
     const int64_t stride = s.n * N;
