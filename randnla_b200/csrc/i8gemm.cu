@@ -564,21 +564,37 @@ slice_b2_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int
 // all digit pairs of a sweep, one MMA each, on one step of 32 contraction indices; FRESH: the first step of an accumulation (the
 // first MMA into an accumulator overwrites it)
 constexpr int ASTEP = 4096;                  // one digit plane of a step (128 x 32)
-template <bool TN, int PU, int G0, int NG, bool FRESH>
-__device__ __forceinline__ void issue_step2(uint32_t tmem, uint32_t a_base, uint32_t b_base, uint32_t acc_cols, uint32_t bplane, uint32_t idesc) {
+template <bool TN, int PU, int G0, int NG, bool WIDE, bool FRESH>
+__device__ __forceinline__ void issue_step2(uint32_t tmem, uint32_t a_base, uint32_t b_base, uint32_t w, uint32_t bplane, uint32_t idesc) {
+    static_assert(!WIDE || (NG % 2 == 0 && G0 + NG <= PU), "a pair of groups needs the partner plane tb + 1 < PU");
     unsigned touched = FRESH ? 0u : 0xffu;
 #pragma unroll
     for (int ta = 0; ta < PU; ++ta) {
         // A S:   MN-major, step plane [I 8][J 4][128 B]:  K stride (J) 128, M stride (I) 512
         // A^T Y: K-major,  step plane [I 2][J 16][128 B]: K stride (I) 2048, M stride (J) 128
         const uint64_t ad = TN ? smem_desc(a_base + ta * ASTEP, 2048, 128) : smem_desc(a_base + ta * ASTEP, 128, 512);
+        if constexpr (WIDE) {
+            // One MMA of double width per (plane of A, PAIR of groups 2 p, 2 p + 1): the thin operand's planes tb, tb + 1 are neighbours
+            // along N in shared memory, and each CTA's half of the N = 4 w columns is [plane tb: w][plane tb + 1: w], so the accumulators
+            // of a pair of groups sit as [rank 0: g, g + 1][rank 1: g, g + 1].  A is read from shared memory 12 instead of 22 times per
+            // step.  A group without a partner plane (tb = -1) multiplies the zero plane that precedes plane 0 in every slot.
 #pragma unroll
-        for (int tb = 0; tb < PU; ++tb) {
-            const int g = ta + tb - G0;
-            if (g < 0 || g >= NG) continue;
-            const uint64_t bd = smem_desc(b_base + tb * bplane, 128, 256);     // thin operand, K-major: k chunks 128 B apart, n groups 256 B apart
-            tc_mma2_i8(tmem + (uint32_t)g * acc_cols, ad, bd, idesc, (touched >> g) & 1u);
-            touched |= 1u << g;
+            for (int pi = 0; pi < NG / 2; ++pi) {
+                const int tb = G0 + 2 * pi - ta;                 // plane of group 2 pi; group 2 pi + 1 takes plane tb + 1
+                if (tb + 1 < 0 || tb >= PU) continue;
+                const uint64_t bd = smem_desc(b_base + (tb + 1) * bplane, 128, 256);     // slot = [zero plane][plane 0] ... [plane PU - 1]
+                tc_mma2_i8(tmem + (uint32_t)pi * 4u * w, ad, bd, idesc, (touched >> pi) & 1u);
+                touched |= 1u << pi;
+            }
+        } else {
+#pragma unroll
+            for (int tb = 0; tb < PU; ++tb) {
+                const int g = ta + tb - G0;
+                if (g < 0 || g >= NG) continue;
+                const uint64_t bd = smem_desc(b_base + (tb + 1) * bplane, 128, 256);     // thin operand, K-major: k chunks 128 B apart, n groups 256 B apart
+                tc_mma2_i8(tmem + (uint32_t)g * 2u * w, ad, bd, idesc, (touched >> g) & 1u);
+                touched |= 1u << g;
+            }
         }
     }
 }
@@ -589,17 +605,18 @@ __device__ __forceinline__ void issue_step2(uint32_t tmem, uint32_t a_base, uint
 // Barriers: the LEADER's fullA / fullB count the bytes of both CTAs' tiled TMA loads (cp.async.bulk.tensor with cta_group::2 may
 // report to a barrier in the peer); emptyA / emptyB / accum are committed by the leader's MMAs in both CTAs; the leader's `drained`
 // collects the epilogue warps of both.
-template <bool TN, int PU, int G0, int NG, bool ADD>
+template <bool TN, int PU, int G0, int NG, bool ADD, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMA_THREADS, 1)
-i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t cblocks, int64_t tiles, int w, int w8,
+i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t cblocks, int64_t tiles, int w8,
                int na, int nbs, int pfd, int64_t kblocks_total, int64_t kblocks_per_chunk, int flush, double* __restrict__ C, int64_t ldc, int64_t rows,
                int ncols, const double* __restrict__ rs_up, const double* __restrict__ cs_up, int64_t chunk_stride) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t bplane = (uint32_t)w8 * 32;                 // one plane of a step of this rank's columns
-    const uint32_t a_bytes = PU * ASTEP, b_bytes = PU * bplane;
+    const uint32_t a_bytes = PU * ASTEP, b_bytes = PU * bplane, b_slot = (PU + 1) * bplane;   // slot of the thin operand: [zero plane][PU planes]
+    const int w = w8;                                          // columns per rank the MMA reads: N_mma = 2 w (4 w for a pair of groups)
     uint8_t* bring = smem + (size_t)na * a_bytes;
-    uint64_t* fullA = reinterpret_cast<uint64_t*>(bring + (size_t)nbs * b_bytes + 512);     // 512: what the last plane's MMA window overlaps
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(bring + (size_t)nbs * b_slot);
     uint64_t* emptyA = fullA + MAX_RING2;
     uint64_t* fullB = emptyA + MAX_RING2;
     uint64_t* emptyB = fullB + MAX_RING2;
@@ -624,6 +641,9 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_fence_init();
     }
     if (warp == 1) tc_alloc2(tmem_slot, 512);
+    for (int s = 0; s < nbs; ++s)                              // the zero planes (never written again)
+        for (uint32_t q = threadIdx.x * 16; q < bplane; q += MMA_THREADS * 16) *reinterpret_cast<uint4*>(bring + (size_t)s * b_slot + q) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's reads
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                        // the peer's barriers exist before anything is signalled across
@@ -658,14 +678,13 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < ns; ++j) {
                 mbar_wait(emptyB + s, ph);
                 if (rank == 0) mbar_arrive_expect_tx(fullB + s, 2 * b_bytes);
-                tma2_load_3d(bring + (size_t)s * b_bytes, &tmB, leader_addr(fullB + s), 0, 0, (int)((gs0 + j) * 2 + rank));   // the leading PU planes
+                tma2_load_3d(bring + (size_t)s * b_slot + bplane, &tmB, leader_addr(fullB + s), 0, 0, (int)((gs0 + j) * 2 + rank));   // the leading PU planes
                 if (++s == nbs) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = instr_desc(!TN, false, 2 * w, 2 * BM);
-            const uint32_t acc_cols = 2u * (uint32_t)w;
+            const uint32_t idesc = instr_desc(!TN, false, (WIDE ? 4 : 2) * w, 2 * BM);
             const int fsteps = 2 * flush;
             int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
             int since = 0, drains = 0;                          // steps since the last drain of the accumulators
@@ -681,9 +700,9 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(fullA + sa, pha);
                 mbar_wait(fullB + sb, phb);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(smem + (size_t)sa * a_bytes), b_base = smem_u32(bring + (size_t)sb * b_bytes);
-                if (fresh) issue_step2<TN, PU, G0, NG, true>(tmem, a_base, b_base, acc_cols, bplane, idesc);
-                else issue_step2<TN, PU, G0, NG, false>(tmem, a_base, b_base, acc_cols, bplane, idesc);
+                const uint32_t a_base = smem_u32(smem + (size_t)sa * a_bytes), b_base = smem_u32(bring + (size_t)sb * b_slot);
+                if (fresh) issue_step2<TN, PU, G0, NG, WIDE, true>(tmem, a_base, b_base, (uint32_t)w, bplane, idesc);
+                else issue_step2<TN, PU, G0, NG, WIDE, false>(tmem, a_base, b_base, (uint32_t)w, bplane, idesc);
                 tc_commit2(emptyA + sa);
                 tc_commit2(emptyB + sb);
                 if (++sa == na) { sa = 0; pha ^= 1; }
@@ -705,7 +724,8 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int c0 = 0; c0 < cnt; c0 += 16) {
                     uint32_t d[NG][16];
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 2 * w + seg * w + c0), d[g]);
+                    for (int g = 0; g < NG; ++g)       // WIDE: pairs of groups as [rank 0: g, g + 1][rank 1: g, g + 1]; else [rank 0: g][rank 1: g]
+                        tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)((WIDE ? (g >> 1) * 4 * w + seg * 2 * w + (g & 1) * w : g * 2 * w + seg * w) + c0), d[g]);
                     tc_wait_ld();
                     if (r < rows) {
 #pragma unroll
@@ -785,13 +805,9 @@ inline bool pair_enabled() {
     return on;
 }
 inline int pair_w8(int N) { return 8 * ((N + 15) / 16); }                 // thin-operand columns per rank in the images
-// columns per rank the MMA reads (N_mma = 2 w).  tcgen05.mma.cta_group::2.kind::i8 takes N in steps of 16 (w = w8: N_mma = 112 at
-// l = 110; CuTe's static_assert of N % 32 is a library limit -- all products are bit-identical to the CPU emulation at N_mma = 16, 48,
-// 80, 112, ... on the B200, tests/test_gpu_parity.py); RNLA_I8_N32=1 pads to a multiple of 32 (measured: 7.55 instead of 7.1 ms).
-inline int pair_w(int N) {
-    static const bool n32 = [] { const char* e = getenv("RNLA_I8_N32"); return e && e[0] == '1'; }();
-    return n32 ? 16 * ((pair_w8(N) + 15) / 16) : pair_w8(N);
-}
+// tcgen05.mma.cta_group::2.kind::i8 takes N in steps of 16: the MMA reads exactly the w8 columns per rank that the images hold
+// (N_mma = 112 at l = 110; CuTe's static_assert of N % 32 is a library limit -- the products are bit-identical to the CPU emulation
+// at N_mma = 16, 48, 80, 112, ... on the B200, tests/test_gpu_parity.py).
 template <int P>
 void launch_slice_b(const double* X, int64_t ldx, int64_t K, int N, int nb, const double* rs, int64_t kblocks, cudaStream_t st) {
     slice_b_kernel<P><<<(unsigned)kblocks, 256, 0, st>>>(X, ldx, K, N, nb, rs, g_sl.cdown.d(), g_sl.bimg.as<uint8_t>());
@@ -862,9 +878,9 @@ rnla_status launch_mma(dim3 grid, int nb, int64_t kblocks_total, int64_t per, in
     return RNLA_OK;
 }
 // ring sizes of the pair kernel: the thin operand's half-stages are PU x w8 x 32 bytes; four of them, A takes the rest
-constexpr size_t SMEM_FIXED2 = 1024 + 512 + 1024;                  // alignment slack + the MMA window past the last plane + barriers
+constexpr size_t SMEM_FIXED2 = 1024 + 1024;                        // alignment slack + barriers
 inline void mma2_rings(int pu, int w8, int* na, int* nbs) {
-    const size_t a = (size_t)pu * ASTEP, b = (size_t)pu * w8 * 32;
+    const size_t a = (size_t)pu * ASTEP, b = (size_t)(pu + 1) * w8 * 32;
     int s = 4;
     if (const char* ov = getenv("RNLA_I8_NBS2")) { const int v = atoi(ov); if (v >= 2 && v <= MAX_RING2 && (SMEM_MAX - SMEM_FIXED2 - (size_t)v * b) / a >= 2) s = v; }
     *nbs = s;
@@ -901,13 +917,18 @@ rnla_status launch_mma2(dim3 grid, int N, int64_t kblocks_total, int64_t per, in
     Sliced& s = g_sl;
     static bool attr = false;
     if (!attr) {
-        RNLA_CUDA(cudaFuncSetAttribute(i8_mma2_kernel<TN, PU, G0, NG, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma2_kernel<TN, PU, G0, NG, ADD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma2_kernel<TN, PU, G0, NG, ADD, NG % 2 == 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         attr = true;
     }
-    const int w8 = pair_w8(N), w = pair_w(N);
+    const int w8 = pair_w8(N);
     int na, nbs;
     mma2_rings(PU, w8, &na, &nbs);
-    const size_t smem = (size_t)na * PU * ASTEP + (size_t)nbs * PU * w8 * 32 + SMEM_FIXED2;
+    const size_t smem = (size_t)na * PU * ASTEP + (size_t)nbs * (PU + 1) * w8 * 32 + SMEM_FIXED2;
+    // pairs of groups in one MMA of double width where the sweep has an even number of groups and the accumulators fit (4 w8 <= 256)
+    constexpr bool WIDE = NG % 2 == 0;
+    static const bool wide_on = [] { const char* e = getenv("RNLA_I8_WIDE"); return !(e && e[0] == '0'); }();
+    const bool wide = WIDE && wide_on && 4 * w8 <= 256;
     static const std::string kname = std::string("k:i8_mma<") + (TN ? "A^T B" : "A B") + ", planes " + std::to_string(PU) + ", groups " +
                                      std::to_string(G0) + ".." + std::to_string(G0 + NG - 1) + ">";
     const int64_t tiles = grid.x;
@@ -927,8 +948,12 @@ rnla_status launch_mma2(dim3 grid, int N, int64_t kblocks_total, int64_t per, in
     int pfd = 1 << 30;                                          // L2 prefetch distance in stages (none)
     if (const char* e = getenv("RNLA_I8_PFD")) { const int v = atoi(e); if (v > 0) pfd = v; }
     kernel_phase_begin(kname.c_str());
-    i8_mma2_kernel<TN, PU, G0, NG, ADD><<<grid, MMA_THREADS, smem, c.stream>>>(
-        tmA, tmB, s.cblocks, tiles, w, w8, na, nbs, pfd, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, s.cup.d(), chunk_stride);
+    if (wide)
+        i8_mma2_kernel<TN, PU, G0, NG, ADD, WIDE><<<grid, MMA_THREADS, smem, c.stream>>>(
+            tmA, tmB, s.cblocks, tiles, w8, na, nbs, pfd, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, s.cup.d(), chunk_stride);
+    else
+        i8_mma2_kernel<TN, PU, G0, NG, ADD, false><<<grid, MMA_THREADS, smem, c.stream>>>(
+            tmA, tmB, s.cblocks, tiles, w8, na, nbs, pfd, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, s.cup.d(), chunk_stride);
     kernel_phase_end();
     ++g_kernel_launches;
     RNLA_CUDA(cudaGetLastError());
