@@ -586,7 +586,7 @@ def run_ours(args):
         t_ms = kernels[dom]
         mean_pass = float(np.mean(list(pass_ms.values())))
         roofline = {
-            "bound": "tensor", "kernel": dom[2:] + " (tcgen05.mma kind::i8, TMEM int32 accumulators, cp.async.bulk of pre-tiled digit planes)",
+            "bound": "tensor", "kernel": dom[2:] + " (CTA pairs: tcgen05.mma.cta_group::2 kind::i8 with M = 256, TMEM int32 accumulators, tiled TMA loads of the pre-tiled digit planes)",
             "achieved": ops / (t_ms * 1e-3) * 1e-12, "peak": i8_sust.value, "unit": "TFLOP/s", "frac": ops / (t_ms * 1e-3) * 1e-12 / i8_sust.value,
             "peak_source": "int8 tensor-core rate measured live by rnla_measure_int8_roof on this GPU, 0.25 s back-to-back under the power cap "
                            "(MEASURED_PEAKS.json holds bf16 only; int8 dense = 2 x bf16 on this part)",

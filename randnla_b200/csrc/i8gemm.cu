@@ -13,9 +13,11 @@
 // block of A and per plane [I 8][J 16][8 x 16 B] (I: 16-row group, J: 8-column group; a core matrix holds 16 rows x 8 columns of A
 // as 8 rows (columns of A) of 16 bytes (rows of A)).  The same 128 bytes are an MN-major core matrix of A S (contraction over
 // columns) and a K-major one of A^T Y (contraction over rows); because the descriptors take both strides, ONE arrangement serves
-// both passes: a stage of A^T Y is one contiguous 8 KB bulk copy per plane, a stage of A S eight 1 KB copies per plane.
+// both passes, and one tiled TMA load (cp.async.bulk.tensor over a 5-D view of the images) fetches a step of either.
 //
-// TMEM holds four 128-column int32 accumulators, so a product is at most two sweeps over the images:
+// The sweeps run as CTA PAIRS (tcgen05.mma.cta_group::2, M = 256 over the two SMs of a TPC): each CTA holds its own 128-row tile of A
+// and half of the thin operand's columns.  TMEM holds four 112-column int32 accumulators per CTA at l = 110, so a product is at most two
+// sweeps over the images:
 //   4 planes: groups 0..3 (10 pairs; 31-bit operands, result to ~2^-27), optionally groups 4..6 (6 pairs)
 //   6 planes: groups 0..3 on planes 0..3 + groups 4, 5 on planes 0..5 (11 pairs)
 //   7 planes: groups 0..2 on planes 0..2 (6 pairs) + groups 3..6 on all seven planes (22 pairs): the product of the 55-bit
@@ -37,34 +39,15 @@ namespace rnla {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;   // CTA tile: 128 x (<= 128) outputs, 64 contraction indices per stage
+constexpr int BM = 128, BN = 128;            // CTA tile: 128 x (<= 128) outputs; the work split and `flush` count blocks of 64 contraction indices
 constexpr int APLANE = 16384;                // one digit plane of a 128 x 128 block of A
-constexpr int ASTAGE = 8192;                 // one digit plane of a stage (128 x 64)
 constexpr int MMA_THREADS = 224;             // warp 0 A producer, warp 1 MMA issuer, warps 2-5 epilogue, warp 6 B producer
 // stages of 64 contraction indices per int32 accumulation (worst group of the sweep, |d_0| <= 64, |d_t| <= 128)
 constexpr int FLUSH_P4 = 682, FLUSH_P6 = 408, FLUSH_P7 = 340;
 
 // ---------------------------------------------------------------------------------------------- tcgen05 wrappers
-__device__ __forceinline__ void tc_alloc(uint32_t* smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], int8 x int8 -> int32
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
@@ -287,235 +270,6 @@ colmax_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, const
         atomicMax(bits + c, (unsigned long long)__double_as_longlong(mx));
     }
 }
-// thin-operand images: [k block of 32][k group 4][plane P][n block nb][8 x 16 B]; columns >= N and rows >= K are zero.  The planes of a
-// k group are adjacent so that ONE MMA of width 2 x 16 nb can multiply a plane of A by two neighbouring planes tb, tb + 1 at once.
-template <int P>
-__global__ void __launch_bounds__(256)
-slice_b_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int nb, const double* __restrict__ rs, const double* __restrict__ cdown,
-               uint8_t* __restrict__ out) {
-    const int64_t kb = blockIdx.x;                          // 64 contraction indices = two image blocks
-    const int kl = threadIdx.x & 63;
-    const int64_t k = kb * 64 + kl;
-    const double rsk = (k < K) ? (rs ? rs[k] : 1.0) : 0.0;
-    const int plane = nb * 128;                             // one plane of one k group
-    uint8_t* dst = out + (kb * 2 + (kl >> 5)) * (int64_t)(P * nb * 512);
-    for (int cq = threadIdx.x >> 6; cq < 4 * nb; cq += 4) {
-        const int c0 = 4 * cq;
-        unsigned w[P];
-#pragma unroll
-        for (int t = 0; t < P; ++t) w[t] = 0u;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = c0 + e;
-            int d[P];
-#pragma unroll
-            for (int t = 0; t < P; ++t) d[t] = 0;
-            if (k < K && c < N) digits<P>(X[k + (int64_t)c * ldx] * rsk, cdown[c], d);
-#pragma unroll
-            for (int t = 0; t < P; ++t) w[t] |= ((unsigned)d[t] & 0xffu) << (8 * e);
-        }
-        const int intra = ((kl & 31) >> 3) * (P * plane) + (c0 >> 4) * 128 + (kl & 7) * 16 + (c0 & 15);
-#pragma unroll
-        for (int t = 0; t < P; ++t) *reinterpret_cast<unsigned*>(dst + t * plane + intra) = w[t];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- the MMA kernel
-// One sweep: digit pairs (ta, tb), ta, tb < PU, with G0 <= ta + tb < G0 + NG into NG TMEM accumulators.
-// TN = false:  C(rows tile*128.., :) (+)= rs_up(i) cs_up(c) 2^{-(14+8 G0)} sum_g 2^{-8(g-G0)} D_g,  contraction over all blocks of 64 columns
-// TN = true :  P[chunk](cols tile*128.., :) (+)= 2^{-(14+8 G0)} sum_g ...,                          contraction over this chunk's blocks of 64 rows
-// ADD: the sweep adds to what an earlier sweep of the same product wrote.  Every `flush` stages the accumulators are drained into
-// the output (the first drain stores unless ADD), which keeps the int32 sums exact for any contraction length.
-//
-// Two decoupled shared-memory rings.  The planes of A come from HBM: what hides its latency is bytes in flight, so A gets a deep ring
-// of `na` stages of 64 contraction indices (PU x 8 KB each).  The thin operand comes from L2 and is as large per stage as A (l ~ 128):
-// it gets a shallow ring of `nbs` half-stages of 32 indices, so that it costs 2-3 x PU x nb x 512 B of shared memory instead of
-// doubling every stage of A.  Warp 0 feeds the A ring, warp 6 the B ring, one lane of warp 1 issues the MMAs, warps 2-5 drain TMEM.
-constexpr int MAX_RING = 16, MAX_RING2 = 24;
-// The MMAs of one K step of a sweep, decided at compile time: for every plane ta of A the planes tb of the thin operand whose group
-// g = ta + tb the sweep owns; neighbouring planes tb, tb + 1 go into ONE MMA of double width (accumulators g and g + 1 are
-// neighbours in TMEM) whenever both accumulators are in the same state (both already written in this accumulation, or both not):
-// A is then read from shared memory 6 instead of 10 times per K step in the LO sweep, 12 instead of 18 times in HI7.
-// FRESH: the first K step of an accumulation, where the first MMA into an accumulator overwrites it.
-template <int PU, int G0, int NG, bool FRESH>
-struct Sched {
-    int n = 0;
-    int ta[32], tb[32], wide[32], acc[32];
-    constexpr Sched() : ta{}, tb{}, wide{}, acc{} {
-        unsigned touched = FRESH ? 0u : 0xffu;
-        for (int a = 0; a < PU; ++a)
-            for (int b = 0; b < PU; ++b) {
-                const int g = a + b;
-                if (g < G0 || g >= G0 + NG) continue;
-                const unsigned m1 = 1u << (g - G0), m2 = 3u << (g - G0);
-                const bool can2 = b + 1 < PU && g + 1 < G0 + NG && ((touched & m2) == 0u || (touched & m2) == m2);
-                const unsigned mk = can2 ? m2 : m1;
-                ta[n] = a; tb[n] = b; wide[n] = can2 ? 1 : 0; acc[n] = (touched & mk) ? 1 : 0;
-                touched |= mk;
-                ++n;
-                if (can2) ++b;
-            }
-    }
-};
-template <bool TN, class S>
-__device__ __forceinline__ void issue_kstep(uint32_t tmem, uint32_t a_base, uint32_t b_base, int ks, int nb, int pu, int g0, uint32_t idesc1,
-                                            uint32_t idesc2) {
-    constexpr S sc{};
-    const uint32_t aw = (uint32_t)nb * 16;                      // TMEM columns per accumulator
-#pragma unroll
-    for (int i = 0; i < sc.n; ++i) {
-        // A S:   MN-major, stage plane [I 8][J 8][128 B]:  32 columns = 4 J = 512 B;  K stride (J) 128, M stride (I) 1024
-        // A^T Y: K-major,  stage plane [I 4][J 16][128 B]: 32 rows = 2 I = 4096 B;   K stride (I) 2048, M stride (J) 128
-        const uint64_t ad = TN ? smem_desc(a_base + sc.ta[i] * ASTAGE + ks * 4096, 2048, 128)
-                               : smem_desc(a_base + sc.ta[i] * ASTAGE + ks * 512, 128, 1024);
-        // thin operand: MN-major, half-stage [k group 4][plane PU][n block nb][128 B]: planes tb, tb + 1 are adjacent along N
-        const uint64_t bd = smem_desc(b_base + sc.tb[i] * nb * 128, pu * nb * 128, 128);
-        tc_mma_i8(tmem + (uint32_t)(sc.ta[i] + sc.tb[i] - g0) * aw, ad, bd, sc.wide[i] ? idesc2 : idesc1, (uint32_t)sc.acc[i]);
-    }
-}
-template <bool TN, int PU, int G0, int NG, bool ADD>
-__global__ void __launch_bounds__(MMA_THREADS, 1)
-i8_mma_kernel(const uint8_t* __restrict__ Aimg, int pst, int64_t cblocks, const uint8_t* __restrict__ Bimg, int pb, int nb, int na, int nbs,
-              int64_t kblocks_total, int64_t kblocks_per_chunk, int flush, double* __restrict__ C, int64_t ldc, int64_t rows, int ncols,
-              const double* __restrict__ rs_up, const double* __restrict__ cs_up, int64_t chunk_stride) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int bplane = nb * 512;                               // one plane of a half-stage of the thin operand
-    const uint32_t a_bytes = PU * ASTAGE, b_bytes = (uint32_t)(PU * bplane);
-    uint8_t* bring = smem + (size_t)na * a_bytes;
-    uint64_t* fullA = reinterpret_cast<uint64_t*>(bring + (size_t)nbs * b_bytes);
-    uint64_t* emptyA = fullA + MAX_RING;
-    uint64_t* fullB = emptyA + MAX_RING;
-    uint64_t* emptyB = fullB + 4;
-    uint64_t* accum = emptyB + 4;
-    uint64_t* drained = accum + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tile = blockIdx.x;
-    const int64_t kb0 = (int64_t)blockIdx.y * kblocks_per_chunk;
-    const int64_t kb1 = min(kblocks_total, kb0 + kblocks_per_chunk);
-    const int nk = (int)(kb1 - kb0);
-    const int nflush = (nk + flush - 1) / flush;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < na; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); }
-        for (int s = 0; s < nbs; ++s) { mbar_init(fullB + s, 1); mbar_init(emptyB + s, 1); }
-        mbar_init(accum, 1);
-        mbar_init(drained, 4);
-        mbar_fence_init();
-    }
-    if (warp == 1) tc_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 0) {
-        int s = 0; uint32_t ph = 1;                            // parity of the `empty` phase to wait for: the first lap passes at once
-        for (int it = 0; it < nk; ++it) {
-            mbar_wait(emptyA + s, ph);
-            const int64_t kb = kb0 + it, blk2 = kb >> 1;
-            const int h = (int)(kb & 1);
-            uint8_t* st = smem + (size_t)s * a_bytes;
-            if (lane == 0) mbar_arrive_expect_tx(fullA + s, a_bytes);
-            __syncwarp();
-            if (TN) {
-                // stage = 128 columns (tile) x 64 rows (half h of row block blk2): [I 4][J 16][128 B] = 8 KB contiguous per plane
-                const uint8_t* src = Aimg + ((blk2 * cblocks + tile) * pst) * (int64_t)APLANE + h * ASTAGE;
-                if (lane < PU) bulk_g2s(st + lane * ASTAGE, src + (int64_t)lane * APLANE, ASTAGE, fullA + s);
-            } else {
-                // stage = 128 rows (tile) x 64 columns (half h of column block blk2): per plane and 16-row group I one 1 KB run
-                const uint8_t* src = Aimg + ((tile * cblocks + blk2) * pst) * (int64_t)APLANE + h * 1024;
-                for (int q = lane; q < PU * 8; q += 32)
-                    bulk_g2s(st + (q >> 3) * ASTAGE + (q & 7) * 1024, src + (int64_t)(q >> 3) * APLANE + (q & 7) * 2048, 1024, fullA + s);
-            }
-            if (++s == na) { s = 0; ph ^= 1; }
-        }
-    } else if (warp == 6) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 1;
-            const uint8_t* src = Bimg + 2 * kb0 * (int64_t)(pb * bplane);
-            for (int j = 0; j < 2 * nk; ++j) {
-                mbar_wait(emptyB + s, ph);
-                mbar_arrive_expect_tx(fullB + s, b_bytes);
-                uint8_t* dst = bring + (size_t)s * b_bytes;
-                const uint8_t* blk = src + (int64_t)j * (pb * bplane);
-                if (pb == PU) bulk_g2s(dst, blk, b_bytes, fullB + s);
-                else                                            // the leading PU planes of each of the four k groups
-                    for (int kg = 0; kg < 4; ++kg) bulk_g2s(dst + kg * (PU * nb * 128), blk + kg * (pb * nb * 128), PU * nb * 128, fullB + s);
-                if (++s == nbs) { s = 0; ph ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc1 = instr_desc(!TN, true, nb * 16), idesc2 = instr_desc(!TN, true, 2 * nb * 16);
-            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
-            int since = 0, drains = 0;                          // stages since the last drain of the accumulators
-            for (int it = 0; it < nk; ++it) {
-                const bool fresh = since == 0;                  // first stage of an accumulation: overwrite the accumulators
-                if (fresh && it > 0) {
-                    tc_commit(accum);                           // everything issued so far -> the epilogue warps drain
-                    mbar_wait(drained, drains & 1);
-                    ++drains;
-                    tc_fence_after();
-                }
-                if (++since == flush) since = 0;
-                mbar_wait(fullA + sa, pha);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(smem + (size_t)sa * a_bytes);
-#pragma unroll
-                for (int ks = 0; ks < BK / 32; ++ks) {
-                    mbar_wait(fullB + sb, phb);
-                    tc_fence_after();
-                    const uint32_t b_base = smem_u32(bring + (size_t)sb * b_bytes);
-                    if (fresh && ks == 0) issue_kstep<TN, Sched<PU, G0, NG, true>>(tmem, a_base, b_base, ks, nb, PU, G0, idesc1, idesc2);
-                    else issue_kstep<TN, Sched<PU, G0, NG, false>>(tmem, a_base, b_base, ks, nb, PU, G0, idesc1, idesc2);
-                    tc_commit(emptyB + sb);
-                    if (++sb == nbs) { sb = 0; phb ^= 1; }
-                }
-                tc_commit(emptyA + sa);
-                if (++sa == na) { sa = 0; pha ^= 1; }
-            }
-            tc_commit(accum);
-        }
-    } else {
-        const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
-        const int64_t r = tile * BM + quad * 32 + lane;     // output row (A S) / output row = column of A (A^T Y)
-        const double rsc = (!TN && r < rows) ? rs_up[r] : 1.0;
-        double* out = C + (TN ? (int64_t)blockIdx.y * chunk_stride : 0);
-        if (nk <= 0 && !ADD && r < rows) for (int c = 0; c < ncols; ++c) out[r + (int64_t)c * ldc] = 0.0;
-        for (int f = 0; f < nflush; ++f) {
-            mbar_wait(accum, f & 1);
-            tc_fence_after();
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
-                uint32_t d[NG][16];
-#pragma unroll
-                for (int g = 0; g < NG; ++g) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * nb * 16 + c0), d[g]);
-                tc_wait_ld();
-                if (r < rows) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int c = c0 + e;
-                        if (c < ncols) {
-                            double v = (double)(int)d[NG - 1][e];
-#pragma unroll
-                            for (int g = NG - 2; g >= 0; --g) v = v * 0.00390625 + (double)(int)d[g][e];
-                            v *= 1.0 / (double)(1ull << (14 + 8 * G0));                         // 2^-(14 + 8 G0): weight of the sweep's first group
-                            if (!TN) v *= rsc * cs_up[c];
-                            double* o = out + r + (int64_t)c * ldc;
-                            if (ADD || f > 0) *o += v; else *o = v;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            if (f + 1 < nflush) { __syncwarp(); if (lane == 0) mbar_arrive(drained); }
-        }
-    }
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tc_dealloc(tmem, 512); }
-}
-
 // ---------------------------------------------------------------------------------------------- the CTA-pair MMA kernel
 // The single-CTA sweeps above are bound by what the SMs can take in from L2, and half of that traffic is the thin
 // operand: every 128-row tile of A re-reads all of it.  Here two CTAs of a cluster (the two SMs of a TPC) work on two neighbouring
@@ -564,6 +318,7 @@ slice_b2_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int
 // all digit pairs of a sweep, one MMA each, on one step of 32 contraction indices; FRESH: the first step of an accumulation (the
 // first MMA into an accumulator overwrites it)
 constexpr int ASTEP = 4096;                  // one digit plane of a step (128 x 32)
+constexpr int MAX_RING2 = 24;                // slots per ring (barrier arrays)
 template <bool TN, int PU, int G0, int NG, bool WIDE, bool FRESH>
 __device__ __forceinline__ void issue_step2(uint32_t tmem, uint32_t a_base, uint32_t b_base, uint32_t w, uint32_t bplane, uint32_t idesc) {
     static_assert(!WIDE || (NG % 2 == 0 && G0 + NG <= PU), "a pair of groups needs the partner plane tb + 1 < PU");
@@ -799,85 +554,34 @@ int g_planes = 4;             // precision of the next products: digit planes of
 bool g_all_pairs = false;     // ... and, for 4 planes, whether the second sweep (groups 4..6) runs
 int g_flush_override = 0;     // tests: drain the accumulators every this many stages (0: the exactness bound FLUSH_P*)
 
-// The CTA-pair kernels (tcgen05 cta_group::2) are the product path; RNLA_I8_PAIR=0 keeps the single-CTA sweeps for comparison runs.
-inline bool pair_enabled() {
-    static const bool on = [] { const char* e = getenv("RNLA_I8_PAIR"); return !(e && e[0] == '0'); }();
-    return on;
-}
 inline int pair_w8(int N) { return 8 * ((N + 15) / 16); }                 // thin-operand columns per rank in the images
 // tcgen05.mma.cta_group::2.kind::i8 takes N in steps of 16: the MMA reads exactly the w8 columns per rank that the images hold
 // (N_mma = 112 at l = 110; CuTe's static_assert of N % 32 is a library limit -- the products are bit-identical to the CPU emulation
 // at N_mma = 16, 48, 80, 112, ... on the B200, tests/test_gpu_parity.py).
-template <int P>
-void launch_slice_b(const double* X, int64_t ldx, int64_t K, int N, int nb, const double* rs, int64_t kblocks, cudaStream_t st) {
-    slice_b_kernel<P><<<(unsigned)kblocks, 256, 0, st>>>(X, ldx, K, N, nb, rs, g_sl.cdown.d(), g_sl.bimg.as<uint8_t>());
-}
-rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, int nb, const double* rs, int64_t kblocks, int planes) {
+rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, const double* rs, int64_t kblocks, int planes) {
     Ctx& c = ctx();
-    RNLA_CUDA(g_sl.bimg.ensure((size_t)kblocks * planes * nb * 1024));      // kblocks blocks of 64 = 2 kblocks image blocks of 32
+    const int w8 = pair_w8(N);
+    RNLA_CUDA(g_sl.bimg.ensure((size_t)kblocks * planes * w8 * 128));       // kblocks blocks of 64 = 2 kblocks steps of 32, two ranks each
     RNLA_CUDA(cudaMemsetAsync(g_sl.cbits.p, 0, 128 * 8, c.stream));
     const int64_t rows_per = 32768;
     colmax_kernel<<<dim3((unsigned)N, (unsigned)((K + rows_per - 1) / rows_per)), 256, 0, c.stream>>>(X, ldx, K, N, rs, rows_per,
                                                                                                       g_sl.cbits.as<unsigned long long>());
     scales_kernel<<<1, 128, 0, c.stream>>>(g_sl.cbits.as<unsigned long long>(), 128, g_sl.cup.d(), g_sl.cdown.d(), g_sl.flags.as<int>() + 1);
-    if (pair_enabled()) {
-        const int w8 = pair_w8(N);
-        uint8_t* out = g_sl.bimg.as<uint8_t>();
-        if (planes == 4) slice_b2_kernel<4><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
-        else if (planes == 6) slice_b2_kernel<6><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
-        else slice_b2_kernel<7><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
-    } else if (planes == 4) launch_slice_b<4>(X, ldx, K, N, nb, rs, kblocks, c.stream);
-    else if (planes == 6) launch_slice_b<6>(X, ldx, K, N, nb, rs, kblocks, c.stream);
-    else launch_slice_b<7>(X, ldx, K, N, nb, rs, kblocks, c.stream);
+    uint8_t* out = g_sl.bimg.as<uint8_t>();
+    if (planes == 4) slice_b2_kernel<4><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
+    else if (planes == 6) slice_b2_kernel<6><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
+    else slice_b2_kernel<7><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
     g_kernel_launches += 3;
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;
 }
 
-// ring sizes: the thin operand gets `nbs` half-stages -- 4 while the A ring still gets at least 3 stages (measured on the
-// 3-plane sweep at the headline size: 3.7 / 4.9 ms with 2, 3.0 / 3.8 with 3, 3.0 / 3.2 with 4), else 3, else 2 -- and A the rest of
-// the 227 KB of dynamic shared memory.  The 7-plane sweep is insensitive (7.9 ms with 2, 3 or 4): it is bound by what one SM can
-// take in from L2.
-constexpr size_t SMEM_MAX = 232448, SMEM_FIXED = 1024 + 1024;      // alignment slack + barriers
-inline void mma_rings(int pu, int nb, int* na, int* nbs) {
-    const size_t a = (size_t)pu * ASTAGE, b = (size_t)pu * nb * 512;
-    int s = 4;
-    while (s > 2 && (SMEM_MAX - SMEM_FIXED - (size_t)s * b) / a < 3) --s;
-    static const char* ov = getenv("RNLA_I8_NBS");           // experiments: force the depth of the thin-operand ring
-    if (ov && ov[0] >= '2' && ov[0] <= '4' && (SMEM_MAX - SMEM_FIXED - (size_t)(ov[0] - '0') * b) / a >= 1) s = ov[0] - '0';
-    *nbs = s;
-    *na = (int)std::min<size_t>(MAX_RING, (SMEM_MAX - SMEM_FIXED - s * b) / a);
-}
-inline size_t mma_smem(int pu, int nb) {
-    int na, nbs;
-    mma_rings(pu, nb, &na, &nbs);
-    return (size_t)na * pu * ASTAGE + (size_t)nbs * pu * nb * 512 + SMEM_FIXED;
-}
-
-template <bool TN, int PU, int G0, int NG, bool ADD>
-rnla_status launch_mma(dim3 grid, int nb, int64_t kblocks_total, int64_t per, int flush, double* C, int64_t ldc, int64_t rows, int ncols,
-                       const double* rs_up, int64_t chunk_stride) {
-    Ctx& c = ctx();
-    Sliced& s = g_sl;
-    static bool attr = false;
-    if (!attr) {
-        RNLA_CUDA(cudaFuncSetAttribute(i8_mma_kernel<TN, PU, G0, NG, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-        attr = true;
-    }
-    int na, nbs;
-    mma_rings(PU, nb, &na, &nbs);
-    static const std::string kname = std::string("k:i8_mma<") + (TN ? "A^T B" : "A B") + ", planes " + std::to_string(PU) + ", groups " +
-                                     std::to_string(G0) + ".." + std::to_string(G0 + NG - 1) + ">";
-    kernel_phase_begin(kname.c_str());
-    i8_mma_kernel<TN, PU, G0, NG, ADD><<<grid, MMA_THREADS, mma_smem(PU, nb), c.stream>>>(
-        s.img.as<uint8_t>(), s.planes, s.cblocks, s.bimg.as<uint8_t>(), g_planes, nb, na, nbs, kblocks_total, per, flush, C, ldc, rows, ncols,
-        rs_up, s.cup.d(), chunk_stride);
-    kernel_phase_end();
-    ++g_kernel_launches;
-    RNLA_CUDA(cudaGetLastError());
-    return RNLA_OK;
-}
-// ring sizes of the pair kernel: the thin operand's half-stages are PU x w8 x 32 bytes; four of them, A takes the rest
+// Ring sizes: both operands advance in steps of 32 contraction indices.  The thin operand (L2-resident) gets four slots of
+// (PU + 1) x w8 x 32 bytes, the planes of A the rest of the 227 KB of dynamic shared memory (6 steps of 28 KB in the 7-plane sweep).
+// Measured at the headline size (profiles/r02_pair_experiments_last.log): 3, 4 or 6 slots for the thin operand, steps of 64 instead of
+// 32 for A, and L2 prefetch 3 .. 12 steps ahead all leave the 7-plane sweep within 2 % -- under the power cap it is the energy of a
+// product that sets its time, not the latency the rings cover.
+constexpr size_t SMEM_MAX = 232448;
 constexpr size_t SMEM_FIXED2 = 1024 + 1024;                        // alignment slack + barriers
 inline void mma2_rings(int pu, int w8, int* na, int* nbs) {
     const size_t a = (size_t)pu * ASTEP, b = (size_t)(pu + 1) * w8 * 32;
@@ -959,27 +663,21 @@ rnla_status launch_mma2(dim3 grid, int N, int64_t kblocks_total, int64_t per, in
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;
 }
-template <bool TN, int PU, int G0, int NG, bool ADD>
-rnla_status launch_sweep(dim3 grid, int nb, int N, int64_t kblocks_total, int64_t per, int flush, double* C, int64_t ldc, int64_t rows, int ncols,
-                         const double* rs_up, int64_t chunk_stride) {
-    if (pair_enabled()) return launch_mma2<TN, PU, G0, NG, ADD>(grid, N, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, chunk_stride);
-    return launch_mma<TN, PU, G0, NG, ADD>(grid, nb, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, chunk_stride);
-}
 // the sweeps of one product at the current precision
 template <bool TN>
-rnla_status run_sweeps(dim3 grid, int nb, int64_t kblocks_total, int64_t per, double* C, int64_t ldc, int64_t rows, int ncols,
+rnla_status run_sweeps(dim3 grid, int64_t kblocks_total, int64_t per, double* C, int64_t ldc, int64_t rows, int ncols,
                        const double* rs_up, int64_t chunk_stride) {
     const int f4 = g_flush_override ? g_flush_override : FLUSH_P4, f6 = g_flush_override ? g_flush_override : FLUSH_P6,
               f7 = g_flush_override ? g_flush_override : FLUSH_P7;
     if (g_planes == 7) {
         // 28 pairs: groups 0..2 need planes 0..2 only (6 pairs), groups 3..6 all seven (22 pairs): 3 + 7 planes of each operand enter
         // the SMs per product instead of 4 + 7 -- the kernels are bound by the L2 -> SM traffic
-        RNLA_TRY((launch_sweep<TN, 3, 0, 3, false>(grid, nb, ncols, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
-        return launch_sweep<TN, 7, 3, 4, true>(grid, nb, ncols, kblocks_total, per, f7, C, ldc, rows, ncols, rs_up, chunk_stride);
+        RNLA_TRY((launch_mma2<TN, 3, 0, 3, false>(grid, ncols, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
+        return launch_mma2<TN, 7, 3, 4, true>(grid, ncols, kblocks_total, per, f7, C, ldc, rows, ncols, rs_up, chunk_stride);
     }
-    RNLA_TRY((launch_sweep<TN, 4, 0, 4, false>(grid, nb, ncols, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
-    if (g_planes == 6) return launch_sweep<TN, 6, 4, 2, true>(grid, nb, ncols, kblocks_total, per, f6, C, ldc, rows, ncols, rs_up, chunk_stride);
-    if (g_all_pairs) return launch_sweep<TN, 4, 4, 3, true>(grid, nb, ncols, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride);
+    RNLA_TRY((launch_mma2<TN, 4, 0, 4, false>(grid, ncols, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride)));
+    if (g_planes == 6) return launch_mma2<TN, 6, 4, 2, true>(grid, ncols, kblocks_total, per, f6, C, ldc, rows, ncols, rs_up, chunk_stride);
+    if (g_all_pairs) return launch_mma2<TN, 4, 4, 3, true>(grid, ncols, kblocks_total, per, f4, C, ldc, rows, ncols, rs_up, chunk_stride);
     return RNLA_OK;
 }
 
@@ -1106,10 +804,9 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, int p
 // C (m x N) = A * B (n x N) on the split A
 static rnla_status i8_gemm_nn_tile(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc) {
     Sliced& s = g_sl;
-    const int nb = (int)((N + 15) / 16);
     const int64_t kblocks = 2 * s.cblocks;
-    RNLA_TRY(slice_b(B, ldb, s.n, (int)N, nb, nullptr, kblocks, g_planes));
-    return run_sweeps<false>(dim3((unsigned)s.rblocks, 1), nb, kblocks, kblocks, C, ldc, s.m, (int)N, s.up.d(), 0);
+    RNLA_TRY(slice_b(B, ldb, s.n, (int)N, nullptr, kblocks, g_planes));
+    return run_sweeps<false>(dim3((unsigned)s.rblocks, 1), kblocks, kblocks, C, ldc, s.m, (int)N, s.up.d(), 0);
 }
 rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc) {
     for (int64_t c0 = 0; c0 < N; c0 += BN)
@@ -1137,17 +834,15 @@ static int64_t pair_chunks(int64_t pairs, int64_t kblocks, int sms) {
 static rnla_status i8_gemm_tn_tile(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz) {
     Ctx& c = ctx();
     Sliced& s = g_sl;
-    const int nb = (int)((N + 15) / 16);
     const int64_t kblocks = 2 * s.rblocks;
-    RNLA_TRY(slice_b(Q, ldq, s.m, (int)N, nb, s.up.d(), kblocks, g_planes));
+    RNLA_TRY(slice_b(Q, ldq, s.m, (int)N, s.up.d(), kblocks, g_planes));
     // row chunks: enough (column block, chunk) units to fill the SMs a few times over; the partials are summed in chunk order
-    int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>((4LL * c.sms + s.cblocks - 1) / s.cblocks, kblocks));
-    if (pair_enabled()) nchunks = pair_chunks((s.cblocks + 1) / 2, kblocks, c.sms);
+    int64_t nchunks = pair_chunks((s.cblocks + 1) / 2, kblocks, c.sms);
     const int64_t per = (kblocks + nchunks - 1) / nchunks;
     nchunks = (kblocks + per - 1) / per;
     const int64_t stride = s.n * N;
     RNLA_CUDA(s.part.ensure((size_t)nchunks * stride * 8));
-    RNLA_TRY(run_sweeps<true>(dim3((unsigned)s.cblocks, (unsigned)nchunks), nb, kblocks, per, s.part.d(), s.n, s.n, (int)N, nullptr, stride));
+    RNLA_TRY(run_sweeps<true>(dim3((unsigned)s.cblocks, (unsigned)nchunks), kblocks, per, s.part.d(), s.n, s.n, (int)N, nullptr, stride));
     i8_tn_reduce_kernel<<<(unsigned)std::min<int64_t>(148 * 8, (stride + 255) / 256), 256, 0, c.stream>>>(s.part.d(), (int)nchunks, stride, s.n, (int)N,
                                                                                                            s.cup.d(), Z, ldz);
     ++g_kernel_launches;
