@@ -360,33 +360,50 @@ __device__ __forceinline__ void issue_step2(uint32_t tmem, uint32_t a_base, uint
 // Barriers: the LEADER's fullA / fullB count the bytes of both CTAs' tiled TMA loads (cp.async.bulk.tensor with cta_group::2 may
 // report to a barrier in the peer); emptyA / emptyB / accum are committed by the leader's MMAs in both CTAs; the leader's `drained`
 // collects the epilogue warps of both.
-template <bool TN, int PU, int G0, int NG, bool ADD, bool WIDE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMA_THREADS, 1)
-i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t cblocks, int64_t tiles, int w8,
-               int na, int nbs, int pfd, int64_t kblocks_total, int64_t kblocks_per_chunk, int flush, double* __restrict__ C, int64_t ldc, int64_t rows,
-               int ncols, const double* __restrict__ rs_up, const double* __restrict__ cs_up, int64_t chunk_stride) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+// what a sweep needs besides its tensor maps
+struct SweepArgs {
+    int64_t cblocks, tiles;                 // column blocks of the images; valid tiles along grid.x
+    int w8;                                 // thin-operand columns per rank
+    int pfd;                                // experiments: L2 prefetch distance in steps (RNLA_I8_PFD)
+    int64_t kblocks_total, kblocks_per_chunk;
+    double* C; int64_t ldc, rows; int ncols;
+    const double* rs_up; const double* cs_up;
+    int64_t chunk_stride;
+};
+constexpr int BAR_SET_BYTES = 1024;          // one set of ring barriers (4 x MAX_RING2 + accum + drained)
+constexpr size_t SMEM_MAX = 232448;
+constexpr size_t RING_BYTES = SMEM_MAX - 128 - 2 * BAR_SET_BYTES - 64;       // alignment slack, two barrier sets, the TMEM slot
+
+// One sweep of a CTA pair over its tile: digit pairs (ta, tb), ta, tb < PU, with G0 <= ta + tb < G0 + NG into NG TMEM accumulators.
+// `set` selects the barrier set (a kernel that runs several sweeps back to back gives each its own); `add`: add to what is in C.
+// (Both sweeps of a 55-bit product in one launch, pairs alternating which one they run first so that the chip always holds a mix of
+// the light and the heavy sweep, was measured: 10.1 - 10.9 ms against 10.1 - 10.2 ms for two launches -- the time of a product is the
+// sum of its sweeps' energies under the power cap, not a matter of which resource idles; profiles/r02_pair_both_vs_separate.log.)
+template <bool TN, int PU, int G0, int NG, bool WIDE>
+__device__ __forceinline__ void pair_sweep(const CUtensorMap* tmA, const CUtensorMap* tmB, const SweepArgs& a, uint8_t* smem, int set, uint32_t tmem,
+                                           int na, int nbs, int flush, bool add) {
+    const int w8 = a.w8;
     const uint32_t bplane = (uint32_t)w8 * 32;                 // one plane of a step of this rank's columns
     const uint32_t a_bytes = PU * ASTEP, b_bytes = PU * bplane, b_slot = (PU + 1) * bplane;   // slot of the thin operand: [zero plane][PU planes]
     const int w = w8;                                          // columns per rank the MMA reads: N_mma = 2 w (4 w for a pair of groups)
     uint8_t* bring = smem + (size_t)na * a_bytes;
-    uint64_t* fullA = reinterpret_cast<uint64_t*>(bring + (size_t)nbs * b_slot);
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + RING_BYTES + (size_t)set * BAR_SET_BYTES);
     uint64_t* emptyA = fullA + MAX_RING2;
     uint64_t* fullB = emptyA + MAX_RING2;
     uint64_t* emptyB = fullB + MAX_RING2;
     uint64_t* accum = emptyB + MAX_RING2;
     uint64_t* drained = accum + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
-    const int64_t tile_raw = blockIdx.x, tile = min(tile_raw, tiles - 1);
-    const int64_t kb0 = (int64_t)blockIdx.y * kblocks_per_chunk;
-    const int64_t kb1 = min(kblocks_total, kb0 + kblocks_per_chunk);
+    const int64_t tile_raw = blockIdx.x, tile = min(tile_raw, a.tiles - 1);
+    const int64_t cblocks = a.cblocks;
+    const int64_t kb0 = (int64_t)blockIdx.y * a.kblocks_per_chunk;
+    const int64_t kb1 = min(a.kblocks_total, kb0 + a.kblocks_per_chunk);
     const int nk = (int)max((int64_t)0, kb1 - kb0);            // blocks of 64 contraction indices (the unit of the work split and of `flush`)
     const int ns = 2 * nk;                                     // steps of 32
     const int64_t gs0 = 2 * kb0;                               // first step
     const int nflush = (nk + flush - 1) / flush;
+    const int pfd = a.pfd;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < na; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); }
@@ -395,15 +412,13 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(drained, 8);
         mbar_fence_init();
     }
-    if (warp == 1) tc_alloc2(tmem_slot, 512);
-    for (int s = 0; s < nbs; ++s)                              // the zero planes (never written again)
+    for (int s = 0; s < nbs; ++s)                              // the zero planes (the TMA loads land behind them)
         for (uint32_t q = threadIdx.x * 16; q < bplane; q += MMA_THREADS * 16) *reinterpret_cast<uint4*>(bring + (size_t)s * b_slot + q) = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's reads
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                        // the peer's barriers exist before anything is signalled across
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -415,14 +430,13 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int q = (int)(gs & 3);
                 if (rank == 0) mbar_arrive_expect_tx(fullA + s, 2 * a_bytes);         // the leader's barrier counts both CTAs' bytes
                 uint8_t* st = smem + (size_t)s * a_bytes;
-                if (TN) tma2_load_5d(st, &tmA, leader_addr(fullA + s), 0, 0, 2 * q, 0, (int)(blk2 * cblocks + tile));
-                else tma2_load_5d(st, &tmA, leader_addr(fullA + s), 0, q, 0, 0, (int)(tile * cblocks + blk2));
+                if (TN) tma2_load_5d(st, tmA, leader_addr(fullA + s), 0, 0, 2 * q, 0, (int)(blk2 * cblocks + tile));
+                else tma2_load_5d(st, tmA, leader_addr(fullA + s), 0, q, 0, 0, (int)(tile * cblocks + blk2));
                 if (j + pfd < ns) {
-                    // experiments (RNLA_I8_PFD): ask L2 for the step `pfd` ahead
                     const int64_t gp = gs + pfd, bp = gp >> 2;
                     const int qp = (int)(gp & 3);
-                    if (TN) tma_prefetch_l2_5d(&tmA, 0, 0, 2 * qp, 0, (int)(bp * cblocks + tile));
-                    else tma_prefetch_l2_5d(&tmA, 0, qp, 0, 0, (int)(tile * cblocks + bp));
+                    if (TN) tma_prefetch_l2_5d(tmA, 0, 0, 2 * qp, 0, (int)(bp * cblocks + tile));
+                    else tma_prefetch_l2_5d(tmA, 0, qp, 0, 0, (int)(tile * cblocks + bp));
                 }
                 if (++s == na) { s = 0; ph ^= 1; }
             }
@@ -433,7 +447,7 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < ns; ++j) {
                 mbar_wait(emptyB + s, ph);
                 if (rank == 0) mbar_arrive_expect_tx(fullB + s, 2 * b_bytes);
-                tma2_load_3d(bring + (size_t)s * b_slot + bplane, &tmB, leader_addr(fullB + s), 0, 0, (int)((gs0 + j) * 2 + rank));   // the leading PU planes
+                tma2_load_3d(bring + (size_t)s * b_slot + bplane, tmB, leader_addr(fullB + s), 0, 0, (int)((gs0 + j) * 2 + rank));   // the leading PU planes
                 if (++s == nbs) { s = 0; ph ^= 1; }
             }
         }
@@ -468,14 +482,16 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
         const int64_t r = tile_raw * BM + quad * 32 + lane;     // output row (A S) / output row = column of A (A^T Y)
-        const double rsc = (!TN && r < rows) ? rs_up[r] : 1.0;
-        double* out = C + (TN ? (int64_t)blockIdx.y * chunk_stride : 0);
-        if (nk <= 0 && !ADD && r < rows) for (int c = 0; c < ncols; ++c) out[r + (int64_t)c * ldc] = 0.0;
+        const int ncols = a.ncols;
+        const int64_t rows = a.rows, ldc = a.ldc;
+        const double rsc = (!TN && r < rows) ? a.rs_up[r] : 1.0;
+        double* out = a.C + (TN ? (int64_t)blockIdx.y * a.chunk_stride : 0);
+        if (nk <= 0 && !add && r < rows) for (int c = 0; c < ncols; ++c) out[r + (int64_t)c * ldc] = 0.0;
         for (int f = 0; f < nflush; ++f) {
             mbar_wait(accum, f & 1);
             tc_fence_after();
             for (int seg = 0; seg < 2; ++seg) {
-                const int cbase = seg * w8, cnt = min(ncols - cbase, w8);     // output columns [cbase, cbase + cnt) <- accumulator columns seg * w + ..
+                const int cbase = seg * w8, cnt = min(ncols - cbase, w8);     // output columns [cbase, cbase + cnt) <- this rank's accumulator columns
                 for (int c0 = 0; c0 < cnt; c0 += 16) {
                     uint32_t d[NG][16];
 #pragma unroll
@@ -491,9 +507,9 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                                 for (int g = NG - 2; g >= 0; --g) v = v * 0.00390625 + (double)(int)d[g][e];
                                 v *= 1.0 / (double)(1ull << (14 + 8 * G0));                     // 2^-(14 + 8 G0): weight of the sweep's first group
-                                if (!TN) v *= rsc * cs_up[c];
+                                if (!TN) v *= rsc * a.cs_up[c];
                                 double* o = out + r + (int64_t)c * ldc;
-                                if (ADD || f > 0) *o += v; else *o = v;
+                                if (add || f > 0) *o += v; else *o = v;
                             }
                         }
                     }
@@ -508,10 +524,29 @@ i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                                        // nobody leaves (or frees TMEM) while the pair's MMAs can still touch it
-    if (warp == 1) { tc_fence_after(); tc_dealloc2(tmem, 512); }
+    cluster_sync_all();                                        // every MMA of the pair has completed, every load has been consumed
+    tc_fence_after();
 }
 
+// grid.x = 2 x pairs of tiles (cluster = blockIdx.x {2p, 2p + 1}); `tiles` = valid tiles (an odd count leaves a phantom that loads
+// the last tile again and stores nothing).  Both operands advance in steps of 32 contraction indices (one MMA K step) through their
+// own rings.  Barriers: the LEADER's fullA / fullB count the bytes of both CTAs' tiled TMA loads (cp.async.bulk.tensor with
+// cta_group::2 may report to a barrier in the peer); emptyA / emptyB / accum are committed by the leader's MMAs in both CTAs; the
+// leader's `drained` collects the epilogue warps of both.
+template <bool TN, int PU, int G0, int NG, bool ADD, bool WIDE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMA_THREADS, 1)
+i8_mma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SweepArgs a, int na, int nbs, int flush) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RING_BYTES + 2 * BAR_SET_BYTES);
+    if ((threadIdx.x >> 5) == 1) tc_alloc2(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pair_sweep<TN, PU, G0, NG, WIDE>(&tmA, &tmB, a, smem, 0, tmem, na, nbs, flush, ADD);
+    if ((threadIdx.x >> 5) == 1) tc_dealloc2(tmem, 512);
+}
 // Z(j, c) = cs_up(c) * sum over chunks, fixed order
 __global__ void __launch_bounds__(256)
 i8_tn_reduce_kernel(const double* __restrict__ P, int nchunks, int64_t chunk_stride, int64_t n, int ncols,
@@ -581,14 +616,12 @@ rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, const double
 // Measured at the headline size (profiles/r02_pair_experiments_last.log): 3, 4 or 6 slots for the thin operand, steps of 64 instead of
 // 32 for A, and L2 prefetch 3 .. 12 steps ahead all leave the 7-plane sweep within 2 % -- under the power cap it is the energy of a
 // product that sets its time, not the latency the rings cover.
-constexpr size_t SMEM_MAX = 232448;
-constexpr size_t SMEM_FIXED2 = 1024 + 1024;                        // alignment slack + barriers
 inline void mma2_rings(int pu, int w8, int* na, int* nbs) {
     const size_t a = (size_t)pu * ASTEP, b = (size_t)(pu + 1) * w8 * 32;
     int s = 4;
-    if (const char* ov = getenv("RNLA_I8_NBS2")) { const int v = atoi(ov); if (v >= 2 && v <= MAX_RING2 && (SMEM_MAX - SMEM_FIXED2 - (size_t)v * b) / a >= 2) s = v; }
+    if (const char* ov = getenv("RNLA_I8_NBS2")) { const int v = atoi(ov); if (v >= 2 && v <= MAX_RING2 && (RING_BYTES - (size_t)v * b) / a >= 2) s = v; }
     *nbs = s;
-    *na = (int)std::min<size_t>(MAX_RING2, (SMEM_MAX - SMEM_FIXED2 - (size_t)s * b) / a);
+    *na = (int)std::min<size_t>(MAX_RING2, (RING_BYTES - (size_t)s * b) / a);
 }
 // Tensor maps over the images (elements: 8-byte words).  A: [block][plane][I 8][quarter 4][512 B]; a step (32 contraction indices) of
 // A S is the box (512 B, one quarter, all I, PU planes), a step of A^T Y the box (512 B, all quarters, two I, PU planes): ONE copy
@@ -614,50 +647,53 @@ inline rnla_status make_tensor_map(CUtensorMap* tm, void* base, int rank, const 
     if (r != CUDA_SUCCESS) return fail(RNLA_ERR_COMPUTATION, "int8 passes: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return RNLA_OK;
 }
+inline rnla_status sweep_tensor_maps(bool tn, int pu, int w8, int64_t kblocks_total, CUtensorMap* tmA, CUtensorMap* tmB) {
+    Sliced& s = g_sl;
+    const cuuint64_t dims[5] = {64, 4, 8, (cuuint64_t)s.planes, (cuuint64_t)(s.rblocks * s.cblocks)};
+    const cuuint64_t strides[4] = {512, 2048, (cuuint64_t)APLANE, (cuuint64_t)s.planes * APLANE};
+    const cuuint32_t box_nn[5] = {64, 1, 8, (cuuint32_t)pu, 1}, box_tn[5] = {64, 4, 2, (cuuint32_t)pu, 1};
+    RNLA_TRY(make_tensor_map(tmA, s.img.p, 5, dims, strides, tn ? box_tn : box_nn));
+    // thin operand: [block of 32 k x rank][plane][w8 x 32 bytes]
+    const cuuint64_t bdims[3] = {(cuuint64_t)w8 * 4, (cuuint64_t)g_planes, (cuuint64_t)(4 * kblocks_total)};
+    const cuuint64_t bstrides[2] = {(cuuint64_t)w8 * 32, (cuuint64_t)g_planes * w8 * 32};
+    const cuuint32_t bbox[3] = {(cuuint32_t)w8 * 4, (cuuint32_t)pu, 1};
+    return make_tensor_map(tmB, s.bimg.p, 3, bdims, bstrides, bbox);
+}
+inline SweepArgs sweep_args(dim3* grid, int N, int64_t kblocks_total, int64_t per, double* C, int64_t ldc, int64_t rows, int ncols, const double* rs_up,
+                            int64_t chunk_stride) {
+    SweepArgs a;
+    a.cblocks = g_sl.cblocks; a.tiles = grid->x; a.w8 = pair_w8(N);
+    a.pfd = 1 << 30;
+    if (const char* e = getenv("RNLA_I8_PFD")) { const int v = atoi(e); if (v > 0) a.pfd = v; }
+    a.kblocks_total = kblocks_total; a.kblocks_per_chunk = per;
+    a.C = C; a.ldc = ldc; a.rows = rows; a.ncols = ncols; a.rs_up = rs_up; a.cs_up = g_sl.cup.d(); a.chunk_stride = chunk_stride;
+    grid->x = (unsigned)(2 * ((a.tiles + 1) / 2));
+    return a;
+}
 template <bool TN, int PU, int G0, int NG, bool ADD>
 rnla_status launch_mma2(dim3 grid, int N, int64_t kblocks_total, int64_t per, int flush, double* C, int64_t ldc, int64_t rows, int ncols,
                         const double* rs_up, int64_t chunk_stride) {
     Ctx& c = ctx();
-    Sliced& s = g_sl;
+    // pairs of groups in one MMA of double width where the sweep has an even number of groups and the accumulators fit (4 w8 <= 256)
+    constexpr bool WIDE = NG % 2 == 0;
     static bool attr = false;
     if (!attr) {
         RNLA_CUDA(cudaFuncSetAttribute(i8_mma2_kernel<TN, PU, G0, NG, ADD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-        RNLA_CUDA(cudaFuncSetAttribute(i8_mma2_kernel<TN, PU, G0, NG, ADD, NG % 2 == 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        RNLA_CUDA(cudaFuncSetAttribute(i8_mma2_kernel<TN, PU, G0, NG, ADD, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         attr = true;
     }
-    const int w8 = pair_w8(N);
+    const SweepArgs a = sweep_args(&grid, N, kblocks_total, per, C, ldc, rows, ncols, rs_up, chunk_stride);
     int na, nbs;
-    mma2_rings(PU, w8, &na, &nbs);
-    const size_t smem = (size_t)na * PU * ASTEP + (size_t)nbs * (PU + 1) * w8 * 32 + SMEM_FIXED2;
-    // pairs of groups in one MMA of double width where the sweep has an even number of groups and the accumulators fit (4 w8 <= 256)
-    constexpr bool WIDE = NG % 2 == 0;
+    mma2_rings(PU, a.w8, &na, &nbs);
     static const bool wide_on = [] { const char* e = getenv("RNLA_I8_WIDE"); return !(e && e[0] == '0'); }();
-    const bool wide = WIDE && wide_on && 4 * w8 <= 256;
+    const bool wide = WIDE && wide_on && 4 * a.w8 <= 256;
     static const std::string kname = std::string("k:i8_mma<") + (TN ? "A^T B" : "A B") + ", planes " + std::to_string(PU) + ", groups " +
                                      std::to_string(G0) + ".." + std::to_string(G0 + NG - 1) + ">";
-    const int64_t tiles = grid.x;
-    grid.x = (unsigned)(2 * ((tiles + 1) / 2));
     CUtensorMap tmA, tmB;
-    {
-        const cuuint64_t dims[5] = {64, 4, 8, (cuuint64_t)s.planes, (cuuint64_t)(s.rblocks * s.cblocks)};
-        const cuuint64_t strides[4] = {512, 2048, (cuuint64_t)APLANE, (cuuint64_t)s.planes * APLANE};
-        const cuuint32_t box_nn[5] = {64, 1, 8, (cuuint32_t)PU, 1}, box_tn[5] = {64, 4, 2, (cuuint32_t)PU, 1};
-        RNLA_TRY(make_tensor_map(&tmA, s.img.p, 5, dims, strides, TN ? box_tn : box_nn));
-        // thin operand: [block of 32 k x rank][plane][w8 x 32 bytes]
-        const cuuint64_t bdims[3] = {(cuuint64_t)w8 * 4, (cuuint64_t)g_planes, (cuuint64_t)(4 * kblocks_total)};
-        const cuuint64_t bstrides[2] = {(cuuint64_t)w8 * 32, (cuuint64_t)g_planes * w8 * 32};
-        const cuuint32_t bbox[3] = {(cuuint32_t)w8 * 4, (cuuint32_t)PU, 1};
-        RNLA_TRY(make_tensor_map(&tmB, s.bimg.p, 3, bdims, bstrides, bbox));
-    }
-    int pfd = 1 << 30;                                          // L2 prefetch distance in stages (none)
-    if (const char* e = getenv("RNLA_I8_PFD")) { const int v = atoi(e); if (v > 0) pfd = v; }
+    RNLA_TRY(sweep_tensor_maps(TN, PU, a.w8, kblocks_total, &tmA, &tmB));
     kernel_phase_begin(kname.c_str());
-    if (wide)
-        i8_mma2_kernel<TN, PU, G0, NG, ADD, WIDE><<<grid, MMA_THREADS, smem, c.stream>>>(
-            tmA, tmB, s.cblocks, tiles, w8, na, nbs, pfd, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, s.cup.d(), chunk_stride);
-    else
-        i8_mma2_kernel<TN, PU, G0, NG, ADD, false><<<grid, MMA_THREADS, smem, c.stream>>>(
-            tmA, tmB, s.cblocks, tiles, w8, na, nbs, pfd, kblocks_total, per, flush, C, ldc, rows, ncols, rs_up, s.cup.d(), chunk_stride);
+    if (wide) i8_mma2_kernel<TN, PU, G0, NG, ADD, WIDE><<<grid, MMA_THREADS, SMEM_MAX, c.stream>>>(tmA, tmB, a, na, nbs, flush);
+    else i8_mma2_kernel<TN, PU, G0, NG, ADD, false><<<grid, MMA_THREADS, SMEM_MAX, c.stream>>>(tmA, tmB, a, na, nbs, flush);
     kernel_phase_end();
     ++g_kernel_launches;
     RNLA_CUDA(cudaGetLastError());
