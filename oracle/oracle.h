@@ -30,6 +30,9 @@ float orc_gauss_from_u32(uint32_t k);
  * src/sketch.rs:112-127 with rand 0.8.5 Uniform<f64> / Bernoulli over the seed-0 ThreeFry stream.  Returns -1 for Gaussian
  * (needs rand_distr's ziggurat tables, not in the tree). */
 int orc_sketching_operator_ref(int dist, uint64_t seed, int64_t rows, int64_t cols, double* out);
+/* rand_distr 0.4.3 StandardNormal (ziggurat) on the ThreeFry2x64Rng stream: tables, and `count` samples (returns the stream words consumed) */
+void orc_ziggurat_tables(double* x257, double* f257);
+int64_t orc_threefry_gaussian(uint64_t seed, int64_t count, double* out);
 
 /* ---- L2 dense kernels with nalgebra 0.33 conventions ------------------------------------------- */
 void orc_gemm_nn(const double* A, int64_t lda, int64_t m, int64_t K, const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "rnla_sketching_operator": (c_i32, [c_i32, c_i64, c_i64, P]),
     "rnla_sketch_fill": (c_i32, [c_i32, c_i32, c_u64, c_u32, c_i64, c_i64, c_i64, P, c_i64]),
     "rnla_sketch_fill_dev": (c_i32, [c_i32, c_i32, c_u64, c_u32, c_i64, c_i64, c_i64, P, c_i64]),
+    "rnla_ziggurat_tables": (c_i32, [P, P]),
     "rnla_haar_sample": (c_i32, [c_i64, c_i64, c_i32, P]),
     "rnla_orth": (c_i32, [P, c_i64, c_i64, P, P, C.POINTER(c_i64)]),
     "rnla_stabilizer": (c_i32, [P, c_i64, c_i64, P, C.POINTER(c_i64)]),

@@ -102,17 +102,22 @@ rnla_status rnla_sketch_fill_dev(int32_t generator, int32_t dist, uint64_t seed,
     if (ld < rows) return fail(RNLA_ERR_INVALID_DIMENSIONS, "leading dimension smaller than rows");
     RNLA_TRY(ensure_ctx());
     if (generator == RNLA_GEN_THREEFRY) {
-        if (dist == RNLA_GAUSSIAN)
-            return fail(RNLA_ERR_INVALID_PARAMETERS,
-                        "the reference's Gaussian stream needs rand_distr's ziggurat tables, which are not part of the reference tree; use RNLA_GEN_PHILOX");
         if (row_offset != 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "the ThreeFry stream is sequential: row_offset must be 0");
         uint64_t key[2];
         threefry_key_from_u64(seed, key);
+        // Gaussian: rand_distr 0.4.3 StandardNormal (ziggurat) on the same sequential stream (src/sketch.rs:112-117), csrc/ziggurat.cu
+        if (dist == RNLA_GAUSSIAN) return fill_threefry_gaussian(key[0], key[1], rows, cols, d_out, ld, nullptr);
         RNLA_CUDA(fill_threefry(dist, key[0], key[1], rows, cols, d_out, ld, ctx().stream));
         return RNLA_OK;
     }
     if (generator != RNLA_GEN_PHILOX) return fail(RNLA_ERR_INVALID_PARAMETERS, "unknown generator");
     RNLA_CUDA(fill_philox(dist, seed, stream, rows, cols, row_offset, d_out, ld, ctx().stream));
+    return RNLA_OK;
+}
+rnla_status rnla_ziggurat_tables(double* x257, double* f257) {
+    RNLA_API_GUARD;
+    if (!x257 || !f257) return fail(RNLA_ERR_INVALID_PARAMETERS, "ziggurat tables: null output");
+    ziggurat_tables_host(x257, f257);
     return RNLA_OK;
 }
 rnla_status rnla_sketch_fill(int32_t generator, int32_t dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols,

@@ -38,7 +38,8 @@ def sketching_operator(dist_type, rows, cols):
 
 def sketch_fill(dist_type, rows, cols, seed=0, stream=0, row_offset=0, generator=runtime.GEN_PHILOX):
     """Extended operator generation: explicit seed / Philox stream / global row offset / generator.
-    `generator=GEN_THREEFRY` reproduces the reference's ThreeFry2x64 stream for Uniform and Rademacher."""
+    `generator=GEN_THREEFRY` reproduces the reference's operator: its sequential ThreeFry2x64 stream with rand's Uniform / Bernoulli
+    and rand_distr's ziggurat Gaussian (src/sketch.rs:112-127)."""
     lib = _lib.load()
     rows, cols = int(rows), int(cols)
     out = np.empty((max(rows, 0), max(cols, 0)), dtype=np.float64, order="F")
