@@ -16,7 +16,8 @@ P = C.c_void_p
 class Options(C.Structure):
     """`rnla_options` (include/rnla.h)."""
     _fields_ = [("mode", c_i32), ("dist", c_i32), ("seed", c_u64), ("num_passes", c_i32),
-                ("passes_per_stab", c_i32), ("fused_sketch", c_i32), ("range_passes_int8", c_i32)]
+                ("passes_per_stab", c_i32), ("fused_sketch", c_i32), ("range_passes_int8", c_i32), ("generator", c_i32),
+                ("reserved_", c_i32)]
 
 
 class LsqrResult(C.Structure):

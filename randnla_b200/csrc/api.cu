@@ -38,20 +38,6 @@ static rnla_status d2h(double* host, const double* dev, size_t count) {
     return RNLA_OK;
 }
 
-// rand_core 0.6.4 SeedableRng::seed_from_u64 (PCG32 expansion) -> ThreeFry2x64 key (rust-random123/src/threefry.rs:23-27)
-static void threefry_key_from_u64(uint64_t state, uint64_t key[2]) {
-    const uint64_t MUL = 6364136223846793005ull, INC = 11634580027462260723ull;
-    uint32_t w[4];
-    for (int i = 0; i < 4; ++i) {
-        state = state * MUL + INC;
-        const uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27);
-        const uint32_t rot = (uint32_t)(state >> 59);
-        w[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
-    }
-    key[0] = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
-    key[1] = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
-}
-
 static rnla_status validate_svd_like(int64_t k, double epsilon, int64_t s) {
     // reference src/lora_drivers.rs:31-45 / :89-103
     if (k <= 0) return fail(RNLA_ERR_INVALID_PARAMETERS, fmt("Rank k must be positive, current input is %lld", (long long)k));
@@ -101,18 +87,8 @@ rnla_status rnla_sketch_fill_dev(int32_t generator, int32_t dist, uint64_t seed,
     if (dist < RNLA_GAUSSIAN || dist > RNLA_RADEMACHER) return fail(RNLA_ERR_INVALID_PARAMETERS, "unknown distribution");
     if (ld < rows) return fail(RNLA_ERR_INVALID_DIMENSIONS, "leading dimension smaller than rows");
     RNLA_TRY(ensure_ctx());
-    if (generator == RNLA_GEN_THREEFRY) {
-        if (row_offset != 0) return fail(RNLA_ERR_INVALID_PARAMETERS, "the ThreeFry stream is sequential: row_offset must be 0");
-        uint64_t key[2];
-        threefry_key_from_u64(seed, key);
-        // Gaussian: rand_distr 0.4.3 StandardNormal (ziggurat) on the same sequential stream (src/sketch.rs:112-117), csrc/ziggurat.cu
-        if (dist == RNLA_GAUSSIAN) return fill_threefry_gaussian(key[0], key[1], rows, cols, d_out, ld, nullptr);
-        RNLA_CUDA(fill_threefry(dist, key[0], key[1], rows, cols, d_out, ld, ctx().stream));
-        return RNLA_OK;
-    }
-    if (generator != RNLA_GEN_PHILOX) return fail(RNLA_ERR_INVALID_PARAMETERS, "unknown generator");
-    RNLA_CUDA(fill_philox(dist, seed, stream, rows, cols, row_offset, d_out, ld, ctx().stream));
-    return RNLA_OK;
+    if (generator != RNLA_GEN_PHILOX && generator != RNLA_GEN_THREEFRY) return fail(RNLA_ERR_INVALID_PARAMETERS, "unknown generator");
+    return fill_operator(generator, dist, seed, stream, rows, cols, row_offset, d_out, ld);
 }
 rnla_status rnla_ziggurat_tables(double* x257, double* f257) {
     RNLA_API_GUARD;
@@ -162,7 +138,7 @@ rnla_status rnla_haar_sample(int64_t rows, int64_t cols, int32_t attr, double* o
     Ctx& c = ctx();
     DevBuf G, T;
     RNLA_CUDA(G.alloc((size_t)m * n * 8));
-    RNLA_CUDA(fill_philox(RNLA_GAUSSIAN, c.opts.seed, 0, m, n, 0, G.d(), m, c.stream));      // :68-72
+    RNLA_TRY(fill_operator(c.opts.generator, RNLA_GAUSSIAN, c.opts.seed, 0, m, n, 0, G.d(), m));   // :68-72 (generator = THREEFRY: the reference's own m n samples)
     ShardInfo sh{m, 0, m};
     RNLA_TRY(orth_inplace(G.d(), m, sh, (int)n, false, nullptr, nullptr));                  // :73-80 (R_ii >= 0, sign fix is a no-op)
     if (attr == RNLA_ROW) {
@@ -309,8 +285,8 @@ rnla_status rnla_rand_svd(const double* A, int64_t m, int64_t n, int64_t k, doub
             RNLA_CUDA(cudaEventCreateWithFlags(&ev_ready.e, cudaEventDisableTiming));
             RNLA_CUDA(cudaEventCreateWithFlags(&ev_landed.e, cudaEventDisableTiming));
             cudaEvent_t ready = ev_ready.e, landed = ev_landed.e;
-            const bool fused = o.fused_sketch == 1 || (o.fused_sketch == 2 && (double)n * l * 8.0 > 48.0 * 1024 * 1024);
-            if (!fused) RNLA_CUDA(fill_philox(o.dist, o.seed, 1 /* STREAM_RANGE_N */, n, l, 0, S, n, c.stream));
+            const bool fused = o.generator == RNLA_GEN_PHILOX && (o.fused_sketch == 1 || (o.fused_sketch == 2 && (double)n * l * 8.0 > 48.0 * 1024 * 1024));
+            if (!fused) RNLA_TRY(fill_operator(o.generator, o.dist, o.seed, 1 /* STREAM_RANGE_N */, n, l, 0, S, n));
             RNLA_CUDA(cudaEventRecord(ready, c.stream));                    // dA is allocated stream-ordered on c.stream
             RNLA_CUDA(cudaStreamWaitEvent(c.copy_stream, ready, 0));
             const int64_t nblk = std::min<int64_t>(16, (m + 8191) / 8192);

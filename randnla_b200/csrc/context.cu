@@ -38,6 +38,9 @@ static void default_opts(rnla_options* o) {
     const char* r8 = getenv("RNLA_RANGE_INT8");
     if (r8 && r8[0] >= '0' && r8[0] <= '3' && !r8[1]) o->range_passes_int8 = r8[0] - '0';
     if (r8 && !strcmp(r8, "auto")) o->range_passes_int8 = -1;
+    o->generator = RNLA_GEN_PHILOX;
+    const char* gen = getenv("RNLA_GENERATOR");
+    if (gen && (!strcmp(gen, "threefry") || !strcmp(gen, "THREEFRY") || !strcmp(gen, "1"))) o->generator = RNLA_GEN_THREEFRY;
     const char* m = getenv("RNLA_MODE");
     if (m && (!strcmp(m, "literal") || !strcmp(m, "LITERAL") || !strcmp(m, "1"))) o->mode = RNLA_MODE_LITERAL;
 }
@@ -221,6 +224,8 @@ rnla_status rnla_set_options(const rnla_options* opt) {
         return fail(RNLA_ERR_INVALID_PARAMETERS, "rnla_set_options: unknown mode");
     if (opt->dist < RNLA_GAUSSIAN || opt->dist > RNLA_RADEMACHER)
         return fail(RNLA_ERR_INVALID_PARAMETERS, "rnla_set_options: unknown distribution");
+    if (opt->generator != RNLA_GEN_PHILOX && opt->generator != RNLA_GEN_THREEFRY)
+        return fail(RNLA_ERR_INVALID_PARAMETERS, "rnla_set_options: unknown generator");
     RNLA_TRY(ensure_ctx());
     g_ctx.opts = *opt;
     return RNLA_OK;

@@ -178,13 +178,13 @@ rnla_status orth_inplace(double* X, int64_t ldx, const ShardInfo& sh, int p, boo
 // profiles/r01_*); once it no longer fits the 126 MB L2 it would stream from HBM once per row block, and the fused
 // in-kernel generator is the only sane choice.  fused_sketch = 2 picks by that criterion.
 static inline bool use_fused(const rnla_options& o, int64_t n, int l) {
-    if (o.fused_sketch == 0) return false;
+    if (o.fused_sketch == 0 || o.generator != RNLA_GEN_PHILOX) return false;      // the reference's sequential stream cannot be evaluated per tile
     if (o.fused_sketch == 1) return true;
     return (double)n * l * 8.0 > 48.0 * 1024 * 1024;
 }
 static bool g_i8_deferred = false;
 static I8Plan g_plan;          // how the current driver call spends the integer tensor cores (dev_qb1 / dev_rand_evd2 set it)
-static inline bool use_fused_forced(const rnla_options& o) { return o.fused_sketch == 1; }
+static inline bool use_fused_forced(const rnla_options& o) { return o.fused_sketch == 1 && o.generator == RNLA_GEN_PHILOX; }
 // rnla_options.range_passes_int8 -> which passes run on the integer tensor cores and at which precision:
 //   0  every pass in FP64 (DMMA)
 //   1  A Omega, A^T Y on 31-bit operands (10 digit pairs), A S with all 16 pairs; Q^T A in FP64        (spectrum-conditional)
@@ -221,7 +221,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
     } else {
         PhaseScope ph("tsog1:At_Omega");
         // S = A^T * Omega(m x l)                                                    lora_helpers.rs:74-76
-        RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_M, m, l, sh.row_off, Ytmp, std::max<int64_t>(m, 1), c.stream));
+        RNLA_TRY(fill_operator(o.generator, o.dist, o.seed, STREAM_RANGE_M, m, l, sh.row_off, Ytmp, std::max<int64_t>(m, 1)));
         i8_set_precision(g_plan.early, g_plan.early_all);
         RNLA_TRY(dev_gemm_tn(A, lda, m, n, Ytmp, std::max<int64_t>(m, 1), l, S, n, true));
         done = 1;
@@ -254,7 +254,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
             } else if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
                 RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
             } else {
-                if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n, c.stream));
+                if (virt) RNLA_TRY(fill_operator(o.generator, o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n));
                 i8_set_precision(g_plan.early, g_plan.early_all);
                 RNLA_TRY(dev_gemm_nn(A, lda, m, n, S, n, l, Ytmp, std::max<int64_t>(m, 1)));
             }
@@ -271,7 +271,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
         if (done % pps == 0) { PhaseScope ph("stab:S"); RNLA_TRY(orth_inplace(S, n, nside, l, false, nullptr, nullptr, 1)); }
     }
     if (virt && !allow_virtual) {
-        RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n, c.stream));
+        RNLA_TRY(fill_operator(o.generator, o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n));
         virt = false;
     }
     if (S_is_omega) *S_is_omega = virt;
@@ -307,7 +307,7 @@ rnla_status dev_rf1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
         if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
             RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Q, ldq));
         } else {
-            if (virt) RNLA_CUDA(fill_philox(o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S.d(), n, c.stream));
+            if (virt) RNLA_TRY(fill_operator(o.generator, o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S.d(), n));
             i8_set_precision(g_plan.last, g_plan.last_all);      // Y = A S is the product whose range becomes Q (no-op on the FP64 path)
             RNLA_TRY(dev_gemm_nn(A, lda, m, n, S.d(), n, l, Q, ldq));
         }

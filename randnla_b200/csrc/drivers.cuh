@@ -127,6 +127,9 @@ I8Plan i8_plan(const rnla_options& o, int64_t m_local, int64_t n, int l);
 // ziggurat.cu: the reference's Gaussian entries (rand_distr 0.4.3 StandardNormal on the sequential ThreeFry stream, sketch.rs:112-117)
 rnla_status fill_threefry_gaussian(uint64_t key0, uint64_t key1, int64_t rows, int64_t cols, double* out, int64_t ld, int64_t* words_consumed);
 void ziggurat_tables_host(double* x257, double* f257);
+void threefry_key_from_u64(uint64_t state, uint64_t key[2]);
+rnla_status fill_operator(int generator, int dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols, int64_t row_off, double* out,
+                          int64_t ld);
 
 // literal.cu: bug-compatible pieces of the reference
 rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n, int l, int q, int pps,

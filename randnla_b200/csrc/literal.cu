@@ -213,11 +213,11 @@ rnla_status literal_tsog1(const double* A, int64_t lda, const ShardInfo& sh, int
     RNLA_CUDA(cudaMemsetAsync(S, 0, (size_t)n * l * 8, c.stream));                                   // :67
     if (q % 2 == 0) {
         // :70-72  S = Omega(n x k) -- overwritten by the loop below, so only materialised when the loop does not run
-        if (q < 2) RNLA_CUDA(fill_philox(o.dist, o.seed, 1 /* STREAM_RANGE_N */, n, l, 0, S, n, c.stream));
+        if (q < 2) RNLA_TRY(fill_operator(o.generator, o.dist, o.seed, 1 /* STREAM_RANGE_N */, n, l, 0, S, n));
     } else {
         // :73-82  S1 = A^T Omega(m x k); its stabilised copy `_S2` is discarded
         PhaseScope ph("tsog1:At_Omega");
-        RNLA_CUDA(fill_philox(o.dist, o.seed, 2 /* STREAM_RANGE_M */, m, l, 0, T.d(), mm, c.stream));
+        RNLA_TRY(fill_operator(o.generator, o.dist, o.seed, 2 /* STREAM_RANGE_M */, m, l, 0, T.d(), mm));
         RNLA_TRY(dev_gemm_tn(A, lda, m, n, T.d(), mm, l, S1.d(), n, false));
         s1_zero = false;
         done = 1;

@@ -13,6 +13,7 @@
 #include "context.cuh"
 #include "drivers.cuh"
 #include "gemm.cuh"
+#include "panel.cuh"
 #include "rng.cuh"
 #include <cmath>
 #include <cstdio>
@@ -139,6 +140,38 @@ void ziggurat_tables_host(double* x_out, double* f_out) {
     for (int i = 2; i < 256; ++i) { const double last = x[i - 1]; x[i] = std::sqrt(-2.0 * std::log(V / last + std::exp(-last * last / 2.0))); }
     x[256] = 0.0;
     for (int i = 0; i < 257; ++i) { x_out[i] = through_text(x[i]); f_out[i] = through_text(std::exp(-x[i] * x[i] / 2.0)); }
+}
+
+// rand_core 0.6.4 SeedableRng::seed_from_u64 (PCG32 expansion) -> ThreeFry2x64 key (rust-random123/src/threefry.rs:23-27)
+void threefry_key_from_u64(uint64_t state, uint64_t key[2]) {
+    const uint64_t MUL = 6364136223846793005ull, INC = 11634580027462260723ull;
+    uint32_t w[4];
+    for (int i = 0; i < 4; ++i) {
+        state = state * MUL + INC;
+        const uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27);
+        const uint32_t rot = (uint32_t)(state >> 59);
+        w[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+    }
+    key[0] = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+    key[1] = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
+}
+
+// One sketching operator (src/sketch.rs:102-130) into device memory.  Philox: entry (row_off + r, c) of stream `stream`.  ThreeFry: the
+// reference's own operator -- a fresh sequential stream per call, column-major fill (row_off must be 0).
+rnla_status fill_operator(int generator, int dist, uint64_t seed, uint32_t stream, int64_t rows, int64_t cols, int64_t row_off, double* out,
+                          int64_t ld) {
+    Ctx& c = ctx();
+    if (generator == RNLA_GEN_THREEFRY) {
+        if (row_off != 0 || c.nranks > 1)
+            return fail(RNLA_ERR_INVALID_PARAMETERS, "the ThreeFry stream is sequential: row_offset must be 0 (single GPU, unsharded operator)");
+        uint64_t key[2];
+        threefry_key_from_u64(seed, key);
+        if (dist == RNLA_GAUSSIAN) return fill_threefry_gaussian(key[0], key[1], rows, cols, out, ld, nullptr);
+        RNLA_CUDA(fill_threefry(dist, key[0], key[1], rows, cols, out, ld, c.stream));
+        return RNLA_OK;
+    }
+    RNLA_CUDA(fill_philox(dist, seed, stream, rows, cols, row_off, out, ld, c.stream));
+    return RNLA_OK;
 }
 
 rnla_status fill_threefry_gaussian(uint64_t key0, uint64_t key1, int64_t rows, int64_t cols, double* out, int64_t ld, int64_t* words_consumed) {

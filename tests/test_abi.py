@@ -139,7 +139,8 @@ def test_sketch_and_precondition_validation():
 
 def test_options_struct_layout():
     from randnla_b200 import _lib
-    assert C.sizeof(_lib.Options) == 32
+    assert C.sizeof(_lib.Options) == 40
+    assert _lib.Options.generator.offset == 32 and _lib.Options.range_passes_int8.offset == 28 and _lib.Options.seed.offset == 8
 
 
 # ---- static agreement of the three bindings with include/rnla.h (the Rust crate cannot be compiled here: no toolchain) ----

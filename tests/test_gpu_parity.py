@@ -100,6 +100,37 @@ def test_reference_gaussian_stream_on_the_device(rb, orc, rows, cols, seed):
         assert tail.sum() > 0 and abs(got.mean()) < 0.01 and abs(got.std() - 1) < 0.01
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_drivers_with_the_reference_operator(rb, orc, mode):
+    """rnla_options.generator = THREEFRY: the range finder draws the reference's own Omega (every sketching_operator call restarts the
+    seed-0 ThreeFry stream: lora_helpers.rs:71,74 -> sketch.rs:112-117), so rand_svd / rand_evd2 are compared with the oracle fed the
+    oracle's restatement of that operator -- in the intended mode and in the literal (bug-compatible) one, even and odd pass counts."""
+    from randnla_b200 import runtime as rt
+    rng = np.random.default_rng(3)
+    m, n, k, s = 500, 260, 12, 6
+    A = np.asfortranarray(rng.standard_normal((m, 20)) @ rng.standard_normal((20, n)) + 1e-3 * rng.standard_normal((m, n)))
+    l = k + s
+    om_n, om_m = orc.sketching_operator_ref(0, n, l), orc.sketching_operator_ref(0, m, l)
+    for q in (2, 3):
+        with rt.options(mode=mode, generator=rt.GEN_THREEFRY, num_passes=q, range_passes_int8=0):
+            U, S, Vt = rb.lora_drivers.rand_svd(A, k, 1e-6, s)
+        Uo, So, Vto = orc.rand_svd(A, k, 1e-6, s, orc.make_opts(mode=mode, num_passes=q, omega_n=om_n, omega_m=om_m))
+        assert np.abs(np.diag(S) - np.diag(So)).max() <= 1e-10 * np.diag(So).max()
+    # rand_evd2 (odd pass count by default: the m x l operator is really used, lora_drivers.rs:186)
+    G = np.asfortranarray(A.T @ A)
+    with rt.options(mode=mode, generator=rt.GEN_THREEFRY, range_passes_int8=0):
+        V, lam = rb.lora_drivers.rand_evd2(G, k, s)
+    Vo, lo = orc.rand_evd2(G, k, s, orc.make_opts(mode=mode, omega_n=om_n, omega_m=om_n, skip_psd_check=True))      # A is n x n: both operators are n x l
+    vec = lambda x: np.diag(x) if np.ndim(x) == 2 else np.asarray(x, dtype=float)
+    assert len(vec(lam)) == len(vec(lo)) and np.abs(vec(lam) - vec(lo)).max() <= 1e-9 * vec(lo).max()
+    # haar_sample draws its m n samples from the same stream (sketch.rs:68-72)
+    with rt.options(generator=rt.GEN_THREEFRY):
+        Q = rb.sketch.haar_sample(40, 7, rb.sketch.MatrixAttribute.Column)
+    Gm = orc.sketching_operator_ref(0, 40, 7)
+    Qr, Rr = np.linalg.qr(Gm)
+    assert np.abs(Q - Qr * np.sign(np.diag(Rr))).max() < 1e-12
+
+
 def test_haar_sample(rb, orc):
     """src/sketch.rs:140-214 test_row_attribute / test_column_attribute, and parity with the oracle's restatement of :45-85
     (Householder Q of the same Gaussian matrix, sign-fixed): the device's CholeskyQR2 Q has R_ii > 0, i.e. it is that matrix"""
