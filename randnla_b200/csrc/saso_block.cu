@@ -123,6 +123,12 @@ template <int R> __device__ __forceinline__ double sign_f64(uint32_t sb) {
     return __hiloint2double((int)hi, 0);
 }
 
+template <int OFF> __device__ __forceinline__ double lds_f64(uint32_t addr) {       // ld.shared with an immediate offset
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
 template <int W, int BPT, int CB, bool TMA>
 __global__ void __launch_bounds__(SB_T, 1)
 saso_block_kernel(const SbArgs a) {
@@ -239,51 +245,60 @@ saso_block_kernel(const SbArgs a) {
             // slots of this chunk: block i walks y_i, y_i + step, ...  The first nfull rounds are valid for every lane
             // (threads without a block accumulate into registers that are never written back), so they carry no
             // predicates and the BPT independent chains interleave; one tail round takes the remaining slots.
-            int y[BPT];
+            // The loop is issue-bound at d = 8000 (48 accumulators, 16 warps per SM), so a slot is kept to the instructions it
+            // needs: the table is walked through a running shared-memory address per block (one add per round), the element offset is
+            // one shift-and-mask of the entry, the three loads of a slot use immediate offsets from one address.
+            const uint32_t tile_a = smem_u32(tile), tabs_a = smem_u32(tabs);
+            uint32_t ta[BPT];                      // shared address of the next table entry of block i
+            unsigned tailv = 0u;                   // bit i: block i has a slot in the tail round
 #pragma unroll
             for (int i = 0; i < BPT; ++i) {
                 int yy = bb[i] - (int)tabs[tabo[i] + SB_R]; if (yy < 0) yy += nbs;
-                y[i] = yy + part * nbs;
+                yy += part * nbs;
+                ta[i] = tabs_a + 2u * (uint32_t)(tabo[i] + yy);
+                if (yy + nfull * step < SB_R) tailv |= 1u << i;
             }
-            auto round = [&](auto tail) {
-                constexpr bool TAIL = decltype(tail)::value;
+            const uint32_t step2 = 2u * (uint32_t)step;
+            auto slot = [&](int i) {
+                uint32_t e;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(ta[i]));
+                const uint32_t src = tile_a + ((e << 3) & (uint32_t)((SB_R - 1) * 8));
+                double v[CB];
+                if constexpr (CB > 0) v[0] = lds_f64<0>(src);
+                if constexpr (CB > 1) v[1 % CB] = lds_f64<SB_R * 8>(src);
+                if constexpr (CB > 2) v[2 % CB] = lds_f64<2 * SB_R * 8>(src);
+                if constexpr (CB > 3) v[3 % CB] = lds_f64<3 * SB_R * 8>(src);
+                const uint32_t sb = sign_bytes(e);
+                if constexpr (W >= 1) {
+                    const double sg = sign_f64<0>(sb);
 #pragma unroll
-                for (int i = 0; i < BPT; ++i) {
-                    if (!TAIL || y[i] < SB_R) {
-                        const uint32_t e = tabs[tabo[i] + y[i]];
-                        const unsigned char* src = reinterpret_cast<const unsigned char*>(tile) + (e & (uint32_t)(SB_R - 1)) * 8u;
-                        double v[CB];
-#pragma unroll
-                        for (int c = 0; c < CB; ++c) v[c] = *reinterpret_cast<const double*>(src + (size_t)c * SB_R * 8);
-                        const uint32_t sb = sign_bytes(e);
-                        if constexpr (W >= 1) {
-                            const double sg = sign_f64<0>(sb);
-#pragma unroll
-                            for (int c = 0; c < CB; ++c) acc[i][0][c] = fma(sg, v[c], acc[i][0][c]);
-                        }
-                        if constexpr (W >= 2) {
-                            const double sg = sign_f64<1>(sb);
-#pragma unroll
-                            for (int c = 0; c < CB; ++c) acc[i][1 % W][c] = fma(sg, v[c], acc[i][1 % W][c]);
-                        }
-                        if constexpr (W >= 4) {
-                            const double s2 = sign_f64<2>(sb), s3 = sign_f64<3>(sb);
-#pragma unroll
-                            for (int c = 0; c < CB; ++c) {
-                                acc[i][2 % W][c] = fma(s2, v[c], acc[i][2 % W][c]);
-                                acc[i][3 % W][c] = fma(s3, v[c], acc[i][3 % W][c]);
-                            }
-                        }
-                    }
-                    y[i] += step;
+                    for (int c = 0; c < CB; ++c) acc[i][0][c] = fma(sg, v[c], acc[i][0][c]);
                 }
+                if constexpr (W >= 2) {
+                    const double sg = sign_f64<1>(sb);
+#pragma unroll
+                    for (int c = 0; c < CB; ++c) acc[i][1 % W][c] = fma(sg, v[c], acc[i][1 % W][c]);
+                }
+                if constexpr (W >= 4) {
+                    const double s2 = sign_f64<2>(sb), s3 = sign_f64<3>(sb);
+#pragma unroll
+                    for (int c = 0; c < CB; ++c) {
+                        acc[i][2 % W][c] = fma(s2, v[c], acc[i][2 % W][c]);
+                        acc[i][3 % W][c] = fma(s3, v[c], acc[i][3 % W][c]);
+                    }
+                }
+                ta[i] += step2;
             };
 #pragma unroll 1
-            for (int it = 0; it < nfull; ++it) round(std::false_type{});
-            bool more = false;
+            for (int it = 0; it < nfull; ++it) {
 #pragma unroll
-            for (int i = 0; i < BPT; ++i) more |= y[i] < SB_R;
-            if (__any_sync(0xffffffffu, more)) round(std::true_type{});
+                for (int i = 0; i < BPT; ++i) slot(i);
+            }
+            if (__any_sync(0xffffffffu, tailv != 0u)) {
+#pragma unroll
+                for (int i = 0; i < BPT; ++i)
+                    if (tailv & (1u << i)) slot(i);
+            }
         }
         if (TMA) {
             __syncwarp();
