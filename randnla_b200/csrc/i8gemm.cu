@@ -148,6 +148,46 @@ __device__ __forceinline__ void digits(double x, double down, int (&d)[P]) {
     d[1] = sext8(vh); vh = (vh - d[1]) >> 8;
     d[0] = vh;
 }
+// The digits of four elements at once, packed for the images: byte e of w[t] = digit t of element e.  Balanced digits are the
+// bytes of a biased integer: v = sum d_t 256^t with d_t in [-128, 127]  <=>  the unsigned bytes of v + sum 128 * 256^t are d_t + 128, and
+// d_t + 128 as an unsigned byte is d_t as a signed byte with the top bit flipped.  So (v + 0x00808080) ^ 0x00808080 holds planes 3, 2, 1
+// in its low bytes and plane 0 (no bias: the signed remainder) in its top byte; likewise the trailing planes, whose overflow (the top
+// digit coming out as +128) is the byte above them and is carried into v.  Two integer operations per element instead of a shift /
+// sign-extend / subtract chain per digit, then a 4 x 4 byte transpose (eight PRMT) across the four elements.  Same digits as digits<P>
+// (the representation is unique), which the images of the thin operand and the CPU emulation use.
+template <int P>
+__device__ __forceinline__ void digits4_packed(const double (&x)[4], const double (&sc)[4], unsigned (&w)[P]) {
+    unsigned wh[4], wl[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double y = x[e] * sc[e];
+        double yr;
+        int vh = rint_bits(y, &yr);
+        if constexpr (P > 4) {
+            double r2;
+            const int vl = rint_bits((y - yr) * (P == 6 ? 65536.0 : 16777216.0), &r2);
+            const unsigned bias = P == 6 ? 0x00008080u : 0x00808080u;
+            const unsigned ul = (unsigned)vl + bias;
+            vh += (int)(ul >> (P == 6 ? 16 : 24));               // 0 or 1
+            wl[e] = ul ^ bias;
+        }
+        wh[e] = ((unsigned)vh + 0x00808080u) ^ 0x00808080u;
+    }
+    {
+        const unsigned t0 = __byte_perm(wh[0], wh[1], 0x5140), t1 = __byte_perm(wh[0], wh[1], 0x7362);
+        const unsigned t2 = __byte_perm(wh[2], wh[3], 0x5140), t3 = __byte_perm(wh[2], wh[3], 0x7362);
+        w[3] = __byte_perm(t0, t2, 0x5410); w[2] = __byte_perm(t0, t2, 0x7632);
+        w[1] = __byte_perm(t1, t3, 0x5410); w[0] = __byte_perm(t1, t3, 0x7632);
+    }
+    if constexpr (P > 4) {
+        const unsigned t0 = __byte_perm(wl[0], wl[1], 0x5140), t2 = __byte_perm(wl[2], wl[3], 0x5140);
+        w[P - 1] = __byte_perm(t0, t2, 0x5410); w[P - 2] = __byte_perm(t0, t2, 0x7632);
+        if constexpr (P == 7) {
+            const unsigned t1 = __byte_perm(wl[0], wl[1], 0x7362), t3 = __byte_perm(wl[2], wl[3], 0x7362);
+            w[4] = __byte_perm(t1, t3, 0x5410);
+        }
+    }
+}
 // exponent bookkeeping from the bit pattern of a maximum (biased exponent E: max < 2^(E-1022)): up = 2^(E-1021), down = 2^31 / up.
 // flags: 1 = Inf / NaN seen, 2 = a non-zero maximum too small to scale (below 2^-959)
 __device__ __forceinline__ void scales_from_max_bits(unsigned long long bits, double* up, double* down, int* flags) {
@@ -193,9 +233,6 @@ __global__ void scales_kernel(const unsigned long long* __restrict__ bits, int64
 // staging-buffer swizzle (the 16-byte row inside a core matrix is XORed with the index I of its 16-row group): lanes that write the
 // same row of the eight core matrices of one column hit different banks; undone by the copy-out
 __device__ __forceinline__ int stage_swz(int off) { return off ^ (((off >> 9) & 7) << 4); }
-__device__ __forceinline__ unsigned pack4(int a, int b, int c, int d) {
-    return __byte_perm(__byte_perm((unsigned)a, (unsigned)b, 0x0040), __byte_perm((unsigned)c, (unsigned)d, 0x0040), 0x5410);
-}
 
 // The digit split of A: one CTA per 128 rows x 32 columns (a quarter of an image block: 16 elements per thread keep the register
 // count low enough for several resident CTAs per SM, which is what keeps loads in flight while other CTAs form digits and store).
@@ -235,13 +272,11 @@ slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, 
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int jl = warp + 8 * r;                        // 0 .. 31
-        int d[4][P];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) digits<P>(x[r][e], sc[e], d[e]);
+        unsigned wd[P];
+        digits4_packed<P>(x[r], sc, wd);
         const int intra = (il >> 4) * 512 + (jl >> 3) * 128 + (jl & 7) * 16 + (il & 15);
 #pragma unroll
-        for (int t = 0; t < P; ++t)
-            *reinterpret_cast<unsigned*>(stg + stage_swz(t * SL_PLANE + intra)) = pack4(d[0][t], d[1][t], d[2][t], d[3][t]);
+        for (int t = 0; t < P; ++t) *reinterpret_cast<unsigned*>(stg + stage_swz(t * SL_PLANE + intra)) = wd[t];
     }
     __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(stg);

@@ -9,7 +9,7 @@ m, n = 200000, 20000
 sig = bench.planted_sigma()
 dA = rt.empty_colmajor(m, n); pA, lda = rt.dev_ptr_ld(dA)
 _lib.check(lib.rnla_generate_lowrank_dev(pA, lda, m, n, 0, m, bench.R0, sig.ctypes.data_as(C.c_void_p), 1e-7, 1234))
-for level in (2, 1):
+for level in (3, 1):
     opts = rt.make_options(range_passes_int8=level)
     best = None
     for _ in range(4):
