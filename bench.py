@@ -52,6 +52,15 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.idx = gpu_index
+        self.t0 = self.t1 = None
+
+    # nvidia-smi is started BEFORE the warm-up (its start-up -- NVML initialisation, the first query -- was seen to stall the first
+    # timed steps of a run by hundreds of milliseconds); only the samples that arrive between begin() and end() are reported
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -64,7 +73,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -75,7 +84,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if (self.t0 is not None and ts < self.t0) or (self.t1 is not None and ts > self.t1 + 0.1):
+                continue
             try:
                 sm.append(float(r[1])); smax.append(float(r[2]))
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
@@ -429,12 +440,14 @@ def run_ours(args):
     opts = make_opts(args.mode)
     _lib.check(lib.rnla_set_kernel_timing(1))
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):                                   # warm-up outside the clock sampling window
         ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     ms_step, (U, S, Vt), phases_all, launches = timed_steps(opts, 0, args.steps, collect=True)
+    sampler.end()
     clocks = sampler.stop() if rank == 0 else None
     _lib.check(lib.rnla_set_kernel_timing(0))
     kernels = {k_: v for k_, v in phases_all.items() if k_.startswith("k:")}

@@ -56,7 +56,7 @@ for mode in ("auto", "fp64"):
     for k, (cnt, b, ms) in sorted(agg.items(), key=lambda kv: -kv[1][2])[:14]:
         text.append(f"   {cnt:3d} x {k[:88]:<88} {ms:8.2f} ms  {b * 1e-9:8.2f} GB  ({b / max(cnt, 1) * 1e-9:.2f} GB per launch)")
     for k, (cnt, b, ms) in agg.items():
-        if mode == "auto" and "i8_mma_kernel<0, 7" in k.replace("(bool)", "").replace("(int)", ""):
+        if mode == "auto" and "i8_mma2_kernel<0, 7" in k.replace("(bool)", "").replace("(int)", ""):
             out["dominant_kernel_dram_bytes_per_launch"] = b / cnt
     if mode == "fp64":
         big = [d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for (i, nm), d in list(per.items())[start:] if "gemm_nn_kernel" in nm]

@@ -1,9 +1,9 @@
 """SASS evidence: per-kernel counts of the Blackwell-native mnemonics in randnla_b200/librnla.so (cuobjdump -sass), written to
-profiles/r02_sass_summary.txt.  UTCIMMA = tcgen05.mma kind::i8, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (TMA engine),
+profiles/r02_sass_summary.txt.  UTCIMMA = tcgen05.mma kind::i8 (.2CTA: cta_group::2), UTMALDG = cp.async.bulk.tensor (tiled TMA), LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (TMA engine),
 SYNCS = mbarrier, DMMA = mma.sync f64."""
 import re, subprocess, sys, collections
 out = subprocess.run(["cuobjdump", "-sass", "randnla_b200/librnla.so"], capture_output=True, text=True).stdout
-pat = ["UTCIMMA", "UTCBAR", "LDTM", "UBLKCP", "UTMALDG", "SYNCS", "DMMA", "LDGSTS", "REDUX", "ATOMS"]
+pat = ["UTCIMMA", "UTCBAR", "LDTM", "UBLKCP", "UTMALDG", "UTMAPF", "SYNCS", "DMMA", "LDGSTS", "REDUX", "ATOMS"]
 cur = None
 per = collections.OrderedDict()
 for line in out.splitlines():
@@ -19,7 +19,7 @@ tot = collections.Counter()
 rows = []
 for (k, c), nm in zip(per.items(), names):
     tot.update(c)
-    if any(c[p] for p in ("UTCIMMA", "LDTM", "UBLKCP", "DMMA")):
+    if any(c[p] for p in ("UTCIMMA", "LDTM", "UBLKCP", "UTMALDG", "DMMA")):
         short = nm.replace("rnla::", "").replace("(anonymous namespace)::", "").replace("void ", "")
         short = re.sub(r"\((?!anonymous).*", "", short)
         rows.append((short, c))
