@@ -44,18 +44,23 @@ def algorithmic_flops(m, n, l):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe), read through NVML in a thread of this
+    process (nvidia_ml_py).  An `nvidia-smi -lms 100` child did the same in round 1, but its queries were seen to stall the timed steps
+    now and then (one 20 - 150 ms gap in some runs, with normal phase sums): the NVML calls below take microseconds.  The sampler is
+    started before the warm-up; only samples taken between begin() and end() are reported.  Falls back to nvidia-smi if NVML is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows = []
+    def __init__(self, gpu_index, period_s=0.05):
+        self.rows = []                      # (timestamp, sm_mhz, sm_max_mhz, set of reasons)
         self.proc = None
         self.idx = gpu_index
+        self.period = period_s
         self.t0 = self.t1 = None
+        self.stop_flag = threading.Event()
+        self.th = None
+        self.source = None
 
-    # nvidia-smi is started BEFORE the warm-up (its start-up -- NVML initialisation, the first query -- was seen to stall the first
-    # timed steps of a run by hundreds of milliseconds); only the samples that arrive between begin() and end() are reported
     def begin(self):
         self.t0 = time.perf_counter()
 
@@ -64,38 +69,68 @@ class ClockSampler:
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {pynvml.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     pynvml.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.rows.append((time.perf_counter(), sm, smax, {nm for bit, nm in names.items() if mask & bit}))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(self.period)
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
+            self.source = "NVML (nvidia_ml_py), in-process, every %d ms" % int(self.period * 1e3)
+            return
+        except Exception:
+            self.th = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            self.source = "nvidia-smi -lms 100"
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for ts, r in self.rows:
-            if (self.t0 is not None and ts < self.t0) or (self.t1 is not None and ts > self.t1 + 0.1):
-                continue
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                reasons = {name for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9])
+                           if v.lower().startswith("active")}
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]), reasons))
             except Exception:
                 pass
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        elif self.th:
+            self.th.join(timeout=1)
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        sm, smax, reasons = [], [], set()
+        for ts, a, b, rs in self.rows:
+            if (self.t0 is not None and ts < self.t0) or (self.t1 is not None and ts > self.t1):
+                continue
+            sm.append(a); smax.append(b); reasons |= rs
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def host_threads():
@@ -426,21 +461,25 @@ def run_ours(args):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        walls = []
         for _ in range(steps):
+            tw = time.perf_counter()
             out = ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
+            walls.append(1e3 * (time.perf_counter() - tw))      # the call returns with the library's stream drained
             if collect:
                 for name, ms in rt.timings():     # library-side CUDA events of this step (stream already drained by the call)
                     acc.setdefault(name, []).append(ms)
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+        timed_steps.last_walls = walls
         return ms, out, {k_: float(np.mean(v)) for k_, v in acc.items()}, rt.kernel_launches() - launches0
 
     # ---- device-resident timing of the headline mode ----
     opts = make_opts(args.mode)
     _lib.check(lib.rnla_set_kernel_timing(1))
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("RNLA_BENCH_NO_CLOCKS"):      # (debug switch: is a stall the sampler's doing?)
         sampler.start()
     for _ in range(args.warmup):                                   # warm-up outside the clock sampling window
         ld.rand_svd_dev(dA, K_RANK, S_OVER, opts)
@@ -448,6 +487,7 @@ def run_ours(args):
     sampler.begin()
     ms_step, (U, S, Vt), phases_all, launches = timed_steps(opts, 0, args.steps, collect=True)
     sampler.end()
+    headline_walls = list(timed_steps.last_walls)             # host wall time of every timed step (diagnostic: a stalled step shows here)
     clocks = sampler.stop() if rank == 0 else None
     _lib.check(lib.rnla_set_kernel_timing(0))
     kernels = {k_: v for k_, v in phases_all.items() if k_.startswith("k:")}
@@ -655,7 +695,7 @@ def run_ours(args):
                    "sketch": "auto (materialised while Omega is L2-resident)" if args.fused == 2 else ("fused in-kernel Philox" if args.fused == 1 else "materialised"),
                    "mode": args.mode, "range_passes_int8": MODES[args.mode],
                    "l2": f"inputs larger than L2 (A shard = {8 * m_local * n / 2**30:.1f} GiB per GPU, streamed 4x per step)"},
-        "rand_svd_ms": ms_step, "tflops_fp64_equivalent": algorithmic_flops(m_global, n, l) / (ms_step * 1e-3) * 1e-12,
+        "rand_svd_ms": ms_step, "step_wall_ms": [round(w, 2) for w in headline_walls], "tflops_fp64_equivalent": algorithmic_flops(m_global, n, l) / (ms_step * 1e-3) * 1e-12,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cb, "phases_ms": phases, "secondary": secondary,
         "accuracy": {"max_abs_UtU_minus_I": orth_err, "max_rel_sigma_vs_planted(noise-limited)": sigma_vs_planted},

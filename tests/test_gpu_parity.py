@@ -1035,6 +1035,25 @@ def test_i8_accumulators_are_drained_without_changing_the_result(rb):
     assert float((C2 - A2 @ B2).abs().max() / (A2.abs().max() * B2.abs().max() * 23000 ** 0.5)) < 2.0 ** -49
 
 
+@pytest.mark.parametrize("N", [1, 8, 9, 16, 17, 56, 57, 112, 113, 129, 256])
+def test_i8_pair_kernels_thin_operand_widths_and_odd_tile_counts(rb, N):
+    """The CTA-pair sweeps (tcgen05 cta_group::2) over the widths of the thin operand that change their geometry -- columns per rank
+    8 ceil(N / 16), N_mma = 16 .. 128 per group and twice that for a pair of groups, a second 128-column tile from N = 129 -- on a
+    matrix with an ODD number of 128-row and 128-column tiles (the last pair runs with a phantom CTA) and ragged edges."""
+    import torch
+    from randnla_b200 import runtime as rt
+    g = torch.Generator(device="cuda").manual_seed(100 + N)
+    m, n = 128 * 3 + 5, 128 * 5 - 9
+    A = rt.empty_colmajor(m, n); A.copy_(torch.randn((m, n), generator=g, device="cuda", dtype=torch.float64))
+    B = rt.empty_colmajor(n, N); B.copy_(torch.randn((n, N), generator=g, device="cuda", dtype=torch.float64))
+    Q = rt.empty_colmajor(m, N); Q.copy_(torch.randn((m, N), generator=g, device="cuda", dtype=torch.float64))
+    for planes, all_pairs in ((7, True), (4, True)):
+        tol = I8_TOL[(planes, all_pairs)]
+        Cn = _i8_gemm(rt, 0, planes, all_pairs, A, B); Ct = _i8_gemm(rt, 1, planes, all_pairs, A, Q)
+        assert float((Cn - A @ B).abs().max() / (A.abs().max() * B.abs().max() * n ** 0.5)) < tol
+        assert float((Ct - A.t() @ Q).abs().max() / (A.abs().max() * Q.abs().max() * m ** 0.5)) < tol
+
+
 I8_SWEEP = [(kappa, gap) for kappa in (1e2, 1e3, 1e4, 1e6, 1e8) for gap in (1e-2, 1.0, None)]
 
 
