@@ -371,7 +371,10 @@ rnla_status rnla_rand_svd_dev(const double* dA, int64_t lda, int64_t m_local, in
     RNLA_TRY(validate_svd_like(k, 1.0, s));
     RNLA_TRY(ensure_ctx());
     const rnla_options o = pick(opt);
-    return dev_rand_svd(dA, lda, m_local, n, k, s, o, dU, ldu, dSigma, dVt, ldvt, r);
+    host_trace_mark("enter rnla_rand_svd_dev");
+    const rnla_status st = dev_rand_svd(dA, lda, m_local, n, k, s, o, dU, ldu, dSigma, dVt, ldvt, r);
+    host_trace_mark("leave rnla_rand_svd_dev");
+    return st;
 }
 rnla_status rnla_rand_evd1_dev(const double* dA, int64_t lda, int64_t n, int64_t k, int64_t s, const rnla_options* opt,
                                double* dV, int64_t ldv, double* dLambda, int64_t* r) {

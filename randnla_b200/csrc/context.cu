@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is dlopen'ed so librnla.so has no link-time NCCL dependency
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 
@@ -154,7 +155,21 @@ void phases_reset() {
 }
 // Phases nest: a kernel-level entry ("k:..." names, recorded only while kernel timing is on, rnla_set_kernel_timing) may sit inside
 // a driver-level phase; phase_end closes the innermost open one.
+// RNLA_TRACE_HOST=1: report on stderr every stretch of more than 20 ms of HOST time between two consecutive phase marks (where does a
+// call spend time that no phase accounts for?)
+static void host_mark(const char* what, const char* name) {
+    static const bool on = [] { const char* e = getenv("RNLA_TRACE_HOST"); return e && e[0] == '1'; }();
+    if (!on) return;
+    static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    static std::string last_what = "start";
+    const auto now = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(now - last).count();
+    if (ms > 20.0) fprintf(stderr, "[rnla host gap] %.1f ms between <%s> and <%s %s>\n", ms, last_what.c_str(), what, name);
+    last = now; last_what = std::string(what) + " " + name;
+}
+void host_trace_mark(const char* name) { host_mark("mark", name); }
 void phase_begin(const char* name) {
+    host_mark("begin", name);
     Ctx& c = g_ctx;
     PhaseTiming p; p.name = name; p.e0 = get_event(); p.e1 = get_event();
     cudaEventRecord(p.e0, c.stream);
@@ -166,7 +181,7 @@ void phase_end() {
     if (c.open_phases.empty()) return;
     const int i = c.open_phases.back();
     c.open_phases.pop_back();
-    if (i < (int)c.phases.size()) cudaEventRecord(c.phases[(size_t)i].e1, c.stream);
+    if (i < (int)c.phases.size()) { host_mark("end", c.phases[(size_t)i].name.c_str()); cudaEventRecord(c.phases[(size_t)i].e1, c.stream); }
 }
 void kernel_phase_begin(const char* name) { if (g_ctx.kernel_timing) phase_begin(name); }
 void kernel_phase_end() { if (g_ctx.kernel_timing) phase_end(); }

@@ -85,6 +85,7 @@ rnla_status allreduce_sum_f64(double* buf, size_t count);
 rnla_status allgather_i64(const int64_t* send_dev, int64_t* recv_dev, size_t count_per_rank);
 
 void phase_begin(const char* name);
+void host_trace_mark(const char* name);     // RNLA_TRACE_HOST=1 diagnostics
 void phase_end();
 void kernel_phase_begin(const char* name);   // no-ops unless kernel timing is on
 void kernel_phase_end();
