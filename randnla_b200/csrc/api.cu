@@ -631,6 +631,18 @@ rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, i
     return trans ? dev_gemv_t(dA, lda, m, n, dx, dy) : dev_gemv_n(dA, lda, m, n, dx, dy);
 }
 
+int32_t rnla_normal_pass_supported(const double* dA, int64_t lda, int64_t m_local, int64_t n) {
+    RNLA_API_GUARD;
+    if (ensure_ctx() != RNLA_OK) return 0;
+    return normal_pass_supported(dA, lda, m_local, n) ? 1 : 0;
+}
+rnla_status rnla_normal_pass_dev(const double* dA, int64_t lda, int64_t m_local, int64_t n, const double* dx, double cq, const double* dy,
+                                 double cy, double* du, double* dt) {
+    RNLA_API_GUARD;
+    RNLA_TRY(ensure_ctx());
+    return dev_normal_pass(dA, lda, m_local, n, dx, cq, dy, cy, du, dt);
+}
+
 rnla_status rnla_sketch_gemm_dev(const double* dA, int64_t lda, int64_t m, int64_t K, int32_t dist, uint64_t seed, uint32_t stream,
                                  int64_t N, double* dC, int64_t ldc) {
     RNLA_API_GUARD;

@@ -64,6 +64,11 @@ rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, c
                      double conlim, int64_t iter_lim, int calc_var, const double* x0, double* x, rnla_lsqr_result* res,
                      double* arnorms, int64_t arnorms_cap, double* var);
 
+// normal_pass.cu: u = cq (A x) + cy y, t[0..n) = A^T u, t[n] = u . u with A streamed once (clusters hold row slabs in shared memory)
+bool normal_pass_supported(const double* A, int64_t lda, int64_t m_local, int64_t n);
+rnla_status dev_normal_pass(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* x, double cq, const double* y, double cy,
+                            double* uout, double* t);
+
 rnla_status dev_small_gemv(const double* M, int64_t ld, int n, int trans, const double* x, double* y);
 rnla_status dev_axpby_vec(double a, const double* x, double b, double* y, int64_t n);
 rnla_status dev_cgls_operator(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, const double* M, double* z,

@@ -20,6 +20,8 @@
 #include "ptx.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace rnla {
@@ -291,8 +293,8 @@ rnla_status dev_tri_inv_blocked(const double* R, int64_t ldr, int n, double* Rin
 
 // cgls(a = A M, b, tolerance, num_iterations, x = z) of src/cg.rs:18-61 in operator form: M (n x n, ld n) is applied to
 // n-vectors, A is streamed twice per iteration.  z: initial guess in, solution of the preconditioned system out.
-static rnla_status cgls_operator(Solver& S, const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b,
-                                 const double* M, double* z, double epsilon, int64_t maxit, int64_t* it_out, int32_t* conv_out) {
+static rnla_status cgls_operator_twopass(Solver& S, const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b,
+                                         const double* M, double* z, double epsilon, int64_t maxit, int64_t* it_out, int32_t* conv_out) {
     Ctx& c = S.c;
     PhaseScope ph("cgls");
     const int nn = (int)n;
@@ -331,6 +333,130 @@ static rnla_status cgls_operator(Solver& S, const double* A, int64_t lda, int64_
     }
     *it_out = it; *conv_out = conv;
     return RNLA_OK;
+}
+
+// ---- the same iteration with A streamed ONCE per iteration (normal_pass.cu) ---------------------------------------------------
+// One pass gives q = a p and a^T q together, so  s_new = a^T (r - alpha q) = s - alpha a^T q  (src/cg.rs:39-40 by linearity; r itself
+// is never needed: cgls returns x only).  Every scalar of the iteration stays on the device; the host reads ||s_new||^2 once per
+// iteration for the reference's stopping rule (:44), which -- as in the reference -- is applied to the residual the recurrence
+// carries.  RNLA_ONEPASS_CONFIRM=1 additionally confirms a stop on s = a^T (b - a x) recomputed from x (one more pass) and restarts
+// the directions from it when it is not below the tolerance (stricter than the reference: where the tolerance is below what the
+// recurrences resolve, e.g. 1e-10 at cond(a) = 1e5 in operator form, that takes a few iterations more than the reference does).
+constexpr int CG_HIST = 1024;
+// p = s, gamma = s . s -> st[0] and *out
+__global__ void __launch_bounds__(1024)
+cgls_restart_kernel(int n, const double* __restrict__ s, double* __restrict__ p, double* __restrict__ st, double* __restrict__ out) {
+    __shared__ double red[32];
+    double loc = 0.0;
+    for (int j = threadIdx.x; j < n; j += 1024) { const double v = s[j]; p[j] = v; loc = fma(v, v, loc); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double g = 0.0; for (int w = 0; w < 32; ++w) g += red[w]; st[0] = g; out[0] = g; }
+}
+// alpha = gamma / qq;  x += alpha p;  s -= alpha t;  gamma' = s . s;  beta = gamma' / gamma;  p = s + beta p     src/cg.rs:37-52
+__global__ void __launch_bounds__(1024)
+cgls_update_kernel(int n, const double* __restrict__ t, const double* __restrict__ qq, double* __restrict__ x, double* __restrict__ s,
+                   double* __restrict__ p, double* __restrict__ st, double* __restrict__ out) {
+    __shared__ double red[32];
+    __shared__ double gnew;
+    const double gamma = st[0];
+    const double alpha = gamma / qq[0];
+    double loc = 0.0;
+    for (int j = threadIdx.x; j < n; j += 1024) {
+        x[j] += alpha * p[j];
+        const double v = s[j] - alpha * t[j];
+        s[j] = v;
+        loc = fma(v, v, loc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double g = 0.0; for (int w = 0; w < 32; ++w) g += red[w]; gnew = g; }
+    __syncthreads();
+    const double beta = gnew / gamma;
+    for (int j = threadIdx.x; j < n; j += 1024) p[j] = s[j] + beta * p[j];
+    if (threadIdx.x == 0) { st[0] = gnew; out[0] = gnew; }
+}
+static rnla_status cgls_operator_onepass(Solver& S, const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b,
+                                         const double* M, double* z, double epsilon, int64_t maxit, int64_t* it_out, int32_t* conv_out) {
+    Ctx& c = S.c;
+    PhaseScope ph("cgls");
+    const int nn = (int)n;
+    DevBuf s, p, xh, t, u, st, hist;
+    RNLA_CUDA(s.alloc((size_t)n * 8)); RNLA_CUDA(p.alloc((size_t)n * 8)); RNLA_CUDA(xh.alloc((size_t)n * 8)); RNLA_CUDA(t.alloc((size_t)n * 8));
+    RNLA_CUDA(u.alloc((size_t)(n + 1) * 8)); RNLA_CUDA(st.alloc(8)); RNLA_CUDA(hist.alloc((size_t)(CG_HIST + 1) * 8));
+    auto to_hat = [&](const double* in) -> const double* { if (!M) return in; S.small_gemv(M, n, nn, 0, in, xh.d()); return xh.d(); };
+    auto read = [&](const double* dev, double* out) -> rnla_status {
+        RNLA_CUDA(cudaMemcpyAsync(out, dev, 8, cudaMemcpyDeviceToHost, c.stream));
+        RNLA_CUDA(cudaStreamSynchronize(c.stream));
+        return RNLA_OK;
+    };
+    // s = a^T (b - a x) at the current x, p = s, gamma = s . s (also on the host)
+    auto restart = [&](double* gamma) -> rnla_status {
+        RNLA_TRY(dev_normal_pass(A, lda, m_local, n, to_hat(z), -1.0, b, 1.0, nullptr, u.d()));                  // :30-31
+        if (M) RNLA_TRY(S.small_gemv(M, n, nn, 1, u.d(), s.d()));
+        else RNLA_CUDA(cudaMemcpyAsync(s.p, u.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c.stream));
+        cgls_restart_kernel<<<1, 1024, 0, c.stream>>>(nn, s.d(), p.d(), st.d(), hist.d() + CG_HIST);             // :32-33
+        ++g_kernel_launches;
+        RNLA_CUDA(cudaGetLastError());
+        return read(hist.d() + CG_HIST, gamma);
+    };
+    double gamma = 0.0;
+    RNLA_TRY(restart(&gamma));
+    const double gamma0 = gamma;
+    const char* ce = getenv("RNLA_ONEPASS_CONFIRM");
+    const bool confirm = ce && ce[0] == '1';
+    int64_t it = 0; int32_t conv = 0;
+    while (it < maxit) {
+        RNLA_TRY(dev_normal_pass(A, lda, m_local, n, to_hat(p.d()), 1.0, nullptr, 0.0, nullptr, u.d()));         // q = a p, a^T q, q . q   :36
+        const double* tt = u.d();
+        if (M) { RNLA_TRY(S.small_gemv(M, n, nn, 1, u.d(), t.d())); tt = t.d(); }
+        double* slot = hist.d() + (it % CG_HIST);
+        cgls_update_kernel<<<1, 1024, 0, c.stream>>>(nn, tt, u.d() + n, z, s.d(), p.d(), st.d(), slot);          // :37-52
+        ++g_kernel_launches;
+        RNLA_CUDA(cudaGetLastError());
+        ++it;
+        RNLA_TRY(read(slot, &gamma));
+        if (std::sqrt(gamma) < epsilon) {                                                                       // :44
+            if (!confirm) { conv = 1; break; }
+            const double rec = gamma;
+            RNLA_TRY(restart(&gamma));                  // confirm on a^T (b - a x) itself; not confirmed: carry on from that residual
+            if (getenv("RNLA_NP_VERBOSE"))
+                fprintf(stderr, "cgls one-pass: it %lld recurrence |s| %.3e, a^T (b - a x) %.3e, |s_0| %.3e, eps %.3e\n", (long long)it, std::sqrt(rec),
+                        std::sqrt(gamma), std::sqrt(gamma0), epsilon);
+            if (std::sqrt(gamma) < epsilon) { conv = 1; break; }
+        }
+    }
+    *it_out = it; *conv_out = conv;
+    return RNLA_OK;
+}
+// One pass per iteration where the operator is a preconditioned one (the sketch-and-precondition drivers: cond(A M) = O(1), the s
+// recurrence is as accurate as the reference's r recurrence) and the one-pass kernel takes the shape; plain cgls(a, ...) keeps the
+// reference's recurrence unless RNLA_ONEPASS=2.  Row shards must agree (lda / alignment differ per rank).
+// whether every rank's shard is taken by the one-pass kernel (lda / alignment differ per rank; the ranks must choose alike)
+static rnla_status onepass_agreed(Solver& S, const double* A, int64_t lda, int64_t m_local, int64_t n, bool* one) {
+    Ctx& c = S.c;
+    *one = normal_pass_supported(A, lda, m_local, n);
+    if (c.nranks > 1) {
+        double flag = *one ? 1.0 : 0.0;
+        RNLA_CUDA(cudaMemcpyAsync(S.scal.p, &flag, 8, cudaMemcpyHostToDevice, c.stream));
+        RNLA_TRY(allreduce_sum_f64(S.scal.d(), 1));
+        RNLA_CUDA(cudaMemcpyAsync(&flag, S.scal.p, 8, cudaMemcpyDeviceToHost, c.stream));
+        RNLA_CUDA(cudaStreamSynchronize(c.stream));
+        *one = flag > (double)c.nranks - 0.5;
+    }
+    return RNLA_OK;
+}
+static rnla_status cgls_operator(Solver& S, const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b,
+                                 const double* M, double* z, double epsilon, int64_t maxit, int64_t* it_out, int32_t* conv_out) {
+    const char* e = getenv("RNLA_ONEPASS");
+    bool one = false;
+    if (M != nullptr || (e && e[0] == '2')) RNLA_TRY(onepass_agreed(S, A, lda, m_local, n, &one));
+    if (one) return cgls_operator_onepass(S, A, lda, m_local, n, b, M, z, epsilon, maxit, it_out, conv_out);
+    return cgls_operator_twopass(S, A, lda, m_local, n, b, M, z, epsilon, maxit, it_out, conv_out);
 }
 
 // building blocks of the other sketch-and-precondition / sketch-and-solve drivers (next_rows.cu)
@@ -589,9 +715,30 @@ rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, c
         return RNLA_OK;
     }
     const double ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
+    bool onepass = false;
+    RNLA_TRY(onepass_agreed(S, A, lda, m_local, n, &onepass));
+    DevBuf tn1;
+    if (onepass) RNLA_CUDA(tn1.alloc((size_t)(n + 1) * 8));
+    double uscale = 1.0;                                      // one-pass iterations keep u unnormalised: u_reference = uscale * u
     while (itn < iter_lim) {
         if (arnorms && itn < arnorms_cap) arnorms[itn] = arnorm;                                          // :191
         nhist = ++itn;
+        if (onepass) {
+            // u~ = a v - alfa u and a^T u~ from ONE pass over a (normal_pass.cu): beta = ||u~||, a^T (u~ / beta) = (a^T u~) / beta.  u stays
+            // unnormalised in memory; its factor 1 / beta goes into the next iteration's coefficient                :195-203
+            RNLA_TRY(dev_normal_pass(A, lda, m_local, n, v.d(), 1.0, u.d(), -alfa * uscale, u.d(), tn1.d()));
+            double uu = 0.0;
+            RNLA_CUDA(cudaMemcpyAsync(&uu, tn1.d() + n, 8, cudaMemcpyDeviceToHost, c.stream));
+            RNLA_CUDA(cudaStreamSynchronize(c.stream));
+            beta = std::sqrt(uu);
+            uscale = 1.0;
+            if (beta > 0.0) {
+                uscale = 1.0 / beta;
+                anorm = std::sqrt(anorm * anorm + alfa * alfa + beta * beta + dampsq);                    // :200
+                RNLA_TRY(axpby_nrm2(S, 1.0 / beta, tn1.d(), -beta, v.d(), n, false, &alfa));              // :202-203
+                RNLA_TRY(S.axpby(0.0, v.d(), alfa > 0.0 ? 1.0 / alfa : 0.0, v.d(), n));                   // :204
+            }
+        } else {
         RNLA_TRY(dev_gemv_n(A, lda, m_local, n, v.d(), tm.d()));
         RNLA_TRY(axpby_nrm2(S, 1.0, tm.d(), -alfa, u.d(), m_local, true, &beta));                         // :195-196
         if (beta > 0.0) {
@@ -600,6 +747,7 @@ rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, c
             RNLA_TRY(dev_gemv_t(A, lda, m_local, n, u.d(), tn.d()));
             RNLA_TRY(axpby_nrm2(S, 1.0, tn.d(), -beta, v.d(), n, false, &alfa));                          // :202-203
             RNLA_TRY(S.axpby(0.0, v.d(), alfa > 0.0 ? 1.0 / alfa : 0.0, v.d(), n));                       // :204
+        }
         }
         const double rhobar1 = std::sqrt(rhobar * rhobar + dampsq);                                       // :208-212
         const double cs1 = rhobar / rhobar1, sn1 = damp / rhobar1;

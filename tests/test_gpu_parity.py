@@ -694,7 +694,11 @@ def test_lsrn_end_to_end(rb, orc, kind, m, n, cond):
     xl = np.linalg.lstsq(A, b, rcond=None)[0]
     nrm = np.linalg.norm(xl)
     assert info["converged"] and convo and abs(info["iterations"] - ito) <= 2 and info["iterations"] < 100
-    assert np.linalg.norm(x - xo) <= 1e-8 * nrm
+    # Two runs that both stop at ||s|| < tol differ in x = N y by up to (||s_1|| + ||s_2||) / sigma_min(A) (A N is orthonormal to the
+    # sketch's accuracy, N = V Sigma^-1 amplifies by 1 / sigma_min): 1e-10 x 1e5 per run at cond = 1e5, where both recurrences (the
+    # reference's r, the device's s = s - alpha a^T (a p) from one pass over A) also carry operator-form errors of eps cond per
+    # product, i.e. a true residual of ~1e-9.  At cond = 1e2 the plain 1e-8 bound holds.
+    assert np.linalg.norm(x - xo) <= max(1e-8 * nrm, 20 * 1e-10 * cond)
     assert np.linalg.norm(x - xl) <= 1e-7 * nrm * max(1.0, cond * 1e-5)
     with pytest.raises(InvalidParameters):
         sp.lsrn_overdetermined(A, b, 1e-6, 10, 0.5)

@@ -291,8 +291,37 @@ def _solver_worker(rank, world, port, m, n, out):
         xc = xc + alpha * p; r = r - alpha * ap
         s = allsum(Al.T @ r); nn = float(s @ s)
         p = s + (nn / ns) * p; ns = nn
+    # the same two solvers on the ONE-PASS dataflow (csrc/normal_pass.cu): per iteration one local pass gives u = cq A_l x + cy y_l,
+    # A_l^T u and u . u, and ONE all-reduce of n + 1 doubles combines the shards
+    def normal_pass(xv, cq, y, cy):
+        ul = cq * (Al @ xv) + (cy * y if y is not None else 0.0)
+        t = allsum(np.concatenate([Al.T @ ul, [ul @ ul]]))
+        return ul, t[:n], float(t[n])
+    # LSQR: u stays unnormalised in memory, its factor goes into the next coefficient (dev_lsqr, `uscale`)
+    x1 = np.zeros(n); u = bl.copy()
+    beta = float(np.sqrt(allsum(u @ u)[0])); u /= beta
+    v = allsum(Al.T @ u); alfa = float(np.linalg.norm(v)); v /= alfa
+    w = v.copy(); rhobar, phibar = alfa, beta; uscale = 1.0
+    for _ in range(6):
+        u, t, uu = normal_pass(v, 1.0, u, -alfa * uscale)
+        beta = float(np.sqrt(uu)); uscale = 1.0 / beta
+        v = t / beta - beta * v
+        alfa = float(np.linalg.norm(v)); v /= alfa
+        rho = np.hypot(rhobar, beta); cs, sn = rhobar / rho, beta / rho
+        theta = sn * alfa; rhobar = -cs * alfa; phi = cs * phibar; phibar = sn * phibar
+        x1 = x1 + (phi / rho) * w
+        w = v - (theta / rho) * w
+    # CGLS: s_new = s - alpha A^T (A p) (cgls_operator_onepass); r is never formed
+    xc1 = np.zeros(n)
+    _, s, _ = normal_pass(xc1, -1.0, bl, 1.0); p = s.copy(); ns = float(s @ s)
+    for _ in range(5):
+        _, t, qq = normal_pass(p, 1.0, None, 0.0)
+        alpha = ns / qq
+        xc1 = xc1 + alpha * p; s = s - alpha * t
+        nn = float(s @ s)
+        p = s + (nn / ns) * p; ns = nn
     if rank == 0:
-        np.savez(out, x=x, xc=xc)
+        np.savez(out, x=x, xc=xc, x1=x1, xc1=xc1)
     dist.destroy_process_group()
 
 
@@ -308,3 +337,6 @@ def test_row_sharded_solver_dataflow_matches_single_process_oracle(tmp_path, orc
     xc, it, conv = orc.cgls(A, b, 1e-300, 5)
     assert np.abs(got["x"] - xl).max() <= 1e-12 * np.abs(xl).max()
     assert np.abs(got["xc"] - xc[:, 0]).max() <= 1e-12 * np.abs(xc).max()
+    # the one-pass dataflow is the same iteration up to rounding
+    assert np.abs(got["x1"] - xl).max() <= 1e-12 * np.abs(xl).max()
+    assert np.abs(got["xc1"] - xc[:, 0]).max() <= 1e-12 * np.abs(xc).max()
