@@ -250,10 +250,43 @@ def secondary_configs(torch, rt, _lib, lib, dA_headline, hbm_peak):
     dx = rt.empty_colmajor(n, 1); it = C.c_int64(0); cv = C.c_int32(0)
     ms = timed(lambda: _lib.check(lib.rnla_blendenpik_overdetermined_dev(pA, lda, m, n, C.c_void_p(db.data_ptr()), 1e-8, 100, 4.0, 2, 0, 8,
                                                                          C.c_void_p(dx.data_ptr()), C.byref(it), C.byref(cv))), 1)
-    out["c4_blendenpik_block_sparse_sign_sf4"] = {"ms": ms, "cgls_iterations": int(it.value), "converged": bool(cv.value),
-                                                  "rel_err_vs_planted": float(torch.linalg.vector_norm(dx - xt) / torch.linalg.vector_norm(xt)),
-                                                  "normal_eq_residual": float(torch.linalg.vector_norm(A4.t() @ (db - A4 @ dx)) / torch.linalg.vector_norm(A4.t() @ db)),
-                                                  "phases_ms": [[k, v] for k, v in rt.timings()]}
+    def c4_entry(ms):
+        ph = rt.timings()
+        cg_ms = sum(v for k_, v in ph if k_ == "cgls")
+        passes = int(it.value) + 1                                  # one pass per iteration + the initial residual (two-pass mode: 2 x that)
+        return {"ms": ms, "cgls_iterations": int(it.value), "converged": bool(cv.value),
+                "rel_err_vs_planted": float(torch.linalg.vector_norm(dx - xt) / torch.linalg.vector_norm(xt)),
+                "normal_eq_residual": float(torch.linalg.vector_norm(A4.t() @ (db - A4 @ dx)) / torch.linalg.vector_norm(A4.t() @ db)),
+                "cgls_ms_per_iteration": cg_ms / passes,
+                "iteration_GBps_of_A": 8.0 * m * n / (cg_ms / passes * 1e-3) * 1e-9,
+                "phases_ms": [[k_, v] for k_, v in ph]}
+    out["c4_blendenpik_block_sparse_sign_sf4"] = c4_entry(ms)
+    out["c4_blendenpik_block_sparse_sign_sf4"]["iteration"] = ("one pass over A per CGLS iteration (csrc/normal_pass.cu: clusters hold 32-row slabs in distributed "
+                                                               "shared memory; a p and a^T (a p) together): iteration_GBps_of_A counts 8 m n bytes per iteration")
+    # the same call on the two streaming mat-vec kernels (A read twice per iteration, the reference's recurrence): RNLA_ONEPASS=0
+    x_one = dx.clone()
+    os.environ["RNLA_ONEPASS"] = "0"
+    try:
+        ms2 = timed(lambda: _lib.check(lib.rnla_blendenpik_overdetermined_dev(pA, lda, m, n, C.c_void_p(db.data_ptr()), 1e-8, 100, 4.0, 2, 0, 8,
+                                                                              C.c_void_p(dx.data_ptr()), C.byref(it), C.byref(cv))), 1)
+        e2 = c4_entry(ms2)
+        e2["x_rel_diff_vs_one_pass"] = float(torch.linalg.vector_norm(dx - x_one) / torch.linalg.vector_norm(x_one))
+        out["c4_blendenpik_two_pass_iteration"] = e2
+    finally:
+        del os.environ["RNLA_ONEPASS"]
+    # lsqr (src/solvers.rs:115-278) on the same system: ten iterations with the stopping tests off
+    res_l = _lib.LsqrResult(); hist = np.zeros(16)
+    def run_lsqr():
+        _lib.check(lib.rnla_lsqr_dev(pA, lda, m, n, C.c_void_p(db.data_ptr()), 0.0, 0.0, 0.0, 0.0, 10, 0, None, C.c_void_p(dx.data_ptr()),
+                                     C.byref(res_l), C.c_void_p(hist.ctypes.data), hist.size, None))
+    ms_l1 = timed(run_lsqr, 2)
+    os.environ["RNLA_ONEPASS"] = "0"
+    try:
+        ms_l2 = timed(run_lsqr, 2)
+    finally:
+        del os.environ["RNLA_ONEPASS"]
+    out["c4_lsqr_1Mx2000_10_iterations"] = {"ms_per_iteration_one_pass": ms_l1 / 10.0, "ms_per_iteration_two_pass": ms_l2 / 10.0,
+                                            "iteration_GBps_of_A_one_pass": 8.0 * m * n / (ms_l1 / 10.0 * 1e-3) * 1e-9, "itn": int(res_l.itn)}
     nn_, r0, k, s = 50000, 400, 200, 10
     A5 = flat[: nn_ * nn_].view(nn_, nn_).t()
     V0 = rt.empty_colmajor(nn_, r0); pV, ldv = rt.dev_ptr_ld(V0)
