@@ -725,7 +725,9 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": f"rand_svd f64 {m_global}x{n} low-rank+noise, k={K_RANK}, p={S_OVER}, q={Q_PASSES}, Gaussian sketch",
                    "rows_per_gpu": m_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
-                   "sketch": "auto (materialised while Omega is L2-resident)" if args.fused == 2 else ("fused in-kernel Philox" if args.fused == 1 else "materialised"),
+                   "sketch": ("in-kernel Philox: the int8 digit planes of Omega are formed from the Philox blocks inside the operand kernels of A*Omega; "
+                              "Omega is never materialised in FP64" if any("Philox inside" in k_ for k_ in phases) else
+                              "auto (materialised while Omega is L2-resident)" if args.fused == 2 else ("fused in-kernel Philox" if args.fused == 1 else "materialised")),
                    "mode": args.mode, "range_passes_int8": MODES[args.mode],
                    "l2": f"inputs larger than L2 (A shard = {8 * m_local * n / 2**30:.1f} GiB per GPU, streamed 4x per step)"},
         "rand_svd_ms": ms_step, "step_wall_ms": [round(w, 2) for w in headline_walls], "tflops_fp64_equivalent": algorithmic_flops(m_global, n, l) / (ms_step * 1e-3) * 1e-12,

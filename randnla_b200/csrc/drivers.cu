@@ -185,6 +185,16 @@ static inline bool use_fused(const rnla_options& o, int64_t n, int l) {
 static bool g_i8_deferred = false;
 static I8Plan g_plan;          // how the current driver call spends the integer tensor cores (dev_qb1 / dev_rand_evd2 set it)
 static inline bool use_fused_forced(const rnla_options& o) { return o.fused_sketch == 1 && o.generator == RNLA_GEN_PHILOX; }
+// Integer passes: Omega enters the product as int8 digit planes (15 MB at the headline size, L2-resident).  With the counter-based
+// generator the planes are formed straight from the Philox blocks inside the operand kernels (i8gemm.cu, ThinSrc): Omega's FP64
+// values are never written to memory.  fused_sketch = 0 keeps the materialise-then-split route (bit-identical, tests compare them).
+static inline bool omega_from_generator(const rnla_options& o, const double* A, int64_t lda, int64_t m, int64_t n, int l) {
+    return o.generator == RNLA_GEN_PHILOX && o.fused_sketch != 0 && i8_active_for(A, lda, m, n, l);
+}
+static inline const char* first_pass_name(const rnla_options& o, const double* A, int64_t lda, int64_t m, int64_t n, int l) {
+    if (omega_from_generator(o, A, lda, m, n, l)) return "pass:A*Omega(Philox inside the operand kernels)";
+    return use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)";
+}
 // rnla_options.range_passes_int8 -> which passes run on the integer tensor cores and at which precision:
 //   0  every pass in FP64 (DMMA)
 //   1  A Omega, A^T Y on 31-bit operands (10 digit pairs), A S with all 16 pairs; Q^T A in FP64        (spectrum-conditional)
@@ -229,7 +239,7 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
     }
     while (q - done >= 2) {
         {
-            PhaseScope ph(virt ? (c.first_pass_hook ? (g_i8_deferred ? "upload+pass:A*Omega+i8:split(A)" : "upload+pass:A*Omega") : use_fused(o, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)") : "pass:A*S");
+            PhaseScope ph(virt ? (c.first_pass_hook ? (g_i8_deferred ? "upload+pass:A*Omega+i8:split(A)" : "upload+pass:A*Omega") : first_pass_name(o, A, lda, m, n, l)) : "pass:A*S");
             if (virt && c.first_pass_hook) {
                 // host-buffer entry point: A is still arriving over PCIe, row block by row block (api.cu)
                 auto hook = std::move(c.first_pass_hook);
@@ -253,6 +263,9 @@ static rnla_status tsog1_intended(const double* A, int64_t lda, const ShardInfo&
                 if (!split_ok) i8_deactivate();
             } else if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
                 RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
+            } else if (virt && omega_from_generator(o, A, lda, m, n, l)) {
+                i8_set_precision(g_plan.early, g_plan.early_all);
+                RNLA_TRY(i8_gemm_nn_omega(o.dist, o.seed, STREAM_RANGE_N, l, Ytmp, std::max<int64_t>(m, 1)));
             } else {
                 if (virt) RNLA_TRY(fill_operator(o.generator, o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S, n));
                 i8_set_precision(g_plan.early, g_plan.early_all);
@@ -303,9 +316,12 @@ rnla_status dev_rf1(const double* A, int64_t lda, const ShardInfo& sh, int64_t n
         DevBuf Ytmp; double* ytmp = Q;
         if (ldq != std::max<int64_t>(m, 1)) { RNLA_CUDA(Ytmp.alloc((size_t)std::max<int64_t>(m, 1) * l * 8)); ytmp = Ytmp.d(); }
         RNLA_TRY(tsog1_intended(A, lda, sh, n, l, q, pps, o, S.d(), ytmp, true, &virt));
-        PhaseScope ph(virt ? (use_fused(o, n, l) ? "pass:A*Omega(fused)" : "pass:A*Omega(materialised)") : "pass:A*S");
+        PhaseScope ph(virt ? first_pass_name(o, A, lda, m, n, l) : "pass:A*S");
         if (virt && use_fused(o, n, l) && !i8_active_for(A, lda, m, n, l)) {
             RNLA_TRY(dev_sketch_gemm(A, lda, m, n, o.dist, o.seed, STREAM_RANGE_N, l, Q, ldq));
+        } else if (virt && omega_from_generator(o, A, lda, m, n, l)) {
+            i8_set_precision(g_plan.last, g_plan.last_all);
+            RNLA_TRY(i8_gemm_nn_omega(o.dist, o.seed, STREAM_RANGE_N, l, Q, ldq));
         } else {
             if (virt) RNLA_TRY(fill_operator(o.generator, o.dist, o.seed, STREAM_RANGE_N, n, l, 0, S.d(), n));
             i8_set_precision(g_plan.last, g_plan.last_all);      // Y = A S is the product whose range becomes Q (no-op on the FP64 path)

@@ -120,6 +120,8 @@ rnla_status i8_prepare_rows(int64_t r0, int64_t count, bool phases = false);
 rnla_status i8_prepare_end(bool* usable);
 rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc);
 rnla_status i8_gemm_tn(const double* Q, int64_t ldq, int64_t N, double* Z, int64_t ldz);
+// C = A * Omega with Omega(k, c) drawn from the Philox entry map inside the operand kernels (never materialised in FP64)
+rnla_status i8_gemm_nn_omega(int dist, uint64_t seed, uint32_t stream, int64_t N, double* C, int64_t ldc);
 // how a driver spends the integer tensor cores (resolved from rnla_options.range_passes_int8 and the shape)
 struct I8Plan {
     int stored = 0;                       // digit planes of the split of A (0: FP64 kernels everywhere)

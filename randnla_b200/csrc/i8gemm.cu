@@ -28,6 +28,7 @@
 #include "gemm.cuh"
 #include "panel.cuh"
 #include "ptx.cuh"
+#include "rng.cuh"
 #include <cuda.h>
 #include <algorithm>
 #include <cmath>
@@ -287,15 +288,28 @@ slice_a_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, 
     }
 }
 
+// Where the thin operand comes from: a matrix X in memory, or -- for the first product of the range finder, Y = A Omega -- the
+// counter-based generator itself (rng.cuh: omega(k, c) is a pure function of (seed, stream, k, c)), so that Omega's FP64 values are
+// never materialised: its digit planes are formed straight from the Philox blocks, and the column maxima the split needs come from a
+// first evaluation of the same function (2.2 M Gaussians at the headline size: microseconds).  Bit-identical to materialising Omega
+// and splitting it.
+struct ThinSrc {
+    const double* X; int64_t ldx;
+    int dist;                                   // < 0: read X; else generate with (dist, seed, stream, column offset c0)
+    uint64_t seed; uint32_t stream; uint32_t c0;
+};
+__device__ __forceinline__ double thin_value(const ThinSrc& t, int64_t k, int c) {
+    return t.dist < 0 ? t.X[k + (int64_t)c * t.ldx] : omega_entry(t.dist, t.seed, t.stream, (uint64_t)k, t.c0 + (uint32_t)c);
+}
 // per-column maxima of X (K x N), optionally with the row scale folded in (X(k, c) * rs[k])
 __global__ void __launch_bounds__(256)
-colmax_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, const double* __restrict__ rs, int64_t rows_per,
+colmax_kernel(const ThinSrc src, int64_t K, int N, const double* __restrict__ rs, int64_t rows_per,
               unsigned long long* __restrict__ bits) {
     __shared__ double red[8];
     const int c = blockIdx.x;
     const int64_t k0 = (int64_t)blockIdx.y * rows_per, k1 = min(K, k0 + rows_per);
     double mx = 0.0;
-    for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) mx = fmax(mx, fabs(X[k + (int64_t)c * ldx] * (rs ? rs[k] : 1.0)));
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) mx = fmax(mx, fabs(thin_value(src, k, c) * (rs ? rs[k] : 1.0)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -317,7 +331,7 @@ colmax_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, const
 // accumulator columns [w8, w) and [w + w8, 2 w), which nobody reads.
 template <int P>
 __global__ void __launch_bounds__(256)
-slice_b2_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int w8, const double* __restrict__ rs, const double* __restrict__ cdown,
+slice_b2_kernel(const ThinSrc src, int64_t K, int N, int w8, const double* __restrict__ rs, const double* __restrict__ cdown,
                 uint8_t* __restrict__ out) {
     const int64_t kb = blockIdx.x;                          // 64 contraction indices = two image blocks
     const int kq = threadIdx.x & 15;                        // four consecutive k: one 4-byte piece of a 16-byte row of a core matrix
@@ -334,12 +348,22 @@ slice_b2_kernel(const double* __restrict__ X, int64_t ldx, int64_t K, int N, int
         for (int t = 0; t < P; ++t) wd[t] = 0u;
         if (c < N) {
             const double cd = cdown[c];
+            double xv[4];
+            if (src.dist < 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) xv[e] = k0 + e < K ? src.X[k0 + e + (int64_t)c * src.ldx] : 0.0;
+            } else {
+                // k0 is a multiple of 4: the four values are the four words of ONE Philox block (rng.cuh omega_block)
+                const u32x4 b = omega_block(src.seed, src.stream, (uint64_t)k0 >> 2, src.c0 + (uint32_t)c);
+                xv[0] = sample_from_u32(src.dist, b.x); xv[1] = sample_from_u32(src.dist, b.y);
+                xv[2] = sample_from_u32(src.dist, b.z); xv[3] = sample_from_u32(src.dist, b.w);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 int d[P];
 #pragma unroll
                 for (int t = 0; t < P; ++t) d[t] = 0;
-                if (k0 + e < K) digits<P>(X[k0 + e + (int64_t)c * ldx] * rsk[e], cd, d);
+                if (k0 + e < K) digits<P>(xv[e] * rsk[e], cd, d);
 #pragma unroll
                 for (int t = 0; t < P; ++t) wd[t] |= ((unsigned)d[t] & 0xffu) << (8 * e);
             }
@@ -628,19 +652,19 @@ inline int pair_w8(int N) { return 8 * ((N + 15) / 16); }                 // thi
 // tcgen05.mma.cta_group::2.kind::i8 takes N in steps of 16: the MMA reads exactly the w8 columns per rank that the images hold
 // (N_mma = 112 at l = 110; CuTe's static_assert of N % 32 is a library limit -- the products are bit-identical to the CPU emulation
 // at N_mma = 16, 48, 80, 112, ... on the B200, tests/test_gpu_parity.py).
-rnla_status slice_b(const double* X, int64_t ldx, int64_t K, int N, const double* rs, int64_t kblocks, int planes) {
+rnla_status slice_b(const ThinSrc& src, int64_t K, int N, const double* rs, int64_t kblocks, int planes) {
     Ctx& c = ctx();
     const int w8 = pair_w8(N);
     RNLA_CUDA(g_sl.bimg.ensure((size_t)kblocks * planes * w8 * 128));       // kblocks blocks of 64 = 2 kblocks steps of 32, two ranks each
     RNLA_CUDA(cudaMemsetAsync(g_sl.cbits.p, 0, 128 * 8, c.stream));
     const int64_t rows_per = 32768;
-    colmax_kernel<<<dim3((unsigned)N, (unsigned)((K + rows_per - 1) / rows_per)), 256, 0, c.stream>>>(X, ldx, K, N, rs, rows_per,
+    colmax_kernel<<<dim3((unsigned)N, (unsigned)((K + rows_per - 1) / rows_per)), 256, 0, c.stream>>>(src, K, N, rs, rows_per,
                                                                                                       g_sl.cbits.as<unsigned long long>());
     scales_kernel<<<1, 128, 0, c.stream>>>(g_sl.cbits.as<unsigned long long>(), 128, g_sl.cup.d(), g_sl.cdown.d(), g_sl.flags.as<int>() + 1);
     uint8_t* out = g_sl.bimg.as<uint8_t>();
-    if (planes == 4) slice_b2_kernel<4><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
-    else if (planes == 6) slice_b2_kernel<6><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
-    else slice_b2_kernel<7><<<(unsigned)kblocks, 256, 0, c.stream>>>(X, ldx, K, N, w8, rs, g_sl.cdown.d(), out);
+    if (planes == 4) slice_b2_kernel<4><<<(unsigned)kblocks, 256, 0, c.stream>>>(src, K, N, w8, rs, g_sl.cdown.d(), out);
+    else if (planes == 6) slice_b2_kernel<6><<<(unsigned)kblocks, 256, 0, c.stream>>>(src, K, N, w8, rs, g_sl.cdown.d(), out);
+    else slice_b2_kernel<7><<<(unsigned)kblocks, 256, 0, c.stream>>>(src, K, N, w8, rs, g_sl.cdown.d(), out);
     g_kernel_launches += 3;
     RNLA_CUDA(cudaGetLastError());
     return RNLA_OK;
@@ -873,15 +897,21 @@ rnla_status i8_prepare(const double* A, int64_t lda, int64_t m, int64_t n, int p
 }
 
 // C (m x N) = A * B (n x N) on the split A
-static rnla_status i8_gemm_nn_tile(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc) {
+static rnla_status i8_gemm_nn_tile(const ThinSrc& src, int64_t N, double* C, int64_t ldc) {
     Sliced& s = g_sl;
     const int64_t kblocks = 2 * s.cblocks;
-    RNLA_TRY(slice_b(B, ldb, s.n, (int)N, nullptr, kblocks, g_planes));
+    RNLA_TRY(slice_b(src, s.n, (int)N, nullptr, kblocks, g_planes));
     return run_sweeps<false>(dim3((unsigned)s.rblocks, 1), kblocks, kblocks, C, ldc, s.m, (int)N, s.up.d(), 0);
 }
 rnla_status i8_gemm_nn(const double* B, int64_t ldb, int64_t N, double* C, int64_t ldc) {
     for (int64_t c0 = 0; c0 < N; c0 += BN)
-        RNLA_TRY(i8_gemm_nn_tile(B + c0 * ldb, ldb, std::min<int64_t>(BN, N - c0), C + c0 * ldc, ldc));
+        RNLA_TRY(i8_gemm_nn_tile(ThinSrc{B + c0 * ldb, ldb, -1, 0, 0, 0}, std::min<int64_t>(BN, N - c0), C + c0 * ldc, ldc));
+    return RNLA_OK;
+}
+// C (m x N) = A * Omega (n x N), Omega(k, c) = the Philox entry map of rng.cuh: Omega is never materialised in FP64
+rnla_status i8_gemm_nn_omega(int dist, uint64_t seed, uint32_t stream, int64_t N, double* C, int64_t ldc) {
+    for (int64_t c0 = 0; c0 < N; c0 += BN)
+        RNLA_TRY(i8_gemm_nn_tile(ThinSrc{nullptr, 0, dist, seed, stream, (uint32_t)c0}, std::min<int64_t>(BN, N - c0), C + c0 * ldc, ldc));
     return RNLA_OK;
 }
 
@@ -906,7 +936,7 @@ static rnla_status i8_gemm_tn_tile(const double* Q, int64_t ldq, int64_t N, doub
     Ctx& c = ctx();
     Sliced& s = g_sl;
     const int64_t kblocks = 2 * s.rblocks;
-    RNLA_TRY(slice_b(Q, ldq, s.m, (int)N, s.up.d(), kblocks, g_planes));
+    RNLA_TRY(slice_b(ThinSrc{Q, ldq, -1, 0, 0, 0}, s.m, (int)N, s.up.d(), kblocks, g_planes));
     // row chunks: enough (column block, chunk) units to fill the SMs a few times over; the partials are summed in chunk order
     int64_t nchunks = pair_chunks((s.cblocks + 1) / 2, kblocks, c.sms);
     const int64_t per = (kblocks + nchunks - 1) / nchunks;

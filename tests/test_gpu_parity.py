@@ -1123,6 +1123,28 @@ def test_rand_svd_int8_range_passes_match_the_oracle(rb, orc, m, n, k, s, level)
     assert not any("i8:split(A)" in nm for nm, _ in rt.timings())
 
 
+@pytest.mark.parametrize("m,n,k,s,q", [(6000, 1500, 32, 10, 2), (4224, 2300, 40, 8, 4), (5000, 1200, 150, 10, 2)])
+def test_int8_first_pass_draws_omega_inside_the_operand_kernels(rb, orc, m, n, k, s, q):
+    """Default path (integer passes, Philox generator): the digit planes of Omega are formed straight from the Philox blocks inside
+    the operand kernels of Y = A Omega (csrc/i8gemm.cu ThinSrc) -- Omega's FP64 values never exist in memory.  The result is
+    BIT-IDENTICAL to materialising Omega and splitting it (fused_sketch = 0), for one and for two 128-column tiles of the thin
+    operand, and agrees with the oracle (same Omega) to the north_star tolerance."""
+    from randnla_b200 import runtime as rt, lora_drivers as ld
+    A, sig = lowrank_plus_noise(m, n, seed=7, k=k)
+    out = {}
+    for fused in (2, 0):
+        with rt.options(fused_sketch=fused, num_passes=q):
+            out[fused] = ld.rand_svd(A, k, 1e-6, s)
+            names = [nm for nm, _ in rt.timings()]
+        assert any("i8:split(A)" in nm for nm in names)
+        want = "pass:A*Omega(Philox inside the operand kernels)" if fused == 2 else "pass:A*Omega(materialised)"
+        assert want in names, names
+    for a, b in zip(out[2], out[0]):
+        assert np.array_equal(a, b)
+    _, So, _ = orc.rand_svd(A, k, 1e-6, s, orc.make_opts(mode=0, num_passes=q))
+    assert np.max(np.abs(np.diag(out[2][1]) - np.diag(So)) / np.diag(So)) < SIG_TOL
+
+
 @pytest.mark.parametrize("level", [1, 2, 3])
 def test_rand_evd1_int8_passes_match_the_oracle(rb, orc, level):
     """rand_evd1 (reference src/lora_drivers.rs:87-151) goes through QB1 as well: with the passes on the integer tensor cores
