@@ -50,4 +50,5 @@ def test_row_sharded_drivers_match_the_single_gpu_run(world):
     assert out["max_rel_sigma_diff_vs_1gpu"] < 1e-10 and out["orth"] < 1e-12
     assert out["saso_block_max_abs_diff_vs_1gpu"] < 1e-12 and out["blendenpik_x_rel_diff_vs_1gpu"] < 1e-8
     assert out["lsqr_x_rel_diff_vs_1gpu"] < 1e-9 and out["cgls_plain_x_rel_diff_vs_1gpu"] < 1e-9
+    assert out["solver_iterations_read_A_once"] and ref["solver_iterations_read_A_once"]      # the sharded one-pass dataflow ran
     assert out["pass"], out

@@ -35,11 +35,16 @@ d = 1200
 dS = rt.empty_colmajor(d, N); pS, lds = rt.dev_ptr_ld(dS)
 _lib.check(lib.rnla_sketch_apply_dev(2, 0, 5, d, 8, pA, lda, ml, N, off, pS, lds)); rt.synchronize()
 sk = dS.cpu().numpy()
-# blendenpik on a least-squares problem built from the same shard
+# blendenpik on a least-squares problem built from the same shard.  The solvers take 1600 columns: within the width (n <= 2048) at which
+# their iterations read A once per iteration (csrc/normal_pass.cu), so the sharded one-pass dataflow (one all-reduce of n + 1 doubles per
+# iteration) is what runs here
+N_RANDSVD = N
+N = 1600
 torch.manual_seed(1)
 xt = torch.rand(N, 1, dtype=torch.float64, device="cuda") * 2 - 1
 dB = rt.empty_colmajor(ml, N); pB, ldb = rt.dev_ptr_ld(dB)
 _lib.check(lib.rnla_sketch_fill_dev(0, 0, 9, 9, ml, N, off, pB, ldb)); rt.synchronize()
+one_pass = bool(lib.rnla_normal_pass_supported(pB, ldb, ml, N))
 db = rt.empty_colmajor(ml, 1); db.copy_(dB @ xt)
 dx = rt.empty_colmajor(N, 1); it = C.c_int64(0); cv = C.c_int32(0)
 _lib.check(lib.rnla_blendenpik_overdetermined_dev(pB, ldb, ml, N, C.c_void_p(db.data_ptr()), 1e-9, 100, 2.0, 2, 0, 8,
@@ -58,7 +63,7 @@ xl = dxl.cpu().numpy()
 dxc = rt.empty_colmajor(N, 1); dxc.zero_(); itc = C.c_int64(0); cvc = C.c_int32(0)
 _lib.check(lib.rnla_cgls_dev(pB, ldb, ml, N, C.c_void_p(db2.data_ptr()), 1e-9, 200, C.c_void_p(dxc.data_ptr()), C.byref(itc), C.byref(cvc)))
 xc = dxc.cpu().numpy()
-lsq = {"lsqr_istop": int(res.istop), "lsqr_itn": int(res.itn), "lsqr_r1norm": res.r1norm, "lsqr_anorm": res.anorm, "lsqr_xnorm": res.xnorm,
+lsq = {"solver_iterations_read_A_once": one_pass, "lsqr_istop": int(res.istop), "lsqr_itn": int(res.itn), "lsqr_r1norm": res.r1norm, "lsqr_anorm": res.anorm, "lsqr_xnorm": res.xnorm,
        "cgls_plain_iterations": int(itc.value), "cgls_plain_converged": bool(cvc.value),
        "lsqr_vs_cgls_x_rel_diff": float(np.linalg.norm(xl - xc) / np.linalg.norm(xc))}
 os.makedirs("gpurun_out", exist_ok=True)
