@@ -130,8 +130,15 @@ normal_pass_kernel(const __grid_constant__ CUtensorMap tmA, const NpArgs a) {
 #pragma unroll
                 for (int ww = 0; ww < NP_GW; ++ww) part += rd[ww * 32 + lane];
                 const int slot = i % NP_XS;
-                const uint32_t dst = smem_u32(xbuf + (slot * NP_CMAX + (int)rank) * 32 + lane), bar = smem_u32(xfull + slot);
-                for (uint32_t c = 0; c < csize; ++c) np_st_async(dst, bar, c, part);
+                if (csize == 1) {
+                    // a cluster of one CTA has no distributed shared memory: plain store, the warp's arrival completes the slot's phase
+                    xbuf[slot * NP_CMAX * 32 + lane] = part;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(xfull + slot);
+                } else {
+                    const uint32_t dst = smem_u32(xbuf + (slot * NP_CMAX + (int)rank) * 32 + lane), bar = smem_u32(xfull + slot);
+                    for (uint32_t c = 0; c < csize; ++c) np_st_async(dst, bar, c, part);
+                }
             }
         }
     } else {
@@ -142,13 +149,14 @@ normal_pass_kernel(const __grid_constant__ CUtensorMap tmA, const NpArgs a) {
         for (int k = 0; k < 32; ++k) acc[k] = 0.0;
         double uu = 0.0;
         const uint32_t xbytes = csize * 32u * 8u;
-        if (cnt > 0 && w == 0 && lane == 0) mbar_arrive_expect_tx(xfull + 0, xbytes);
+        const bool arm = csize > 1 && w == 0 && lane == 0;       // (one CTA: the row group's arrival completes the phase instead)
+        if (cnt > 0 && arm) mbar_arrive_expect_tx(xfull + 0, xbytes);
         int64_t row = g * NP_R + lane;
         double yv = (cnt > 0 && a.y != nullptr && row < a.m) ? a.y[row] : 0.0;
         for (int i = 0; i < cnt; ++i) {
             const int st = i % NP_STAGES, slot = i % NP_XS;
             // next slab: arm its exchange barrier (its previous phase, slab i + 1 - 8, completed long ago) and fetch its y
-            if (i + 1 < cnt && w == 0 && lane == 0) mbar_arrive_expect_tx(xfull + (i + 1) % NP_XS, xbytes);
+            if (i + 1 < cnt && arm) mbar_arrive_expect_tx(xfull + (i + 1) % NP_XS, xbytes);
             const int64_t row_next = (g + (int64_t)(i + 1) * G) * NP_R + lane;
             const double y_next = (i + 1 < cnt && a.y != nullptr && row_next < a.m) ? a.y[row_next] : 0.0;
             mbar_wait(full + st, (uint32_t)(i / NP_STAGES) & 1u);
