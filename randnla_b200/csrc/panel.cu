@@ -4,6 +4,7 @@
 #include "gemm.cuh"
 #include "rng.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cfloat>
 #include <cooperative_groups.h>
 #include <cmath>
@@ -245,6 +246,162 @@ tri_inv_upper_smem_kernel(const double* __restrict__ R, int64_t ldr, int p, doub
         double* x = X + (int64_t)j * ldi;
         for (int i = l16; i < p; i += 16) x[i] = i <= j ? xs[i] : 0.0;
         __syncwarp(gmask);
+    }
+}
+
+// Blocked variants (round 2): the kernels above pay three CTA-wide barriers, a square root and a division per COLUMN (p = 128: 140 us
+// per factorisation, 112 us per inverse -- 80 such launches are 10 ms of blendenpik's preconditioner).  Here the p dependent steps
+// become p / 16 (p / 32) block steps.
+//   chol_upper_blocked_kernel: right-looking over column blocks of 16 on the packed upper triangle: warp 0 factors the 16 x 16
+//     diagonal block (same pivot / deficiency rule per column, in the same order), one thread per trailing column solves the 16-row
+//     panel by forward substitution in registers, and the whole CTA applies the rank-16 update.  A deficient column has pivot 1, a
+//     zero row and contributes nothing, exactly as in the unblocked kernels.
+//   tri_inv_upper_blocked_kernel (p <= 144): blocks of 32; every diagonal block is inverted by one warp (lane = column of the
+//     inverse, private back substitution on its own column in shared memory, reciprocal diagonal precomputed), then block back substitution
+//     X_IJ = - X_II sum_{I < K <= J} R_IK X_KJ for I = J - 1, J - 2, ... with the whole CTA on every block (lane = row: the loads of R
+//     and X_II are consecutive, those of X_KJ and of the intermediate product broadcasts).
+constexpr int CHB = 16;
+__global__ void __launch_bounds__(512)
+chol_upper_blocked_kernel(double* __restrict__ G, int64_t ld, int p, double tol2, int* __restrict__ flags, int* __restrict__ info) {
+    extern __shared__ double gs[];
+    double* diag0 = gs + (size_t)p * (p + 1) / 2;       // original diagonal
+    __shared__ double b_inv[CHB];
+    __shared__ int s_ndef, s_bad, s_nzero;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        if (r <= c) { const double v = G[r + (int64_t)c * ld]; gs[pk(r, c)] = v; if (r == c) diag0[c] = v; }
+    }
+    if (tid == 0) { s_ndef = 0; s_bad = 0; s_nzero = 0; }
+    __syncthreads();
+    for (int j0 = 0; j0 < p; j0 += CHB) {
+        const int nb = min(CHB, p - j0), j1 = j0 + nb;
+        if (warp == 0) {
+            for (int jj = 0; jj < nb; ++jj) {
+                const int j = j0 + jj;
+                const double gjj = diag0[j];
+                const double d = gs[pk(j, j)];          // G_jj - sum_{k<j} R_kj^2 after the updates so far
+                int def = 0;
+                if (!(gjj > 0.0)) def = 2;
+                else if (!(d > tol2 * gjj)) def = 1;
+                const bool bad = !isfinite(gjj) || !isfinite(d);
+                if (bad) def = 2;
+                const double piv = def ? 1.0 : sqrt(d), inv = def ? 0.0 : 1.0 / piv;
+                __syncwarp();                           // every lane has read d
+                if (lane == 0) {
+                    gs[pk(j, j)] = piv; flags[j] = def; b_inv[jj] = inv;
+                    if (bad) s_bad = 1;
+                    s_ndef += (def != 0); s_nzero += (def == 2);
+                }
+                const int i = j + 1 + lane;             // scale row j inside the block
+                if (i < j1) gs[pk(j, i)] = def ? 0.0 : gs[pk(j, i)] * inv;
+                __syncwarp();
+                if (!def) {
+                    // rank-1 update of the rest of the block, its 16 x 16 index square spread over the lanes
+#pragma unroll
+                    for (int e = lane; e < CHB * CHB; e += 32) {
+                        const int k = j0 + (e & (CHB - 1)), c = j0 + (e >> 4);
+                        if (k > j && k <= c && c < j1) gs[pk(k, c)] = fma(-gs[pk(j, k)], gs[pk(j, c)], gs[pk(k, c)]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // the 16-row panel right of the block: R[j0.., i] = D^-T G[j0.., i], one thread per column i
+        for (int i = j1 + tid; i < p; i += blockDim.x) {
+            double* gi = gs + pk(0, i);
+            double g[CHB];
+#pragma unroll
+            for (int kk = 0; kk < CHB; ++kk) g[kk] = kk < nb ? gi[j0 + kk] : 0.0;
+#pragma unroll
+            for (int kk = 0; kk < CHB; ++kk) {
+                if (kk < nb) {
+                    const double* rk = gs + pk(0, j0 + kk);
+                    double sum = g[kk];
+#pragma unroll
+                    for (int l = 0; l < kk; ++l) sum = fma(-rk[j0 + l], g[l], sum);
+                    g[kk] = sum * b_inv[kk];            // a deficient column: inverse pivot 0, zero row
+                    gi[j0 + kk] = g[kk];
+                }
+            }
+        }
+        __syncthreads();
+        // rank-nb update of the trailing triangle
+        for (int i = j1 + warp; i < p; i += (int)(blockDim.x >> 5)) {
+            double ri[CHB];
+            double* gi = gs + pk(0, i);
+#pragma unroll
+            for (int kk = 0; kk < CHB; ++kk) ri[kk] = kk < nb ? gi[j0 + kk] : 0.0;
+            for (int k = j1 + lane; k <= i; k += 32) {
+                const double* gk = gs + pk(0, k);
+                double sum = gi[k];
+#pragma unroll
+                for (int kk = 0; kk < CHB; ++kk) sum = fma(-gk[min(j0 + kk, j1 - 1)], ri[kk], sum);
+                gi[k] = sum;
+            }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        G[r + (int64_t)c * ld] = r <= c ? gs[pk(r, c)] : 0.0;
+    }
+    if (tid == 0) { info[0] = s_ndef; info[1] = s_bad; info[2] = s_nzero; }
+}
+
+constexpr int TIB = 32;
+__global__ void __launch_bounds__(1024)
+tri_inv_upper_blocked_kernel(const double* __restrict__ R, int64_t ldr, int p, double* __restrict__ X, int64_t ldi) {
+    extern __shared__ double gs[];
+    const size_t tri = (size_t)p * (p + 1) / 2;
+    double* rs = gs;                                    // R, packed by columns: (k, j), k <= j, at j (j + 1) / 2 + k
+    double* xs = gs + tri;                              // the inverse, same packing
+    double* dinv = xs + tri;                            // 1 / R_ii
+    double* tb = dinv + p;                              // 32 x 32 intermediate block, [c][r]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbk = (p + TIB - 1) / TIB;
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        if (r <= c) { const double v = R[r + (int64_t)c * ldr]; rs[pk(r, c)] = v; if (r == c) dinv[r] = 1.0 / v; }
+    }
+    __syncthreads();
+    // diagonal blocks: warp b inverts block b, lane = column of the inverse
+    if (warp < nbk) {
+        const int c0 = warp * TIB, j = c0 + lane;
+        if (j < p) {
+            double* xc = xs + pk(0, j);                 // this lane's column of the inverse, rows c0 .. j
+            for (int ii = lane; ii >= 0; --ii) {
+                double sum = (ii == lane) ? 1.0 : 0.0;
+                for (int kk = ii + 1; kk <= lane; ++kk) sum = fma(-rs[pk(c0 + ii, c0 + kk)], xc[c0 + kk], sum);
+                xc[c0 + ii] = sum * dinv[c0 + ii];
+            }
+        }
+    }
+    __syncthreads();
+    // block back substitution, distance s from the diagonal: every thread one element (r = lane, c = warp) of every block (I, I + s)
+    for (int sdist = 1; sdist < nbk; ++sdist) {
+        for (int J = sdist; J < nbk; ++J) {
+            const int I = J - sdist;
+            const int row = I * TIB + lane, col = J * TIB + warp;
+            double t = 0.0;
+            if (col < p) {
+                const double* xc = xs + pk(0, col);
+                for (int k = (I + 1) * TIB; k <= min(col, (J + 1) * TIB - 1); ++k) t = fma(rs[pk(row, k)], xc[k], t);     // row < k: inside the triangle
+            }
+            tb[warp * TIB + lane] = t;
+            __syncthreads();
+            if (col < p) {
+                double v = 0.0;
+                for (int kk = lane; kk < TIB; ++kk) v = fma(xs[pk(row, I * TIB + kk)], tb[warp * TIB + kk], v);
+                xs[pk(row, col)] = -v;
+            }
+            __syncthreads();
+        }
+    }
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        X[r + (int64_t)c * ldi] = r <= c ? xs[pk(r, c)] : 0.0;
     }
 }
 
@@ -736,16 +893,33 @@ cudaError_t chol_upper(double* G, int64_t ld, int p, double tol2, int* flags, in
         static bool attr = false;
         if (!attr) {
             cudaError_t e = cudaFuncSetAttribute(chol_upper_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_upper_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM);
             if (e != cudaSuccess) return e;
             attr = true;
         }
-        chol_upper_smem_kernel<<<1, 1024, need, st>>>(G, ld, p, tol2, flags, info);
+        const char* oe = getenv("RNLA_SMALL_OLD");              // the unblocked kernels, for comparison
+        const bool old_kernels = oe && oe[0] == '1';
+        if (old_kernels) chol_upper_smem_kernel<<<1, 1024, need, st>>>(G, ld, p, tol2, flags, info);
+        else chol_upper_blocked_kernel<<<1, 512, need, st>>>(G, ld, p, tol2, flags, info);
     } else {
         chol_upper_kernel<<<1, 1024, 0, st>>>(G, ld, p, tol2, flags, info);
     }
     return LAUNCHED();
 }
 cudaError_t tri_inv_upper(const double* R, int64_t ldr, int p, double* Rinv, int64_t ldi, cudaStream_t st) {
+    const char* oe = getenv("RNLA_SMALL_OLD");
+    const bool old_kernels = oe && oe[0] == '1';
+    const size_t need_blocked = ((size_t)p * (p + 1) + (size_t)p + TIB * TIB) * 8;
+    if (!old_kernels && p >= 1 && need_blocked <= SMALL_SMEM) {
+        static bool battr = false;
+        if (!battr) {
+            cudaError_t e = cudaFuncSetAttribute(tri_inv_upper_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM);
+            if (e != cudaSuccess) return e;
+            battr = true;
+        }
+        tri_inv_upper_blocked_kernel<<<1, 1024, need_blocked, st>>>(R, ldr, p, Rinv, ldi);
+        return LAUNCHED();
+    }
     const size_t base = ((size_t)p * (p + 1) / 2 + (size_t)p) * 8;
     int ngrp = base + 2 * (size_t)p * 8 <= SMALL_SMEM ? (int)((SMALL_SMEM - base) / ((size_t)p * 8)) : 0;
     ngrp = std::min(64, ngrp) & ~1;                       // whole warps
