@@ -405,6 +405,64 @@ tri_inv_upper_blocked_kernel(const double* __restrict__ R, int64_t ldr, int p, d
     }
 }
 
+// The same inverse IN PLACE on one packed triangle, for 144 < p <= 210 (two triangles no longer fit in shared memory): diagonal blocks
+// one after the other through a 32 x 32 scratch block, then block columns from the LAST to the first and, inside a block column, block
+// rows upwards: X_IJ = - X_II sum_{I < K <= J} R_IK X_KJ overwrites R_IJ when nothing needs it any more (the blocks R_IK, K < J, belong
+// to block columns that come later; X_KJ, K > I, were finished just before).
+__global__ void __launch_bounds__(1024)
+tri_inv_upper_inplace_kernel(const double* __restrict__ R, int64_t ldr, int p, double* __restrict__ X, int64_t ldi) {
+    extern __shared__ double gs[];
+    double* rs = gs;                                    // R on entry, its inverse on exit; packed by columns
+    double* dinv = gs + (size_t)p * (p + 1) / 2;
+    double* tb = dinv + p;                              // 32 x 32 scratch, [c][r]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbk = (p + TIB - 1) / TIB;
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        if (r <= c) { const double v = R[r + (int64_t)c * ldr]; rs[pk(r, c)] = v; if (r == c) dinv[r] = 1.0 / v; }
+    }
+    __syncthreads();
+    for (int b = 0; b < nbk; ++b) {
+        const int c0 = b * TIB;
+        if (warp == 0) {
+            const int j = c0 + lane;
+            double* xc = tb + lane * TIB;               // this lane's column of the block's inverse
+            if (j < p) {
+                for (int ii = lane; ii >= 0; --ii) {
+                    double sum = (ii == lane) ? 1.0 : 0.0;
+                    for (int kk = ii + 1; kk <= lane; ++kk) sum = fma(-rs[pk(c0 + ii, c0 + kk)], xc[kk], sum);
+                    xc[ii] = sum * dinv[c0 + ii];
+                }
+            }
+            __syncwarp();
+            if (j < p) for (int ii = 0; ii <= lane; ++ii) rs[pk(c0 + ii, j)] = xc[ii];
+        }
+        __syncthreads();
+    }
+    for (int J = nbk - 1; J >= 1; --J) {
+        for (int I = J - 1; I >= 0; --I) {
+            const int row = I * TIB + lane, col = J * TIB + warp;
+            double t = 0.0;
+            if (col < p) {
+                const double* xc = rs + pk(0, col);
+                for (int k = (I + 1) * TIB; k <= min(col, (J + 1) * TIB - 1); ++k) t = fma(rs[pk(row, k)], xc[k], t);
+            }
+            tb[warp * TIB + lane] = t;
+            __syncthreads();
+            if (col < p) {
+                double v = 0.0;
+                for (int kk = lane; kk < TIB; ++kk) v = fma(rs[pk(row, I * TIB + kk)], tb[warp * TIB + kk], v);
+                rs[pk(row, col)] = -v;
+            }
+            __syncthreads();
+        }
+    }
+    for (int idx = tid; idx < p * p; idx += blockDim.x) {
+        const int c = idx / p, r = idx - c * p;
+        X[r + (int64_t)c * ldi] = r <= c ? rs[pk(r, c)] : 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 small_gemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
                   double* __restrict__ C, int64_t ldc, int M, int N, int K) {
@@ -918,6 +976,17 @@ cudaError_t tri_inv_upper(const double* R, int64_t ldr, int p, double* Rinv, int
             battr = true;
         }
         tri_inv_upper_blocked_kernel<<<1, 1024, need_blocked, st>>>(R, ldr, p, Rinv, ldi);
+        return LAUNCHED();
+    }
+    const size_t need_inplace = ((size_t)p * (p + 1) / 2 + (size_t)p + TIB * TIB) * 8;
+    if (!old_kernels && p >= 1 && need_inplace <= SMALL_SMEM) {
+        static bool iattr = false;
+        if (!iattr) {
+            cudaError_t e = cudaFuncSetAttribute(tri_inv_upper_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM);
+            if (e != cudaSuccess) return e;
+            iattr = true;
+        }
+        tri_inv_upper_inplace_kernel<<<1, 1024, need_inplace, st>>>(R, ldr, p, Rinv, ldi);
         return LAUNCHED();
     }
     const size_t base = ((size_t)p * (p + 1) / 2 + (size_t)p) * 8;

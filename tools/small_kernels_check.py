@@ -17,7 +17,7 @@ def orth(X):
 rng = np.random.default_rng(0)
 worst = 0.0
 for (m, p, kind) in [(3000, 5, "rand"), (4000, 16, "rand"), (5000, 17, "ill"), (8000, 110, "rand"), (8000, 128, "ill"), (6000, 97, "rankdef"), (7000, 144, "rand"),
-                     (9000, 145, "rand"), (5000, 210, "ill"), (4000, 64, "zero"), (5000, 33, "rankdef")]:
+                     (9000, 145, "rand"), (5000, 210, "ill"), (6000, 200, "rand"), (5000, 177, "rankdef"), (4000, 64, "zero"), (5000, 33, "rankdef")]:
     X = rng.standard_normal((m, p))
     if kind == "ill": X = X * np.logspace(0, -6, p)
     if kind == "rankdef": X[:, p // 2] = X[:, 0] + X[:, 1]; X[:, p - 1] = 2 * X[:, 3]
