@@ -661,6 +661,104 @@ rnla_status axpby_nrm2(Solver& S, double a, const double* x, double b, double* y
     return RNLA_OK;
 }
 
+// ---- one iteration's n-vector work and scalar recurrences in ONE single-CTA kernel (one-pass mode: n <= 2048) -------------------------
+// Input t (n + 1): a^T u~ and ||u~||^2 from normal_pass.cu.  The kernel does :196-261 of src/solvers.rs: beta, the v update and alfa,
+// the plane rotations, the x / w / var update with ||dk||^2, the norm estimates and the seven stopping tests; the host reads the state
+// back once per iteration (it needs alfa and beta for the next pass's coefficient, arnorm for the history and istop).
+struct LsqrState {
+    double alfa, beta, rhobar, phibar, anorm, ddnorm, res2, xnorm, xxnorm, z, cs2, sn2;     // carried from iteration to iteration
+    double arnorm, rnorm, r1norm, r2norm, acond, istop;                                      // produced
+};
+__device__ __forceinline__ double dev_sgn(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
+__device__ __forceinline__ void dev_sym_ortho(double a, double b, double* c, double* s, double* r) {      // :84-103
+    if (b == 0.0) { *c = dev_sgn(a); *s = 0.0; *r = fabs(a); }
+    else if (a == 0.0) { *c = 0.0; *s = dev_sgn(b); *r = fabs(b); }
+    else if (fabs(b) > fabs(a)) { const double tau = a / b; *s = dev_sgn(b) / sqrt(1.0 + tau * tau); *c = *s * tau; *r = b / *s; }
+    else { const double tau = b / a; *c = dev_sgn(a) / sqrt(1.0 + tau * tau); *s = *c * tau; *r = a / *c; }
+}
+// sum over the CTA in a fixed order; every thread gets the result
+__device__ __forceinline__ double cta_sum_1024(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += red[w];
+    return t;
+}
+__global__ void __launch_bounds__(1024)
+lsqr_step_kernel(int n, const double* __restrict__ t, double* __restrict__ v, double* __restrict__ w, double* __restrict__ x,
+                 double* __restrict__ var, LsqrState* __restrict__ st, double damp, double bnorm, double atol, double btol, double ctol,
+                 long long itn, long long iter_lim) {
+    __shared__ double red[32];
+    const double eps = 2.220446049250313e-16, dampsq = damp * damp;
+    LsqrState s = *st;
+    const int tid = threadIdx.x;
+    double alfa = s.alfa, anorm = s.anorm;
+    const double beta = sqrt(t[n]);                                                                       // :196
+    if (beta > 0.0) {
+        const double a = 1.0 / beta, b = -beta;                                                           // u = u~ / beta stays implicit
+        double loc = 0.0;
+        for (int j = tid; j < n; j += 1024) { const double val = a * t[j] + b * v[j]; v[j] = val; loc = fma(val, val, loc); }   // :202
+        const double vv = cta_sum_1024(loc, red);
+        anorm = sqrt(anorm * anorm + alfa * alfa + beta * beta + dampsq);                                 // :200
+        alfa = sqrt(vv);                                                                                  // :203
+        const double sc = alfa > 0.0 ? 1.0 / alfa : 0.0;
+        for (int j = tid; j < n; j += 1024) v[j] *= sc;                                                   // :204
+    }
+    const double rhobar1 = sqrt(s.rhobar * s.rhobar + dampsq);                                            // :208-212
+    const double cs1 = s.rhobar / rhobar1, sn1 = damp / rhobar1;
+    const double psi = sn1 * s.phibar;
+    double phibar = s.phibar * cs1;
+    double cs, sn, rho;
+    dev_sym_ortho(rhobar1, beta, &cs, &sn, &rho);                                                         // :214
+    const double theta = sn * alfa;
+    const double rhobar = -cs * alfa;
+    const double phi = cs * phibar;
+    phibar *= sn;
+    const double tau = sn * phi;
+    const double t1 = phi / rho, t2 = -theta / rho, inv_rho = 1.0 / rho;                                  // :222-223
+    double loc = 0.0;
+    for (int j = tid; j < n; j += 1024) {                                                                 // :224-232
+        const double wi = w[j], dk = wi * inv_rho;
+        x[j] += t1 * wi;
+        w[j] = v[j] + t2 * wi;
+        loc = fma(dk, dk, loc);
+        if (var) var[j] += dk * dk;
+    }
+    const double ddnorm = s.ddnorm + cta_sum_1024(loc, red);
+    const double delta = s.sn2 * rho, gambar = -s.cs2 * rho, rhs = phi - delta * s.z, zbar = rhs / gambar;   // :235-244
+    const double xnorm = sqrt(s.xxnorm + zbar * zbar);
+    const double gamma = sqrt(gambar * gambar + theta * theta);
+    const double cs2 = gambar / gamma, sn2 = theta / gamma, z = rhs / gamma;
+    const double xxnorm = s.xxnorm + z * z;
+    const double acond = anorm * sqrt(ddnorm);                                                            // :247-251
+    const double res1 = phibar * phibar;
+    const double res2 = s.res2 + psi * psi;
+    const double rnorm = sqrt(res1 + res2);
+    const double arnorm = alfa * fabs(tau);
+    const double r1sq = rnorm * rnorm - dampsq * xxnorm;                                                  // :253-255
+    const double r1norm = sqrt(fabs(r1sq));
+    const double test1 = rnorm / bnorm, test2 = arnorm / (anorm * rnorm + eps), test3 = 1.0 / (acond + eps);   // :257-261
+    const double tt1 = test1 / (1.0 + anorm * xnorm / bnorm), rtol = atol + btol * (anorm * xnorm / bnorm);
+    int istop = 0;
+    if (itn >= iter_lim) istop = 7;                                                                       // :264-270
+    if (1.0 + test3 <= 1.0) istop = 6;
+    if (1.0 + test2 <= 1.0) istop = 5;
+    if (1.0 + tt1 <= 1.0) istop = 4;
+    if (test3 <= ctol) istop = 3;
+    if (test2 <= atol) istop = 2;
+    if (test1 <= rtol) istop = 1;
+    if (tid == 0) {
+        LsqrState o;
+        o.alfa = alfa; o.beta = beta; o.rhobar = rhobar; o.phibar = phibar; o.anorm = anorm; o.ddnorm = ddnorm; o.res2 = res2;
+        o.xnorm = xnorm; o.xxnorm = xxnorm; o.z = z; o.cs2 = cs2; o.sn2 = sn2;
+        o.arnorm = arnorm; o.rnorm = rnorm; o.r1norm = r1norm; o.r2norm = rnorm; o.acond = acond; o.istop = (double)istop;
+        *st = o;
+    }
+}
+
 }  // namespace
 
 rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b, double damp, double atol, double btol,
@@ -720,25 +818,39 @@ rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, c
     DevBuf tn1;
     if (onepass) RNLA_CUDA(tn1.alloc((size_t)(n + 1) * 8));
     double uscale = 1.0;                                      // one-pass iterations keep u unnormalised: u_reference = uscale * u
+    if (onepass) {
+        // u~ = a v - alfa u and a^T u~ from ONE pass over a (normal_pass.cu): beta = ||u~||, a^T (u~ / beta) = (a^T u~) / beta.  u stays
+        // unnormalised in memory; its factor 1 / beta goes into the next iteration's coefficient.  Everything else of the iteration
+        // is lsqr_step_kernel; one read-back per iteration.
+        DevBuf stb;
+        RNLA_CUDA(stb.alloc(sizeof(LsqrState)));
+        LsqrState hs{};
+        hs.alfa = alfa; hs.beta = beta; hs.rhobar = rhobar; hs.phibar = phibar; hs.anorm = anorm; hs.ddnorm = ddnorm; hs.res2 = res2;
+        hs.xnorm = xnorm; hs.xxnorm = xxnorm; hs.z = z; hs.cs2 = cs2; hs.sn2 = sn2;
+        RNLA_CUDA(cudaMemcpyAsync(stb.p, &hs, sizeof(LsqrState), cudaMemcpyHostToDevice, c.stream));
+        RNLA_CUDA(cudaStreamSynchronize(c.stream));
+        while (itn < iter_lim) {
+            if (arnorms && itn < arnorms_cap) arnorms[itn] = arnorm;                                      // :191
+            nhist = ++itn;
+            RNLA_TRY(dev_normal_pass(A, lda, m_local, n, v.d(), 1.0, u.d(), -alfa * uscale, u.d(), tn1.d()));   // :195, :201
+            lsqr_step_kernel<<<1, 1024, 0, c.stream>>>((int)n, tn1.d(), v.d(), w.d(), x, dvar, stb.as<LsqrState>(), damp, bnorm, atol, btol,
+                                                       ctol, (long long)itn, (long long)iter_lim);
+            ++g_kernel_launches;
+            RNLA_CUDA(cudaGetLastError());
+            RNLA_CUDA(cudaMemcpyAsync(&hs, stb.p, sizeof(LsqrState), cudaMemcpyDeviceToHost, c.stream));
+            RNLA_CUDA(cudaStreamSynchronize(c.stream));
+            alfa = hs.alfa; beta = hs.beta; uscale = beta > 0.0 ? 1.0 / beta : 1.0;
+            anorm = hs.anorm; acond = hs.acond; xnorm = hs.xnorm; arnorm = hs.arnorm; r1norm = hs.r1norm; r2norm = hs.r2norm;
+            istop = (int64_t)hs.istop;
+            if (istop != 0) break;
+        }
+        RNLA_CUDA(cudaStreamSynchronize(c.stream));
+        *res = rnla_lsqr_result{istop, itn, r1norm, r2norm, anorm, acond, xnorm, nhist};
+        return RNLA_OK;
+    }
     while (itn < iter_lim) {
         if (arnorms && itn < arnorms_cap) arnorms[itn] = arnorm;                                          // :191
         nhist = ++itn;
-        if (onepass) {
-            // u~ = a v - alfa u and a^T u~ from ONE pass over a (normal_pass.cu): beta = ||u~||, a^T (u~ / beta) = (a^T u~) / beta.  u stays
-            // unnormalised in memory; its factor 1 / beta goes into the next iteration's coefficient                :195-203
-            RNLA_TRY(dev_normal_pass(A, lda, m_local, n, v.d(), 1.0, u.d(), -alfa * uscale, u.d(), tn1.d()));
-            double uu = 0.0;
-            RNLA_CUDA(cudaMemcpyAsync(&uu, tn1.d() + n, 8, cudaMemcpyDeviceToHost, c.stream));
-            RNLA_CUDA(cudaStreamSynchronize(c.stream));
-            beta = std::sqrt(uu);
-            uscale = 1.0;
-            if (beta > 0.0) {
-                uscale = 1.0 / beta;
-                anorm = std::sqrt(anorm * anorm + alfa * alfa + beta * beta + dampsq);                    // :200
-                RNLA_TRY(axpby_nrm2(S, 1.0 / beta, tn1.d(), -beta, v.d(), n, false, &alfa));              // :202-203
-                RNLA_TRY(S.axpby(0.0, v.d(), alfa > 0.0 ? 1.0 / alfa : 0.0, v.d(), n));                   // :204
-            }
-        } else {
         RNLA_TRY(dev_gemv_n(A, lda, m_local, n, v.d(), tm.d()));
         RNLA_TRY(axpby_nrm2(S, 1.0, tm.d(), -alfa, u.d(), m_local, true, &beta));                         // :195-196
         if (beta > 0.0) {
@@ -747,7 +859,6 @@ rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, c
             RNLA_TRY(dev_gemv_t(A, lda, m_local, n, u.d(), tn.d()));
             RNLA_TRY(axpby_nrm2(S, 1.0, tn.d(), -beta, v.d(), n, false, &alfa));                          // :202-203
             RNLA_TRY(S.axpby(0.0, v.d(), alfa > 0.0 ? 1.0 / alfa : 0.0, v.d(), n));                       // :204
-        }
         }
         const double rhobar1 = std::sqrt(rhobar * rhobar + dampsq);                                       // :208-212
         const double cs1 = rhobar / rhobar1, sn1 = damp / rhobar1;
