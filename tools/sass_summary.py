@@ -1,9 +1,9 @@
 """SASS evidence: per-kernel counts of the Blackwell-native mnemonics in randnla_b200/librnla.so (cuobjdump -sass), written to
 profiles/r02_sass_summary.txt.  UTCIMMA = tcgen05.mma kind::i8 (.2CTA: cta_group::2), UTMALDG = cp.async.bulk.tensor (tiled TMA), LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (TMA engine),
-SYNCS = mbarrier, DMMA = mma.sync f64."""
+SYNCS = mbarrier, STAS = st.async (remote shared-memory store completing on the receiver's mbarrier), DMMA = mma.sync f64."""
 import re, subprocess, sys, collections
 out = subprocess.run(["cuobjdump", "-sass", "randnla_b200/librnla.so"], capture_output=True, text=True).stdout
-pat = ["UTCIMMA", "UTCBAR", "LDTM", "UBLKCP", "UTMALDG", "UTMAPF", "SYNCS", "DMMA", "LDGSTS", "REDUX", "ATOMS"]
+pat = ["UTCIMMA", "UTCBAR", "LDTM", "UBLKCP", "UTMALDG", "UTMAPF", "SYNCS", "STAS", "DMMA", "LDGSTS", "REDUX", "ATOMS"]
 cur = None
 per = collections.OrderedDict()
 for line in out.splitlines():
