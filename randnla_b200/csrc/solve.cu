@@ -433,9 +433,6 @@ static rnla_status cgls_operator_onepass(Solver& S, const double* A, int64_t lda
     *it_out = it; *conv_out = conv;
     return RNLA_OK;
 }
-// One pass per iteration where the operator is a preconditioned one (the sketch-and-precondition drivers: cond(A M) = O(1), the s
-// recurrence is as accurate as the reference's r recurrence) and the one-pass kernel takes the shape; plain cgls(a, ...) keeps the
-// reference's recurrence unless RNLA_ONEPASS=2.  Row shards must agree (lda / alignment differ per rank).
 // whether every rank's shard is taken by the one-pass kernel (lda / alignment differ per rank; the ranks must choose alike)
 static rnla_status onepass_agreed(Solver& S, const double* A, int64_t lda, int64_t m_local, int64_t n, bool* one) {
     Ctx& c = S.c;
@@ -450,6 +447,10 @@ static rnla_status onepass_agreed(Solver& S, const double* A, int64_t lda, int64
     }
     return RNLA_OK;
 }
+// One pass per iteration where the operator is a preconditioned one (the sketch-and-precondition drivers: the caller's tolerance sits
+// above the rounding floor, where the s recurrence IS the reference's iteration; the two only differ at the floor, where the carried
+// residual of the s recurrence keeps shrinking while a^T (b - a x) stagnates -- tests/test_host_logic.py) and the one-pass kernel
+// takes the shape; plain cgls(a, ...) keeps the reference's recurrence unless RNLA_ONEPASS=2.
 static rnla_status cgls_operator(Solver& S, const double* A, int64_t lda, int64_t m_local, int64_t n, const double* b,
                                  const double* M, double* z, double epsilon, int64_t maxit, int64_t* it_out, int32_t* conv_out) {
     const char* e = getenv("RNLA_ONEPASS");

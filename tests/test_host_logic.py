@@ -340,3 +340,85 @@ def test_row_sharded_solver_dataflow_matches_single_process_oracle(tmp_path, orc
     # the one-pass dataflow is the same iteration up to rounding
     assert np.abs(got["x1"] - xl).max() <= 1e-12 * np.abs(xl).max()
     assert np.abs(got["xc1"] - xc[:, 0]).max() <= 1e-12 * np.abs(xc).max()
+
+
+# ---- the CGLS recurrence of the one-pass iteration (csrc/solve.cu cgls_operator_onepass) against the reference's (src/cg.rs:29-52) ----
+def _cgls_r_recurrence(A, b, tol, maxit):
+    """src/cg.rs:29-52 statement for statement: r updated, s = a^T r recomputed every iteration"""
+    x = np.zeros(A.shape[1]); r = b - A @ x; s = A.T @ r; p = s.copy(); ns = s @ s
+    hist = []
+    for i in range(maxit):
+        ap = A @ p
+        alpha = ns / (ap @ ap)
+        x = x + alpha * p; r = r - alpha * ap
+        s = A.T @ r; nn = s @ s
+        hist.append(np.sqrt(nn))
+        if np.sqrt(nn) < tol:
+            return x, i + 1, hist
+        p = s + (nn / ns) * p; ns = nn
+    return x, maxit, hist
+
+
+def _cgls_s_recurrence(A, b, tol, maxit):
+    """what the device runs when a p and a^T (a p) come from one pass over a: s_new = s - alpha a^T (a p); r is never formed"""
+    x = np.zeros(A.shape[1]); s = A.T @ (b - A @ x); p = s.copy(); ns = s @ s
+    hist = []
+    for i in range(maxit):
+        q = A @ p; t = A.T @ q
+        alpha = ns / (q @ q)
+        x = x + alpha * p; s = s - alpha * t
+        nn = s @ s
+        hist.append(np.sqrt(nn))
+        if np.sqrt(nn) < tol:
+            return x, i + 1, hist
+        p = s + (nn / ns) * p; ns = nn
+    return x, maxit, hist
+
+
+@pytest.mark.parametrize("cond", [1.5, 3.0, 10.0])
+def test_one_pass_cgls_recurrence_is_the_reference_iteration_on_preconditioned_operators(cond):
+    """On a preconditioned operator (cond(A M) = O(1): what blendenpik / LSRN / the saddle-point driver hand to cgls) the s recurrence
+    of the one-pass iteration and the reference's r recurrence are the same iteration to rounding: same stopping iteration, same solution to
+    1e-11, residual histories equal to rounding over the first ten iterations.  (Why plain cgls(a, ...) keeps the reference's recurrence: at cond 1e4 the two histories
+    part after a few dozen iterations -- asserted below as a fact about the recurrences, not about the device.)"""
+    rng = np.random.default_rng(int(cond * 10))
+    m, n = 400, 60
+    U, _ = np.linalg.qr(rng.standard_normal((m, n))); V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = (U * np.linspace(1.0, 1.0 / cond, n)) @ V.T
+    b = A @ rng.uniform(-100, 100, n) + 1e-2 * rng.standard_normal(m)
+    xr, itr, hr = _cgls_r_recurrence(A, b, 1e-9, 200)
+    xs, its, hs = _cgls_s_recurrence(A, b, 1e-9, 200)
+    assert itr == its and itr < 120
+    assert np.abs(xr - xs).max() <= 1e-11 * np.abs(xr).max()
+    # residual histories: equal to rounding while the Krylov basis is still orthogonal; later any two CG implementations drift apart
+    # at the rate rounding errors are amplified (not a property of the recurrence: two summation orders of the SAME recurrence do so too)
+    assert np.abs(np.array(hr[:10]) - np.array(hs[:10])).max() <= 1e-12 * hr[0]
+    assert np.abs(np.array(hr) - np.array(hs)).max() <= 1e-5 * hr[0]
+    assert np.linalg.norm(A.T @ (b - A @ xs)) < 1e-8
+
+
+def test_recurrences_differ_only_at_the_rounding_floor():
+    """Unpreconditioned, cond(a) = 1e3, run far past convergence: both recurrences reach the SAME true residual a^T (b - a x) (the
+    rounding floor), but what they carry differs there -- the s recurrence's carried residual keeps shrinking (it is never
+    re-anchored on r) while the reference's stays within a few hundred times the true one.  So a tolerance below the floor stops the
+    two at different iterations; above the floor they are the same iteration.  This is why the one-pass iteration is the default only
+    where the caller's tolerance sits above the floor by construction (the preconditioned drivers) and plain cgls(a, ...) keeps the
+    reference's recurrence (RNLA_ONEPASS=2 opts it in; RNLA_ONEPASS_CONFIRM=1 re-anchors a stop on the true residual)."""
+    rng = np.random.default_rng(3)
+    m, n = 400, 60
+    U, _ = np.linalg.qr(rng.standard_normal((m, n))); V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = (U * np.logspace(0, -3, n)) @ V.T
+    b = A @ rng.uniform(-100, 100, n) + 1e-2 * rng.standard_normal(m)
+    s0 = np.linalg.norm(A.T @ b)
+    # above the floor: same carried residuals, equal to the true ones
+    xr, _, hr = _cgls_r_recurrence(A, b, 1e-30, 400)
+    xs, _, hs = _cgls_s_recurrence(A, b, 1e-30, 400)
+    for x, h in ((xr, hr), (xs, hs)):
+        assert abs(np.linalg.norm(A.T @ (b - A @ x)) - h[-1]) <= 1e-6 * h[-1] + 1e-13 * s0
+    # at the floor
+    xr, _, hr = _cgls_r_recurrence(A, b, 1e-30, 2000)
+    xs, _, hs = _cgls_s_recurrence(A, b, 1e-30, 2000)
+    true_r = np.linalg.norm(A.T @ (b - A @ xr)); true_s = np.linalg.norm(A.T @ (b - A @ xs))
+    assert true_r < 1e-11 * s0 and true_s < 1e-11 * s0 and 0.01 < true_s / true_r < 100.0      # the same floor
+    assert hr[-1] > 1e-4 * true_r                                                                  # the reference's carried residual stays near it
+    assert hs[-1] < 1e-8 * true_s                                                                  # the s recurrence's does not
