@@ -19,7 +19,8 @@
 // So each element is read from shared memory twice (conflict-free, lane = row), costs two DFMAs, and nothing else per element; the
 // exchange latency only delays the column group behind the row group.  Every sum has a fixed order (columns of a thread, warps,
 // cluster ranks, slabs of a cluster, row classes, clusters), so results are reproducible.
-// Limits: n <= 8 x 256 (portable cluster size), lda even and A 16-byte aligned (tensor map); callers fall back to the two-pass kernels.
+// Limit: n <= 8 x 256 (portable cluster size); beyond it callers keep the two streaming kernels.  Any leading dimension and any 8-byte
+// aligned base are addressed through tensor maps (see normal_pass_supported).
 #include "drivers.cuh"
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -40,7 +41,8 @@ constexpr int NP_NCB = 256;              // columns per CTA (slots k 8 + w, k < 
 constexpr int NP_STAGES = 3;
 constexpr int NP_CMAX = 8;               // portable cluster size
 constexpr int NP_XS = 8;                 // exchange slots (a sender is never more than 6 slabs ahead of a receiver, see below)
-constexpr uint32_t NP_STAGE_BYTES = NP_R * NP_NCB * 8;     // 64 KB
+constexpr int NP_RP = NP_R + 2;          // rows of a box when a column may start 8 bytes off a 16-byte boundary (see normal_pass_supported)
+constexpr uint32_t NP_STAGE_BYTES = NP_RP * NP_NCB * 8 + 128;   // 68 KB (+ the odd columns' box starts on a 128-byte boundary)
 constexpr size_t NP_SMEM = (size_t)NP_STAGES * NP_STAGE_BYTES + (size_t)NP_XS * NP_CMAX * 32 * 8 + 2 * NP_GW * 32 * 8 + 256 + 128;
 
 struct NpArgs {
@@ -48,6 +50,9 @@ struct NpArgs {
     int n, ncb;                          // columns, columns per CTA
     int64_t nslabs;
     const double* x; const double* y; double cq, cy; double* uout;
+    int ne;                              // stage positions [0, ne): local columns 0, 2, 4, ... (map E); [ne, ncb): 1, 3, 5, ... (map O); ne = ncb: one map, identity
+    int shift_e, shift_o;                // 1: the columns of that map start 8 bytes off; their boxes start one element early
+    int pitch;                           // rows per column in a stage: 32, or 34 when some column starts 8 bytes off
     double* tpart;                       // [clusters][n]
     double* uupart;                      // [clusters]
 };
@@ -74,8 +79,11 @@ __device__ __forceinline__ void np_tma_load_2d(void* dst, const CUtensorMap* tm,
 // group released slab i - 3, which needed the partial of slab i - 3 from every CTA Y; Y sent that after ITS stage of slab i - 3 was
 // loaded, i.e. after Y's column group released slab i - 6 (and had read the slot of slab i - 6).  Eight slots therefore never collide,
 // and a completion can never land on an mbarrier phase that is still open for an older slab.
+// PAD: some column starts 8 bytes off a 16-byte boundary (34-row boxes, two kinds of columns); otherwise the plain 32-row layout with
+// compile-time strides
+template <bool PAD>
 __global__ void __launch_bounds__(NP_THREADS, 1)
-normal_pass_kernel(const __grid_constant__ CUtensorMap tmA, const NpArgs a) {
+normal_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmO, const NpArgs a) {
     extern __shared__ uint8_t np_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(np_smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t* stages = smem;
@@ -89,19 +97,39 @@ normal_pass_kernel(const __grid_constant__ CUtensorMap tmA, const NpArgs a) {
     const int64_t G = gridDim.x / csize, g = blockIdx.x / csize;
     const int cnt = (int)((a.nslabs - g + G - 1) / G);         // slabs of this cluster: g, g + G, ...
     const int col0 = (int)rank * a.ncb;
+    const bool split = a.ne < a.ncb;                           // odd leading dimension: even and odd columns through two tensor maps
+    // stage position -> local column
+    auto lcol = [&](int pos) { return !split ? pos : (pos < a.ne ? 2 * pos : 2 * (pos - a.ne) + 1); };
+    constexpr int pitch = PAD ? NP_RP : NP_R;
+    const int obase = (a.ne * pitch + 15) & ~15;               // doubles: where the second box of a stage starts (128-byte aligned)
+    const int wq = (tid >> 5) & (NP_GW - 1);                   // this warp's column class: positions k 8 + wq
+    const int kE = max(0, min(32, (a.ne - wq + 7) / 8));       // positions k 8 + wq with k < kE lie in the first box
+    // element (row `lane`, position k 8 + wq) of a stage sits at (k < kE ? offE : offO) + k 8 pitch: a column that starts 8 bytes off a
+    // 16-byte boundary was loaded from one element earlier (row offset 1)
+    const int offE = wq * pitch + lane + a.shift_e;
+    const int offO = obase + (wq - a.ne) * pitch + lane + a.shift_o;
+    const uint32_t box_bytes = (uint32_t)a.ncb * (uint32_t)pitch * 8u;
+    auto load_slab = [&](int i) {                              // one thread: slab i of this cluster into stage i % NP_STAGES
+        const int st = i % NP_STAGES;
+        const int r0 = (int)((g + (int64_t)i * G) * NP_R);      // (a view shifted by one element starts its box at the same coordinate:
+        uint8_t* dst = stages + (size_t)st * NP_STAGE_BYTES;   //  one element early, on a 16-byte boundary)
+        mbar_arrive_expect_tx(full + st, box_bytes);
+        if (!split) np_tma_load_2d(dst, &tmA, full + st, r0, col0);
+        else {
+            np_tma_load_2d(dst, &tmA, full + st, r0, col0 / 2);
+            np_tma_load_2d(dst + (size_t)obase * 8, &tmO, full + st, r0, col0 / 2);
+        }
+    };
     // the columns of the stages that no load ever writes (ncb < 256) must read as zeros
     for (int st = 0; st < NP_STAGES; ++st) {
-        double* tail = reinterpret_cast<double*>(stages + (size_t)st * NP_STAGE_BYTES) + (size_t)a.ncb * NP_R;
-        for (int q = tid; q < (NP_NCB - a.ncb) * NP_R; q += NP_THREADS) tail[q] = 0.0;
+        double* tail = reinterpret_cast<double*>(stages + (size_t)st * NP_STAGE_BYTES) + (((a.ne * (PAD ? NP_RP : NP_R)) + 15) & ~15) + (size_t)(a.ncb - a.ne) * (PAD ? NP_RP : NP_R);
+        for (int q = tid; q < (NP_NCB - a.ncb) * (PAD ? NP_RP : NP_R); q += NP_THREADS) tail[q] = 0.0;
     }
     if (tid == 0) {
         for (int st = 0; st < NP_STAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, NP_GW); }
         for (int sl = 0; sl < NP_XS; ++sl) mbar_init(xfull + sl, 1);
         mbar_fence_init();
-        for (int i = 0; i < NP_STAGES && i < cnt; ++i) {
-            mbar_arrive_expect_tx(full + i, (uint32_t)a.ncb * NP_R * 8);
-            np_tma_load_2d(stages + (size_t)i * NP_STAGE_BYTES, &tmA, full + i, (int)((g + (int64_t)i * G) * NP_R), col0);
-        }
+        for (int i = 0; i < NP_STAGES && i < cnt; ++i) load_slab(i);
     }
     __syncthreads();
     np_cluster_sync();                                         // every CTA's barriers exist before anyone sends to it
@@ -111,16 +139,19 @@ normal_pass_kernel(const __grid_constant__ CUtensorMap tmA, const NpArgs a) {
         const int w = warp;
         double p[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) { const int lc = k * 8 + w; p[k] = (lc < a.ncb && col0 + lc < a.n) ? a.x[col0 + lc] : 0.0; }
+        for (int k = 0; k < 32; ++k) { const int pos = k * 8 + w, lc = lcol(pos); p[k] = (pos < a.ncb && col0 + lc < a.n) ? a.x[col0 + lc] : 0.0; }
         for (int i = 0; i < cnt; ++i) {
             const int st = i % NP_STAGES;
             mbar_wait(full + st, (uint32_t)(i / NP_STAGES) & 1u);
-            const double* sp = reinterpret_cast<const double*>(stages + (size_t)st * NP_STAGE_BYTES) + w * NP_R + lane;
+            const double* sg = reinterpret_cast<const double*>(stages + (size_t)st * NP_STAGE_BYTES);
+            const double* spE = sg + offE; const double* spO = sg + offO;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
             for (int k = 0; k < 32; k += 4) {
-                s0 = fma(sp[(k * 8) * NP_R], p[k], s0); s1 = fma(sp[((k + 1) * 8) * NP_R], p[k + 1], s1);
-                s2 = fma(sp[((k + 2) * 8) * NP_R], p[k + 2], s2); s3 = fma(sp[((k + 3) * 8) * NP_R], p[k + 3], s3);
+                s0 = fma(((!PAD || k < kE) ? spE : spO)[(k * 8) * pitch], p[k], s0);
+                s1 = fma(((!PAD || k + 1 < kE) ? spE : spO)[((k + 1) * 8) * pitch], p[k + 1], s1);
+                s2 = fma(((!PAD || k + 2 < kE) ? spE : spO)[((k + 2) * 8) * pitch], p[k + 2], s2);
+                s3 = fma(((!PAD || k + 3 < kE) ? spE : spO)[((k + 3) * 8) * pitch], p[k + 3], s3);
             }
             double* rd = red + (i & 1) * NP_GW * 32;
             rd[w * 32 + lane] = (s0 + s1) + (s2 + s3);
@@ -169,16 +200,16 @@ normal_pass_kernel(const __grid_constant__ CUtensorMap tmA, const NpArgs a) {
                 uu = fma(u, u, uu);
                 if (a.uout != nullptr && row < a.m) a.uout[row] = u;
             }
-            const double* sp = reinterpret_cast<const double*>(stages + (size_t)st * NP_STAGE_BYTES) + w * NP_R + lane;
+            const double* sg = reinterpret_cast<const double*>(stages + (size_t)st * NP_STAGE_BYTES);
+            const double* spE = sg + offE; const double* spO = sg + offO;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) acc[k] = fma(sp[(k * 8) * NP_R], u, acc[k]);
+            for (int k = 0; k < 32; ++k) acc[k] = fma(((!PAD || k < kE) ? spE : spO)[(k * 8) * pitch], u, acc[k]);
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(empty + st);
                 if (w == 0 && i + NP_STAGES < cnt) {           // producer: refill the stage once all eight warps have released it
                     mbar_wait(empty + st, (uint32_t)(i / NP_STAGES) & 1u);
-                    mbar_arrive_expect_tx(full + st, (uint32_t)a.ncb * NP_R * 8);
-                    np_tma_load_2d(stages + (size_t)st * NP_STAGE_BYTES, &tmA, full + st, (int)((g + (int64_t)(i + NP_STAGES) * G) * NP_R), col0);
+                    load_slab(i + NP_STAGES);
                 }
             }
             row = row_next; yv = y_next;
@@ -194,8 +225,8 @@ normal_pass_kernel(const __grid_constant__ CUtensorMap tmA, const NpArgs a) {
                 acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
             }
         }
-        const int lc = lane * 8 + w;
-        if (lc < a.ncb && col0 + lc < a.n) a.tpart[g * a.n + col0 + lc] = acc[0];
+        const int pos = lane * 8 + w, lc = lcol(pos);
+        if (pos < a.ncb && col0 + lc < a.n) a.tpart[g * a.n + col0 + lc] = acc[0];
         if (w == 0 && rank == 0) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) uu += __shfl_xor_sync(0xffffffffu, uu, o);
@@ -232,11 +263,14 @@ inline int np_cluster_size_for(int64_t n) { int c = 1; while ((int64_t)c * NP_NC
 
 }  // namespace
 
-// whether the one-pass kernel takes this operand (same answer on every rank is the caller's business: lda may differ per shard)
+// whether the one-pass kernel takes this operand: n <= 2048.  A tensor map wants a 16-byte aligned base and strides that are multiples
+// of 16 bytes, and every row of a box must start on a 16-byte boundary: a column that starts 8 bytes off is loaded from one element
+// earlier (34-row boxes, read at row offset 1), and with an odd leading dimension -- columns alternate between the two cases -- the even
+// and the odd columns get a map each.
 bool normal_pass_supported(const double* A, int64_t lda, int64_t m_local, int64_t n) {
     if (const char* e = getenv("RNLA_ONEPASS")) { if (e[0] == '0') return false; }
-    return n >= 1 && n <= (int64_t)NP_CMAX * NP_NCB && m_local >= 1 && m_local < ((int64_t)1 << 31) - 64 && lda % 2 == 0 &&
-           (reinterpret_cast<uintptr_t>(A) & 15) == 0 && np_encoder() != nullptr;
+    return n >= 1 && n <= (int64_t)NP_CMAX * NP_NCB && m_local >= 1 && m_local < ((int64_t)1 << 31) - 64 && lda >= m_local &&
+           (reinterpret_cast<uintptr_t>(A) & 7) == 0 && np_encoder() != nullptr;
 }
 
 // t (n + 1 doubles, device): t[0..n) = A^T u, t[n] = u . u with u = cq (A x) + cy y; all-reduced over the row shards.
@@ -246,10 +280,13 @@ rnla_status dev_normal_pass(const double* A, int64_t lda, int64_t m_local, int64
     Ctx& c = ctx();
     if (!normal_pass_supported(A, lda, m_local, n)) return fail(RNLA_ERR_COMPUTATION, "normal_pass: operand not supported by the one-pass kernel");
     const int C = np_cluster_size_for(n);
-    const int ncb = (int)((n + C - 1) / C);
+    const bool odd_ld = (lda & 1) != 0;
+    int ncb = (int)((n + C - 1) / C);
+    if (odd_ld && C > 1) ncb += ncb & 1;                       // every CTA starts on an even column
     static bool attr = false;
     if (!attr) {
-        RNLA_CUDA(cudaFuncSetAttribute(normal_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NP_SMEM));
+        RNLA_CUDA(cudaFuncSetAttribute(normal_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NP_SMEM));
+        RNLA_CUDA(cudaFuncSetAttribute(normal_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NP_SMEM));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -261,7 +298,7 @@ rnla_status dev_normal_pass(const double* A, int64_t lda, int64_t m_local, int64
     if (clusters_for[C] == 0) {
         cfg.gridDim = dim3((unsigned)(C * c.sms));
         int nc = 0;
-        RNLA_CUDA(cudaOccupancyMaxActiveClusters(&nc, normal_pass_kernel, &cfg));
+        RNLA_CUDA(cudaOccupancyMaxActiveClusters(&nc, normal_pass_kernel<true>, &cfg));
         clusters_for[C] = std::max(1, nc);
     }
     NpArgs a;
@@ -271,18 +308,35 @@ rnla_status dev_normal_pass(const double* A, int64_t lda, int64_t m_local, int64
     RNLA_CUDA(part.alloc(((size_t)G * n + G) * 8));
     if (getenv("RNLA_NP_VERBOSE")) fprintf(stderr, "normal_pass: C = %d, ncb = %d, clusters = %d (max %d), slabs = %lld\n", C, ncb, G, clusters_for[C], (long long)a.nslabs);
     a.x = x; a.y = y; a.cq = cq; a.cy = cy; a.uout = uout; a.tpart = part.d(); a.uupart = part.d() + (size_t)G * n;
-    CUtensorMap tm;
-    {
-        const cuuint64_t dims[2] = {(cuuint64_t)m_local, (cuuint64_t)n};
-        const cuuint64_t strides[1] = {(cuuint64_t)lda * 8};
-        const cuuint32_t box[2] = {(cuuint32_t)NP_R, (cuuint32_t)ncb}, ones[2] = {1, 1};
-        const CUresult r = np_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(A), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // Column j starts at A + 8 j lda: on a 16-byte boundary iff (A / 8 + j lda) is even.  TMA wants every row of a box to start on one,
+    // so the columns that do not are loaded from ONE ELEMENT EARLIER (a view whose base is A - 8, same coordinates) with a box of 34
+    // rows, and read at row offset 1; with an odd leading dimension the two kinds alternate and get a tensor map each.
+    const int par0 = (int)((reinterpret_cast<uintptr_t>(A) >> 3) & 1);
+    a.ne = odd_ld ? (ncb + 1) / 2 : ncb;
+    a.shift_e = par0; a.shift_o = odd_ld ? 1 - par0 : par0;
+    a.pitch = (odd_ld || par0) ? NP_RP : NP_R;
+    CUtensorMap tm, tmo;
+    auto encode = [&](CUtensorMap* out, const double* first_col, int shift, int64_t ncols, int64_t col_stride, int box_cols) -> rnla_status {
+        const cuuint64_t dims[2] = {(cuuint64_t)(m_local + shift), (cuuint64_t)std::max<int64_t>(ncols, 1)};
+        const cuuint64_t strides[1] = {(cuuint64_t)col_stride * 8};
+        const cuuint32_t box[2] = {(cuuint32_t)a.pitch, (cuuint32_t)std::max(box_cols, 1)}, ones[2] = {1, 1};
+        const CUresult r = np_encoder()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(first_col - shift), dims, strides, box, ones,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(RNLA_ERR_COMPUTATION, "normal_pass: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        return RNLA_OK;
+    };
+    if (!odd_ld) {
+        RNLA_TRY(encode(&tm, A, a.shift_e, n, lda, ncb));
+        tmo = tm;
+    } else {
+        RNLA_TRY(encode(&tm, A, a.shift_e, (n + 1) / 2, 2 * lda, a.ne));                // columns 0, 2, 4, ...
+        RNLA_TRY(encode(&tmo, A + lda, a.shift_o, n / 2, 2 * lda, ncb - a.ne));        // columns 1, 3, 5, ...
     }
     cfg.gridDim = dim3((unsigned)(G * C));
     kernel_phase_begin("k:normal_pass");
-    RNLA_CUDA(cudaLaunchKernelEx(&cfg, normal_pass_kernel, tm, a));
+    if (a.pitch == NP_RP) RNLA_CUDA(cudaLaunchKernelEx(&cfg, normal_pass_kernel<true>, tm, tmo, a));
+    else RNLA_CUDA(cudaLaunchKernelEx(&cfg, normal_pass_kernel<false>, tm, tmo, a));
     kernel_phase_end();
     normal_pass_reduce_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c.stream>>>(a.tpart, a.uupart, G, (int)n, t);
     g_kernel_launches += 2;

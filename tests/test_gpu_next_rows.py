@@ -543,16 +543,18 @@ def _normal_pass(A, x, cq, y, cy, store):
 
 
 @pytest.mark.parametrize("m,n", [(2, 1), (32, 8), (64, 9), (1000, 100), (4100, 255), (4096, 256), (5000, 257), (7778, 500), (3002, 1000),
-                                 (9000, 2000), (2500, 2048), (100000, 640)])
+                                 (9000, 2000), (2500, 2048), (100000, 640),
+                                 (1, 1), (31, 7), (33, 9), (4099, 255), (4097, 256), (7777, 500), (3001, 1000), (9001, 2000), (2501, 2048), (60001, 640)])
 def test_normal_pass_matches_numpy(rb, m, n):
     """csrc/normal_pass.cu: u = cq A x + cy y, t = A^T u, u . u from one pass over A (clusters of 1, 2, 4, 8 CTAs; ragged last slab
-    and ragged last column block), against numpy; bit-reproducible from call to call."""
+    and ragged last column block; odd leading dimensions: even and odd columns through a tensor map each), against numpy;
+    bit-reproducible from call to call."""
     rng = np.random.default_rng(m + n)
     A = np.asfortranarray(rng.standard_normal((m, n)))
     x = rng.standard_normal(n); y = rng.standard_normal(m)
     for cq, yy, cy, store in [(1.0, None, 0.0, False), (-1.0, y, 1.0, True), (1.0, y, -0.37, True)]:
         got = _normal_pass(A, x, cq, yy, cy, store)
-        assert got is not None, "an even leading dimension and n <= 2048 must be taken by the one-pass kernel"
+        assert got is not None, "n <= 2048 must be taken by the one-pass kernel"
         t, uu, u = got
         ur = cq * (A @ x) + (cy * yy if yy is not None else 0.0)
         assert np.abs(t - A.T @ ur).max() <= 1e-13 * (np.abs(A).T @ np.abs(ur)).max()
@@ -563,11 +565,40 @@ def test_normal_pass_matches_numpy(rb, m, n):
         assert np.array_equal(t, t2) and uu == uu2
 
 
-def test_normal_pass_declines_what_the_tensor_map_cannot_address(rb):
-    """odd leading dimension (column stride not a multiple of 16 bytes) and n > 2048: the solvers keep the two streaming kernels"""
+def test_normal_pass_declines_more_than_2048_columns(rb):
+    """n > 8 x 256 (portable cluster size): the solvers keep the two streaming kernels"""
     rng = np.random.default_rng(0)
-    assert _normal_pass(np.asfortranarray(rng.standard_normal((4099, 16))), np.ones(16), 1.0, None, 0.0, False) is None
     assert _normal_pass(np.asfortranarray(rng.standard_normal((64, 2050))), np.ones(2050), 1.0, None, 0.0, False) is None
+
+
+@pytest.mark.parametrize("m,n,ld", [(5000, 300, 5002), (5000, 301, 5003), (4999, 1000, 5000), (777, 20, 779)])
+def test_normal_pass_on_a_view_that_starts_8_bytes_off(rb, m, n, ld):
+    """a row block of a larger matrix: the base is only 8-byte aligned (tensor maps want 16) and the leading dimension is that of the
+    parent, even or odd -- addressed through views whose base sits one element earlier"""
+    import ctypes as C
+    import torch
+    from randnla_b200 import runtime as rt, _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(m + n)
+    parent = np.asfortranarray(rng.standard_normal((ld, n)))
+    dP = rt.to_device_colmajor(parent)
+    pP, ldp = rt.dev_ptr_ld(dP)
+    assert ldp == ld
+    base = dP.data_ptr() + 8                                            # row 1 of the parent
+    A = parent[1:1 + m]
+    x = rng.standard_normal(n); y = rng.standard_normal(m)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    dt = torch.empty(n + 1, dtype=torch.float64, device="cuda"); du = torch.empty(m, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    assert lib.rnla_normal_pass_supported(C.c_void_p(base), ld, m, n)
+    _lib.check(lib.rnla_normal_pass_dev(C.c_void_p(base), ld, m, n, C.c_void_p(dx.data_ptr()), -1.0, C.c_void_p(dy.data_ptr()), 1.0,
+                                        C.c_void_p(du.data_ptr()), C.c_void_p(dt.data_ptr())))
+    rt.synchronize()
+    ur = y - A @ x
+    t = dt.cpu().numpy()
+    assert np.abs(du.cpu().numpy() - ur).max() <= 1e-13 * ((np.abs(A) @ np.abs(x)).max() + np.abs(y).max())
+    assert np.abs(t[:n] - A.T @ ur).max() <= 1e-13 * (np.abs(A).T @ np.abs(ur)).max()
+    assert abs(t[n] - ur @ ur) <= 1e-13 * (ur @ ur)
 
 
 @pytest.mark.parametrize("m,n,cond", [(6000, 40, 1e2), (9000, 300, 1e3), (20000, 1200, 1e2)])

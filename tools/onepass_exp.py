@@ -30,3 +30,9 @@ def two():
     _lib.check(lib.rnla_gemv_dev(pA, lda, m, n, 1, P(y), P(u2)))
 ms2 = ev(two)
 print(f"two streaming kernels: {ms2:.3f} ms = {16.0 * m * n / ms2 * 1e-6:.0f} GB/s per kernel", flush=True)
+# the same product on an operand with an ODD leading dimension (even / odd columns through a tensor map each)
+if m % 2 == 0:
+    dB = rt.empty_colmajor(m + 1, n); pB, ldb = rt.dev_ptr_ld(dB)
+    _lib.check(lib.rnla_sketch_fill_dev(0, 0, 77, 9, m + 1, n, 0, pB, ldb)); rt.synchronize()
+    ms3 = ev(lambda: _lib.check(lib.rnla_normal_pass_dev(pB, ldb, m + 1, n, P(x), 1.0, None, 0.0, None, P(t))))
+    print(f"one pass, odd leading dimension: {ms3:.3f} ms = {8.0 * (m + 1) * n / ms3 * 1e-6:.0f} GB/s of A", flush=True)
