@@ -1,7 +1,7 @@
 // One pass over a tall column-major A for BOTH products of a least-squares iteration (reference: the two products of every
 // cgls iteration, src/cg.rs:36 `a * &p` and :40 `a.transpose() * &r`; of every lsqr iteration, src/solvers.rs:188 and :196):
 //
-//   u  = cq * (A x) + cy * y          m_local values (y optional; u optionally stored, may overwrite y)
+//   u  = cq * (A x) + cy * y          m_local values (y optional; u optionally stored; u = y goes through a temporary)
 //   t  = A^T u                        n values
 //   uu = u . u
 //
@@ -307,7 +307,12 @@ rnla_status dev_normal_pass(const double* A, int64_t lda, int64_t m_local, int64
     DevBuf part;
     RNLA_CUDA(part.alloc(((size_t)G * n + G) * 8));
     if (getenv("RNLA_NP_VERBOSE")) fprintf(stderr, "normal_pass: C = %d, ncb = %d, clusters = %d (max %d), slabs = %lld\n", C, ncb, G, clusters_for[C], (long long)a.nslabs);
-    a.x = x; a.y = y; a.cq = cq; a.cy = cy; a.uout = uout; a.tpart = part.d(); a.uupart = part.d() + (size_t)G * n;
+    // u may be asked to overwrite y: every column warp of every CTA of a cluster reads y_row (up to three slabs apart from one another)
+    // while ONE warp writes u_row, so an in-place update would race; it goes through a temporary and is copied back
+    DevBuf utmp;
+    double* uw = uout;
+    if (uout != nullptr && uout == y) { RNLA_CUDA(utmp.alloc((size_t)m_local * 8)); uw = utmp.d(); }
+    a.x = x; a.y = y; a.cq = cq; a.cy = cy; a.uout = uw; a.tpart = part.d(); a.uupart = part.d() + (size_t)G * n;
     // Column j starts at A + 8 j lda: on a 16-byte boundary iff (A / 8 + j lda) is even.  TMA wants every row of a box to start on one,
     // so the columns that do not are loaded from ONE ELEMENT EARLIER (a view whose base is A - 8, same coordinates) with a box of 34
     // rows, and read at row offset 1; with an odd leading dimension the two kinds alternate and get a tensor map each.
@@ -341,6 +346,7 @@ rnla_status dev_normal_pass(const double* A, int64_t lda, int64_t m_local, int64
     normal_pass_reduce_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c.stream>>>(a.tpart, a.uupart, G, (int)n, t);
     g_kernel_launches += 2;
     RNLA_CUDA(cudaGetLastError());
+    if (uw != uout) RNLA_CUDA(cudaMemcpyAsync(uout, uw, (size_t)m_local * 8, cudaMemcpyDeviceToDevice, c.stream));
     if (c.nranks > 1) RNLA_TRY(allreduce_sum_f64(t, (size_t)n + 1));
     return RNLA_OK;
 }

@@ -833,7 +833,10 @@ rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, c
         while (itn < iter_lim) {
             if (arnorms && itn < arnorms_cap) arnorms[itn] = arnorm;                                      // :191
             nhist = ++itn;
-            RNLA_TRY(dev_normal_pass(A, lda, m_local, n, v.d(), 1.0, u.d(), -alfa * uscale, u.d(), tn1.d()));   // :195, :201
+            // (u~ is written to the other of two m-vectors: the kernel's column warps still read the old u while one warp writes the new)
+            double* u_old = (itn & 1) ? u.d() : tm.d();
+            double* u_new = (itn & 1) ? tm.d() : u.d();
+            RNLA_TRY(dev_normal_pass(A, lda, m_local, n, v.d(), 1.0, u_old, -alfa * uscale, u_new, tn1.d()));   // :195, :201
             lsqr_step_kernel<<<1, 1024, 0, c.stream>>>((int)n, tn1.d(), v.d(), w.d(), x, dvar, stb.as<LsqrState>(), damp, bnorm, atol, btol,
                                                        ctol, (long long)itn, (long long)iter_lim);
             ++g_kernel_launches;
