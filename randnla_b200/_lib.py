@@ -88,6 +88,7 @@ SIGNATURES = {
     "rnla_plan_saso_block": (c_i32, [c_i64, c_i32, c_i32, c_i64, c_i64, c_i32, P, P, c_i32, P]),
     "rnla_gemv_dev": (c_i32, [P, c_i64, c_i64, c_i64, c_i32, P, P]),
     "rnla_normal_pass_supported": (c_i32, [P, c_i64, c_i64, c_i64]),
+    "rnla_plan_normal_pass": (c_i32, [c_u64, c_i64, c_i64, P]),
     "rnla_normal_pass_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, c_f64, P, c_f64, P, P]),
     "rnla_blendenpik_overdetermined": (c_i32, [P, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),
     "rnla_blendenpik_overdetermined_dev": (c_i32, [P, c_i64, c_i64, c_i64, P, C.c_double, c_i64, C.c_double, c_i32, c_i32, c_i32, P, P, P]),

@@ -631,6 +631,12 @@ rnla_status rnla_gemv_dev(const double* dA, int64_t lda, int64_t m, int64_t n, i
     return trans ? dev_gemv_t(dA, lda, m, n, dx, dy) : dev_gemv_n(dA, lda, m, n, dx, dy);
 }
 
+int32_t rnla_plan_normal_pass(uint64_t base_address, int64_t lda, int64_t n, int32_t* out /* 7 */) {
+    if (n < 1 || n > 2048 || lda < 1 || (base_address & 7) != 0) return 0;
+    const NormalPassPlan p = normal_pass_plan(base_address, lda, n);
+    out[0] = p.cluster; out[1] = p.ncb; out[2] = p.ne; out[3] = p.shift_e; out[4] = p.shift_o; out[5] = p.pitch; out[6] = p.stage_bytes;
+    return 1;
+}
 int32_t rnla_normal_pass_supported(const double* dA, int64_t lda, int64_t m_local, int64_t n) {
     RNLA_API_GUARD;
     if (ensure_ctx() != RNLA_OK) return 0;

@@ -66,6 +66,8 @@ rnla_status dev_lsqr(const double* A, int64_t lda, int64_t m_local, int64_t n, c
 
 // normal_pass.cu: u = cq (A x) + cy y, t[0..n) = A^T u, t[n] = u . u with A streamed once (clusters hold row slabs in shared memory)
 bool normal_pass_supported(const double* A, int64_t lda, int64_t m_local, int64_t n);
+struct NormalPassPlan { int cluster, ncb, ne, shift_e, shift_o, pitch, stage_bytes; };
+NormalPassPlan normal_pass_plan(uint64_t base_address, int64_t lda, int64_t n);
 rnla_status dev_normal_pass(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* x, double cq, const double* y, double cy,
                             double* uout, double* t);
 

@@ -273,16 +273,34 @@ bool normal_pass_supported(const double* A, int64_t lda, int64_t m_local, int64_
            (reinterpret_cast<uintptr_t>(A) & 7) == 0 && np_encoder() != nullptr;
 }
 
+// Host logic of the launch, separated so that it can be checked without a GPU (rnla_plan_normal_pass, tests/test_host_logic.py):
+// cluster size, columns per CTA, and how the columns of a CTA are served by the tensor maps.
+NormalPassPlan normal_pass_plan(uint64_t base_address, int64_t lda, int64_t n) {
+    NormalPassPlan p;
+    p.cluster = np_cluster_size_for(n);
+    const bool odd_ld = (lda & 1) != 0;
+    p.ncb = (int)((n + p.cluster - 1) / p.cluster);
+    if (odd_ld && p.cluster > 1) p.ncb += p.ncb & 1;           // every CTA starts on an even column
+    // Column j starts at A + 8 j lda: on a 16-byte boundary iff (A / 8 + j lda) is even.  TMA wants every row of a box to start on one,
+    // so the columns that do not are loaded from ONE ELEMENT EARLIER (a view whose base is A - 8, same coordinates) with a box of 34
+    // rows, and read at row offset 1; with an odd leading dimension the two kinds alternate and get a tensor map each.
+    const int par0 = (int)((base_address >> 3) & 1);
+    p.ne = odd_ld ? (p.ncb + 1) / 2 : p.ncb;
+    p.shift_e = par0; p.shift_o = odd_ld ? 1 - par0 : par0;
+    p.pitch = (odd_ld || par0) ? NP_RP : NP_R;
+    p.stage_bytes = (int)NP_STAGE_BYTES;
+    return p;
+}
+
 // t (n + 1 doubles, device): t[0..n) = A^T u, t[n] = u . u with u = cq (A x) + cy y; all-reduced over the row shards.
 // uout (optional, m_local) receives u and may be y itself.
 rnla_status dev_normal_pass(const double* A, int64_t lda, int64_t m_local, int64_t n, const double* x, double cq, const double* y, double cy,
                             double* uout, double* t) {
     Ctx& c = ctx();
     if (!normal_pass_supported(A, lda, m_local, n)) return fail(RNLA_ERR_COMPUTATION, "normal_pass: operand not supported by the one-pass kernel");
-    const int C = np_cluster_size_for(n);
+    const NormalPassPlan plan = normal_pass_plan((uint64_t)reinterpret_cast<uintptr_t>(A), lda, n);
+    const int C = plan.cluster, ncb = plan.ncb;
     const bool odd_ld = (lda & 1) != 0;
-    int ncb = (int)((n + C - 1) / C);
-    if (odd_ld && C > 1) ncb += ncb & 1;                       // every CTA starts on an even column
     static bool attr = false;
     if (!attr) {
         RNLA_CUDA(cudaFuncSetAttribute(normal_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NP_SMEM));
@@ -313,13 +331,7 @@ rnla_status dev_normal_pass(const double* A, int64_t lda, int64_t m_local, int64
     double* uw = uout;
     if (uout != nullptr && uout == y) { RNLA_CUDA(utmp.alloc((size_t)m_local * 8)); uw = utmp.d(); }
     a.x = x; a.y = y; a.cq = cq; a.cy = cy; a.uout = uw; a.tpart = part.d(); a.uupart = part.d() + (size_t)G * n;
-    // Column j starts at A + 8 j lda: on a 16-byte boundary iff (A / 8 + j lda) is even.  TMA wants every row of a box to start on one,
-    // so the columns that do not are loaded from ONE ELEMENT EARLIER (a view whose base is A - 8, same coordinates) with a box of 34
-    // rows, and read at row offset 1; with an odd leading dimension the two kinds alternate and get a tensor map each.
-    const int par0 = (int)((reinterpret_cast<uintptr_t>(A) >> 3) & 1);
-    a.ne = odd_ld ? (ncb + 1) / 2 : ncb;
-    a.shift_e = par0; a.shift_o = odd_ld ? 1 - par0 : par0;
-    a.pitch = (odd_ld || par0) ? NP_RP : NP_R;
+    a.ne = plan.ne; a.shift_e = plan.shift_e; a.shift_o = plan.shift_o; a.pitch = plan.pitch;
     CUtensorMap tm, tmo;
     auto encode = [&](CUtensorMap* out, const double* first_col, int shift, int64_t ncols, int64_t col_stride, int box_cols) -> rnla_status {
         const cuuint64_t dims[2] = {(cuuint64_t)(m_local + shift), (cuuint64_t)std::max<int64_t>(ncols, 1)};

@@ -422,3 +422,50 @@ def test_recurrences_differ_only_at_the_rounding_floor():
     assert true_r < 1e-11 * s0 and true_s < 1e-11 * s0 and 0.01 < true_s / true_r < 100.0      # the same floor
     assert hr[-1] > 1e-4 * true_r                                                                  # the reference's carried residual stays near it
     assert hs[-1] < 1e-8 * true_s                                                                  # the s recurrence's does not
+
+
+# ---- host logic of the one-pass kernel's launch (csrc/normal_pass.cu, rnla_plan_normal_pass): which tensor map serves which column ----
+@pytest.mark.parametrize("addr", [0x7f0000000000, 0x7f0000000008])
+@pytest.mark.parametrize("lda", [1000, 1001, 4096, 4097])
+@pytest.mark.parametrize("n", [1, 2, 7, 255, 256, 257, 500, 999, 1000, 2000, 2047, 2048])
+def test_one_pass_launch_geometry(addr, lda, n):
+    """every column of every CTA is served by exactly one stage position; the map that serves it knows whether the column starts on a
+    16-byte boundary (TMA's requirement for every row of a box) or 8 bytes off it (then the box starts one element early and the
+    stage keeps 34 rows per column); the stage fits; an odd leading dimension makes every CTA start on an even column"""
+    import ctypes as C
+    from randnla_b200 import _lib
+    lib = _lib.load()
+    out = (C.c_int32 * 7)()
+    assert lib.rnla_plan_normal_pass(addr, lda, n, out) == 1
+    cl, ncb, ne, she, sho, pitch, stage_bytes = list(out)
+    assert cl in (1, 2, 4, 8) and cl * ncb >= n and ncb <= 256 and (cl == 1 or (cl // 2) * 256 < n)
+    odd = lda % 2 == 1
+    if odd and cl > 1:
+        assert ncb % 2 == 0
+    any_off = False
+    for rank in range(cl):
+        col0 = rank * ncb
+        seen = set()
+        for pos in range(ncb):
+            lc = pos if ne == ncb else (2 * pos if pos < ne else 2 * (pos - ne) + 1)
+            assert 0 <= lc < ncb and lc not in seen
+            seen.add(lc)
+            j = col0 + lc
+            off = ((addr >> 3) + j * lda) & 1                  # 1: column j starts 8 bytes off a 16-byte boundary
+            assert off == (she if pos < ne else sho), (rank, pos, lc)
+            any_off |= bool(off) and j < n
+        assert seen == set(range(ncb))
+    assert pitch == (34 if (odd or (addr >> 3) & 1) else 32)
+    if any_off:
+        assert pitch == 34
+    second_box = (ne * pitch + 15) // 16 * 16                     # doubles; the second box starts on a 128-byte boundary
+    assert (second_box + (256 - ne) * pitch) * 8 <= stage_bytes
+    assert 3 * stage_bytes + 8 * 8 * 32 * 8 + 2 * 8 * 32 * 8 + 256 + 128 <= 227 * 1024
+
+
+def test_one_pass_launch_geometry_declines_wide_operands():
+    import ctypes as C
+    from randnla_b200 import _lib
+    out = (C.c_int32 * 7)()
+    assert _lib.load().rnla_plan_normal_pass(0x7f0000000000, 1000, 2049, out) == 0
+    assert _lib.load().rnla_plan_normal_pass(0x7f0000000004, 1000, 100, out) == 0
